@@ -1,0 +1,343 @@
+// Direct (CUDA-core) NHWC convolutions for the tiny-K, HBM-bound layers and as the generic cross-check
+// path: the 5x5 stems (network/ugan.py:26), the discriminator's 4x4 s2 stem with bias (network/ugan.py:202),
+// the 1x1 heads with bias/tanh (network/ugan.py:70-83), conv_src / conv_cls (network/ugan.py:213-215).
+// Weights are the fp32 OIHW masters; accumulation is fp32.
+#include "../../include/smsut_b200.h"
+#include "common.cuh"
+
+namespace smsut {
+
+void count_launch();
+
+struct DirectParams {
+  int n, h, w, cin, cout, kh, kw, stride, pad, ho, wo;
+  const void* x; int x_ld, x_f32;
+  const float* wt; const float* bias;
+  void* y; int y_ld, y_f32;
+  int act; float slope; int accumulate;
+  int cch;  // channel chunk staged in smem
+};
+
+__device__ __forceinline__ float load_act(const void* p, size_t idx, int f32) {
+  return f32 ? reinterpret_cast<const float*>(p)[idx] : bf2f(reinterpret_cast<const __nv_bfloat16*>(p)[idx]);
+}
+__device__ __forceinline__ void store_act(void* p, size_t idx, int f32, float v, int accumulate) {
+  if (f32) {
+    float* q = reinterpret_cast<float*>(p) + idx;
+    *q = accumulate ? *q + v : v;
+  } else {
+    __nv_bfloat16* q = reinterpret_cast<__nv_bfloat16*>(p) + idx;
+    *q = f2bf(accumulate ? bf2f(*q) + v : v);
+  }
+}
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == SMSUT_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == SMSUT_ACT_LRELU) return lrelu(v, slope);
+  if (act == 3) return tanhf(v);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fprop: one thread = one output pixel x CT output channels
+// ---------------------------------------------------------------------------------------------
+template <int CT>
+__global__ void __launch_bounds__(128) direct_fprop_kernel(const DirectParams p) {
+  extern __shared__ float ws[];  // [taps][cch][CT]
+  const int taps = p.kh * p.kw;
+  const int co0 = blockIdx.y * CT;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)p.n * p.ho * p.wo;
+  const bool active = pix < npix;
+  int wo = 0, ho = 0, n = 0;
+  if (active) {
+    long long t = pix;
+    wo = (int)(t % p.wo); t /= p.wo;
+    ho = (int)(t % p.ho); n = (int)(t / p.ho);
+  }
+  float acc[CT];
+#pragma unroll
+  for (int o = 0; o < CT; ++o) acc[o] = 0.f;
+
+  for (int c0 = 0; c0 < p.cin; c0 += p.cch) {
+    const int cn = min(p.cch, p.cin - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < taps * cn * CT; i += blockDim.x) {
+      const int o = i % CT;
+      const int c = (i / CT) % cn;
+      const int t = i / (CT * cn);
+      const int co = co0 + o;
+      ws[i] = co < p.cout ? p.wt[((size_t)co * p.cin + (c0 + c)) * taps + t] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int iy = ho * p.stride - p.pad + ky;
+      if (iy < 0 || iy >= p.h) continue;
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int ix = wo * p.stride - p.pad + kx;
+        if (ix < 0 || ix >= p.w) continue;
+        const size_t base = (((size_t)n * p.h + iy) * p.w + ix) * p.x_ld + c0;
+        const float* wrow = ws + (size_t)(ky * p.kw + kx) * cn * CT;
+        if (!p.x_f32 && (cn & 7) == 0 && (p.x_ld & 7) == 0 && (c0 & 7) == 0) {
+          const uint4* xp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + base);
+          for (int c8 = 0; c8 < cn; c8 += 8) {
+            float xv[8];
+            unpack8(xp[c8 >> 3], xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float* wv = wrow + (size_t)(c8 + j) * CT;
+#pragma unroll
+              for (int o = 0; o < CT; ++o) acc[o] = fmaf(xv[j], wv[o], acc[o]);
+            }
+          }
+        } else {
+          for (int c = 0; c < cn; ++c) {
+            const float xv = load_act(p.x, base + c, p.x_f32);
+            const float* wv = wrow + (size_t)c * CT;
+#pragma unroll
+            for (int o = 0; o < CT; ++o) acc[o] = fmaf(xv, wv[o], acc[o]);
+          }
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const size_t obase = (size_t)pix * p.y_ld;
+#pragma unroll
+  for (int o = 0; o < CT; ++o) {
+    const int co = co0 + o;
+    if (co >= p.y_ld) break;
+    float v = acc[o];
+    if (co < p.cout) {
+      if (p.bias) v += p.bias[co];
+      v = apply_act(v, p.act, p.slope);
+    } else {
+      v = 0.f;  // channel padding
+    }
+    store_act(p.y, obase + co, p.y_f32, v, p.accumulate);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dgrad: one thread = one input pixel x CT input channels (gather form)
+//   dx[n,iy,ix,ci] = sum_{co,ky,kx : oy*stride - pad + ky == iy} dy[n,oy,ox,co] * w[co,ci,ky,kx]
+// here p.x / x_ld / x_f32 describe dx (written) and p.y / y_ld / y_f32 describe dy (read).
+// ---------------------------------------------------------------------------------------------
+template <int CT>
+__global__ void __launch_bounds__(128) direct_dgrad_kernel(const DirectParams p) {
+  extern __shared__ float ws[];  // [taps][cch(co)][CT(ci)]
+  const int taps = p.kh * p.kw;
+  const int ci0 = blockIdx.y * CT;
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)p.n * p.h * p.w;
+  const bool active = pix < npix;
+  int ix = 0, iy = 0, n = 0;
+  if (active) {
+    long long t = pix;
+    ix = (int)(t % p.w); t /= p.w;
+    iy = (int)(t % p.h); n = (int)(t / p.h);
+  }
+  float acc[CT];
+#pragma unroll
+  for (int o = 0; o < CT; ++o) acc[o] = 0.f;
+
+  for (int c0 = 0; c0 < p.cout; c0 += p.cch) {
+    const int cn = min(p.cch, p.cout - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < taps * cn * CT; i += blockDim.x) {
+      const int o = i % CT;
+      const int c = (i / CT) % cn;
+      const int t = i / (CT * cn);
+      const int ci = ci0 + o;
+      ws[i] = ci < p.cin ? p.wt[((size_t)(c0 + c) * p.cin + ci) * taps + t] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int ky = 0; ky < p.kh; ++ky) {
+      const int ty = iy + p.pad - ky;
+      if (ty < 0 || ty % p.stride != 0) continue;
+      const int oy = ty / p.stride;
+      if (oy >= p.ho) continue;
+      for (int kx = 0; kx < p.kw; ++kx) {
+        const int tx = ix + p.pad - kx;
+        if (tx < 0 || tx % p.stride != 0) continue;
+        const int ox = tx / p.stride;
+        if (ox >= p.wo) continue;
+        const size_t base = (((size_t)n * p.ho + oy) * p.wo + ox) * p.y_ld + c0;
+        const float* wrow = ws + (size_t)(ky * p.kw + kx) * cn * CT;
+        for (int c = 0; c < cn; ++c) {
+          const float gv = load_act(p.y, base + c, p.y_f32);
+          const float* wv = wrow + (size_t)c * CT;
+#pragma unroll
+          for (int o = 0; o < CT; ++o) acc[o] = fmaf(gv, wv[o], acc[o]);
+        }
+      }
+    }
+  }
+  if (!active) return;
+  const size_t obase = (size_t)pix * p.x_ld;
+#pragma unroll
+  for (int o = 0; o < CT; ++o) {
+    const int ci = ci0 + o;
+    if (ci >= p.x_ld) break;
+    store_act(const_cast<void*>(p.x), obase + ci, p.x_f32, ci < p.cin ? acc[o] : 0.f, p.accumulate);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: block = a strip of output rows; thread owns up to OPT (co,ci,tap) outputs (grid.y chunks)
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgOPT = 4;
+__global__ void __launch_bounds__(256) direct_wgrad_kernel(const DirectParams p, float* dw, float* dbias,
+                                                           int rows_per_block) {
+  const int taps = p.kh * p.kw;
+  const int nout = p.cout * p.cin * taps;
+  const long long total_rows = (long long)p.n * p.ho;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  long long row1 = row0 + rows_per_block;
+  if (row1 > total_rows) row1 = total_rows;
+
+  int oidx[kWgOPT], co[kWgOPT], ci[kWgOPT], ky[kWgOPT], kx[kWgOPT];
+  float acc[kWgOPT];
+#pragma unroll
+  for (int j = 0; j < kWgOPT; ++j) {
+    oidx[j] = (blockIdx.y * kWgOPT + j) * blockDim.x + threadIdx.x;
+    acc[j] = 0.f;
+    int t = oidx[j] < nout ? oidx[j] : 0;
+    kx[j] = t % p.kw; t /= p.kw;
+    ky[j] = t % p.kh; t /= p.kh;
+    ci[j] = t % p.cin; co[j] = t / p.cin;
+  }
+  for (long long r = row0; r < row1; ++r) {
+    const int n = (int)(r / p.ho), oy = (int)(r % p.ho);
+    const size_t dybase = ((size_t)n * p.ho + oy) * p.wo * p.y_ld;
+#pragma unroll
+    for (int j = 0; j < kWgOPT; ++j) {
+      if (oidx[j] >= nout) continue;
+      const int iy = oy * p.stride - p.pad + ky[j];
+      if (iy < 0 || iy >= p.h) continue;
+      const size_t xbase = ((size_t)n * p.h + iy) * p.w * p.x_ld;
+      float a = 0.f;
+      for (int ox = 0; ox < p.wo; ++ox) {
+        const int ix = ox * p.stride - p.pad + kx[j];
+        if (ix < 0 || ix >= p.w) continue;
+        a = fmaf(load_act(p.y, dybase + (size_t)ox * p.y_ld + co[j], p.y_f32),
+                 load_act(p.x, xbase + (size_t)ix * p.x_ld + ci[j], p.x_f32), a);
+      }
+      acc[j] += a;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kWgOPT; ++j)
+    if (oidx[j] < nout && acc[j] != 0.f) atomicAdd(dw + oidx[j], acc[j]);
+
+  if (dbias != nullptr && blockIdx.y == 0) {
+    for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
+      float s = 0.f;
+      for (long long r = row0; r < row1; ++r) {
+        const size_t dybase = (size_t)r * p.wo * p.y_ld;
+        for (int ox = 0; ox < p.wo; ++ox) s += load_act(p.y, dybase + (size_t)ox * p.y_ld + c, p.y_f32);
+      }
+      atomicAdd(dbias + c, s);
+    }
+  }
+}
+
+static int fill_params(const smsut_conv_direct_args* a, DirectParams* p) {
+  SMSUT_CHECK(a != nullptr, -1, "null args");
+  SMSUT_CHECK(a->n > 0 && a->h > 0 && a->w > 0 && a->cin > 0 && a->cout > 0 && a->stride > 0, -1, "bad conv dims");
+  SMSUT_CHECK(a->ho == (a->h + 2 * a->pad - a->kh) / a->stride + 1 && a->wo == (a->w + 2 * a->pad - a->kw) / a->stride + 1,
+              -1, "output dims %dx%d inconsistent with input %dx%d k%d s%d p%d", a->ho, a->wo, a->h, a->w, a->kh,
+              a->stride, a->pad);
+  p->n = a->n; p->h = a->h; p->w = a->w; p->cin = a->cin; p->cout = a->cout; p->kh = a->kh; p->kw = a->kw;
+  p->stride = a->stride; p->pad = a->pad; p->ho = a->ho; p->wo = a->wo;
+  p->x = a->x; p->x_ld = a->x_ld; p->x_f32 = a->x_f32; p->wt = a->wt; p->bias = a->bias;
+  p->y = a->y; p->y_ld = a->y_ld; p->y_f32 = a->y_f32; p->act = a->act; p->slope = a->slope;
+  p->accumulate = a->accumulate;
+  return 0;
+}
+
+static int pick_cch(int taps, int ct, int cdim) {
+  int cch = 11264 / (taps * ct);  // <= 44 KB of fp32 weights
+  if (cch >= cdim) return cdim;
+  cch &= ~7;
+  return cch < 1 ? 1 : cch;
+}
+
+static int direct_fprop(const smsut_conv_direct_args* a, cudaStream_t stream) {
+  DirectParams p;
+  int rc = fill_params(a, &p);
+  if (rc) return rc;
+  const long long npix = (long long)p.n * p.ho * p.wo;
+  const int taps = p.kh * p.kw;
+  const int cw = p.cout > p.y_ld ? p.cout : p.y_ld;  // channels to write (incl. zero padding)
+  if (cw <= 1) {
+    p.cch = pick_cch(taps, 1, p.cin);
+    dim3 grid((unsigned)((npix + 127) / 128), 1);
+    direct_fprop_kernel<1><<<grid, 128, (size_t)taps * p.cch * 1 * 4, stream>>>(p);
+  } else if (cw <= 8) {
+    p.cch = pick_cch(taps, 8, p.cin);
+    dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 7) / 8));
+    direct_fprop_kernel<8><<<grid, 128, (size_t)taps * p.cch * 8 * 4, stream>>>(p);
+  } else {
+    p.cch = pick_cch(taps, 16, p.cin);
+    dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 15) / 16));
+    direct_fprop_kernel<16><<<grid, 128, (size_t)taps * p.cch * 16 * 4, stream>>>(p);
+  }
+  count_launch();
+  return launch_status("direct_fprop_kernel");
+}
+
+static int direct_dgrad(const smsut_conv_direct_args* a, cudaStream_t stream) {
+  DirectParams p;
+  int rc = fill_params(a, &p);
+  if (rc) return rc;
+  const long long npix = (long long)p.n * p.h * p.w;
+  const int taps = p.kh * p.kw;
+  const int cw = p.cin > p.x_ld ? p.cin : p.x_ld;
+  if (cw <= 1) {
+    p.cch = pick_cch(taps, 1, p.cout);
+    dim3 grid((unsigned)((npix + 127) / 128), 1);
+    direct_dgrad_kernel<1><<<grid, 128, (size_t)taps * p.cch * 1 * 4, stream>>>(p);
+  } else if (cw <= 8) {
+    p.cch = pick_cch(taps, 8, p.cout);
+    dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 7) / 8));
+    direct_dgrad_kernel<8><<<grid, 128, (size_t)taps * p.cch * 8 * 4, stream>>>(p);
+  } else {
+    p.cch = pick_cch(taps, 16, p.cout);
+    dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 15) / 16));
+    direct_dgrad_kernel<16><<<grid, 128, (size_t)taps * p.cch * 16 * 4, stream>>>(p);
+  }
+  count_launch();
+  return launch_status("direct_dgrad_kernel");
+}
+
+static int direct_wgrad(const smsut_conv_direct_args* a, float* dw, float* dbias, cudaStream_t stream) {
+  DirectParams p;
+  int rc = fill_params(a, &p);
+  if (rc) return rc;
+  SMSUT_CHECK(dw != nullptr, -1, "null dw");
+  const int nout = p.cout * p.cin * p.kh * p.kw;
+  const long long total_rows = (long long)p.n * p.ho;
+  const int chunks = (nout + 256 * kWgOPT - 1) / (256 * kWgOPT);
+  long long want_blocks = 4LL * device_sm_count() / chunks;
+  if (want_blocks < 1) want_blocks = 1;
+  int rows_per_block = (int)((total_rows + want_blocks - 1) / want_blocks);
+  if (rows_per_block < 1) rows_per_block = 1;
+  dim3 grid((unsigned)((total_rows + rows_per_block - 1) / rows_per_block), (unsigned)chunks);
+  direct_wgrad_kernel<<<grid, 256, 0, stream>>>(p, dw, dbias, rows_per_block);
+  count_launch();
+  return launch_status("direct_wgrad_kernel");
+}
+
+}  // namespace smsut
+
+extern "C" int smsut_conv_direct_fprop(const smsut_conv_direct_args* a, smsut_stream_t s) {
+  return smsut::direct_fprop(a, reinterpret_cast<cudaStream_t>(s));
+}
+extern "C" int smsut_conv_direct_dgrad(const smsut_conv_direct_args* a, smsut_stream_t s) {
+  return smsut::direct_dgrad(a, reinterpret_cast<cudaStream_t>(s));
+}
+extern "C" int smsut_conv_direct_wgrad(const smsut_conv_direct_args* a, float* dw, float* dbias, smsut_stream_t s) {
+  return smsut::direct_wgrad(a, dw, dbias, reinterpret_cast<cudaStream_t>(s));
+}

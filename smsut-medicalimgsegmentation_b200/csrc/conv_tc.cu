@@ -1,0 +1,492 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores for sm_100a.
+//
+//   D[m, col] = sum_k A[m, k] * B[col, k]
+//     m   = output pixel (n, h, w)            -> 128-row tiles (tn x th x tw pixels)
+//     col = output channel (or tap*Cout+co for the transposed conv)
+//     k   = (tap, source, channel)            -> one pipeline step per (tap, source, <=64-channel chunk)
+//
+// A tiles are fetched by TMA straight from the NHWC bf16 activation tensor(s): a 4-D box
+// (chunk, tw, th, tn) whose start coordinate is shifted by the tap offset, so zero padding is the
+// TMA out-of-bounds fill and no im2col buffer ever exists.  B tiles come from the packed bf16 weight
+// matrix.  Both land in the canonical K-major swizzled layout (swizzle = chunk bytes: 32/64/128) that
+// tcgen05.mma consumes through shared-memory descriptors; accumulation is fp32 in TMEM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias/activation/accumulate -> NHWC store or 2x2 scatter).
+//
+// Reference semantics: network/blocks.py:10-16 (conv3x3/conv1x1), :41 (ConvTranspose2d k2 s2),
+// :50 (torch.cat eliminated by the two-source K loop), network/ugan.py:295 (Linear).
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/smsut_b200.h"
+#include "common.cuh"
+
+namespace smsut {
+
+constexpr int kMaxSteps = 80;
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+
+struct KStep {
+  int8_t map;   // which A tensor map
+  int8_t dy, dx;
+  int8_t pad;
+  int16_t c0;   // channel coordinate inside that map
+  int16_t pad2;
+  int32_t k;    // K coordinate in the packed weight matrix
+};
+
+struct ConvTcParams {
+  int n, h, w;             // GEMM-row space
+  int tn, th, tw;          // tile (tn*th*tw == 128)
+  int tiles_h, tiles_w;
+  int cc;                  // channels per K step (16/32/64)
+  int nsteps;
+  int bn;                  // N tile
+  int stages;
+  uint32_t tmem_cols;
+  uint32_t a_bytes, b_bytes, stage_bytes;
+  uint32_t layout_type, sbo;
+  // epilogue
+  int mode;                // 0 plain, 1 transposed-conv scatter
+  void* out0; int ld0, coff0;
+  void* out1; int ld1, coff1, split;
+  int cout_t;              // Cout of the transposed conv (mode 1)
+  int ncols;               // valid columns
+  const float* bias;
+  int act; float slope;
+  int accumulate, out_f32;
+  KStep steps[kMaxSteps];
+};
+
+template <typename T>
+__device__ __forceinline__ void store_chunk(T* dst, const float* v, int nvalid, bool accumulate);
+
+template <>
+__device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* dst, const float* v, int nvalid,
+                                                            bool accumulate) {
+  if (nvalid == 16) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = v[i];
+    uint4* p = reinterpret_cast<uint4*>(dst);
+    if (accumulate) {
+      float o[8];
+      uint4 q0 = p[0], q1 = p[1];
+      unpack8(q0, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += o[i];
+      unpack8(q1, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[8 + i] += o[i];
+    }
+    p[0] = pack8(f);
+    p[1] = pack8(f + 8);
+  } else {
+    for (int i = 0; i < nvalid; ++i) {
+      float x = v[i];
+      if (accumulate) x += bf2f(dst[i]);
+      dst[i] = f2bf(x);
+    }
+  }
+}
+template <>
+__device__ __forceinline__ void store_chunk<float>(float* dst, const float* v, int nvalid, bool accumulate) {
+  if (nvalid == 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    float4* p = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 q = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (accumulate) {
+        float4 o = p[i];
+        q.x += o.x; q.y += o.y; q.z += o.z; q.w += o.w;
+      }
+      p[i] = q;
+    }
+  } else {
+    for (int i = 0; i < nvalid; ++i) dst[i] = accumulate ? dst[i] + v[i] : v[i];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8];
+  __shared__ __align__(8) uint64_t empty_bar[8];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // 1024-byte aligned stage ring (required by the 128B swizzle atoms)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tw_i = tile % p.tiles_w; tile /= p.tiles_w;
+  const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
+  const int n0 = tile * p.tn;
+  const int h0 = th_i * p.th;
+  const int w0 = tw_i * p.tw;
+  const int col0 = blockIdx.y * p.bn;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < p.nsteps; ++i) {
+        const KStep st = p.steps[i];
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+        void* a_dst = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * p.stage_bytes;
+        void* b_dst = (uint8_t*)a_dst + p.a_bytes;
+        const CUtensorMap* m = st.map == 0 ? &map_a0 : (st.map == 1 ? &map_a1 : (st.map == 2 ? &map_a2 : &map_a3));
+        tma_load_4d(a_dst, m, &full_bar[stage], st.c0, w0 + st.dx, h0 + st.dy, n0);
+        tma_load_2d(b_dst, &map_w, &full_bar[stage], st.k, col0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: fp32 accum, bf16 x bf16, both K-major, N = bn, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < p.nsteps; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_base + (uint32_t)stage * p.stage_bytes;
+        const uint32_t b_addr = a_addr + p.a_bytes;
+        const int kk = p.cc >> 4;
+        for (int k = 0; k < kk; ++k) {
+          const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, p.sbo, p.layout_type);
+          const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, p.sbo, p.layout_type);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (i == p.nsteps - 1) umma_commit(&tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int wl = r % p.tw;
+    const int hl = (r / p.tw) % p.th;
+    const int nl = r / (p.tw * p.th);
+    const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+    const bool row_ok = (n < p.n) && (h < p.h) && (w < p.w);
+
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+
+    const int nchunks = p.bn >> 4;
+    for (int j = 0; j < nchunks; ++j) {
+      uint32_t raw[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
+      tmem_ld_wait();
+      const int col = col0 + j * 16;
+      if (!row_ok || col >= p.ncols) continue;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+      int nvalid = p.ncols - col;
+      if (nvalid > 16) nvalid = 16;
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nvalid) v[i] += p.bias[col + i];
+      }
+      if (p.act == SMSUT_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+      } else if (p.act == SMSUT_ACT_LRELU) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = lrelu(v[i], p.slope);
+      }
+      // destination
+      void* base;
+      int ld, coff, c;
+      size_t pix;
+      if (p.mode == 0) {
+        pix = ((size_t)n * p.h + h) * p.w + w;
+        if (p.split > 0 && col >= p.split) {
+          base = p.out1; ld = p.ld1; coff = p.coff1; c = col - p.split;
+        } else {
+          base = p.out0; ld = p.ld0; coff = p.coff0; c = col;
+          if (p.split > 0 && col + nvalid > p.split) nvalid = p.split - col;
+        }
+      } else {
+        const int t = col / p.cout_t;
+        c = col - t * p.cout_t;
+        const int ty = t >> 1, tx = t & 1;
+        pix = ((size_t)n * (2 * p.h) + (2 * h + ty)) * (size_t)(2 * p.w) + (2 * w + tx);
+        base = p.out0; ld = p.ld0; coff = p.coff0;
+      }
+      const size_t off = pix * (size_t)ld + coff + c;
+      if (p.out_f32)
+        store_chunk<float>(reinterpret_cast<float*>(base) + off, v, nvalid, p.accumulate != 0);
+      else
+        store_chunk<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(base) + off, v, nvalid, p.accumulate != 0);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// 4-D activation map: dims (C, W, H, N) with element strides (1, sw, sh, sn); box (cc, tw, th, tn).
+int make_act_map(CUtensorMap* m, const void* ptr, int c, int w, int h, int n, int64_t sw, int64_t sh, int64_t sn,
+                 int cc, int tw, int th, int tn) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  SMSUT_CHECK(enc != nullptr, -2, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  SMSUT_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, -3, "activation pointer must be 16-byte aligned");
+  SMSUT_CHECK((sw * 2) % 16 == 0 && (sh * 2) % 16 == 0 && (sn * 2) % 16 == 0, -3,
+              "activation strides must be multiples of 16 bytes (sw=%lld)", (long long)sw);
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)cc, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(cc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMSUT_CHECK(r == CUDA_SUCCESS, -4,
+              "cuTensorMapEncodeTiled(activation) failed: %d (c=%d w=%d h=%d n=%d box=%d,%d,%d,%d)", (int)r, c, w, h,
+              n, cc, tw, th, tn);
+  return 0;
+}
+
+// 2-D matrix map: rows x kdim (kdim contiguous); box (cc, rows_box).
+int make_mat_map(CUtensorMap* m, const void* ptr, int64_t kdim, int64_t rows, int64_t ld, int cc, int rows_box) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  SMSUT_CHECK(enc != nullptr, -2, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  SMSUT_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, -3, "matrix pointer must be 16-byte aligned");
+  SMSUT_CHECK((ld * 2) % 16 == 0, -3, "matrix row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)cc, (cuuint32_t)rows_box};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_bytes(cc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SMSUT_CHECK(r == CUDA_SUCCESS, -4, "cuTensorMapEncodeTiled(matrix) failed: %d (k=%lld rows=%lld box=%d,%d)", (int)r,
+              (long long)kdim, (long long)rows, cc, rows_box);
+  return 0;
+}
+
+static int pow2_floor_dividing(int x, int cap) {
+  int t = 1;
+  while (t * 2 <= cap && x % (t * 2) == 0) t *= 2;
+  return t;
+}
+
+// Choose the 128-pixel tile (tn, th, tw) for an (n, h, w) GEMM-row space.
+int choose_tile(int n, int h, int w, int* tn, int* th, int* tw) {
+  int a = pow2_floor_dividing(w, kTileM);
+  int b = pow2_floor_dividing(h, kTileM / a);
+  int c = kTileM / (a * b);
+  (void)n;
+  *tw = a; *th = b; *tn = c;
+  SMSUT_CHECK(c <= 256, -5, "unsupported spatial shape %dx%d for 128-pixel tiling", h, w);
+  return 0;
+}
+
+void count_launch();
+
+static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
+  SMSUT_CHECK(a != nullptr, -1, "null args");
+  SMSUT_CHECK(a->nsrc == 1 || a->nsrc == 2, -1, "nsrc must be 1 or 2");
+  SMSUT_CHECK(a->n > 0 && a->h > 0 && a->w > 0, -1, "bad dims");
+  const int ctot = a->src_c[0] + (a->nsrc == 2 ? a->src_c[1] : 0);
+  for (int s = 0; s < a->nsrc; ++s)
+    SMSUT_CHECK(a->src_c[s] % 16 == 0 && a->src_c[s] > 0 && a->src_ld[s] >= a->src_c[s] && a->src_ld[s] % 8 == 0, -1,
+                "source %d channels (%d, ld %d) must be a positive multiple of 16", s, a->src_c[s], a->src_ld[s]);
+  SMSUT_CHECK(a->ncols_pad % 16 == 0 && a->ncols <= a->ncols_pad && a->ncols > 0, -1, "bad ncols/ncols_pad");
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = a->n; p.h = a->h; p.w = a->w;
+  int rc = choose_tile(a->n, a->h, a->w, &p.tn, &p.th, &p.tw);
+  if (rc) return rc;
+  p.tiles_h = a->h / p.th;
+  p.tiles_w = a->w / p.tw;
+  SMSUT_CHECK(p.tiles_h * p.th == a->h && p.tiles_w * p.tw == a->w, -5, "spatial dims %dx%d not tileable", a->h, a->w);
+  const int tiles_n = (a->n + p.tn - 1) / p.tn;
+  const int m_tiles = tiles_n * p.tiles_h * p.tiles_w;
+
+  // channel chunk = largest of 64/32/16 dividing every source's channel count
+  int cc = 64;
+  for (int s = 0; s < a->nsrc; ++s)
+    while (a->src_c[s] % cc != 0) cc >>= 1;
+  p.cc = cc;
+  p.layout_type = cc == 64 ? 2u : (cc == 32 ? 4u : 6u);
+  p.sbo = 8u * (uint32_t)cc * 2u;
+
+  // K steps and A tensor maps
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  int ns = 0;
+  if (a->kind == SMSUT_TC_CONV || a->kind == SMSUT_TC_CONVT_FWD) {
+    const int ks = a->kind == SMSUT_TC_CONV ? a->ksize : 1;
+    SMSUT_CHECK(ks == 1 || ks == 3, -1, "ksize must be 1 or 3");
+    for (int s = 0; s < a->nsrc; ++s) {
+      rc = make_act_map(&maps[s], a->src[s], a->src_c[s], a->w, a->h, a->n, a->src_ld[s],
+                        (int64_t)a->src_ld[s] * a->w, (int64_t)a->src_ld[s] * a->w * a->h, cc, p.tw, p.th, p.tn);
+      if (rc) return rc;
+    }
+    const int r = ks / 2;
+    int t = 0;
+    for (int dy = -r; dy <= r; ++dy)
+      for (int dx = -r; dx <= r; ++dx, ++t) {
+        int coff = 0;
+        for (int s = 0; s < a->nsrc; ++s) {
+          for (int c0 = 0; c0 < a->src_c[s]; c0 += cc) {
+            SMSUT_CHECK(ns < kMaxSteps, -6, "too many K steps");
+            KStep& st = p.steps[ns++];
+            st.map = (int8_t)s; st.dy = (int8_t)dy; st.dx = (int8_t)dx; st.c0 = (int16_t)c0;
+            st.k = t * ctot + coff + c0;
+          }
+          coff += a->src_c[s];
+        }
+      }
+  } else if (a->kind == SMSUT_TC_CONVT_DGRAD) {
+    SMSUT_CHECK(a->nsrc == 1, -1, "convT dgrad takes one source");
+    // four strided planes dy[:, ty::2, tx::2, :]
+    const int64_t ld = a->src_ld[0];
+    const int64_t W2 = 2 * (int64_t)a->w, H2 = 2 * (int64_t)a->h;
+    for (int t = 0; t < 4; ++t) {
+      const int ty = t >> 1, tx = t & 1;
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(a->src[0]) + ((int64_t)ty * W2 + tx) * ld;
+      rc = make_act_map(&maps[t], base, a->src_c[0], a->w, a->h, a->n, 2 * ld, 2 * W2 * ld, H2 * W2 * ld, cc, p.tw,
+                        p.th, p.tn);
+      if (rc) return rc;
+      for (int c0 = 0; c0 < a->src_c[0]; c0 += cc) {
+        SMSUT_CHECK(ns < kMaxSteps, -6, "too many K steps");
+        KStep& st = p.steps[ns++];
+        st.map = (int8_t)t; st.dy = 0; st.dx = 0; st.c0 = (int16_t)c0;
+        st.k = t * ctot + c0;
+      }
+    }
+  } else {
+    SMSUT_CHECK(false, -1, "unknown kind %d", a->kind);
+  }
+  p.nsteps = ns;
+  const int64_t ktot = (a->kind == SMSUT_TC_CONV ? (int64_t)a->ksize * a->ksize : (a->kind == SMSUT_TC_CONVT_DGRAD ? 4 : 1)) * ctot;
+
+  // N tile
+  int bn = a->bn;
+  if (bn <= 0) {
+    const int cands[5] = {256, 128, 64, 32, 16};
+    bn = 16;
+    for (int i = 0; i < 5; ++i) {
+      const int c = cands[i];
+      if (c > a->ncols_pad || a->ncols_pad % c != 0) continue;
+      bn = c;
+      if ((int64_t)m_tiles * (a->ncols_pad / c) >= 120 || c <= 64) break;
+    }
+  }
+  SMSUT_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && a->ncols_pad % bn == 0, -1, "bad N tile %d for %d columns", bn,
+              a->ncols_pad);
+  p.bn = bn;
+  uint32_t tc = 32;
+  while ((int)tc < bn) tc <<= 1;
+  p.tmem_cols = tc;
+
+  CUtensorMap map_w;
+  rc = make_mat_map(&map_w, a->wpack, ktot, a->ncols_pad, ktot, cc, bn);
+  if (rc) return rc;
+
+  p.a_bytes = (uint32_t)kTileM * cc * 2;
+  p.b_bytes = (uint32_t)bn * cc * 2;
+  p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
+  int stages = (int)((200u * 1024u) / p.stage_bytes);
+  if (stages > 6) stages = 6;
+  if (stages > ns) stages = ns;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+
+  p.mode = a->kind == SMSUT_TC_CONVT_FWD ? 1 : 0;
+  p.out0 = a->out0; p.ld0 = a->out0_ld; p.coff0 = a->out0_coff;
+  p.out1 = a->out1; p.ld1 = a->out1_ld; p.coff1 = a->out1_coff; p.split = a->out1 ? a->split : 0;
+  p.cout_t = a->kind == SMSUT_TC_CONVT_FWD ? a->ncols / 4 : 0;
+  if (p.mode == 1) SMSUT_CHECK(p.cout_t % 16 == 0, -1, "convT Cout must be a multiple of 16");
+  if (p.split > 0) SMSUT_CHECK(p.split % 16 == 0, -1, "split must be a multiple of 16");
+  p.ncols = a->ncols;
+  p.bias = a->bias; p.act = a->act; p.slope = a->slope;
+  p.accumulate = a->accumulate; p.out_f32 = a->out_f32;
+  SMSUT_CHECK(a->out0 != nullptr, -1, "null output");
+  if (!a->out_f32)
+    SMSUT_CHECK(a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 || a->ncols < 16, -1, "bf16 output pitch/offset must be multiples of 8");
+
+  dim3 grid((unsigned)m_tiles, (unsigned)(a->ncols_pad / bn));
+  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], map_w, p);
+  count_launch();
+  return launch_status("conv_tc_kernel");
+}
+
+}  // namespace smsut
+
+extern "C" int smsut_conv_tc(const smsut_conv_tc_args* a, smsut_stream_t stream) {
+  return smsut::conv_tc_impl(a, reinterpret_cast<cudaStream_t>(stream));
+}

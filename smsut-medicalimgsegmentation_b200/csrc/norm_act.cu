@@ -1,0 +1,570 @@
+// InstanceNorm2d(affine) + LeakyReLU + residual, forward / backward / double backward, on NHWC bf16.
+// All kernels are HBM-bound streaming passes with 128-bit accesses: one thread owns 8 consecutive channels
+// and strides over the pixels of one sample; per-(n,c) reductions go warp-shuffle -> shared -> one fp32
+// atomic per block and channel.
+//
+// Reference semantics: nn.InstanceNorm2d(C, affine=True) (network/blocks.py:22-23; eps 1e-5, biased variance,
+// no running stats), nn.LeakyReLU(0.01) (network/blocks.py:28-34), `x += identity` (network/blocks.py:78,115)
+// and, for the double backward, torch.autograd.grad(create_graph=True) through them
+// (trainer/uganShp0Trainer.py:127-134).
+#include "../../include/smsut_b200.h"
+#include "common.cuh"
+
+namespace smsut {
+
+void count_launch();
+
+constexpr int kNT = 256;
+constexpr float kEps = 1e-5f;
+
+struct Strip {
+  int cg;       // channel groups of 8
+  int g;        // this thread's group
+  int lane0;    // first pixel handled by this thread (relative to the strip)
+  int nlanes;   // pixel stride
+  long long p0, p1;  // pixel range of this block inside the sample
+};
+
+__device__ __forceinline__ Strip make_strip(int c, int hw, int splits) {
+  Strip s;
+  s.cg = c >> 3;
+  s.g = threadIdx.x % s.cg;
+  s.lane0 = threadIdx.x / s.cg;
+  s.nlanes = kNT / s.cg;
+  const long long per = ((long long)hw + splits - 1) / splits;
+  s.p0 = (long long)blockIdx.y * per;
+  s.p1 = s.p0 + per;
+  if (s.p1 > hw) s.p1 = hw;
+  return s;
+}
+
+// Reduce NV values across threads that share a channel group and add them to dst[v * vstride + g*8 + j].
+template <int NV>
+__device__ __forceinline__ void block_reduce_add(float (&acc)[NV][8], float* sh, const Strip& s, float* dst, int c,
+                                                 size_t vstride) {
+  // sh: [NV][c] floats
+  for (int i = threadIdx.x; i < NV * c; i += kNT) sh[i] = 0.f;
+  __syncthreads();
+  if (s.cg <= 16) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float x = acc[v][j];
+        for (int off = 16; off >= s.cg; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        acc[v][j] = x;
+      }
+    if ((threadIdx.x & 31) < s.cg) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sh[v * c + s.g * 8 + j], acc[v][j]);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sh[v * c + s.g * 8 + j], acc[v][j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NV * c; i += kNT) {
+    const int v = i / c, ch = i - v * c;
+    atomicAdd(dst + v * vstride + ch, sh[i]);
+  }
+}
+
+__device__ __forceinline__ uint4 ldg16(const void* base, size_t elem_off) {
+  return *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
+}
+__device__ __forceinline__ void stg16(void* base, size_t elem_off, const uint4& v) {
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + elem_off) = v;
+}
+
+// mean / rstd of 8 channels from stats[n][2][c] = {sum, sumsq}
+__device__ __forceinline__ void load_mean_rstd(const float* stats, int n, int c, int ch0, float inv_hw, float* mean,
+                                               float* rstd) {
+  const float* s0 = stats + (size_t)n * 2 * c + ch0;
+  const float* s1 = s0 + c;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = s0[j] * inv_hw;
+    float var = s1[j] * inv_hw - m * m;
+    var = fmaxf(var, 0.f);
+    mean[j] = m;
+    rstd[j] = rsqrtf(var + kEps);
+  }
+}
+
+__device__ __forceinline__ float act_grad(float out, int act, float slope) {
+  if (act == SMSUT_ACT_LRELU) return out > 0.f ? 1.f : slope;
+  if (act == SMSUT_ACT_RELU) return out > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT) in_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, int hw,
+                                                       int c, int splits) {
+  extern __shared__ float sh[];
+  const Strip s = make_strip(c, hw, splits);
+  const int n = blockIdx.x;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  const size_t base = (size_t)n * hw * c + s.g * 8;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    float v[8];
+    unpack8(ldg16(x, base + (size_t)p * c), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += v[j];
+      acc[1][j] = fmaf(v[j], v[j], acc[1][j]);
+    }
+  }
+  block_reduce_add<2>(acc, sh, s, stats + (size_t)n * 2 * c, c, c);
+}
+
+__global__ void __launch_bounds__(kNT)
+in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                const float* __restrict__ beta_a, const void* __restrict__ xb, const float* __restrict__ stats_b,
+                const float* __restrict__ gamma_b, const float* __restrict__ beta_b, const void* __restrict__ res,
+                void* __restrict__ out, int hw, int c, int cp, int splits, int act, float slope) {
+  const Strip s = make_strip(c, hw, splits);
+  const int n = blockIdx.x;
+  const int ch0 = s.g * 8;
+  const float inv_hw = 1.f / (float)hw;
+  float sa[8], ta[8], sb[8], tb[8];
+  {
+    float m[8], r[8];
+    load_mean_rstd(stats_a, n, c, ch0, inv_hw, m, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = ch0 + j < cp;
+      const float g = ok ? gamma_a[ch0 + j] : 0.f, b = ok ? beta_a[ch0 + j] : 0.f;
+      sa[j] = g * r[j];
+      ta[j] = b - m[j] * sa[j];
+    }
+    if (xb != nullptr) {
+      load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = ch0 + j < cp;
+        const float g = ok ? gamma_b[ch0 + j] : 0.f, b = ok ? beta_b[ch0 + j] : 0.f;
+        sb[j] = g * r[j];
+        tb[j] = b - m[j] * sb[j];
+      }
+    }
+  }
+  const size_t base = (size_t)n * hw * c + ch0;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    const size_t off = base + (size_t)p * c;
+    float v[8], o[8];
+    unpack8(ldg16(xa, off), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sa[j], ta[j]);
+    if (xb != nullptr) {
+      unpack8(ldg16(xb, off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += fmaf(v[j], sb[j], tb[j]);
+    }
+    if (res != nullptr) {
+      unpack8(ldg16(res, off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += v[j];
+    }
+    if (act == SMSUT_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = lrelu(o[j], slope);
+    } else if (act == SMSUT_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    stg16(out, off, pack8(o));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT)
+in_bwd_reduce_kernel(const void* __restrict__ dout, const void* __restrict__ out, const void* __restrict__ xa,
+                     const float* __restrict__ stats_a, const void* __restrict__ xb,
+                     const float* __restrict__ stats_b, float* __restrict__ red, int hw, int c, int splits, int act,
+                     float slope) {
+  extern __shared__ float sh[];
+  const Strip s = make_strip(c, hw, splits);
+  const int n = blockIdx.x;
+  const int ch0 = s.g * 8;
+  const float inv_hw = 1.f / (float)hw;
+  float ma[8], ra[8], mb[8], rb[8];
+  load_mean_rstd(stats_a, n, c, ch0, inv_hw, ma, ra);
+  if (xb != nullptr) load_mean_rstd(stats_b, n, c, ch0, inv_hw, mb, rb);
+  float acc[3][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+  const size_t base = (size_t)n * hw * c + ch0;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    const size_t off = base + (size_t)p * c;
+    float g[8], v[8];
+    unpack8(ldg16(dout, off), g);
+    if (act != SMSUT_ACT_NONE) {
+      unpack8(ldg16(out, off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
+    }
+    unpack8(ldg16(xa, off), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += g[j];
+      acc[1][j] = fmaf(g[j], (v[j] - ma[j]) * ra[j], acc[1][j]);
+    }
+    if (xb != nullptr) {
+      unpack8(ldg16(xb, off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g[j], (v[j] - mb[j]) * rb[j], acc[2][j]);
+    }
+  }
+  block_reduce_add<3>(acc, sh, s, red + (size_t)n * 3 * c, c, c);
+}
+
+__global__ void __launch_bounds__(kNT)
+in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out, const void* __restrict__ xa,
+                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a, void* __restrict__ dxa,
+                    float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const void* __restrict__ xb,
+                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b, void* __restrict__ dxb,
+                    float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, void* __restrict__ dres,
+                    const float* __restrict__ red, int hw, int c, int cp, int splits, int act, float slope) {
+  const Strip s = make_strip(c, hw, splits);
+  const int n = blockIdx.x;
+  const int ch0 = s.g * 8;
+  const float inv_hw = 1.f / (float)hw;
+  float ma[8], ra[8], mb[8], rb[8], sa[8], sb[8], mg[8], mga[8], mgb[8];
+  load_mean_rstd(stats_a, n, c, ch0, inv_hw, ma, ra);
+  if (xb != nullptr) load_mean_rstd(stats_b, n, c, ch0, inv_hw, mb, rb);
+  const float* r0 = red + (size_t)n * 3 * c + ch0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool ok = ch0 + j < cp;
+    mg[j] = r0[j] * inv_hw;
+    mga[j] = r0[c + j] * inv_hw;
+    mgb[j] = r0[2 * c + j] * inv_hw;
+    sa[j] = (ok ? gamma_a[ch0 + j] : 0.f) * ra[j];
+    sb[j] = (xb != nullptr && ok) ? gamma_b[ch0 + j] * rb[j] : 0.f;
+  }
+  // parameter gradients: one block per sample adds its (n, c) sums
+  if (blockIdx.y == 0 && s.lane0 == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (ch0 + j >= cp) continue;
+      if (dgamma_a) atomicAdd(dgamma_a + ch0 + j, r0[c + j]);
+      if (dbeta_a) atomicAdd(dbeta_a + ch0 + j, r0[j]);
+      if (xb != nullptr) {
+        if (dgamma_b) atomicAdd(dgamma_b + ch0 + j, r0[2 * c + j]);
+        if (dbeta_b) atomicAdd(dbeta_b + ch0 + j, r0[j]);
+      }
+    }
+  }
+  const size_t base = (size_t)n * hw * c + ch0;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    const size_t off = base + (size_t)p * c;
+    float g[8], v[8], o[8];
+    unpack8(ldg16(dout, off), g);
+    if (act != SMSUT_ACT_NONE) {
+      unpack8(ldg16(out, off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
+    }
+    if (dres != nullptr) stg16(dres, off, pack8(g));
+    unpack8(ldg16(xa, off), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = sa[j] * (g[j] - mg[j] - (v[j] - ma[j]) * ra[j] * mga[j]);
+    stg16(dxa, off, pack8(o));
+    if (xb != nullptr) {
+      unpack8(ldg16(xb, off), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = sb[j] * (g[j] - mg[j] - (v[j] - mb[j]) * rb[j] * mgb[j]);
+      stg16(dxb, off, pack8(o));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// double backward of InstanceNorm (see header for the formulas)
+//   dx = gamma*r*(dy - mean(dy) - xhat*mean(dy*xhat));  L = <u, dx>
+//   g_dy = gamma*r*(u - mean(u) - xhat*mean(u*xhat))
+//   g_x  = -gamma*r^2*[ xhat*(mean(u*dy) - mean(u)mean(dy) - 3*b*cu) + cu*(dy - mean(dy)) + b*(u - mean(u)) ]
+//          with b = mean(dy*xhat), cu = mean(u*xhat)
+//   dgamma += r*HW*(mean(u*dy) - mean(u)mean(dy) - b*cu)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNT)
+in_bwd2_reduce_kernel(const void* __restrict__ u, const void* __restrict__ dy, const void* __restrict__ x,
+                      const float* __restrict__ stats, float* __restrict__ red2, int hw, int c, int splits) {
+  extern __shared__ float sh[];
+  const Strip s = make_strip(c, hw, splits);
+  const int n = blockIdx.x;
+  const int ch0 = s.g * 8;
+  const float inv_hw = 1.f / (float)hw;
+  float m[8], r[8];
+  load_mean_rstd(stats, n, c, ch0, inv_hw, m, r);
+  float acc[5][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = acc[4][j] = 0.f;
+  const size_t base = (size_t)n * hw * c + ch0;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    const size_t off = base + (size_t)p * c;
+    float uu[8], dd[8], xx[8];
+    unpack8(ldg16(u, off), uu);
+    unpack8(ldg16(dy, off), dd);
+    unpack8(ldg16(x, off), xx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xx[j] - m[j]) * r[j];
+      acc[0][j] += uu[j];
+      acc[1][j] += dd[j];
+      acc[2][j] = fmaf(uu[j], xh, acc[2][j]);
+      acc[3][j] = fmaf(dd[j], xh, acc[3][j]);
+      acc[4][j] = fmaf(uu[j], dd[j], acc[4][j]);
+    }
+  }
+  block_reduce_add<5>(acc, sh, s, red2 + (size_t)n * 5 * c, c, c);
+}
+
+__global__ void __launch_bounds__(kNT)
+in_bwd2_apply_kernel(const void* __restrict__ u, const void* __restrict__ dy, const void* __restrict__ x,
+                     const float* __restrict__ stats, const float* __restrict__ gamma,
+                     const float* __restrict__ red2, void* __restrict__ g_dy, void* __restrict__ g_x,
+                     float* __restrict__ dgamma, int hw, int c, int splits) {
+  const Strip s = make_strip(c, hw, splits);
+  const int n = blockIdx.x;
+  const int ch0 = s.g * 8;
+  const float inv_hw = 1.f / (float)hw;
+  float m[8], r[8], mu[8], md[8], cu[8], b[8], e[8], gr[8];
+  load_mean_rstd(stats, n, c, ch0, inv_hw, m, r);
+  const float* r0 = red2 + (size_t)n * 5 * c + ch0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = r0[j] * inv_hw;
+    md[j] = r0[c + j] * inv_hw;
+    cu[j] = r0[2 * c + j] * inv_hw;
+    b[j] = r0[3 * c + j] * inv_hw;
+    e[j] = r0[4 * c + j] * inv_hw;
+    gr[j] = gamma[ch0 + j] * r[j];
+  }
+  if (dgamma != nullptr && blockIdx.y == 0 && s.lane0 == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      atomicAdd(dgamma + ch0 + j, r[j] * (float)hw * (e[j] - mu[j] * md[j] - b[j] * cu[j]));
+  }
+  const size_t base = (size_t)n * hw * c + ch0;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    const size_t off = base + (size_t)p * c;
+    float uu[8], dd[8], xx[8], o1[8], o2[8];
+    unpack8(ldg16(u, off), uu);
+    unpack8(ldg16(dy, off), dd);
+    unpack8(ldg16(x, off), xx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xx[j] - m[j]) * r[j];
+      o1[j] = gr[j] * (uu[j] - mu[j] - xh * cu[j]);
+      o2[j] = -gr[j] * r[j] *
+              (xh * (e[j] - mu[j] * md[j] - 3.f * b[j] * cu[j]) + cu[j] * (dd[j] - md[j]) + b[j] * (uu[j] - mu[j]));
+    }
+    stg16(g_dy, off, pack8(o1));
+    stg16(g_x, off, pack8(o2));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise
+// ---------------------------------------------------------------------------------------------
+__global__ void act_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long nvec, int act,
+                               float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(x[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act == SMSUT_ACT_LRELU ? lrelu(v[j], slope) : (act == SMSUT_ACT_RELU ? fmaxf(v[j], 0.f) : v[j]);
+    y[i] = pack8(v);
+  }
+}
+__global__ void act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ ref,
+                               const uint4* __restrict__ add, uint4* __restrict__ dx, long long nvec, int act,
+                               float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], r[8];
+    unpack8(dy[i], g);
+    if (act != SMSUT_ACT_NONE) {
+      unpack8(ref[i], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= act_grad(r[j], act, slope);
+    }
+    if (add != nullptr) {
+      unpack8(add[i], r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += r[j];
+    }
+    dx[i] = pack8(g);
+  }
+}
+__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                           long long nvec) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(a[i], x);
+    unpack8(b[i], y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    out[i] = pack8(x);
+  }
+}
+
+// column sums of a (rows, c) bf16 matrix (bias gradients of the netF Linear layers)
+__global__ void __launch_bounds__(kNT) colsum_kernel(const void* __restrict__ x, float* __restrict__ out, int rows,
+                                                     int c, int splits) {
+  extern __shared__ float sh[];
+  const Strip s = make_strip(c, rows, splits);
+  float acc[1][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = 0.f;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    float v[8];
+    unpack8(ldg16(x, (size_t)p * c + s.g * 8), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
+  }
+  block_reduce_add<1>(acc, sh, s, out, c, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static int pick_splits(int n, int hw, int c) {
+  // >= ~4 blocks per SM overall, each block streaming >= 32 KB
+  const long long bytes = (long long)hw * c * 2;
+  long long s = bytes / (32 * 1024);
+  const long long want = (4LL * device_sm_count() + n - 1) / n;
+  if (s > want) s = want;
+  if (s < 1) s = 1;
+  if (s > hw) s = hw;
+  return (int)s;
+}
+
+static int check_nc(int n, int hw, int c) {
+  SMSUT_CHECK(n > 0 && hw > 0 && c >= 8 && (c & 7) == 0 && kNT % (c >> 3) == 0, -1,
+              "instance-norm kernels need C in {8,16,...,2048} dividing 2048 (got n=%d hw=%d c=%d)", n, hw, c);
+  return 0;
+}
+
+static inline int grid_for(long long nvec) {
+  long long b = (nvec + 255) / 256;
+  const long long cap = 8LL * device_sm_count();
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace smsut
+
+using namespace smsut;
+
+extern "C" int smsut_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float* stats, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  const int splits = pick_splits(n, hw, c);
+  in_stats_kernel<<<dim3(n, splits), kNT, 2 * c * sizeof(float), (cudaStream_t)st>>>(x, stats, hw, c, splits);
+  count_launch();
+  return launch_status("in_stats_kernel");
+}
+
+extern "C" int smsut_in_apply(const void* xa, const float* stats_a, const float* gamma_a, const float* beta_a,
+                              const void* xb, const float* stats_b, const float* gamma_b, const float* beta_b,
+                              const void* res, void* out, int32_t n, int32_t hw, int32_t c, int32_t cp, int32_t act,
+                              float slope, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  const int splits = pick_splits(n, hw, c);
+  in_apply_kernel<<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(xa, stats_a, gamma_a, beta_a, xb, stats_b, gamma_b,
+                                                                 beta_b, res, out, hw, c, cp, splits, act, slope);
+  count_launch();
+  return launch_status("in_apply_kernel");
+}
+
+extern "C" int smsut_in_bwd_reduce(const void* dout, const void* out, const void* xa, const float* stats_a,
+                                   const void* xb, const float* stats_b, float* red, int32_t n, int32_t hw, int32_t c,
+                                   int32_t act, float slope, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  const int splits = pick_splits(n, hw, c);
+  in_bwd_reduce_kernel<<<dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st>>>(
+      dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
+  count_launch();
+  return launch_status("in_bwd_reduce_kernel");
+}
+
+extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void* xa, const float* stats_a,
+                                  const float* gamma_a, void* dxa, float* dgamma_a, float* dbeta_a, const void* xb,
+                                  const float* stats_b, const float* gamma_b, void* dxb, float* dgamma_b,
+                                  float* dbeta_b, void* dres, const float* red, int32_t n, int32_t hw, int32_t c,
+                                  int32_t cp, int32_t act, float slope, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  const int splits = pick_splits(n, hw, c);
+  in_bwd_apply_kernel<<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(dout, out, xa, stats_a, gamma_a, dxa, dgamma_a,
+                                                                     dbeta_a, xb, stats_b, gamma_b, dxb, dgamma_b,
+                                                                     dbeta_b, dres, red, hw, c, cp, splits, act, slope);
+  count_launch();
+  return launch_status("in_bwd_apply_kernel");
+}
+
+extern "C" int smsut_in_bwd2_reduce(const void* u, const void* dy, const void* x, const float* stats, float* red2,
+                                    int32_t n, int32_t hw, int32_t c, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  const int splits = pick_splits(n, hw, c);
+  in_bwd2_reduce_kernel<<<dim3(n, splits), kNT, 5 * c * sizeof(float), (cudaStream_t)st>>>(u, dy, x, stats, red2, hw,
+                                                                                          c, splits);
+  count_launch();
+  return launch_status("in_bwd2_reduce_kernel");
+}
+
+extern "C" int smsut_in_bwd2_apply(const void* u, const void* dy, const void* x, const float* stats,
+                                   const float* gamma, const float* red2, void* g_dy, void* g_x, float* dgamma,
+                                   int32_t n, int32_t hw, int32_t c, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  const int splits = pick_splits(n, hw, c);
+  in_bwd2_apply_kernel<<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(u, dy, x, stats, gamma, red2, g_dy, g_x, dgamma,
+                                                                      hw, c, splits);
+  count_launch();
+  return launch_status("in_bwd2_apply_kernel");
+}
+
+extern "C" int smsut_colsum_bf16(const void* x, int32_t rows, int32_t c, float* out, smsut_stream_t st) {
+  int rc = check_nc(1, rows, c);
+  if (rc) return rc;
+  const int splits = pick_splits(1, rows, c);
+  colsum_kernel<<<dim3(1, splits), kNT, c * sizeof(float), (cudaStream_t)st>>>(x, out, rows, c, splits);
+  count_launch();
+  return launch_status("colsum_kernel");
+}
+
+extern "C" int smsut_act_fwd(const void* x, void* y, int64_t count, int32_t act, float slope, smsut_stream_t st) {
+  SMSUT_CHECK(count % 8 == 0, -1, "element count must be a multiple of 8");
+  act_fwd_kernel<<<grid_for(count / 8), 256, 0, (cudaStream_t)st>>>((const uint4*)x, (uint4*)y, count / 8, act, slope);
+  count_launch();
+  return launch_status("act_fwd_kernel");
+}
+extern "C" int smsut_act_bwd(const void* dy, const void* ref, const void* add, void* dx, int64_t count, int32_t act,
+                             float slope, smsut_stream_t st) {
+  SMSUT_CHECK(count % 8 == 0, -1, "element count must be a multiple of 8");
+  act_bwd_kernel<<<grid_for(count / 8), 256, 0, (cudaStream_t)st>>>((const uint4*)dy, (const uint4*)ref,
+                                                                    (const uint4*)add, (uint4*)dx, count / 8, act, slope);
+  count_launch();
+  return launch_status("act_bwd_kernel");
+}
+extern "C" int smsut_add_bf16(const void* a, const void* b, void* out, int64_t count, smsut_stream_t st) {
+  SMSUT_CHECK(count % 8 == 0, -1, "element count must be a multiple of 8");
+  add_kernel<<<grid_for(count / 8), 256, 0, (cudaStream_t)st>>>((const uint4*)a, (const uint4*)b, (uint4*)out,
+                                                                count / 8);
+  count_launch();
+  return launch_status("add_kernel");
+}

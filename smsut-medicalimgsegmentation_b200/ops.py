@@ -1,0 +1,523 @@
+"""Tensor-level wrappers over the C ABI (include/smsut_b200.h).  No autograd here, no fallbacks.
+
+Conventions: activations are contiguous bf16 torch tensors of shape (N, H, W, C) (NHWC) living on the
+current CUDA device; every call launches on torch's current stream, so the wrappers are safe inside CUDA-graph
+capture and on the autograd engine thread.  Shapes are validated in Python, the library validates the rest and
+reports through smsut_last_error().
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, TC_CONV, TC_CONVT_DGRAD, TC_CONVT_FWD, ConvDirectArgs,
+                   ConvTcArgs, PackEntry, WgradTcArgs, call)
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _chk(t, dtype, name):
+    if t.device.type != "cuda":
+        raise _lib.SmsutError(f"{name}: SMSUT kernels need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+# ----------------------------------------------------------------------------------------------
+# weight packing
+# ----------------------------------------------------------------------------------------------
+class PackedWeight:
+    """bf16 GEMM-ready copies of one fp32 master weight (see smsut_pack_entry)."""
+
+    def __init__(self, weight, transposed=False, need_dgrad=True):
+        self.weight = weight
+        self.transposed = transposed
+        if transposed:
+            cin, cout, kh, kw = weight.shape
+            assert kh == 2 and kw == 2 and cin % 16 == 0 and cout % 16 == 0
+            self.cin_pad, self.cout_pad = cin, cout
+        else:
+            cout, cin, kh, kw = weight.shape
+            self.cin_pad, self.cout_pad = pad16(cin), pad16(cout)
+        self.cin, self.cout, self.kh, self.kw = cin, cout, kh, kw
+        n = self.cin_pad * self.cout_pad * kh * kw
+        dev = weight.device
+        self.fprop = torch.empty(n, dtype=BF16, device=dev)
+        self.dgrad = torch.empty(n, dtype=BF16, device=dev) if need_dgrad else None
+        self.version = -1
+
+    def entry(self):
+        e = PackEntry()
+        e.w = self.weight.data_ptr()
+        e.fprop = self.fprop.data_ptr()
+        e.dgrad = self.dgrad.data_ptr() if self.dgrad is not None else 0
+        e.cout, e.cin, e.kh, e.kw = self.cout, self.cin, self.kh, self.kw
+        e.transposed = 1 if self.transposed else 0
+        e.cout_pad, e.cin_pad = self.cout_pad, self.cin_pad
+        return e
+
+
+class PackTable:
+    """Device table of pack entries: one launch refreshes every bf16 weight copy of a network."""
+
+    def __init__(self, packs):
+        self.packs = list(packs)
+        self._table = None
+        self._ptrs = None
+
+    def _build(self):
+        arr = (PackEntry * len(self.packs))(*[p.entry() for p in self.packs])
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self._table = raw.to(self.packs[0].weight.device)
+        self._ptrs = [p.weight.data_ptr() for p in self.packs]
+
+    def refresh(self, force=False):
+        """Repack if any master weight changed (tensor version counter) or moved."""
+        if not self.packs:
+            return
+        ptrs = [p.weight.data_ptr() for p in self.packs]
+        if self._table is None or ptrs != self._ptrs:
+            self._build()
+            force = True
+        if not force and all(p.version == p.weight._version for p in self.packs):
+            return
+        call("smsut_pack_weights", _p(self._table), len(self.packs), _stream())
+        for p in self.packs:
+            p.version = p.weight._version
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core convolutions
+# ----------------------------------------------------------------------------------------------
+def conv_tc(kind, ksize, n, h, w, srcs, wpack, ncols, ncols_pad, out0, out0_ld, out0_coff=0, out1=None, out1_ld=0,
+            out1_coff=0, split=0, bias=None, act=ACT_NONE, slope=0.01, accumulate=False, out_f32=False, bn=0):
+    """srcs: list of (tensor, channels_used, channel_pitch)."""
+    a = ConvTcArgs()
+    a.kind, a.ksize, a.n, a.h, a.w, a.nsrc = kind, ksize, n, h, w, len(srcs)
+    for i, (t, c, ld) in enumerate(srcs):
+        _chk(t, BF16, "conv_tc src")
+        a.src[i] = t.data_ptr()
+        a.src_c[i] = c
+        a.src_ld[i] = ld
+    a.wpack = wpack.data_ptr()
+    a.ncols, a.ncols_pad = ncols, ncols_pad
+    a.out0, a.out0_ld, a.out0_coff = out0.data_ptr(), out0_ld, out0_coff
+    if out1 is not None:
+        a.out1, a.out1_ld, a.out1_coff, a.split = out1.data_ptr(), out1_ld, out1_coff, split
+    a.bias = bias.data_ptr() if bias is not None else 0
+    a.act, a.slope, a.accumulate, a.out_f32, a.bn = act, slope, int(accumulate), int(out_f32), bn
+    call("smsut_conv_tc", C.byref(a), _stream())
+
+
+def conv_fprop(xs, pw, bias=None, act=ACT_NONE, out_f32=False):
+    """y = conv(cat(xs, channel), W) for a 1x1 / 3x3 stride-1 'same' conv.  xs: NHWC bf16 tensors."""
+    n, h, w, _ = xs[0].shape
+    srcs = [(x, x.shape[3], x.shape[3]) for x in xs]
+    assert sum(s[1] for s in srcs) == pw.cin_pad, (sum(s[1] for s in srcs), pw.cin_pad)
+    y = torch.empty((n, h, w, pw.cout_pad), dtype=F32 if out_f32 else BF16, device=xs[0].device)
+    conv_tc(TC_CONV, pw.kh, n, h, w, srcs, pw.fprop, pw.cout_pad, pw.cout_pad, y, pw.cout_pad, bias=bias, act=act,
+            out_f32=out_f32)
+    return y
+
+
+def conv_dgrad(dy, pw, splits=None):
+    """dx (or one dx per concatenated source) of conv_fprop."""
+    n, h, w, c = dy.shape
+    assert c == pw.cout_pad
+    if splits is None or len(splits) == 1:
+        dx = torch.empty((n, h, w, pw.cin_pad), dtype=BF16, device=dy.device)
+        conv_tc(TC_CONV, pw.kh, n, h, w, [(dy, c, c)], pw.dgrad, pw.cin_pad, pw.cin_pad, dx, pw.cin_pad)
+        return [dx]
+    c0, c1 = splits
+    dx0 = torch.empty((n, h, w, c0), dtype=BF16, device=dy.device)
+    dx1 = torch.empty((n, h, w, c1), dtype=BF16, device=dy.device)
+    conv_tc(TC_CONV, pw.kh, n, h, w, [(dy, c, c)], pw.dgrad, pw.cin_pad, pw.cin_pad, dx0, c0, 0, dx1, c1, 0, c0)
+    return [dx0, dx1]
+
+
+def wgrad_tc(kind, ksize, n, h, w, x, x_c, dy, dy_c, dw, cin_total, ci_off, cout_total, c_valid=0):
+    a = WgradTcArgs()
+    a.kind, a.ksize, a.n, a.h, a.w = kind, ksize, n, h, w
+    a.x, a.x_c, a.x_ld = _chk(x, BF16, "wgrad x").data_ptr(), x_c, x.shape[-1]
+    a.dy, a.dy_c, a.dy_ld = _chk(dy, BF16, "wgrad dy").data_ptr(), dy_c, dy.shape[-1]
+    a.dw = _chk(dw, F32, "wgrad dw").data_ptr()
+    a.cin_total, a.ci_off, a.cout_total, a.c_valid = cin_total, ci_off, cout_total, c_valid
+    call("smsut_wgrad_tc", C.byref(a), _stream())
+
+
+def conv_wgrad(xs, dy, pw):
+    """fp32 OIHW weight gradient of conv_fprop (fresh zeroed tensor)."""
+    n, h, w, _ = xs[0].shape
+    assert pw.cout % 16 == 0, "tensor-core wgrad needs Cout % 16 == 0"
+    dw = torch.zeros_like(pw.weight, dtype=F32)
+    off = 0
+    for x in xs:
+        c = x.shape[3]
+        valid = min(c, pw.cin - off)
+        wgrad_tc(TC_CONV, pw.kh, n, h, w, x, c, dy, pw.cout, dw, pw.cin, off, pw.cout, c_valid=valid)
+        off += c
+    return dw
+
+
+def convt_fprop(x, pw):
+    n, h, w, c = x.shape
+    assert c == pw.cin
+    y = torch.empty((n, 2 * h, 2 * w, pw.cout), dtype=BF16, device=x.device)
+    conv_tc(TC_CONVT_FWD, 1, n, h, w, [(x, c, c)], pw.fprop, 4 * pw.cout, 4 * pw.cout, y, pw.cout)
+    return y
+
+
+def convt_dgrad(dy, pw):
+    n, h2, w2, c = dy.shape
+    assert c == pw.cout
+    dx = torch.empty((n, h2 // 2, w2 // 2, pw.cin), dtype=BF16, device=dy.device)
+    conv_tc(TC_CONVT_DGRAD, 1, n, h2 // 2, w2 // 2, [(dy, c, c)], pw.dgrad, pw.cin, pw.cin, dx, pw.cin)
+    return dx
+
+
+def convt_wgrad(x, dy, pw):
+    n, h, w, c = x.shape
+    dw = torch.zeros_like(pw.weight, dtype=F32)
+    wgrad_tc(TC_CONVT_FWD, 1, n, h, w, x, c, dy, pw.cout, dw, pw.cin, 0, pw.cout)
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------
+# direct convolutions (stems / heads)
+# ----------------------------------------------------------------------------------------------
+def _direct_args(x, weight, y, stride, pad, bias, act, slope, accumulate, cin=None):
+    cout, wcin, kh, kw = weight.shape
+    n, h, w, x_ld = x.shape
+    _, ho, wo, y_ld = y.shape
+    a = ConvDirectArgs()
+    a.n, a.h, a.w, a.cin = n, h, w, wcin if cin is None else cin
+    a.cout, a.kh, a.kw, a.stride, a.pad, a.ho, a.wo = cout, kh, kw, stride, pad, ho, wo
+    a.x, a.x_ld, a.x_f32 = x.data_ptr(), x_ld, int(x.dtype == F32)
+    a.wt = _chk(weight, F32, "direct conv weight").data_ptr()
+    a.bias = bias.data_ptr() if bias is not None else 0
+    a.y, a.y_ld, a.y_f32 = y.data_ptr(), y_ld, int(y.dtype == F32)
+    a.act, a.slope, a.accumulate = act, slope, int(accumulate)
+    return a
+
+
+def direct_out_hw(h, w, k, stride, pad):
+    return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+
+
+def conv_direct_fprop(x, weight, stride, pad, bias=None, act=ACT_NONE, slope=0.01, out_c=None, out_f32=False):
+    """x (N,H,W,x_ld) bf16|fp32 with weight.shape[1] live channels -> (N,Ho,Wo,out_c); channels >= Cout are zero."""
+    cout, _, kh, kw = weight.shape
+    n, h, w, _ = x.shape
+    ho, wo = direct_out_hw(h, w, kh, stride, pad)
+    y = torch.empty((n, ho, wo, out_c or cout), dtype=F32 if out_f32 else BF16, device=x.device)
+    a = _direct_args(x, weight, y, stride, pad, bias, act, slope, False)
+    call("smsut_conv_direct_fprop", C.byref(a), _stream())
+    return y
+
+
+def conv_direct_dgrad(dy, weight, x_shape, x_dtype, stride, pad):
+    dx = torch.empty(x_shape, dtype=x_dtype, device=dy.device)
+    a = _direct_args(dx, weight, dy, stride, pad, None, ACT_NONE, 0.0, False)
+    call("smsut_conv_direct_dgrad", C.byref(a), _stream())
+    return dx
+
+
+def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias):
+    dw = torch.zeros_like(weight, dtype=F32)
+    db = torch.zeros(weight.shape[0], dtype=F32, device=weight.device) if want_bias else None
+    a = _direct_args(x, weight, dy, stride, pad, None, ACT_NONE, 0.0, False)
+    call("smsut_conv_direct_wgrad", C.byref(a), _p(dw), _p(db), _stream())
+    return dw, db
+
+
+# ----------------------------------------------------------------------------------------------
+# InstanceNorm / activations
+# ----------------------------------------------------------------------------------------------
+def in_stats(x):
+    n, h, w, c = _chk(x, BF16, "in_stats x").shape
+    stats = torch.zeros((n, 2, c), dtype=F32, device=x.device)
+    call("smsut_in_stats", _p(x), n, h * w, c, _p(stats), _stream())
+    return stats
+
+
+def in_apply(xa, sa, ga, ba, xb=None, sb=None, gb=None, bb=None, res=None, act=ACT_NONE, slope=0.01, c_params=None):
+    n, h, w, c = xa.shape
+    out = torch.empty_like(xa)
+    call("smsut_in_apply", _p(xa), _p(sa), _p(ga), _p(ba), _p(xb), _p(sb), _p(gb), _p(bb), _p(res), _p(out), n, h * w, c,
+         c if c_params is None else c_params, act, slope, _stream())
+    return out
+
+
+def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=ACT_NONE, slope=0.01, c_params=None):
+    """returns dxa, dgamma_a, dbeta_a, dxb, dgamma_b, dbeta_b, dres"""
+    n, h, w, c = xa.shape
+    cp = c if c_params is None else c_params
+    dev = xa.device
+    red = torch.zeros((n, 3, c), dtype=F32, device=dev)
+    call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(xb), _p(sb), _p(red), n, h * w, c, act, slope,
+         _stream())
+    dxa = torch.empty_like(xa)
+    pg = torch.zeros((4, cp), dtype=F32, device=dev)
+    dxb = torch.empty_like(xa) if xb is not None else None
+    dres = torch.empty_like(xa) if want_res else None
+    call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(dxa), _p(pg[0]), _p(pg[1]), _p(xb), _p(sb),
+         _p(gb), _p(dxb), _p(pg[2]) if xb is not None else _p(None), _p(pg[3]) if xb is not None else _p(None),
+         _p(dres), _p(red), n, h * w, c, cp, act, slope, _stream())
+    return dxa, pg[0], pg[1], dxb, (pg[2] if xb is not None else None), (pg[3] if xb is not None else None), dres
+
+
+def in_bwd2(u, dy, x, stats, gamma):
+    """double backward of plain InstanceNorm: returns g_dy, g_x, dgamma"""
+    n, h, w, c = x.shape
+    red2 = torch.zeros((n, 5, c), dtype=F32, device=x.device)
+    call("smsut_in_bwd2_reduce", _p(u), _p(dy), _p(x), _p(stats), _p(red2), n, h * w, c, _stream())
+    g_dy, g_x = torch.empty_like(x), torch.empty_like(x)
+    dgamma = torch.zeros(c, dtype=F32, device=x.device)
+    call("smsut_in_bwd2_apply", _p(u), _p(dy), _p(x), _p(stats), _p(gamma), _p(red2), _p(g_dy), _p(g_x), _p(dgamma), n,
+         h * w, c, _stream())
+    return g_dy, g_x, dgamma
+
+
+def act_fwd(x, act, slope=0.01):
+    y = torch.empty_like(x)
+    call("smsut_act_fwd", _p(_chk(x, BF16, "act x")), _p(y), x.numel(), act, slope, _stream())
+    return y
+
+
+def act_bwd(dy, ref, add=None, act=ACT_LRELU, slope=0.01):
+    dx = torch.empty_like(dy)
+    call("smsut_act_bwd", _p(_chk(dy, BF16, "act dy")), _p(ref), _p(add), _p(dx), dy.numel(), act, slope, _stream())
+    return dx
+
+
+def add_bf16(a, b):
+    out = torch.empty_like(a)
+    call("smsut_add_bf16", _p(_chk(a, BF16, "add a")), _p(_chk(b, BF16, "add b")), _p(out), a.numel(), _stream())
+    return out
+
+
+def colsum(x):
+    rows, c = x.shape
+    out = torch.zeros(c, dtype=F32, device=x.device)
+    call("smsut_colsum_bf16", _p(_chk(x, BF16, "colsum x")), rows, c, _p(out), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling / resampling / layout
+# ----------------------------------------------------------------------------------------------
+def maxpool2_fwd(x):
+    n, h, w, c = _chk(x, BF16, "maxpool x").shape
+    y = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=x.device)
+    call("smsut_maxpool2_fwd", _p(x), _p(y), n, h, w, c, _stream())
+    return y
+
+
+def maxpool2_bwd(x, dy, add=None):
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    call("smsut_maxpool2_bwd", _p(x), _p(_chk(dy, BF16, "maxpool dy")), _p(add), _p(dx), n, h, w, c, _stream())
+    return dx
+
+
+def avgpool2_fwd(x):
+    n, h, w, c = _chk(x, BF16, "avgpool x").shape
+    y = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=x.device)
+    call("smsut_avgpool2_fwd", _p(x), _p(y), n, h, w, c, _stream())
+    return y
+
+
+def avgpool2_bwd(dy, add=None):
+    n, ho, wo, c = _chk(dy, BF16, "avgpool dy").shape
+    dx = torch.empty((n, 2 * ho, 2 * wo, c), dtype=BF16, device=dy.device)
+    call("smsut_avgpool2_bwd", _p(dy), _p(add), _p(dx), n, 2 * ho, 2 * wo, c, _stream())
+    return dx
+
+
+def bilinear2_fwd(x):
+    n, h, w, c = _chk(x, BF16, "bilinear x").shape
+    y = torch.empty((n, 2 * h, 2 * w, c), dtype=BF16, device=x.device)
+    call("smsut_bilinear2_fwd", _p(x), _p(y), n, h, w, c, _stream())
+    return y
+
+
+def bilinear2_bwd(dy):
+    n, h2, w2, c = _chk(dy, BF16, "bilinear dy").shape
+    dx = torch.empty((n, h2 // 2, w2 // 2, c), dtype=BF16, device=dy.device)
+    call("smsut_bilinear2_bwd", _p(dy), _p(dx), n, h2 // 2, w2 // 2, c, _stream())
+    return dx
+
+
+def nchw_to_nhwc(x, c_pad):
+    n, c, h, w = _chk(x, F32, "nchw x").shape
+    y = torch.empty((n, h, w, c_pad), dtype=BF16, device=x.device)
+    call("smsut_nchw_f32_to_nhwc_bf16", _p(x), _p(y), n, c, h, w, c_pad, _stream())
+    return y
+
+
+def nhwc_to_nchw(x, c):
+    n, h, w, ld = _chk(x, BF16, "nhwc x").shape
+    y = torch.empty((n, c, h, w), dtype=F32, device=x.device)
+    call("smsut_nhwc_bf16_to_nchw_f32", _p(x), _p(y), n, c, h, w, ld, _stream())
+    return y
+
+
+def build_tsl_input(x, m, c_pad):
+    n, _, h, w = _chk(x, F32, "tsl x").shape
+    y = torch.empty((n, h, w, c_pad), dtype=BF16, device=x.device)
+    call("smsut_build_tsl_input", _p(x), _p(_chk(m, F32, "tsl m")), _p(y), n, h * w, m.shape[1], c_pad, _stream())
+    return y
+
+
+# ----------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------
+def dice_ce_fwd(logits, labels, label_logits, acc):
+    """logits fp32 (npix, c) NHWC-flattened; accumulates tp/fp/fn/ce sums into acc[3c+1]."""
+    npix, c = logits.shape
+    call("smsut_dice_ce_fwd", _p(_chk(logits, F32, "dice logits")), _p(labels), _p(label_logits), _p(acc), npix, c,
+         _stream())
+
+
+def dice_ce_finish(acc, npix_total, c, w_dc, w_ce):
+    loss = torch.empty(1, dtype=F32, device=acc.device)
+    call("smsut_dice_ce_finish", _p(acc), _p(loss), npix_total, c, w_dc, w_ce, _stream())
+    return loss
+
+
+def dice_ce_bwd(logits, labels, label_logits, acc, gscale, scale, npix_total, w_dc, w_ce):
+    npix, c = logits.shape
+    d = torch.empty_like(logits)
+    call("smsut_dice_ce_bwd", _p(logits), _p(labels), _p(label_logits), _p(acc), _p(gscale), scale, _p(d), npix,
+         npix_total, c, w_dc, w_ce, _stream())
+    return d
+
+
+def argmax_c(logits):
+    npix, c = logits.shape
+    out = torch.empty(npix, dtype=torch.int64, device=logits.device)
+    call("smsut_argmax_c", _p(_chk(logits, F32, "argmax logits")), _p(out), npix, c, _stream())
+    return out
+
+
+def l1_fwd(a, b, out, scale):
+    call("smsut_l1_fwd", _p(_chk(a, F32, "l1 a")), _p(_chk(b, F32, "l1 b")), _p(out), a.numel(), scale, _stream())
+
+
+def l1_bwd(a, b, gscale, scale):
+    da = torch.empty_like(a)
+    call("smsut_l1_bwd", _p(a), _p(b), _p(gscale), scale, _p(da), a.numel(), _stream())
+    return da
+
+
+def sum_f32(x, out, scale):
+    call("smsut_sum_f32", _p(_chk(x, F32, "sum x")), _p(out), x.numel(), scale, _stream())
+
+
+def fill_f32(x, value):
+    call("smsut_fill_f32", _p(x), x.numel(), value, _stream())
+
+
+def ce_rows_fwd(logits, target, out, scale):
+    rows, c = logits.shape
+    call("smsut_ce_rows_fwd", _p(_chk(logits, F32, "ce logits")), _p(target), _p(out), rows, c, scale, _stream())
+
+
+def ce_rows_bwd(logits, target, gscale, scale):
+    rows, c = logits.shape
+    d = torch.empty_like(logits)
+    call("smsut_ce_rows_bwd", _p(logits), _p(target), _p(gscale), scale, _p(d), rows, c, _stream())
+    return d
+
+
+def gp_fwd(g, out, scale):
+    b = g.shape[0]
+    per = g.numel() // b
+    norm = torch.empty(b, dtype=F32, device=g.device)
+    call("smsut_gp_fwd", _p(_chk(g, F32, "gp g")), _p(norm), _p(out), b, per, scale, _stream())
+    return norm
+
+
+def gp_bwd(g, norm, gscale, scale):
+    b = g.shape[0]
+    u = torch.empty_like(g)
+    call("smsut_gp_bwd", _p(g), _p(norm), _p(gscale), scale, _p(u), b, g.numel() // b, _stream())
+    return u
+
+
+def gather_rows(feat, ids):
+    n, h, w, c = _chk(feat, BF16, "gather feat").shape
+    out = torch.empty((n * ids.numel(), c), dtype=BF16, device=feat.device)
+    call("smsut_gather_rows", _p(feat), _p(ids), _p(out), n, h * w, c, ids.numel(), _stream())
+    return out
+
+
+def scatter_rows_add(dout, ids, dfeat):
+    n, h, w, c = dfeat.shape
+    call("smsut_scatter_rows_add", _p(_chk(dout, BF16, "scatter dout")), _p(ids), _p(dfeat), n, h * w, c, ids.numel(),
+         _stream())
+
+
+def l2norm_fwd(x):
+    rows, c = _chk(x, F32, "l2norm x").shape
+    y = torch.empty_like(x)
+    norm = torch.empty(rows, dtype=F32, device=x.device)
+    call("smsut_l2norm_fwd", _p(x), _p(y), _p(norm), rows, c, _stream())
+    return y, norm
+
+
+def l2norm_bwd(dy, y, norm):
+    rows, c = y.shape
+    dx = torch.empty((rows, c), dtype=BF16, device=y.device)
+    call("smsut_l2norm_bwd", _p(_chk(dy, F32, "l2norm dy")), _p(y), _p(norm), _p(dx), rows, c, _stream())
+    return dx
+
+
+def patchnce_fwd(q, k, groups, np_, inv_t, out, scale):
+    rows, c = q.shape
+    loss_rows = torch.empty(rows, dtype=F32, device=q.device)
+    call("smsut_patchnce_fwd", _p(_chk(q, F32, "nce q")), _p(_chk(k, F32, "nce k")), _p(loss_rows), _p(out), groups,
+         np_, c, inv_t, scale, _stream())
+    return loss_rows
+
+
+def patchnce_bwd(q, k, groups, np_, inv_t, gscale, scale):
+    dq = torch.empty_like(q)
+    call("smsut_patchnce_bwd", _p(q), _p(k), _p(gscale), scale, _p(dq), groups, np_, q.shape[1], inv_t, _stream())
+    return dq
+
+
+# ----------------------------------------------------------------------------------------------
+# optimisers over flat fp32 buffers
+# ----------------------------------------------------------------------------------------------
+def sgd_step(p, g, mom, lr, momentum, weight_decay, grad_scale=1.0):
+    call("smsut_sgd_step", _p(p), _p(g), _p(mom), p.numel(), _p(lr), momentum, weight_decay, grad_scale, _stream())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=1.0):
+    call("smsut_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(lr), beta1, beta2, eps, weight_decay, _p(state),
+         grad_scale, _stream())
+
+
+def ema_update(ema, p, alpha):
+    call("smsut_ema_update", _p(ema), _p(p), p.numel(), _p(alpha), _stream())
+
+
+def poly_lr_tick(iter_state, lr_out, base_lr, max_iter, power):
+    call("smsut_poly_lr_tick", _p(iter_state), _p(lr_out), base_lr, max_iter, power, _stream())

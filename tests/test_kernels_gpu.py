@@ -1,0 +1,418 @@
+"""GPU parity of every C-ABI kernel against a plain PyTorch fp32 statement of the same op.
+
+Inputs are rounded to bf16 first so the only differences are accumulation order and the final bf16 rounding:
+tolerance is relative L2 <= 1e-2 for bf16 outputs (north_star: 2e-2 per layer) and 1e-4..1e-3 for fp32 outputs.
+All calls go through the C ABI (smsut_b200.ops -> ctypes -> libsmsut_b200.so).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+def nhwc(t):  # NCHW fp32 -> NHWC bf16 contiguous
+    return bf(t).permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(t):  # NHWC -> NCHW fp32
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def rnd(*shape, scale=1.0, seed=None):
+    if seed is not None:
+        torch.manual_seed(seed)
+    return bf(torch.randn(*shape, device=DEV) * scale).float()
+
+
+@pytest.fixture(scope="module")
+def ops(pkg):
+    from smsut_b200 import ops as o
+    return o
+
+
+def make_pack(ops, weight, transposed=False):
+    pw = ops.PackedWeight(weight, transposed=transposed)
+    ops.PackTable([pw]).refresh()
+    return pw
+
+
+# (cin list, cout, h, n, ksize)  -- the layer classes of SURVEY.md section 8(d) plus the discriminator's
+CONV_CASES = [
+    ([16], 16, 256, 2, 3), ([16, 16], 16, 256, 1, 3), ([16], 32, 128, 2, 3), ([32], 32, 128, 2, 3),
+    ([32, 32], 32, 128, 2, 3), ([32], 64, 64, 2, 3), ([64], 64, 64, 3, 3), ([64, 64], 64, 64, 2, 3),
+    ([64], 128, 32, 2, 3), ([128], 128, 32, 2, 3), ([128, 128], 128, 32, 2, 3), ([128], 256, 16, 2, 3),
+    ([256], 256, 16, 2, 3), ([256], 256, 8, 4, 3), ([256], 256, 4, 16, 3), ([256], 256, 4, 3, 3),
+    ([16], 32, 128, 2, 1), ([32, 32], 32, 128, 1, 1), ([128], 256, 16, 2, 1), ([16], 16, 256, 1, 1),
+    ([64], 32, 64, 2, 1), ([256], 128, 32, 2, 1),
+]
+
+
+@pytest.mark.parametrize("cins,cout,h,n,ks", CONV_CASES)
+def test_conv_tc_fprop_dgrad_wgrad(ops, cins, cout, h, n, ks):
+    torch.manual_seed(1)
+    cin = sum(cins)
+    xs = [rnd(n, c, h, h) for c in cins]
+    wt = rnd(cout, cin, ks, ks, scale=(2.0 / (cin * ks * ks)) ** 0.5)
+    pw = make_pack(ops, wt)
+    x_cat = torch.cat(xs, 1)
+    y_ref = F.conv2d(x_cat, wt, padding=ks // 2)
+    y = ops.conv_fprop([nhwc(x) for x in xs], pw)
+    assert rel(nchw(y), y_ref) < 1e-2
+
+    dy = rnd(n, cout, h, h)
+    dx_ref = torch.nn.grad.conv2d_input(x_cat.shape, wt, dy, padding=ks // 2)
+    dxs = ops.conv_dgrad(nhwc(dy), pw, splits=cins)
+    dx = torch.cat([nchw(d) for d in dxs], 1)
+    assert rel(dx, dx_ref) < 1e-2
+
+    dw_ref = torch.nn.grad.conv2d_weight(x_cat, wt.shape, dy, padding=ks // 2)
+    dw = ops.conv_wgrad([nhwc(x) for x in xs], nhwc(dy), pw)
+    assert rel(dw, dw_ref) < 1e-2
+
+
+def test_conv_tc_padded_input_channels(ops):
+    """8 live channels in a 16-channel tensor (the 5x5 stem feeds enc1.conv1 this way)."""
+    n, h, cin, cout = 2, 64, 8, 16
+    x = rnd(n, cin, h, h, seed=2)
+    wt = rnd(cout, cin, 3, 3, scale=0.1)
+    pw = make_pack(ops, wt)
+    xp = torch.cat([x, torch.zeros_like(x)], 1)
+    y = ops.conv_fprop([nhwc(xp)], pw)
+    assert rel(nchw(y), F.conv2d(x, wt, padding=1)) < 1e-2
+    dy = rnd(n, cout, h, h)
+    dx = nchw(ops.conv_dgrad(nhwc(dy), pw)[0])
+    assert dx[:, cin:].abs().max().item() == 0.0
+    assert rel(dx[:, :cin], torch.nn.grad.conv2d_input(x.shape, wt, dy, padding=1)) < 1e-2
+    dw = ops.conv_wgrad([nhwc(xp)], nhwc(dy), pw)
+    assert rel(dw, torch.nn.grad.conv2d_weight(x, wt.shape, dy, padding=1)) < 1e-2
+
+
+def test_conv_tc_bias_relu_f32_linear(ops):
+    """netF's Linear(256,256)+ReLU as a 1x1 conv over (1, 8, 128) 'pixels' with fp32 output."""
+    rows, c = 1024, 256
+    x = rnd(rows, c, seed=3)
+    wt = rnd(c, c, scale=0.05)
+    b = torch.randn(c, device=DEV)
+    pw = make_pack(ops, wt.view(c, c, 1, 1))
+    y = ops.conv_fprop([bf(x).view(1, 8, 128, c)], pw, bias=b, act=ops.ACT_RELU, out_f32=True)
+    assert y.dtype == torch.float32
+    assert rel(y.view(rows, c), F.relu(x @ wt.t() + b)) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,h,n", [(32, 16, 128, 2), (64, 32, 64, 2), (128, 64, 32, 2), (256, 128, 16, 2)])
+def test_convt_tc(ops, cin, cout, h, n):
+    x = rnd(n, cin, h, h, seed=4)
+    wt = rnd(cin, cout, 2, 2, scale=(1.0 / cin) ** 0.5)
+    pw = make_pack(ops, wt, transposed=True)
+    y_ref = F.conv_transpose2d(x, wt, stride=2)
+    y = ops.convt_fprop(nhwc(x), pw)
+    assert rel(nchw(y), y_ref) < 1e-2
+    dy = rnd(n, cout, 2 * h, 2 * h)
+    dx_ref = F.conv2d(dy, wt, stride=2)
+    assert rel(nchw(ops.convt_dgrad(nhwc(dy), pw)), dx_ref) < 1e-2
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, wr, stride=2).backward(dy)
+    assert rel(ops.convt_wgrad(nhwc(x), nhwc(dy), pw), wr.grad) < 1e-2
+
+
+DIRECT_CASES = [
+    # cin, cout, k, stride, pad, h, x_f32, bias
+    (1, 8, 5, 1, 2, 64, False, False), (5, 8, 5, 1, 2, 64, False, False), (1, 16, 4, 2, 1, 64, True, True),
+    (16, 1, 1, 1, 0, 64, False, True), (16, 5, 1, 1, 0, 64, False, True), (256, 1, 3, 1, 1, 4, False, False),
+    (256, 4, 4, 1, 0, 4, False, False),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,h,x_f32,bias", DIRECT_CASES)
+def test_conv_direct(ops, cin, cout, k, stride, pad, h, x_f32, bias):
+    n = 3
+    torch.manual_seed(5)
+    x = rnd(n, cin, h, h)
+    wt = torch.randn(cout, cin, k, k, device=DEV) * (1.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, device=DEV) if bias else None
+    xin = x.permute(0, 2, 3, 1).contiguous() if x_f32 else F.pad(nhwc(x), (0, (-cin) % 8))
+    y_ref = F.conv2d(x, wt, b, stride=stride, padding=pad)
+    y = ops.conv_direct_fprop(xin, wt, stride, pad, bias=b, out_f32=True)
+    assert rel(nchw(y), y_ref) < 1e-4
+    ypad = ops.conv_direct_fprop(xin, wt, stride, pad, bias=b, out_c=16)
+    assert ypad.dtype == torch.bfloat16 and ypad.shape[-1] == 16
+    assert rel(nchw(ypad)[:, :cout], y_ref) < 1e-2
+    assert ypad[..., cout:].abs().max().item() == 0.0
+
+    dy = torch.randn_like(y_ref)
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    dx_ref = torch.nn.grad.conv2d_input(x.shape, wt, dy, stride=stride, padding=pad)
+    dx = ops.conv_direct_dgrad(dyn, wt, (n, h, h, cin), torch.float32, stride, pad)
+    assert rel(nchw(dx), dx_ref) < 1e-4
+    dw_ref = torch.nn.grad.conv2d_weight(x, wt.shape, dy, stride=stride, padding=pad)
+    dw, db = ops.conv_direct_wgrad(xin, dyn, wt, stride, pad, want_bias=bias)
+    assert rel(dw, dw_ref) < 1e-4
+    if bias:
+        assert rel(db, dy.sum((0, 2, 3))) < 1e-4
+
+
+def in_ref(x, g, b):
+    return F.instance_norm(x, weight=g, bias=b, eps=1e-5)
+
+
+@pytest.mark.parametrize("c,h,n", [(16, 64, 3), (32, 32, 2), (256, 16, 2), (64, 8, 5)])
+def test_instance_norm_fwd_bwd(ops, c, h, n):
+    torch.manual_seed(6)
+    xa, xb, res = rnd(n, c, h, h) * 2 + 0.5, rnd(n, c, h, h), rnd(n, c, h, h)
+    ga, ba, gb, bb = [torch.randn(c, device=DEV) for _ in range(4)]
+    a, b2 = nhwc(xa), nhwc(xb)
+    sa, sb = ops.in_stats(a), ops.in_stats(b2)
+    assert rel(sa[:, 0], xa.sum((2, 3))) < 1e-4
+    # plain IN + lrelu
+    out = ops.in_apply(a, sa, ga, ba, act=ops.ACT_LRELU)
+    xr = xa.clone().requires_grad_(True)
+    gr, br = ga.clone().requires_grad_(True), ba.clone().requires_grad_(True)
+    ref = F.leaky_relu(in_ref(xr, gr, br), 0.01)
+    assert rel(nchw(out), ref) < 1e-2
+    dout = rnd(n, c, h, h)
+    ref.backward(dout)
+    dxa, dga, dba, *_ = ops.in_bwd(nhwc(dout), out, a, sa, ga, act=ops.ACT_LRELU)
+    assert rel(nchw(dxa), xr.grad) < 2e-2
+    assert rel(dga, gr.grad) < 2e-2 and rel(dba, br.grad) < 2e-2
+    # two normalised branches + residual + lrelu
+    out2 = ops.in_apply(a, sa, ga, ba, b2, sb, gb, bb, res=nhwc(res), act=ops.ACT_LRELU)
+    leaves = [t.clone().requires_grad_(True) for t in (xa, ga, ba, xb, gb, bb, res)]
+    ref2 = F.leaky_relu(in_ref(*leaves[0:3]) + in_ref(*leaves[3:6]) + leaves[6], 0.01)
+    assert rel(nchw(out2), ref2) < 1e-2
+    ref2.backward(dout)
+    got = ops.in_bwd(nhwc(dout), out2, a, sa, ga, b2, sb, gb, want_res=True, act=ops.ACT_LRELU)
+    for g_, l_ in zip(got, leaves):
+        g_ = nchw(g_) if g_.dim() == 4 else g_
+        assert rel(g_, l_.grad) < 2e-2
+
+
+@pytest.mark.parametrize("c,h,n", [(16, 32, 2), (64, 16, 3)])
+def test_instance_norm_double_backward(ops, c, h, n):
+    torch.manual_seed(7)
+    x = (rnd(n, c, h, h) * 1.5 + 0.3).requires_grad_(True)
+    g = (torch.rand(c, device=DEV) + 0.5).requires_grad_(True)
+    b = torch.zeros(c, device=DEV, requires_grad=True)
+    dy = rnd(n, c, h, h).requires_grad_(True)
+    u = rnd(n, c, h, h)
+    y = in_ref(x, g, b)
+    (dx,) = torch.autograd.grad(y, x, dy, create_graph=True)
+    g_dy, g_x, g_g = torch.autograd.grad(dx, (dy, x, g), u)
+    xs = nhwc(x.detach())
+    st = ops.in_stats(xs)
+    k_dy, k_x, k_g = ops.in_bwd2(nhwc(u), nhwc(dy.detach()), xs, st, g.detach())
+    assert rel(nchw(k_dy), g_dy) < 2e-2
+    assert rel(nchw(k_x), g_x) < 3e-2
+    assert rel(k_g, g_g) < 3e-2
+
+
+def test_elementwise_and_colsum(ops):
+    x, y = rnd(2, 16, 32, 32, seed=8), rnd(2, 16, 32, 32)
+    a, b = nhwc(x), nhwc(y)
+    assert rel(nchw(ops.act_fwd(a, ops.ACT_LRELU)), F.leaky_relu(x, 0.01)) < 1e-2
+    assert rel(nchw(ops.add_bf16(a, b)), x + y) < 1e-2
+    ref = y * torch.where(x > 0, 1.0, 0.01) + x
+    assert rel(nchw(ops.act_bwd(b, a, add=a, act=ops.ACT_LRELU)), ref) < 1e-2
+    m = rnd(1024, 256)
+    assert rel(ops.colsum(bf(m)), m.sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("c,h,n", [(16, 64, 2), (128, 16, 3)])
+def test_pool_and_resample(ops, c, h, n):
+    torch.manual_seed(9)
+    x = rnd(n, c, h, h)
+    a = nhwc(x)
+    xr = x.clone().requires_grad_(True)
+    mp = F.max_pool2d(xr, 2, 2)
+    assert torch.equal(nchw(ops.maxpool2_fwd(a)), mp.detach())
+    dy = rnd(n, c, h // 2, h // 2)
+    mp.backward(dy)
+    assert rel(nchw(ops.maxpool2_bwd(a, nhwc(dy))), xr.grad) < 1e-6
+    assert rel(nchw(ops.maxpool2_bwd(a, nhwc(dy), add=a)), xr.grad + x) < 1e-2
+    assert rel(nchw(ops.avgpool2_fwd(a)), F.avg_pool2d(x, 2)) < 1e-2
+    assert rel(nchw(ops.avgpool2_bwd(nhwc(dy))), 0.25 * F.interpolate(dy, scale_factor=2, mode="nearest")) < 1e-2
+    xr2 = x.clone().requires_grad_(True)
+    up = F.interpolate(xr2, scale_factor=2, mode="bilinear", align_corners=False)
+    assert rel(nchw(ops.bilinear2_fwd(a)), up) < 1e-2
+    d2 = rnd(n, c, 2 * h, 2 * h)
+    up.backward(d2)
+    assert rel(nchw(ops.bilinear2_bwd(nhwc(d2))), xr2.grad) < 1e-2
+
+
+def test_maxpool_ties_route_to_first(ops):
+    x = torch.zeros(1, 8, 4, 4, device=DEV)
+    dy = torch.ones(1, 8, 2, 2, device=DEV)
+    xr = x.clone().requires_grad_(True)
+    F.max_pool2d(xr, 2, 2).backward(dy)
+    assert torch.equal(nchw(ops.maxpool2_bwd(nhwc(x), nhwc(dy))), xr.grad)
+
+
+def test_layout_kernels(ops):
+    x = torch.randn(3, 5, 16, 16, device=DEV)
+    y = ops.nchw_to_nhwc(x, 8)
+    assert torch.equal(y[..., :5], nhwc(x)) and y[..., 5:].abs().max().item() == 0
+    assert torch.equal(ops.nhwc_to_nchw(y, 5), bf(x).float())
+    img = torch.randn(3, 1, 16, 16, device=DEV)
+    m = torch.tensor([[1., 0, -1, 0], [0, 0, 0, 0], [-1, 1, 0, 0]], device=DEV)
+    t = ops.build_tsl_input(img, m, 8)
+    ref = torch.cat([img, m.view(3, 4, 1, 1).repeat(1, 1, 16, 16)], 1)
+    assert torch.equal(t[..., :5], nhwc(ref)) and t[..., 5:].abs().max().item() == 0
+
+
+def dice_ce_ref(logits, labels, w_ce=0.5, w_dc=0.5):
+    # restates misc/loss.py:16-63 (batch dice, background dropped, double epsilon)
+    p = torch.softmax(logits, 1)
+    oh = F.one_hot(labels, logits.shape[1]).permute(0, 3, 1, 2).float()
+    tp, fp, fn = (p * oh).sum((0, 2, 3)), (p * (1 - oh)).sum((0, 2, 3)), ((1 - p) * oh).sum((0, 2, 3))
+    dc = (2 * tp + 1e-5) / (2 * tp + fp + fn + 1e-5 + 1e-8)
+    return w_dc * (1 - dc[1:].mean()) + w_ce * F.cross_entropy(logits, labels)
+
+
+@pytest.mark.parametrize("pseudo", [False, True])
+def test_dice_ce(ops, pseudo):
+    torch.manual_seed(10)
+    n, c, h = 4, 5, 64
+    logits = (torch.randn(n, c, h, h, device=DEV) * 2).requires_grad_(True)
+    other = torch.randn(n, c, h, h, device=DEV)
+    labels = other.argmax(1) if pseudo else torch.randint(0, c, (n, h, h), device=DEV)
+    ref = dice_ce_ref(logits, labels)
+    ref.backward()
+    lg = logits.detach().permute(0, 2, 3, 1).reshape(-1, c).contiguous()
+    ol = other.permute(0, 2, 3, 1).reshape(-1, c).contiguous() if pseudo else None
+    lab = None if pseudo else labels.reshape(-1).contiguous()
+    acc = torch.zeros(3 * c + 1, device=DEV)
+    ops.dice_ce_fwd(lg, lab, ol, acc)
+    loss = ops.dice_ce_finish(acc, lg.shape[0], c, 0.5, 0.5)
+    assert abs(loss.item() - ref.item()) < 1e-4 * max(1.0, abs(ref.item()))
+    one = torch.ones(1, device=DEV)
+    d = ops.dice_ce_bwd(lg, lab, ol, acc, one, 1.0, lg.shape[0], 0.5, 0.5)
+    assert rel(d.view(n, h, h, c).permute(0, 3, 1, 2), logits.grad) < 1e-3
+    if pseudo:
+        assert torch.equal(ops.argmax_c(ol), labels.reshape(-1))
+
+
+def test_small_losses(ops):
+    torch.manual_seed(11)
+    a = torch.randn(4, 1, 32, 32, device=DEV, requires_grad=True)
+    b = torch.randn(4, 1, 32, 32, device=DEV)
+    out = torch.zeros(1, device=DEV)
+    ops.l1_fwd(a.detach(), b, out, 1.0 / a.numel())
+    ref = (a - b).abs().mean()
+    ref.backward()
+    assert abs(out.item() - ref.item()) < 1e-5
+    one = torch.ones(1, device=DEV)
+    assert rel(ops.l1_bwd(a.detach(), b, one, 1.0 / a.numel()), a.grad) < 1e-6
+    # modality CE
+    z = torch.randn(16, 4, device=DEV, requires_grad=True)
+    t = torch.randint(0, 4, (16,), device=DEV)
+    out.zero_()
+    ops.ce_rows_fwd(z.detach(), t, out, 1.0)
+    ref = F.cross_entropy(z, t)
+    ref.backward()
+    assert abs(out.item() - ref.item()) < 1e-5
+    assert rel(ops.ce_rows_bwd(z.detach(), t, one, 1.0), z.grad) < 1e-5
+    # gradient penalty (trainer/uganShp0Trainer.py:127-134)
+    g = torch.randn(8, 1, 32, 32, device=DEV, requires_grad=True)
+    out.zero_()
+    norm = ops.gp_fwd(g.detach(), out, 1.0)
+    ref = ((g.view(8, -1).pow(2).sum(1).sqrt() - 1) ** 2).mean()
+    ref.backward()
+    assert abs(out.item() - ref.item()) < 1e-4 * ref.item()
+    assert rel(ops.gp_bwd(g.detach(), norm, one, 1.0), g.grad) < 1e-5
+    # mean
+    out.zero_()
+    ops.sum_f32(b, out, 1.0 / b.numel())
+    assert abs(out.item() - b.mean().item()) < 1e-5
+
+
+def test_patchnce_pipeline(ops):
+    """gather -> L2 normalise -> PatchNCE (network/ugan.py:316-334, network/patchnce.py:13-51)."""
+    torch.manual_seed(12)
+    n, c, hw, nid, groups = 4, 256, 16, 64, 2
+    feat = rnd(n, c, hw, hw)
+    ids = torch.randperm(hw * hw, device=DEV)[:nid]
+    rows = ops.gather_rows(nhwc(feat), ids)
+    ref_rows = feat.permute(0, 2, 3, 1).flatten(1, 2)[:, ids, :].flatten(0, 1)
+    assert torch.equal(rows.float(), ref_rows)
+    d = torch.zeros(n, hw, hw, c, device=DEV, dtype=torch.bfloat16)
+    ops.scatter_rows_add(rows, ids, d)
+    refd = torch.zeros(n, hw * hw, c, device=DEV)
+    refd[:, ids, :] = ref_rows.view(n, nid, c)
+    assert torch.equal(d.float().view(n, hw * hw, c), refd)
+
+    q0 = torch.randn(n * nid, c, device=DEV, requires_grad=True)
+    k0 = torch.randn(n * nid, c, device=DEV)
+    qn = q0 / (q0.pow(2).sum(1, keepdim=True).sqrt() + 1e-7)
+    kn = k0 / (k0.pow(2).sum(1, keepdim=True).sqrt() + 1e-7)
+    y, norm = ops.l2norm_fwd(q0.detach())
+    assert rel(y, qn) < 1e-5
+    # reference PatchNCE restated
+    B = n * nid
+    l_pos = (qn * kn).sum(1, keepdim=True)
+    qg, kg = qn.view(groups, -1, c), kn.view(groups, -1, c)
+    npg = qg.shape[1]
+    l_neg = torch.bmm(qg, kg.transpose(2, 1))
+    eye = torch.eye(npg, device=DEV, dtype=torch.bool)[None]
+    l_neg = l_neg.masked_fill(eye, -10.0).view(-1, npg)
+    outl = torch.cat((l_pos, l_neg), 1) / 0.07
+    ref_rows_loss = F.cross_entropy(outl, torch.zeros(B, dtype=torch.long, device=DEV), reduction="none")
+    ref = ref_rows_loss.mean()
+    ref.backward()
+    out = torch.zeros(1, device=DEV)
+    kk, _ = ops.l2norm_fwd(k0)
+    lr = ops.patchnce_fwd(y, kk, groups, npg, 1 / 0.07, out, 1.0)
+    assert rel(lr, ref_rows_loss) < 1e-4 and abs(out.item() - ref.item()) < 1e-4
+    one = torch.ones(1, device=DEV)
+    dq = ops.patchnce_bwd(y, kk, groups, npg, 1 / 0.07, one, 1.0)
+    dx = ops.l2norm_bwd(dq, y, norm)
+    assert rel(dx, q0.grad) < 1e-2
+
+
+def test_optimisers(ops):
+    torch.manual_seed(13)
+    n = 100003
+    p0, g = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+    lr = torch.tensor([1e-2], device=DEV)
+    # SGD momentum 0.9 wd 1e-3, two steps
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=1e-2, momentum=0.9, weight_decay=1e-3)
+    p, mom = p0.clone(), torch.zeros(n, device=DEV)
+    for _ in range(2):
+        pr.grad = g.clone()
+        opt.step()
+        ops.sgd_step(p, g, mom, lr, 0.9, 1e-3)
+    assert rel(p, pr.detach()) < 1e-6
+    # Adam with L2 weight decay, three steps
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-2, betas=(0.9, 0.999), weight_decay=1e-3)
+    p, m, v, st = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(1, device=DEV)
+    for _ in range(3):
+        pr.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, lr, 0.9, 0.999, 1e-8, 1e-3, st)
+    assert rel(p, pr.detach()) < 1e-5
+    # EMA
+    ema, alpha = torch.randn(n, device=DEV), torch.tensor([0.99], device=DEV)
+    ref = 0.99 * ema + 0.01 * p0
+    ops.ema_update(ema, p0, alpha)
+    assert rel(ema, ref) < 1e-6
+    # poly LR: lr used at step k+1 is base*(1-k/max)^0.9
+    it, lro = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    got = []
+    for _ in range(4):
+        ops.poly_lr_tick(it, lro, 1e-2, 30000.0, 0.9)
+        got.append(lro.item())
+    want = [1e-2 * (1 - max(k - 1, 0) / 30000.0) ** 0.9 for k in range(4)]
+    assert max(abs(a - b) for a, b in zip(got, want)) < 1e-8
