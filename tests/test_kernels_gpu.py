@@ -11,6 +11,9 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
+# the torch statements must be true fp32 (cuDNN / cuBLAS default to TF32 for fp32 inputs)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def rel(a, b):
@@ -150,7 +153,8 @@ def test_conv_direct(ops, cin, cout, k, stride, pad, h, x_f32, bias):
     ypad = ops.conv_direct_fprop(xin, wt, stride, pad, bias=b, out_c=16)
     assert ypad.dtype == torch.bfloat16 and ypad.shape[-1] == 16
     assert rel(nchw(ypad)[:, :cout], y_ref) < 1e-2
-    assert ypad[..., cout:].abs().max().item() == 0.0
+    if cout < 16:
+        assert ypad[..., cout:].abs().max().item() == 0.0
 
     dy = torch.randn_like(y_ref)
     dyn = dy.permute(0, 2, 3, 1).contiguous()
@@ -171,7 +175,7 @@ def in_ref(x, g, b):
 @pytest.mark.parametrize("c,h,n", [(16, 64, 3), (32, 32, 2), (256, 16, 2), (64, 8, 5)])
 def test_instance_norm_fwd_bwd(ops, c, h, n):
     torch.manual_seed(6)
-    xa, xb, res = rnd(n, c, h, h) * 2 + 0.5, rnd(n, c, h, h), rnd(n, c, h, h)
+    xa, xb, res = bf(rnd(n, c, h, h) * 2 + 0.5).float(), rnd(n, c, h, h), rnd(n, c, h, h)
     ga, ba, gb, bb = [torch.randn(c, device=DEV) for _ in range(4)]
     a, b2 = nhwc(xa), nhwc(xb)
     sa, sb = ops.in_stats(a), ops.in_stats(b2)
@@ -202,7 +206,7 @@ def test_instance_norm_fwd_bwd(ops, c, h, n):
 @pytest.mark.parametrize("c,h,n", [(16, 32, 2), (64, 16, 3)])
 def test_instance_norm_double_backward(ops, c, h, n):
     torch.manual_seed(7)
-    x = (rnd(n, c, h, h) * 1.5 + 0.3).requires_grad_(True)
+    x = bf(rnd(n, c, h, h) * 1.5 + 0.3).float().requires_grad_(True)
     g = (torch.rand(c, device=DEV) + 0.5).requires_grad_(True)
     b = torch.zeros(c, device=DEV, requires_grad=True)
     dy = rnd(n, c, h, h).requires_grad_(True)
