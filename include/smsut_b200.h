@@ -194,6 +194,13 @@ int smsut_l1_bwd(const float* a, const float* b, const float* gscale, float scal
 /* out[0] += scale * sum(x) (fp32) */
 int smsut_sum_f32(const float* x, float* out, int64_t count, float scale, smsut_stream_t stream);
 int smsut_fill_f32(float* x, int64_t count, float value, smsut_stream_t stream);
+/* x[i] = gscale[0]*scale: backward of the adversarial means -mean(D(x)) (trainer/uganConsisTrainer.py:130,136,154) */
+int smsut_fill_scaled_f32(float* x, int64_t count, const float* gscale, float scale, smsut_stream_t stream);
+/* dx = dy*(1 - y^2): backward of the tanh fused into the translation head (network/ugan.py:73,82) */
+int smsut_tanh_bwd(const float* dy, const float* y, float* dx, int64_t count, smsut_stream_t stream);
+/* out[r][i] = alpha[r]*x[r][i] + (1-alpha[r])*y[r][i]: x_hat of the gradient penalty (trainer/uganConsisTrainer.py:139) */
+int smsut_lerp_rows_f32(const float* alpha, const float* x, const float* y, float* out, int32_t rows, int64_t per,
+                        smsut_stream_t stream);
 /* softmax cross-entropy on small (rows, c<=8) fp32 logits with int64 targets: out[0] += scale*mean CE;
  * dlogits = gscale*scale*(p - onehot)/rows */
 int smsut_ce_rows_fwd(const float* logits, const int64_t* target, float* out, int32_t rows, int32_t c, float scale,

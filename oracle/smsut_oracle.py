@@ -378,21 +378,18 @@ def unet_step(sd, opt_state, x, y, lr, dice_stats_hook=None):
     return loss.detach(), grads
 
 
-def ugan_consis_step(G, D, g_state, d_state, x_real, y_real, modal_org, mj, alpha, sample_ids, lr, it, lambda_semi,
-                     nce_batch=None, semi_from_iter=1000, lambdas=(1.0, 10.0, 10.0, 10.0)):
-    """One iteration of UGANConsisTrainer.train_epoch (trainer/uganConsisTrainer.py:110-203), n_critic = 1, with
-    the random draws (target modality mj L114, alpha L138, patch ids ugan.py:321) injected.
-    Returns the 10 losses, the D and G gradients; G, D and the optimiser states are updated in place."""
-    lambda_cls, lambda_rec, lambda_gp, lambda_seg = lambdas
-    bs = y_real.shape[0]
-    n_modal = D["conv_cls.weight"].shape[0]
-    dev = x_real.device
+def _modal_vectors(modal_org, mj, n_modal, dev):
     modal_trg = torch.full_like(modal_org, mj)
     vec_org = label2onehot(modal_org.cpu(), n_modal).to(dev); vec_trg = label2onehot(modal_trg.cpu(), n_modal).to(dev)
-    vec_ot, vec_to = vec_trg - vec_org, vec_org - vec_trg
-    nce_batch = nce_batch or bs
+    return modal_trg, vec_trg - vec_org, vec_org - vec_trg
 
-    # ---- D phase (L129-146)
+
+def ugan_d_phase(G, D, d_state, x_real, modal_org, mj, alpha, sample_ids, lr, lambdas=(1.0, 10.0, 10.0, 10.0)):
+    """D step of UGANConsisTrainer.train_epoch (trainer/uganConsisTrainer.py:129-149) with the random draws
+    (target modality L114, alpha L138, patch ids ugan.py:321) injected.  Updates D / d_state in place."""
+    lambda_cls, _, lambda_gp, _ = lambdas
+    n_modal = D["conv_cls.weight"].shape[0]
+    _, vec_ot, _ = _modal_vectors(modal_org, mj, n_modal, x_real.device)
     Dl = _leaf(D)
     out_src, out_cls = discriminator_forward(Dl, x_real)
     d_real = -out_src.mean()
@@ -407,8 +404,19 @@ def ugan_consis_step(G, D, g_state, d_state, x_real, y_real, modal_org, mj, alph
     d_loss = d_real + d_fake + lambda_cls * d_cls + lambda_gp * d_gp
     d_grads = dict(zip(Dl, torch.autograd.grad(d_loss, list(Dl.values()))))
     adam_update(D, d_grads, d_state, lr)
+    losses = dict(D_real=d_real, D_fake=d_fake, D_cls=d_cls, D_gp=d_gp)
+    return {k: float(v.detach()) for k, v in losses.items()}, d_grads
 
-    # ---- G phase (L151-180); D already stepped
+
+def ugan_g_phase(G, D, g_state, x_real, y_real, modal_org, mj, sample_ids, lr, it, lambda_semi, nce_batch=None,
+                 semi_from_iter=1000, lambdas=(1.0, 10.0, 10.0, 10.0)):
+    """G step (trainer/uganConsisTrainer.py:151-188) against the already-updated D.  Updates G / g_state in place."""
+    lambda_cls, lambda_rec, _, lambda_seg = lambdas
+    bs = y_real.shape[0]
+    dev = x_real.device
+    n_modal = D["conv_cls.weight"].shape[0]
+    modal_trg, vec_ot, vec_to = _modal_vectors(modal_org, mj, n_modal, dev)
+    nce_batch = nce_batch or bs
     Gl = _leaf(G)
     y_fake, x_fake, feat_x, _ = ugannce_forward(Gl, x_real, vec_ot, sample_ids=sample_ids)
     out_src, out_cls = discriminator_forward(D, x_fake)
@@ -425,9 +433,18 @@ def ugan_consis_step(G, D, g_state, d_state, x_real, y_real, modal_org, mj, alph
     g_loss = g_fake + lambda_rec * g_rec + lambda_cls * g_cls + lambda_seg * g_seg + lambda_semi * g_semi + g_nce
     g_grads = dict(zip(Gl, torch.autograd.grad(g_loss, list(Gl.values()))))
     sgd_update(G, g_grads, g_state, lr)
-    losses = dict(D_real=d_real, D_fake=d_fake, D_cls=d_cls, D_gp=d_gp, G_fake=g_fake, G_rec=g_rec, G_cls=g_cls,
-                  G_seg=g_seg, G_semi=g_semi, G_nce=g_nce)
-    return {k: float(v) for k, v in losses.items()}, d_grads, g_grads
+    losses = dict(G_fake=g_fake, G_rec=g_rec, G_cls=g_cls, G_seg=g_seg, G_semi=g_semi, G_nce=g_nce)
+    return {k: float(v.detach()) for k, v in losses.items()}, g_grads
+
+
+def ugan_consis_step(G, D, g_state, d_state, x_real, y_real, modal_org, mj, alpha, sample_ids, lr, it, lambda_semi,
+                     nce_batch=None, semi_from_iter=1000, lambdas=(1.0, 10.0, 10.0, 10.0)):
+    """One iteration of UGANConsisTrainer.train_epoch (trainer/uganConsisTrainer.py:110-203), n_critic = 1.
+    Returns the 10 losses, the D and G gradients; G, D and the optimiser states are updated in place."""
+    d_losses, d_grads = ugan_d_phase(G, D, d_state, x_real, modal_org, mj, alpha, sample_ids, lr, lambdas)
+    g_losses, g_grads = ugan_g_phase(G, D, g_state, x_real, y_real, modal_org, mj, sample_ids, lr, it, lambda_semi,
+                                     nce_batch, semi_from_iter, lambdas)
+    return {**d_losses, **g_losses}, d_grads, g_grads
 
 
 def ema_alpha(it, base=0.99, warm=100):

@@ -91,6 +91,9 @@ _PROTOS = {
     "smsut_l1_bwd": [P, P, P, c_float, P, c_int64, P],
     "smsut_sum_f32": [P, P, c_int64, c_float, P],
     "smsut_fill_f32": [P, c_int64, c_float, P],
+    "smsut_fill_scaled_f32": [P, c_int64, P, c_float, P],
+    "smsut_tanh_bwd": [P, P, P, c_int64, P],
+    "smsut_lerp_rows_f32": [P, P, P, P, c_int, c_int64, P],
     "smsut_ce_rows_fwd": [P, P, P, c_int, c_int, c_float, P],
     "smsut_ce_rows_bwd": [P, P, P, c_float, P, c_int, c_int, P],
     "smsut_gp_fwd": [P, P, P, c_int, c_int64, c_float, P],

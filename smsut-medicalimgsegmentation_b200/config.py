@@ -1,0 +1,39 @@
+# -*- coding: utf-8 -*-
+"""Module-level constants of the hot path; same names and values as the reference's config.py (the values are
+the contract: config.py:7-11 modalities, :23-33 training constants, :36-37 network, :49 input size, :57 batch,
+:74-78 optimiser and NCE layers).  Dataset roots and augmentation settings are out of scope (synthetic data)."""
+from enum import Enum
+
+
+class Modality(Enum):
+    ct = 0
+    t1in = 1
+    t1out = 2
+    t2 = 3
+
+
+seed = 2020
+n_modal = len(Modality.__members__)
+n_label = 4
+
+num_iter_per_epoch = 150
+max_epoch = 200
+exp_alpha = 1.
+weight_dc = 0.5
+weight_ce = 0.5
+
+img_channels = 1
+base_width = 16
+
+input_size = 256
+mod_type = ('ct, t1in, t1out, t2')
+
+batch_size = 8
+num_workers = 6
+
+lr = 1e-2
+weight_decay = 1e-3
+
+nce_layers = [5]
+
+expr_root = './smsut-out'

@@ -227,6 +227,27 @@ __global__ void fill_kernel(float* __restrict__ x, long long count, float v) {
     x[i] = v;
 }
 
+// dx = dy * (1 - y^2)  (backward of the tanh fused into the translation head, network/ugan.py:73,82)
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                                long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * (1.f - y[i] * y[i]);
+}
+__global__ void fill_scaled_kernel(float* __restrict__ x, long long count, const float* __restrict__ gscale,
+                                   float scale) {
+  const float v = (gscale ? gscale[0] : 1.f) * scale;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    x[i] = v;
+}
+// out = a*x + (1-a)*y with one coefficient per sample (x_hat of the gradient penalty, uganConsisTrainer.py:139)
+__global__ void lerp_rows_kernel(const float* __restrict__ alpha, const float* __restrict__ x,
+                                 const float* __restrict__ y, float* __restrict__ out, long long per, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float a = alpha[i / per];
+    out[i] = a * x[i] + (1.f - a) * y[i];
+  }
+}
+
 // small-row cross entropy (rows <= a few hundred, c <= 8): one block
 __global__ void ce_rows_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                    float* __restrict__ out, int rows, int c, float scale) {
@@ -486,6 +507,23 @@ extern "C" int smsut_fill_f32(float* x, int64_t count, float value, smsut_stream
   fill_kernel<<<grid_for(count), 256, 0, (cudaStream_t)st>>>(x, count, value);
   count_launch();
   return launch_status("fill_kernel");
+}
+extern "C" int smsut_tanh_bwd(const float* dy, const float* y, float* dx, int64_t count, smsut_stream_t st) {
+  tanh_bwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)st>>>(dy, y, dx, count);
+  count_launch();
+  return launch_status("tanh_bwd_kernel");
+}
+extern "C" int smsut_fill_scaled_f32(float* x, int64_t count, const float* gscale, float scale, smsut_stream_t st) {
+  fill_scaled_kernel<<<grid_for(count), 256, 0, (cudaStream_t)st>>>(x, count, gscale, scale);
+  count_launch();
+  return launch_status("fill_scaled_kernel");
+}
+extern "C" int smsut_lerp_rows_f32(const float* alpha, const float* x, const float* y, float* out, int32_t rows,
+                                   int64_t per, smsut_stream_t st) {
+  lerp_rows_kernel<<<grid_for((long long)rows * per), 256, 0, (cudaStream_t)st>>>(alpha, x, y, out, per,
+                                                                                 (long long)rows * per);
+  count_launch();
+  return launch_status("lerp_rows_kernel");
 }
 extern "C" int smsut_ce_rows_fwd(const float* logits, const int64_t* target, float* out, int32_t rows, int32_t c,
                                  float scale, smsut_stream_t st) {

@@ -1,0 +1,507 @@
+"""Autograd wiring of the C-ABI kernels.
+
+Every Function works on NHWC bf16 activations (fp32 at the network heads) and launches only libsmsut_b200
+kernels.  First-order backwards use the fused kernels.  When autograd runs a backward with create_graph=True
+(the WGAN-GP term, trainer/uganShp0Trainer.py:127-134) the same Functions emit a *differentiable* backward made
+of the `*BwdFn` Functions below, whose own backwards are the hand-derived second-order kernels
+(smsut_in_bwd2_*, conv fprop/wgrad of the cotangent, avg-pool forward of the cotangent ...).
+"""
+import threading
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, BF16, F32
+
+SLOPE = 0.01
+
+
+class _Mode(threading.local):
+    inputs_only = False  # create_graph backward: skip parameter gradients (only d/d(input) is requested)
+
+
+mode = _Mode()
+_inputs_only_global = [False]  # the autograd engine runs backward on its own thread: use a process-wide flag
+
+
+class inputs_only:
+    """Context for torch.autograd.grad(..., inputs=x, create_graph=True): parameter gradients of the first-order
+    pass are not requested (gradient_penalty), so the differentiable backward skips them."""
+
+    def __enter__(self):
+        self.prev = _inputs_only_global[0]
+        _inputs_only_global[0] = True
+
+    def __exit__(self, *a):
+        _inputs_only_global[0] = self.prev
+
+
+def _c(t):
+    """contiguous view of a gradient (autograd may hand over expanded / permuted tensors)"""
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def to_nhwc(x):
+    """logical NCHW tensor -> NHWC bf16 contiguous.  Zero-copy for the channels-last bf16 views our modules
+    return; fp32 NCHW inputs go through the layout kernel."""
+    if x.dim() != 4:
+        raise ValueError("expected a 4-D NCHW tensor")
+    if x.dtype == BF16:
+        v = x.permute(0, 2, 3, 1)
+        if v.is_contiguous():
+            return v
+        return v.contiguous()
+    if x.dtype == F32:
+        n, c, h, w = x.shape
+        if x.requires_grad:
+            return x.permute(0, 2, 3, 1).to(BF16).contiguous()
+        return ops.nchw_to_nhwc(x.contiguous(), ops.pad16(c) if c > 1 else 8)
+    raise TypeError(f"unsupported activation dtype {x.dtype}")
+
+
+def to_nchw(y):
+    """NHWC tensor -> logical NCHW view (channels-last strides, no copy)"""
+    return y.permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# tensor-core convolutions
+# ----------------------------------------------------------------------------------------------
+class ConvDgradFn(Function):
+    """dx = dgrad(dy; W) as a differentiable op (single source)."""
+
+    @staticmethod
+    def forward(ctx, pw, weight, dy):
+        ctx.pw = pw
+        ctx.save_for_backward(dy)
+        return ops.conv_dgrad(dy, pw)[0]
+
+    @staticmethod
+    def backward(ctx, u):
+        (dy,) = ctx.saved_tensors
+        u = _c(u)
+        g_dy = ops.conv_fprop([u], ctx.pw) if ctx.needs_input_grad[2] else None
+        g_w = ops.conv_wgrad([u], dy, ctx.pw) if ctx.needs_input_grad[1] else None
+        return None, g_w, g_dy
+
+
+class ConvFn(Function):
+    """y = conv(cat(xs), W): 1x1 / 3x3, stride 1, 'same'.  A second (pw2, weight2) pair computes a second conv of
+    the same input in the same node (BasicBlock's conv1 + shortcut1) so the input gets ONE gradient."""
+
+    @staticmethod
+    def forward(ctx, pw, weight, pw2, weight2, *xs):
+        ctx.pw, ctx.pw2 = pw, pw2
+        ctx.save_for_backward(weight, weight2, *xs)
+        y = ops.conv_fprop(list(xs), pw)
+        if pw2 is None:
+            return y
+        return y, ops.conv_fprop(list(xs), pw2)
+
+    @staticmethod
+    def backward(ctx, dy, dy2=None):
+        weight, weight2, *xs = ctx.saved_tensors
+        pw, pw2 = ctx.pw, ctx.pw2
+        dy = _c(dy)
+        need_x = any(ctx.needs_input_grad[4:])
+        splits = [x.shape[3] for x in xs]
+        if torch.is_grad_enabled():
+            assert pw2 is None and len(xs) == 1, "double backward is implemented for single-source convs"
+            dx = ConvDgradFn.apply(pw, weight, dy) if need_x else None
+            dw = None
+            if ctx.needs_input_grad[1] and not _inputs_only_global[0]:
+                dw = ops.conv_wgrad(xs, dy.detach(), pw)
+            return None, dw, None, None, dx
+        dxs = [None] * len(xs)
+        if need_x:
+            dxs = ops.conv_dgrad(dy, pw, splits)
+        dw = ops.conv_wgrad(xs, dy, pw) if ctx.needs_input_grad[1] else None
+        dw2 = None
+        if pw2 is not None:
+            dy2 = _c(dy2)
+            if need_x:
+                ops.conv_dgrad_accumulate(dy2, pw2, dxs)
+            dw2 = ops.conv_wgrad(xs, dy2, pw2) if ctx.needs_input_grad[3] else None
+        return (None, dw, None, dw2, *dxs)
+
+
+class ConvTFn(Function):
+    """nn.ConvTranspose2d(k=2, s=2, bias=False) (network/blocks.py:41)"""
+
+    @staticmethod
+    def forward(ctx, pw, weight, x):
+        ctx.pw = pw
+        ctx.save_for_backward(weight, x)
+        return ops.convt_fprop(x, pw)
+
+    @staticmethod
+    def backward(ctx, dy):
+        _, x = ctx.saved_tensors
+        dy = _c(dy)
+        dx = ops.convt_dgrad(dy, ctx.pw) if ctx.needs_input_grad[2] else None
+        dw = ops.convt_wgrad(x, dy, ctx.pw) if ctx.needs_input_grad[1] else None
+        return None, dw, dx
+
+
+# ----------------------------------------------------------------------------------------------
+# direct convolutions (stems and heads)
+# ----------------------------------------------------------------------------------------------
+class DirectDgradFn(Function):
+    @staticmethod
+    def forward(ctx, weight, g, x_shape, x_dtype, stride, pad):
+        ctx.meta = (stride, pad, g.shape[3], g.dtype)
+        ctx.save_for_backward(weight, g)
+        return ops.conv_direct_dgrad(g, weight, x_shape, x_dtype, stride, pad)
+
+    @staticmethod
+    def backward(ctx, u):
+        weight, g = ctx.saved_tensors
+        stride, pad, gc, gdt = ctx.meta
+        u = _c(u)
+        g_g = None
+        if ctx.needs_input_grad[1]:
+            g_g = ops.conv_direct_fprop(u, weight, stride, pad, out_c=gc, out_f32=(gdt == F32))
+        g_w = None
+        if ctx.needs_input_grad[0]:
+            g_w, _ = ops.conv_direct_wgrad(u, g, weight, stride, pad, want_bias=False)
+        return g_w, g_g, None, None, None, None
+
+
+class DirectConvFn(Function):
+    """Stem / head convolutions on CUDA cores (tiny K, HBM-bound): x NHWC (bf16 or fp32), fp32 OIHW weights,
+    optional bias and fused LeakyReLU / tanh."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act, out_c, out_f32):
+        y = ops.conv_direct_fprop(x, weight, stride, pad, bias=bias, act=act, slope=SLOPE, out_c=out_c, out_f32=out_f32)
+        ctx.meta = (stride, pad, act)
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        stride, pad, act = ctx.meta
+        dy = _c(dy)
+        diff = torch.is_grad_enabled()
+        if act == ACT_TANH:
+            assert not diff, "double backward through the tanh head is not on the path"
+            g = ops.tanh_bwd(dy, y)
+        elif act != ACT_NONE:
+            g = LReluBwdFn.apply(dy, y, act) if diff else ops.act_bwd(dy, y, act=act, slope=SLOPE)
+        else:
+            g = dy
+        dx = dw = db = None
+        if diff:
+            if ctx.needs_input_grad[0]:
+                dx = DirectDgradFn.apply(weight, g, tuple(x.shape), x.dtype, stride, pad)
+            if not _inputs_only_global[0] and ctx.needs_input_grad[1]:
+                dw, db = ops.conv_direct_wgrad(x, g.detach(), weight, stride, pad, want_bias=ctx.has_bias)
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = ops.conv_direct_dgrad(g, weight, tuple(x.shape), x.dtype, stride, pad)
+            if ctx.needs_input_grad[1]:
+                dw, db = ops.conv_direct_wgrad(x, g, weight, stride, pad, want_bias=ctx.has_bias)
+        return dx, dw, db, None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# InstanceNorm + activation + residual
+# ----------------------------------------------------------------------------------------------
+class LReluBwdFn(Function):
+    """g = dy * act'(ref)  (ref = the activation's output; piecewise linear => second derivative is zero)"""
+
+    @staticmethod
+    def forward(ctx, dy, ref, act):
+        ctx.act = act
+        ctx.save_for_backward(ref)
+        return ops.act_bwd(dy, ref, act=act, slope=SLOPE)
+
+    @staticmethod
+    def backward(ctx, u):
+        (ref,) = ctx.saved_tensors
+        return ops.act_bwd(_c(u), ref, act=ctx.act, slope=SLOPE), None, None
+
+
+class INBwdFn(Function):
+    """dx = gamma*rstd*(g - mean g - xhat*mean(g*xhat)) as a differentiable op (stats are functions of x)."""
+
+    @staticmethod
+    def forward(ctx, g, x, stats, gamma):
+        ctx.save_for_backward(g, x, stats, gamma)
+        return ops.in_bwd(g, None, x, stats, gamma, act=ACT_NONE)[0]
+
+    @staticmethod
+    def backward(ctx, u):
+        g, x, stats, gamma = ctx.saved_tensors
+        g_g, g_x, g_gamma = ops.in_bwd2(_c(u), g, x, stats, gamma)
+        return g_g, g_x, None, g_gamma
+
+
+class INActFn(Function):
+    """out = act( IN(xa; ga, ba) [+ IN(xb; gb, bb)] [+ res] )  (network/blocks.py:66-80, 99-117)"""
+
+    @staticmethod
+    def forward(ctx, xa, ga, ba, xb, gb, bb, res, act, c_params):
+        sa = ops.in_stats(xa)
+        sb = ops.in_stats(xb) if xb is not None else None
+        out = ops.in_apply(xa, sa, ga, ba, xb, sb, gb, bb, res=res, act=act, slope=SLOPE, c_params=c_params)
+        ctx.act, ctx.cp, ctx.has_res = act, c_params, res is not None
+        ctx.save_for_backward(xa, sa, ga, xb, sb, gb, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xa, sa, ga, xb, sb, gb, out = ctx.saved_tensors
+        dout = _c(dout)
+        act, cp = ctx.act, ctx.cp
+        want_res = ctx.has_res and ctx.needs_input_grad[6]
+        if torch.is_grad_enabled():
+            assert cp is None or cp == xa.shape[3]
+            g = LReluBwdFn.apply(dout, out, act) if act != ACT_NONE else dout
+            dxa = INBwdFn.apply(g, xa, sa, ga)
+            dxb = INBwdFn.apply(g, xb, sb, gb) if xb is not None else None
+            dga = dba = dgb = dbb = None
+            if not _inputs_only_global[0]:
+                _, dga, dba, _, dgb, dbb, _ = ops.in_bwd(dout.detach(), out, xa, sa, ga, xb, sb, gb, False, act, SLOPE, cp)
+            return dxa, dga, dba, dxb, dgb, dbb, (g if want_res else None), None, None
+        dxa, dga, dba, dxb, dgb, dbb, dres = ops.in_bwd(dout, out, xa, sa, ga, xb, sb, gb, want_res, act, SLOPE, cp)
+        return dxa, dga, dba, dxb, dgb, dbb, dres, None, None
+
+
+def in_act(xa, norm_a, xb=None, norm_b=None, res=None, act=ACT_LRELU, c_params=None):
+    return INActFn.apply(xa, norm_a.weight, norm_a.bias, xb, norm_b.weight if norm_b is not None else None,
+                         norm_b.bias if norm_b is not None else None, res, act, c_params)
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling / resampling
+# ----------------------------------------------------------------------------------------------
+class MaxPoolSkipFn(Function):
+    """nn.MaxPool2d(2, 2) that also hands back its input as the skip tensor, so the pooled path and the skip
+    path deliver their gradients to ONE backward (fused route + add)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool2_fwd(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(x, _c(dy), add=_c(dskip) if dskip is not None else None)
+
+
+class MaxPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(x, _c(dy))
+
+
+class AvgPoolBwdFn(Function):
+    @staticmethod
+    def forward(ctx, dy):
+        return ops.avgpool2_bwd(dy)
+
+    @staticmethod
+    def backward(ctx, u):
+        return ops.avgpool2_fwd(_c(u))
+
+
+class AvgPoolFn(Function):
+    """F.avg_pool2d(x, 2) (network/blocks.py:101-112)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.avgpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        if torch.is_grad_enabled():
+            return AvgPoolBwdFn.apply(dy)
+        return ops.avgpool2_bwd(dy)
+
+
+class BilinearFn(Function):
+    """nn.Upsample(x2, bilinear, align_corners=False) (network/blocks.py:44)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.bilinear2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.bilinear2_bwd(_c(dy))
+
+
+# ----------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------
+_dice_allreduce = [None]  # callable(acc[:3c]) summing the Dice statistics over data-parallel ranks, or None
+_world = [1]
+
+
+def set_data_parallel(allreduce_fn, world_size):
+    """Data-parallel hook: batch-Dice is a non-linear function of batch-wide sums, so tp/fp/fn are summed over
+    ranks inside the loss (the reference's DataParallel computes the loss on the gathered batch)."""
+    _dice_allreduce[0] = allreduce_fn
+    _world[0] = world_size
+
+
+class DiceCEFn(Function):
+    """DiceAndCrossEntropyLoss (misc/loss.py:8-63, batch dice) on fp32 NHWC logits (npix, C); targets are int64
+    labels or the argmax of `label_logits` (consistency_loss, trainer/uganConsisTrainer.py:45-53)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, label_logits, w_ce, w_dc):
+        npix, c = logits.shape
+        acc = torch.zeros(3 * c + 1, dtype=F32, device=logits.device)
+        ops.dice_ce_fwd(logits, labels, label_logits, acc)
+        if _dice_allreduce[0] is not None:
+            _dice_allreduce[0](acc[:3 * c])
+        loss = ops.dice_ce_finish(acc, npix, c, w_dc, w_ce)
+        ctx.save_for_backward(logits, labels, label_logits, acc)
+        ctx.w = (w_ce, w_dc)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, label_logits, acc = ctx.saved_tensors
+        w_ce, w_dc = ctx.w
+        d = ops.dice_ce_bwd(logits, labels, label_logits, acc, _c(g).view(1), 1.0, logits.shape[0], w_dc * _world[0], w_ce)
+        return d, None, None, None, None
+
+
+class L1MeanFn(Function):
+    """mean |a - b| with gradient to a (g_loss_rec, trainer/uganConsisTrainer.py:162)"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        out = torch.zeros(1, dtype=F32, device=a.device)
+        ops.l1_fwd(a, b, out, 1.0 / a.numel())
+        ctx.save_for_backward(a, b)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return ops.l1_bwd(a, b, _c(g).view(1), 1.0 / a.numel()), None
+
+
+class MeanFn(Function):
+    """scale * mean(x) (adversarial terms, trainer/uganConsisTrainer.py:130,136,154)"""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        out = torch.zeros(1, dtype=F32, device=x.device)
+        ops.sum_f32(x, out, scale / x.numel())
+        ctx.meta = (tuple(x.shape), scale / x.numel())
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        shape, s = ctx.meta
+        return ops.fill_scaled(shape, _c(g).view(1), s, g.device), None
+
+
+class CERowsFn(Function):
+    """F.cross_entropy on (rows, C<=8) logits (modality classification, uganConsisTrainer.py:131,155)"""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        out = torch.zeros(1, dtype=F32, device=logits.device)
+        ops.ce_rows_fwd(logits, target, out, 1.0)
+        ctx.save_for_backward(logits, target)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target = ctx.saved_tensors
+        return ops.ce_rows_bwd(logits, target, _c(g).view(1), 1.0), None
+
+
+class GradPenaltyFn(Function):
+    """mean_b (||g_b||_2 - 1)^2 (trainer/uganShp0Trainer.py:131-134); g is the (differentiable) dD/dx_hat."""
+
+    @staticmethod
+    def forward(ctx, g):
+        out = torch.zeros(1, dtype=F32, device=g.device)
+        norm = ops.gp_fwd(g, out, 1.0)
+        ctx.save_for_backward(g, norm)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, gs):
+        g, norm = ctx.saved_tensors
+        return ops.gp_bwd(g, norm, _c(gs).view(1), 1.0)
+
+
+class PatchSampleFn(Function):
+    """PatchSampleF.forward for one feature map (network/ugan.py:316-334): gather `ids` rows of the NHWC
+    bottleneck, Linear-ReLU-Linear on the tensor cores, L2 normalise (network/networks.py:241-242)."""
+
+    @staticmethod
+    def forward(ctx, feat, ids, pw1, w1, b1, pw2, w2, b2):
+        rows = ops.gather_rows(feat, ids)                      # (R, C) bf16
+        r, c = rows.shape
+        tw = 128
+        while r % tw:
+            tw //= 2
+        x4 = rows.view(1, r // tw, tw, c)                      # GEMM rows laid out as (1, r/tw, tw) "pixels"
+        h = ops.conv_fprop([x4], pw1, bias=b1, act=ACT_RELU)   # bf16
+        y = ops.conv_fprop([h], pw2, bias=b2, out_f32=True)    # fp32
+        q, norm = ops.l2norm_fwd(y.view(r, -1))
+        ctx.pw = (pw1, pw2)
+        ctx.fshape = tuple(feat.shape)
+        ctx.save_for_backward(ids, x4, h, q, norm, w1, w2)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        ids, x4, h, q, norm, w1, w2 = ctx.saved_tensors
+        pw1, pw2 = ctx.pw
+        r = q.shape[0]
+        dy = ops.l2norm_bwd(_c(dq), q, norm).view(1, x4.shape[1], x4.shape[2], -1)      # bf16
+        dw2 = ops.conv_wgrad([h], dy, pw2)
+        db2 = ops.colsum(dy.view(r, -1))
+        dh = ops.conv_dgrad(dy, pw2)[0]
+        dh = ops.act_bwd(dh, h, act=ACT_RELU)
+        dw1 = ops.conv_wgrad([x4], dh, pw1)
+        db1 = ops.colsum(dh.view(r, -1))
+        dfeat = None
+        if ctx.needs_input_grad[0]:
+            drows = ops.conv_dgrad(dh, pw1)[0].view(r, -1)
+            dfeat = torch.zeros(ctx.fshape, dtype=BF16, device=dq.device)
+            ops.scatter_rows_add(drows, ids, dfeat)
+        return dfeat, None, None, dw1.view_as(w1), db1, None, dw2.view_as(w2), db2
+
+
+class PatchNCEFn(Function):
+    """PatchNCELoss.forward (network/patchnce.py:13-51): per-row loss; feat_k is detached."""
+
+    @staticmethod
+    def forward(ctx, q, k, groups):
+        rows = q.shape[0]
+        out = torch.zeros(1, dtype=F32, device=q.device)
+        loss_rows = ops.patchnce_fwd(q, k, groups, rows // groups, 1.0 / 0.07, out, 1.0)
+        ctx.groups = groups
+        ctx.save_for_backward(q, k)
+        return loss_rows
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        q, k = ctx.saved_tensors
+        rows = q.shape[0]
+        ones = torch.ones(1, dtype=F32, device=q.device)
+        # d(loss_rows[r])/dq[r] * g_rows[r]: the kernel bakes 1/rows in, undo it and apply the per-row cotangent
+        dq = ops.patchnce_bwd(q, k, ctx.groups, rows // ctx.groups, 1.0 / 0.07, ones, float(rows))
+        return dq * _c(g_rows).view(rows, 1), None, None

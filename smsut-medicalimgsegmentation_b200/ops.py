@@ -39,6 +39,11 @@ def pad16(c):
     return (c + 15) // 16 * 16
 
 
+# bumped by the fused optimisers (they write parameters through raw pointers, which does not advance
+# torch's per-tensor version counters); PackTable repacks when it or any tensor version changes
+param_generation = [0]
+
+
 # ----------------------------------------------------------------------------------------------
 # weight packing
 # ----------------------------------------------------------------------------------------------
@@ -60,7 +65,12 @@ class PackedWeight:
         dev = weight.device
         self.fprop = torch.empty(n, dtype=BF16, device=dev)
         self.dgrad = torch.empty(n, dtype=BF16, device=dev) if need_dgrad else None
-        self.version = -1
+        self.version = None
+        self.ptr = 0
+
+    def stale(self):
+        w = self.weight
+        return self.version != (w._version, param_generation[0]) or self.ptr != w.data_ptr()
 
     def entry(self):
         e = PackEntry()
@@ -95,11 +105,13 @@ class PackTable:
         if self._table is None or ptrs != self._ptrs:
             self._build()
             force = True
-        if not force and all(p.version == p.weight._version for p in self.packs):
+        if not force and not any(p.stale() for p in self.packs):
             return
         call("smsut_pack_weights", _p(self._table), len(self.packs), _stream())
+        gen = param_generation[0]
         for p in self.packs:
-            p.version = p.weight._version
+            p.version = (p.weight._version, gen)
+            p.ptr = p.weight.data_ptr()
 
 
 # ----------------------------------------------------------------------------------------------
@@ -149,6 +161,18 @@ def conv_dgrad(dy, pw, splits=None):
     dx1 = torch.empty((n, h, w, c1), dtype=BF16, device=dy.device)
     conv_tc(TC_CONV, pw.kh, n, h, w, [(dy, c, c)], pw.dgrad, pw.cin_pad, pw.cin_pad, dx0, c0, 0, dx1, c1, 0, c0)
     return [dx0, dx1]
+
+
+def conv_dgrad_accumulate(dy, pw, dxs):
+    """dxs[i] += the slice of dgrad(dy; W) that belongs to source i (fused read-modify-write epilogue)."""
+    n, h, w, c = dy.shape
+    if len(dxs) == 1:
+        conv_tc(TC_CONV, pw.kh, n, h, w, [(dy, c, c)], pw.dgrad, pw.cin_pad, pw.cin_pad, dxs[0], pw.cin_pad,
+                accumulate=True)
+    else:
+        c0, c1 = dxs[0].shape[3], dxs[1].shape[3]
+        conv_tc(TC_CONV, pw.kh, n, h, w, [(dy, c, c)], pw.dgrad, pw.cin_pad, pw.cin_pad, dxs[0], c0, 0, dxs[1], c1, 0,
+                c0, accumulate=True)
 
 
 def wgrad_tc(kind, ksize, n, h, w, x, x_c, dy, dy_c, dw, cin_total, ci_off, cout_total, c_valid=0):
@@ -434,6 +458,26 @@ def fill_f32(x, value):
     call("smsut_fill_f32", _p(x), x.numel(), value, _stream())
 
 
+def fill_scaled(shape, gscale, scale, device):
+    x = torch.empty(shape, dtype=F32, device=device)
+    call("smsut_fill_scaled_f32", _p(x), x.numel(), _p(gscale), scale, _stream())
+    return x
+
+
+def tanh_bwd(dy, y):
+    dx = torch.empty_like(y)
+    call("smsut_tanh_bwd", _p(_chk(dy, F32, "tanh dy")), _p(_chk(y, F32, "tanh y")), _p(dx), y.numel(), _stream())
+    return dx
+
+
+def lerp_rows(alpha, x, y):
+    out = torch.empty_like(x)
+    rows = x.shape[0]
+    call("smsut_lerp_rows_f32", _p(_chk(alpha, F32, "lerp alpha")), _p(_chk(x, F32, "lerp x")), _p(_chk(y, F32, "lerp y")),
+         _p(out), rows, x.numel() // rows, _stream())
+    return out
+
+
 def ce_rows_fwd(logits, target, out, scale):
     rows, c = logits.shape
     call("smsut_ce_rows_fwd", _p(_chk(logits, F32, "ce logits")), _p(target), _p(out), rows, c, scale, _stream())
@@ -507,15 +551,18 @@ def patchnce_bwd(q, k, groups, np_, inv_t, gscale, scale):
 # optimisers over flat fp32 buffers
 # ----------------------------------------------------------------------------------------------
 def sgd_step(p, g, mom, lr, momentum, weight_decay, grad_scale=1.0):
+    param_generation[0] += 1
     call("smsut_sgd_step", _p(p), _p(g), _p(mom), p.numel(), _p(lr), momentum, weight_decay, grad_scale, _stream())
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=1.0):
+    param_generation[0] += 1
     call("smsut_adam_step", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(lr), beta1, beta2, eps, weight_decay, _p(state),
          grad_scale, _stream())
 
 
 def ema_update(ema, p, alpha):
+    param_generation[0] += 1
     call("smsut_ema_update", _p(ema), _p(p), p.numel(), _p(alpha), _stream())
 
 

@@ -1,0 +1,99 @@
+"""Fused optimisers with the torch.optim surface the trainers use (param_groups[...]['lr'], step(), zero_grad()).
+
+Parameters and gradients of a network are re-homed into two flat fp32 buffers, so one kernel updates the whole
+network (the reference loops over 175 / 46 tensors: ~1300 aten calls per step) and one NCCL all-reduce covers
+every gradient.  The learning rate lives in a device scalar so a captured CUDA graph follows the poly schedule.
+Reference semantics: torch.optim.SGD(momentum=0.9, weight_decay) / torch.optim.Adam(betas, weight_decay) as
+constructed at trainer/uganShp0Trainer.py:72-74 and trainer/unetTrainer.py:47.
+"""
+import torch
+
+from . import ops
+
+
+class _FlatOptimizer:
+    def __init__(self, params, lr):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("optimizer got an empty parameter list")
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
+        total = sum(sizes)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p, sz in zip(self.params, sizes):
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)
+                p.grad = self.grad[off:off + n].view(p.shape)
+                off += sz
+        self.param_groups = [dict(params=self.params, lr=lr)]
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = float(lr)
+        self.grad_scale = 1.0      # 1/world_size after a summing all-reduce of `grad`
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+        for p in self.params:    # autograd may have swapped a .grad tensor in: re-attach the flat views
+            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr() or \
+                    p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
+                self._reattach()
+                break
+
+    def _reattach(self):
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.grad[off:off + n].view(p.shape)
+            off += (n + 3) // 4 * 4
+
+    def _sync_lr(self):
+        lr = float(self.param_groups[0]['lr'])
+        if lr != self._lr_host:
+            self.lr_dev.fill_(lr)
+            self._lr_host = lr
+
+
+class SGD(_FlatOptimizer):
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
+        super().__init__(params, lr)
+        self.momentum, self.weight_decay = momentum, weight_decay
+        self.mom = torch.zeros_like(self.flat)
+
+    def step(self):
+        self._sync_lr()
+        ops.sgd_step(self.flat, self.grad, self.mom, self.lr_dev, self.momentum, self.weight_decay, self.grad_scale)
+
+
+class Adam(_FlatOptimizer):
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        super().__init__(params, lr)
+        self.betas, self.eps, self.weight_decay = tuple(betas), eps, weight_decay
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.state = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
+
+    def step(self):
+        self._sync_lr()
+        ops.adam_step(self.flat, self.grad, self.m, self.v, self.lr_dev, self.betas[0], self.betas[1], self.eps,
+                      self.weight_decay, self.state, self.grad_scale)
+
+
+class PolyLR:
+    """lr_k = base * (1 - (k-1)/max_iter)^0.9 for step k >= 1 (step 0 runs at base): the reference sets the LR
+    after step k from iter = k (trainer/uganConsisTrainer.py:198-203).  tick() runs on the device."""
+
+    def __init__(self, optimizers, base_lr, max_iter, power=0.9):
+        self.opts, self.base, self.max_iter, self.power = list(optimizers), base_lr, max_iter, power
+        dev = self.opts[0].flat.device
+        self.iter_state = torch.zeros(1, dtype=torch.float32, device=dev)
+        for o in self.opts[1:]:
+            o.lr_dev = self.opts[0].lr_dev    # one shared device scalar
+
+    def tick(self):
+        ops.poly_lr_tick(self.iter_state, self.opts[0].lr_dev, self.base, float(self.max_iter), self.power)
+
+    def host_lr(self, it):
+        return self.base * (1.0 - max(it - 1, 0) / self.max_iter) ** self.power

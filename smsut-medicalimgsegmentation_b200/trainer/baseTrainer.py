@@ -1,0 +1,113 @@
+# -*- coding: utf-8 -*-
+"""Counterpart of the reference's trainer/baseTrainer.py restricted to what the hot path needs: construction
+(device, network, Dice+CE loss: baseTrainer.py:35-62), sigmoid_rampup (:64-72), save_model (:120-123), the epoch
+loop `fit` (:125-201) over synthetic loaders, and a device-side validate_epoch (:207-244).  Experiment folders,
+TensorBoard, medpy metrics and PNG datasets are out of scope."""
+import abc
+import os
+import time
+from os.path import join as pjoin
+
+import numpy as np
+import torch
+
+from .. import config as cfg
+from ..data_loader import syntheticLoader as synlod
+from ..misc.loss import DiceAndCrossEntropyLoss
+
+
+class BaseTrainer(object):
+    def __init__(self, phase, args=None):
+        self.args = args
+        if not torch.cuda.is_available() and os.environ.get("SMSUT_ALLOW_CPU_TEST_DOUBLE") != "1":
+            raise RuntimeError("the SMSUT B200 trainers need a CUDA device: there is no CPU fallback")
+        self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
+        self.phase = phase
+        self.fold = 0 if args is None else getattr(args, 'fold', 0)
+        if args is None or getattr(args, 'expr_name', None) is None or len(args.expr_name) == 0:
+            expr_name = self.__class__.__name__
+        else:
+            expr_name = args.expr_name
+        self.expr_root, self.model_idx = pjoin(cfg.expr_root, expr_name), '000'
+        self.modality = 'all'
+        self.input_size = getattr(args, 'input_size', None) or cfg.input_size
+        self.net = None
+        self.build_network()
+        self.loss = DiceAndCrossEntropyLoss(weight_ce=cfg.weight_ce, weight_dc=cfg.weight_dc, batch_dice=True)
+        self.epoch = 0
+        self.iter = 0
+
+    @staticmethod
+    def sigmoid_rampup(current, rampup_length):
+        """Exponential rampup from https://arxiv.org/abs/1610.02242"""
+        if rampup_length == 0:
+            return 1.0
+        else:
+            current = np.clip(current, 0.0, rampup_length)
+            phase = 1.0 - current / rampup_length
+            return float(np.exp(-5.0 * phase * phase))
+
+    def info(self, msg):
+        print(msg, flush=True)
+
+    @abc.abstractmethod
+    def build_network(self):
+        pass
+
+    def save_model(self, prefix):
+        path = pjoin(self.expr_root, self.model_idx, 'ckpt', f'{prefix}.ckpt')
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        torch.save({k: v.detach().cpu() for k, v in self.net.state_dict().items()}, path)
+        self.info(f'Save model to {path}.')
+
+    def load_model(self, model_idx, which_ckpt):
+        path = pjoin(self.expr_root, model_idx, 'ckpt', f'{which_ckpt}.ckpt')
+        self.net.load_state_dict(torch.load(path, map_location='cpu'))
+
+    def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None):
+        train_lb_loader = synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size)
+        train_ul_loader = synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size)
+        test_loader = synlod.get_loader(None, 'test', 0, cfg.batch_size, size=self.input_size, pool_batches=4)
+        best, best_epoch = -1.0, -1
+        for epoch in range(max_epoch or cfg.max_epoch):
+            tic = time.time()
+            self.train_epoch(train_lb_loader, train_ul_loader, None, num_iter=iters_per_epoch)
+            self.epoch += 1
+            dice = self.validate_epoch(test_loader)
+            self.info('[TRN/TST] Epoch: %d(%d)/%d, elapsed: %.2fs, dice: %.4f' %
+                      (epoch, best_epoch, cfg.max_epoch, time.time() - tic, dice))
+            if dice >= best:
+                best, best_epoch = dice, epoch
+                self.save_model(prefix='best')
+        self.save_model(prefix='last')
+
+    @abc.abstractmethod
+    def train_epoch(self, lb_loader, ul_loader, meter, num_iter=None):
+        pass
+
+    def segment(self, img):
+        return self.net(img)
+
+    def validate_epoch(self, loader, npys=None, meter=None, save_path=None):
+        """Mean foreground Dice of argmax predictions over the loader (pads a ragged last batch to cfg.batch_size
+        like baseTrainer.py:214-219); the confusion counts stay on the device."""
+        self.net.eval()
+        n_cls = cfg.n_label + 1
+        inter = torch.zeros(n_cls, device=self.device)
+        denom = torch.zeros(n_cls, device=self.device)
+        with torch.no_grad():
+            for img, msk, mdl, inm in loader:
+                b, c, h, w = img.shape
+                if b != cfg.batch_size:
+                    img = torch.cat([img, torch.zeros((cfg.batch_size - b, c, h, w), dtype=img.dtype)], dim=0)
+                img = img.to(self.device, non_blocking=True)
+                msk = msk.to(self.device, non_blocking=True)
+                out = self.segment(img)[:b]
+                pred = torch.argmax(out, dim=1)
+                for k in range(1, n_cls):
+                    p, g = pred == k, msk == k
+                    inter[k] += (p & g).sum()
+                    denom[k] += p.sum() + g.sum()
+        dice = (2 * inter[1:] / denom[1:].clamp_min(1)).mean().item()
+        self.net.train()
+        return dice

@@ -1,0 +1,218 @@
+# -*- coding: utf-8 -*-
+"""Counterpart of the reference's trainer/uganConsisTrainer.py: the UGANConsisTrainer iteration
+(uganConsisTrainer.py:66-214) -- D step (WGAN-GP + modality classification) and G step (adversarial,
+classification, Dice/CE segmentation, L1 cycle, pseudo-label consistency, PatchNCE) -- on libsmsut_b200 kernels.
+
+Differences that do not change the arithmetic:
+  * the D-phase generator forward (L133) and the G-phase one (L151) see the same weights and inputs, so ONE
+    forward serves both (its detached translation feeds D);
+  * the weight gradients of D produced by g_loss.backward() are zeroed unread by the reference (L144): they are
+    not computed;
+  * the ten losses stay on the device (one D2H copy when logging) instead of eleven .item() syncs per step;
+  * the poly LR schedule ticks on the device.
+"""
+import argparse
+import os
+import random
+import sys
+import time
+
+if __package__ in (None, ""):      # `python trainer/uganConsisTrainer.py -p train -f 0` from the package directory
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    import __graft_entry__ as _g
+    _g.load_package()
+    __package__ = "smsut_b200.trainer"
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import config as cfg
+from .. import functional as Fn
+from .. import ops
+from .uganShp0Trainer import UGANShp0Trainer
+
+LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
+
+
+class UGANConsisTrainer(UGANShp0Trainer):
+    def __init__(self, phase, args):
+        super(UGANConsisTrainer, self).__init__(phase, args)
+        self.lambda_semi = 10
+        self.semi_from_iter = 1000
+        self.parallel = None           # parallel.DataParallelContext when launched under torchrun
+
+    def consistency_loss(self, source, target):
+        # Dice+CE of `source` against argmax(target): the argmax is taken inside the fused loss kernel
+        return self.loss(source, target)
+
+    def nce_loss(self, feat_x_pool, feat_f_pool):
+        n_layers = cfg.nce_layers
+        n = len(n_layers)
+        total_nce_loss = 0.0
+        for f_f, f_x, crit, nce_layer in zip(feat_f_pool, feat_x_pool, self.criterionNCE, n_layers):
+            loss = crit(f_f, f_x) * 1.0
+            total_nce_loss += loss.mean()
+        return total_nce_loss / n
+
+    # ------------------------------------------------------------------------------------------
+    def train_step(self, x_real, y_real, modal_org, modal_trg, vec_ot, vec_to, alpha, sample_ids, lambda_semi,
+                   use_semi):
+        """The body of the hot loop (uganConsisTrainer.py:129-203) on device tensors.  `alpha` (B,) ~ N(0,1) and
+        `sample_ids` ([ids (64,) int64]) are the iteration's random draws (L138, network/ugan.py:321).
+        Returns the ten losses as one device vector ordered like LOSS_KEYS."""
+        lambda_cls, lambda_gp = self.lambda_cls, self.lambda_gp
+        lambda_seg, lambda_rec = self.lambda_seg, self.lambda_rec
+        bs = y_real.shape[0]
+        self.lr_sched.tick()
+
+        # generator forward shared by the D phase (detached) and the G phase
+        y_fake, x_fake, feat_x_pool, sample_ids = self.net(x_real, vec_ot, sample_ids=sample_ids)
+
+        # ---------------- D phase (L129-146)
+        out_src, out_cls = self.D(x_real)
+        d_loss_real = Fn.MeanFn.apply(out_src, -1.0)
+        d_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_org)
+
+        x_fake_d = x_fake.detach()
+        out_src, out_cls = self.D(x_fake_d)
+        d_loss_fake = Fn.MeanFn.apply(out_src, 1.0)
+
+        x_hat = ops.lerp_rows(alpha, x_real, x_fake_d.contiguous()).requires_grad_(True)
+        out_src, _ = self.D(x_hat)
+        d_loss_gp = self.gradient_penalty(out_src, x_hat)
+
+        d_loss = d_loss_real + d_loss_fake + lambda_cls * d_loss_cls + lambda_gp * d_loss_gp
+        self.d_optimizer.zero_grad()
+        d_loss.backward()
+        if self.parallel is not None:
+            self.parallel.all_reduce_grads(self.d_optimizer)
+        self.d_optimizer.step()
+
+        # ---------------- G phase (L151-180); D's parameters are constants here
+        for p in self.d_optimizer.params:
+            p.requires_grad_(False)
+        out_src, out_cls = self.D(x_fake)
+        for p in self.d_optimizer.params:
+            p.requires_grad_(True)
+        g_loss_fake = Fn.MeanFn.apply(out_src, -1.0)
+        g_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_trg)
+        g_loss_seg = self.loss(y_fake[:bs], y_real)
+
+        y_rec, x_rec, feat_f_pool, _ = self.net(x_fake, vec_to, sample_ids=sample_ids)
+        g_loss_rec = Fn.L1MeanFn.apply(x_rec.contiguous(), x_real)
+
+        if use_semi:
+            g_loss_semi = self.consistency_loss(y_rec, y_fake)
+        else:
+            g_loss_semi = torch.zeros((), device=x_real.device)
+
+        g_loss_nce = self.nce_loss(feat_x_pool, feat_f_pool)
+
+        g_loss = g_loss_fake + lambda_rec * g_loss_rec + lambda_cls * g_loss_cls + \
+            lambda_seg * g_loss_seg + \
+            lambda_semi * g_loss_semi + \
+            1.0 * g_loss_nce
+        self.optimizer.zero_grad()
+        g_loss.backward()
+        if self.parallel is not None:
+            self.parallel.all_reduce_grads(self.optimizer)
+        self.optimizer.step()
+
+        return torch.stack([d_loss_real.detach(), d_loss_fake.detach(), d_loss_cls.detach(), d_loss_gp.detach(),
+                            g_loss_fake.detach(), g_loss_rec.detach(), g_loss_cls.detach(), g_loss_seg.detach(),
+                            g_loss_semi.detach(), g_loss_nce.detach()])
+
+    def draw(self, batch, generator=None):
+        """The random draws of one iteration, made outside the (capturable) step: alpha ~ N(0,1) per sample
+        (L138, sic: randn, not rand) and the 64 shared patch positions (network/ugan.py:321-322)."""
+        hw = (self.input_size // 16) ** 2
+        alpha = torch.randn(batch, device=self.device, generator=generator)
+        ids = torch.randperm(hw, device=self.device, generator=generator)[:min(64, hw)]
+        return alpha, [ids]
+
+    def prepare_batch(self, x_real1, y_real, modal_org1, x_real2, modal_org2, mj):
+        """Host-side assembly of L110-127: concatenate the labelled and unlabelled halves, build the modality
+        difference vectors and move everything to the device."""
+        x_real = torch.cat([x_real1, x_real2], dim=0)
+        modal_org = torch.cat([modal_org1, modal_org2], dim=0)
+        modal_trg = torch.zeros_like(modal_org).fill_(mj)
+        vec_org = self.label2onehot(modal_org, cfg.n_modal)
+        vec_trg = self.label2onehot(modal_trg, cfg.n_modal)
+        dev = self.device
+        return (x_real.to(dev, non_blocking=True), y_real.to(dev, non_blocking=True),
+                modal_org.to(dev, non_blocking=True), modal_trg.to(dev, non_blocking=True),
+                (vec_trg - vec_org).to(dev, non_blocking=True), (vec_org - vec_trg).to(dev, non_blocking=True))
+
+    def train_epoch(self, lb_loader, ul_loader, meter, num_iter=None):
+        self.net.train()
+        self.D.train()
+        lambda_semi = self.lambda_semi * self.sigmoid_rampup(self.epoch, cfg.max_epoch)
+        n_critic = self.n_critic
+        print(f'\nlambda_seg: {self.lambda_seg}, lambda_semi: {lambda_semi}.')
+
+        lb_itr = iter(lb_loader)
+        ul_itr = iter(ul_loader)
+        tic = time.time()
+        losses = None
+        for i in range(n_critic * (num_iter or cfg.num_iter_per_epoch)):
+            try:
+                x_real1, y_real, modal_org1, _ = next(lb_itr)
+            except StopIteration:
+                lb_itr = iter(lb_loader)
+                x_real1, y_real, modal_org1, _ = next(lb_itr)
+            try:
+                x_real2, _, modal_org2, _ = next(ul_itr)
+            except StopIteration:
+                ul_itr = iter(ul_loader)
+                x_real2, _, modal_org2, _ = next(ul_itr)
+
+            mj = random.randint(0, cfg.n_modal - 1)
+            batch = self.prepare_batch(x_real1, y_real, modal_org1, x_real2, modal_org2, mj)
+            alpha, sample_ids = self.draw(batch[0].size(0))
+            losses = self.train_step(*batch, alpha, sample_ids, lambda_semi, self.iter >= self.semi_from_iter)
+
+            if (i + 1) % (n_critic * self.log_step) == 0:
+                vals = losses.tolist()      # the only device->host sync of the loop
+                log = 'Iter: %d/%d(%d), elapsed: %.2fs,' \
+                    % (i, n_critic * cfg.num_iter_per_epoch, self.iter, time.time() - tic)
+                tic = time.time()
+                for k, v in zip(LOSS_KEYS, vals):
+                    log += ' %s: %.4f,' % (k, v)
+                print(log, flush=True)
+
+            lr_ = self.lr_sched.host_lr(self.iter + 1)
+            for opt in (self.optimizer, self.d_optimizer):
+                for param_group in opt.param_groups:
+                    param_group['lr'] = lr_
+                opt._lr_host = lr_
+            self.iter += 1
+        return losses
+
+
+if __name__ == '__main__':
+    parser = argparse.ArgumentParser()
+    parser.add_argument('-p', '--phase', type=str, default='train')
+    parser.add_argument('-f', '--fold', type=int, default=0)
+    parser.add_argument('-nm', '--expr_name', type=str, default=None)
+    parser.add_argument('-i', '--model_id', type=str, default=None)
+    parser.add_argument('-wh', '--which_ckpt', type=str, default='last')
+    parser.add_argument('--epochs', type=int, default=None, help='(extension) shorten the run')
+    parser.add_argument('--iters', type=int, default=None, help='(extension) iterations per epoch')
+    args = parser.parse_args()
+
+    random.seed(cfg.seed)
+    np.random.seed(cfg.seed)
+    torch.manual_seed(cfg.seed)
+    torch.cuda.manual_seed(cfg.seed)
+
+    if args.phase == 'train':
+        trainer = UGANConsisTrainer('train', args)
+        trainer.fit('inTurn', max_epoch=args.epochs, iters_per_epoch=args.iters)
+    elif args.phase == 'test':
+        from ..data_loader import syntheticLoader as synlod
+        trainer = UGANConsisTrainer('test', args)
+        trainer.load_model(args.model_id or '000', args.which_ckpt)
+        print('dice: %.4f' % trainer.validate_epoch(synlod.get_loader(None, 'test', 0, cfg.batch_size, pool_batches=4)))
+    else:
+        raise NotImplementedError
