@@ -1,0 +1,209 @@
+"""GPU parity of the drop-in modules and trainer steps (all arithmetic through libsmsut_b200's kernels) against the
+oracle (oracle/smsut_oracle.py, plain PyTorch fp32 with TF32 off) on identical seeded inputs and weights.
+
+Tolerances (north_star): activations / logits within 2e-2 relative L2 (bf16 storage), losses within 1%, argmax
+masks bit-exact wherever the oracle's top-2 logit margin exceeds the activation tolerance.  Parameter gradients
+are compared per tensor; their bound is looser (5e-2, a few cancelling sums up to 0.15) because bf16 rounding of
+a pre-activation near zero flips its LeakyReLU mask (tests/test_host_logic.py quantifies the same effect in fp32).
+A JSON report with every number is written to gpurun_out/parity_<name>.json.
+"""
+import json
+import os
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from oracle import smsut_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def report(name, data):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
+def to_dev(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+def grad_report(named_params, ref_grads):
+    out = {}
+    for k, p in named_params:
+        if p.grad is not None and k in ref_grads and ref_grads[k] is not None:
+            out[k] = rel(p.grad, ref_grads[k])
+    return out
+
+
+def check_grads(g, bound=5e-2, hard=0.2, frac=0.9):
+    vals = sorted(g.values())
+    assert vals, "no gradients compared"
+    assert vals[int(frac * (len(vals) - 1))] < bound, (vals[int(frac * (len(vals) - 1))], max(g, key=g.get))
+    assert vals[-1] < hard, (vals[-1], max(g, key=g.get))
+
+
+def margin_mask(ref_logits, tol=2e-2):
+    """pixels whose top-2 margin exceeds tol * logit scale (computed from the ORACLE's fp32 logits)"""
+    top2 = ref_logits.topk(2, dim=1).values
+    scale = ref_logits.abs().amax(dim=1)
+    return (top2[:, 0] - top2[:, 1]) > 2 * tol * scale.clamp_min(1e-6)
+
+
+@pytest.mark.parametrize("size,n", [(256, 2), (64, 4)])
+def test_unet_parity(pkg, size, n):
+    from smsut_b200.misc.loss import DiceAndCrossEntropyLoss
+    from smsut_b200.network.unet import UNet
+    sd = to_dev(O.make_weights(O.unet_shapes(), 1))
+    net = UNet(1, 5, 16, 'instance', 'lrelu').to(DEV)
+    net.load_state_dict(sd)
+    x, y = O.synthetic_batch(n, size, 3, device=DEV)
+    out = net(x)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.unet_forward(leaf, x)
+    r_fwd = rel(out, ref)
+    loss = DiceAndCrossEntropyLoss(0.5, 0.5, batch_dice=True)(out, y)
+    lref = O.dice_ce_loss(ref, y)
+    loss.backward()
+    lref.backward()
+    g = grad_report(net.named_parameters(), {k: v.grad for k, v in leaf.items()})
+    mask = margin_mask(ref.detach())
+    agree = (out.argmax(1) == ref.argmax(1))[mask].float().mean().item()
+    report(f"unet_{size}", dict(logits_rel=r_fwd, loss=loss.item(), loss_ref=lref.item(), grads=g,
+                                argmax_agree_on_margin=agree, margin_excluded_frac=1 - mask.float().mean().item()))
+    assert r_fwd < 2e-2
+    assert abs(loss.item() - lref.item()) < 1e-2 * abs(lref.item())
+    assert agree == 1.0
+    check_grads(g)
+
+
+def test_ugannce_parity(pkg):
+    from smsut_b200.network.ugan import UGANnce
+    sd = to_dev(O.make_weights(O.ugan_shapes(), 4))
+    net = UGANnce(1, 5, 4, 16).to(DEV)
+    net.load_state_dict(sd)
+    x, _ = O.synthetic_batch(2, 256, 4, device=DEV)
+    m = torch.tensor([[1., 0, -1, 0], [0, 1., -1, 0]], device=DEV)
+    ids = [torch.randperm(256, generator=torch.Generator().manual_seed(0))[:64].to(DEV)]
+    seg, tsl, feats, _ = net(x, m, sample_ids=ids)
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    rseg, rtsl, rfeats, _ = O.ugannce_forward(leaf, x, m, sample_ids=ids)
+    r = dict(seg=rel(seg, rseg), tsl=rel(tsl, rtsl), feat=rel(feats[0], rfeats[0]))
+    w = torch.randn_like(rseg)
+    (seg * w).mean().add(tsl.mean()).add((feats[0] ** 3).sum()).backward()
+    (rseg * w).mean().add(rtsl.mean()).add((rfeats[0] ** 3).sum()).backward()
+    g = grad_report(net.named_parameters(), {k: v.grad for k, v in leaf.items()})
+    report("ugannce", dict(outputs=r, grads=g))
+    assert max(r.values()) < 2e-2, r
+    assert len(net(x, val_phase=True)) == 2
+    check_grads(g, bound=8e-2, hard=0.5)
+
+
+def test_discriminator_gp_parity(pkg):
+    from smsut_b200.network.ugan import Discriminator
+    from smsut_b200.trainer.uganShp0Trainer import UGANShp0Trainer
+    sd = to_dev(O.make_weights(O.disc_shapes(256), 5))
+    D = Discriminator(256, 4, 16, max_width=256).to(DEV)
+    D.load_state_dict(sd)
+    x, _ = O.synthetic_batch(4, 256, 6, device=DEV)
+    x_hat = (x + 0.1 * torch.randn_like(x)).requires_grad_(True)
+    out_src, out_cls = D(x_hat)
+    gp = UGANShp0Trainer.gradient_penalty(None, out_src, x_hat)
+    (gp * 10 + out_src.mean() + out_cls.pow(2).mean()).backward()
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x_hat.detach().clone().requires_grad_(True)
+    rsrc, rcls = O.discriminator_forward(leaf, xr)
+    rgp = O.gradient_penalty(rsrc, xr)
+    (rgp * 10 + rsrc.mean() + rcls.pow(2).mean()).backward()
+    g = grad_report(D.named_parameters(), {k: v.grad for k, v in leaf.items()})
+    r = dict(src=rel(out_src, rsrc), cls=rel(out_cls, rcls), gp=gp.item(), gp_ref=rgp.item())
+    report("discriminator_gp", dict(outputs=r, grads=g))
+    assert r["src"] < 2e-2 and r["cls"] < 2e-2
+    assert abs(gp.item() - rgp.item()) < 5e-2 * abs(rgp.item())
+    check_grads(g, bound=8e-2, hard=0.5)
+
+
+def _trainer(size, G_seed=7, D_seed=8):
+    from smsut_b200.trainer.uganConsisTrainer import UGANConsisTrainer
+    tr = UGANConsisTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=size))
+    G = to_dev(O.make_weights(O.ugan_shapes(), G_seed))
+    D = to_dev(O.make_weights(O.disc_shapes(size), D_seed))
+    tr.net.load_state_dict(G)
+    tr.D.load_state_dict(D)
+    return tr, G, D
+
+
+@pytest.mark.parametrize("use_semi", [False, True])
+def test_ugan_consis_step_parity(pkg, use_semi):
+    """One teacher-forced UGANConsisTrainer iteration at 256x256, 2 labelled + 2 unlabelled slices."""
+    from smsut_b200.trainer.uganConsisTrainer import LOSS_KEYS
+    size, bs = 256, 2
+    tr, G, D = _trainer(size)
+    x1, y = O.synthetic_batch(bs, size, 11)
+    x2, _ = O.synthetic_batch(bs, size, 12)
+    mod1, mod2 = torch.full((bs,), 1), torch.full((bs,), 3)
+    gen = torch.Generator().manual_seed(3)
+    mj = 2
+    alpha = torch.randn(2 * bs, generator=gen).to(DEV)
+    ids = [torch.randperm(256, generator=gen)[:64].to(DEV)]
+    batch = tr.prepare_batch(x1, y, mod1, x2, mod2, mj)
+    got = tr.train_step(*batch, alpha, ids, 0.7, use_semi).tolist()
+    xr, mr = torch.cat([x1, x2]).to(DEV), torch.cat([mod1, mod2]).to(DEV)
+    ref, d_grads = O.ugan_d_phase(G, D, {}, xr, mr, mj, alpha.view(-1, 1, 1, 1), ids, 1e-2)
+    gd = grad_report(tr.D.named_parameters(), d_grads)
+    D2 = {k: v.detach().clone() for k, v in tr.D.state_dict().items()}       # teacher-force the G phase
+    g_ref, g_grads = O.ugan_g_phase(G, D2, {}, xr, y.to(DEV), mr, mj, ids, 1e-2, 1000 if use_semi else 0, 0.7,
+                                    nce_batch=8)
+    ref.update(g_ref)
+    gg = grad_report(tr.net.named_parameters(), g_grads)
+    losses = {k: (v, ref[k]) for k, v in zip(LOSS_KEYS, got)}
+    report(f"consis_step_semi{int(use_semi)}", dict(losses=losses, d_grads=gd, g_grads=gg))
+    for k, (v, r) in losses.items():
+        tol = 5e-2 if k in ("D_gp",) else 2e-2
+        assert abs(v - r) < tol * max(1.0, abs(r)), (k, v, r)
+    check_grads(gd, bound=0.1, hard=0.6)
+    check_grads(gg, bound=0.15, hard=0.8)
+
+
+def test_unet_free_running_loss_trajectory(pkg):
+    """SGD-only U-Net path: 40 free-running steps stay within 1.5% of the fp32 oracle's loss (SURVEY 7.2 item 7:
+    this path is well conditioned, unlike the GAN step)."""
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=128))
+    sd = to_dev(O.make_weights(O.unet_shapes(), 21))
+    tr.net.load_state_dict(sd)
+    st, worst, traj = {}, 0.0, []
+    for it in range(40):
+        x, y = O.synthetic_batch(4, 128, 30 + it % 8, device=DEV)
+        loss = tr.train_step(x, y).item()
+        ref, _ = O.unet_step(sd, st, x, y, O.poly_lr(1e-2, max(it - 1, 0), 30000))
+        traj.append((loss, ref.item()))
+        worst = max(worst, abs(loss - ref.item()) / abs(ref.item()))
+    report("unet_trajectory", dict(worst_rel=worst, trajectory=traj))
+    assert worst < 1.5e-2, worst
+    assert traj[-1][0] < 0.7 * traj[0][0], "the loss did not go down"
+
+
+def test_inference_sweep_matches_oracle_argmax(pkg):
+    """config 5: U-Net segmentation of slice batches 1..16 (incl. a ragged 3): argmax bit-exact on margin pixels"""
+    from smsut_b200.network.unet import UNet
+    sd = to_dev(O.make_weights(O.unet_shapes(), 1))
+    net = UNet(1, 5, 16, 'instance', 'lrelu').to(DEV).eval()
+    net.load_state_dict(sd)
+    with torch.no_grad():
+        for n in (1, 3, 8, 16):
+            x, _ = O.synthetic_batch(n, 256, 50 + n, device=DEV)
+            out, ref = net(x), O.unet_forward(sd, x)
+            mask = margin_mask(ref)
+            assert (out.argmax(1) == ref.argmax(1))[mask].all()
+            assert mask.float().mean() > 0.9
