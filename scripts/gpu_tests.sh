@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 rc=0
 for f in "$@"; do
   name=$(basename "$f" .py)
-  timeout 600 python -m pytest "$f" -m gpu -q -x --timeout=300 -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
+  timeout 600 python -m pytest "$f" -m gpu -q --timeout=300 -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
   r=$?
   echo "== $f -> exit $r"
   tail -n 25 "gpurun_out/$name.log"

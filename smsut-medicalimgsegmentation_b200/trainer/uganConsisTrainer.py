@@ -106,6 +106,8 @@ class UGANConsisTrainer(UGANShp0Trainer):
             g_loss_semi = self.consistency_loss(y_rec, y_fake)
         else:
             g_loss_semi = torch.zeros((), device=x_real.device)
+        if isinstance(lambda_semi, torch.Tensor):
+            lambda_semi = lambda_semi.reshape(())      # device scalar: one captured graph serves every epoch
 
         g_loss_nce = self.nce_loss(feat_x_pool, feat_f_pool)
 
@@ -122,6 +124,15 @@ class UGANConsisTrainer(UGANShp0Trainer):
         return torch.stack([d_loss_real.detach(), d_loss_fake.detach(), d_loss_cls.detach(), d_loss_gp.detach(),
                             g_loss_fake.detach(), g_loss_rec.detach(), g_loss_cls.detach(), g_loss_seg.detach(),
                             g_loss_semi.detach(), g_loss_nce.detach()])
+
+    def graphed_step(self, example, use_semi):
+        """Capture train_step for the given example inputs (x_real, y_real, modal_org, modal_trg, vec_ot, vec_to,
+        alpha, ids, lambda_semi[device scalar]) into a CUDA graph; returns a callable with the same arguments."""
+        from ..graph import GraphedStep
+
+        def fn(x_real, y_real, modal_org, modal_trg, vec_ot, vec_to, alpha, ids, lam):
+            return self.train_step(x_real, y_real, modal_org, modal_trg, vec_ot, vec_to, alpha, [ids], lam, use_semi)
+        return GraphedStep(fn, example)
 
     def draw(self, batch, generator=None):
         """The random draws of one iteration, made outside the (capturable) step: alpha ~ N(0,1) per sample

@@ -257,7 +257,7 @@ def bilinear2_fwd(x):
 def bilinear2_bwd(dy):
     n, h2, w2, c = dy.shape
     with torch.enable_grad():
-        xr = torch.zeros(n, c, h2 // 2, w2 // 2, requires_grad=True)
+        xr = torch.zeros(n, c, h2 // 2, w2 // 2, requires_grad=True, device=dy.device)
         F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False).backward(_nchw(dy))
     return _nhwc(xr.grad)
 
@@ -395,9 +395,9 @@ def _nce_rows(q, k, groups, np_, inv_t):
     c = q.shape[1]
     l_pos = (q * k).sum(1, keepdim=True)
     l_neg = torch.bmm(q.view(groups, np_, c), k.view(groups, np_, c).transpose(2, 1))
-    l_neg = l_neg.masked_fill(torch.eye(np_, dtype=torch.bool)[None], -10.0).view(-1, np_)
+    l_neg = l_neg.masked_fill(torch.eye(np_, dtype=torch.bool, device=q.device)[None], -10.0).view(-1, np_)
     out = torch.cat((l_pos, l_neg), 1) * inv_t
-    return F.cross_entropy(out, torch.zeros(q.shape[0], dtype=torch.long), reduction="none")
+    return F.cross_entropy(out, torch.zeros(q.shape[0], dtype=torch.long, device=q.device), reduction="none")
 
 
 def patchnce_fwd(q, k, groups, np_, inv_t, out, scale):

@@ -1,0 +1,131 @@
+"""Pins the oracle (oracle/smsut_oracle.py) against fixtures produced by the REAL reference modules
+(tests/golden/make_golden.py, run once in the build container where /root/reference is mounted)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import smsut_oracle as O
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(G, name + ".npz")))
+
+
+def close(a, b, tol=1e-4):
+    a, b = torch.as_tensor(np.asarray(a)).double(), torch.as_tensor(np.asarray(b)).double()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item() < tol
+
+
+def leaf(sd):
+    return {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+
+
+def check_grad_norms(fix, prefix, leafs, tol=1e-3):
+    n = 0
+    for k, v in leafs.items():
+        key = prefix + k
+        if key in fix:
+            n += 1
+            assert abs(v.grad.norm().item() - float(fix[key])) < tol * max(1e-3, float(fix[key])), k
+    assert n > 10
+
+
+def test_unet_matches_reference_fixture():
+    f = load("unet")
+    sd = leaf(O.make_weights(O.unet_shapes(), 1))
+    x, y = O.synthetic_batch(2, 64, 3)
+    out = O.unet_forward(sd, x)
+    assert close(out.detach(), f["logits"], 1e-5)
+    loss = O.dice_ce_loss(out, y)
+    assert abs(loss.item() - float(f["loss"])) < 1e-6
+    loss.backward()
+    assert close(sd["decoder.fc.weight"].grad, f["fc_grad"]) and close(sd["encoder.pre_conv.weight"].grad, f["pre_grad"])
+    check_grad_norms(f, "gn.", sd)
+
+
+def test_ugannce_matches_reference_fixture():
+    f = load("ugannce")
+    sd = leaf(O.make_weights(O.ugan_shapes(), 4))
+    x, _ = O.synthetic_batch(2, 64, 4)
+    m = torch.tensor([[1., 0, -1, 0], [0, 1., -1, 0]])
+    ids = [torch.as_tensor(f["ids"])]
+    seg, tsl, feats, _ = O.ugannce_forward(sd, x, m, sample_ids=ids)
+    assert close(seg.detach(), f["seg"], 1e-5) and close(tsl.detach(), f["tsl"], 1e-5)
+    assert close(feats[0].detach(), f["feat"], 1e-5)
+    (seg.mean() + tsl.mean() + (feats[0] ** 3).sum()).backward()
+    check_grad_norms(f, "gn.", sd)
+    assert len(O.ugannce_forward(sd, x, val_phase=True)) == 2
+
+
+def test_discriminator_and_gradient_penalty_match_reference_fixture():
+    f = load("discriminator")
+    sd = leaf(O.make_weights(O.disc_shapes(64), 5))
+    x_hat = torch.as_tensor(f["x_hat"]).requires_grad_(True)
+    out_src, out_cls = O.discriminator_forward(sd, x_hat)
+    assert close(out_src.detach(), f["out_src"], 1e-5) and close(out_cls.detach(), f["out_cls"], 1e-5)
+    gp = O.gradient_penalty(out_src, x_hat)
+    assert abs(gp.item() - float(f["gp"])) < 1e-4 * float(f["gp"])
+    (10 * gp + out_src.mean() + out_cls.pow(2).mean()).backward()
+    check_grad_norms(f, "gn.", sd)
+
+
+def test_losses_match_reference_fixture():
+    f = load("losses")
+    logits = torch.as_tensor(f["logits"]).requires_grad_(True)
+    l = O.dice_ce_loss(logits, torch.as_tensor(f["labels"]))
+    assert abs(l.item() - float(f["dice_ce"])) < 1e-6
+    l.backward()
+    assert close(logits.grad, f["dlogits"], 1e-5)
+    q = torch.as_tensor(f["q"]).requires_grad_(True)
+    rows = O.patchnce_loss(q, torch.as_tensor(f["k"]), 8)
+    assert close(rows.detach(), f["nce_rows"], 1e-5)
+    rows.mean().backward()
+    assert close(q.grad, f["dq"], 1e-5)
+
+
+def test_two_consis_iterations_match_reference_fixture():
+    """two consecutive iterations (consistency loss off, then on) with torch.optim SGD/Adam state carried over"""
+    f = load("consis_step")
+    size, bs = 64, 2
+    Gw, Dw = O.make_weights(O.ugan_shapes(), 7), O.make_weights(O.disc_shapes(size), 8)
+    g_state, d_state = {}, {}
+    x1, y = O.synthetic_batch(bs, size, 11)
+    x2, _ = O.synthetic_batch(bs, size, 12)
+    x_real = torch.cat([x1, x2])
+    modal = torch.cat([torch.full((bs,), 1), torch.full((bs,), 3)])
+    keys = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
+    for s in (0, 1):
+        losses, d_grads, g_grads = O.ugan_consis_step(
+            Gw, Dw, g_state, d_state, x_real, y, modal, 2, torch.as_tensor(f[f"s{s}.alpha"]),
+            [torch.as_tensor(f[f"s{s}.ids"])], 1e-2, 1000 if s else 0, 0.7, nce_batch=8)
+        # step 1 starts from weights that went through Adam's sign-like first update: fp32 round-off is amplified
+        tol = 1e-4 if s == 0 else 3e-2
+        for k, ref in zip(keys, f[f"s{s}.losses"]):
+            assert abs(losses[k] - ref) < tol * max(1.0, abs(ref)), (s, k, losses[k], ref)
+        for k, v in d_grads.items():
+            ref = float(f[f"s{s}.dgn.{k}"])
+            assert abs(v.norm().item() - ref) < (1e-3 if s == 0 else 0.2) * max(ref, 1e-3), (s, k)
+        if s == 0:
+            for k, v in g_grads.items():
+                ref = float(f[f"s{s}.ggn.{k}"])
+                assert abs(v.norm().item() - ref) < 5e-2 * max(ref, 1e-3), (s, k)
+            dsum = np.array([v.double().sum().item() for v in Dw.values()])
+            assert np.abs(dsum - f["s0.D_checksum"]).max() < 0.5      # Adam: lr * sign(g) on near-zero gradients
+            gsum = np.array([v.double().sum().item() for v in Gw.values()])
+            assert np.allclose(gsum, f["s0.G_checksum"], rtol=2e-2, atol=0.5)
+
+
+def test_schedules_and_helpers():
+    assert O.poly_lr(1e-2, 0, 30000) == 1e-2 and abs(O.poly_lr(1e-2, 15000, 30000) - 1e-2 * 0.5 ** 0.9) < 1e-12
+    assert O.sigmoid_rampup(0, 200) == pytest.approx(float(np.exp(-5.0)))
+    assert O.sigmoid_rampup(200, 200) == 1.0 and O.sigmoid_rampup(5, 0) == 1.0
+    assert O.ema_alpha(50) == 0.0 and O.ema_alpha(100) == 0.99 and O.ema_alpha(10 ** 6) == 0.99
+    oh = O.label2onehot(torch.tensor([0, 3, 1]), 4)
+    assert oh.tolist() == [[1, 0, 0, 0], [0, 0, 0, 1], [0, 1, 0, 0]]
+    img, lab = O.synthetic_batch(2, 64, 0)
+    assert img.shape == (2, 1, 64, 64) and img.min() >= -1 and img.max() <= 1 and set(lab.unique().tolist()) <= {0, 1, 2, 3, 4}
+    assert 0.5 < (lab == 0).float().mean() < 0.95
