@@ -23,6 +23,7 @@ from .baseTrainer import BaseTrainer
 class UnetTrainer(BaseTrainer):
     def __init__(self, phase, args=None):
         super(UnetTrainer, self).__init__(phase, args)
+        self.parallel = None           # parallel.DataParallelContext under torchrun
 
     def build_network(self):
         self.net = UNet(cfg.img_channels, cfg.n_label + 1, cfg.base_width, norm_type='instance', act_type='lrelu')
@@ -38,6 +39,8 @@ class UnetTrainer(BaseTrainer):
         sample_loss = self.loss(out, msk)
         self.optimizer.zero_grad()
         sample_loss.backward()
+        if self.parallel is not None:
+            self.parallel.all_reduce_grads(self.optimizer)
         self.optimizer.step()
         self.iter += 1
         return sample_loss.detach()
