@@ -39,7 +39,7 @@ enum { SMSUT_ACT_NONE = 0, SMSUT_ACT_RELU = 1, SMSUT_ACT_LRELU = 2 };
 
 typedef struct smsut_conv_tc_args {
   int32_t kind;       /* SMSUT_TC_* */
-  int32_t ksize;      /* 1 or 3 (kind CONV); ignored otherwise */
+  int32_t ksize;      /* 1, 3 or 5 (kind CONV); ignored otherwise */
   int32_t n, h, w;    /* GEMM-row space: output dims for CONV; the transposed conv's INPUT dims otherwise */
   int32_t nsrc;       /* 1 or 2 activation sources (channel-concatenated, src[0] first) */
   const void* src[2]; /* bf16 NHWC; CONVT_DGRAD: the (n, 2h, 2w, src_c[0]) output gradient */
@@ -68,7 +68,7 @@ int smsut_conv_tc(const smsut_conv_tc_args* a, smsut_stream_t stream);
  *   dW[ci_off+ci][co][ty][tx] += sum_p x[p][ci] * dy[2p + tap][co]                    (CONVT) */
 typedef struct smsut_wgrad_tc_args {
   int32_t kind;  /* SMSUT_TC_CONV or SMSUT_TC_CONVT_FWD */
-  int32_t ksize; /* 1 or 3 */
+  int32_t ksize; /* 1, 3 or 5 */
   int32_t n, h, w;
   const void* x;  /* bf16 NHWC input activations (n,h,w,*) */
   int32_t x_c, x_ld;
@@ -106,6 +106,12 @@ int smsut_conv_direct_fprop(const smsut_conv_direct_args* a, smsut_stream_t stre
 int smsut_conv_direct_dgrad(const smsut_conv_direct_args* a, smsut_stream_t stream);
 /* dW[co,ci,ky,kx] += sum x * dy ; dbias[co] += sum dy (if dbias != NULL) */
 int smsut_conv_direct_wgrad(const smsut_conv_direct_args* a, float* dw, float* dbias, smsut_stream_t stream);
+
+/* Fused backward of the 1x1 heads (network/ugan.py:70-83: tsl/seg `fc`, network/blocks.py:166: U-Net `fc`):
+ * g = dy * (1 - y^2) when y != NULL (tanh head); dx = g W (bf16, optional); dW += g^T x; dbias += sum g.
+ * x (npix, 16) bf16, dy / y (npix, cout) fp32, w fp32 (cout, 16). */
+int smsut_head1x1_bwd(const void* x, const float* dy, const float* y, const float* w, void* dx, float* dw, float* db,
+                      int64_t npix, int32_t cin, int32_t cout, smsut_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * InstanceNorm2d(affine) + LeakyReLU + residual  (network/blocks.py:22-34, 66-80, 99-117)

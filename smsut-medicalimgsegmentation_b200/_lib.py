@@ -63,6 +63,7 @@ _PROTOS = {
     "smsut_conv_direct_fprop": [C.POINTER(ConvDirectArgs), P],
     "smsut_conv_direct_dgrad": [C.POINTER(ConvDirectArgs), P],
     "smsut_conv_direct_wgrad": [C.POINTER(ConvDirectArgs), P, P, P],
+    "smsut_head1x1_bwd": [P, P, P, P, P, P, P, c_int64, c_int, c_int, P],
     "smsut_in_stats": [P, c_int, c_int, c_int, P, P],
     "smsut_in_apply": [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smsut_in_bwd_reduce": [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P],

@@ -217,14 +217,24 @@ __global__ void __launch_bounds__(256) direct_wgrad_kernel(const DirectParams p,
       const int iy = oy * p.stride - p.pad + ky[j];
       if (iy < 0 || iy >= p.h) continue;
       const size_t xbase = ((size_t)n * p.h + iy) * p.w * p.x_ld;
-      float a = 0.f;
-      for (int ox = 0; ox < p.wo; ++ox) {
-        const int ix = ox * p.stride - p.pad + kx[j];
-        if (ix < 0 || ix >= p.w) continue;
-        a = fmaf(load_act(p.y, dybase + (size_t)ox * p.y_ld + co[j], p.y_f32),
-                 load_act(p.x, xbase + (size_t)ix * p.x_ld + ci[j], p.x_f32), a);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      // valid ox range for this tap, then 4 independent accumulators (the loads are L1 hits: latency-bound)
+      int ox0 = 0, ox1 = p.wo;
+      while (ox0 < ox1 && ox0 * p.stride - p.pad + kx[j] < 0) ++ox0;
+      while (ox1 > ox0 && (ox1 - 1) * p.stride - p.pad + kx[j] >= p.w) --ox1;
+      const size_t dyo = dybase + co[j];
+      const long long xo = (long long)xbase + ci[j] + (long long)(kx[j] - p.pad) * p.x_ld;
+      const size_t xs = (size_t)p.stride * p.x_ld;
+      int ox = ox0;
+      for (; ox + 3 < ox1; ox += 4) {
+        a0 = fmaf(load_act(p.y, dyo + (size_t)ox * p.y_ld, p.y_f32), load_act(p.x, xo + ox * xs, p.x_f32), a0);
+        a1 = fmaf(load_act(p.y, dyo + (size_t)(ox + 1) * p.y_ld, p.y_f32), load_act(p.x, xo + (ox + 1) * xs, p.x_f32), a1);
+        a2 = fmaf(load_act(p.y, dyo + (size_t)(ox + 2) * p.y_ld, p.y_f32), load_act(p.x, xo + (ox + 2) * xs, p.x_f32), a2);
+        a3 = fmaf(load_act(p.y, dyo + (size_t)(ox + 3) * p.y_ld, p.y_f32), load_act(p.x, xo + (ox + 3) * xs, p.x_f32), a3);
       }
-      acc[j] += a;
+      for (; ox < ox1; ++ox)
+        a0 = fmaf(load_act(p.y, dyo + (size_t)ox * p.y_ld, p.y_f32), load_act(p.x, xo + ox * xs, p.x_f32), a0);
+      acc[j] += (a0 + a1) + (a2 + a3);
     }
   }
 #pragma unroll
@@ -240,6 +250,62 @@ __global__ void __launch_bounds__(256) direct_wgrad_kernel(const DirectParams p,
       }
       atomicAdd(dbias + c, s);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused backward of the 1x1 heads (network/ugan.py:70-83, network/blocks.py:166): one pass over the pixels gives
+// dx (bf16), dW and dbias (fp32 atomics); optional tanh' from the saved output.  x: (npix, 16) bf16.
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(256)
+head1x1_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                   const float* __restrict__ w, uint4* __restrict__ dx, float* __restrict__ dw,
+                   float* __restrict__ db, long long npix) {
+  __shared__ float sh[COUT * 17];
+  float wr[COUT][16], aw[COUT][16], ab[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    ab[o] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { wr[o][c] = w[o * 16 + c]; aw[o][c] = 0.f; }
+  }
+  for (int i = threadIdx.x; i < COUT * 17; i += blockDim.x) sh[i] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    float xv[16], g[COUT], d[16];
+    unpack8(x[2 * p], xv);
+    unpack8(x[2 * p + 1], xv + 8);
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      g[o] = dy[p * COUT + o];
+      if (y != nullptr) { const float t = y[p * COUT + o]; g[o] *= 1.f - t * t; }
+      ab[o] += g[o];
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) { a = fmaf(g[o], wr[o][c], a); aw[o][c] = fmaf(g[o], xv[c], aw[o][c]); }
+      d[c] = a;
+    }
+    if (dx != nullptr) { dx[2 * p] = pack8(d); dx[2 * p + 1] = pack8(d + 8); }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float v = warp_sum(aw[o][c]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&sh[o * 17 + c], v);
+    }
+    const float v = warp_sum(ab[o]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sh[o * 17 + 16], v);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * 17; i += blockDim.x) {
+    const int o = i / 17, c = i - o * 17;
+    if (c < 16) { if (dw) atomicAdd(dw + o * 16 + c, sh[i]); }
+    else if (db) atomicAdd(db + o, sh[i]);
   }
 }
 
@@ -332,6 +398,20 @@ static int direct_wgrad(const smsut_conv_direct_args* a, float* dw, float* dbias
 
 }  // namespace smsut
 
+extern "C" int smsut_head1x1_bwd(const void* x, const float* dy, const float* y, const float* w, void* dx, float* dw,
+                                 float* db, int64_t npix, int32_t cin, int32_t cout, smsut_stream_t s) {
+  using namespace smsut;
+  SMSUT_CHECK(cin == 16 && cout >= 1 && cout <= 8 && npix > 0, -1, "head1x1_bwd supports Cin = 16, Cout <= 8");
+  long long blocks = (npix + 255) / 256;
+  const long long cap = 4LL * device_sm_count();
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+#define HEAD_CASE(C) case C: head1x1_bwd_kernel<C><<<(unsigned)blocks, 256, 0, st>>>((const uint4*)x, dy, y, w, (uint4*)dx, dw, db, npix); break;
+  switch (cout) { HEAD_CASE(1) HEAD_CASE(2) HEAD_CASE(3) HEAD_CASE(4) HEAD_CASE(5) HEAD_CASE(6) HEAD_CASE(7) HEAD_CASE(8) }
+#undef HEAD_CASE
+  count_launch();
+  return launch_status("head1x1_bwd_kernel");
+}
 extern "C" int smsut_conv_direct_fprop(const smsut_conv_direct_args* a, smsut_stream_t s) {
   return smsut::direct_fprop(a, reinterpret_cast<cudaStream_t>(s));
 }

@@ -388,7 +388,7 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   int ns = 0;
   if (a->kind == SMSUT_TC_CONV || a->kind == SMSUT_TC_CONVT_FWD) {
     const int ks = a->kind == SMSUT_TC_CONV ? a->ksize : 1;
-    SMSUT_CHECK(ks == 1 || ks == 3, -1, "ksize must be 1 or 3");
+    SMSUT_CHECK(ks == 1 || ks == 3 || ks == 5, -1, "ksize must be 1, 3 or 5");
     for (int s = 0; s < a->nsrc; ++s) {
       rc = make_act_map(&maps[s], a->src[s], a->src_c[s], a->w, a->h, a->n, a->src_ld[s],
                         (int64_t)a->src_ld[s] * a->w, (int64_t)a->src_ld[s] * a->w * a->h, cc, p.tw, p.th, p.tn);

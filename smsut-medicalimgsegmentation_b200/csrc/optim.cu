@@ -183,7 +183,7 @@ extern "C" int smsut_poly_lr_tick(float* iter_state, float* lr_out, float base_l
 }
 extern "C" int smsut_pack_weights(const smsut_pack_entry* table, int32_t n, smsut_stream_t st) {
   SMSUT_CHECK(table && n > 0, -1, "bad pack args");
-  pack_weights_kernel<<<dim3(n, 16), 256, 0, (cudaStream_t)st>>>(table);
+  pack_weights_kernel<<<dim3(n, 96), 256, 0, (cudaStream_t)st>>>(table);
   count_launch();
   return launch_status("pack_weights_kernel");
 }

@@ -229,7 +229,7 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
 
   int nb = 0;
   if (!convt) {
-    SMSUT_CHECK(a->ksize == 1 || a->ksize == 3, -1, "ksize must be 1 or 3");
+    SMSUT_CHECK(a->ksize == 1 || a->ksize == 3 || a->ksize == 5, -1, "ksize must be 1, 3 or 5");
     rc = make_act_map(&map_b[0], a->x, a->x_c, a->w, a->h, a->n, b_ld, (int64_t)b_ld * a->w,
                       (int64_t)b_ld * a->w * a->h, bc, p.tw, p.th, p.tn);
     if (rc) return rc;
@@ -243,7 +243,8 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
           b.map = 0; b.dy = (int8_t)dy; b.dx = (int8_t)dx; b.tap = (int8_t)t; b.c0 = (int16_t)c0;
         }
     p.taps = a->ksize * a->ksize;
-    p.m_total = a->dy_c; p.m_off = 0; p.nc = a->cin_total; p.c_off = a->ci_off;
+    p.m_total = a->dy_c < a->cout_total ? a->dy_c : a->cout_total;  // dy may carry zero padding channels
+    p.m_off = 0; p.nc = a->cin_total; p.c_off = a->ci_off;
     p.c_valid = a->c_valid > 0 ? a->c_valid : a->x_c;
   } else {
     const int64_t W2 = 2 * (int64_t)a->w, H2 = 2 * (int64_t)a->h;

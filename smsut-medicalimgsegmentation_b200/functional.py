@@ -37,6 +37,36 @@ class inputs_only:
         _inputs_only_global[0] = self.prev
 
 
+_accumulate = [False]
+
+
+class accumulate_param_grads:
+    """Inside this context (the trainers' backward calls) the weight-gradient kernels accumulate straight into the
+    parameters' existing `.grad` tensors (the flat gradient buffer of optim.py) and autograd is handed `None`:
+    no zero-fill + add pair per parameter.  Outside it the Functions return fresh gradient tensors as usual."""
+
+    def __enter__(self):
+        self.prev = _accumulate[0]
+        _accumulate[0] = True
+
+    def __exit__(self, *a):
+        _accumulate[0] = self.prev
+
+
+def _target(param):
+    """the tensor to accumulate a parameter gradient into, or None (return the gradient to autograd)"""
+    if not _accumulate[0] or param is None:
+        return None
+    g = param.grad
+    if g is None or g.dtype != F32 or not g.is_contiguous() or g.shape != param.shape:
+        return None
+    return g
+
+
+def _ret(grad, target):
+    return None if target is not None else grad
+
+
 def _c(t):
     """contiguous view of a gradient (autograd may hand over expanded / permuted tensors)"""
     return t if t.is_contiguous() else t.contiguous()
@@ -54,10 +84,26 @@ def to_nhwc(x):
         return v.contiguous()
     if x.dtype == F32:
         n, c, h, w = x.shape
+        if c <= 16:
+            return ImageInputFn.apply(x)
         if x.requires_grad:
             return x.permute(0, 2, 3, 1).to(BF16).contiguous()
-        return ops.nchw_to_nhwc(x.contiguous(), ops.pad16(c) if c > 1 else 8)
+        return ops.nchw_to_nhwc(x.contiguous(), ops.pad16(c))
     raise TypeError(f"unsupported activation dtype {x.dtype}")
+
+
+class ImageInputFn(Function):
+    """(N, C<=16, H, W) fp32 network input -> (N, H, W, 16) bf16 (zero channel padding) for the tensor-core stem;
+    the gradient of the image is the leading C channels of the stem's input gradient."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return ops.nchw_to_nhwc(x.contiguous(), 16)
+
+    @staticmethod
+    def backward(ctx, d):
+        return d[..., :ctx.c].float().permute(0, 3, 1, 2)
 
 
 def to_nchw(y):
@@ -74,6 +120,7 @@ class ConvDgradFn(Function):
     @staticmethod
     def forward(ctx, pw, weight, dy):
         ctx.pw = pw
+        ctx.pw_weight = weight
         ctx.save_for_backward(dy)
         return ops.conv_dgrad(dy, pw)[0]
 
@@ -82,7 +129,10 @@ class ConvDgradFn(Function):
         (dy,) = ctx.saved_tensors
         u = _c(u)
         g_dy = ops.conv_fprop([u], ctx.pw) if ctx.needs_input_grad[2] else None
-        g_w = ops.conv_wgrad([u], dy, ctx.pw) if ctx.needs_input_grad[1] else None
+        g_w = None
+        if ctx.needs_input_grad[1]:
+            t = _target(ctx.pw_weight)
+            g_w = _ret(ops.conv_wgrad([u], dy, ctx.pw, out=t), t)
         return None, g_w, g_dy
 
 
@@ -116,13 +166,17 @@ class ConvFn(Function):
         dxs = [None] * len(xs)
         if need_x:
             dxs = ops.conv_dgrad(dy, pw, splits)
-        dw = ops.conv_wgrad(xs, dy, pw) if ctx.needs_input_grad[1] else None
-        dw2 = None
+        dw = dw2 = None
+        if ctx.needs_input_grad[1]:
+            t = _target(weight)
+            dw = _ret(ops.conv_wgrad(xs, dy, pw, out=t), t)
         if pw2 is not None:
             dy2 = _c(dy2)
             if need_x:
                 ops.conv_dgrad_accumulate(dy2, pw2, dxs)
-            dw2 = ops.conv_wgrad(xs, dy2, pw2) if ctx.needs_input_grad[3] else None
+            if ctx.needs_input_grad[3]:
+                t = _target(weight2)
+                dw2 = _ret(ops.conv_wgrad(xs, dy2, pw2, out=t), t)
         return (None, dw, None, dw2, *dxs)
 
 
@@ -137,10 +191,13 @@ class ConvTFn(Function):
 
     @staticmethod
     def backward(ctx, dy):
-        _, x = ctx.saved_tensors
+        weight, x = ctx.saved_tensors
         dy = _c(dy)
         dx = ops.convt_dgrad(dy, ctx.pw) if ctx.needs_input_grad[2] else None
-        dw = ops.convt_wgrad(x, dy, ctx.pw) if ctx.needs_input_grad[1] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            t = _target(weight)
+            dw = _ret(ops.convt_wgrad(x, dy, ctx.pw, out=t), t)
         return None, dw, dx
 
 
@@ -164,7 +221,9 @@ class DirectDgradFn(Function):
             g_g = ops.conv_direct_fprop(u, weight, stride, pad, out_c=gc, out_f32=(gdt == F32))
         g_w = None
         if ctx.needs_input_grad[0]:
-            g_w, _ = ops.conv_direct_wgrad(u, g, weight, stride, pad, want_bias=False)
+            t = _target(weight)
+            g_w, _ = ops.conv_direct_wgrad(u, g, weight, stride, pad, want_bias=False, dw=t)
+            g_w = _ret(g_w, t)
         return g_w, g_g, None, None, None, None
 
 
@@ -176,16 +235,24 @@ class DirectConvFn(Function):
     def forward(ctx, x, weight, bias, stride, pad, act, out_c, out_f32):
         y = ops.conv_direct_fprop(x, weight, stride, pad, bias=bias, act=act, slope=SLOPE, out_c=out_c, out_f32=out_f32)
         ctx.meta = (stride, pad, act)
-        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None, bias)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight, y = ctx.saved_tensors
+        x, weight, y, bias = ctx.saved_tensors
         stride, pad, act = ctx.meta
         dy = _c(dy)
         diff = torch.is_grad_enabled()
+        tw, tb = _target(weight), _target(bias)
+        if (not diff and weight.shape[2] == 1 and weight.shape[3] == 1 and stride == 1 and pad == 0 and x.dtype == BF16
+                and x.shape[3] == 16 and weight.shape[1] == 16 and weight.shape[0] <= 8 and dy.dtype == F32
+                and act in (ACT_NONE, ACT_TANH)):
+            # 1x1 head: dx, dW and dbias in one fused pass
+            dx, dw, db = ops.head1x1_bwd(x, dy, y if act == ACT_TANH else None, weight, ctx.needs_input_grad[0], dw=tw,
+                                         db=tb, want_bias=ctx.has_bias)
+            return dx, _ret(dw, tw), (_ret(db, tb) if ctx.has_bias else None), None, None, None, None, None
         if act == ACT_TANH:
             assert not diff, "double backward through the tanh head is not on the path"
             g = ops.tanh_bwd(dy, y)
@@ -203,7 +270,8 @@ class DirectConvFn(Function):
             if ctx.needs_input_grad[0]:
                 dx = ops.conv_direct_dgrad(g, weight, tuple(x.shape), x.dtype, stride, pad)
             if ctx.needs_input_grad[1]:
-                dw, db = ops.conv_direct_wgrad(x, g, weight, stride, pad, want_bias=ctx.has_bias)
+                dw, db = ops.conv_direct_wgrad(x, g, weight, stride, pad, want_bias=ctx.has_bias, dw=tw, db=tb)
+                dw, db = _ret(dw, tw), (_ret(db, tb) if ctx.has_bias else None)
         return dx, dw, db, None, None, None, None, None
 
 
@@ -249,12 +317,12 @@ class INActFn(Function):
         sb = ops.in_stats(xb) if xb is not None else None
         out = ops.in_apply(xa, sa, ga, ba, xb, sb, gb, bb, res=res, act=act, slope=SLOPE, c_params=c_params)
         ctx.act, ctx.cp, ctx.has_res = act, c_params, res is not None
-        ctx.save_for_backward(xa, sa, ga, xb, sb, gb, out)
+        ctx.save_for_backward(xa, sa, ga, xb, sb, gb, out, ba, bb)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xa, sa, ga, xb, sb, gb, out = ctx.saved_tensors
+        xa, sa, ga, xb, sb, gb, out, ba, bb = ctx.saved_tensors
         dout = _c(dout)
         act, cp = ctx.act, ctx.cp
         want_res = ctx.has_res and ctx.needs_input_grad[6]
@@ -267,7 +335,17 @@ class INActFn(Function):
             if not _inputs_only_global[0]:
                 _, dga, dba, _, dgb, dbb, _ = ops.in_bwd(dout.detach(), out, xa, sa, ga, xb, sb, gb, False, act, SLOPE, cp)
             return dxa, dga, dba, dxb, dgb, dbb, (g if want_res else None), None, None
-        dxa, dga, dba, dxb, dgb, dbb, dres = ops.in_bwd(dout, out, xa, sa, ga, xb, sb, gb, want_res, act, SLOPE, cp)
+        targets = None
+        need = ctx.needs_input_grad
+        if not (need[1] or need[2] or need[4] or need[5]):
+            targets = [None, None, None, None]          # frozen parameters: no parameter gradients at all
+        else:
+            tg = [_target(ga), _target(ba), _target(gb) if xb is not None else None,
+                  _target(bb) if xb is not None else None]
+            if tg[0] is not None and tg[1] is not None and (xb is None or (tg[2] is not None and tg[3] is not None)):
+                targets = tg
+        dxa, dga, dba, dxb, dgb, dbb, dres = ops.in_bwd(dout, out, xa, sa, ga, xb, sb, gb, want_res, act, SLOPE, cp,
+                                                        targets=targets)
         return dxa, dga, dba, dxb, dgb, dbb, dres, None, None
 
 
@@ -364,7 +442,7 @@ class DiceCEFn(Function):
     @staticmethod
     def forward(ctx, logits, labels, label_logits, w_ce, w_dc):
         npix, c = logits.shape
-        acc = torch.zeros(3 * c + 1, dtype=F32, device=logits.device)
+        acc = ops.zeros(3 * c + 1, logits.device)
         ops.dice_ce_fwd(logits, labels, label_logits, acc)
         if _dice_allreduce[0] is not None:
             _dice_allreduce[0](acc[:3 * c])
@@ -386,7 +464,7 @@ class L1MeanFn(Function):
 
     @staticmethod
     def forward(ctx, a, b):
-        out = torch.zeros(1, dtype=F32, device=a.device)
+        out = ops.zeros(1, a.device)
         ops.l1_fwd(a, b, out, 1.0 / a.numel())
         ctx.save_for_backward(a, b)
         return out.view(())
@@ -402,7 +480,7 @@ class MeanFn(Function):
 
     @staticmethod
     def forward(ctx, x, scale):
-        out = torch.zeros(1, dtype=F32, device=x.device)
+        out = ops.zeros(1, x.device)
         ops.sum_f32(x, out, scale / x.numel())
         ctx.meta = (tuple(x.shape), scale / x.numel())
         return out.view(())
@@ -418,7 +496,7 @@ class CERowsFn(Function):
 
     @staticmethod
     def forward(ctx, logits, target):
-        out = torch.zeros(1, dtype=F32, device=logits.device)
+        out = ops.zeros(1, logits.device)
         ops.ce_rows_fwd(logits, target, out, 1.0)
         ctx.save_for_backward(logits, target)
         return out.view(())
@@ -434,7 +512,7 @@ class GradPenaltyFn(Function):
 
     @staticmethod
     def forward(ctx, g):
-        out = torch.zeros(1, dtype=F32, device=g.device)
+        out = ops.zeros(1, g.device)
         norm = ops.gp_fwd(g, out, 1.0)
         ctx.save_for_backward(g, norm)
         return out.view(())
@@ -491,7 +569,7 @@ class PatchNCEFn(Function):
     @staticmethod
     def forward(ctx, q, k, groups):
         rows = q.shape[0]
-        out = torch.zeros(1, dtype=F32, device=q.device)
+        out = ops.zeros(1, q.device)
         loss_rows = ops.patchnce_fwd(q, k, groups, rows // groups, 1.0 / 0.07, out, 1.0)
         ctx.groups = groups
         ctx.save_for_backward(q, k)

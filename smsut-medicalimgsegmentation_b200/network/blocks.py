@@ -35,9 +35,8 @@ class Conv2d(nn.Conv2d):
         super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=bias, **kw)
         k = self.kernel_size[0]
         assert self.kernel_size[0] == self.kernel_size[1] and self.groups == 1 and self.dilation == (1, 1)
-        self.tensor_core = (k in (1, 3) and self.stride == (1, 1) and self.padding == (k // 2, k // 2)
-                            and out_channels % 16 == 0 and in_channels >= 8 and not bias and fused_act == ACT_NONE
-                            and not out_f32)
+        self.tensor_core = (k in (1, 3, 5) and self.stride == (1, 1) and self.padding == (k // 2, k // 2)
+                            and out_channels % 8 == 0 and not bias and fused_act == ACT_NONE and not out_f32)
         self.out_pad, self.out_f32, self.fused_act = out_pad, out_f32, fused_act
         self._pw = None
 
@@ -63,9 +62,8 @@ class Conv2d(nn.Conv2d):
                                      self.out_pad, self.out_f32)
 
     def forward(self, x):
-        if self.in_channels == 1 and x.dtype == torch.float32:
-            xin = x.permute(0, 2, 3, 1)
-            xin = xin if xin.is_contiguous() else xin.contiguous()
+        if not self.tensor_core and self.in_channels == 1 and x.dtype == torch.float32:
+            xin = _image_nhwc(x)        # the direct kernel reads the fp32 single-channel image in place
         else:
             xin = to_nhwc(x)
         return to_nchw(self.forward_nhwc([xin]))
@@ -282,8 +280,8 @@ class BottleBlock(nn.Module):
 
 
 def _stem(conv, bn, relu, x):
-    """5x5 stem conv -> IN -> act on an fp32 single-channel image or a prepared NHWC bf16 input; the 8-channel
-    result lives in a 16-channel tensor (channels 8..15 are zero) so the next conv runs on the tensor cores."""
+    """5x5 stem conv (tcgen05, 25 taps over a 16-channel zero-padded bf16 input) -> IN -> act; the 8-channel result
+    lives in a 16-channel tensor (channels 8..15 are zero) so the next conv reads it directly."""
     y = conv.forward_nhwc([x])
     return Fn.in_act(y, bn, act=_act_code(relu), c_params=bn.num_features if y.shape[3] != bn.num_features else None)
 
@@ -297,8 +295,7 @@ def _image_nhwc(x):
 class Encoder(nn.Module):
     def __init__(self, in_ch, block, width=32, norm='batch', act='lrelu', **kwargs):
         super(Encoder, self).__init__()
-        self.pre_conv = Conv2d(in_ch, width // 2, kernel_size=5, stride=1, padding=2, bias=False,
-                               out_pad=ops.pad16(width // 2))
+        self.pre_conv = Conv2d(in_ch, width // 2, kernel_size=5, stride=1, padding=2, bias=False)
         self.pre_bn = get_norm(width // 2, norm)
         self.pre_relu = get_act(act)
 
@@ -314,8 +311,7 @@ class Encoder(nn.Module):
 
     def forward(self, x):
         skips = []
-        xin = _image_nhwc(x) if x.shape[1] == 1 and x.dtype == torch.float32 else to_nhwc(x)
-        h = _stem(self.pre_conv, self.pre_bn, self.pre_relu, xin)
+        h = _stem(self.pre_conv, self.pre_bn, self.pre_relu, to_nhwc(x))
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             h = layer.forward_nhwc([h])
             h, skip = Fn.MaxPoolSkipFn.apply(h)

@@ -23,7 +23,7 @@ class _TslInputFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, m):
-        return ops.build_tsl_input(x.contiguous(), m.contiguous().float(), 8)
+        return ops.build_tsl_input(x.contiguous(), m.contiguous().float(), 16)
 
     @staticmethod
     def backward(ctx, d):
@@ -34,8 +34,7 @@ class Encoder(nn.Module):
     def __init__(self, in_ch, base_width=32, norm_type='batch', act_type='relu'):
         super(Encoder, self).__init__()
         self.pre = nn.Sequential(
-            Conv2d(in_ch, base_width // 2, kernel_size=5, stride=1, padding=2, bias=False,
-                   out_pad=ops.pad16(base_width // 2)),
+            Conv2d(in_ch, base_width // 2, kernel_size=5, stride=1, padding=2, bias=False),
             get_norm(base_width // 2, norm_type),
             get_act(act_type)
         )
@@ -49,7 +48,7 @@ class Encoder(nn.Module):
         self.pool4 = nn.MaxPool2d(2, stride=2)  # x16
 
     def forward_nhwc(self, xin):
-        """xin: (N,H,W,1) fp32 image or the prepared (N,H,W,8) bf16 translation input"""
+        """xin: (N,H,W,16) bf16 zero-padded image (ImageInputFn) or translation input (_TslInputFn)"""
         retn = []
         h = _stem(self.pre[0], self.pre[1], self.pre[2], xin)
         for enc in (self.enc1, self.enc2, self.enc3, self.enc4):
@@ -60,8 +59,7 @@ class Encoder(nn.Module):
         return h, retn
 
     def forward(self, x):
-        xin = _image_nhwc(x) if x.shape[1] == 1 and x.dtype == torch.float32 else to_nhwc(x)
-        h, retn = self.forward_nhwc(xin)
+        h, retn = self.forward_nhwc(to_nhwc(x))
         return to_nchw(h), retn
 
 
@@ -128,7 +126,7 @@ class UGAN(nn.Module):
         tsl_out_1 = self.enc5.forward_nhwc([tsl_out])
         tsl = self.tsl_decoder(to_nchw(tsl_out_1), tsl_ens)
 
-        seg_out, seg_ens = self.seg_encoder.forward_nhwc(_image_nhwc(x))
+        seg_out, seg_ens = self.seg_encoder.forward_nhwc(Fn.ImageInputFn.apply(x))
         seg_out = self.enc5.forward_nhwc([seg_out])
         seg = self.seg_decoder(to_nchw(seg_out), seg_ens)
         return seg, tsl, tsl_out_1

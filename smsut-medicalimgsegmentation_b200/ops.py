@@ -45,6 +45,51 @@ param_generation = [0]
 
 
 # ----------------------------------------------------------------------------------------------
+# zero-initialised scratch (statistics, reduction buffers, loss accumulators)
+# ----------------------------------------------------------------------------------------------
+class _Arena:
+    """One buffer cleared by ONE memset at the start of a training iteration; the hundreds of small zeroed
+    accumulators of the iteration are slices of it (each would otherwise be its own fill launch)."""
+    buf = None
+    off = 0
+    active = False
+
+
+def arena_begin(device, nbytes=48 << 20):
+    if _Arena.buf is None or _Arena.buf.device != torch.device(device) or _Arena.buf.numel() != nbytes:
+        _Arena.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    _Arena.buf.zero_()
+    _Arena.off = 0
+    _Arena.active = True
+
+
+def arena_end():
+    _Arena.active = False
+
+
+def zeros(shape, device, dtype=F32):
+    if isinstance(shape, int):
+        shape = (shape,)
+    n = 1
+    for d in shape:
+        n *= d
+    nbytes = n * (4 if dtype == F32 else 2)
+    if _Arena.active and _Arena.buf.device == torch.device(device) and _Arena.off + nbytes <= _Arena.buf.numel():
+        # a tensor over the arena's storage that is NOT an autograd view of it (own version counter): it can be
+        # saved for backward and returned from Functions while other slices are written in place
+        item = 4 if dtype == F32 else 2
+        strides, acc = [], 1
+        for d in reversed(shape):
+            strides.append(acc)
+            acc *= d
+        t = torch.empty(0, dtype=dtype, device=_Arena.buf.device)
+        t.set_(_Arena.buf.untyped_storage(), _Arena.off // item, tuple(shape), tuple(reversed(strides)))
+        _Arena.off += (nbytes + 255) // 256 * 256
+        return t
+    return torch.zeros(shape, dtype=dtype, device=device)
+
+
+# ----------------------------------------------------------------------------------------------
 # weight packing
 # ----------------------------------------------------------------------------------------------
 class PackedWeight:
@@ -185,16 +230,15 @@ def wgrad_tc(kind, ksize, n, h, w, x, x_c, dy, dy_c, dw, cin_total, ci_off, cout
     call("smsut_wgrad_tc", C.byref(a), _stream())
 
 
-def conv_wgrad(xs, dy, pw):
-    """fp32 OIHW weight gradient of conv_fprop (fresh zeroed tensor)."""
+def conv_wgrad(xs, dy, pw, out=None):
+    """fp32 OIHW weight gradient of conv_fprop, accumulated (atomics) into `out` or a fresh zeroed tensor."""
     n, h, w, _ = xs[0].shape
-    assert pw.cout % 16 == 0, "tensor-core wgrad needs Cout % 16 == 0"
-    dw = torch.zeros_like(pw.weight, dtype=F32)
+    dw = out if out is not None else torch.zeros_like(pw.weight, dtype=F32)
     off = 0
     for x in xs:
         c = x.shape[3]
         valid = min(c, pw.cin - off)
-        wgrad_tc(TC_CONV, pw.kh, n, h, w, x, c, dy, pw.cout, dw, pw.cin, off, pw.cout, c_valid=valid)
+        wgrad_tc(TC_CONV, pw.kh, n, h, w, x, c, dy, pw.cout_pad, dw, pw.cin, off, pw.cout, c_valid=valid)
         off += c
     return dw
 
@@ -215,9 +259,9 @@ def convt_dgrad(dy, pw):
     return dx
 
 
-def convt_wgrad(x, dy, pw):
+def convt_wgrad(x, dy, pw, out=None):
     n, h, w, c = x.shape
-    dw = torch.zeros_like(pw.weight, dtype=F32)
+    dw = out if out is not None else torch.zeros_like(pw.weight, dtype=F32)
     wgrad_tc(TC_CONVT_FWD, 1, n, h, w, x, c, dy, pw.cout, dw, pw.cin, 0, pw.cout)
     return dw
 
@@ -262,9 +306,25 @@ def conv_direct_dgrad(dy, weight, x_shape, x_dtype, stride, pad):
     return dx
 
 
-def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias):
-    dw = torch.zeros_like(weight, dtype=F32)
-    db = torch.zeros(weight.shape[0], dtype=F32, device=weight.device) if want_bias else None
+def head1x1_bwd(x, dy, y, weight, want_dx, dw=None, db=None, want_bias=False):
+    """fused backward of a 1x1 head: returns dx (bf16 or None), dW, dbias"""
+    n, h, w, c = _chk(x, BF16, "head x").shape
+    cout = weight.shape[0]
+    dx = torch.empty_like(x) if want_dx else None
+    dw = dw if dw is not None else torch.zeros_like(weight, dtype=F32)
+    if want_bias and db is None:
+        db = torch.zeros(cout, dtype=F32, device=x.device)
+    call("smsut_head1x1_bwd", _p(x), _p(_chk(dy, F32, "head dy")), _p(y), _p(weight), _p(dx), _p(dw), _p(db), n * h * w, c,
+         cout, _stream())
+    return dx, dw, db
+
+
+def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias, dw=None, db=None):
+    dw = dw if dw is not None else torch.zeros_like(weight, dtype=F32)
+    if want_bias and db is None:
+        db = torch.zeros(weight.shape[0], dtype=F32, device=weight.device)
+    if not want_bias:
+        db = None
     a = _direct_args(x, weight, dy, stride, pad, None, ACT_NONE, 0.0, False)
     call("smsut_conv_direct_wgrad", C.byref(a), _p(dw), _p(db), _stream())
     return dw, db
@@ -275,7 +335,7 @@ def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias):
 # ----------------------------------------------------------------------------------------------
 def in_stats(x):
     n, h, w, c = _chk(x, BF16, "in_stats x").shape
-    stats = torch.zeros((n, 2, c), dtype=F32, device=x.device)
+    stats = zeros((n, 2, c), x.device)
     call("smsut_in_stats", _p(x), n, h * w, c, _p(stats), _stream())
     return stats
 
@@ -288,28 +348,35 @@ def in_apply(xa, sa, ga, ba, xb=None, sb=None, gb=None, bb=None, res=None, act=A
     return out
 
 
-def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=ACT_NONE, slope=0.01, c_params=None):
-    """returns dxa, dgamma_a, dbeta_a, dxb, dgamma_b, dbeta_b, dres"""
+def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=ACT_NONE, slope=0.01, c_params=None,
+           targets=None):
+    """returns dxa, dgamma_a, dbeta_a, dxb, dgamma_b, dbeta_b, dres.  `targets` = (dga, dba, dgb, dbb) fp32 tensors the
+    parameter gradients are accumulated INTO (the flat .grad views); they are then returned as None."""
     n, h, w, c = xa.shape
     cp = c if c_params is None else c_params
     dev = xa.device
-    red = torch.zeros((n, 3, c), dtype=F32, device=dev)
+    red = zeros((n, 3, c), dev)
     call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(xb), _p(sb), _p(red), n, h * w, c, act, slope,
          _stream())
     dxa = torch.empty_like(xa)
-    pg = torch.zeros((4, cp), dtype=F32, device=dev)
     dxb = torch.empty_like(xa) if xb is not None else None
     dres = torch.empty_like(xa) if want_res else None
-    call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(dxa), _p(pg[0]), _p(pg[1]), _p(xb), _p(sb),
-         _p(gb), _p(dxb), _p(pg[2]) if xb is not None else _p(None), _p(pg[3]) if xb is not None else _p(None),
-         _p(dres), _p(red), n, h * w, c, cp, act, slope, _stream())
-    return dxa, pg[0], pg[1], dxb, (pg[2] if xb is not None else None), (pg[3] if xb is not None else None), dres
+    if targets is not None:
+        t = list(targets)
+        ret = [None, None, None, None]
+    else:
+        pg = zeros((4, cp), dev)
+        t = [pg[0], pg[1], pg[2] if xb is not None else None, pg[3] if xb is not None else None]
+        ret = t
+    call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(dxa), _p(t[0]), _p(t[1]), _p(xb), _p(sb),
+         _p(gb), _p(dxb), _p(t[2]), _p(t[3]), _p(dres), _p(red), n, h * w, c, cp, act, slope, _stream())
+    return dxa, ret[0], ret[1], dxb, ret[2], ret[3], dres
 
 
 def in_bwd2(u, dy, x, stats, gamma):
     """double backward of plain InstanceNorm: returns g_dy, g_x, dgamma"""
     n, h, w, c = x.shape
-    red2 = torch.zeros((n, 5, c), dtype=F32, device=x.device)
+    red2 = zeros((n, 5, c), x.device)
     call("smsut_in_bwd2_reduce", _p(u), _p(dy), _p(x), _p(stats), _p(red2), n, h * w, c, _stream())
     g_dy, g_x = torch.empty_like(x), torch.empty_like(x)
     dgamma = torch.zeros(c, dtype=F32, device=x.device)

@@ -64,6 +64,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
         lambda_cls, lambda_gp = self.lambda_cls, self.lambda_gp
         lambda_seg, lambda_rec = self.lambda_seg, self.lambda_rec
         bs = y_real.shape[0]
+        ops.arena_begin(x_real.device)      # one memset serves every zeroed accumulator of the iteration
         self.lr_sched.tick()
 
         # generator forward shared by the D phase (detached) and the G phase
@@ -84,7 +85,8 @@ class UGANConsisTrainer(UGANShp0Trainer):
 
         d_loss = d_loss_real + d_loss_fake + lambda_cls * d_loss_cls + lambda_gp * d_loss_gp
         self.d_optimizer.zero_grad()
-        d_loss.backward()
+        with Fn.accumulate_param_grads():   # wgrad kernels add straight into the flat gradient buffer
+            d_loss.backward()
         if self.parallel is not None:
             self.parallel.all_reduce_grads(self.d_optimizer)
         self.d_optimizer.step()
@@ -116,11 +118,13 @@ class UGANConsisTrainer(UGANShp0Trainer):
             lambda_semi * g_loss_semi + \
             1.0 * g_loss_nce
         self.optimizer.zero_grad()
-        g_loss.backward()
+        with Fn.accumulate_param_grads():
+            g_loss.backward()
         if self.parallel is not None:
             self.parallel.all_reduce_grads(self.optimizer)
         self.optimizer.step()
 
+        ops.arena_end()
         return torch.stack([d_loss_real.detach(), d_loss_fake.detach(), d_loss_cls.detach(), d_loss_gp.detach(),
                             g_loss_fake.detach(), g_loss_rec.detach(), g_loss_cls.detach(), g_loss_seg.detach(),
                             g_loss_semi.detach(), g_loss_nce.detach()])

@@ -15,6 +15,8 @@ import numpy as np
 import torch
 
 from .. import config as cfg
+from .. import functional as Fn
+from .. import ops
 from ..network.unet import UNet
 from ..optim import SGD, PolyLR
 from .baseTrainer import BaseTrainer
@@ -34,16 +36,19 @@ class UnetTrainer(BaseTrainer):
 
     def train_step(self, img, msk):
         """One iteration of unetTrainer.py:71-85 on device tensors; returns the loss as a device scalar."""
+        ops.arena_begin(img.device)
         self.lr_sched.tick()
         out = self.net(img)
         sample_loss = self.loss(out, msk)
         self.optimizer.zero_grad()
-        sample_loss.backward()
+        with Fn.accumulate_param_grads():
+            sample_loss.backward()
         if self.parallel is not None:
             self.parallel.all_reduce_grads(self.optimizer)
         self.optimizer.step()
+        ops.arena_end()
         self.iter += 1
-        return sample_loss.detach()
+        return sample_loss.detach().clone()
 
     def train_epoch(self, lb_loader, ul_loader, meter, num_iter=None):
         self.net.train()

@@ -97,9 +97,16 @@ def conv_dgrad_accumulate(dy, pw, dxs):
         off += c
 
 
-def conv_wgrad(xs, dy, pw):
+def _acc(out, g):
+    if out is None:
+        return g
+    out += g.view_as(out)
+    return out
+
+
+def conv_wgrad(xs, dy, pw, out=None):
     x = torch.cat([_nchw(t) for t in xs], 1)[:, :pw.cin]
-    return torch.nn.grad.conv2d_weight(x, pw.weight.shape, _nchw(dy)[:, :pw.cout], padding=pw.kh // 2)
+    return _acc(out, torch.nn.grad.conv2d_weight(x, pw.weight.shape, _nchw(dy)[:, :pw.cout], padding=pw.kh // 2))
 
 
 def convt_fprop(x, pw):
@@ -110,11 +117,11 @@ def convt_dgrad(dy, pw):
     return _nhwc(F.conv2d(_nchw(dy), _wq(pw), stride=2))
 
 
-def convt_wgrad(x, dy, pw):
+def convt_wgrad(x, dy, pw, out=None):
     with torch.enable_grad():
         w = pw.weight.detach().clone().requires_grad_(True)
         F.conv_transpose2d(_nchw(x), w, stride=2).backward(_nchw(dy))
-    return w.grad
+    return _acc(out, w.grad)
 
 
 def direct_out_hw(h, w, k, stride, pad):
@@ -137,11 +144,21 @@ def conv_direct_dgrad(dy, weight, x_shape, x_dtype, stride, pad):
     return _pad_c(_nhwc(g[:, :live], F32), ld).to(x_dtype)
 
 
-def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias):
+def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias, dw=None, db=None):
     cout, cin = weight.shape[:2]
     g = _nchw(dy)[:, :cout]
-    dw = torch.nn.grad.conv2d_weight(_nchw(x)[:, :cin], weight.shape, g, stride=stride, padding=pad)
-    return dw, (g.sum((0, 2, 3)) if want_bias else None)
+    gw = torch.nn.grad.conv2d_weight(_nchw(x)[:, :cin], weight.shape, g, stride=stride, padding=pad)
+    return _acc(dw, gw), (_acc(db, g.sum((0, 2, 3))) if want_bias else None)
+
+
+def head1x1_bwd(x, dy, y, weight, want_dx, dw=None, db=None, want_bias=False):
+    g = dy.float()
+    if y is not None:
+        g = g * (1 - y * y)
+    w2 = weight.detach().view(weight.shape[0], -1)
+    dx = (g @ w2).to(_AD.t) if want_dx else None
+    gw = torch.einsum("nhwo,nhwc->oc", g, x.float()).view_as(weight)
+    return dx, _acc(dw, gw), (_acc(db, g.sum((0, 1, 2))) if want_bias else None)
 
 
 def in_stats(x):
@@ -181,7 +198,8 @@ def _in_bwd_one(g, x, stats, gamma, c):
     return dx, (g * xh).sum((0, 1, 2)), g.sum((0, 1, 2))
 
 
-def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=0, slope=0.01, c_params=None):
+def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=0, slope=0.01, c_params=None,
+           targets=None):
     c = xa.shape[3]
     cp = c if c_params is None else c_params
     g = dout.float()
@@ -192,7 +210,14 @@ def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act
     if xb is not None:
         dxb, dgb, dbb = _in_bwd_one(g, xb, sb, gb, c)
         dxb, dgb, dbb = dxb.to(_AD.t), dgb[:cp].clone(), dbb[:cp].clone()
-    return dxa.to(_AD.t), dga[:cp].clone(), dba[:cp].clone(), dxb, dgb, dbb, (g.to(_AD.t) if want_res else None)
+    dres = g.to(_AD.t) if want_res else None
+    if targets is not None:
+        if targets[0] is not None:
+            targets[0].add_(dga[:cp]); targets[1].add_(dba[:cp])
+        if xb is not None and targets[2] is not None:
+            targets[2].add_(dgb); targets[3].add_(dbb)
+        return dxa.to(_AD.t), None, None, dxb, None, None, dres
+    return dxa.to(_AD.t), dga[:cp].clone(), dba[:cp].clone(), dxb, dgb, dbb, dres
 
 
 def in_bwd2(u, dy, x, stats, gamma):

@@ -420,3 +420,46 @@ def test_optimisers(ops):
         got.append(lro.item())
     want = [1e-2 * (1 - max(k - 1, 0) / 30000.0) ** 0.9 for k in range(4)]
     assert max(abs(a - b) for a, b in zip(got, want)) < 1e-8
+
+
+@pytest.mark.parametrize("cin", [1, 5])
+def test_stem_5x5_on_tensor_cores(ops, cin):
+    """5x5 stem (network/ugan.py:26): Cin in {1,5} zero-padded to 16 channels, Cout = 8 padded to 16"""
+    n, h, cout = 2, 128, 8
+    x = rnd(n, cin, h, h, seed=14)
+    wt = rnd(cout, cin, 5, 5, scale=0.1)
+    pw = make_pack(ops, wt)
+    assert pw.cin_pad == 16 and pw.cout_pad == 16
+    xp = nhwc(F.pad(x, (0, 0, 0, 0, 0, 16 - cin)))
+    y = ops.conv_fprop([xp], pw)
+    y_ref = F.conv2d(x, wt, padding=2)
+    assert rel(nchw(y)[:, :cout], y_ref) < 1e-2 and y[..., cout:].abs().max().item() == 0
+    dy = F.pad(rnd(n, cout, h, h), (0, 0, 0, 0, 0, 16 - cout))
+    dx = nchw(ops.conv_dgrad(nhwc(dy), pw)[0])
+    assert rel(dx[:, :cin], torch.nn.grad.conv2d_input(x.shape, wt, dy[:, :cout], padding=2)) < 1e-2
+    assert dx[:, cin:].abs().max().item() == 0
+    dw = ops.conv_wgrad([xp], nhwc(dy), pw)
+    assert dw.shape == wt.shape
+    assert rel(dw, torch.nn.grad.conv2d_weight(x, wt.shape, dy[:, :cout], padding=2)) < 1e-2
+    acc = torch.ones_like(wt)
+    ops.conv_wgrad([xp], nhwc(dy), pw, out=acc)          # accumulate-into-grad form
+    assert rel(acc - 1, dw) < 1e-5
+
+
+@pytest.mark.parametrize("cout,tanh", [(5, False), (1, True)])
+def test_fused_head_backward(ops, cout, tanh):
+    torch.manual_seed(15)
+    n, h = 2, 64
+    x = rnd(n, 16, h, h)
+    wt = torch.randn(cout, 16, 1, 1, device=DEV) * 0.3
+    b = torch.randn(cout, device=DEV)
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, br)
+    y_ref = torch.tanh(y_ref) if tanh else y_ref
+    dy = torch.randn_like(y_ref)
+    y_ref.backward(dy)
+    y = ops.conv_direct_fprop(nhwc(x), wt, 1, 0, bias=b, act=ops.ACT_TANH if tanh else ops.ACT_NONE, out_f32=True)
+    assert rel(nchw(y), y_ref) < 1e-4
+    dx, dw, db = ops.head1x1_bwd(nhwc(x), dy.permute(0, 2, 3, 1).contiguous(), y if tanh else None, wt, True,
+                                 want_bias=True)
+    assert rel(nchw(dx), xr.grad) < 1e-2 and rel(dw, wr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
