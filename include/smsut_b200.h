@@ -191,6 +191,11 @@ int smsut_dice_ce_finish(const float* acc, float* loss, int64_t npix_total, int3
 int smsut_dice_ce_bwd(const float* logits, const int64_t* labels, const float* label_logits, const float* acc,
                       const float* gscale, float scale, float* dlogits, int64_t npix, int64_t npix_total, int32_t c,
                       float w_dc, float w_ce, smsut_stream_t stream);
+/* out[0] += mean over (pixels, classes) of (softmax(zs) - softmax(zt))^2; dzs = gscale * d/dzs (zt is constant):
+ * the mean-teacher consistency term (trainer/meanTeacherTrainer.py:124-130).  fp32 (npix, c) logits. */
+int smsut_softmax_mse_fwd(const float* zs, const float* zt, float* out, int64_t npix, int32_t c, smsut_stream_t stream);
+int smsut_softmax_mse_bwd(const float* zs, const float* zt, const float* gscale, float* dzs, int64_t npix, int32_t c,
+                          smsut_stream_t stream);
 /* argmax over channels -> int64 (n,h,w)  (trainer/uganConsisTrainer.py:52, trainer/baseTrainer.py:230) */
 int smsut_argmax_c(const float* logits, int64_t* out, int64_t npix, int32_t c, smsut_stream_t stream);
 /* out[0] += scale * sum|a-b| ; dA = gscale*scale*sign(a-b) */

@@ -456,3 +456,20 @@ def ema_update(ema, sd, alpha):
     with torch.no_grad():
         for k in ema:
             ema[k].mul_(alpha).add_(sd[k], alpha=1 - alpha)
+
+
+def mean_teacher_step(sd, ema, opt_state, x, y, noise, lr, it, lambda_semi, warm=100):
+    """trainer/meanTeacherTrainer.py:95-153: student on 2*bs slices, EMA teacher (no grad) on the noisy unlabelled half,
+    Dice+CE on the labelled half + lambda * mean((softmax_s - softmax_t)^2) once it >= warm, SGD, EMA update."""
+    bs = y.shape[0]
+    leaf = _leaf(sd)
+    out = unet_forward(leaf, x)
+    with torch.no_grad():
+        t_soft = torch.softmax(unet_forward(ema, x[bs:] + noise), 1)
+    seg = dice_ce_loss(out[:bs], y)
+    semi = torch.zeros((), device=x.device) if it < warm else ((torch.softmax(out, 1)[bs:] - t_soft) ** 2).mean()
+    total = seg + lambda_semi * semi
+    grads = dict(zip(leaf, torch.autograd.grad(total, list(leaf.values()))))
+    sgd_update(sd, grads, opt_state, lr)
+    ema_update(ema, sd, ema_alpha(it, warm=warm))
+    return float(seg.detach()), float(semi.detach())

@@ -87,6 +87,8 @@ _PROTOS = {
     "smsut_dice_ce_fwd": [P, P, P, P, c_int64, c_int, P],
     "smsut_dice_ce_finish": [P, P, c_int64, c_int, c_float, c_float, P],
     "smsut_dice_ce_bwd": [P, P, P, P, P, c_float, P, c_int64, c_int64, c_int, c_float, c_float, P],
+    "smsut_softmax_mse_fwd": [P, P, P, c_int64, c_int, P],
+    "smsut_softmax_mse_bwd": [P, P, P, P, c_int64, c_int, P],
     "smsut_argmax_c": [P, P, c_int64, c_int, P],
     "smsut_l1_fwd": [P, P, P, c_int64, c_float, P],
     "smsut_l1_bwd": [P, P, P, c_float, P, c_int64, P],

@@ -186,6 +186,35 @@ dice_ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict
   }
 }
 
+// mean over (pixels, classes) of (softmax(zs) - softmax(zt))^2 : mean-teacher consistency
+// (trainer/meanTeacherTrainer.py:124-130).  The teacher logits are constants.
+template <int C, bool BWD>
+__global__ void __launch_bounds__(256)
+softmax_mse_kernel(const float* __restrict__ zs, const float* __restrict__ zt, float* __restrict__ out,
+                   const float* __restrict__ gscale, float scale, float* __restrict__ dzs, long long npix) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  const float gs = BWD ? (gscale ? gscale[0] : 1.f) * scale * 2.f : 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    float a[C], b[C], p[C], t[C], lse;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { a[c] = zs[i * C + c]; b[c] = zt[i * C + c]; }
+    softmax_c<C>(a, p, lse);
+    softmax_c<C>(b, t, lse);
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { const float d = p[c] - t[c]; acc = fmaf(d, d, acc); dot = fmaf(d, p[c], dot); }
+    if (BWD) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) dzs[i * C + c] = gs * p[c] * ((p[c] - t[c]) - dot);
+    }
+  }
+  if (!BWD) {
+    const float r = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(out, r * scale);
+  }
+}
+
 template <int C>
 __global__ void argmax_kernel(const float* __restrict__ logits, long long* __restrict__ out, long long npix) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
@@ -480,6 +509,24 @@ extern "C" int smsut_dice_ce_bwd(const float* logits, const int64_t* labels, con
                     1.f / (float)npix_total, w_dc, w_ce)));
   count_launch();
   return launch_status("dice_ce_bwd_kernel");
+}
+extern "C" int smsut_softmax_mse_fwd(const float* zs, const float* zt, float* out, int64_t npix, int32_t c,
+                                     smsut_stream_t st) {
+  const int grid = grid_for(npix);
+  const float scale = 1.f / ((float)npix * (float)c);
+  DISPATCH_C(c, (softmax_mse_kernel<C_, false><<<grid, 256, 0, (cudaStream_t)st>>>(zs, zt, out, nullptr, scale,
+                                                                                 nullptr, npix)));
+  count_launch();
+  return launch_status("softmax_mse_fwd_kernel");
+}
+extern "C" int smsut_softmax_mse_bwd(const float* zs, const float* zt, const float* gscale, float* dzs, int64_t npix,
+                                     int32_t c, smsut_stream_t st) {
+  const int grid = grid_for(npix);
+  const float scale = 1.f / ((float)npix * (float)c);
+  DISPATCH_C(c, (softmax_mse_kernel<C_, true><<<grid, 256, 0, (cudaStream_t)st>>>(zs, zt, nullptr, gscale, scale, dzs,
+                                                                                npix)));
+  count_launch();
+  return launch_status("softmax_mse_bwd_kernel");
 }
 extern "C" int smsut_argmax_c(const float* logits, int64_t* out, int64_t npix, int32_t c, smsut_stream_t st) {
   const int grid = grid_for(npix);

@@ -459,6 +459,22 @@ class DiceCEFn(Function):
         return d, None, None, None, None
 
 
+class SoftmaxMSEFn(Function):
+    """mean((softmax(zs) - softmax(zt))**2) with gradient to zs (trainer/meanTeacherTrainer.py:124-130)"""
+
+    @staticmethod
+    def forward(ctx, zs, zt):
+        out = ops.zeros(1, zs.device)
+        ops.softmax_mse_fwd(zs, zt, out)
+        ctx.save_for_backward(zs, zt)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        zs, zt = ctx.saved_tensors
+        return ops.softmax_mse_bwd(zs, zt, _c(g).view(1)), None
+
+
 class L1MeanFn(Function):
     """mean |a - b| with gradient to a (g_loss_rec, trainer/uganConsisTrainer.py:162)"""
 

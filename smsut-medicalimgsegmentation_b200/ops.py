@@ -500,6 +500,17 @@ def dice_ce_bwd(logits, labels, label_logits, acc, gscale, scale, npix_total, w_
     return d
 
 
+def softmax_mse_fwd(zs, zt, out):
+    npix, c = zs.shape
+    call("smsut_softmax_mse_fwd", _p(_chk(zs, F32, "mse zs")), _p(_chk(zt, F32, "mse zt")), _p(out), npix, c, _stream())
+
+
+def softmax_mse_bwd(zs, zt, gscale):
+    d = torch.empty_like(zs)
+    call("smsut_softmax_mse_bwd", _p(zs), _p(zt), _p(gscale), _p(d), zs.shape[0], zs.shape[1], _stream())
+    return d
+
+
 def argmax_c(logits):
     npix, c = logits.shape
     out = torch.empty(npix, dtype=torch.int64, device=logits.device)

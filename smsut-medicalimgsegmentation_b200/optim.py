@@ -11,6 +11,23 @@ import torch
 from . import ops
 
 
+class FlatParams:
+    """Re-homes a parameter list into one flat fp32 buffer (no gradients): the EMA teacher's weights."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p, sz in zip(self.params, sizes):
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)
+                off += sz
+
+
 class _FlatOptimizer:
     def __init__(self, params, lr):
         self.params = [p for p in params]

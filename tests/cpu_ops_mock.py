@@ -499,7 +499,8 @@ def installed(exact=False):
                 return f(*[det(v) for v in a], **{n: det(v) for n, v in k.items()})
         return run
 
-    for n in _NAMES:
+    names = [n for n, v in list(me.items()) if callable(v) and not n.startswith("_") and n not in ("contextlib", "installed")]
+    for n in names:
         if hasattr(ops, n):
             saved[n] = getattr(ops, n)
             setattr(ops, n, me[n] if isinstance(me[n], type) else opaque(me[n]))
@@ -509,3 +510,14 @@ def installed(exact=False):
         _AD.t, functional.BF16 = prev_adt, prev_fbf
         for n, v in saved.items():
             setattr(ops, n, v)
+
+
+def softmax_mse_fwd(zs, zt, out):
+    out += ((torch.softmax(zs, 1) - torch.softmax(zt, 1)) ** 2).mean()
+
+
+def softmax_mse_bwd(zs, zt, gscale):
+    with torch.enable_grad():
+        z = zs.detach().clone().requires_grad_(True)
+        ((torch.softmax(z, 1) - torch.softmax(zt.detach(), 1)) ** 2).mean().backward()
+    return z.grad * gscale

@@ -175,3 +175,26 @@ def test_bf16_double_tracks_oracle_within_tolerance(pkg):
         net.load_state_dict(sd)
         x, _ = O.synthetic_batch(2, 64, 3)
         assert rel(net(x), O.unet_forward(sd, x)) < 3e-2
+
+
+def test_mean_teacher_steps_match_oracle(exact):
+    from types import SimpleNamespace
+    from smsut_b200.trainer.meanTeacherTrainer import MeanTeacherTrainer
+    tr = MeanTeacherTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=64))
+    tr.semi_from_iter = 1
+    sd, ema = O.make_weights(O.unet_shapes(), 31), O.make_weights(O.unet_shapes(), 32)
+    tr.net.load_state_dict(sd)
+    tr.ema.load_state_dict(ema)
+    st = {}
+    for it in range(3):
+        x1, y = O.synthetic_batch(2, 64, 40 + it)
+        x2, _ = O.synthetic_batch(2, 64, 50 + it)
+        x = torch.cat([x1, x2])
+        noise = torch.clamp(torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(it)) * 0.01, -0.02, 0.02)
+        got = tr.train_step(x, y, noise, 0.8).tolist()
+        ref = O.mean_teacher_step(sd, ema, st, x, y, noise, O.poly_lr(1e-2, max(it - 1, 0), 30000), it, 0.8, warm=1)
+        assert abs(got[0] - ref[0]) < 1e-4 and abs(got[1] - ref[1]) < 1e-5, (it, got, ref)
+        for k, p in tr.net.named_parameters():
+            assert rel(p, sd[k]) < 1e-3, (it, k)
+        for k, p in tr.ema.named_parameters():
+            assert rel(p, ema[k]) < 1e-3, (it, k)
