@@ -17,6 +17,7 @@
 // Reference semantics: network/blocks.py:10-16 (conv3x3/conv1x1), :41 (ConvTranspose2d k2 s2),
 // :50 (torch.cat eliminated by the two-source K loop), network/ugan.py:295 (Linear).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/smsut_b200.h"
@@ -57,6 +58,7 @@ struct ConvTcParams {
   const float* bias;
   int act; float slope;
   int accumulate, out_f32;
+  int dbg_rowshift;        // experiment: load the A tile one pixel to the left and start the descriptor one row later
   KStep steps[kMaxSteps];
 };
 
@@ -165,7 +167,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         void* a_dst = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * p.stage_bytes;
         void* b_dst = (uint8_t*)a_dst + p.a_bytes;
         const CUtensorMap* m = st.map == 0 ? &map_a0 : (st.map == 1 ? &map_a1 : (st.map == 2 ? &map_a2 : &map_a3));
-        tma_load_4d(a_dst, m, &full_bar[stage], st.c0, w0 + st.dx, h0 + st.dy, n0);
+        tma_load_4d(a_dst, m, &full_bar[stage], st.c0, w0 + st.dx - (p.dbg_rowshift ? 1 : 0), h0 + st.dy, n0);
         tma_load_2d(b_dst, &map_w, &full_bar[stage], st.k, col0);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
@@ -184,7 +186,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const uint32_t b_addr = a_addr + p.a_bytes;
         const int kk = p.cc >> 4;
         for (int k = 0; k < kk; ++k) {
-          const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, p.sbo, p.layout_type);
+          uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, p.sbo, p.layout_type);
+          if (p.dbg_rowshift) {
+            const uint32_t sa = a_addr + (uint32_t)p.cc * 2u + k * 32;   // one row (= cc*2 bytes) further
+            adesc = make_smem_desc(sa, 16, p.sbo, p.layout_type);
+            if (p.dbg_rowshift == 2) adesc |= (uint64_t)((sa >> 7) & 7u) << 49;
+          }
           const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, p.sbo, p.layout_type);
           umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
         }
@@ -475,6 +482,10 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   p.ncols = a->ncols;
   p.bias = a->bias; p.act = a->act; p.slope = a->slope;
   p.accumulate = a->accumulate; p.out_f32 = a->out_f32;
+  {
+    const char* e = getenv("SMSUT_DEBUG_ROWSHIFT");
+    p.dbg_rowshift = e ? atoi(e) : 0;
+  }
   SMSUT_CHECK(a->out0 != nullptr, -1, "null output");
   if (!a->out_f32)
     SMSUT_CHECK(a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 || a->ncols < 16, -1, "bf16 output pitch/offset must be multiples of 8");

@@ -267,7 +267,9 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   p.nblk_total = nb;
   p.blk_per_group = 256 / bc;
   if (p.blk_per_group > nb) p.blk_per_group = nb;
-  const int ngroups = (nb + p.blk_per_group - 1) / p.blk_per_group;
+  int ngroups = (nb + p.blk_per_group - 1) / p.blk_per_group;
+  p.blk_per_group = (nb + ngroups - 1) / ngroups;   // balance the column groups (e.g. 9 blocks -> 5 + 4, not 8 + 1)
+  ngroups = (nb + p.blk_per_group - 1) / p.blk_per_group;
   const int mblocks = (a_c + 127) / 128;
 
   uint32_t tc = 32;
