@@ -1,0 +1,339 @@
+// "Band" implicit-GEMM convolution for the wide, narrow-channel layers (W % 128 == 0, C in {16, 32, 64} per
+// source): the layers whose tap-by-tap TMA re-reads made conv_tc_kernel L2-bound (ncu: 340 MB of L2->SM traffic
+// for a 33 MB input, 43 % LTS throughput, 6 % DRAM).
+//
+// One CTA walks down a strip of 128 pixels x R output rows of one image.  Every input row of the strip (with its
+// +-r pixel halo, r = ksize/2) is fetched by TMA ONCE into a ring of row slots; the (2r+1)^2 taps are formed from
+// the ring purely by shared-memory descriptor arithmetic: a vertical tap picks another slot, a horizontal tap
+// starts the K-major A descriptor (dx + r) rows later (the swizzle phase follows the absolute smem address, so a
+// row-shifted start reads the bytes TMA wrote -- verified on hardware with scripts/rowshift_probe.py).  All
+// weights of the layer stay resident in shared memory for the CTA's lifetime.  Accumulators are double-buffered in
+// TMEM so the epilogue of row h overlaps the MMAs of row h+1.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue.
+// L2->SM traffic per output row: (128 + 2r) * C * 2 bytes instead of (2r+1)^2 * 128 * C * 2.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/smsut_b200.h"
+#include "common.cuh"
+
+namespace smsut {
+
+void count_launch();
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_act_map(CUtensorMap* m, const void* ptr, int c, int w, int h, int n, int64_t sw, int64_t sh, int64_t sn,
+                 int cc, int tw, int th, int tn);
+int make_mat_map(CUtensorMap* m, const void* ptr, int64_t kdim, int64_t rows, int64_t ld, int cc, int rows_box);
+
+constexpr int kBandThreads = 192;
+constexpr int kBandMaxSlots = 12;
+
+struct BandParams {
+  int n, h, w;
+  int ks, r;               // kernel size, radius
+  int nsrc, cc;            // sources, channels per source (16 / 32 / 64)
+  int ctot;                // nsrc * cc
+  int ncols, ncols_pad;    // valid / padded GEMM columns (<= 256)
+  int wtiles, segs, rows_per_seg;
+  int nslots;
+  uint32_t slot_bytes, src_bytes;     // bytes of one ring slot / of one source inside it (1024-aligned)
+  uint32_t wtile_bytes;               // bytes of one (tap, source) weight tile
+  uint32_t w_bytes;                   // all weights
+  uint32_t layout_type, sbo, pitch;
+  uint32_t tmem_cols, acc_cols;
+  // epilogue (same contract as conv_tc_kernel, mode 0)
+  void* out0; int ld0, coff0;
+  void* out1; int ld1, coff1, split;
+  const float* bias;
+  int act; float slope;
+  int accumulate, out_f32;
+};
+
+__device__ __forceinline__ void band_store16(void* base, size_t off, const float* v, int nvalid, bool f32,
+                                             bool accumulate) {
+  if (f32) {
+    float* dst = reinterpret_cast<float*>(base) + off;
+    for (int i = 0; i < nvalid; ++i) dst[i] = accumulate ? dst[i] + v[i] : v[i];
+    return;
+  }
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base) + off;
+  if (nvalid == 16) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = v[i];
+    uint4* p = reinterpret_cast<uint4*>(dst);
+    if (accumulate) {
+      float o[8];
+      unpack8(p[0], o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += o[i];
+      unpack8(p[1], o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[8 + i] += o[i];
+    }
+    p[0] = pack8(f);
+    p[1] = pack8(f + 8);
+  } else {
+    for (int i = 0; i < nvalid; ++i) dst[i] = f2bf(accumulate ? bf2f(dst[i]) + v[i] : v[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kBandThreads, 1)
+conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ BandParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t slot_full[kBandMaxSlots];
+  __shared__ __align__(8) uint64_t slot_empty[kBandMaxSlots];
+  __shared__ __align__(8) uint64_t w_full;
+  __shared__ __align__(8) uint64_t tmem_full[2];
+  __shared__ __align__(8) uint64_t tmem_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t ring_base = smem_base + ((p.w_bytes + 1023u) & ~1023u);
+  uint8_t* ring_ptr = smem_al + ((p.w_bytes + 1023u) & ~1023u);
+
+  // strip coordinates
+  int b = blockIdx.x;
+  const int seg = b % p.segs; b /= p.segs;
+  const int wt = b % p.wtiles; b /= p.wtiles;
+  const int n = b;
+  const int w0 = wt * 128;
+  const int h_begin = seg * p.rows_per_seg;
+  int h_end = h_begin + p.rows_per_seg;
+  if (h_end > p.h) h_end = p.h;
+  const int nrows_out = h_end - h_begin;
+  const int nrows_in = nrows_out + 2 * p.r;
+  const int ntaps = p.ks * p.ks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    tma_prefetch_desc(&map_w);
+    for (int s = 0; s < p.nslots; ++s) {
+      mbar_init(&slot_full[s], 1);
+      mbar_init(&slot_empty[s], 1);
+    }
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // resident weights: one tile per (tap, source), K coordinate = tap * ctot + source * cc
+      mbar_arrive_expect_tx(&w_full, p.w_bytes);
+      for (int t = 0; t < ntaps; ++t)
+        for (int s = 0; s < p.nsrc; ++s)
+          tma_load_2d(smem_al + (size_t)(t * p.nsrc + s) * p.wtile_bytes, &map_w, &w_full, t * p.ctot + s * p.cc, 0);
+      // input rows h_begin - r .. h_end - 1 + r, each fetched once (out-of-image rows / halo pixels: TMA zero fill)
+      for (int j = 0; j < nrows_in; ++j) {
+        const int slot = j % p.nslots;
+        const uint32_t phase = (uint32_t)(j / p.nslots) & 1u;
+        mbar_wait(&slot_empty[slot], phase ^ 1u);
+        mbar_arrive_expect_tx(&slot_full[slot], (uint32_t)p.nsrc * (uint32_t)(128 + 2 * p.r) * p.pitch);
+        uint8_t* dst = ring_ptr + (size_t)slot * p.slot_bytes;
+        const int hin = h_begin - p.r + j;
+        tma_load_4d(dst, &map_a0, &slot_full[slot], 0, w0 - p.r, hin, n);
+        if (p.nsrc == 2) tma_load_4d(dst + p.src_bytes, &map_a1, &slot_full[slot], 0, w0 - p.r, hin, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc =
+        (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ncols_pad >> 3) << 17) | ((128u >> 4) << 24);
+    mbar_wait(&w_full, 0);
+    int rows_ready = 0;   // input rows whose slot_full barrier has been consumed
+    for (int i = 0; i < nrows_out; ++i) {
+      const int buf = i & 1;
+      const uint32_t use = (uint32_t)(i >> 1);
+      mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
+      // output row i needs input rows i .. i + 2r (indices relative to the strip's first input row)
+      while (rows_ready <= i + 2 * p.r) {
+        mbar_wait(&slot_full[rows_ready % p.nslots], (uint32_t)(rows_ready / p.nslots) & 1u);
+        ++rows_ready;
+      }
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)buf * p.acc_cols;
+        uint32_t first = 1;
+        const int kk = p.cc >> 4;
+        for (int ty = 0; ty < p.ks; ++ty) {
+          const uint32_t slot_addr = ring_base + (uint32_t)((i + ty) % p.nslots) * p.slot_bytes;
+          for (int tx = 0; tx < p.ks; ++tx) {
+            const int t = ty * p.ks + tx;
+            for (int s = 0; s < p.nsrc; ++s) {
+              const uint32_t a_addr = slot_addr + (uint32_t)s * p.src_bytes + (uint32_t)tx * p.pitch;
+              const uint32_t b_addr = smem_base + (uint32_t)(t * p.nsrc + s) * p.wtile_bytes;
+              for (int k = 0; k < kk; ++k) {
+                const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, p.sbo, p.layout_type);
+                const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, p.sbo, p.layout_type);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+          }
+        }
+        umma_commit(&tmem_full[buf]);
+        umma_commit(&slot_empty[i % p.nslots]);   // the oldest input row of this window is no longer needed
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int r = q * 32 + lane;          // pixel inside the strip row
+    const int w = w0 + r;
+    const int nchunks = p.ncols_pad >> 4;
+    for (int i = 0; i < nrows_out; ++i) {
+      const int buf = i & 1;
+      const uint32_t use = (uint32_t)(i >> 1);
+      mbar_wait(&tmem_full[buf], use & 1u);
+      tc_fence_after();
+      const int h = h_begin + i;
+      const size_t pix = ((size_t)n * p.h + h) * p.w + w;
+      for (int j = 0; j < nchunks; ++j) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + (uint32_t)buf * p.acc_cols + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
+        tmem_ld_wait();
+        const int col = j * 16;
+        if (col >= p.ncols) continue;
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
+        int nvalid = p.ncols - col;
+        if (nvalid > 16) nvalid = 16;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (k < nvalid) v[k] += p.bias[col + k];
+        }
+        if (p.act == SMSUT_ACT_RELU) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = fmaxf(v[k], 0.f);
+        } else if (p.act == SMSUT_ACT_LRELU) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = lrelu(v[k], p.slope);
+        }
+        void* base;
+        int ld, coff, c;
+        if (p.split > 0 && col >= p.split) {
+          base = p.out1; ld = p.ld1; coff = p.coff1; c = col - p.split;
+        } else {
+          base = p.out0; ld = p.ld0; coff = p.coff0; c = col;
+          if (p.split > 0 && col + nvalid > p.split) nvalid = p.split - col;
+        }
+        band_store16(base, pix * (size_t)ld + coff + c, v, nvalid, p.out_f32 != 0, p.accumulate != 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// returns 1 if the launch was handled by the band kernel, 0 if the shape is not eligible, < 0 on error
+int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
+  if (a->kind != SMSUT_TC_CONV) return 0;
+  if (!(a->ksize == 1 || a->ksize == 3 || a->ksize == 5)) return 0;
+  if (a->w % 128 != 0) return 0;
+  const int cc = a->src_c[0];
+  if (!(cc == 16 || cc == 32 || cc == 64)) return 0;
+  if (a->nsrc == 2 && a->src_c[1] != cc) return 0;
+  if (a->ncols_pad > 256 || a->ncols_pad % 16 != 0) return 0;
+  {
+    const char* e = getenv("SMSUT_NO_BAND");
+    if (e && e[0] == '1') return 0;
+  }
+  BandParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = a->n; p.h = a->h; p.w = a->w;
+  p.ks = a->ksize; p.r = a->ksize / 2;
+  p.nsrc = a->nsrc; p.cc = cc; p.ctot = cc * a->nsrc;
+  p.ncols = a->ncols; p.ncols_pad = a->ncols_pad;
+  p.pitch = (uint32_t)cc * 2u;
+  p.layout_type = cc == 64 ? 2u : (cc == 32 ? 4u : 6u);
+  p.sbo = 8u * p.pitch;
+  const int taps = p.ks * p.ks;
+  p.wtile_bytes = (uint32_t)a->ncols_pad * p.pitch;
+  p.w_bytes = (uint32_t)taps * a->nsrc * p.wtile_bytes;
+  if (p.w_bytes > 96u * 1024u) return 0;
+  p.src_bytes = (((uint32_t)(128 + 2 * p.r) * p.pitch) + 1023u) & ~1023u;
+  p.slot_bytes = p.src_bytes * (uint32_t)a->nsrc;
+  int nslots = (int)((200u * 1024u - ((p.w_bytes + 1023u) & ~1023u)) / p.slot_bytes);
+  if (nslots > kBandMaxSlots) nslots = kBandMaxSlots;
+  if (nslots > 2 * p.r + 1 + 5) nslots = 2 * p.r + 1 + 5;
+  if (nslots < 2 * p.r + 2) return 0;
+  p.nslots = nslots;
+  p.acc_cols = (uint32_t)a->ncols_pad;
+  uint32_t tc = 32;
+  while (tc < 2u * p.acc_cols) tc <<= 1;
+  p.tmem_cols = tc;
+
+  // strip decomposition: ~3 CTAs per SM, at least 4 output rows per strip
+  p.wtiles = a->w / 128;
+  const int sms = device_sm_count();
+  int segs = (3 * sms + a->n * p.wtiles - 1) / (a->n * p.wtiles);
+  if (segs < 1) segs = 1;
+  int rows = (a->h + segs - 1) / segs;
+  if (rows < 4) rows = a->h < 4 ? a->h : 4;
+  p.rows_per_seg = rows;
+  p.segs = (a->h + rows - 1) / rows;
+
+  p.out0 = a->out0; p.ld0 = a->out0_ld; p.coff0 = a->out0_coff;
+  p.out1 = a->out1; p.ld1 = a->out1_ld; p.coff1 = a->out1_coff; p.split = a->out1 ? a->split : 0;
+  p.bias = a->bias; p.act = a->act; p.slope = a->slope;
+  p.accumulate = a->accumulate; p.out_f32 = a->out_f32;
+  SMSUT_CHECK(a->out0 != nullptr, -1, "null output");
+  if (p.split > 0) SMSUT_CHECK(p.split % 16 == 0, -1, "split must be a multiple of 16");
+
+  CUtensorMap maps[2], map_w;
+  memset(maps, 0, sizeof(maps));
+  for (int s = 0; s < a->nsrc; ++s) {
+    int rc = make_act_map(&maps[s], a->src[s], a->src_c[s], a->w, a->h, a->n, a->src_ld[s], (int64_t)a->src_ld[s] * a->w,
+                          (int64_t)a->src_ld[s] * a->w * a->h, cc, 128 + 2 * p.r, 1, 1);
+    if (rc) return rc;
+  }
+  const int64_t ktot = (int64_t)taps * p.ctot;
+  int rc = make_mat_map(&map_w, a->wpack, ktot, a->ncols_pad, ktot, cc, a->ncols_pad);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + (size_t)p.nslots * p.slot_bytes + 1024;
+  const unsigned grid = (unsigned)(a->n * p.wtiles * p.segs);
+  conv_band_kernel<<<grid, kBandThreads, smem, stream>>>(maps[0], maps[1], map_w, p);
+  count_launch();
+  int st = launch_status("conv_band_kernel");
+  return st ? st : 1;
+}
+
+}  // namespace smsut

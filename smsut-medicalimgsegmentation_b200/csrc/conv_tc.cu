@@ -353,6 +353,7 @@ int choose_tile(int n, int h, int w, int* tn, int* th, int* tw) {
 }
 
 void count_launch();
+int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream);
 
 static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a != nullptr, -1, "null args");
@@ -363,6 +364,12 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
     SMSUT_CHECK(a->src_c[s] % 16 == 0 && a->src_c[s] > 0 && a->src_ld[s] >= a->src_c[s] && a->src_ld[s] % 8 == 0, -1,
                 "source %d channels (%d, ld %d) must be a positive multiple of 16", s, a->src_c[s], a->src_ld[s]);
   SMSUT_CHECK(a->ncols_pad % 16 == 0 && a->ncols <= a->ncols_pad && a->ncols > 0, -1, "bad ncols/ncols_pad");
+
+  // wide, narrow-channel layers: the band kernel (each input row fetched once, taps by descriptor arithmetic)
+  if (a->bn == 0 && a->ncols_pad % 16 == 0 && a->src_c[0] % 16 == 0) {
+    const int rb = conv_band_try(a, stream);
+    if (rb != 0) return rb < 0 ? rb : 0;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {

@@ -104,8 +104,15 @@ __device__ __forceinline__ float act_grad(float out, int act, float slope) {
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNT) in_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, int hw,
-                                                       int c, int splits) {
+// All streaming loops below keep U independent 128-bit loads per tensor in flight per thread (the kernels are
+// HBM-bound: ncu showed long-scoreboard stalls at 2 blocks/SM) and stay under 64 registers (4 blocks/SM).
+constexpr int kUS = 4;  // pixels per thread per iteration, statistics / apply
+constexpr int kUB = 2;  // backward kernels (3-4 tensors per pixel)
+
+__device__ __forceinline__ uint4 zero4() { return make_uint4(0u, 0u, 0u, 0u); }
+
+__global__ void __launch_bounds__(kNT, 4) in_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, int hw,
+                                                          int c, int splits) {
   extern __shared__ float sh[];
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
@@ -113,19 +120,29 @@ __global__ void __launch_bounds__(kNT) in_stats_kernel(const void* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   const size_t base = (size_t)n * hw * c + s.g * 8;
-  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
-    float v[8];
-    unpack8(ldg16(x, base + (size_t)p * c), v);
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += (long long)kUS * s.nlanes) {
+    uint4 q[kUS];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += v[j];
-      acc[1][j] = fmaf(v[j], v[j], acc[1][j]);
+    for (int u = 0; u < kUS; ++u) {
+      const long long pp = p + (long long)u * s.nlanes;
+      q[u] = pp < s.p1 ? ldg16(x, base + (size_t)pp * c) : zero4();
+    }
+#pragma unroll
+    for (int u = 0; u < kUS; ++u) {
+      float v[8];
+      unpack8(q[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += v[j];
+        acc[1][j] = fmaf(v[j], v[j], acc[1][j]);
+      }
     }
   }
   block_reduce_add<2>(acc, sh, s, stats + (size_t)n * 2 * c, c, c);
 }
 
-__global__ void __launch_bounds__(kNT)
+template <bool HAS_B, bool HAS_RES>
+__global__ void __launch_bounds__(kNT, 4)
 in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
                 const float* __restrict__ beta_a, const void* __restrict__ xb, const float* __restrict__ stats_b,
                 const float* __restrict__ gamma_b, const float* __restrict__ beta_b, const void* __restrict__ res,
@@ -134,7 +151,7 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
-  float sa[8], ta[8], sb[8], tb[8];
+  float sa[8], ta[8], sb[8];
   {
     float m[8], r[8];
     load_mean_rstd(stats_a, n, c, ch0, inv_hw, m, r);
@@ -145,49 +162,67 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
       sa[j] = g * r[j];
       ta[j] = b - m[j] * sa[j];
     }
-    if (xb != nullptr) {
+    if (HAS_B) {
       load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const bool ok = ch0 + j < cp;
         const float g = ok ? gamma_b[ch0 + j] : 0.f, b = ok ? beta_b[ch0 + j] : 0.f;
         sb[j] = g * r[j];
-        tb[j] = b - m[j] * sb[j];
+        ta[j] += b - m[j] * sb[j];      // both shifts folded into one
       }
     }
   }
   const size_t base = (size_t)n * hw * c + ch0;
-  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
-    const size_t off = base + (size_t)p * c;
-    float v[8], o[8];
-    unpack8(ldg16(xa, off), v);
+  constexpr int U = (HAS_B || HAS_RES) ? 2 : kUS;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += (long long)U * s.nlanes) {
+    uint4 qa[U], qb[U], qr[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sa[j], ta[j]);
-    if (xb != nullptr) {
-      unpack8(ldg16(xb, off), v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += fmaf(v[j], sb[j], tb[j]);
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * s.nlanes;
+      const bool ok = pp < s.p1;
+      const size_t off = base + (size_t)pp * c;
+      qa[u] = ok ? ldg16(xa, off) : zero4();
+      if (HAS_B) qb[u] = ok ? ldg16(xb, off) : zero4();
+      if (HAS_RES) qr[u] = ok ? ldg16(res, off) : zero4();
     }
-    if (res != nullptr) {
-      unpack8(ldg16(res, off), v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += v[j];
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * s.nlanes;
+      if (pp >= s.p1) break;
+      float v[8], o[8];
+      unpack8(qa[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sa[j], ta[j]);
+      if (HAS_B) {
+        unpack8(qb[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sb[j], o[j]);
+      }
+      if (HAS_RES) {
+        unpack8(qr[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += v[j];
+      }
+      if (act == SMSUT_ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = lrelu(o[j], slope);
+      } else if (act == SMSUT_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+      }
+      stg16(out, base + (size_t)pp * c, pack8(o));
     }
-    if (act == SMSUT_ACT_LRELU) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = lrelu(o[j], slope);
-    } else if (act == SMSUT_ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-    }
-    stg16(out, off, pack8(o));
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNT)
+// pass 1: red[n] = { sum g, sum g*xhat_a, sum g*xhat_b } with g = dout * act'(out).
+// In the loop only sum g*(x - mean) is accumulated; rstd is applied once at the end.
+template <bool HAS_B>
+__global__ void __launch_bounds__(kNT, 3)
 in_bwd_reduce_kernel(const void* __restrict__ dout, const void* __restrict__ out, const void* __restrict__ xa,
                      const float* __restrict__ stats_a, const void* __restrict__ xb,
                      const float* __restrict__ stats_b, float* __restrict__ red, int hw, int c, int splits, int act,
@@ -197,38 +232,73 @@ in_bwd_reduce_kernel(const void* __restrict__ dout, const void* __restrict__ out
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
-  float ma[8], ra[8], mb[8], rb[8];
-  load_mean_rstd(stats_a, n, c, ch0, inv_hw, ma, ra);
-  if (xb != nullptr) load_mean_rstd(stats_b, n, c, ch0, inv_hw, mb, rb);
+  float ma[8], mb[8];
+  {
+    const float* s0 = stats_a + (size_t)n * 2 * c + ch0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ma[j] = s0[j] * inv_hw;
+    if (HAS_B) {
+      const float* t0 = stats_b + (size_t)n * 2 * c + ch0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mb[j] = t0[j] * inv_hw;
+    }
+  }
   float acc[3][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
   const size_t base = (size_t)n * hw * c + ch0;
-  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
-    const size_t off = base + (size_t)p * c;
-    float g[8], v[8];
-    unpack8(ldg16(dout, off), g);
-    if (act != SMSUT_ACT_NONE) {
-      unpack8(ldg16(out, off), v);
+  const bool has_act = act != SMSUT_ACT_NONE;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += (long long)kUB * s.nlanes) {
+    uint4 qd[kUB], qo[kUB], qa[kUB], qb[kUB];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
+    for (int u = 0; u < kUB; ++u) {
+      const long long pp = p + (long long)u * s.nlanes;
+      const bool ok = pp < s.p1;
+      const size_t off = base + (size_t)pp * c;
+      qd[u] = ok ? ldg16(dout, off) : zero4();          // g = 0 beyond the strip: contributes nothing
+      qo[u] = (ok && has_act) ? ldg16(out, off) : zero4();
+      qa[u] = ok ? ldg16(xa, off) : zero4();
+      if (HAS_B) qb[u] = ok ? ldg16(xb, off) : zero4();
     }
-    unpack8(ldg16(xa, off), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += g[j];
-      acc[1][j] = fmaf(g[j], (v[j] - ma[j]) * ra[j], acc[1][j]);
+    for (int u = 0; u < kUB; ++u) {
+      float g[8], v[8];
+      unpack8(qd[u], g);
+      if (has_act) {
+        unpack8(qo[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
+      }
+      unpack8(qa[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g[j];
+        acc[1][j] = fmaf(g[j], v[j] - ma[j], acc[1][j]);
+      }
+      if (HAS_B) {
+        unpack8(qb[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g[j], v[j] - mb[j], acc[2][j]);
+      }
     }
-    if (xb != nullptr) {
-      unpack8(ldg16(xb, off), v);
+  }
+  {
+    float m[8], r[8];
+    load_mean_rstd(stats_a, n, c, ch0, inv_hw, m, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g[j], (v[j] - mb[j]) * rb[j], acc[2][j]);
+    for (int j = 0; j < 8; ++j) acc[1][j] *= r[j];
+    if (HAS_B) {
+      load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[2][j] *= r[j];
     }
   }
   block_reduce_add<3>(acc, sh, s, red + (size_t)n * 3 * c, c, c);
 }
 
-__global__ void __launch_bounds__(kNT)
+// pass 2: dx = A*g + B*x + C per channel with A = gamma*rstd, B = -A*rstd*mean(g xhat), C = -A*mean(g) - B*mean
+template <bool HAS_B, bool HAS_RES>
+__global__ void __launch_bounds__(kNT, 3)
 in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out, const void* __restrict__ xa,
                     const float* __restrict__ stats_a, const float* __restrict__ gamma_a, void* __restrict__ dxa,
                     float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const void* __restrict__ xb,
@@ -239,18 +309,28 @@ in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out,
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
-  float ma[8], ra[8], mb[8], rb[8], sa[8], sb[8], mg[8], mga[8], mgb[8];
-  load_mean_rstd(stats_a, n, c, ch0, inv_hw, ma, ra);
-  if (xb != nullptr) load_mean_rstd(stats_b, n, c, ch0, inv_hw, mb, rb);
+  float Aa[8], Ba[8], Ca[8], Ab[8], Bb[8], Cb[8];
   const float* r0 = red + (size_t)n * 3 * c + ch0;
+  {
+    float m[8], r[8];
+    load_mean_rstd(stats_a, n, c, ch0, inv_hw, m, r);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const bool ok = ch0 + j < cp;
-    mg[j] = r0[j] * inv_hw;
-    mga[j] = r0[c + j] * inv_hw;
-    mgb[j] = r0[2 * c + j] * inv_hw;
-    sa[j] = (ok ? gamma_a[ch0 + j] : 0.f) * ra[j];
-    sb[j] = (xb != nullptr && ok) ? gamma_b[ch0 + j] * rb[j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = ch0 + j < cp;
+      const float A = (ok ? gamma_a[ch0 + j] : 0.f) * r[j];
+      const float B = -A * r[j] * (r0[c + j] * inv_hw);
+      Aa[j] = A; Ba[j] = B; Ca[j] = -A * (r0[j] * inv_hw) - B * m[j];
+    }
+    if (HAS_B) {
+      load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = ch0 + j < cp;
+        const float A = (ok ? gamma_b[ch0 + j] : 0.f) * r[j];
+        const float B = -A * r[j] * (r0[2 * c + j] * inv_hw);
+        Ab[j] = A; Bb[j] = B; Cb[j] = -A * (r0[j] * inv_hw) - B * m[j];
+      }
+    }
   }
   // parameter gradients: one block per sample adds its (n, c) sums
   if (blockIdx.y == 0 && s.lane0 == 0) {
@@ -259,32 +339,49 @@ in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out,
       if (ch0 + j >= cp) continue;
       if (dgamma_a) atomicAdd(dgamma_a + ch0 + j, r0[c + j]);
       if (dbeta_a) atomicAdd(dbeta_a + ch0 + j, r0[j]);
-      if (xb != nullptr) {
+      if (HAS_B) {
         if (dgamma_b) atomicAdd(dgamma_b + ch0 + j, r0[2 * c + j]);
         if (dbeta_b) atomicAdd(dbeta_b + ch0 + j, r0[j]);
       }
     }
   }
   const size_t base = (size_t)n * hw * c + ch0;
-  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
-    const size_t off = base + (size_t)p * c;
-    float g[8], v[8], o[8];
-    unpack8(ldg16(dout, off), g);
-    if (act != SMSUT_ACT_NONE) {
-      unpack8(ldg16(out, off), v);
+  const bool has_act = act != SMSUT_ACT_NONE;
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += (long long)kUB * s.nlanes) {
+    uint4 qd[kUB], qo[kUB], qa[kUB], qb[kUB];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
+    for (int u = 0; u < kUB; ++u) {
+      const long long pp = p + (long long)u * s.nlanes;
+      const bool ok = pp < s.p1;
+      const size_t off = base + (size_t)pp * c;
+      qd[u] = ok ? ldg16(dout, off) : zero4();
+      qo[u] = (ok && has_act) ? ldg16(out, off) : zero4();
+      qa[u] = ok ? ldg16(xa, off) : zero4();
+      if (HAS_B) qb[u] = ok ? ldg16(xb, off) : zero4();
     }
-    if (dres != nullptr) stg16(dres, off, pack8(g));
-    unpack8(ldg16(xa, off), v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = sa[j] * (g[j] - mg[j] - (v[j] - ma[j]) * ra[j] * mga[j]);
-    stg16(dxa, off, pack8(o));
-    if (xb != nullptr) {
-      unpack8(ldg16(xb, off), v);
+    for (int u = 0; u < kUB; ++u) {
+      const long long pp = p + (long long)u * s.nlanes;
+      if (pp >= s.p1) break;
+      const size_t off = base + (size_t)pp * c;
+      float g[8], v[8], o[8];
+      unpack8(qd[u], g);
+      if (has_act) {
+        unpack8(qo[u], v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = sb[j] * (g[j] - mg[j] - (v[j] - mb[j]) * rb[j] * mgb[j]);
-      stg16(dxb, off, pack8(o));
+        for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
+      }
+      if (HAS_RES) stg16(dres, off, pack8(g));
+      unpack8(qa[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(Aa[j], g[j], fmaf(Ba[j], v[j], Ca[j]));
+      stg16(dxa, off, pack8(o));
+      if (HAS_B) {
+        unpack8(qb[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(Ab[j], g[j], fmaf(Bb[j], v[j], Cb[j]));
+        stg16(dxb, off, pack8(o));
+      }
     }
   }
 }
@@ -440,10 +537,10 @@ __global__ void __launch_bounds__(kNT) colsum_kernel(const void* __restrict__ x,
 // host launchers
 // ---------------------------------------------------------------------------------------------
 static int pick_splits(int n, int hw, int c) {
-  // >= ~4 blocks per SM overall, each block streaming >= 32 KB
+  // ~8 blocks per SM overall (two waves at 4 resident blocks), each block streaming >= 16 KB
   const long long bytes = (long long)hw * c * 2;
-  long long s = bytes / (32 * 1024);
-  const long long want = (4LL * device_sm_count() + n - 1) / n;
+  long long s = bytes / (16 * 1024);
+  const long long want = (8LL * device_sm_count() + n - 1) / n;
   if (s > want) s = want;
   if (s < 1) s = 1;
   if (s > hw) s = hw;
@@ -482,8 +579,12 @@ extern "C" int smsut_in_apply(const void* xa, const float* stats_a, const float*
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  in_apply_kernel<<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(xa, stats_a, gamma_a, beta_a, xb, stats_b, gamma_b,
-                                                                 beta_b, res, out, hw, c, cp, splits, act, slope);
+#define IN_APPLY(HB, HR)                                                                                          \
+  in_apply_kernel<HB, HR><<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(xa, stats_a, gamma_a, beta_a, xb, stats_b, \
+                                                                         gamma_b, beta_b, res, out, hw, c, cp, splits, act, slope)
+  if (xb != nullptr) { if (res != nullptr) IN_APPLY(true, true); else IN_APPLY(true, false); }
+  else { if (res != nullptr) IN_APPLY(false, true); else IN_APPLY(false, false); }
+#undef IN_APPLY
   count_launch();
   return launch_status("in_apply_kernel");
 }
@@ -494,8 +595,12 @@ extern "C" int smsut_in_bwd_reduce(const void* dout, const void* out, const void
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  in_bwd_reduce_kernel<<<dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st>>>(
-      dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
+  if (xb != nullptr)
+    in_bwd_reduce_kernel<true><<<dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st>>>(
+        dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
+  else
+    in_bwd_reduce_kernel<false><<<dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st>>>(
+        dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
   count_launch();
   return launch_status("in_bwd_reduce_kernel");
 }
@@ -508,9 +613,13 @@ extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void*
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  in_bwd_apply_kernel<<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(dout, out, xa, stats_a, gamma_a, dxa, dgamma_a,
-                                                                     dbeta_a, xb, stats_b, gamma_b, dxb, dgamma_b,
-                                                                     dbeta_b, dres, red, hw, c, cp, splits, act, slope);
+#define IN_BWD_APPLY(HB, HR)                                                                                       \
+  in_bwd_apply_kernel<HB, HR><<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(                                       \
+      dout, out, xa, stats_a, gamma_a, dxa, dgamma_a, dbeta_a, xb, stats_b, gamma_b, dxb, dgamma_b, dbeta_b, dres, red, \
+      hw, c, cp, splits, act, slope)
+  if (xb != nullptr) { if (dres != nullptr) IN_BWD_APPLY(true, true); else IN_BWD_APPLY(true, false); }
+  else { if (dres != nullptr) IN_BWD_APPLY(false, true); else IN_BWD_APPLY(false, false); }
+#undef IN_BWD_APPLY
   count_launch();
   return launch_status("in_bwd_apply_kernel");
 }

@@ -279,11 +279,13 @@ def test_cuda_graph_replay_equals_eager_step(pkg):
     assert step.launches_per_replay > 500
     reset()
     lg = step(*batch, a1, i1, lam).clone()
-    wg = torch.cat([p.detach().flatten() for p in tr.net.parameters()]).clone()
+    dg = tr.d_optimizer.grad.clone()
     reset()
     le = tr.train_step(*batch, a1, [i1], lam, True)
-    we = torch.cat([p.detach().flatten() for p in tr.net.parameters()])
-    report("graph_vs_eager", dict(eager=le.tolist(), graph=lg.tolist(), weights_rel=rel(wg, we)))
-    # fp32 atomics reorder sums between the two runs; D_gp ~ 5e3 amplifies that into the G-phase terms
+    de = tr.d_optimizer.grad.clone()
+    report("graph_vs_eager", dict(eager=le.tolist(), graph=lg.tolist(), d_grad_rel=rel(dg, de)))
+    # same kernels, same inputs: only the order of fp32 atomics differs.  The D phase must agree tightly; the G
+    # phase sits behind D's Adam step (lr * sign(g) on near-zero gradients) and D_gp ~ 5e3, which amplify that noise
+    assert rel(lg[:4], le[:4]) < 2e-3, (lg.tolist(), le.tolist())
+    assert rel(dg, de) < 2e-2
     assert rel(lg, le) < 5e-2, (lg.tolist(), le.tolist())
-    assert rel(wg, we) < 5e-2
