@@ -302,6 +302,12 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   if (segs < 1) segs = 1;
   int rows = (a->h + segs - 1) / segs;
   if (rows < 4) rows = a->h < 4 ? a->h : 4;
+  {
+    const char* e = getenv("SMSUT_BAND_ROWS");      // tuning knobs (development)
+    if (e && atoi(e) > 0) rows = atoi(e);
+    e = getenv("SMSUT_BAND_SLOTS");
+    if (e && atoi(e) >= 2 * p.r + 2 && atoi(e) <= kBandMaxSlots) p.nslots = atoi(e);
+  }
   p.rows_per_seg = rows;
   p.segs = (a->h + rows - 1) / rows;
 
