@@ -82,6 +82,10 @@ __device__ __forceinline__ void band_store16(void* base, size_t off, const float
   }
 }
 
+// KS = kernel size, NSRC = sources, KK = channels per source / 16: compile-time so that the single MMA-issuing
+// thread runs a fully unrolled stream of descriptor adds + tcgen05.mma (ncu: with runtime loops, modulo slot
+// arithmetic and descriptor rebuilds that one thread took ~2.7 us per output row and every other warp waited on it)
+template <int KS, int NSRC, int KK>
 __global__ void __launch_bounds__(kBandThreads, 1)
 conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ BandParams p) {
@@ -145,9 +149,9 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         for (int s = 0; s < p.nsrc; ++s)
           tma_load_2d(smem_al + (size_t)(t * p.nsrc + s) * p.wtile_bytes, &map_w, &w_full, t * p.ctot + s * p.cc, 0);
       // input rows h_begin - r .. h_end - 1 + r, each fetched once (out-of-image rows / halo pixels: TMA zero fill)
-      for (int j = 0; j < nrows_in; ++j) {
-        const int slot = j % p.nslots;
-        const uint32_t phase = (uint32_t)(j / p.nslots) & 1u;
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nrows_in; ++j, slot = (slot + 1 == p.nslots ? 0 : slot + 1), phase ^= (slot == 0 ? 1u : 0u)) {
         mbar_wait(&slot_empty[slot], phase ^ 1u);
         mbar_arrive_expect_tx(&slot_full[slot], (uint32_t)p.nsrc * (uint32_t)(128 + 2 * p.r) * p.pitch);
         uint8_t* dst = ring_ptr + (size_t)slot * p.slot_bytes;
@@ -161,41 +165,53 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const uint32_t idesc =
         (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ncols_pad >> 3) << 17) | ((128u >> 4) << 24);
     mbar_wait(&w_full, 0);
-    int rows_ready = 0;   // input rows whose slot_full barrier has been consumed
+    // descriptors: hi word constant; lo word = (start >> 4) | (LBO = 1) << 16, advanced by plain adds (16-byte units)
+    const uint64_t desc_hi = make_smem_desc(0, 16, p.sbo, p.layout_type) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_flags = 1u << 16;
+    const uint32_t ring_lo = (ring_base >> 4) | lo_flags;
+    const uint32_t w_lo = (smem_base >> 4) | lo_flags;
+    const uint32_t slot_u = p.slot_bytes >> 4, src_u = p.src_bytes >> 4, pitch_u = p.pitch >> 4, wtile_u = p.wtile_bytes >> 4;
+    const int nslots = p.nslots;
+    int rows_ready = 0;       // input rows whose slot_full barrier has been consumed
+    int ready_slot = 0;       // rows_ready % nslots, and its wrap count
+    uint32_t ready_phase = 0;
+    int base_slot = 0;        // i % nslots
     for (int i = 0; i < nrows_out; ++i) {
       const int buf = i & 1;
-      const uint32_t use = (uint32_t)(i >> 1);
-      mbar_wait(&tmem_empty[buf], (use & 1u) ^ 1u);
+      mbar_wait(&tmem_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
       // output row i needs input rows i .. i + 2r (indices relative to the strip's first input row)
-      while (rows_ready <= i + 2 * p.r) {
-        mbar_wait(&slot_full[rows_ready % p.nslots], (uint32_t)(rows_ready / p.nslots) & 1u);
+      while (rows_ready <= i + KS - 1) {
+        mbar_wait(&slot_full[ready_slot], ready_phase);
         ++rows_ready;
+        if (++ready_slot == nslots) { ready_slot = 0; ready_phase ^= 1u; }
       }
       tc_fence_after();
       if (lane == 0) {
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * p.acc_cols;
-        uint32_t first = 1;
-        const int kk = p.cc >> 4;
-        for (int ty = 0; ty < p.ks; ++ty) {
-          const uint32_t slot_addr = ring_base + (uint32_t)((i + ty) % p.nslots) * p.slot_bytes;
-          for (int tx = 0; tx < p.ks; ++tx) {
-            const int t = ty * p.ks + tx;
-            for (int s = 0; s < p.nsrc; ++s) {
-              const uint32_t a_addr = slot_addr + (uint32_t)s * p.src_bytes + (uint32_t)tx * p.pitch;
-              const uint32_t b_addr = smem_base + (uint32_t)(t * p.nsrc + s) * p.wtile_bytes;
-              for (int k = 0; k < kk; ++k) {
-                const uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, p.sbo, p.layout_type);
-                const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, p.sbo, p.layout_type);
-                umma_bf16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
-                first = 0;
+#pragma unroll
+        for (int ty = 0; ty < KS; ++ty) {
+          int slot = base_slot + ty;
+          if (slot >= nslots) slot -= nslots;
+          const uint32_t row_lo = ring_lo + (uint32_t)slot * slot_u;
+#pragma unroll
+          for (int tx = 0; tx < KS; ++tx) {
+#pragma unroll
+            for (int s = 0; s < NSRC; ++s) {
+              const uint32_t a_lo = row_lo + (uint32_t)s * src_u + (uint32_t)tx * pitch_u;
+              const uint32_t b_lo = w_lo + (uint32_t)((ty * KS + tx) * NSRC + s) * wtile_u;
+#pragma unroll
+              for (int k = 0; k < KK; ++k) {
+                umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
+                          (ty | tx | s | k) != 0 ? 1u : 0u);
               }
             }
           }
         }
         umma_commit(&tmem_full[buf]);
-        umma_commit(&slot_empty[i % p.nslots]);   // the oldest input row of this window is no longer needed
+        umma_commit(&slot_empty[base_slot]);   // the oldest input row of this window is no longer needed
       }
       __syncwarp();
+      if (++base_slot == nslots) base_slot = 0;
     }
   } else {
     // ===================== epilogue =====================
@@ -329,14 +345,25 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   int rc = make_mat_map(&map_w, a->wpack, ktot, a->ncols_pad, ktot, cc, a->ncols_pad);
   if (rc) return rc;
 
-  static bool attr_set = false;
-  if (!attr_set) {
-    SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
   const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + (size_t)p.nslots * p.slot_bytes + 1024;
   const unsigned grid = (unsigned)(a->n * p.wtiles * p.segs);
-  conv_band_kernel<<<grid, kBandThreads, smem, stream>>>(maps[0], maps[1], map_w, p);
+  bool launched = false;
+#define BAND_CASE(KS_, NS_, KK_)                                                                                  \
+  if (!launched && p.ks == KS_ && a->nsrc == NS_ && (cc >> 4) == KK_) {                                            \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_band_kernel<KS_, NS_, KK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         220 * 1024));                                                             \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    conv_band_kernel<KS_, NS_, KK_><<<grid, kBandThreads, smem, stream>>>(maps[0], maps[1], map_w, p);             \
+    launched = true;                                                                                               \
+  }
+  BAND_CASE(1, 1, 1) BAND_CASE(1, 1, 2) BAND_CASE(1, 1, 4) BAND_CASE(1, 2, 1) BAND_CASE(1, 2, 2) BAND_CASE(1, 2, 4)
+  BAND_CASE(3, 1, 1) BAND_CASE(3, 1, 2) BAND_CASE(3, 1, 4) BAND_CASE(3, 2, 1) BAND_CASE(3, 2, 2) BAND_CASE(3, 2, 4)
+  BAND_CASE(5, 1, 1) BAND_CASE(5, 1, 2) BAND_CASE(5, 1, 4)
+#undef BAND_CASE
+  if (!launched) return 0;
   count_launch();
   int st = launch_status("conv_band_kernel");
   return st ? st : 1;

@@ -118,6 +118,39 @@ __global__ void __launch_bounds__(128) direct_fprop_kernel(const DirectParams p)
   }
 }
 
+// fprop for very few output pixels (conv_cls: 16 outputs of K = 4096; conv_src: 256 outputs of K = 2304):
+// one warp per (output pixel, output channel), lanes split the input channels (coalesced NHWC reads).
+__global__ void __launch_bounds__(256) direct_fprop_small_kernel(const DirectParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nout = (long long)p.n * p.ho * p.wo * p.cout;
+  if (wid >= nout) return;
+  const int co = (int)(wid % p.cout);
+  long long t = wid / p.cout;
+  const int wo = (int)(t % p.wo); t /= p.wo;
+  const int ho = (int)(t % p.ho);
+  const int n = (int)(t / p.ho);
+  const int taps = p.kh * p.kw;
+  float acc = 0.f;
+  for (int ky = 0; ky < p.kh; ++ky) {
+    const int iy = ho * p.stride - p.pad + ky;
+    if (iy < 0 || iy >= p.h) continue;
+    for (int kx = 0; kx < p.kw; ++kx) {
+      const int ix = wo * p.stride - p.pad + kx;
+      if (ix < 0 || ix >= p.w) continue;
+      const size_t base = (((size_t)n * p.h + iy) * p.w + ix) * p.x_ld;
+      const float* wr = p.wt + (size_t)co * p.cin * taps + ky * p.kw + kx;
+      for (int c = lane; c < p.cin; c += 32) acc = fmaf(load_act(p.x, base + c, p.x_f32), wr[(size_t)c * taps], acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (p.bias) acc += p.bias[co];
+    acc = apply_act(acc, p.act, p.slope);
+    store_act(p.y, (size_t)(wid / p.cout) * p.y_ld + co, p.y_f32, acc, p.accumulate);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // dgrad: one thread = one input pixel x CT input channels (gather form)
 //   dx[n,iy,ix,ci] = sum_{co,ky,kx : oy*stride - pad + ky == iy} dy[n,oy,ox,co] * w[co,ci,ky,kx]
@@ -337,7 +370,10 @@ static int direct_fprop(const smsut_conv_direct_args* a, cudaStream_t stream) {
   const long long npix = (long long)p.n * p.ho * p.wo;
   const int taps = p.kh * p.kw;
   const int cw = p.cout > p.y_ld ? p.cout : p.y_ld;  // channels to write (incl. zero padding)
-  if (cw <= 1) {
+  if (npix * p.cout <= 4096 && p.y_ld == p.cout && p.cin >= 32) {
+    const long long warps = npix * p.cout;
+    direct_fprop_small_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(p);
+  } else if (cw <= 1) {
     p.cch = pick_cch(taps, 1, p.cin);
     dim3 grid((unsigned)((npix + 127) / 128), 1);
     direct_fprop_kernel<1><<<grid, 128, (size_t)taps * p.cch * 1 * 4, stream>>>(p);

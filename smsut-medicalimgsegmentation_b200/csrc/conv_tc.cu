@@ -176,24 +176,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== MMA issuer =====================
     // instruction descriptor: fp32 accum, bf16 x bf16, both K-major, N = bn, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((128u >> 4) << 24);
+    // descriptors: constant hi word, lo word advanced by adds (16-byte units); the issuing thread's instruction
+    // stream is the critical path of the deep layers (36-72 K steps per tile), so keep it minimal
+    const uint64_t desc_hi = make_smem_desc(0, 16, p.sbo, p.layout_type) & 0xFFFFFFFF00000000ull;
+    const uint32_t base_lo = (smem_base >> 4) | (1u << 16);
+    const uint32_t stage_u = p.stage_bytes >> 4, a_u = p.a_bytes >> 4;
+    const int kk = p.cc >> 4;
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < p.nsteps; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_addr = smem_base + (uint32_t)stage * p.stage_bytes;
-        const uint32_t b_addr = a_addr + p.a_bytes;
-        const int kk = p.cc >> 4;
-        for (int k = 0; k < kk; ++k) {
-          uint64_t adesc = make_smem_desc(a_addr + k * 32, 16, p.sbo, p.layout_type);
-          if (p.dbg_rowshift) {
-            const uint32_t sa = a_addr + (uint32_t)p.cc * 2u + k * 32;   // one row (= cc*2 bytes) further
-            adesc = make_smem_desc(sa, 16, p.sbo, p.layout_type);
-            if (p.dbg_rowshift == 2) adesc |= (uint64_t)((sa >> 7) & 7u) << 49;
-          }
-          const uint64_t bdesc = make_smem_desc(b_addr + k * 32, 16, p.sbo, p.layout_type);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (i | k) != 0 ? 1u : 0u);
+        uint32_t a_lo = base_lo + (uint32_t)stage * stage_u;
+        if (p.dbg_rowshift) a_lo += (uint32_t)(p.cc * 2) >> 4;   // experiment: start one row later
+        const uint32_t b_lo = base_lo + (uint32_t)stage * stage_u + a_u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < kk)
+            umma_bf16(tmem_base, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
+                      (i | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
         if (i == p.nsteps - 1) umma_commit(&tmem_full_bar);

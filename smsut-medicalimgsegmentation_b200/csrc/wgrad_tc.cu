@@ -126,19 +126,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // fp32 accum, bf16 x bf16, A and B MN-major, N = ncols, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(ncols >> 3) << 17) | ((128u >> 4) << 24);
+    // constant descriptor words outside the loop; per UMMA only the start address advances
+    const uint64_t a_hi = make_smem_desc(0, p.a_lbo, p.a_sbo, p.a_layout) & 0xFFFFFFFFFFFF0000ull;
+    const uint64_t b_hi = make_smem_desc(0, p.b_block_bytes, p.b_sbo, p.b_layout) & 0xFFFFFFFFFFFF0000ull;
+    const uint32_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4, stage_u = p.stage_bytes >> 4;
+    const uint32_t a_off = a_stage_bytes >> 4, base_u = smem_base >> 4;
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < ntiles; ++t) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (lane == 0) {
-        const uint32_t a_addr = smem_base + (uint32_t)stage * p.stage_bytes;
-        const uint32_t b_addr = a_addr + a_stage_bytes;
-#pragma unroll 1
+        const uint32_t a0 = base_u + (uint32_t)stage * stage_u;
+        const uint32_t b0 = a0 + a_off;
+#pragma unroll
         for (int k = 0; k < 8; ++k) {  // 128 pixels / 16 per UMMA
-          const uint64_t adesc = make_smem_desc(a_addr + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_layout);
-          const uint64_t bdesc = make_smem_desc(b_addr + k * p.b_kadv, p.b_block_bytes, p.b_sbo, p.b_layout);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (t | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, a_hi | (uint64_t)((a0 + k * a_step) & 0x3FFFu), b_hi | (uint64_t)((b0 + k * b_step) & 0x3FFFu),
+                    idesc, (t | k) != 0 ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
         if (t == ntiles - 1) umma_commit(&tmem_full_bar);
