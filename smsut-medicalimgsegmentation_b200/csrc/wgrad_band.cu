@@ -1,0 +1,259 @@
+// "Band" weight gradient for the wide, narrow-channel layers (W % 128 == 0, Cin-chunk in {16, 32}, Cout <= 64):
+//   dW[co][ci][ty][tx] = sum_{n,h,w} dy[n,h,w,co] * x[n, h+ty-r, w+tx-r, ci]
+// One CTA walks down a strip of 128 pixels x R rows.  Each x row (with its halo) and each dy row is fetched by TMA
+// once into a ring of row slots; per output row and vertical tap ty ONE chain of 8 UMMAs (K = 16 pixels each)
+// accumulates D_ty[(tx, ci)][co]: the horizontal taps are the M-blocks of the MN-major A operand, whose leading
+// byte offset is one pixel row (LBO = pitch), i.e. block tx is the same smem row band started tx pixels later.
+// Accumulators stay in TMEM for the whole strip; the epilogue adds them to the fp32 OIHW gradient with atomics.
+// L2->SM traffic per row: (128 + 2r)*Cin*2 + 128*Cout*2 bytes, instead of (1 + taps) tiles in wgrad_tc_kernel.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/smsut_b200.h"
+#include "common.cuh"
+
+namespace smsut {
+
+void count_launch();
+int make_act_map(CUtensorMap* m, const void* ptr, int c, int w, int h, int n, int64_t sw, int64_t sh, int64_t sn,
+                 int cc, int tw, int th, int tn);
+
+constexpr int kWbThreads = 192;
+constexpr int kWbMaxSlots = 12;
+
+struct WgradBandParams {
+  int n, h, w, ks, r;
+  int xc, dc;                   // channels of the x / dy tiles (16 or 32 / 16, 32 or 64)
+  int wtiles, segs, rows_per_seg;
+  int nslots;
+  uint32_t x_slot_bytes, d_slot_bytes, d_base_off;
+  uint32_t x_pitch, d_pitch, x_layout, d_layout;
+  uint32_t tmem_cols;
+  float* dw;
+  int cout, cin_total, ci_off, c_valid, taps;
+};
+
+template <int KS>
+__global__ void __launch_bounds__(kWbThreads, 1)
+wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                  const __grid_constant__ WgradBandParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t x_full[kWbMaxSlots];
+  __shared__ __align__(8) uint64_t x_empty[kWbMaxSlots];
+  __shared__ __align__(8) uint64_t d_full[kWbMaxSlots];
+  __shared__ __align__(8) uint64_t d_empty[kWbMaxSlots];
+  __shared__ __align__(8) uint64_t acc_full;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  int b = blockIdx.x;
+  const int seg = b % p.segs; b /= p.segs;
+  const int wt = b % p.wtiles; b /= p.wtiles;
+  const int n = b;
+  const int w0 = wt * 128;
+  const int h_begin = seg * p.rows_per_seg;
+  int h_end = h_begin + p.rows_per_seg;
+  if (h_end > p.h) h_end = p.h;
+  const int nrows = h_end - h_begin;
+  const int nrows_in = nrows + 2 * p.r;
+  const int nslots = p.nslots;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    for (int s = 0; s < nslots; ++s) {
+      mbar_init(&x_full[s], 1);
+      mbar_init(&x_empty[s], 1);
+      mbar_init(&d_full[s], 1);
+      mbar_init(&d_empty[s], 1);
+    }
+    mbar_init(&acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_smem, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: x rows (with halo) and dy rows, each exactly once =====================
+    if (lane == 0) {
+      int xs = 0, ds = 0;
+      uint32_t xph = 0, dph = 0;
+      for (int j = 0; j < nrows_in; ++j) {
+        mbar_wait(&x_empty[xs], xph ^ 1u);
+        mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(128 + 2 * p.r) * p.x_pitch);
+        tma_load_4d(smem_al + (size_t)xs * p.x_slot_bytes, &map_x, &x_full[xs], 0, w0 - p.r, h_begin - p.r + j, n);
+        if (++xs == nslots) { xs = 0; xph ^= 1u; }
+        if (j < nrows) {
+          mbar_wait(&d_empty[ds], dph ^ 1u);
+          mbar_arrive_expect_tx(&d_full[ds], 128u * p.d_pitch);
+          tma_load_4d(smem_al + p.d_base_off + (size_t)ds * p.d_slot_bytes, &map_dy, &d_full[ds], 0, w0, h_begin + j, n);
+          if (++ds == nslots) { ds = 0; dph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // A = x slot, MN-major, M = (tx, ci): M-blocks of xc channels one pixel row apart (LBO = pitch);
+    // B = dy slot, MN-major, N = dc;  K = pixels (16 per UMMA)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(p.dc >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t a_hi = make_smem_desc(0, p.x_pitch, 8u * p.x_pitch, p.x_layout) & 0xFFFFFFFFFFFF0000ull;
+    const uint64_t b_hi = make_smem_desc(0, 0, 8u * p.d_pitch, p.d_layout) & 0xFFFFFFFFFFFF0000ull;
+    const uint32_t x_base = smem_base >> 4, d_base = (smem_base + p.d_base_off) >> 4;
+    const uint32_t xslot_u = p.x_slot_bytes >> 4, dslot_u = p.d_slot_bytes >> 4;
+    const uint32_t xk_u = (16u * p.x_pitch) >> 4, dk_u = (16u * p.d_pitch) >> 4;
+    int rows_ready = 0, ready_slot = 0, base_slot = 0, dslot = 0;
+    uint32_t ready_phase = 0, dphase = 0;
+    for (int i = 0; i < nrows; ++i) {
+      while (rows_ready <= i + KS - 1) {
+        mbar_wait(&x_full[ready_slot], ready_phase);
+        ++rows_ready;
+        if (++ready_slot == nslots) { ready_slot = 0; ready_phase ^= 1u; }
+      }
+      mbar_wait(&d_full[dslot], dphase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t b0 = d_base + (uint32_t)dslot * dslot_u;
+#pragma unroll
+        for (int ty = 0; ty < KS; ++ty) {
+          int slot = base_slot + ty;
+          if (slot >= nslots) slot -= nslots;
+          const uint32_t a0 = x_base + (uint32_t)slot * xslot_u;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(ty * p.dc);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(d_tmem, a_hi | (uint64_t)((a0 + k * xk_u) & 0x3FFFu), b_hi | (uint64_t)((b0 + k * dk_u) & 0x3FFFu),
+                      idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&x_empty[base_slot]);   // oldest x row of the window
+        umma_commit(&d_empty[dslot]);
+        if (i == nrows - 1) umma_commit(&acc_full);
+      }
+      __syncwarp();
+      if (++base_slot == nslots) base_slot = 0;
+      if (++dslot == nslots) { dslot = 0; dphase ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue: D_ty[(tx, ci)][co] -> atomics into dW[co][ci_off + ci][ty][tx] ==========
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int tx = row / p.xc, ci = row - tx * p.xc;
+    const bool row_ok = tx < KS && ci < p.c_valid;
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+    const int nch = (KS * p.dc) >> 4;
+    for (int j = 0; j < nch; ++j) {
+      uint32_t raw[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      const int col = j * 16;
+      const int ty = col / p.dc, co0 = col - ty * p.dc;
+      const int tap = ty * KS + tx;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int co = co0 + k;
+        if (co < p.cout)
+          atomicAdd(p.dw + ((size_t)co * p.cin_total + p.ci_off + ci) * p.taps + tap, __uint_as_float(raw[k]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+static uint32_t layout_for(int c) { return c == 64 ? 2u : (c == 32 ? 4u : 6u); }
+
+// returns 1 if handled, 0 if not eligible, < 0 on error
+int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
+  if (a->kind != SMSUT_TC_CONV) return 0;
+  if (!(a->ksize == 1 || a->ksize == 3 || a->ksize == 5)) return 0;
+  if (a->w % 128 != 0) return 0;
+  const int xc = a->x_c, dc = a->dy_c;
+  if (!(xc == 16 || xc == 32)) return 0;
+  if (!(dc == 16 || dc == 32 || dc == 64)) return 0;
+  if (a->ksize * xc > 128) return 0;                 // the horizontal taps must fit the 128 accumulator rows
+  {
+    const char* e = getenv("SMSUT_NO_BAND");
+    if (e && e[0] == '1') return 0;
+  }
+  WgradBandParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = a->n; p.h = a->h; p.w = a->w; p.ks = a->ksize; p.r = a->ksize / 2;
+  p.xc = xc; p.dc = dc;
+  p.x_pitch = (uint32_t)xc * 2u; p.d_pitch = (uint32_t)dc * 2u;
+  p.x_layout = layout_for(xc); p.d_layout = layout_for(dc);
+  // the last M-block starts (128/xc - 1) pixel rows into the band and K runs over 128 rows: pad the slot
+  p.x_slot_bytes = (((uint32_t)(128 + 2 * p.r + 128 / xc) * p.x_pitch) + 1023u) & ~1023u;
+  p.d_slot_bytes = ((128u * p.d_pitch) + 1023u) & ~1023u;
+  p.nslots = 2 * p.r + 1 + 4;
+  if (p.nslots > kWbMaxSlots) return 0;
+  p.d_base_off = (uint32_t)p.nslots * p.x_slot_bytes;
+  uint32_t tc = 32;
+  while ((int)tc < a->ksize * dc) tc <<= 1;
+  p.tmem_cols = tc;
+  p.dw = a->dw;
+  p.cout = dc < a->cout_total ? dc : a->cout_total;
+  p.cin_total = a->cin_total; p.ci_off = a->ci_off;
+  p.c_valid = a->c_valid > 0 ? a->c_valid : xc;
+  p.taps = a->ksize * a->ksize;
+  SMSUT_CHECK(a->dw != nullptr, -1, "null dw");
+
+  p.wtiles = a->w / 128;
+  const int sms = device_sm_count();
+  int segs = (3 * sms + a->n * p.wtiles - 1) / (a->n * p.wtiles);
+  if (segs < 1) segs = 1;
+  int rows = (a->h + segs - 1) / segs;
+  if (rows < 8) rows = a->h < 8 ? a->h : 8;
+  {
+    const char* e = getenv("SMSUT_BAND_ROWS");
+    if (e && atoi(e) > 0) rows = atoi(e);
+  }
+  p.rows_per_seg = rows;
+  p.segs = (a->h + rows - 1) / rows;
+
+  CUtensorMap map_x, map_dy;
+  int rc = make_act_map(&map_x, a->x, xc, a->w, a->h, a->n, a->x_ld, (int64_t)a->x_ld * a->w,
+                        (int64_t)a->x_ld * a->w * a->h, xc, 128 + 2 * p.r, 1, 1);
+  if (rc) return rc;
+  rc = make_act_map(&map_dy, a->dy, dc, a->w, a->h, a->n, a->dy_ld, (int64_t)a->dy_ld * a->w,
+                    (int64_t)a->dy_ld * a->w * a->h, dc, 128, 1, 1);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)p.nslots * (p.x_slot_bytes + p.d_slot_bytes) + 2048;
+  const unsigned grid = (unsigned)(a->n * p.wtiles * p.segs);
+  bool launched = false;
+#define WB_CASE(KS_)                                                                                               \
+  if (!launched && a->ksize == KS_) {                                                                              \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      SMSUT_CUDA_OK(cudaFuncSetAttribute(wgrad_band_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    wgrad_band_kernel<KS_><<<grid, kWbThreads, smem, stream>>>(map_x, map_dy, p);                                  \
+    launched = true;                                                                                               \
+  }
+  WB_CASE(1) WB_CASE(3) WB_CASE(5)
+#undef WB_CASE
+  count_launch();
+  int st = launch_status("wgrad_band_kernel");
+  return st ? st : 1;
+}
+
+}  // namespace smsut

@@ -184,8 +184,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
 static uint32_t layout_for_chunk(int cc) { return cc == 64 ? 2u : (cc == 32 ? 4u : 6u); }
 
+int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream);
+
 static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a != nullptr, -1, "null args");
+  if (a->dw != nullptr && a->x_c % 16 == 0 && a->dy_c % 16 == 0) {
+    const int rb = wgrad_band_try(a, stream);     // wide, narrow-channel layers: rows fetched once, taps by descriptor
+    if (rb != 0) return rb < 0 ? rb : 0;
+  }
   SMSUT_CHECK(a->kind == SMSUT_TC_CONV || a->kind == SMSUT_TC_CONVT_FWD, -1, "wgrad kind must be CONV or CONVT_FWD");
   SMSUT_CHECK(a->x_c % 16 == 0 && a->dy_c % 16 == 0 && a->x_c > 0 && a->dy_c > 0, -1,
               "wgrad channel counts must be multiples of 16 (x %d, dy %d)", a->x_c, a->dy_c);
