@@ -58,9 +58,14 @@ typedef struct smsut_conv_tc_args {
   int32_t accumulate; /* out += result (read-modify-write) */
   int32_t out_f32;    /* store fp32 instead of bf16 */
   int32_t bn;         /* N tile, 0 = auto */
+  float* stats;       /* optional fused InstanceNorm statistics (network/blocks.py:22-23): stats[n][2][ncols_pad] +=
+                         {sum, sum of squares} over H*W of the STORED (bf16-rounded) outputs.  Only valid when
+                         smsut_conv_tc_fuses_stats() returns 1 for these arguments; must be zeroed by the caller. */
 } smsut_conv_tc_args;
 
 int smsut_conv_tc(const smsut_conv_tc_args* a, smsut_stream_t stream);
+/* 1 if smsut_conv_tc would honour a->stats for this shape (wide layers on the band kernel), else 0 */
+int smsut_conv_tc_fuses_stats(const smsut_conv_tc_args* a);
 
 /* Weight gradient on tcgen05 (MN-major operands, split-K over pixels, fp32 atomics into OIHW grads).
  * Replaces aten::convolution_backward(weight) for the same layer classes.

@@ -23,7 +23,7 @@ class ConvTcArgs(C.Structure):
         ("out0", c_void_p), ("out0_ld", c_int), ("out0_coff", c_int),
         ("out1", c_void_p), ("out1_ld", c_int), ("out1_coff", c_int), ("split", c_int),
         ("bias", c_void_p), ("act", c_int), ("slope", c_float), ("accumulate", c_int), ("out_f32", c_int),
-        ("bn", c_int),
+        ("bn", c_int), ("stats", c_void_p),
     ]
 
 
@@ -59,6 +59,7 @@ class PackEntry(C.Structure):
 P = c_void_p
 _PROTOS = {
     "smsut_conv_tc": [C.POINTER(ConvTcArgs), P],
+    "smsut_conv_tc_fuses_stats": [C.POINTER(ConvTcArgs)],
     "smsut_wgrad_tc": [C.POINTER(WgradTcArgs), P],
     "smsut_conv_direct_fprop": [C.POINTER(ConvDirectArgs), P],
     "smsut_conv_direct_dgrad": [C.POINTER(ConvDirectArgs), P],

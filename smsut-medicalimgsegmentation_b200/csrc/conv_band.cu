@@ -51,6 +51,7 @@ struct BandParams {
   const float* bias;
   int act; float slope;
   int accumulate, out_f32;
+  float* stats;            // fused InstanceNorm statistics [n][2][ncols_pad] (optional)
 };
 
 __device__ __forceinline__ void band_store16(void* base, size_t off, const float* v, int nvalid, bool f32,
@@ -219,6 +220,8 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const int r = q * 32 + lane;          // pixel inside the strip row
     const int w = w0 + r;
     const int nchunks = p.ncols_pad >> 4;
+    float st_acc[4] = {0.f, 0.f, 0.f, 0.f};   // lane l: l < 16 -> sum of channel l, else sum of squares of l - 16
+    const bool do_stats = p.stats != nullptr;
     for (int i = 0; i < nrows_out; ++i) {
       const int buf = i & 1;
       const uint32_t use = (uint32_t)(i >> 1);
@@ -258,10 +261,38 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
           if (p.split > 0 && col + nvalid > p.split) nvalid = p.split - col;
         }
         band_store16(base, pix * (size_t)ld + coff + c, v, nvalid, p.out_f32 != 0, p.accumulate != 0);
+        if (do_stats && j < 4) {
+          // reduce-scatter over the 32 pixels of this warp: 31 shuffles leave the total of value `lane` in vals[0]
+          float vals[32];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const float r = bf2f(f2bf(v[k]));      // statistics of the values as stored
+            vals[k] = r;
+            vals[16 + k] = r * r;
+          }
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const bool upper = (lane & step) != 0;
+#pragma unroll
+            for (int k = 0; k < step; ++k) {
+              const float send = upper ? vals[k] : vals[k + step];
+              const float keep = upper ? vals[k + step] : vals[k];
+              vals[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+            }
+          }
+          st_acc[j] += vals[0];
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+    if (do_stats) {
+      for (int j = 0; j < nchunks && j < 4; ++j) {
+        const int col = j * 16 + (lane & 15);
+        if (col < p.ncols)
+          atomicAdd(p.stats + ((size_t)n * 2 + (lane >> 4)) * p.ncols_pad + col, st_acc[j]);
+      }
     }
   }
 
@@ -273,19 +304,32 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   }
 }
 
+bool conv_band_eligible(const smsut_conv_tc_args* a) {
+  if (a->kind != SMSUT_TC_CONV) return false;
+  if (!(a->ksize == 1 || a->ksize == 3 || a->ksize == 5)) return false;
+  if (a->ksize == 5 && a->nsrc != 1) return false;
+  if (a->w % 128 != 0 || a->bn != 0) return false;
+  const int cc = a->src_c[0];
+  if (!(cc == 16 || cc == 32 || cc == 64)) return false;
+  if (a->nsrc == 2 && a->src_c[1] != cc) return false;
+  if (a->ncols_pad > 256 || a->ncols_pad % 16 != 0) return false;
+  const uint32_t w_bytes = (uint32_t)(a->ksize * a->ksize) * a->nsrc * a->ncols_pad * cc * 2u;
+  if (w_bytes > 96u * 1024u) return false;
+  const char* e = getenv("SMSUT_NO_BAND");
+  if (e && e[0] == '1') return false;
+  return true;
+}
+
+// statistics are fused when the band kernel takes the launch and every column goes to one bf16 destination
+bool conv_band_fuses_stats(const smsut_conv_tc_args* a) {
+  return conv_band_eligible(a) && a->ncols_pad <= 64 && a->out1 == nullptr && !a->out_f32 && !a->accumulate &&
+         a->act == SMSUT_ACT_NONE && a->bias == nullptr;
+}
+
 // returns 1 if the launch was handled by the band kernel, 0 if the shape is not eligible, < 0 on error
 int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
-  if (a->kind != SMSUT_TC_CONV) return 0;
-  if (!(a->ksize == 1 || a->ksize == 3 || a->ksize == 5)) return 0;
-  if (a->w % 128 != 0) return 0;
+  if (!conv_band_eligible(a)) return 0;
   const int cc = a->src_c[0];
-  if (!(cc == 16 || cc == 32 || cc == 64)) return 0;
-  if (a->nsrc == 2 && a->src_c[1] != cc) return 0;
-  if (a->ncols_pad > 256 || a->ncols_pad % 16 != 0) return 0;
-  {
-    const char* e = getenv("SMSUT_NO_BAND");
-    if (e && e[0] == '1') return 0;
-  }
   BandParams p;
   memset(&p, 0, sizeof(p));
   p.n = a->n; p.h = a->h; p.w = a->w;
@@ -331,6 +375,11 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   p.out1 = a->out1; p.ld1 = a->out1_ld; p.coff1 = a->out1_coff; p.split = a->out1 ? a->split : 0;
   p.bias = a->bias; p.act = a->act; p.slope = a->slope;
   p.accumulate = a->accumulate; p.out_f32 = a->out_f32;
+  p.stats = nullptr;
+  if (a->stats != nullptr) {
+    SMSUT_CHECK(conv_band_fuses_stats(a), -1, "stats requested for a shape that does not fuse them");
+    p.stats = a->stats;
+  }
   SMSUT_CHECK(a->out0 != nullptr, -1, "null output");
   if (p.split > 0) SMSUT_CHECK(p.split % 16 == 0, -1, "split must be a multiple of 16");
 

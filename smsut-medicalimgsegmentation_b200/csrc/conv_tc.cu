@@ -356,6 +356,7 @@ int choose_tile(int n, int h, int w, int* tn, int* th, int* tw) {
 
 void count_launch();
 int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream);
+bool conv_band_fuses_stats(const smsut_conv_tc_args* a);
 
 static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a != nullptr, -1, "null args");
@@ -367,6 +368,8 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
                 "source %d channels (%d, ld %d) must be a positive multiple of 16", s, a->src_c[s], a->src_ld[s]);
   SMSUT_CHECK(a->ncols_pad % 16 == 0 && a->ncols <= a->ncols_pad && a->ncols > 0, -1, "bad ncols/ncols_pad");
 
+  if (a->stats != nullptr)
+    SMSUT_CHECK(conv_band_fuses_stats(a), -1, "conv_tc: stats requested but smsut_conv_tc_fuses_stats() is 0 for this shape");
   // wide, narrow-channel layers: the band kernel (each input row fetched once, taps by descriptor arithmetic)
   if (a->bn == 0 && a->ncols_pad % 16 == 0 && a->src_c[0] % 16 == 0) {
     const int rb = conv_band_try(a, stream);
@@ -507,6 +510,9 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
 
 }  // namespace smsut
 
+extern "C" int smsut_conv_tc_fuses_stats(const smsut_conv_tc_args* a) {
+  return (a != nullptr && a->ncols_pad % 16 == 0 && a->src_c[0] % 16 == 0 && smsut::conv_band_fuses_stats(a)) ? 1 : 0;
+}
 extern "C" int smsut_conv_tc(const smsut_conv_tc_args* a, smsut_stream_t stream) {
   return smsut::conv_tc_impl(a, reinterpret_cast<cudaStream_t>(stream));
 }

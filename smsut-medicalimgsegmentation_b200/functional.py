@@ -141,43 +141,51 @@ class ConvFn(Function):
     the same input in the same node (BasicBlock's conv1 + shortcut1) so the input gets ONE gradient."""
 
     @staticmethod
-    def forward(ctx, pw, weight, pw2, weight2, *xs):
+    def forward(ctx, want_stats, pw, weight, pw2, weight2, *xs):
+        """returns (y, stats) or (y, stats, y2, stats2): stats = InstanceNorm statistics of the conv output
+        (fused into the conv epilogue on the wide layers; non-differentiable), or an empty tensor if not wanted"""
         ctx.pw, ctx.pw2 = pw, pw2
         ctx.save_for_backward(weight, weight2, *xs)
-        y = ops.conv_fprop(list(xs), pw)
+        if want_stats:
+            y, st = ops.conv_fprop(list(xs), pw, want_stats=True)
+        else:
+            y, st = ops.conv_fprop(list(xs), pw), torch.empty(0, device=xs[0].device)
+        ctx.mark_non_differentiable(st)
         if pw2 is None:
-            return y
-        return y, ops.conv_fprop(list(xs), pw2)
+            return y, st
+        y2, st2 = ops.conv_fprop(list(xs), pw2, want_stats=True)
+        ctx.mark_non_differentiable(st2)
+        return y, st, y2, st2
 
     @staticmethod
-    def backward(ctx, dy, dy2=None):
+    def backward(ctx, dy, _ds=None, dy2=None, _ds2=None):
         weight, weight2, *xs = ctx.saved_tensors
         pw, pw2 = ctx.pw, ctx.pw2
         dy = _c(dy)
-        need_x = any(ctx.needs_input_grad[4:])
+        need_x = any(ctx.needs_input_grad[5:])
         splits = [x.shape[3] for x in xs]
         if torch.is_grad_enabled():
             assert pw2 is None and len(xs) == 1, "double backward is implemented for single-source convs"
             dx = ConvDgradFn.apply(pw, weight, dy) if need_x else None
             dw = None
-            if ctx.needs_input_grad[1] and not _inputs_only_global[0]:
+            if ctx.needs_input_grad[2] and not _inputs_only_global[0]:
                 dw = ops.conv_wgrad(xs, dy.detach(), pw)
-            return None, dw, None, None, dx
+            return None, None, dw, None, None, dx
         dxs = [None] * len(xs)
         if need_x:
             dxs = ops.conv_dgrad(dy, pw, splits)
         dw = dw2 = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[2]:
             t = _target(weight)
             dw = _ret(ops.conv_wgrad(xs, dy, pw, out=t), t)
         if pw2 is not None:
             dy2 = _c(dy2)
             if need_x:
                 ops.conv_dgrad_accumulate(dy2, pw2, dxs)
-            if ctx.needs_input_grad[3]:
+            if ctx.needs_input_grad[4]:
                 t = _target(weight2)
                 dw2 = _ret(ops.conv_wgrad(xs, dy2, pw2, out=t), t)
-        return (None, dw, None, dw2, *dxs)
+        return (None, None, dw, None, dw2, *dxs)
 
 
 class ConvTFn(Function):
@@ -312,9 +320,11 @@ class INActFn(Function):
     """out = act( IN(xa; ga, ba) [+ IN(xb; gb, bb)] [+ res] )  (network/blocks.py:66-80, 99-117)"""
 
     @staticmethod
-    def forward(ctx, xa, ga, ba, xb, gb, bb, res, act, c_params):
-        sa = ops.in_stats(xa)
-        sb = ops.in_stats(xb) if xb is not None else None
+    def forward(ctx, xa, ga, ba, xb, gb, bb, res, act, c_params, sa=None, sb=None):
+        if sa is None:
+            sa = ops.in_stats(xa)
+        if xb is not None and sb is None:
+            sb = ops.in_stats(xb)
         out = ops.in_apply(xa, sa, ga, ba, xb, sb, gb, bb, res=res, act=act, slope=SLOPE, c_params=c_params)
         ctx.act, ctx.cp, ctx.has_res = act, c_params, res is not None
         ctx.save_for_backward(xa, sa, ga, xb, sb, gb, out, ba, bb)
@@ -334,7 +344,7 @@ class INActFn(Function):
             dga = dba = dgb = dbb = None
             if not _inputs_only_global[0]:
                 _, dga, dba, _, dgb, dbb, _ = ops.in_bwd(dout.detach(), out, xa, sa, ga, xb, sb, gb, False, act, SLOPE, cp)
-            return dxa, dga, dba, dxb, dgb, dbb, (g if want_res else None), None, None
+            return dxa, dga, dba, dxb, dgb, dbb, (g if want_res else None), None, None, None, None
         targets = None
         need = ctx.needs_input_grad
         if not (need[1] or need[2] or need[4] or need[5]):
@@ -346,12 +356,12 @@ class INActFn(Function):
                 targets = tg
         dxa, dga, dba, dxb, dgb, dbb, dres = ops.in_bwd(dout, out, xa, sa, ga, xb, sb, gb, want_res, act, SLOPE, cp,
                                                         targets=targets)
-        return dxa, dga, dba, dxb, dgb, dbb, dres, None, None
+        return dxa, dga, dba, dxb, dgb, dbb, dres, None, None, None, None
 
 
-def in_act(xa, norm_a, xb=None, norm_b=None, res=None, act=ACT_LRELU, c_params=None):
+def in_act(xa, norm_a, xb=None, norm_b=None, res=None, act=ACT_LRELU, c_params=None, stats_a=None, stats_b=None):
     return INActFn.apply(xa, norm_a.weight, norm_a.bias, xb, norm_b.weight if norm_b is not None else None,
-                         norm_b.bias if norm_b is not None else None, res, act, c_params)
+                         norm_b.bias if norm_b is not None else None, res, act, c_params, stats_a, stats_b)
 
 
 # ----------------------------------------------------------------------------------------------

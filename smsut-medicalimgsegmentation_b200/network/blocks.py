@@ -53,13 +53,16 @@ class Conv2d(nn.Conv2d):
             self._table.refresh(force=True)
         return pw
 
-    def forward_nhwc(self, xs):
-        """xs: list of NHWC tensors (channel-concatenated input without the concat)"""
+    def forward_nhwc(self, xs, with_stats=False):
+        """xs: list of NHWC tensors (channel-concatenated input without the concat).  with_stats: also return the
+        InstanceNorm statistics of the output (fused into the conv epilogue on the wide layers), or None."""
         if self.tensor_core:
-            return Fn.ConvFn.apply(self.ensure_packed(), self.weight, None, None, *xs)
+            y, st = Fn.ConvFn.apply(with_stats, self.ensure_packed(), self.weight, None, None, *xs)
+            return (y, st) if with_stats else y
         assert len(xs) == 1
-        return Fn.DirectConvFn.apply(xs[0], self.weight, self.bias, self.stride[0], self.padding[0], self.fused_act,
-                                     self.out_pad, self.out_f32)
+        y = Fn.DirectConvFn.apply(xs[0], self.weight, self.bias, self.stride[0], self.padding[0], self.fused_act,
+                                  self.out_pad, self.out_f32)
+        return (y, None) if with_stats else y
 
     def forward(self, x):
         if not self.tensor_core and self.in_channels == 1 and x.dtype == torch.float32:
@@ -232,16 +235,16 @@ class BasicBlock(nn.Module):
     def forward_nhwc(self, xs):
         act = _act_code(self.relu)
         if self.downsample:
-            c1, cs = Fn.ConvFn.apply(self.conv1.ensure_packed(), self.conv1.weight, self.shortcut1.ensure_packed(),
-                                     self.shortcut1.weight, *xs)
+            c1, s1, cs, ss = Fn.ConvFn.apply(True, self.conv1.ensure_packed(), self.conv1.weight,
+                                             self.shortcut1.ensure_packed(), self.shortcut1.weight, *xs)
         else:
             assert len(xs) == 1
-            c1, cs = self.conv1.forward_nhwc(xs), None
-        a1 = Fn.in_act(c1, self.bn1, act=act)
-        c2 = self.conv2.forward_nhwc([a1])
+            (c1, s1), cs, ss = self.conv1.forward_nhwc(xs, with_stats=True), None, None
+        a1 = Fn.in_act(c1, self.bn1, act=act, stats_a=s1)
+        c2, s2 = self.conv2.forward_nhwc([a1], with_stats=True)
         if self.downsample:
-            return Fn.in_act(c2, self.bn2, xb=cs, norm_b=self.shortcut2, act=act)
-        return Fn.in_act(c2, self.bn2, res=xs[0], act=act)
+            return Fn.in_act(c2, self.bn2, xb=cs, norm_b=self.shortcut2, act=act, stats_a=s2, stats_b=ss)
+        return Fn.in_act(c2, self.bn2, res=xs[0], act=act, stats_a=s2)
 
     def forward(self, x):
         return to_nchw(self.forward_nhwc(_sources(x)))
@@ -266,14 +269,15 @@ class BottleBlock(nn.Module):
     def forward_nhwc(self, x):
         act = _act_code(self.relu)
         identity = Fn.AvgPoolFn.apply(x) if self.stride == 2 else x
-        out = Fn.in_act(self.conv1.forward_nhwc([x]), self.bn1, act=act)
+        c1, s1 = self.conv1.forward_nhwc([x], with_stats=True)
+        out = Fn.in_act(c1, self.bn1, act=act, stats_a=s1)
         if self.stride == 2:
             out = Fn.AvgPoolFn.apply(out)
-        out = self.conv2.forward_nhwc([out])
+        out, s2 = self.conv2.forward_nhwc([out], with_stats=True)
         if self.downsample is not None:
-            cs = self.downsample[0].forward_nhwc([identity])
-            return Fn.in_act(out, self.bn2, xb=cs, norm_b=self.downsample[1], act=act)
-        return Fn.in_act(out, self.bn2, res=identity, act=act)
+            cs, ss = self.downsample[0].forward_nhwc([identity], with_stats=True)
+            return Fn.in_act(out, self.bn2, xb=cs, norm_b=self.downsample[1], act=act, stats_a=s2, stats_b=ss)
+        return Fn.in_act(out, self.bn2, res=identity, act=act, stats_a=s2)
 
     def forward(self, x):
         return to_nchw(self.forward_nhwc(to_nhwc(x)))
@@ -282,8 +286,9 @@ class BottleBlock(nn.Module):
 def _stem(conv, bn, relu, x):
     """5x5 stem conv (tcgen05, 25 taps over a 16-channel zero-padded bf16 input) -> IN -> act; the 8-channel result
     lives in a 16-channel tensor (channels 8..15 are zero) so the next conv reads it directly."""
-    y = conv.forward_nhwc([x])
-    return Fn.in_act(y, bn, act=_act_code(relu), c_params=bn.num_features if y.shape[3] != bn.num_features else None)
+    y, st = conv.forward_nhwc([x], with_stats=True)
+    return Fn.in_act(y, bn, act=_act_code(relu), c_params=bn.num_features if y.shape[3] != bn.num_features else None,
+                     stats_a=st)
 
 
 def _image_nhwc(x):

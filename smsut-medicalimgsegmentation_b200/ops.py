@@ -162,9 +162,8 @@ class PackTable:
 # ----------------------------------------------------------------------------------------------
 # tensor-core convolutions
 # ----------------------------------------------------------------------------------------------
-def conv_tc(kind, ksize, n, h, w, srcs, wpack, ncols, ncols_pad, out0, out0_ld, out0_coff=0, out1=None, out1_ld=0,
-            out1_coff=0, split=0, bias=None, act=ACT_NONE, slope=0.01, accumulate=False, out_f32=False, bn=0):
-    """srcs: list of (tensor, channels_used, channel_pitch)."""
+def _conv_args(kind, ksize, n, h, w, srcs, wpack, ncols, ncols_pad, out0, out0_ld, out0_coff=0, out1=None, out1_ld=0,
+               out1_coff=0, split=0, bias=None, act=ACT_NONE, slope=0.01, accumulate=False, out_f32=False, bn=0):
     a = ConvTcArgs()
     a.kind, a.ksize, a.n, a.h, a.w, a.nsrc = kind, ksize, n, h, w, len(srcs)
     for i, (t, c, ld) in enumerate(srcs):
@@ -179,18 +178,33 @@ def conv_tc(kind, ksize, n, h, w, srcs, wpack, ncols, ncols_pad, out0, out0_ld, 
         a.out1, a.out1_ld, a.out1_coff, a.split = out1.data_ptr(), out1_ld, out1_coff, split
     a.bias = bias.data_ptr() if bias is not None else 0
     a.act, a.slope, a.accumulate, a.out_f32, a.bn = act, slope, int(accumulate), int(out_f32), bn
-    call("smsut_conv_tc", C.byref(a), _stream())
+    a.stats = 0
+    return a
 
 
-def conv_fprop(xs, pw, bias=None, act=ACT_NONE, out_f32=False):
-    """y = conv(cat(xs, channel), W) for a 1x1 / 3x3 stride-1 'same' conv.  xs: NHWC bf16 tensors."""
+def conv_tc(*args, **kw):
+    """srcs: list of (tensor, channels_used, channel_pitch)."""
+    call("smsut_conv_tc", C.byref(_conv_args(*args, **kw)), _stream())
+
+
+def conv_fprop(xs, pw, bias=None, act=ACT_NONE, out_f32=False, want_stats=False):
+    """y = conv(cat(xs, channel), W) for a 1x1 / 3x3 / 5x5 stride-1 'same' conv.  xs: NHWC bf16 tensors.
+    want_stats: also return the InstanceNorm statistics (n, 2, C) of y -- fused into the conv epilogue where the
+    library supports it (smsut_conv_tc_fuses_stats), otherwise by the statistics kernel."""
     n, h, w, _ = xs[0].shape
     srcs = [(x, x.shape[3], x.shape[3]) for x in xs]
     assert sum(s[1] for s in srcs) == pw.cin_pad, (sum(s[1] for s in srcs), pw.cin_pad)
     y = torch.empty((n, h, w, pw.cout_pad), dtype=F32 if out_f32 else BF16, device=xs[0].device)
-    conv_tc(TC_CONV, pw.kh, n, h, w, srcs, pw.fprop, pw.cout_pad, pw.cout_pad, y, pw.cout_pad, bias=bias, act=act,
-            out_f32=out_f32)
-    return y
+    a = _conv_args(TC_CONV, pw.kh, n, h, w, srcs, pw.fprop, pw.cout_pad, pw.cout_pad, y, pw.cout_pad, bias=bias, act=act,
+                   out_f32=out_f32)
+    stats = None
+    if want_stats and _lib.lib.smsut_conv_tc_fuses_stats(C.byref(a)) == 1:
+        stats = zeros((n, 2, pw.cout_pad), y.device)
+        a.stats = stats.data_ptr()
+    call("smsut_conv_tc", C.byref(a), _stream())
+    if not want_stats:
+        return y
+    return y, (stats if stats is not None else in_stats(y))
 
 
 def conv_dgrad(dy, pw, splits=None):

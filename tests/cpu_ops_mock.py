@@ -68,11 +68,12 @@ def _pad_c(t, c):
     return F.pad(t, (0, c - t.shape[-1])) if t.shape[-1] < c else t
 
 
-def conv_fprop(xs, pw, bias=None, act=0, out_f32=False):
+def conv_fprop(xs, pw, bias=None, act=0, out_f32=False, want_stats=False):
     x = torch.cat([_nchw(t) for t in xs], 1)[:, :pw.cin]
     y = F.conv2d(x, _wq(pw), bias, padding=pw.kh // 2)
     y = _act(y, act)
-    return _pad_c(_nhwc(y, F32 if out_f32 else _AD.t), pw.cout_pad)
+    y = _pad_c(_nhwc(y, F32 if out_f32 else _AD.t), pw.cout_pad)
+    return (y, in_stats(y)) if want_stats else y
 
 
 def _dgrad_full(dy, pw):

@@ -463,3 +463,15 @@ def test_fused_head_backward(ops, cout, tanh):
     dx, dw, db = ops.head1x1_bwd(nhwc(x), dy.permute(0, 2, 3, 1).contiguous(), y if tanh else None, wt, True,
                                  want_bias=True)
     assert rel(nchw(dx), xr.grad) < 1e-2 and rel(dw, wr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("cins,cout,h", [([16], 16, 256), ([16, 16], 16, 256), ([32], 32, 128), ([16], 32, 128), ([64], 64, 64)])
+def test_conv_fused_instance_norm_statistics(ops, cins, cout, h):
+    """statistics from the conv epilogue (wide layers) or the statistics kernel == sums over the stored output"""
+    torch.manual_seed(16)
+    xs = [rnd(2, c, h, h) for c in cins]
+    wt = rnd(cout, sum(cins), 3, 3, scale=0.1)
+    pw = make_pack(ops, wt)
+    y, st = ops.conv_fprop([nhwc(x) for x in xs], pw, want_stats=True)
+    yf = y.float()
+    assert rel(st[:, 0], yf.sum((1, 2))) < 1e-4 and rel(st[:, 1], (yf * yf).sum((1, 2))) < 1e-4
