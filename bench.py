@@ -282,6 +282,13 @@ def run_ours(args):
                                           f"({sec:.1f} s), fp32, torch CPU"}
     if par.rank == 0:
         print(json.dumps(line), flush=True)
+    if par.world > 1:
+        # tearing down a NCCL communicator that live CUDA graphs still reference can block at exit: everything is
+        # measured and printed, so synchronise, agree that every rank is done, and leave without the teardown
+        torch.cuda.synchronize()
+        par.barrier()
+        sys.stdout.flush()
+        os._exit(0)
     par.close()
 
 

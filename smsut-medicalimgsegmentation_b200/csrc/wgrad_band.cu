@@ -1,11 +1,14 @@
-// "Band" weight gradient for the wide, narrow-channel layers (W % 128 == 0, Cin-chunk in {16, 32}, Cout <= 64):
+// "Band" weight gradient of the stride-1 'same' convolutions (every 1x1 / 3x3 / 5x5 layer with W % 16 == 0):
 //   dW[co][ci][ty][tx] = sum_{n,h,w} dy[n,h,w,co] * x[n, h+ty-r, w+tx-r, ci]
-// One CTA walks down a strip of 128 pixels x R rows.  Each x row (with its halo) and each dy row is fetched by TMA
-// once into a ring of row slots; per output row and vertical tap ty ONE chain of 8 UMMAs (K = 16 pixels each)
-// accumulates D_ty[(tx, ci)][co]: the horizontal taps are the M-blocks of the MN-major A operand, whose leading
-// byte offset is one pixel row (LBO = pitch), i.e. block tx is the same smem row band started tx pixels later.
-// Accumulators stay in TMEM for the whole strip; the epilogue adds them to the fp32 OIHW gradient with atomics.
-// L2->SM traffic per row: (128 + 2r)*Cin*2 + 128*Cout*2 bytes, instead of (1 + taps) tiles in wgrad_tc_kernel.
+// wgrad_tc_kernel re-reads a shifted x tile per tap (and the dy tile per column group): ncu showed it bound by
+// L2->SM operand traffic.  Here one CTA owns (image, row segment, <=128-pixel column tile, <=64-channel chunk of x,
+// <=64-channel chunk of dy) and walks down the rows.  Each x row (with halo) and dy row is fetched by TMA ONCE into a
+// ring of row slots.  Per row, 16-pixel K chunk and vertical tap ty, ONE UMMA (two when the x chunk has 64
+// channels) accumulates D_ty[(tx, ci)][co]: the horizontal taps are the M-blocks of the MN-major A operand whose
+// leading-dimension byte offset is ONE PIXEL ROW (LBO = pitch), i.e. block tx is the same smem band started tx
+// pixels later (the swizzle phase follows the absolute smem address: scripts/rowshift_probe.py).  A 16-pixel K chunk
+// never crosses an image row, so any W % 16 == 0 works.  Accumulators stay in TMEM for the whole segment; the
+// epilogue adds them to the fp32 OIHW gradient with atomics.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,7 +27,10 @@ constexpr int kWbMaxSlots = 12;
 
 struct WgradBandParams {
   int n, h, w, ks, r;
-  int xc, dc;                   // channels of the x / dy tiles (16 or 32 / 16, 32 or 64)
+  int tw, kchunks;              // pixels per row tile (16..128), tw / 16
+  int xcc, dcc;                 // channels of the x / dy chunk (16, 32 or 64)
+  int xchunks, dchunks;         // chunks along Cin / Cout (grid dimensions)
+  int groups, tx_per_group;     // UMMAs per (row, K chunk, ty): ceil(ks * xcc / 128); 128 / xcc
   int wtiles, segs, rows_per_seg;
   int nslots;
   uint32_t x_slot_bytes, d_slot_bytes, d_base_off;
@@ -55,7 +61,8 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const int seg = b % p.segs; b /= p.segs;
   const int wt = b % p.wtiles; b /= p.wtiles;
   const int n = b;
-  const int w0 = wt * 128;
+  const int xch = blockIdx.y, dch = blockIdx.z;
+  const int w0 = wt * p.tw;
   const int h_begin = seg * p.rows_per_seg;
   int h_end = h_begin + p.rows_per_seg;
   if (h_end > p.h) h_end = p.h;
@@ -91,28 +98,32 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       uint32_t xph = 0, dph = 0;
       for (int j = 0; j < nrows_in; ++j) {
         mbar_wait(&x_empty[xs], xph ^ 1u);
-        mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(128 + 2 * p.r) * p.x_pitch);
-        tma_load_4d(smem_al + (size_t)xs * p.x_slot_bytes, &map_x, &x_full[xs], 0, w0 - p.r, h_begin - p.r + j, n);
+        mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(p.tw + 2 * p.r) * p.x_pitch);
+        tma_load_4d(smem_al + (size_t)xs * p.x_slot_bytes, &map_x, &x_full[xs], xch * p.xcc, w0 - p.r, h_begin - p.r + j,
+                    n);
         if (++xs == nslots) { xs = 0; xph ^= 1u; }
         if (j < nrows) {
           mbar_wait(&d_empty[ds], dph ^ 1u);
-          mbar_arrive_expect_tx(&d_full[ds], 128u * p.d_pitch);
-          tma_load_4d(smem_al + p.d_base_off + (size_t)ds * p.d_slot_bytes, &map_dy, &d_full[ds], 0, w0, h_begin + j, n);
+          mbar_arrive_expect_tx(&d_full[ds], (uint32_t)p.tw * p.d_pitch);
+          tma_load_4d(smem_al + p.d_base_off + (size_t)ds * p.d_slot_bytes, &map_dy, &d_full[ds], dch * p.dcc, w0,
+                      h_begin + j, n);
           if (++ds == nslots) { ds = 0; dph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // A = x slot, MN-major, M = (tx, ci): M-blocks of xc channels one pixel row apart (LBO = pitch);
-    // B = dy slot, MN-major, N = dc;  K = pixels (16 per UMMA)
+    // A = x slot, MN-major, M = (tx, ci): M-blocks of xcc channels one pixel row apart (LBO = pitch);
+    // B = dy slot, MN-major, N = dcc;  K = pixels (16 per UMMA)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(p.dc >> 3) << 17) | ((128u >> 4) << 24);
+                           ((uint32_t)(p.dcc >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t a_hi = make_smem_desc(0, p.x_pitch, 8u * p.x_pitch, p.x_layout) & 0xFFFFFFFFFFFF0000ull;
     const uint64_t b_hi = make_smem_desc(0, 0, 8u * p.d_pitch, p.d_layout) & 0xFFFFFFFFFFFF0000ull;
     const uint32_t x_base = smem_base >> 4, d_base = (smem_base + p.d_base_off) >> 4;
     const uint32_t xslot_u = p.x_slot_bytes >> 4, dslot_u = p.d_slot_bytes >> 4;
     const uint32_t xk_u = (16u * p.x_pitch) >> 4, dk_u = (16u * p.d_pitch) >> 4;
+    const uint32_t grp_u = ((uint32_t)p.tx_per_group * p.x_pitch) >> 4;   // next group of horizontal taps
+    const int kchunks = p.kchunks, groups = p.groups;
     int rows_ready = 0, ready_slot = 0, base_slot = 0, dslot = 0;
     uint32_t ready_phase = 0, dphase = 0;
     for (int i = 0; i < nrows; ++i) {
@@ -130,11 +141,13 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           int slot = base_slot + ty;
           if (slot >= nslots) slot -= nslots;
           const uint32_t a0 = x_base + (uint32_t)slot * xslot_u;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(ty * p.dc);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(d_tmem, a_hi | (uint64_t)((a0 + k * xk_u) & 0x3FFFu), b_hi | (uint64_t)((b0 + k * dk_u) & 0x3FFFu),
-                      idesc, (i | k) != 0 ? 1u : 0u);
+          for (int g = 0; g < groups; ++g) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((ty * groups + g) * p.dcc);
+            const uint32_t ag = a0 + (uint32_t)g * grp_u;
+            for (int k = 0; k < kchunks; ++k)
+              umma_bf16(d_tmem, a_hi | (uint64_t)((ag + k * xk_u) & 0x3FFFu), b_hi | (uint64_t)((b0 + k * dk_u) & 0x3FFFu),
+                        idesc, (i | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&x_empty[base_slot]);   // oldest x row of the window
         umma_commit(&d_empty[dslot]);
@@ -145,21 +158,23 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (++dslot == nslots) { dslot = 0; dphase ^= 1u; }
     }
   } else {
-    // ===================== epilogue: D_ty[(tx, ci)][co] -> atomics into dW[co][ci_off + ci][ty][tx] ==========
+    // ===================== epilogue: D_{ty,g}[(tx, ci)][co] -> atomics into dW[co][ci_off + ci][ty][tx] ==========
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int tx = row / p.xc, ci = row - tx * p.xc;
-    const bool row_ok = tx < KS && ci < p.c_valid;
+    const int txl = row / p.xcc, cil = row - txl * p.xcc;
+    const int ci = xch * p.xcc + cil;
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    const int nch = (KS * p.dc) >> 4;
+    const int nch = (KS * p.groups * p.dcc) >> 4;
     for (int j = 0; j < nch; ++j) {
       uint32_t raw[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
       tmem_ld_wait();
-      if (!row_ok) continue;
       const int col = j * 16;
-      const int ty = col / p.dc, co0 = col - ty * p.dc;
+      const int region = col / p.dcc, co0 = dch * p.dcc + (col - region * p.dcc);
+      const int ty = region / p.groups, g = region - ty * p.groups;
+      const int tx = g * p.tx_per_group + txl;
+      if (txl >= p.tx_per_group || tx >= KS || ci >= p.c_valid) continue;
       const int tap = ty * KS + tx;
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
@@ -179,16 +194,13 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 }
 
 static uint32_t layout_for(int c) { return c == 64 ? 2u : (c == 32 ? 4u : 6u); }
+static int chunk_of(int c) { int k = 64; while (c % k) k >>= 1; return k; }
 
 // returns 1 if handled, 0 if not eligible, < 0 on error
 int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   if (a->kind != SMSUT_TC_CONV) return 0;
   if (!(a->ksize == 1 || a->ksize == 3 || a->ksize == 5)) return 0;
-  if (a->w % 128 != 0) return 0;
-  const int xc = a->x_c, dc = a->dy_c;
-  if (!(xc == 16 || xc == 32)) return 0;
-  if (!(dc == 16 || dc == 32 || dc == 64)) return 0;
-  if (a->ksize * xc > 128) return 0;                 // the horizontal taps must fit the 128 accumulator rows
+  if (a->w % 16 != 0 || a->x_c % 16 != 0 || a->dy_c % 16 != 0) return 0;
   {
     const char* e = getenv("SMSUT_NO_BAND");
     if (e && e[0] == '1') return 0;
@@ -196,31 +208,44 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   WgradBandParams p;
   memset(&p, 0, sizeof(p));
   p.n = a->n; p.h = a->h; p.w = a->w; p.ks = a->ksize; p.r = a->ksize / 2;
-  p.xc = xc; p.dc = dc;
-  p.x_pitch = (uint32_t)xc * 2u; p.d_pitch = (uint32_t)dc * 2u;
-  p.x_layout = layout_for(xc); p.d_layout = layout_for(dc);
-  // the last M-block starts (128/xc - 1) pixel rows into the band and K runs over 128 rows: pad the slot
-  p.x_slot_bytes = (((uint32_t)(128 + 2 * p.r + 128 / xc) * p.x_pitch) + 1023u) & ~1023u;
-  p.d_slot_bytes = ((128u * p.d_pitch) + 1023u) & ~1023u;
+  // column tile: the largest multiple of 16 (<= 128) dividing W
+  int tw = 128;
+  while (a->w % tw) tw -= 16;
+  p.tw = tw; p.kchunks = tw / 16; p.wtiles = a->w / tw;
+  p.xcc = chunk_of(a->x_c); p.dcc = chunk_of(a->dy_c);
+  p.xchunks = a->x_c / p.xcc; p.dchunks = a->dy_c / p.dcc;
+  p.tx_per_group = 128 / p.xcc;
+  p.groups = (a->ksize + p.tx_per_group - 1) / p.tx_per_group;
+  p.x_pitch = (uint32_t)p.xcc * 2u; p.d_pitch = (uint32_t)p.dcc * 2u;
+  p.x_layout = layout_for(p.xcc); p.d_layout = layout_for(p.dcc);
+  // A reads up to (groups * tx_per_group - 1) pixel rows past the last K chunk: pad the slot accordingly
+  p.x_slot_bytes = (((uint32_t)(tw + 2 * p.r + p.groups * p.tx_per_group) * p.x_pitch) + 1023u) & ~1023u;
+  p.d_slot_bytes = (((uint32_t)tw * p.d_pitch) + 1023u) & ~1023u;
   p.nslots = 2 * p.r + 1 + 4;
   if (p.nslots > kWbMaxSlots) return 0;
   p.d_base_off = (uint32_t)p.nslots * p.x_slot_bytes;
+  const size_t smem = (size_t)p.nslots * (p.x_slot_bytes + p.d_slot_bytes) + 2048;
+  if (smem > 200u * 1024u) return 0;
+  const int cols = a->ksize * p.groups * p.dcc;
+  if (cols > 512) return 0;
   uint32_t tc = 32;
-  while ((int)tc < a->ksize * dc) tc <<= 1;
+  while ((int)tc < cols) tc <<= 1;
   p.tmem_cols = tc;
   p.dw = a->dw;
-  p.cout = dc < a->cout_total ? dc : a->cout_total;
+  p.cout = a->dy_c < a->cout_total ? a->dy_c : a->cout_total;
   p.cin_total = a->cin_total; p.ci_off = a->ci_off;
-  p.c_valid = a->c_valid > 0 ? a->c_valid : xc;
+  p.c_valid = a->c_valid > 0 ? a->c_valid : a->x_c;
   p.taps = a->ksize * a->ksize;
   SMSUT_CHECK(a->dw != nullptr, -1, "null dw");
 
-  p.wtiles = a->w / 128;
+  // row segments: ~2 CTAs per SM overall, at least 2 rows each (every segment re-reads 2r halo rows)
   const int sms = device_sm_count();
-  int segs = (3 * sms + a->n * p.wtiles - 1) / (a->n * p.wtiles);
+  const int base = a->n * p.wtiles * p.xchunks * p.dchunks;
+  int segs = (2 * sms + base - 1) / base;
   if (segs < 1) segs = 1;
   int rows = (a->h + segs - 1) / segs;
-  if (rows < 8) rows = a->h < 8 ? a->h : 8;
+  const int min_rows = a->ksize > 1 ? 4 : 2;
+  if (rows < min_rows) rows = a->h < min_rows ? a->h : min_rows;
   {
     const char* e = getenv("SMSUT_BAND_ROWS");
     if (e && atoi(e) > 0) rows = atoi(e);
@@ -229,15 +254,14 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   p.segs = (a->h + rows - 1) / rows;
 
   CUtensorMap map_x, map_dy;
-  int rc = make_act_map(&map_x, a->x, xc, a->w, a->h, a->n, a->x_ld, (int64_t)a->x_ld * a->w,
-                        (int64_t)a->x_ld * a->w * a->h, xc, 128 + 2 * p.r, 1, 1);
+  int rc = make_act_map(&map_x, a->x, a->x_c, a->w, a->h, a->n, a->x_ld, (int64_t)a->x_ld * a->w,
+                        (int64_t)a->x_ld * a->w * a->h, p.xcc, tw + 2 * p.r, 1, 1);
   if (rc) return rc;
-  rc = make_act_map(&map_dy, a->dy, dc, a->w, a->h, a->n, a->dy_ld, (int64_t)a->dy_ld * a->w,
-                    (int64_t)a->dy_ld * a->w * a->h, dc, 128, 1, 1);
+  rc = make_act_map(&map_dy, a->dy, a->dy_c, a->w, a->h, a->n, a->dy_ld, (int64_t)a->dy_ld * a->w,
+                    (int64_t)a->dy_ld * a->w * a->h, p.dcc, tw, 1, 1);
   if (rc) return rc;
 
-  const size_t smem = (size_t)p.nslots * (p.x_slot_bytes + p.d_slot_bytes) + 2048;
-  const unsigned grid = (unsigned)(a->n * p.wtiles * p.segs);
+  dim3 grid((unsigned)(a->n * p.wtiles * p.segs), (unsigned)p.xchunks, (unsigned)p.dchunks);
   bool launched = false;
 #define WB_CASE(KS_)                                                                                               \
   if (!launched && a->ksize == KS_) {                                                                              \

@@ -45,12 +45,18 @@ class accumulate_param_grads:
     parameters' existing `.grad` tensors (the flat gradient buffer of optim.py) and autograd is handed `None`:
     no zero-fill + add pair per parameter.  Outside it the Functions return fresh gradient tensors as usual."""
 
+    def __init__(self, side_streams=True):
+        self.side = side_streams
+
     def __enter__(self):
         self.prev = _accumulate[0]
         _accumulate[0] = True
+        ops.side_streams_enable(self.side)     # wgrad kernels run beside the dgrad chain (ops._Side)
 
     def __exit__(self, *a):
         _accumulate[0] = self.prev
+        ops.side_streams_enable(False)
+        ops.side_join()
 
 
 def _target(param):

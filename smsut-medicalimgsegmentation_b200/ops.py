@@ -90,6 +90,58 @@ def zeros(shape, device, dtype=F32):
 
 
 # ----------------------------------------------------------------------------------------------
+# side streams: weight-gradient kernels run beside the dgrad chain
+# ----------------------------------------------------------------------------------------------
+class _Side:
+    """The weight gradients of a backward pass are leaves of the dependency graph: nothing reads them before the
+    optimizer step.  Inside `side_streams()` they are launched on side streams forked from the current stream
+    (captured as parallel branches of the step's CUDA graph), so they fill the SMs the narrow dgrad / norm kernels
+    of the critical path leave idle.  Their operands are held until the join, so the caching allocator cannot hand
+    the memory to a later kernel of the main stream while a side kernel still reads it."""
+    n_streams = 2
+    streams = {}        # device index -> [streams]
+    active = False
+    nxt = 0
+    held = []
+    used = []
+
+
+def side_streams_enable(on=True):
+    _Side.active = bool(on) and _Side.n_streams > 0
+
+
+def side_run(fn, keep):
+    """fn() on a side stream ordered after everything issued so far on the current stream (or inline when side
+    streams are off).  `keep`: the tensors fn's kernels read."""
+    if not _Side.active:
+        fn()
+        return
+    main = torch.cuda.current_stream()
+    pool = _Side.streams.get(main.device_index)
+    if pool is None:
+        pool = [torch.cuda.Stream(device=main.device) for _ in range(_Side.n_streams)]
+        _Side.streams[main.device_index] = pool
+    s = pool[_Side.nxt % len(pool)]
+    _Side.nxt += 1
+    s.wait_stream(main)
+    with torch.cuda.stream(s):
+        fn()
+    if s not in _Side.used:
+        _Side.used.append(s)
+    _Side.held.append(keep)
+
+
+def side_join():
+    """the current stream waits for every side kernel issued since the last join"""
+    if _Side.used:
+        main = torch.cuda.current_stream()
+        for s in _Side.used:
+            main.wait_stream(s)
+    _Side.used = []
+    _Side.held = []
+
+
+# ----------------------------------------------------------------------------------------------
 # weight packing
 # ----------------------------------------------------------------------------------------------
 class PackedWeight:
@@ -248,12 +300,18 @@ def conv_wgrad(xs, dy, pw, out=None):
     """fp32 OIHW weight gradient of conv_fprop, accumulated (atomics) into `out` or a fresh zeroed tensor."""
     n, h, w, _ = xs[0].shape
     dw = out if out is not None else torch.zeros_like(pw.weight, dtype=F32)
-    off = 0
-    for x in xs:
-        c = x.shape[3]
-        valid = min(c, pw.cin - off)
-        wgrad_tc(TC_CONV, pw.kh, n, h, w, x, c, dy, pw.cout_pad, dw, pw.cin, off, pw.cout, c_valid=valid)
-        off += c
+
+    def launch():
+        off = 0
+        for x in xs:
+            c = x.shape[3]
+            valid = min(c, pw.cin - off)
+            wgrad_tc(TC_CONV, pw.kh, n, h, w, x, c, dy, pw.cout_pad, dw, pw.cin, off, pw.cout, c_valid=valid)
+            off += c
+    if out is not None:
+        side_run(launch, (list(xs), dy))
+    else:
+        launch()
     return dw
 
 
@@ -276,7 +334,10 @@ def convt_dgrad(dy, pw):
 def convt_wgrad(x, dy, pw, out=None):
     n, h, w, c = x.shape
     dw = out if out is not None else torch.zeros_like(pw.weight, dtype=F32)
-    wgrad_tc(TC_CONVT_FWD, 1, n, h, w, x, c, dy, pw.cout, dw, pw.cin, 0, pw.cout)
+    if out is not None:
+        side_run(lambda: wgrad_tc(TC_CONVT_FWD, 1, n, h, w, x, c, dy, pw.cout, dw, pw.cin, 0, pw.cout), (x, dy))
+    else:
+        wgrad_tc(TC_CONVT_FWD, 1, n, h, w, x, c, dy, pw.cout, dw, pw.cin, 0, pw.cout)
     return dw
 
 
@@ -334,13 +395,17 @@ def head1x1_bwd(x, dy, y, weight, want_dx, dw=None, db=None, want_bias=False):
 
 
 def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias, dw=None, db=None):
+    side = dw is not None and (db is not None or not want_bias)     # accumulating into the flat gradient buffer
     dw = dw if dw is not None else torch.zeros_like(weight, dtype=F32)
     if want_bias and db is None:
         db = torch.zeros(weight.shape[0], dtype=F32, device=weight.device)
     if not want_bias:
         db = None
     a = _direct_args(x, weight, dy, stride, pad, None, ACT_NONE, 0.0, False)
-    call("smsut_conv_direct_wgrad", C.byref(a), _p(dw), _p(db), _stream())
+    if side:
+        side_run(lambda: call("smsut_conv_direct_wgrad", C.byref(a), _p(dw), _p(db), _stream()), (x, dy, a))
+    else:
+        call("smsut_conv_direct_wgrad", C.byref(a), _p(dw), _p(db), _stream())
     return dw, db
 
 
