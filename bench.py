@@ -150,7 +150,8 @@ def conv_roofline(torch, ops, batch, reps=5):
         ms = 0.0
         for _ in range(reps):
             flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(300000)   # the GPU spins ~150 us while the host queues the launch: the events bracket
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # the kernel only
             e0.record()
             ops.conv_fprop(xs, pw)
             e1.record()

@@ -83,6 +83,11 @@ typedef struct smsut_wgrad_tc_args {
   int32_t cin_total, ci_off; /* full Cin of the weight and channel offset of this source */
   int32_t cout_total;
   int32_t c_valid;           /* CONV: channels of x that exist in the weight (x may be zero-padded); 0 = all */
+  int32_t dw_layout;         /* 0: dw is OIHW / IOHW (scalar atomics, 36-byte stride between lanes);
+                                1: dw is the tap-major scratch [tap][cout][cin] (conv) / [tap][cin][cout] (convT):
+                                   a thread's 16 accumulator columns are 64 contiguous bytes -> red.global.v4.f32,
+                                   a warp's lanes are contiguous channels in the band kernel; smsut_unpack_wgrads
+                                   folds the scratch into the OIHW gradient once per optimizer step */
 } smsut_wgrad_tc_args;
 
 int smsut_wgrad_tc(const smsut_wgrad_tc_args* a, smsut_stream_t stream);
@@ -270,6 +275,16 @@ typedef struct smsut_pack_entry {
 } smsut_pack_entry;
 /* `table` is a DEVICE array of n entries */
 int smsut_pack_weights(const smsut_pack_entry* table, int32_t n, smsut_stream_t stream);
+
+/* Tap-major weight-gradient scratch -> fp32 master-layout gradient (the mirror image of smsut_pack_weights):
+ *   grad[(m * cols + c) * taps + t] += scratch[(t * rows + m) * cols + c]     rows x cols = Cout x Cin (conv), Cin x Cout (convT)
+ * One launch per network and optimizer step; `table` is a DEVICE array of n entries. */
+typedef struct smsut_unpack_entry {
+  const float* scratch;
+  float* grad;
+  int32_t rows, cols, taps, pad;
+} smsut_unpack_entry;
+int smsut_unpack_wgrads(const smsut_unpack_entry* table, int32_t n, smsut_stream_t stream);
 
 #ifdef __cplusplus
 }

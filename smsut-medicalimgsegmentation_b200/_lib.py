@@ -33,6 +33,7 @@ class WgradTcArgs(C.Structure):
         ("x", c_void_p), ("x_c", c_int), ("x_ld", c_int),
         ("dy", c_void_p), ("dy_c", c_int), ("dy_ld", c_int),
         ("dw", c_void_p), ("cin_total", c_int), ("ci_off", c_int), ("cout_total", c_int), ("c_valid", c_int),
+        ("dw_layout", c_int),
     ]
 
 
@@ -54,6 +55,11 @@ class PackEntry(C.Structure):
         ("cout", c_int), ("cin", c_int), ("kh", c_int), ("kw", c_int),
         ("transposed", c_int), ("cout_pad", c_int), ("cin_pad", c_int),
     ]
+
+
+class UnpackEntry(C.Structure):
+    _fields_ = [("scratch", c_void_p), ("grad", c_void_p), ("rows", c_int), ("cols", c_int), ("taps", c_int),
+                ("pad", c_int)]
 
 
 P = c_void_p
@@ -113,6 +119,7 @@ _PROTOS = {
     "smsut_ema_update": [P, P, c_int64, P, P],
     "smsut_poly_lr_tick": [P, P, c_float, c_float, c_float, P],
     "smsut_pack_weights": [P, c_int, P],
+    "smsut_unpack_wgrads": [P, c_int, P],
 }
 
 

@@ -52,6 +52,8 @@ struct BandParams {
   int act; float slope;
   int accumulate, out_f32;
   float* stats;            // fused InstanceNorm statistics [n][2][ncols_pad] (optional)
+  int fast;                // epilogue fast path (see band_epilogue_fast)
+  long long* trace;        // development: per-row clock64 stamps of CTA 0 (SMSUT_BAND_TRACE=1)
 };
 
 __device__ __forceinline__ void band_store16(void* base, size_t off, const float* v, int nvalid, bool f32,
@@ -83,10 +85,95 @@ __device__ __forceinline__ void band_store16(void* base, size_t off, const float
   }
 }
 
+
+// reduce-scatter over the 32 lanes of a warp: on return vals[0] of lane l holds the warp total of element l
+__device__ __forceinline__ float warp_reduce_scatter32(float (&vals)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int k = 0; k < step; ++k) {
+      const float send = upper ? vals[k] : vals[k + step];
+      const float keep = upper ? vals[k + step] : vals[k];
+      vals[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return vals[0];
+}
+
+// Epilogue of the common case (bf16 output, one destination, no bias / activation / accumulate, every column valid):
+// per row and 16-column chunk one tcgen05.ld, 8 packs and two 128-bit stores per thread.  The InstanceNorm
+// statistics (of the values as stored) are carried in registers down the strip -- one FADD + one FFMA per value --
+// and leave the CTA through ONE shuffle reduce-scatter + atomics at the end (the per-row shuffle network of the
+// generic path made the epilogue warps the SM-level issue bottleneck: ~330 instructions per row and warp).
+template <int NCH, bool STATS>
+__device__ __forceinline__ void band_epilogue_fast(const BandParams& p, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                                   uint32_t tmem_base, int q, int lane, int n, int h_begin, int w,
+                                                   int nrows_out) {
+  float s1[STATS ? NCH : 1][16], s2[STATS ? NCH : 1][16];
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s1[j][k] = s2[j][k] = 0.f;
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0;
+  const int ld = p.ld0;
+  const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+  size_t pix = ((size_t)n * p.h + h_begin) * p.w + w;
+  for (int i = 0; i < nrows_out; ++i, pix += p.w) {
+    const int buf = i & 1;
+    mbar_wait(&tmem_full[buf], ((uint32_t)i >> 1) & 1u);
+    tc_fence_after();
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * (size_t)ld);
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      uint32_t raw[16];
+      tmem_ld16(lane_addr + (uint32_t)buf * p.acc_cols + (uint32_t)(j * 16), raw);
+      tmem_ld_wait();
+      if (j == NCH - 1) {
+        // the accumulator buffer is free as soon as its values sit in registers
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      }
+      uint32_t w32[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(__uint_as_float(raw[2 * k]), __uint_as_float(raw[2 * k + 1]));
+      dst[2 * j] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+      dst[2 * j + 1] = make_uint4(w32[4], w32[5], w32[6], w32[7]);
+      if (STATS) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float lo = __uint_as_float(w32[k] << 16), hi = __uint_as_float(w32[k] & 0xffff0000u);
+          s1[j][2 * k] += lo;
+          s1[j][2 * k + 1] += hi;
+          s2[j][2 * k] = fmaf(lo, lo, s2[j][2 * k]);
+          s2[j][2 * k + 1] = fmaf(hi, hi, s2[j][2 * k + 1]);
+        }
+      }
+    }
+  }
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float vals[32];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        vals[k] = s1[j][k];
+        vals[16 + k] = s2[j][k];
+      }
+      const float tot = warp_reduce_scatter32(vals, lane);
+      atomicAdd(p.stats + ((size_t)n * 2 + (lane >> 4)) * p.ncols_pad + j * 16 + (lane & 15), tot);
+    }
+  }
+}
+
 // KS = kernel size, NSRC = sources, KK = channels per source / 16: compile-time so that the single MMA-issuing
 // thread runs a fully unrolled stream of descriptor adds + tcgen05.mma (ncu: with runtime loops, modulo slot
 // arithmetic and descriptor rebuilds that one thread took ~2.7 us per output row and every other warp waited on it)
-template <int KS, int NSRC, int KK>
+// NCH = ncols_pad / 16 for the fast epilogue (1, 2 or 4), 0 = generic epilogue
+template <int KS, int NSRC, int KK, int NCH>
 __global__ void __launch_bounds__(kBandThreads, 1)
 conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ BandParams p) {
@@ -118,6 +205,14 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   const int nrows_in = nrows_out + 2 * p.r;
   const int ntaps = p.ks * p.ks;
 
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    p.trace[512 + blockIdx.x * 4 + 0] = (long long)t;
+    p.trace[512 + blockIdx.x * 4 + 2] = (long long)smid;
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_w);
@@ -142,29 +237,33 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-wide loop, elected issue) =====================
+    {
+      const uint32_t el = elect_one_u32();
       // resident weights: one tile per (tap, source), K coordinate = tap * ctot + source * cc
-      mbar_arrive_expect_tx(&w_full, p.w_bytes);
+      mbar_arrive_expect_tx_e(&w_full, p.w_bytes, el);
       for (int t = 0; t < ntaps; ++t)
         for (int s = 0; s < p.nsrc; ++s)
-          tma_load_2d(smem_al + (size_t)(t * p.nsrc + s) * p.wtile_bytes, &map_w, &w_full, t * p.ctot + s * p.cc, 0);
+          tma_load_2d_e(smem_al + (size_t)(t * p.nsrc + s) * p.wtile_bytes, &map_w, &w_full, t * p.ctot + s * p.cc, 0, el);
       // input rows h_begin - r .. h_end - 1 + r, each fetched once (out-of-image rows / halo pixels: TMA zero fill)
       int slot = 0;
       uint32_t phase = 0;
-      for (int j = 0; j < nrows_in; ++j, slot = (slot + 1 == p.nslots ? 0 : slot + 1), phase ^= (slot == 0 ? 1u : 0u)) {
+      const uint32_t row_bytes = (uint32_t)p.nsrc * (uint32_t)(128 + 2 * p.r) * p.pitch;
+      for (int j = 0; j < nrows_in; ++j) {
         mbar_wait(&slot_empty[slot], phase ^ 1u);
-        mbar_arrive_expect_tx(&slot_full[slot], (uint32_t)p.nsrc * (uint32_t)(128 + 2 * p.r) * p.pitch);
+        mbar_arrive_expect_tx_e(&slot_full[slot], row_bytes, el);
         uint8_t* dst = ring_ptr + (size_t)slot * p.slot_bytes;
         const int hin = h_begin - p.r + j;
-        tma_load_4d(dst, &map_a0, &slot_full[slot], 0, w0 - p.r, hin, n);
-        if (p.nsrc == 2) tma_load_4d(dst + p.src_bytes, &map_a1, &slot_full[slot], 0, w0 - p.r, hin, n);
+        tma_load_4d_e(dst, &map_a0, &slot_full[slot], 0, w0 - p.r, hin, n, el);
+        if (NSRC == 2) tma_load_4d_e(dst + p.src_bytes, &map_a1, &slot_full[slot], 0, w0 - p.r, hin, n, el);
+        if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc =
         (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.ncols_pad >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t el = elect_one_u32();
     mbar_wait(&w_full, 0);
     // descriptors: hi word constant; lo word = (start >> 4) | (LBO = 1) << 16, advanced by plain adds (16-byte units)
     const uint64_t desc_hi = make_smem_desc(0, 16, p.sbo, p.layout_type) & 0xFFFFFFFF00000000ull;
@@ -179,15 +278,19 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     int base_slot = 0;        // i % nslots
     for (int i = 0; i < nrows_out; ++i) {
       const int buf = i & 1;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && i < 64;
+      if (tr) p.trace[i * 8 + 0] = clock64();
       mbar_wait(&tmem_empty[buf], (((uint32_t)i >> 1) & 1u) ^ 1u);
+      if (tr) p.trace[i * 8 + 1] = clock64();
       // output row i needs input rows i .. i + 2r (indices relative to the strip's first input row)
       while (rows_ready <= i + KS - 1) {
         mbar_wait(&slot_full[ready_slot], ready_phase);
         ++rows_ready;
         if (++ready_slot == nslots) { ready_slot = 0; ready_phase ^= 1u; }
       }
+      if (tr) p.trace[i * 8 + 2] = clock64();
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t d_tmem = tmem_base + (uint32_t)buf * p.acc_cols;
 #pragma unroll
         for (int ty = 0; ty < KS; ++ty) {
@@ -202,15 +305,16 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
               const uint32_t b_lo = w_lo + (uint32_t)((ty * KS + tx) * NSRC + s) * wtile_u;
 #pragma unroll
               for (int k = 0; k < KK; ++k) {
-                umma_bf16(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
-                          (ty | tx | s | k) != 0 ? 1u : 0u);
+                umma_bf16_e(d_tmem, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
+                            (ty | tx | s | k) != 0 ? 1u : 0u, el);
               }
             }
           }
         }
-        umma_commit(&tmem_full[buf]);
-        umma_commit(&slot_empty[base_slot]);   // the oldest input row of this window is no longer needed
+        umma_commit_e(&tmem_full[buf], el);
+        umma_commit_e(&slot_empty[base_slot], el);   // the oldest input row of this window is no longer needed
       }
+      if (tr) p.trace[i * 8 + 3] = clock64();
       __syncwarp();
       if (++base_slot == nslots) base_slot = 0;
     }
@@ -222,10 +326,21 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     const int nchunks = p.ncols_pad >> 4;
     float st_acc[4] = {0.f, 0.f, 0.f, 0.f};   // lane l: l < 16 -> sum of channel l, else sum of squares of l - 16
     const bool do_stats = p.stats != nullptr;
+    constexpr int kNchStats = (NCH == 1 || NCH == 2) ? NCH : 1;
+    constexpr int kNchPlain = (NCH >= 1) ? NCH : 1;
+    if (NCH > 0) {
+      if (NCH <= 2 && do_stats)
+        band_epilogue_fast<kNchStats, true>(p, tmem_full, tmem_empty, tmem_base, q, lane, n, h_begin, w, nrows_out);
+      else
+        band_epilogue_fast<kNchPlain, false>(p, tmem_full, tmem_empty, tmem_base, q, lane, n, h_begin, w, nrows_out);
+    } else
     for (int i = 0; i < nrows_out; ++i) {
       const int buf = i & 1;
       const uint32_t use = (uint32_t)(i >> 1);
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64 && i < 64;
+      if (tr) p.trace[i * 8 + 4] = clock64();
       mbar_wait(&tmem_full[buf], use & 1u);
+      if (tr) p.trace[i * 8 + 5] = clock64();
       tc_fence_after();
       const int h = h_begin + i;
       const size_t pix = ((size_t)n * p.h + h) * p.w + w;
@@ -286,6 +401,7 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (tr) p.trace[i * 8 + 6] = clock64();
     }
     if (do_stats) {
       for (int j = 0; j < nchunks && j < 4; ++j) {
@@ -301,6 +417,11 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[512 + blockIdx.x * 4 + 1] = (long long)t;
   }
 }
 
@@ -355,10 +476,17 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   while (tc < 2u * p.acc_cols) tc <<= 1;
   p.tmem_cols = tc;
 
-  // strip decomposition: ~3 CTAs per SM, at least 4 output rows per strip
+  // strip decomposition: ONE balanced wave of co-resident CTAs (as many per SM as registers / shared memory allow,
+  // at most 3), at least 4 output rows per strip.  (148 * 3 = 444 slots: 448 CTAs meant a second wave or 4-deep SMs.)
   p.wtiles = a->w / 128;
   const int sms = device_sm_count();
-  int segs = (3 * sms + a->n * p.wtiles - 1) / (a->n * p.wtiles);
+  const size_t smem_need = ((p.w_bytes + 1023u) & ~1023u) + (size_t)p.nslots * p.slot_bytes + 2048;
+  int per_sm = (int)((227u * 1024u) / smem_need);
+  const int reg_cap = (a->ncols_pad >> 4) == 2 ? 2 : 3;
+  if (per_sm > reg_cap) per_sm = reg_cap;
+  if (per_sm < 1) per_sm = 1;
+  const int strips = a->n * p.wtiles;
+  int segs = (per_sm * sms) / strips;
   if (segs < 1) segs = 1;
   int rows = (a->h + segs - 1) / segs;
   if (rows < 4) rows = a->h < 4 ? a->h : 4;
@@ -382,6 +510,15 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   }
   SMSUT_CHECK(a->out0 != nullptr, -1, "null output");
   if (p.split > 0) SMSUT_CHECK(p.split % 16 == 0, -1, "split must be a multiple of 16");
+  {
+    const int nch = a->ncols_pad >> 4;
+    p.fast = (!a->out_f32 && !a->accumulate && a->bias == nullptr && a->act == SMSUT_ACT_NONE && p.split == 0 &&
+              a->ncols == a->ncols_pad && a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 &&
+              (nch == 1 || nch == 2 || (nch == 4 && p.stats == nullptr)))
+                 ? 1 : 0;
+    const char* e = getenv("SMSUT_BAND_NOFAST");
+    if (e && e[0] == '1') p.fast = 0;
+  }
 
   CUtensorMap maps[2], map_w;
   memset(maps, 0, sizeof(maps));
@@ -396,24 +533,67 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
 
   const size_t smem = ((p.w_bytes + 1023u) & ~1023u) + (size_t)p.nslots * p.slot_bytes + 1024;
   const unsigned grid = (unsigned)(a->n * p.wtiles * p.segs);
+  static long long* trace_dev = nullptr;
+  const bool tracing = getenv("SMSUT_BAND_TRACE") != nullptr;
+  if (tracing) {
+    if (!trace_dev) cudaMalloc(&trace_dev, (512 + 4096) * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, (512 + 4096) * sizeof(long long), stream);
+    p.trace = trace_dev;
+  }
   bool launched = false;
-#define BAND_CASE(KS_, NS_, KK_)                                                                                  \
-  if (!launched && p.ks == KS_ && a->nsrc == NS_ && (cc >> 4) == KK_) {                                            \
+  const int nch = p.fast ? (a->ncols_pad >> 4) : 0;
+#define BAND_CASE1(KS_, NS_, KK_, NCH_)                                                                           \
+  if (!launched && p.ks == KS_ && a->nsrc == NS_ && (cc >> 4) == KK_ && nch == NCH_) {                             \
     static bool attr_set = false;                                                                                  \
     if (!attr_set) {                                                                                               \
-      SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_band_kernel<KS_, NS_, KK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         220 * 1024));                                                             \
+      SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_band_kernel<KS_, NS_, KK_, NCH_>,                                    \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    conv_band_kernel<KS_, NS_, KK_><<<grid, kBandThreads, smem, stream>>>(maps[0], maps[1], map_w, p);             \
+    conv_band_kernel<KS_, NS_, KK_, NCH_><<<grid, kBandThreads, smem, stream>>>(maps[0], maps[1], map_w, p);       \
     launched = true;                                                                                               \
   }
+#define BAND_CASE(KS_, NS_, KK_) \
+  BAND_CASE1(KS_, NS_, KK_, 0) BAND_CASE1(KS_, NS_, KK_, 1) BAND_CASE1(KS_, NS_, KK_, 2) BAND_CASE1(KS_, NS_, KK_, 4)
   BAND_CASE(1, 1, 1) BAND_CASE(1, 1, 2) BAND_CASE(1, 1, 4) BAND_CASE(1, 2, 1) BAND_CASE(1, 2, 2) BAND_CASE(1, 2, 4)
   BAND_CASE(3, 1, 1) BAND_CASE(3, 1, 2) BAND_CASE(3, 1, 4) BAND_CASE(3, 2, 1) BAND_CASE(3, 2, 2) BAND_CASE(3, 2, 4)
   BAND_CASE(5, 1, 1) BAND_CASE(5, 1, 2) BAND_CASE(5, 1, 4)
+#undef BAND_CASE1
 #undef BAND_CASE
   if (!launched) return 0;
   count_launch();
+  if (tracing) {
+    static long long host[512 + 4096];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    const long long t0 = host[0];
+    fprintf(stderr, "band trace ks=%d nsrc=%d cc=%d ncols=%d w=%d rows=%d slots=%d grid=%u smem=%zu\n", p.ks, p.nsrc, cc,
+            p.ncols_pad, p.w, p.rows_per_seg, p.nslots, grid, smem);
+    fprintf(stderr, " row | mma: top  acc_free  rows_in  issued | epi: top  acc_full  done\n");
+    for (int i = 0; i < 64 && i < p.rows_per_seg; ++i)
+      fprintf(stderr, " %3d | %8lld %8lld %8lld %8lld | %8lld %8lld %8lld\n", i, host[i * 8] - t0, host[i * 8 + 1] - t0,
+              host[i * 8 + 2] - t0, host[i * 8 + 3] - t0, host[i * 8 + 4] - t0, host[i * 8 + 5] - t0, host[i * 8 + 6] - t0);
+    // per-CTA wall clock (globaltimer, ns): start / end relative to the earliest start, and the SM it ran on
+    long long g0 = host[512];
+    const unsigned nc = grid < 1024 ? grid : 1024;
+    for (unsigned c = 0; c < nc; ++c) if (host[512 + c * 4] < g0) g0 = host[512 + c * 4];
+    long long smax = 0, emax = 0, dsum = 0, dmax = 0;
+    int per_sm[256] = {0};
+    for (unsigned c = 0; c < nc; ++c) {
+      const long long st = host[512 + c * 4] - g0, en = host[512 + c * 4 + 1] - g0;
+      if (st > smax) smax = st;
+      if (en > emax) emax = en;
+      dsum += en - st;
+      if (en - st > dmax) dmax = en - st;
+      per_sm[host[512 + c * 4 + 2] & 255]++;
+    }
+    int hist[8] = {0};
+    for (int i = 0; i < 256; ++i) hist[per_sm[i] < 7 ? per_sm[i] : 7]++;
+    fprintf(stderr, "CTAs %u: last start %lld ns, last end %lld ns, mean duration %lld ns, max %lld ns; SMs with k CTAs:", nc,
+            smax, emax, dsum / nc, dmax);
+    for (int k = 1; k < 8; ++k) fprintf(stderr, " %d:%d", k, hist[k]);
+    fprintf(stderr, "\n");
+  }
   int st = launch_status("conv_band_kernel");
   return st ? st : 1;
 }

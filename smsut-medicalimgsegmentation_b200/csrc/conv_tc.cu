@@ -156,19 +156,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-wide loop, elected issue) =====================
+    {
+      const uint32_t el = elect_one_u32();
       int stage = 0;
       uint32_t phase = 0;
+      uint8_t* ring = smem_raw + (smem_base - smem_u32(smem_raw));
       for (int i = 0; i < p.nsteps; ++i) {
         const KStep st = p.steps[i];
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
-        void* a_dst = smem_raw + (smem_base - smem_u32(smem_raw)) + (size_t)stage * p.stage_bytes;
+        mbar_arrive_expect_tx_e(&full_bar[stage], p.a_bytes + p.b_bytes, el);
+        void* a_dst = ring + (size_t)stage * p.stage_bytes;
         void* b_dst = (uint8_t*)a_dst + p.a_bytes;
         const CUtensorMap* m = st.map == 0 ? &map_a0 : (st.map == 1 ? &map_a1 : (st.map == 2 ? &map_a2 : &map_a3));
-        tma_load_4d(a_dst, m, &full_bar[stage], st.c0, w0 + st.dx - (p.dbg_rowshift ? 1 : 0), h0 + st.dy, n0);
-        tma_load_2d(b_dst, &map_w, &full_bar[stage], st.k, col0);
+        tma_load_4d_e(a_dst, m, &full_bar[stage], st.c0, w0 + st.dx - (p.dbg_rowshift ? 1 : 0), h0 + st.dy, n0, el);
+        tma_load_2d_e(b_dst, &map_w, &full_bar[stage], st.k, col0, el);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -182,25 +184,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const uint32_t base_lo = (smem_base >> 4) | (1u << 16);
     const uint32_t stage_u = p.stage_bytes >> 4, a_u = p.a_bytes >> 4;
     const int kk = p.cc >> 4;
+    const uint32_t el = elect_one_u32();
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < p.nsteps; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
-        uint32_t a_lo = base_lo + (uint32_t)stage * stage_u;
-        if (p.dbg_rowshift) a_lo += (uint32_t)(p.cc * 2) >> 4;   // experiment: start one row later
-        const uint32_t b_lo = base_lo + (uint32_t)stage * stage_u + a_u;
+      uint32_t a_lo = base_lo + (uint32_t)stage * stage_u;
+      if (p.dbg_rowshift) a_lo += (uint32_t)(p.cc * 2) >> 4;   // experiment: start one row later
+      const uint32_t b_lo = base_lo + (uint32_t)stage * stage_u + a_u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k < kk)
-            umma_bf16(tmem_base, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
-                      (i | k) != 0 ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[stage]);
-        if (i == p.nsteps - 1) umma_commit(&tmem_full_bar);
+      for (int k = 0; k < 4; ++k) {
+        if (k < kk)
+          umma_bf16_e(tmem_base, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
+                      (i | k) != 0 ? 1u : 0u, el);
       }
-      __syncwarp();
+      umma_commit_e(&empty_bar[stage], el);
+      if (i == p.nsteps - 1) umma_commit_e(&tmem_full_bar, el);
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
   } else {

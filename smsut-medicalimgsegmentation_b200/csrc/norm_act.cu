@@ -7,6 +7,8 @@
 // no running stats), nn.LeakyReLU(0.01) (network/blocks.py:28-34), `x += identity` (network/blocks.py:78,115)
 // and, for the double backward, torch.autograd.grad(create_graph=True) through them
 // (trainer/uganShp0Trainer.py:127-134).
+#include <stdlib.h>
+
 #include "../../include/smsut_b200.h"
 #include "common.cuh"
 
@@ -540,7 +542,12 @@ static int pick_splits(int n, int hw, int c) {
   // ~8 blocks per SM overall (two waves at 4 resident blocks), each block streaming >= 16 KB
   const long long bytes = (long long)hw * c * 2;
   long long s = bytes / (16 * 1024);
-  const long long want = (8LL * device_sm_count() + n - 1) / n;
+  static int bps = 0;
+  if (bps == 0) {
+    const char* e = getenv("SMSUT_IN_BPS");      // development knob: blocks per SM over the whole grid
+    bps = e && atoi(e) > 0 ? atoi(e) : 8;
+  }
+  const long long want = ((long long)bps * device_sm_count() + n - 1) / n;
   if (s > want) s = want;
   if (s < 1) s = 1;
   if (s > hw) s = hw;

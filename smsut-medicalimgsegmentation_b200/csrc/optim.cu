@@ -181,6 +181,26 @@ extern "C" int smsut_poly_lr_tick(float* iter_state, float* lr_out, float base_l
   count_launch();
   return launch_status("poly_lr_kernel");
 }
+// one entry per blockIdx.x; see smsut_unpack_entry in the header.  Reads are coalesced over (m, c) for a fixed tap,
+// the taps-strided writes of a warp cover taps * 128 contiguous bytes (both sides stay in L2: <= 2.4 MB per weight).
+__global__ void unpack_wgrads_kernel(const smsut_unpack_entry* __restrict__ table) {
+  const smsut_unpack_entry e = table[blockIdx.x];
+  const long long mc = (long long)e.rows * e.cols;
+  const long long tid = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.y * blockDim.x;
+  for (long long i = tid; i < mc; i += nth) {
+    float* dst = e.grad + i * e.taps;
+    for (int t = 0; t < e.taps; ++t) dst[t] += e.scratch[(size_t)t * mc + i];
+  }
+}
+
+extern "C" int smsut_unpack_wgrads(const smsut_unpack_entry* table, int32_t n, smsut_stream_t st) {
+  SMSUT_CHECK(table && n > 0, -1, "bad unpack args");
+  unpack_wgrads_kernel<<<dim3(n, 48), 256, 0, (cudaStream_t)st>>>(table);
+  count_launch();
+  return launch_status("unpack_wgrads_kernel");
+}
+
 extern "C" int smsut_pack_weights(const smsut_pack_entry* table, int32_t n, smsut_stream_t st) {
   SMSUT_CHECK(table && n > 0, -1, "bad pack args");
   pack_weights_kernel<<<dim3(n, 96), 256, 0, (cudaStream_t)st>>>(table);

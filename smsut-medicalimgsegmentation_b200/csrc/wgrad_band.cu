@@ -36,6 +36,9 @@ struct WgradBandParams {
   uint32_t x_slot_bytes, d_slot_bytes, d_base_off;
   uint32_t x_pitch, d_pitch, x_layout, d_layout;
   uint32_t tmem_cols;
+  int dbg_noepi;   // development: skip the atomics (SMSUT_WGRAD_NOEPI=1)
+  int tap_major;   // dw is the tap-major scratch [tap][cout_total][cin_total]: lanes = contiguous channels
+  int cout_total;
   float* dw;
   int cout, cin_total, ci_off, c_valid, taps;
 };
@@ -93,20 +96,21 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer: x rows (with halo) and dy rows, each exactly once =====================
-    if (lane == 0) {
+    {
+      const uint32_t el = elect_one_u32();   // warp-wide loop, elected issue (see common.cuh)
       int xs = 0, ds = 0;
       uint32_t xph = 0, dph = 0;
       for (int j = 0; j < nrows_in; ++j) {
         mbar_wait(&x_empty[xs], xph ^ 1u);
-        mbar_arrive_expect_tx(&x_full[xs], (uint32_t)(p.tw + 2 * p.r) * p.x_pitch);
-        tma_load_4d(smem_al + (size_t)xs * p.x_slot_bytes, &map_x, &x_full[xs], xch * p.xcc, w0 - p.r, h_begin - p.r + j,
-                    n);
+        mbar_arrive_expect_tx_e(&x_full[xs], (uint32_t)(p.tw + 2 * p.r) * p.x_pitch, el);
+        tma_load_4d_e(smem_al + (size_t)xs * p.x_slot_bytes, &map_x, &x_full[xs], xch * p.xcc, w0 - p.r, h_begin - p.r + j,
+                      n, el);
         if (++xs == nslots) { xs = 0; xph ^= 1u; }
         if (j < nrows) {
           mbar_wait(&d_empty[ds], dph ^ 1u);
-          mbar_arrive_expect_tx(&d_full[ds], (uint32_t)p.tw * p.d_pitch);
-          tma_load_4d(smem_al + p.d_base_off + (size_t)ds * p.d_slot_bytes, &map_dy, &d_full[ds], dch * p.dcc, w0,
-                      h_begin + j, n);
+          mbar_arrive_expect_tx_e(&d_full[ds], (uint32_t)p.tw * p.d_pitch, el);
+          tma_load_4d_e(smem_al + p.d_base_off + (size_t)ds * p.d_slot_bytes, &map_dy, &d_full[ds], dch * p.dcc, w0,
+                        h_begin + j, n, el);
           if (++ds == nslots) { ds = 0; dph ^= 1u; }
         }
       }
@@ -124,6 +128,7 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t xk_u = (16u * p.x_pitch) >> 4, dk_u = (16u * p.d_pitch) >> 4;
     const uint32_t grp_u = ((uint32_t)p.tx_per_group * p.x_pitch) >> 4;   // next group of horizontal taps
     const int kchunks = p.kchunks, groups = p.groups;
+    const uint32_t el = elect_one_u32();
     int rows_ready = 0, ready_slot = 0, base_slot = 0, dslot = 0;
     uint32_t ready_phase = 0, dphase = 0;
     for (int i = 0; i < nrows; ++i) {
@@ -134,7 +139,7 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
       mbar_wait(&d_full[dslot], dphase);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t b0 = d_base + (uint32_t)dslot * dslot_u;
 #pragma unroll
         for (int ty = 0; ty < KS; ++ty) {
@@ -145,15 +150,14 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const uint32_t d_tmem = tmem_base + (uint32_t)((ty * groups + g) * p.dcc);
             const uint32_t ag = a0 + (uint32_t)g * grp_u;
             for (int k = 0; k < kchunks; ++k)
-              umma_bf16(d_tmem, a_hi | (uint64_t)((ag + k * xk_u) & 0x3FFFu), b_hi | (uint64_t)((b0 + k * dk_u) & 0x3FFFu),
-                        idesc, (i | k) != 0 ? 1u : 0u);
+              umma_bf16_e(d_tmem, a_hi | (uint64_t)((ag + k * xk_u) & 0x3FFFu),
+                          b_hi | (uint64_t)((b0 + k * dk_u) & 0x3FFFu), idesc, (i | k) != 0 ? 1u : 0u, el);
           }
         }
-        umma_commit(&x_empty[base_slot]);   // oldest x row of the window
-        umma_commit(&d_empty[dslot]);
-        if (i == nrows - 1) umma_commit(&acc_full);
+        umma_commit_e(&x_empty[base_slot], el);   // oldest x row of the window
+        umma_commit_e(&d_empty[dslot], el);
+        if (i == nrows - 1) umma_commit_e(&acc_full, el);
       }
-      __syncwarp();
       if (++base_slot == nslots) base_slot = 0;
       if (++dslot == nslots) { dslot = 0; dphase ^= 1u; }
     }
@@ -179,8 +183,11 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
       for (int k = 0; k < 16; ++k) {
         const int co = co0 + k;
-        if (co < p.cout)
-          atomicAdd(p.dw + ((size_t)co * p.cin_total + p.ci_off + ci) * p.taps + tap, __uint_as_float(raw[k]));
+        if (co < p.cout && !p.dbg_noepi) {
+          float* dst = p.tap_major ? p.dw + ((size_t)tap * p.cout_total + co) * p.cin_total + p.ci_off + ci
+                                   : p.dw + ((size_t)co * p.cin_total + p.ci_off + ci) * p.taps + tap;
+          atomicAdd(dst, __uint_as_float(raw[k]));
+        }
       }
     }
   }
@@ -204,9 +211,20 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   {
     const char* e = getenv("SMSUT_NO_BAND");
     if (e && e[0] == '1') return 0;
+    // The kernel handles every W % 16 == 0 layer, but measured on B200 it only beats wgrad_tc_kernel on the wide,
+    // narrow-channel layers (launch list r1e: 110 us vs 42-64 us on the 32x32 / 64x64 levels): keep it to those
+    // unless SMSUT_WGRAD_BAND_ALL=1 (development).
+    e = getenv("SMSUT_WGRAD_BAND_ALL");
+    if (!(e && e[0] == '1')) {
+      if (a->w % 128 != 0) return 0;
+      if (!(a->x_c == 16 || a->x_c == 32)) return 0;
+      if (!(a->dy_c == 16 || a->dy_c == 32 || a->dy_c == 64)) return 0;
+      if (a->ksize * a->x_c > 128) return 0;
+    }
   }
   WgradBandParams p;
   memset(&p, 0, sizeof(p));
+  { const char* e = getenv("SMSUT_WGRAD_NOEPI"); p.dbg_noepi = (e && e[0] == '1') ? 1 : 0; }
   p.n = a->n; p.h = a->h; p.w = a->w; p.ks = a->ksize; p.r = a->ksize / 2;
   // column tile: the largest multiple of 16 (<= 128) dividing W
   int tw = 128;
@@ -232,19 +250,25 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   while ((int)tc < cols) tc <<= 1;
   p.tmem_cols = tc;
   p.dw = a->dw;
+  p.tap_major = a->dw_layout == 1 ? 1 : 0;
+  p.cout_total = a->cout_total;
   p.cout = a->dy_c < a->cout_total ? a->dy_c : a->cout_total;
   p.cin_total = a->cin_total; p.ci_off = a->ci_off;
   p.c_valid = a->c_valid > 0 ? a->c_valid : a->x_c;
   p.taps = a->ksize * a->ksize;
   SMSUT_CHECK(a->dw != nullptr, -1, "null dw");
 
-  // row segments: ~2 CTAs per SM overall, at least 2 rows each (every segment re-reads 2r halo rows)
+  // row segments: ONE balanced wave of co-resident CTAs (up to 3 per SM), at least 8 rows each (every segment
+  // re-reads 2r halo rows and pays a full-accumulator atomic epilogue)
   const int sms = device_sm_count();
   const int base = a->n * p.wtiles * p.xchunks * p.dchunks;
-  int segs = (2 * sms + base - 1) / base;
+  int per_sm = (int)((227u * 1024u) / (smem + 1024));
+  if (per_sm > 3) per_sm = 3;
+  if (per_sm < 1) per_sm = 1;
+  int segs = (per_sm * sms) / base;
   if (segs < 1) segs = 1;
   int rows = (a->h + segs - 1) / segs;
-  const int min_rows = a->ksize > 1 ? 4 : 2;
+  const int min_rows = a->ksize > 1 ? 8 : 4;
   if (rows < min_rows) rows = a->h < min_rows ? a->h : min_rows;
   {
     const char* e = getenv("SMSUT_BAND_ROWS");

@@ -47,6 +47,9 @@ struct WgradParams {
   int stages;
   uint32_t stage_bytes, tmem_cols;
   // output mapping: dw[((m_off + m) * nc + c_off + c) * taps + tap]
+  int dbg_noepi;   // development: skip the atomics (SMSUT_WGRAD_NOEPI=1) to time the mainloop alone
+  int tap_major;   // dw is the tap-major scratch [tap][m_full][nc]
+  int m_full;      // rows of the full weight matrix (tap-major addressing)
   float* dw;
   int m_total, m_off, nc, c_off, taps, c_valid;
   BBlock blocks[kWgMaxBlocks];
@@ -99,7 +102,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   const uint32_t a_stage_bytes = (uint32_t)p.a_real_blocks * p.a_block_bytes;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t el = elect_one_u32();   // warp-wide loop, elected issue (see common.cuh)
       int stage = 0;
       uint32_t phase = 0;
       for (int t = tile_begin; t < tile_end; ++t) {
@@ -108,16 +112,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int th_i = tile % p.tiles_h; tile /= p.tiles_h;
         const int n0 = tile * p.tn, h0 = th_i * p.th, w0 = tw_i * p.tw;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[stage], a_stage_bytes + (uint32_t)nblk * p.b_block_bytes);
+        mbar_arrive_expect_tx_e(&full_bar[stage], a_stage_bytes + (uint32_t)nblk * p.b_block_bytes, el);
         uint8_t* base = smem_al + (size_t)stage * p.stage_bytes;
         for (int b = 0; b < p.a_real_blocks; ++b)
-          tma_load_4d(base + (size_t)b * p.a_block_bytes, &map_a, &full_bar[stage], m0 + b * p.a_chunk, w0, h0, n0);
+          tma_load_4d_e(base + (size_t)b * p.a_block_bytes, &map_a, &full_bar[stage], m0 + b * p.a_chunk, w0, h0, n0, el);
         uint8_t* bb = base + a_stage_bytes;
         for (int j = 0; j < nblk; ++j) {
           const BBlock blk = p.blocks[blk0 + j];
           const CUtensorMap* m =
               blk.map == 0 ? &map_b0 : (blk.map == 1 ? &map_b1 : (blk.map == 2 ? &map_b2 : &map_b3));
-          tma_load_4d(bb + (size_t)j * p.b_block_bytes, m, &full_bar[stage], blk.c0, w0 + blk.dx, h0 + blk.dy, n0);
+          tma_load_4d_e(bb + (size_t)j * p.b_block_bytes, m, &full_bar[stage], blk.c0, w0 + blk.dx, h0 + blk.dy, n0, el);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
@@ -131,23 +135,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint64_t b_hi = make_smem_desc(0, p.b_block_bytes, p.b_sbo, p.b_layout) & 0xFFFFFFFFFFFF0000ull;
     const uint32_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4, stage_u = p.stage_bytes >> 4;
     const uint32_t a_off = a_stage_bytes >> 4, base_u = smem_base >> 4;
+    const uint32_t el = elect_one_u32();
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < ntiles; ++t) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t a0 = base_u + (uint32_t)stage * stage_u;
         const uint32_t b0 = a0 + a_off;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // 128 pixels / 16 per UMMA
-          umma_bf16(tmem_base, a_hi | (uint64_t)((a0 + k * a_step) & 0x3FFFu), b_hi | (uint64_t)((b0 + k * b_step) & 0x3FFFu),
-                    idesc, (t | k) != 0 ? 1u : 0u);
+          umma_bf16_e(tmem_base, a_hi | (uint64_t)((a0 + k * a_step) & 0x3FFFu),
+                      b_hi | (uint64_t)((b0 + k * b_step) & 0x3FFFu), idesc, (t | k) != 0 ? 1u : 0u, el);
         }
-        umma_commit(&empty_bar[stage]);
-        if (t == ntiles - 1) umma_commit(&tmem_full_bar);
+        umma_commit_e(&empty_bar[stage], el);
+        if (t == ntiles - 1) umma_commit_e(&tmem_full_bar, el);
       }
-      __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
   } else {
@@ -167,6 +171,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int jb = col / p.b_chunk;
       const BBlock blk = p.blocks[blk0 + jb];
       const int c = blk.c0 + (col - jb * p.b_chunk);
+      if (p.dbg_noepi) continue;
+      if (p.tap_major) {
+        // 16 contiguous floats of row m in the tap-major scratch: four 128-bit reductions
+        float* dst = p.dw + ((size_t)blk.tap * p.m_full + (p.m_off + m)) * p.nc + p.c_off + c;
+        if (c + 16 <= p.c_valid && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(raw[i])),
+                         "f"(__uint_as_float(raw[i + 1])), "f"(__uint_as_float(raw[i + 2])),
+                         "f"(__uint_as_float(raw[i + 3]))
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c + i < p.c_valid) atomicAdd(dst + i, __uint_as_float(raw[i]));
+        }
+        continue;
+      }
       float* dst = p.dw + ((size_t)(p.m_off + m) * p.nc + p.c_off + c) * p.taps + blk.tap;
 #pragma unroll
       for (int i = 0; i < 16; ++i)
@@ -202,6 +224,7 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   }
   WgradParams p;
   memset(&p, 0, sizeof(p));
+  { const char* e = getenv("SMSUT_WGRAD_NOEPI"); p.dbg_noepi = (e && e[0] == '1') ? 1 : 0; }
   p.n = a->n; p.h = a->h; p.w = a->w;
   int rc = choose_tile(a->n, a->h, a->w, &p.tn, &p.th, &p.tw);
   if (rc) return rc;
@@ -255,6 +278,7 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
     p.taps = a->ksize * a->ksize;
     p.m_total = a->dy_c < a->cout_total ? a->dy_c : a->cout_total;  // dy may carry zero padding channels
     p.m_off = 0; p.nc = a->cin_total; p.c_off = a->ci_off;
+    p.m_full = a->cout_total;
     p.c_valid = a->c_valid > 0 ? a->c_valid : a->x_c;
   } else {
     const int64_t W2 = 2 * (int64_t)a->w, H2 = 2 * (int64_t)a->h;
@@ -272,6 +296,7 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
     }
     p.taps = 4;
     p.m_total = a->x_c; p.m_off = a->ci_off; p.nc = a->cout_total; p.c_off = 0;
+    p.m_full = a->cin_total;
     p.c_valid = a->dy_c;
   }
   p.nblk_total = nb;
@@ -302,6 +327,7 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
 
   p.dw = a->dw;
+  p.tap_major = a->dw_layout == 1 ? 1 : 0;
   SMSUT_CHECK(a->dw != nullptr, -1, "null dw");
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
   dim3 grid((unsigned)splits, (unsigned)mblocks, (unsigned)ngroups);

@@ -57,6 +57,7 @@ class accumulate_param_grads:
         _accumulate[0] = self.prev
         ops.side_streams_enable(False)
         ops.side_join()
+        ops.WgradScratch.flush_all()       # after the block every .grad is complete (tap-major scratch folded in)
 
 
 def _target(param):

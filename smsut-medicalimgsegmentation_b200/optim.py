@@ -46,6 +46,8 @@ class _FlatOptimizer:
                 p.data = self.flat[off:off + n].view(p.shape)
                 p.grad = self.grad[off:off + n].view(p.shape)
                 off += sz
+        # tap-major scratch for the tensor-core weight gradients (ops.WgradScratch); folded into `grad` by finish_grads()
+        self.wgrad_scratch = ops.WgradScratch(self.params, [p.grad for p in self.params])
         self.param_groups = [dict(params=self.params, lr=lr)]
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self._lr_host = float(lr)
@@ -58,6 +60,10 @@ class _FlatOptimizer:
                     p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
                 self._reattach()
                 break
+
+    def finish_grads(self):
+        """fold the tensor-core weight-gradient scratch into the flat gradient (no-op when nothing is pending)"""
+        self.wgrad_scratch.flush()
 
     def _reattach(self):
         off = 0
@@ -80,6 +86,7 @@ class SGD(_FlatOptimizer):
         self.mom = torch.zeros_like(self.flat)
 
     def step(self):
+        self.finish_grads()
         self._sync_lr()
         ops.sgd_step(self.flat, self.grad, self.mom, self.lr_dev, self.momentum, self.weight_decay, self.grad_scale)
 
@@ -93,6 +100,7 @@ class Adam(_FlatOptimizer):
         self.state = torch.zeros(1, dtype=torch.float32, device=self.flat.device)
 
     def step(self):
+        self.finish_grads()
         self._sync_lr()
         ops.adam_step(self.flat, self.grad, self.m, self.v, self.lr_dev, self.betas[0], self.betas[1], self.eps,
                       self.weight_decay, self.state, self.grad_scale)

@@ -43,6 +43,7 @@ class DataParallelContext:
     def all_reduce_grads(self, optimizer):
         """sum the flat gradient buffer over ranks; the fused optimizer kernel applies 1/world"""
         if self.world > 1:
+            optimizer.finish_grads()
             dist.all_reduce(optimizer.grad, op=dist.ReduceOp.SUM)
             optimizer.grad_scale = 1.0 / self.world
 

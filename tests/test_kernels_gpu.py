@@ -85,6 +85,48 @@ def test_conv_tc_fprop_dgrad_wgrad(ops, cins, cout, h, n, ks):
     assert rel(dw, dw_ref) < 1e-2
 
 
+@pytest.mark.parametrize("cins,cout,h,n,ks", [([16], 16, 256, 1, 3), ([16, 16], 16, 128, 2, 3), ([32], 64, 64, 2, 3),
+                                              ([64, 64], 64, 64, 2, 3), ([128], 256, 16, 2, 3), ([256], 256, 8, 4, 3),
+                                              ([64], 32, 64, 2, 1)])
+def test_wgrad_tap_major_scratch(ops, cins, cout, h, n, ks):
+    """The weight-gradient path of the trainers: wgrad kernels accumulate into the tap-major scratch beside the flat
+    gradient buffer (ops.WgradScratch, vector reductions) and smsut_unpack_wgrads folds it into the OIHW gradient."""
+    import types
+    torch.manual_seed(5)
+    cin = sum(cins)
+    xs = [rnd(n, c, h, h) for c in cins]
+    wt = rnd(cout, cin, ks, ks, scale=0.1)
+    pw = make_pack(ops, wt)
+    dy = rnd(n, cout, h, h)
+    dw_ref = torch.nn.grad.conv2d_weight(torch.cat(xs, 1), wt.shape, dy, padding=ks // 2)
+    grad = torch.full_like(wt, 0.5)                       # the flat-gradient view already holds something
+    sc = ops.WgradScratch([wt], [grad])
+    ops.conv_wgrad([nhwc(x) for x in xs], nhwc(dy), pw, out=grad)
+    ops.conv_wgrad([nhwc(x) for x in xs], nhwc(dy), pw, out=grad)      # two autograd nodes of one weight
+    ops.side_join()
+    assert sc.dirty and grad.eq(0.5).all()
+    sc.flush()
+    assert not sc.dirty and sc.flat.abs().max().item() == 0.0
+    assert rel(grad - 0.5, 2 * dw_ref) < 1e-2
+    sc.flush()                                            # idempotent
+    assert rel(grad - 0.5, 2 * dw_ref) < 1e-2
+
+
+def test_convt_wgrad_tap_major_scratch(ops):
+    x = rnd(2, 64, 32, 32, seed=6)
+    wt = rnd(64, 32, 2, 2, scale=0.1)
+    pw = make_pack(ops, wt, transposed=True)
+    dy = rnd(2, 32, 64, 64)
+    xr, wr = x.clone().requires_grad_(True), wt.clone().requires_grad_(True)
+    F.conv_transpose2d(xr, wr, stride=2).backward(dy)
+    grad = torch.zeros_like(wt)
+    sc = ops.WgradScratch([wt], [grad])
+    ops.convt_wgrad(nhwc(x), nhwc(dy), pw, out=grad)
+    ops.side_join()
+    sc.flush()
+    assert rel(grad, wr.grad) < 1e-2
+
+
 def test_conv_tc_padded_input_channels(ops):
     """8 live channels in a 16-channel tensor (the 5x5 stem feeds enc1.conv1 this way)."""
     n, h, cin, cout = 2, 64, 8, 16
