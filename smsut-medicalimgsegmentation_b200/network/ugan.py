@@ -121,14 +121,17 @@ class UGAN(nn.Module):
         if m is None:
             m = torch.zeros(x.size(0), self.n_modal, device=x.device)
         x = x.float()
+        # the segmentation half runs on a branch stream beside the translation half (they share only weights)
+        with ops.parallel_branch(0) as br:
+            seg_out, seg_ens = self.seg_encoder.forward_nhwc(Fn.ImageInputFn.apply(x))
+            seg_out = self.enc5.forward_nhwc([seg_out])
+            seg = self.seg_decoder(to_nchw(seg_out), seg_ens)
+
         tsl_in = _TslInputFn.apply(x, m)
         tsl_out, tsl_ens = self.tsl_encoder.forward_nhwc(tsl_in)
         tsl_out_1 = self.enc5.forward_nhwc([tsl_out])
         tsl = self.tsl_decoder(to_nchw(tsl_out_1), tsl_ens)
-
-        seg_out, seg_ens = self.seg_encoder.forward_nhwc(Fn.ImageInputFn.apply(x))
-        seg_out = self.enc5.forward_nhwc([seg_out])
-        seg = self.seg_decoder(to_nchw(seg_out), seg_ens)
+        br.join(seg)
         return seg, tsl, tsl_out_1
 
     def forward(self, x, m=None):

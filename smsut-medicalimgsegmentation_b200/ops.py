@@ -133,6 +133,52 @@ def side_run(fn, keep):
     _Side.held.append(keep)
 
 
+_branch_streams = {}
+branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]
+
+
+class parallel_branch:
+    """`with parallel_branch(k) as br:` runs the enclosed launches on branch stream k, forked from the current stream;
+    `br.join(*outputs)` (after the block) makes the current stream wait for them.  Used for data-independent chains
+    (the translation / segmentation halves of the generator, the three discriminator passes): most of their kernels
+    are far smaller than the machine, so two chains side by side cost little more than one.  Autograd replays each
+    node's backward on its forward stream, so the backward chains overlap as well.  Capturable: the branch joins the
+    capture at the fork and is joined back before the step ends."""
+
+    def __init__(self, k=0):
+        self.k = k
+        self.on = branch_parallel[0] and torch.cuda.is_available()
+
+    def __enter__(self):
+        if not self.on:
+            return self
+        self.main = torch.cuda.current_stream()
+        key = (self.main.device_index, self.k)
+        st = _branch_streams.get(key)
+        if st is None:
+            st = _branch_streams[key] = torch.cuda.Stream(device=self.main.device)
+        self.stream = st
+        st.wait_stream(self.main)
+        self.ctx = torch.cuda.stream(st)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.on:
+            self.ctx.__exit__(*a)
+
+    def join(self, *outputs):
+        """call on the forking stream after the block: orders it after the branch and tells the caching allocator
+        that `outputs` (allocated on the branch stream) are consumed here"""
+        if not self.on:
+            return
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(self.stream)
+        for t in outputs:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(cur)
+
+
 def side_join():
     """the current stream waits for every side kernel issued since the last join"""
     if _Side.used:

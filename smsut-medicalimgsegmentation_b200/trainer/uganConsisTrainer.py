@@ -70,18 +70,22 @@ class UGANConsisTrainer(UGANShp0Trainer):
         # generator forward shared by the D phase (detached) and the G phase
         y_fake, x_fake, feat_x_pool, sample_ids = self.net(x_real, vec_ot, sample_ids=sample_ids)
 
-        # ---------------- D phase (L129-146)
+        # ---------------- D phase (L129-146): the three discriminator passes are independent chains of small
+        # kernels -> real on the current stream, fake and interpolated on branch streams (ops.parallel_branch)
+        x_fake_d = x_fake.detach()
+        with ops.parallel_branch(1) as b_fake:
+            out_src_f, _ = self.D(x_fake_d)
+            d_loss_fake = Fn.MeanFn.apply(out_src_f, 1.0)
+        with ops.parallel_branch(2) as b_hat:
+            x_hat = ops.lerp_rows(alpha, x_real, x_fake_d.contiguous()).requires_grad_(True)
+            out_src_h, _ = self.D(x_hat)
+            d_loss_gp = self.gradient_penalty(out_src_h, x_hat)
+
         out_src, out_cls = self.D(x_real)
         d_loss_real = Fn.MeanFn.apply(out_src, -1.0)
         d_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_org)
-
-        x_fake_d = x_fake.detach()
-        out_src, out_cls = self.D(x_fake_d)
-        d_loss_fake = Fn.MeanFn.apply(out_src, 1.0)
-
-        x_hat = ops.lerp_rows(alpha, x_real, x_fake_d.contiguous()).requires_grad_(True)
-        out_src, _ = self.D(x_hat)
-        d_loss_gp = self.gradient_penalty(out_src, x_hat)
+        b_fake.join(d_loss_fake)
+        b_hat.join(d_loss_gp)
 
         d_loss = d_loss_real + d_loss_fake + lambda_cls * d_loss_cls + lambda_gp * d_loss_gp
         self.d_optimizer.zero_grad()
@@ -92,13 +96,14 @@ class UGANConsisTrainer(UGANShp0Trainer):
         self.d_optimizer.step()
 
         # ---------------- G phase (L151-180); D's parameters are constants here
-        for p in self.d_optimizer.params:
-            p.requires_grad_(False)
-        out_src, out_cls = self.D(x_fake)
-        for p in self.d_optimizer.params:
-            p.requires_grad_(True)
-        g_loss_fake = Fn.MeanFn.apply(out_src, -1.0)
-        g_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_trg)
+        with ops.parallel_branch(1) as b_adv:       # D(G(x)) beside the cycle forward of G
+            for p in self.d_optimizer.params:
+                p.requires_grad_(False)
+            out_src, out_cls = self.D(x_fake)
+            for p in self.d_optimizer.params:
+                p.requires_grad_(True)
+            g_loss_fake = Fn.MeanFn.apply(out_src, -1.0)
+            g_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_trg)
         g_loss_seg = self.loss(y_fake[:bs], y_real)
 
         y_rec, x_rec, feat_f_pool, _ = self.net(x_fake, vec_to, sample_ids=sample_ids)
@@ -112,6 +117,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
             lambda_semi = lambda_semi.reshape(())      # device scalar: one captured graph serves every epoch
 
         g_loss_nce = self.nce_loss(feat_x_pool, feat_f_pool)
+        b_adv.join(g_loss_fake, g_loss_cls)
 
         g_loss = g_loss_fake + lambda_rec * g_loss_rec + lambda_cls * g_loss_cls + \
             lambda_seg * g_loss_seg + \
