@@ -441,6 +441,8 @@ bool conv_band_eligible(const smsut_conv_tc_args* a) {
   return true;
 }
 
+bool conv_band_eligible_c(const smsut_conv_tc_args* a) { return conv_band_eligible(a); }
+
 // statistics are fused when the band kernel takes the launch and every column goes to one bf16 destination
 bool conv_band_fuses_stats(const smsut_conv_tc_args* a) {
   return conv_band_eligible(a) && a->ncols_pad <= 64 && a->out1 == nullptr && !a->out_f32 && !a->accumulate &&

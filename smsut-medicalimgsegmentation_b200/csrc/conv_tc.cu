@@ -59,6 +59,8 @@ struct ConvTcParams {
   int act; float slope;
   int accumulate, out_f32;
   int dbg_rowshift;        // experiment: load the A tile one pixel to the left and start the descriptor one row later
+  float* stats;            // fused InstanceNorm statistics [n][2][ncols_pad] of the stored values (optional)
+  int fast;                // plain epilogue: bf16, one destination, every column valid, no bias / act / accumulate
   KStep steps[kMaxSteps];
 };
 
@@ -217,6 +219,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tc_fence_after();
 
     const int nchunks = p.bn >> 4;
+    if (p.fast) {
+      // common case: two 128-bit stores per 16 columns; the InstanceNorm statistics of the stored values leave the
+      // warp through one shuffle reduce-scatter per chunk (a warp's 32 pixels belong to one image: host-checked)
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0 + col0;
+      const size_t pix = ((size_t)n * p.h + h) * p.w + w;
+      for (int j = 0; j < nchunks; ++j) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
+        tmem_ld_wait();
+        uint32_t w32[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(__uint_as_float(raw[2 * k]), __uint_as_float(raw[2 * k + 1]));
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(out + pix * (size_t)p.ld0 + j * 16);
+          dst[0] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+          dst[1] = make_uint4(w32[4], w32[5], w32[6], w32[7]);
+        }
+        if (p.stats != nullptr) {
+          float vals[32];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float lo = row_ok ? __uint_as_float(w32[k] << 16) : 0.f;
+            const float hi = row_ok ? __uint_as_float(w32[k] & 0xffff0000u) : 0.f;
+            vals[2 * k] = lo; vals[2 * k + 1] = hi;
+            vals[16 + 2 * k] = lo * lo; vals[16 + 2 * k + 1] = hi * hi;
+          }
+#pragma unroll
+          for (int step = 16; step >= 1; step >>= 1) {
+            const bool upper = (lane & step) != 0;
+#pragma unroll
+            for (int k = 0; k < step; ++k) {
+              const float send = upper ? vals[k] : vals[k + step];
+              const float keep = upper ? vals[k + step] : vals[k];
+              vals[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+            }
+          }
+          // lane l: l < 16 -> sum of channel l, else sum of squares of channel l - 16 (image of the warp's first row)
+          const int n_w = n0 + (q * 32) / (p.tw * p.th);
+          if (n_w < p.n)
+            atomicAdd(p.stats + ((size_t)n_w * 2 + (lane >> 4)) * p.ncols + col0 + j * 16 + (lane & 15), vals[0]);
+        }
+      }
+    } else
     for (int j = 0; j < nchunks; ++j) {
       uint32_t raw[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
@@ -357,6 +402,23 @@ int choose_tile(int n, int h, int w, int* tn, int* th, int* tw) {
 void count_launch();
 int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream);
 bool conv_band_fuses_stats(const smsut_conv_tc_args* a);
+bool conv_band_eligible_c(const smsut_conv_tc_args* a);
+
+static bool conv_tc_plain_epilogue(const smsut_conv_tc_args* a) {
+  return a->kind == SMSUT_TC_CONV && !a->out_f32 && !a->accumulate && a->bias == nullptr && a->act == SMSUT_ACT_NONE &&
+         a->out1 == nullptr && a->ncols == a->ncols_pad && a->ncols_pad % 16 == 0 && a->out0_ld % 8 == 0 &&
+         a->out0_coff % 8 == 0;
+}
+
+// conv_tc_kernel fuses the statistics when the epilogue is the plain one and the 32 pixels of an epilogue warp belong
+// to one image (tile = part of one image, or whole images of a multiple of 32 pixels)
+static bool conv_tc_fuses_stats(const smsut_conv_tc_args* a) {
+  if (!conv_tc_plain_epilogue(a)) return false;
+  int tn, th, tw;
+  if (choose_tile(a->n, a->h, a->w, &tn, &th, &tw)) return false;
+  if (a->h % th != 0 || a->w % tw != 0) return false;
+  return tn == 1 || (th * tw) % 32 == 0;
+}
 
 static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a != nullptr, -1, "null args");
@@ -369,7 +431,8 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a->ncols_pad % 16 == 0 && a->ncols <= a->ncols_pad && a->ncols > 0, -1, "bad ncols/ncols_pad");
 
   if (a->stats != nullptr)
-    SMSUT_CHECK(conv_band_fuses_stats(a), -1, "conv_tc: stats requested but smsut_conv_tc_fuses_stats() is 0 for this shape");
+    SMSUT_CHECK(conv_band_fuses_stats(a) || conv_tc_fuses_stats(a), -1,
+                "conv_tc: stats requested but smsut_conv_tc_fuses_stats() is 0 for this shape");
   // wide, narrow-channel layers: the band kernel (each input row fetched once, taps by descriptor arithmetic)
   if (a->bn == 0 && a->ncols_pad % 16 == 0 && a->src_c[0] % 16 == 0) {
     const int rb = conv_band_try(a, stream);
@@ -499,6 +562,12 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
     p.dbg_rowshift = e ? atoi(e) : 0;
   }
   SMSUT_CHECK(a->out0 != nullptr, -1, "null output");
+  p.fast = conv_tc_plain_epilogue(a) ? 1 : 0;
+  p.stats = nullptr;
+  if (a->stats != nullptr) {
+    SMSUT_CHECK(conv_tc_fuses_stats(a), -1, "stats requested for a shape conv_tc_kernel does not fuse them for");
+    p.stats = a->stats;
+  }
   if (!a->out_f32)
     SMSUT_CHECK(a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 || a->ncols < 16, -1, "bf16 output pitch/offset must be multiples of 8");
 
@@ -511,7 +580,9 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
 }  // namespace smsut
 
 extern "C" int smsut_conv_tc_fuses_stats(const smsut_conv_tc_args* a) {
-  return (a != nullptr && a->ncols_pad % 16 == 0 && a->src_c[0] % 16 == 0 && smsut::conv_band_fuses_stats(a)) ? 1 : 0;
+  if (a == nullptr || a->ncols_pad % 16 != 0 || a->src_c[0] % 16 != 0) return 0;
+  if (a->bn == 0 && smsut::conv_band_eligible_c(a)) return smsut::conv_band_fuses_stats(a) ? 1 : 0;
+  return smsut::conv_tc_fuses_stats(a) ? 1 : 0;
 }
 extern "C" int smsut_conv_tc(const smsut_conv_tc_args* a, smsut_stream_t stream) {
   return smsut::conv_tc_impl(a, reinterpret_cast<cudaStream_t>(stream));

@@ -419,21 +419,34 @@ patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float*
   float pos = 0.f;
   for (int i = 0; i < per; ++i) pos = fmaf(qv[i], k[(size_t)row * c + lane + 32 * i], pos);
   pos = warp_sum(pos) * inv_t;
-  // pass 1: online log-sum-exp over [pos, negatives]
+  // pass 1: online log-sum-exp over [pos, negatives].  kJ negatives per step: their dot products and butterfly
+  // reductions are independent instruction streams (one negative at a time is a 128-long chain of dependent
+  // shuffle reductions: 150 us for a 34 MFLOP problem)
+  constexpr int kJ = 8;
   float m = pos, s = 1.f;
-  for (int j = 0; j < np; ++j) {
-    float d;
-    if (j == self) {
-      d = -10.f * inv_t;
-    } else {
+  for (int j0 = 0; j0 < np; j0 += kJ) {
+    float d[kJ];
+#pragma unroll
+    for (int u = 0; u < kJ; ++u) {
+      const int j = j0 + u < np ? j0 + u : np - 1;
       const float* kr = k + ((size_t)grp * np + j) * c;
-      d = 0.f;
-      for (int i = 0; i < per; ++i) d = fmaf(qv[i], kr[lane + 32 * i], d);
-      d = warp_sum(d) * inv_t;
+      float a = 0.f;
+      for (int i = 0; i < per; ++i) a = fmaf(qv[i], kr[lane + 32 * i], a);
+      d[u] = a;
     }
-    const float mn = fmaxf(m, d);
-    s = s * __expf(m - mn) + __expf(d - mn);
-    m = mn;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < kJ; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+#pragma unroll
+    for (int u = 0; u < kJ; ++u) {
+      const int j = j0 + u;
+      if (j >= np) break;
+      const float dj = j == self ? -10.f * inv_t : d[u] * inv_t;
+      const float mn = fmaxf(m, dj);
+      s = s * __expf(m - mn) + __expf(dj - mn);
+      m = mn;
+    }
   }
   const float lse = m + __logf(s);
   if (!BWD) {
@@ -448,15 +461,29 @@ patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float*
   float acc[kMaxPer];
   const float ppos = __expf(pos - lse);
   for (int i = 0; i < per; ++i) acc[i] = (ppos - 1.f) * k[(size_t)row * c + lane + 32 * i];
-  for (int j = 0; j < np; ++j) {
-    if (j == self) continue;
-    const float* kr = k + ((size_t)grp * np + j) * c;
-    float kv[kMaxPer];
-    float d = 0.f;
-    for (int i = 0; i < per; ++i) { kv[i] = kr[lane + 32 * i]; d = fmaf(qv[i], kv[i], d); }
-    d = warp_sum(d) * inv_t;
-    const float pj = __expf(d - lse);
-    for (int i = 0; i < per; ++i) acc[i] = fmaf(pj, kv[i], acc[i]);
+  constexpr int kJ2 = 4;
+  for (int j0 = 0; j0 < np; j0 += kJ2) {
+    float d[kJ2];
+#pragma unroll
+    for (int u = 0; u < kJ2; ++u) {
+      const int j = j0 + u < np ? j0 + u : np - 1;
+      const float* kr = k + ((size_t)grp * np + j) * c;
+      float a = 0.f;
+      for (int i = 0; i < per; ++i) a = fmaf(qv[i], kr[lane + 32 * i], a);
+      d[u] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < kJ2; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], o);
+#pragma unroll
+    for (int u = 0; u < kJ2; ++u) {
+      const int j = j0 + u;
+      if (j >= np || j == self) continue;
+      const float pj = __expf(d[u] * inv_t - lse);
+      const float* kr = k + ((size_t)grp * np + j) * c;
+      for (int i = 0; i < per; ++i) acc[i] = fmaf(pj, kr[lane + 32 * i], acc[i]);
+    }
   }
   for (int i = 0; i < per; ++i) dq[(size_t)row * c + lane + 32 * i] = coef * acc[i];
 }

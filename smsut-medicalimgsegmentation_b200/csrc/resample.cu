@@ -207,6 +207,21 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
     y[i] = f2bf(ch < c ? x[((size_t)b * c + ch) * hw + q] : 0.f);
   }
 }
+// c_pad == 16 (the network inputs: 1 .. 16 channels): one thread assembles a pixel's 16 channels and writes them with
+// two 128-bit stores (the element-per-thread kernel above issues sixteen 2-byte stores per pixel)
+__global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c, int hw) {
+  const long long total = (long long)n * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const int q = (int)(i - (long long)b * hw);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = k < c ? x[((size_t)b * c + k) * hw + q] : 0.f;
+    uint4* dst = reinterpret_cast<uint4*>(y + (size_t)i * 16);
+    dst[0] = pack8(v);
+    dst[1] = pack8(v + 8);
+  }
+}
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int c, int hw,
                                     int x_ld) {
   const long long total = (long long)n * c * hw;
@@ -224,6 +239,15 @@ __global__ void build_tsl_input_kernel(const float* __restrict__ x, const float*
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / hw);
     __nv_bfloat16* dst = y + (size_t)i * c_pad;
+    if (c_pad == 16 && n_modal < 16) {
+      float v[16];
+      v[0] = x[i];
+#pragma unroll
+      for (int k = 1; k < 16; ++k) v[k] = (k <= n_modal && m) ? m[b * n_modal + k - 1] : 0.f;
+      reinterpret_cast<uint4*>(dst)[0] = pack8(v);
+      reinterpret_cast<uint4*>(dst)[1] = pack8(v + 8);
+      continue;
+    }
     dst[0] = f2bf(x[i]);
     for (int k = 0; k < n_modal; ++k) dst[1 + k] = f2bf(m ? m[b * n_modal + k] : 0.f);
     for (int k = 1 + n_modal; k < c_pad; ++k) dst[k] = f2bf(0.f);
@@ -292,7 +316,10 @@ extern "C" int smsut_bilinear2_bwd(const void* dy, void* dx, int32_t n, int32_t 
 extern "C" int smsut_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, int32_t c, int32_t h, int32_t w,
                                            int32_t c_pad, smsut_stream_t st) {
   SMSUT_CHECK(c_pad >= c && n > 0 && c > 0, -1, "bad shape");
-  nchw_to_nhwc_kernel<<<grid_for((long long)n * h * w * c_pad), 256, 0, (cudaStream_t)st>>>(x, (__nv_bfloat16*)y, n, c, h * w, c_pad);
+  if (c_pad == 16 && c <= 16)
+    nchw_to_nhwc16_kernel<<<grid_for((long long)n * h * w), 256, 0, (cudaStream_t)st>>>(x, (__nv_bfloat16*)y, n, c, h * w);
+  else
+    nchw_to_nhwc_kernel<<<grid_for((long long)n * h * w * c_pad), 256, 0, (cudaStream_t)st>>>(x, (__nv_bfloat16*)y, n, c, h * w, c_pad);
   count_launch();
   return launch_status("nchw_to_nhwc_kernel");
 }

@@ -507,11 +507,15 @@ def test_fused_head_backward(ops, cout, tanh):
     assert rel(nchw(dx), xr.grad) < 1e-2 and rel(dw, wr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
 
 
-@pytest.mark.parametrize("cins,cout,h", [([16], 16, 256), ([16, 16], 16, 256), ([32], 32, 128), ([16], 32, 128), ([64], 64, 64)])
-def test_conv_fused_instance_norm_statistics(ops, cins, cout, h):
-    """statistics from the conv epilogue (wide layers) or the statistics kernel == sums over the stored output"""
+@pytest.mark.parametrize("cins,cout,h,n", [([16], 16, 256, 2), ([16, 16], 16, 256, 2), ([32], 32, 128, 2),
+                                            ([16], 32, 128, 2), ([64], 64, 64, 2), ([64, 64], 64, 64, 3),
+                                            ([128], 128, 32, 2), ([128, 128], 128, 32, 2), ([256], 256, 16, 3),
+                                            ([256], 256, 8, 5), ([256], 256, 4, 16), ([64], 128, 32, 2)])
+def test_conv_fused_instance_norm_statistics(ops, cins, cout, h, n):
+    """statistics from the conv epilogue (band kernel: carried down the strip; conv_tc_kernel: per tile, also when a
+    tile holds several whole images) or the statistics kernel == sums over the stored output"""
     torch.manual_seed(16)
-    xs = [rnd(2, c, h, h) for c in cins]
+    xs = [rnd(n, c, h, h) for c in cins]
     wt = rnd(cout, sum(cins), 3, 3, scale=0.1)
     pw = make_pack(ops, wt)
     y, st = ops.conv_fprop([nhwc(x) for x in xs], pw, want_stats=True)
