@@ -117,15 +117,18 @@ __device__ __forceinline__ void band_epilogue_fast(const BandParams& p, uint64_t
 #pragma unroll
       for (int k = 0; k < 16; ++k) s1[j][k] = s2[j][k] = 0.f;
   }
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0;
-  const int ld = p.ld0;
+  // destination of chunk j: out0 below the split column, out1 above (dgrad of a concatenated input); both bf16
+  __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0;
+  __nv_bfloat16* out1 = p.split > 0 ? reinterpret_cast<__nv_bfloat16*>(p.out1) + p.coff1 - p.split : out0;
+  const int ld0 = p.ld0, ld1 = p.split > 0 ? p.ld1 : p.ld0;
+  const int split_chunk = p.split > 0 ? (p.split >> 4) : NCH;
+  const bool acc = p.accumulate != 0;
   const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
   size_t pix = ((size_t)n * p.h + h_begin) * p.w + w;
   for (int i = 0; i < nrows_out; ++i, pix += p.w) {
     const int buf = i & 1;
     mbar_wait(&tmem_full[buf], ((uint32_t)i >> 1) & 1u);
     tc_fence_after();
-    uint4* dst = reinterpret_cast<uint4*>(out + pix * (size_t)ld);
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       uint32_t raw[16];
@@ -137,11 +140,26 @@ __device__ __forceinline__ void band_epilogue_fast(const BandParams& p, uint64_t
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
+      uint4* dst = j < split_chunk ? reinterpret_cast<uint4*>(out0 + pix * (size_t)ld0 + j * 16)
+                                   : reinterpret_cast<uint4*>(out1 + pix * (size_t)ld1 + j * 16);
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
+      if (acc) {
+        float o[8];
+        const uint4 q0 = dst[0], q1 = dst[1];
+        unpack8(q0, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += o[k];
+        unpack8(q1, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[8 + k] += o[k];
+      }
       uint32_t w32[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(__uint_as_float(raw[2 * k]), __uint_as_float(raw[2 * k + 1]));
-      dst[2 * j] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
-      dst[2 * j + 1] = make_uint4(w32[4], w32[5], w32[6], w32[7]);
+      for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+      dst[0] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+      dst[1] = make_uint4(w32[4], w32[5], w32[6], w32[7]);
       if (STATS) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -514,7 +532,10 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   if (p.split > 0) SMSUT_CHECK(p.split % 16 == 0, -1, "split must be a multiple of 16");
   {
     const int nch = a->ncols_pad >> 4;
-    p.fast = (!a->out_f32 && !a->accumulate && a->bias == nullptr && a->act == SMSUT_ACT_NONE && p.split == 0 &&
+    // plain epilogue (see band_epilogue_fast): bf16, every column valid, no bias / activation; accumulate and a
+    // 16-aligned split into two destinations are handled there as well
+    const bool split_ok = p.split == 0 || (p.split % 16 == 0 && a->out1_ld % 8 == 0 && a->out1_coff % 8 == 0);
+    p.fast = (!a->out_f32 && a->bias == nullptr && a->act == SMSUT_ACT_NONE && split_ok &&
               a->ncols == a->ncols_pad && a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 &&
               (nch == 1 || nch == 2 || (nch == 4 && p.stats == nullptr)))
                  ? 1 : 0;

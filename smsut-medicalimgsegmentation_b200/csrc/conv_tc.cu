@@ -222,17 +222,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     if (p.fast) {
       // common case: two 128-bit stores per 16 columns; the InstanceNorm statistics of the stored values leave the
       // warp through one shuffle reduce-scatter per chunk (a warp's 32 pixels belong to one image: host-checked)
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0 + col0;
+      __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0;
+      __nv_bfloat16* out1 = p.split > 0 ? reinterpret_cast<__nv_bfloat16*>(p.out1) + p.coff1 - p.split : out0;
+      const int ld1 = p.split > 0 ? p.ld1 : p.ld0;
       const size_t pix = ((size_t)n * p.h + h) * p.w + w;
       for (int j = 0; j < nchunks; ++j) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
         tmem_ld_wait();
+        const int col = col0 + j * 16;
+        uint4* dst = (p.split > 0 && col >= p.split) ? reinterpret_cast<uint4*>(out1 + pix * (size_t)ld1 + col)
+                                                     : reinterpret_cast<uint4*>(out0 + pix * (size_t)p.ld0 + col);
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
+        if (p.accumulate && row_ok) {
+          float o[8];
+          const uint4 q0 = dst[0], q1 = dst[1];
+          unpack8(q0, o);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] += o[k];
+          unpack8(q1, o);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[8 + k] += o[k];
+        }
         uint32_t w32[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(__uint_as_float(raw[2 * k]), __uint_as_float(raw[2 * k + 1]));
+        for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
         if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(out + pix * (size_t)p.ld0 + j * 16);
           dst[0] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
           dst[1] = make_uint4(w32[4], w32[5], w32[6], w32[7]);
         }
@@ -404,16 +421,18 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream);
 bool conv_band_fuses_stats(const smsut_conv_tc_args* a);
 bool conv_band_eligible_c(const smsut_conv_tc_args* a);
 
+// plain epilogue: bf16 output(s), every column valid, no bias / activation (accumulate and a 16-aligned split allowed)
 static bool conv_tc_plain_epilogue(const smsut_conv_tc_args* a) {
-  return a->kind == SMSUT_TC_CONV && !a->out_f32 && !a->accumulate && a->bias == nullptr && a->act == SMSUT_ACT_NONE &&
-         a->out1 == nullptr && a->ncols == a->ncols_pad && a->ncols_pad % 16 == 0 && a->out0_ld % 8 == 0 &&
-         a->out0_coff % 8 == 0;
+  const bool split_ok = a->out1 == nullptr || (a->split % 16 == 0 && a->out1_ld % 8 == 0 && a->out1_coff % 8 == 0);
+  return (a->kind == SMSUT_TC_CONV || a->kind == SMSUT_TC_CONVT_DGRAD) && !a->out_f32 && a->bias == nullptr &&
+         a->act == SMSUT_ACT_NONE && split_ok && a->ncols == a->ncols_pad && a->ncols_pad % 16 == 0 &&
+         a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0;
 }
 
 // conv_tc_kernel fuses the statistics when the epilogue is the plain one and the 32 pixels of an epilogue warp belong
 // to one image (tile = part of one image, or whole images of a multiple of 32 pixels)
 static bool conv_tc_fuses_stats(const smsut_conv_tc_args* a) {
-  if (!conv_tc_plain_epilogue(a)) return false;
+  if (!conv_tc_plain_epilogue(a) || a->accumulate || a->out1 != nullptr || a->kind != SMSUT_TC_CONV) return false;
   int tn, th, tw;
   if (choose_tile(a->n, a->h, a->w, &tn, &th, &tw)) return false;
   if (a->h % th != 0 || a->w % tw != 0) return false;

@@ -30,6 +30,7 @@ import torch.nn as nn
 from .. import config as cfg
 from .. import functional as Fn
 from .. import ops
+from ..network.blocks import refresh_packs
 from .uganShp0Trainer import UGANShp0Trainer
 
 LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
@@ -73,6 +74,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
         # ---------------- D phase (L129-146): the three discriminator passes are independent chains of small
         # kernels -> real on the current stream, fake and interpolated on branch streams (ops.parallel_branch)
         x_fake_d = x_fake.detach()
+        refresh_packs(self.D)       # before the fork: all three passes read the bf16 weight copies this launch writes
         with ops.parallel_branch(1) as b_fake:
             out_src_f, _ = self.D(x_fake_d)
             d_loss_fake = Fn.MeanFn.apply(out_src_f, 1.0)
