@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace smsut {
 
@@ -47,6 +48,41 @@ static inline int launch_status(const char* what) {
 }
 
 int device_sm_count();
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the library is launched with the
+// programmatic-stream-serialization attribute and starts with pdl_prologue().  `launch_dependents` lets the NEXT
+// kernel of the stream be scheduled (its CTAs set up barriers, TMEM, descriptors) while this grid is still running;
+// `wait` blocks until the PREVIOUS grid has completed and its memory is visible, so no kernel touches global memory
+// early.  One training iteration is ~1300 dependent launches of 5-50 us kernels: the launch latency between them is
+// the target.  Opt-in (SMSUT_PDL=1): inside the captured step graph it measured no gain on B200 (14.9 vs 14.6 ms), so by
+// default kernels launch without the attribute and the two instructions are no-ops.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Small device helpers

@@ -195,6 +195,7 @@ template <int KS, int NSRC, int KK, int NCH>
 __global__ void __launch_bounds__(kBandThreads, 1)
 conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ BandParams p) {
+  pdl_trigger();   // the next kernel may be scheduled; this one waits for its predecessor after its own set-up
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t slot_full[kBandMaxSlots];
   __shared__ __align__(8) uint64_t slot_empty[kBandMaxSlots];
@@ -253,6 +254,7 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();      // barriers, TMEM and descriptors are ready: now the predecessor's results are needed
 
   if (warp == 0) {
     // ===================== TMA producer (warp-wide loop, elected issue) =====================
@@ -573,7 +575,7 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    conv_band_kernel<KS_, NS_, KK_, NCH_><<<grid, kBandThreads, smem, stream>>>(maps[0], maps[1], map_w, p);       \
+    launch_pdl(conv_band_kernel<KS_, NS_, KK_, NCH_>, grid, kBandThreads, smem, stream, maps[0], maps[1], map_w, p);       \
     launched = true;                                                                                               \
   }
 #define BAND_CASE(KS_, NS_, KK_) \

@@ -42,6 +42,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
 // ---------------------------------------------------------------------------------------------
 template <int CT>
 __global__ void __launch_bounds__(128) direct_fprop_kernel(const DirectParams p) {
+  pdl_prologue();
   extern __shared__ float ws[];  // [taps][cch][CT]
   const int taps = p.kh * p.kw;
   const int co0 = blockIdx.y * CT;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(128) direct_fprop_kernel(const DirectParams p)
 // fprop for very few output pixels (conv_cls: 16 outputs of K = 4096; conv_src: 256 outputs of K = 2304):
 // one warp per (output pixel, output channel), lanes split the input channels (coalesced NHWC reads).
 __global__ void __launch_bounds__(256) direct_fprop_small_kernel(const DirectParams p) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nout = (long long)p.n * p.ho * p.wo * p.cout;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(256) direct_fprop_small_kernel(const DirectPar
 // ---------------------------------------------------------------------------------------------
 template <int CT>
 __global__ void __launch_bounds__(128) direct_dgrad_kernel(const DirectParams p) {
+  pdl_prologue();
   extern __shared__ float ws[];  // [taps][cch(co)][CT(ci)]
   const int taps = p.kh * p.kw;
   const int ci0 = blockIdx.y * CT;
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(128) direct_dgrad_kernel(const DirectParams p)
 constexpr int kWgOPT = 4;
 __global__ void __launch_bounds__(256) direct_wgrad_kernel(const DirectParams p, float* dw, float* dbias,
                                                            int rows_per_block) {
+  pdl_prologue();
   const int taps = p.kh * p.kw;
   const int nout = p.cout * p.cin * taps;
   const long long total_rows = (long long)p.n * p.ho;
@@ -295,6 +299,7 @@ __global__ void __launch_bounds__(256)
 head1x1_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
                    const float* __restrict__ w, uint4* __restrict__ dx, float* __restrict__ dw,
                    float* __restrict__ db, long long npix) {
+  pdl_prologue();
   __shared__ float sh[COUT * 17];
   float wr[COUT][16], aw[COUT][16], ab[COUT];
 #pragma unroll
@@ -372,19 +377,19 @@ static int direct_fprop(const smsut_conv_direct_args* a, cudaStream_t stream) {
   const int cw = p.cout > p.y_ld ? p.cout : p.y_ld;  // channels to write (incl. zero padding)
   if (npix * p.cout <= 4096 && p.y_ld == p.cout && p.cin >= 32) {
     const long long warps = npix * p.cout;
-    direct_fprop_small_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(p);
+    launch_pdl(direct_fprop_small_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, stream, p);
   } else if (cw <= 1) {
     p.cch = pick_cch(taps, 1, p.cin);
     dim3 grid((unsigned)((npix + 127) / 128), 1);
-    direct_fprop_kernel<1><<<grid, 128, (size_t)taps * p.cch * 1 * 4, stream>>>(p);
+    launch_pdl(direct_fprop_kernel<1>, grid, 128, (size_t)taps * p.cch * 1 * 4, stream, p);
   } else if (cw <= 8) {
     p.cch = pick_cch(taps, 8, p.cin);
     dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 7) / 8));
-    direct_fprop_kernel<8><<<grid, 128, (size_t)taps * p.cch * 8 * 4, stream>>>(p);
+    launch_pdl(direct_fprop_kernel<8>, grid, 128, (size_t)taps * p.cch * 8 * 4, stream, p);
   } else {
     p.cch = pick_cch(taps, 16, p.cin);
     dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 15) / 16));
-    direct_fprop_kernel<16><<<grid, 128, (size_t)taps * p.cch * 16 * 4, stream>>>(p);
+    launch_pdl(direct_fprop_kernel<16>, grid, 128, (size_t)taps * p.cch * 16 * 4, stream, p);
   }
   count_launch();
   return launch_status("direct_fprop_kernel");
@@ -400,15 +405,15 @@ static int direct_dgrad(const smsut_conv_direct_args* a, cudaStream_t stream) {
   if (cw <= 1) {
     p.cch = pick_cch(taps, 1, p.cout);
     dim3 grid((unsigned)((npix + 127) / 128), 1);
-    direct_dgrad_kernel<1><<<grid, 128, (size_t)taps * p.cch * 1 * 4, stream>>>(p);
+    launch_pdl(direct_dgrad_kernel<1>, grid, 128, (size_t)taps * p.cch * 1 * 4, stream, p);
   } else if (cw <= 8) {
     p.cch = pick_cch(taps, 8, p.cout);
     dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 7) / 8));
-    direct_dgrad_kernel<8><<<grid, 128, (size_t)taps * p.cch * 8 * 4, stream>>>(p);
+    launch_pdl(direct_dgrad_kernel<8>, grid, 128, (size_t)taps * p.cch * 8 * 4, stream, p);
   } else {
     p.cch = pick_cch(taps, 16, p.cout);
     dim3 grid((unsigned)((npix + 127) / 128), (unsigned)((cw + 15) / 16));
-    direct_dgrad_kernel<16><<<grid, 128, (size_t)taps * p.cch * 16 * 4, stream>>>(p);
+    launch_pdl(direct_dgrad_kernel<16>, grid, 128, (size_t)taps * p.cch * 16 * 4, stream, p);
   }
   count_launch();
   return launch_status("direct_dgrad_kernel");
@@ -427,7 +432,7 @@ static int direct_wgrad(const smsut_conv_direct_args* a, float* dw, float* dbias
   int rows_per_block = (int)((total_rows + want_blocks - 1) / want_blocks);
   if (rows_per_block < 1) rows_per_block = 1;
   dim3 grid((unsigned)((total_rows + rows_per_block - 1) / rows_per_block), (unsigned)chunks);
-  direct_wgrad_kernel<<<grid, 256, 0, stream>>>(p, dw, dbias, rows_per_block);
+  launch_pdl(direct_wgrad_kernel, grid, 256, 0, stream, p, dw, dbias, rows_per_block);
   count_launch();
   return launch_status("direct_wgrad_kernel");
 }
@@ -442,7 +447,7 @@ extern "C" int smsut_head1x1_bwd(const void* x, const float* dy, const float* y,
   const long long cap = 4LL * device_sm_count();
   if (blocks > cap) blocks = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
-#define HEAD_CASE(C) case C: head1x1_bwd_kernel<C><<<(unsigned)blocks, 256, 0, st>>>((const uint4*)x, dy, y, w, (uint4*)dx, dw, db, npix); break;
+#define HEAD_CASE(C) case C: launch_pdl(head1x1_bwd_kernel<C>, (unsigned)blocks, 256, 0, st, (const uint4*)x, dy, y, w, (uint4*)dx, dw, db, npix); break;
   switch (cout) { HEAD_CASE(1) HEAD_CASE(2) HEAD_CASE(3) HEAD_CASE(4) HEAD_CASE(5) HEAD_CASE(6) HEAD_CASE(7) HEAD_CASE(8) }
 #undef HEAD_CASE
   count_launch();

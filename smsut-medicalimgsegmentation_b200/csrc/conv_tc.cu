@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvTcParams p) {
+  pdl_trigger();   // the next kernel may be scheduled; this one waits for its predecessor after its own set-up
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
   __shared__ __align__(8) uint64_t empty_bar[8];
@@ -156,6 +157,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();      // barriers, TMEM and descriptors are ready: now the predecessor's results are needed
 
   if (warp == 0) {
     // ===================== TMA producer (warp-wide loop, elected issue) =====================
@@ -591,7 +593,7 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
     SMSUT_CHECK(a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 || a->ncols < 16, -1, "bf16 output pitch/offset must be multiples of 8");
 
   dim3 grid((unsigned)m_tiles, (unsigned)(a->ncols_pad / bn));
-  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], map_w, p);
+  launch_pdl(conv_tc_kernel, grid, kThreads, smem, stream, maps[0], maps[1], maps[2], maps[3], map_w, p);
   count_launch();
   return launch_status("conv_tc_kernel");
 }

@@ -55,6 +55,7 @@ template <int C>
 __global__ void __launch_bounds__(256)
 dice_ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                    const float* __restrict__ label_logits, float* __restrict__ acc, long long npix) {
+  pdl_prologue();
   __shared__ float sh[32];
   float tp[C], fp[C], fn[C], ce = 0.f;
 #pragma unroll
@@ -111,6 +112,7 @@ dice_ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict
 
 __global__ void dice_ce_finish_kernel(const float* __restrict__ acc, float* __restrict__ loss, float inv_npix, int c,
                                       float w_dc, float w_ce) {
+  pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float smooth = 1e-5f;
   float dsum = 0.f;
@@ -128,6 +130,7 @@ dice_ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict
                    const float* __restrict__ label_logits, const float* __restrict__ acc,
                    const float* __restrict__ gscale, float scale, float* __restrict__ dlogits, long long npix,
                    float inv_npix, float w_dc, float w_ce) {
+  pdl_prologue();
   // per-class dice derivative coefficients: d(dc_c)/dp = (2[y=c]*U - I)/U^2
   float I[C], U[C];
   const float smooth = 1e-5f;
@@ -192,6 +195,7 @@ template <int C, bool BWD>
 __global__ void __launch_bounds__(256)
 softmax_mse_kernel(const float* __restrict__ zs, const float* __restrict__ zt, float* __restrict__ out,
                    const float* __restrict__ gscale, float scale, float* __restrict__ dzs, long long npix) {
+  pdl_prologue();
   __shared__ float sh[32];
   float acc = 0.f;
   const float gs = BWD ? (gscale ? gscale[0] : 1.f) * scale * 2.f : 0.f;
@@ -217,6 +221,7 @@ softmax_mse_kernel(const float* __restrict__ zs, const float* __restrict__ zt, f
 
 template <int C>
 __global__ void argmax_kernel(const float* __restrict__ logits, long long* __restrict__ out, long long npix) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
     float z[C];
 #pragma unroll
@@ -227,6 +232,7 @@ __global__ void argmax_kernel(const float* __restrict__ logits, long long* __res
 
 __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                      float* __restrict__ out, long long count, float scale) {
+  pdl_prologue();
   __shared__ float sh[32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
@@ -236,6 +242,7 @@ __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ a
 }
 __global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                               const float* __restrict__ gscale, float scale, float* __restrict__ da, long long count) {
+  pdl_prologue();
   const float gs = (gscale ? gscale[0] : 1.f) * scale;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const float d = a[i] - b[i];
@@ -244,6 +251,7 @@ __global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restri
 }
 __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ x, float* __restrict__ out,
                                                   long long count, float scale) {
+  pdl_prologue();
   __shared__ float sh[32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ x, f
   if (threadIdx.x == 0) atomicAdd(out, r * scale);
 }
 __global__ void fill_kernel(float* __restrict__ x, long long count, float v) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     x[i] = v;
 }
@@ -259,11 +268,13 @@ __global__ void fill_kernel(float* __restrict__ x, long long count, float v) {
 // dx = dy * (1 - y^2)  (backward of the tanh fused into the translation head, network/ugan.py:73,82)
 __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
                                 long long count) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     dx[i] = dy[i] * (1.f - y[i] * y[i]);
 }
 __global__ void fill_scaled_kernel(float* __restrict__ x, long long count, const float* __restrict__ gscale,
                                    float scale) {
+  pdl_prologue();
   const float v = (gscale ? gscale[0] : 1.f) * scale;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     x[i] = v;
@@ -271,6 +282,7 @@ __global__ void fill_scaled_kernel(float* __restrict__ x, long long count, const
 // out = a*x + (1-a)*y with one coefficient per sample (x_hat of the gradient penalty, uganConsisTrainer.py:139)
 __global__ void lerp_rows_kernel(const float* __restrict__ alpha, const float* __restrict__ x,
                                  const float* __restrict__ y, float* __restrict__ out, long long per, long long total) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float a = alpha[i / per];
     out[i] = a * x[i] + (1.f - a) * y[i];
@@ -280,6 +292,7 @@ __global__ void lerp_rows_kernel(const float* __restrict__ alpha, const float* _
 // small-row cross entropy (rows <= a few hundred, c <= 8): one block
 __global__ void ce_rows_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                    float* __restrict__ out, int rows, int c, float scale) {
+  pdl_prologue();
   __shared__ float sh[32];
   float s = 0.f;
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
@@ -296,6 +309,7 @@ __global__ void ce_rows_fwd_kernel(const float* __restrict__ logits, const long 
 __global__ void ce_rows_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                    const float* __restrict__ gscale, float scale, float* __restrict__ dlogits,
                                    int rows, int c) {
+  pdl_prologue();
   const float gs = (gscale ? gscale[0] : 1.f) * scale / (float)rows;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
     const float* z = logits + (size_t)r * c;
@@ -312,6 +326,7 @@ __global__ void ce_rows_bwd_kernel(const float* __restrict__ logits, const long 
 // gradient penalty: one block per sample
 __global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ g, float* __restrict__ norm,
                                                       long long per) {
+  pdl_prologue();
   __shared__ float sh[32];
   const float* p = g + (size_t)blockIdx.x * per;
   float s = 0.f;
@@ -320,6 +335,7 @@ __global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) norm[blockIdx.x] = sqrtf(r);
 }
 __global__ void gp_loss_kernel(const float* __restrict__ norm, float* __restrict__ out, int b, float scale) {
+  pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float s = 0.f;
   for (int i = 0; i < b; ++i) s += (norm[i] - 1.f) * (norm[i] - 1.f);
@@ -328,6 +344,7 @@ __global__ void gp_loss_kernel(const float* __restrict__ norm, float* __restrict
 __global__ void gp_bwd_kernel(const float* __restrict__ g, const float* __restrict__ norm,
                               const float* __restrict__ gscale, float scale, float* __restrict__ u, int b,
                               long long per) {
+  pdl_prologue();
   const long long total = (long long)b * per;
   const float gs = (gscale ? gscale[0] : 1.f) * scale;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -341,6 +358,7 @@ __global__ void gp_bwd_kernel(const float* __restrict__ g, const float* __restri
 // PatchNCE sampling
 __global__ void gather_rows_kernel(const uint4* __restrict__ feat, const long long* __restrict__ ids,
                                    uint4* __restrict__ out, int n, int hw, int cvec, int nids) {
+  pdl_prologue();
   const long long total = (long long)n * nids * cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
@@ -352,6 +370,7 @@ __global__ void gather_rows_kernel(const uint4* __restrict__ feat, const long lo
 }
 __global__ void scatter_rows_add_kernel(const uint4* __restrict__ dout, const long long* __restrict__ ids,
                                         uint4* __restrict__ dfeat, int n, int hw, int cvec, int nids) {
+  pdl_prologue();
   const long long total = (long long)n * nids * cvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % cvec);
@@ -371,6 +390,7 @@ __global__ void scatter_rows_add_kernel(const uint4* __restrict__ dout, const lo
 // L2 normalisation, one warp per row
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norm,
                                   int rows, int c) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -386,6 +406,7 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
 // dx = (dy - y * <dy,y> * (r+eps)/r) / (r+eps); written as bf16 (feeds the tensor-core dgrad/wgrad)
 __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                   const float* __restrict__ norm, __nv_bfloat16* __restrict__ dx, int rows, int c) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -406,6 +427,7 @@ __global__ void __launch_bounds__(128)
 patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float* __restrict__ loss_rows,
                 float* __restrict__ out, const float* __restrict__ gscale, float scale, float* __restrict__ dq,
                 int groups, int np, int c, float inv_t) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int rows = groups * np;
@@ -514,14 +536,14 @@ extern "C" int smsut_dice_ce_fwd(const float* logits, const int64_t* labels, con
   SMSUT_CHECK(npix % 4 == 0 && npix > 0, -1, "pixel count must be a positive multiple of 4");
   SMSUT_CHECK((labels != nullptr) != (label_logits != nullptr), -1, "exactly one of labels / label_logits");
   const int grid = grid_for(npix / 4);
-  DISPATCH_C(c, (dice_ce_fwd_kernel<C_><<<grid, 256, 0, (cudaStream_t)st>>>(logits, (const long long*)labels,
+  DISPATCH_C(c, (launch_pdl(dice_ce_fwd_kernel<C_>, grid, 256, 0, (cudaStream_t)st, logits, (const long long*)labels,
                                                                            label_logits, acc, npix)));
   count_launch();
   return launch_status("dice_ce_fwd_kernel");
 }
 extern "C" int smsut_dice_ce_finish(const float* acc, float* loss, int64_t npix_total, int32_t c, float w_dc,
                                     float w_ce, smsut_stream_t st) {
-  dice_ce_finish_kernel<<<1, 32, 0, (cudaStream_t)st>>>(acc, loss, 1.f / (float)npix_total, c, w_dc, w_ce);
+  launch_pdl(dice_ce_finish_kernel, 1, 32, 0, (cudaStream_t)st, acc, loss, 1.f / (float)npix_total, c, w_dc, w_ce);
   count_launch();
   return launch_status("dice_ce_finish_kernel");
 }
@@ -531,7 +553,7 @@ extern "C" int smsut_dice_ce_bwd(const float* logits, const int64_t* labels, con
   SMSUT_CHECK(npix % 4 == 0 && npix > 0, -1, "pixel count must be a positive multiple of 4");
   SMSUT_CHECK((labels != nullptr) != (label_logits != nullptr), -1, "exactly one of labels / label_logits");
   const int grid = grid_for(npix / 4);
-  DISPATCH_C(c, (dice_ce_bwd_kernel<C_><<<grid, 256, 0, (cudaStream_t)st>>>(
+  DISPATCH_C(c, (launch_pdl(dice_ce_bwd_kernel<C_>, grid, 256, 0, (cudaStream_t)st, 
                     logits, (const long long*)labels, label_logits, acc, gscale, scale, dlogits, npix,
                     1.f / (float)npix_total, w_dc, w_ce)));
   count_launch();
@@ -541,7 +563,7 @@ extern "C" int smsut_softmax_mse_fwd(const float* zs, const float* zt, float* ou
                                      smsut_stream_t st) {
   const int grid = grid_for(npix);
   const float scale = 1.f / ((float)npix * (float)c);
-  DISPATCH_C(c, (softmax_mse_kernel<C_, false><<<grid, 256, 0, (cudaStream_t)st>>>(zs, zt, out, nullptr, scale,
+  DISPATCH_C(c, (launch_pdl(softmax_mse_kernel<C_, false>, grid, 256, 0, (cudaStream_t)st, zs, zt, out, nullptr, scale,
                                                                                  nullptr, npix)));
   count_launch();
   return launch_status("softmax_mse_fwd_kernel");
@@ -550,85 +572,85 @@ extern "C" int smsut_softmax_mse_bwd(const float* zs, const float* zt, const flo
                                      int32_t c, smsut_stream_t st) {
   const int grid = grid_for(npix);
   const float scale = 1.f / ((float)npix * (float)c);
-  DISPATCH_C(c, (softmax_mse_kernel<C_, true><<<grid, 256, 0, (cudaStream_t)st>>>(zs, zt, nullptr, gscale, scale, dzs,
+  DISPATCH_C(c, (launch_pdl(softmax_mse_kernel<C_, true>, grid, 256, 0, (cudaStream_t)st, zs, zt, nullptr, gscale, scale, dzs,
                                                                                 npix)));
   count_launch();
   return launch_status("softmax_mse_bwd_kernel");
 }
 extern "C" int smsut_argmax_c(const float* logits, int64_t* out, int64_t npix, int32_t c, smsut_stream_t st) {
   const int grid = grid_for(npix);
-  DISPATCH_C(c, (argmax_kernel<C_><<<grid, 256, 0, (cudaStream_t)st>>>(logits, (long long*)out, npix)));
+  DISPATCH_C(c, (launch_pdl(argmax_kernel<C_>, grid, 256, 0, (cudaStream_t)st, logits, (long long*)out, npix)));
   count_launch();
   return launch_status("argmax_kernel");
 }
 extern "C" int smsut_l1_fwd(const float* a, const float* b, float* out, int64_t count, float scale, smsut_stream_t st) {
-  l1_fwd_kernel<<<grid_for(count, 1024), 256, 0, (cudaStream_t)st>>>(a, b, out, count, scale);
+  launch_pdl(l1_fwd_kernel, grid_for(count, 1024), 256, 0, (cudaStream_t)st, a, b, out, count, scale);
   count_launch();
   return launch_status("l1_fwd_kernel");
 }
 extern "C" int smsut_l1_bwd(const float* a, const float* b, const float* gscale, float scale, float* da, int64_t count,
                             smsut_stream_t st) {
-  l1_bwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)st>>>(a, b, gscale, scale, da, count);
+  launch_pdl(l1_bwd_kernel, grid_for(count), 256, 0, (cudaStream_t)st, a, b, gscale, scale, da, count);
   count_launch();
   return launch_status("l1_bwd_kernel");
 }
 extern "C" int smsut_sum_f32(const float* x, float* out, int64_t count, float scale, smsut_stream_t st) {
-  sum_kernel<<<grid_for(count, 1024), 256, 0, (cudaStream_t)st>>>(x, out, count, scale);
+  launch_pdl(sum_kernel, grid_for(count, 1024), 256, 0, (cudaStream_t)st, x, out, count, scale);
   count_launch();
   return launch_status("sum_kernel");
 }
 extern "C" int smsut_fill_f32(float* x, int64_t count, float value, smsut_stream_t st) {
-  fill_kernel<<<grid_for(count), 256, 0, (cudaStream_t)st>>>(x, count, value);
+  launch_pdl(fill_kernel, grid_for(count), 256, 0, (cudaStream_t)st, x, count, value);
   count_launch();
   return launch_status("fill_kernel");
 }
 extern "C" int smsut_tanh_bwd(const float* dy, const float* y, float* dx, int64_t count, smsut_stream_t st) {
-  tanh_bwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)st>>>(dy, y, dx, count);
+  launch_pdl(tanh_bwd_kernel, grid_for(count), 256, 0, (cudaStream_t)st, dy, y, dx, count);
   count_launch();
   return launch_status("tanh_bwd_kernel");
 }
 extern "C" int smsut_fill_scaled_f32(float* x, int64_t count, const float* gscale, float scale, smsut_stream_t st) {
-  fill_scaled_kernel<<<grid_for(count), 256, 0, (cudaStream_t)st>>>(x, count, gscale, scale);
+  launch_pdl(fill_scaled_kernel, grid_for(count), 256, 0, (cudaStream_t)st, x, count, gscale, scale);
   count_launch();
   return launch_status("fill_scaled_kernel");
 }
 extern "C" int smsut_lerp_rows_f32(const float* alpha, const float* x, const float* y, float* out, int32_t rows,
                                    int64_t per, smsut_stream_t st) {
-  lerp_rows_kernel<<<grid_for((long long)rows * per), 256, 0, (cudaStream_t)st>>>(alpha, x, y, out, per,
+  launch_pdl(lerp_rows_kernel, grid_for((long long)rows * per), 256, 0, (cudaStream_t)st, alpha, x, y, out, per,
                                                                                  (long long)rows * per);
   count_launch();
   return launch_status("lerp_rows_kernel");
 }
 extern "C" int smsut_ce_rows_fwd(const float* logits, const int64_t* target, float* out, int32_t rows, int32_t c,
                                  float scale, smsut_stream_t st) {
-  ce_rows_fwd_kernel<<<1, 256, 0, (cudaStream_t)st>>>(logits, (const long long*)target, out, rows, c, scale);
+  launch_pdl(ce_rows_fwd_kernel, 1, 256, 0, (cudaStream_t)st, logits, (const long long*)target, out, rows, c, scale);
   count_launch();
   return launch_status("ce_rows_fwd_kernel");
 }
 extern "C" int smsut_ce_rows_bwd(const float* logits, const int64_t* target, const float* gscale, float scale,
                                  float* dlogits, int32_t rows, int32_t c, smsut_stream_t st) {
-  ce_rows_bwd_kernel<<<grid_for(rows), 256, 0, (cudaStream_t)st>>>(logits, (const long long*)target, gscale, scale,
+  launch_pdl(ce_rows_bwd_kernel, grid_for(rows), 256, 0, (cudaStream_t)st, logits, (const long long*)target, gscale, scale,
                                                                    dlogits, rows, c);
   count_launch();
   return launch_status("ce_rows_bwd_kernel");
 }
 extern "C" int smsut_gp_fwd(const float* g, float* norm, float* out, int32_t b, int64_t per, float scale,
                             smsut_stream_t st) {
-  gp_norm_kernel<<<b, 256, 0, (cudaStream_t)st>>>(g, norm, per);
-  gp_loss_kernel<<<1, 32, 0, (cudaStream_t)st>>>(norm, out, b, scale);
+  launch_pdl(gp_norm_kernel, b, 256, 0, (cudaStream_t)st, g, norm, per);
+  launch_pdl(gp_loss_kernel, 1, 32, 0, (cudaStream_t)st, norm, out, b, scale);
   count_launch(); count_launch();
   return launch_status("gp_fwd kernels");
 }
 extern "C" int smsut_gp_bwd(const float* g, const float* norm, const float* gscale, float scale, float* u, int32_t b,
                             int64_t per, smsut_stream_t st) {
-  gp_bwd_kernel<<<grid_for((long long)b * per), 256, 0, (cudaStream_t)st>>>(g, norm, gscale, scale, u, b, per);
+  launch_pdl(gp_bwd_kernel, grid_for((long long)b * per), 256, 0, (cudaStream_t)st, g, norm, gscale, scale, u, b, per);
   count_launch();
   return launch_status("gp_bwd_kernel");
 }
 extern "C" int smsut_gather_rows(const void* feat, const int64_t* ids, void* out, int32_t n, int32_t hw, int32_t c,
                                  int32_t nids, smsut_stream_t st) {
   SMSUT_CHECK(c % 8 == 0, -1, "c must be a multiple of 8");
-  gather_rows_kernel<<<grid_for((long long)n * nids * (c / 8)), 256, 0, (cudaStream_t)st>>>(
+  launch_pdl(gather_rows_kernel, grid_for((long long)n * nids * (c / 8)), 256, 0, (cudaStream_t)st, 
       (const uint4*)feat, (const long long*)ids, (uint4*)out, n, hw, c / 8, nids);
   count_launch();
   return launch_status("gather_rows_kernel");
@@ -636,19 +658,19 @@ extern "C" int smsut_gather_rows(const void* feat, const int64_t* ids, void* out
 extern "C" int smsut_scatter_rows_add(const void* dout, const int64_t* ids, void* dfeat, int32_t n, int32_t hw,
                                       int32_t c, int32_t nids, smsut_stream_t st) {
   SMSUT_CHECK(c % 8 == 0, -1, "c must be a multiple of 8");
-  scatter_rows_add_kernel<<<grid_for((long long)n * nids * (c / 8)), 256, 0, (cudaStream_t)st>>>(
+  launch_pdl(scatter_rows_add_kernel, grid_for((long long)n * nids * (c / 8)), 256, 0, (cudaStream_t)st, 
       (const uint4*)dout, (const long long*)ids, (uint4*)dfeat, n, hw, c / 8, nids);
   count_launch();
   return launch_status("scatter_rows_add_kernel");
 }
 extern "C" int smsut_l2norm_fwd(const float* x, float* y, float* norm, int32_t rows, int32_t c, smsut_stream_t st) {
-  l2norm_fwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)st>>>(x, y, norm, rows, c);
+  launch_pdl(l2norm_fwd_kernel, (rows + 3) / 4, 128, 0, (cudaStream_t)st, x, y, norm, rows, c);
   count_launch();
   return launch_status("l2norm_fwd_kernel");
 }
 extern "C" int smsut_l2norm_bwd(const float* dy, const float* y, const float* norm, void* dx, int32_t rows, int32_t c,
                                 smsut_stream_t st) {
-  l2norm_bwd_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)st>>>(dy, y, norm, (__nv_bfloat16*)dx, rows, c);
+  launch_pdl(l2norm_bwd_kernel, (rows + 3) / 4, 128, 0, (cudaStream_t)st, dy, y, norm, (__nv_bfloat16*)dx, rows, c);
   count_launch();
   return launch_status("l2norm_bwd_kernel");
 }
@@ -656,7 +678,7 @@ extern "C" int smsut_patchnce_fwd(const float* q, const float* k, float* loss_ro
                                   int32_t np, int32_t c, float inv_t, float scale, smsut_stream_t st) {
   SMSUT_CHECK(c % 32 == 0 && c <= 512, -1, "PatchNCE feature dim must be a multiple of 32 and <= 512");
   const int rows = groups * np;
-  patchnce_kernel<false><<<(rows + 3) / 4, 128, 0, (cudaStream_t)st>>>(q, k, loss_rows, out, nullptr, scale, nullptr,
+  launch_pdl(patchnce_kernel<false>, (rows + 3) / 4, 128, 0, (cudaStream_t)st, q, k, loss_rows, out, nullptr, scale, nullptr,
                                                                       groups, np, c, inv_t);
   count_launch();
   return launch_status("patchnce_fwd_kernel");
@@ -665,7 +687,7 @@ extern "C" int smsut_patchnce_bwd(const float* q, const float* k, const float* g
                                   int32_t groups, int32_t np, int32_t c, float inv_t, smsut_stream_t st) {
   SMSUT_CHECK(c % 32 == 0 && c <= 512, -1, "PatchNCE feature dim must be a multiple of 32 and <= 512");
   const int rows = groups * np;
-  patchnce_kernel<true><<<(rows + 3) / 4, 128, 0, (cudaStream_t)st>>>(q, k, nullptr, nullptr, gscale, scale, dq,
+  launch_pdl(patchnce_kernel<true>, (rows + 3) / 4, 128, 0, (cudaStream_t)st, q, k, nullptr, nullptr, gscale, scale, dq,
                                                                      groups, np, c, inv_t);
   count_launch();
   return launch_status("patchnce_bwd_kernel");

@@ -115,6 +115,7 @@ __device__ __forceinline__ uint4 zero4() { return make_uint4(0u, 0u, 0u, 0u); }
 
 __global__ void __launch_bounds__(kNT, 4) in_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, int hw,
                                                           int c, int splits) {
+  pdl_prologue();
   extern __shared__ float sh[];
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
@@ -149,6 +150,7 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
                 const float* __restrict__ beta_a, const void* __restrict__ xb, const float* __restrict__ stats_b,
                 const float* __restrict__ gamma_b, const float* __restrict__ beta_b, const void* __restrict__ res,
                 void* __restrict__ out, int hw, int c, int cp, int splits, int act, float slope) {
+  pdl_prologue();
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
@@ -229,6 +231,7 @@ in_bwd_reduce_kernel(const void* __restrict__ dout, const void* __restrict__ out
                      const float* __restrict__ stats_a, const void* __restrict__ xb,
                      const float* __restrict__ stats_b, float* __restrict__ red, int hw, int c, int splits, int act,
                      float slope) {
+  pdl_prologue();
   extern __shared__ float sh[];
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
@@ -307,6 +310,7 @@ in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out,
                     const float* __restrict__ stats_b, const float* __restrict__ gamma_b, void* __restrict__ dxb,
                     float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, void* __restrict__ dres,
                     const float* __restrict__ red, int hw, int c, int cp, int splits, int act, float slope) {
+  pdl_prologue();
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
@@ -399,6 +403,7 @@ in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out,
 __global__ void __launch_bounds__(kNT)
 in_bwd2_reduce_kernel(const void* __restrict__ u, const void* __restrict__ dy, const void* __restrict__ x,
                       const float* __restrict__ stats, float* __restrict__ red2, int hw, int c, int splits) {
+  pdl_prologue();
   extern __shared__ float sh[];
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
@@ -434,6 +439,7 @@ in_bwd2_apply_kernel(const void* __restrict__ u, const void* __restrict__ dy, co
                      const float* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ red2, void* __restrict__ g_dy, void* __restrict__ g_x,
                      float* __restrict__ dgamma, int hw, int c, int splits) {
+  pdl_prologue();
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
@@ -479,6 +485,7 @@ in_bwd2_apply_kernel(const void* __restrict__ u, const void* __restrict__ dy, co
 // ---------------------------------------------------------------------------------------------
 __global__ void act_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long nvec, int act,
                                float slope) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float v[8];
     unpack8(x[i], v);
@@ -490,6 +497,7 @@ __global__ void act_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ 
 __global__ void act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ ref,
                                const uint4* __restrict__ add, uint4* __restrict__ dx, long long nvec, int act,
                                float slope) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float g[8], r[8];
     unpack8(dy[i], g);
@@ -508,6 +516,7 @@ __global__ void act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __rest
 }
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
                            long long nvec) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
     float x[8], y[8];
     unpack8(a[i], x);
@@ -521,6 +530,7 @@ __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict_
 // column sums of a (rows, c) bf16 matrix (bias gradients of the netF Linear layers)
 __global__ void __launch_bounds__(kNT) colsum_kernel(const void* __restrict__ x, float* __restrict__ out, int rows,
                                                      int c, int splits) {
+  pdl_prologue();
   extern __shared__ float sh[];
   const Strip s = make_strip(c, rows, splits);
   float acc[1][8];
@@ -574,7 +584,7 @@ extern "C" int smsut_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, f
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  in_stats_kernel<<<dim3(n, splits), kNT, 2 * c * sizeof(float), (cudaStream_t)st>>>(x, stats, hw, c, splits);
+  launch_pdl(in_stats_kernel, dim3(n, splits), kNT, 2 * c * sizeof(float), (cudaStream_t)st, x, stats, hw, c, splits);
   count_launch();
   return launch_status("in_stats_kernel");
 }
@@ -587,7 +597,7 @@ extern "C" int smsut_in_apply(const void* xa, const float* stats_a, const float*
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
 #define IN_APPLY(HB, HR)                                                                                          \
-  in_apply_kernel<HB, HR><<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(xa, stats_a, gamma_a, beta_a, xb, stats_b, \
+  launch_pdl(in_apply_kernel<HB, HR>, dim3(n, splits), kNT, 0, (cudaStream_t)st, xa, stats_a, gamma_a, beta_a, xb, stats_b, \
                                                                          gamma_b, beta_b, res, out, hw, c, cp, splits, act, slope)
   if (xb != nullptr) { if (res != nullptr) IN_APPLY(true, true); else IN_APPLY(true, false); }
   else { if (res != nullptr) IN_APPLY(false, true); else IN_APPLY(false, false); }
@@ -603,10 +613,10 @@ extern "C" int smsut_in_bwd_reduce(const void* dout, const void* out, const void
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
   if (xb != nullptr)
-    in_bwd_reduce_kernel<true><<<dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st>>>(
+    launch_pdl(in_bwd_reduce_kernel<true>, dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st, 
         dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
   else
-    in_bwd_reduce_kernel<false><<<dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st>>>(
+    launch_pdl(in_bwd_reduce_kernel<false>, dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st, 
         dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
   count_launch();
   return launch_status("in_bwd_reduce_kernel");
@@ -621,7 +631,7 @@ extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void*
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
 #define IN_BWD_APPLY(HB, HR)                                                                                       \
-  in_bwd_apply_kernel<HB, HR><<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(                                       \
+  launch_pdl(in_bwd_apply_kernel<HB, HR>, dim3(n, splits), kNT, 0, (cudaStream_t)st,                                        \
       dout, out, xa, stats_a, gamma_a, dxa, dgamma_a, dbeta_a, xb, stats_b, gamma_b, dxb, dgamma_b, dbeta_b, dres, red, \
       hw, c, cp, splits, act, slope)
   if (xb != nullptr) { if (dres != nullptr) IN_BWD_APPLY(true, true); else IN_BWD_APPLY(true, false); }
@@ -636,7 +646,7 @@ extern "C" int smsut_in_bwd2_reduce(const void* u, const void* dy, const void* x
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  in_bwd2_reduce_kernel<<<dim3(n, splits), kNT, 5 * c * sizeof(float), (cudaStream_t)st>>>(u, dy, x, stats, red2, hw,
+  launch_pdl(in_bwd2_reduce_kernel, dim3(n, splits), kNT, 5 * c * sizeof(float), (cudaStream_t)st, u, dy, x, stats, red2, hw,
                                                                                           c, splits);
   count_launch();
   return launch_status("in_bwd2_reduce_kernel");
@@ -648,7 +658,7 @@ extern "C" int smsut_in_bwd2_apply(const void* u, const void* dy, const void* x,
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  in_bwd2_apply_kernel<<<dim3(n, splits), kNT, 0, (cudaStream_t)st>>>(u, dy, x, stats, gamma, red2, g_dy, g_x, dgamma,
+  launch_pdl(in_bwd2_apply_kernel, dim3(n, splits), kNT, 0, (cudaStream_t)st, u, dy, x, stats, gamma, red2, g_dy, g_x, dgamma,
                                                                       hw, c, splits);
   count_launch();
   return launch_status("in_bwd2_apply_kernel");
@@ -658,28 +668,28 @@ extern "C" int smsut_colsum_bf16(const void* x, int32_t rows, int32_t c, float* 
   int rc = check_nc(1, rows, c);
   if (rc) return rc;
   const int splits = pick_splits(1, rows, c);
-  colsum_kernel<<<dim3(1, splits), kNT, c * sizeof(float), (cudaStream_t)st>>>(x, out, rows, c, splits);
+  launch_pdl(colsum_kernel, dim3(1, splits), kNT, c * sizeof(float), (cudaStream_t)st, x, out, rows, c, splits);
   count_launch();
   return launch_status("colsum_kernel");
 }
 
 extern "C" int smsut_act_fwd(const void* x, void* y, int64_t count, int32_t act, float slope, smsut_stream_t st) {
   SMSUT_CHECK(count % 8 == 0, -1, "element count must be a multiple of 8");
-  act_fwd_kernel<<<grid_for(count / 8), 256, 0, (cudaStream_t)st>>>((const uint4*)x, (uint4*)y, count / 8, act, slope);
+  launch_pdl(act_fwd_kernel, grid_for(count / 8), 256, 0, (cudaStream_t)st, (const uint4*)x, (uint4*)y, count / 8, act, slope);
   count_launch();
   return launch_status("act_fwd_kernel");
 }
 extern "C" int smsut_act_bwd(const void* dy, const void* ref, const void* add, void* dx, int64_t count, int32_t act,
                              float slope, smsut_stream_t st) {
   SMSUT_CHECK(count % 8 == 0, -1, "element count must be a multiple of 8");
-  act_bwd_kernel<<<grid_for(count / 8), 256, 0, (cudaStream_t)st>>>((const uint4*)dy, (const uint4*)ref,
+  launch_pdl(act_bwd_kernel, grid_for(count / 8), 256, 0, (cudaStream_t)st, (const uint4*)dy, (const uint4*)ref,
                                                                     (const uint4*)add, (uint4*)dx, count / 8, act, slope);
   count_launch();
   return launch_status("act_bwd_kernel");
 }
 extern "C" int smsut_add_bf16(const void* a, const void* b, void* out, int64_t count, smsut_stream_t st) {
   SMSUT_CHECK(count % 8 == 0, -1, "element count must be a multiple of 8");
-  add_kernel<<<grid_for(count / 8), 256, 0, (cudaStream_t)st>>>((const uint4*)a, (const uint4*)b, (uint4*)out,
+  launch_pdl(add_kernel, grid_for(count / 8), 256, 0, (cudaStream_t)st, (const uint4*)a, (const uint4*)b, (uint4*)out,
                                                                 count / 8);
   count_launch();
   return launch_status("add_kernel");

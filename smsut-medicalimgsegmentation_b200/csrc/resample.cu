@@ -18,6 +18,7 @@ __device__ __forceinline__ void st8(void* b, size_t off, const uint4& v) {
 
 // one thread per (pooled pixel, 8-channel group)
 __global__ void maxpool2_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int h, int w, int c) {
+  pdl_prologue();
   const int cg = c >> 3, ho = h >> 1, wo = w >> 1;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -40,6 +41,7 @@ __global__ void maxpool2_fwd_kernel(const void* __restrict__ x, void* __restrict
 
 __global__ void maxpool2_bwd_kernel(const void* __restrict__ x, const void* __restrict__ dy,
                                     const void* __restrict__ add, void* __restrict__ dx, int n, int h, int w, int c) {
+  pdl_prologue();
   const int cg = c >> 3, ho = h >> 1, wo = w >> 1;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -79,6 +81,7 @@ __global__ void maxpool2_bwd_kernel(const void* __restrict__ x, const void* __re
 }
 
 __global__ void avgpool2_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int h, int w, int c) {
+  pdl_prologue();
   const int cg = c >> 3, ho = h >> 1, wo = w >> 1;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -102,6 +105,7 @@ __global__ void avgpool2_fwd_kernel(const void* __restrict__ x, void* __restrict
 // (n, h, w, c) is the FULL-resolution shape of dx; dy is (n, h/2, w/2, c)
 __global__ void avgpool2_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ add, void* __restrict__ dx,
                                     int n, int h, int w, int c) {
+  pdl_prologue();
   const int cg = c >> 3, ho = h >> 1, wo = w >> 1;
   const long long total = (long long)n * h * w * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -133,6 +137,7 @@ __device__ __forceinline__ void bil_taps(int o, int len, int& i0, int& i1, float
 }
 
 __global__ void bilinear2_fwd_kernel(const void* __restrict__ x, void* __restrict__ y, int n, int h, int w, int c) {
+  pdl_prologue();
   const int cg = c >> 3, ho = 2 * h, wo = 2 * w;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -165,6 +170,7 @@ __device__ __forceinline__ void bil_adj(int k, int len, int* o, float* wt) {
   o[3] = 2 * k + 2; wt[3] = k < len - 1 ? 0.25f : 0.f;
 }
 __global__ void bilinear2_bwd_kernel(const void* __restrict__ dy, void* __restrict__ dx, int n, int h, int w, int c) {
+  pdl_prologue();
   const int cg = c >> 3, ho = 2 * h, wo = 2 * w;
   const long long total = (long long)n * h * w * cg;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -198,6 +204,7 @@ __global__ void bilinear2_bwd_kernel(const void* __restrict__ dy, void* __restri
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c, int hw,
                                     int c_pad) {
+  pdl_prologue();
   const long long total = (long long)n * hw * c_pad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i % c_pad);
@@ -210,6 +217,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 // c_pad == 16 (the network inputs: 1 .. 16 channels): one thread assembles a pixel's 16 channels and writes them with
 // two 128-bit stores (the element-per-thread kernel above issues sixteen 2-byte stores per pixel)
 __global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int c, int hw) {
+  pdl_prologue();
   const long long total = (long long)n * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / hw);
@@ -224,6 +232,7 @@ __global__ void nchw_to_nhwc16_kernel(const float* __restrict__ x, __nv_bfloat16
 }
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int c, int hw,
                                     int x_ld) {
+  pdl_prologue();
   const long long total = (long long)n * c * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int q = (int)(i % hw);
@@ -235,6 +244,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 }
 __global__ void build_tsl_input_kernel(const float* __restrict__ x, const float* __restrict__ m,
                                        __nv_bfloat16* __restrict__ y, int n, int hw, int n_modal, int c_pad) {
+  pdl_prologue();
   const long long total = (long long)n * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / hw);
@@ -272,7 +282,7 @@ using namespace smsut;
 extern "C" int smsut_maxpool2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, smsut_stream_t st) {
   int rc = check_pool(n, h, w, c, true);
   if (rc) return rc;
-  maxpool2_fwd_kernel<<<grid_for((long long)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)st>>>(x, y, n, h, w, c);
+  launch_pdl(maxpool2_fwd_kernel, grid_for((long long)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)st, x, y, n, h, w, c);
   count_launch();
   return launch_status("maxpool2_fwd_kernel");
 }
@@ -280,14 +290,14 @@ extern "C" int smsut_maxpool2_bwd(const void* x, const void* dy, const void* add
                                   int32_t w, int32_t c, smsut_stream_t st) {
   int rc = check_pool(n, h, w, c, true);
   if (rc) return rc;
-  maxpool2_bwd_kernel<<<grid_for((long long)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)st>>>(x, dy, add, dx, n, h, w, c);
+  launch_pdl(maxpool2_bwd_kernel, grid_for((long long)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)st, x, dy, add, dx, n, h, w, c);
   count_launch();
   return launch_status("maxpool2_bwd_kernel");
 }
 extern "C" int smsut_avgpool2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, smsut_stream_t st) {
   int rc = check_pool(n, h, w, c, true);
   if (rc) return rc;
-  avgpool2_fwd_kernel<<<grid_for((long long)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)st>>>(x, y, n, h, w, c);
+  launch_pdl(avgpool2_fwd_kernel, grid_for((long long)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)st, x, y, n, h, w, c);
   count_launch();
   return launch_status("avgpool2_fwd_kernel");
 }
@@ -295,21 +305,21 @@ extern "C" int smsut_avgpool2_bwd(const void* dy, const void* add, void* dx, int
                                   smsut_stream_t st) {
   int rc = check_pool(n, h, w, c, true);
   if (rc) return rc;
-  avgpool2_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)st>>>(dy, add, dx, n, h, w, c);
+  launch_pdl(avgpool2_bwd_kernel, grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)st, dy, add, dx, n, h, w, c);
   count_launch();
   return launch_status("avgpool2_bwd_kernel");
 }
 extern "C" int smsut_bilinear2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w, int32_t c, smsut_stream_t st) {
   int rc = check_pool(n, h, w, c, false);
   if (rc) return rc;
-  bilinear2_fwd_kernel<<<grid_for((long long)n * 4 * h * w * (c / 8)), 256, 0, (cudaStream_t)st>>>(x, y, n, h, w, c);
+  launch_pdl(bilinear2_fwd_kernel, grid_for((long long)n * 4 * h * w * (c / 8)), 256, 0, (cudaStream_t)st, x, y, n, h, w, c);
   count_launch();
   return launch_status("bilinear2_fwd_kernel");
 }
 extern "C" int smsut_bilinear2_bwd(const void* dy, void* dx, int32_t n, int32_t h, int32_t w, int32_t c, smsut_stream_t st) {
   int rc = check_pool(n, h, w, c, false);
   if (rc) return rc;
-  bilinear2_bwd_kernel<<<grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)st>>>(dy, dx, n, h, w, c);
+  launch_pdl(bilinear2_bwd_kernel, grid_for((long long)n * h * w * (c / 8)), 256, 0, (cudaStream_t)st, dy, dx, n, h, w, c);
   count_launch();
   return launch_status("bilinear2_bwd_kernel");
 }
@@ -317,23 +327,23 @@ extern "C" int smsut_nchw_f32_to_nhwc_bf16(const float* x, void* y, int32_t n, i
                                            int32_t c_pad, smsut_stream_t st) {
   SMSUT_CHECK(c_pad >= c && n > 0 && c > 0, -1, "bad shape");
   if (c_pad == 16 && c <= 16)
-    nchw_to_nhwc16_kernel<<<grid_for((long long)n * h * w), 256, 0, (cudaStream_t)st>>>(x, (__nv_bfloat16*)y, n, c, h * w);
+    launch_pdl(nchw_to_nhwc16_kernel, grid_for((long long)n * h * w), 256, 0, (cudaStream_t)st, x, (__nv_bfloat16*)y, n, c, h * w);
   else
-    nchw_to_nhwc_kernel<<<grid_for((long long)n * h * w * c_pad), 256, 0, (cudaStream_t)st>>>(x, (__nv_bfloat16*)y, n, c, h * w, c_pad);
+    launch_pdl(nchw_to_nhwc_kernel, grid_for((long long)n * h * w * c_pad), 256, 0, (cudaStream_t)st, x, (__nv_bfloat16*)y, n, c, h * w, c_pad);
   count_launch();
   return launch_status("nchw_to_nhwc_kernel");
 }
 extern "C" int smsut_nhwc_bf16_to_nchw_f32(const void* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w,
                                            int32_t x_ld, smsut_stream_t st) {
   SMSUT_CHECK(x_ld >= c && n > 0 && c > 0, -1, "bad shape");
-  nhwc_to_nchw_kernel<<<grid_for((long long)n * h * w * c), 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, y, n, c, h * w, x_ld);
+  launch_pdl(nhwc_to_nchw_kernel, grid_for((long long)n * h * w * c), 256, 0, (cudaStream_t)st, (const __nv_bfloat16*)x, y, n, c, h * w, x_ld);
   count_launch();
   return launch_status("nhwc_to_nchw_kernel");
 }
 extern "C" int smsut_build_tsl_input(const float* x, const float* m, void* y, int32_t n, int32_t hw, int32_t n_modal,
                                      int32_t c_pad, smsut_stream_t st) {
   SMSUT_CHECK(c_pad >= 1 + n_modal, -1, "c_pad too small");
-  build_tsl_input_kernel<<<grid_for((long long)n * hw), 256, 0, (cudaStream_t)st>>>(x, m, (__nv_bfloat16*)y, n, hw, n_modal, c_pad);
+  launch_pdl(build_tsl_input_kernel, grid_for((long long)n * hw), 256, 0, (cudaStream_t)st, x, m, (__nv_bfloat16*)y, n, hw, n_modal, c_pad);
   count_launch();
   return launch_status("build_tsl_input_kernel");
 }

@@ -47,6 +47,7 @@ template <int KS>
 __global__ void __launch_bounds__(kWbThreads, 1)
 wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
                   const __grid_constant__ WgradBandParams p) {
+  pdl_trigger();   // the next kernel may be scheduled; this one waits for its predecessor after its own set-up
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t x_full[kWbMaxSlots];
   __shared__ __align__(8) uint64_t x_empty[kWbMaxSlots];
@@ -93,6 +94,7 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();      // barriers, TMEM and descriptors are ready: now the predecessor's results are needed
 
   if (warp == 0) {
     // ===================== TMA producer: x rows (with halo) and dy rows, each exactly once =====================
@@ -294,7 +296,7 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
       SMSUT_CUDA_OK(cudaFuncSetAttribute(wgrad_band_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    wgrad_band_kernel<KS_><<<grid, kWbThreads, smem, stream>>>(map_x, map_dy, p);                                  \
+    launch_pdl(wgrad_band_kernel<KS_>, grid, kWbThreads, smem, stream, map_x, map_dy, p);                                  \
     launched = true;                                                                                               \
   }
   WB_CASE(1) WB_CASE(3) WB_CASE(5)

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b0,
                 const __grid_constant__ CUtensorMap map_b1, const __grid_constant__ CUtensorMap map_b2,
                 const __grid_constant__ CUtensorMap map_b3, const __grid_constant__ WgradParams p) {
+  pdl_trigger();   // the next kernel may be scheduled; this one waits for its predecessor after its own set-up
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[4];
   __shared__ __align__(8) uint64_t empty_bar[4];
@@ -98,6 +99,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();      // barriers, TMEM and descriptors are ready: now the predecessor's results are needed
 
   const uint32_t a_stage_bytes = (uint32_t)p.a_real_blocks * p.a_block_bytes;
 
@@ -331,7 +333,7 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a->dw != nullptr, -1, "null dw");
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
   dim3 grid((unsigned)splits, (unsigned)mblocks, (unsigned)ngroups);
-  wgrad_tc_kernel<<<grid, kWgThreads, smem, stream>>>(map_a, map_b[0], map_b[1], map_b[2], map_b[3], p);
+  launch_pdl(wgrad_tc_kernel, grid, kWgThreads, smem, stream, map_a, map_b[0], map_b[1], map_b[2], map_b[3], p);
   count_launch();
   return launch_status("wgrad_tc_kernel");
 }
