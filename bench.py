@@ -129,38 +129,50 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def conv_roofline(torch, ops, batch, reps=5):
-    """conv_tc_kernel alone on the conv classes of one generator forward."""
-    classes = [  # (cin list, cout, H, ksize, count per G forward)
-        ([16], 16, 256, 3, 6), ([16, 16], 16, 256, 3, 2), ([16], 32, 128, 3, 2), ([32], 32, 128, 3, 4),
-        ([32, 32], 32, 128, 3, 2), ([32], 64, 64, 3, 2), ([64], 64, 64, 3, 4), ([64, 64], 64, 64, 3, 2),
-        ([64], 128, 32, 3, 2), ([128], 128, 32, 3, 4), ([128, 128], 128, 32, 3, 2), ([128], 256, 16, 3, 2),
-        ([256], 256, 16, 3, 2),
-    ]
-    flush = torch.empty(192 * 2 ** 20, dtype=torch.uint8, device="cuda")
+CONV_CLASSES = [  # (cin list, cout, H, ksize, count per G forward): SURVEY.md section 8(d)
+    ([16], 16, 256, 3, 6), ([16, 16], 16, 256, 3, 2), ([16], 32, 128, 3, 2), ([32], 32, 128, 3, 4),
+    ([32, 32], 32, 128, 3, 2), ([32], 64, 64, 3, 2), ([64], 64, 64, 3, 4), ([64, 64], 64, 64, 3, 2),
+    ([64], 128, 32, 3, 2), ([128], 128, 32, 3, 4), ([128, 128], 128, 32, 3, 2), ([128], 256, 16, 3, 2),
+    ([256], 256, 16, 3, 2),
+]
+
+
+def conv_roofline(torch, ops, batch, launches_per_class=24):
+    """The implicit-GEMM conv kernels (conv_band_kernel on the W % 128 == 0 layers, conv_tc_kernel below) alone on
+    the 13 3x3 conv classes of one generator forward.  Per class: `launches_per_class` launches captured in a CUDA
+    graph (no host launch latency in the timing), each reading its own input set -- the sets together are larger
+    than L2 (>= 160 MB, or 64 sets) so no launch finds its input cached -- timed with CUDA events around the replay
+    on the replay stream.  Returns (FLOP-weighted TFLOP/s over one G forward, per-class rows, launches timed)."""
     tot_flop = tot_ms = 0.0
     per = []
     launches = 0
-    for cins, cout, h, ks, count in classes:
-        xs = [torch.randn(batch, h, h, c, device="cuda").to(torch.bfloat16) for c in cins]
+    stream = torch.cuda.Stream()
+    for cins, cout, h, ks, count in CONV_CLASSES:
+        bytes_in = batch * h * h * sum(cins) * 2
+        nsets = max(2, min(64, -(-160 * 2 ** 20 // bytes_in)))
+        sets = [[torch.randn(batch, h, h, c, device="cuda").to(torch.bfloat16) for c in cins] for _ in range(nsets)]
         w = torch.randn(cout, sum(cins), ks, ks, device="cuda") * 0.05
         pw = ops.PackedWeight(w)
         ops.PackTable([pw]).refresh()
-        ops.conv_fprop(xs, pw)
-        ms = 0.0
-        for _ in range(reps):
-            flush.zero_()
-            torch.cuda._sleep(300000)   # the GPU spins ~150 us while the host queues the launch: the events bracket
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # the kernel only
-            e0.record()
-            ops.conv_fprop(xs, pw)
-            e1.record()
-            torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
-            launches += 1
-        ms /= reps
+        ops.conv_fprop(sets[0], pw, want_stats=True)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            with torch.cuda.graph(graph, stream=stream):
+                keep = [ops.conv_fprop(sets[r % nsets], pw, want_stats=True) for r in range(launches_per_class)]
+            graph.replay()                         # warm-up replay
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / launches_per_class
+        launches += launches_per_class
+        del keep, graph
         flop = 2.0 * batch * h * h * cout * sum(cins) * ks * ks
-        per.append({"cin": sum(cins), "cout": cout, "hw": h, "k": ks, "us": ms * 1e3, "tflops": flop / ms / 1e9})
+        ideal_us = max(flop / 1.6304e15, (bytes_in + batch * h * h * cout * 2) / 6.4846e12) * 1e6
+        per.append({"cin": sum(cins), "cout": cout, "hw": h, "k": ks, "us": ms * 1e3, "tflops": flop / ms / 1e9,
+                    "gbs": (bytes_in + batch * h * h * cout * 2) / ms / 1e6, "ideal_us": ideal_us})
         tot_flop += flop * count
         tot_ms += ms * count
     return tot_flop / tot_ms / 1e9, per, launches
@@ -272,10 +284,21 @@ def run_ours(args):
                                       f"bf16 GEMM peak ({how})"}}
     if par.rank == 0 and par.world == 1:
         tf, per, _ = conv_roofline(torch, ops, 2 * bs)
+        traffic = None
+        try:   # DRAM bytes per launch of the same launches under `ncu --set full` (profiles/r1_conv_classes_ncu.json)
+            t = json.load(open(os.path.join(ROOT, "profiles", "r1_conv_classes_ncu.json")))
+            traffic = t["dram_bytes_per_launch_weighted"]
+        except Exception:
+            pass
+        algo_bytes = sum(c[4] * (2 * bs) * c[2] * c[2] * (sum(c[0]) + c[1]) * 2 for c in CONV_CLASSES) / \
+            sum(c[4] for c in CONV_CLASSES)
         line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
-                            "traffic": None, "kernel": "conv_tc_kernel",
-                            "how": "FLOP-weighted over the 13 3x3 conv classes of one generator forward at 16 slices, "
-                                   f"each launch timed alone with CUDA events after an L2 flush; peak = burst ({how})",
+                            "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                            "kernel": "conv_band_kernel / conv_tc_kernel (tcgen05 implicit GEMM + fused IN statistics)",
+                            "how": "FLOP-weighted over the 13 3x3 conv classes of one generator forward at 16 slices: "
+                                   "24 launches per class captured in a CUDA graph, each on its own input set (sets "
+                                   "together > L2), CUDA events around the replay on its stream; peak = burst "
+                                   f"({how}); 8 of the 13 classes are HBM-bound (SURVEY.md section 8d): see gbs / ideal_us",
                             "per_class": per}
         rate, sec, threads = cpu_step_rate(2, 1, 0)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",

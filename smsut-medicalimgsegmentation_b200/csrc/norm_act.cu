@@ -225,15 +225,100 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
 // ---------------------------------------------------------------------------------------------
 // pass 1: red[n] = { sum g, sum g*xhat_a, sum g*xhat_b } with g = dout * act'(out).
 // In the loop only sum g*(x - mean) is accumulated; rstd is applied once at the end.
-template <bool HAS_B>
+//
+// ncu (profiles/r1_in_bwd_ncu.md) showed the first version of these two kernels ISSUE-bound at 2.5-3.3 TB/s: 48 % of
+// the issue slots busy at 30 % DRAM throughput, a third of the instructions being 64-bit index arithmetic and
+// per-load bounds predicates, plus a 12 k-instruction unrolled block reduction.  This version walks the strip with
+// 32-bit counters and pointer increments, keeps the bounds check out of the main loop (full steps + a tail), tests
+// the activation sign on the packed bf16 bits, and reduces a block through shuffles + one shared-memory pass.
+struct Strip32 {
+  int cg, g, lane0, nl;     // channel groups of 8, this thread's group, its first pixel in the strip, pixel stride
+  int p0, count;            // first pixel of the block's strip, number of pixels this THREAD visits
+};
+
+__device__ __forceinline__ Strip32 make_strip32(int c, int hw, int splits) {
+  Strip32 s;
+  s.cg = c >> 3;
+  s.g = threadIdx.x % s.cg;
+  s.lane0 = threadIdx.x / s.cg;
+  s.nl = kNT / s.cg;
+  const int per = (hw + splits - 1) / splits;
+  s.p0 = blockIdx.y * per;
+  int p1 = s.p0 + per;
+  if (p1 > hw) p1 = hw;
+  const int span = p1 - s.p0 - s.lane0;
+  s.count = span > 0 ? (span + s.nl - 1) / s.nl : 0;
+  return s;
+}
+
+// g = dout * act'(out) for 8 packed bf16: the sign test works on the raw bits (out > 0  <=>  bits in (0, 0x8000))
+template <bool HAS_ACT>
+__device__ __forceinline__ void load_g(const uint4& qd, const uint4& qo, float neg, float* g) {
+  unpack8(qd, g);
+  if (HAS_ACT) {
+    const uint32_t w[4] = {qo.x, qo.y, qo.z, qo.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lo = w[k] << 16, hi = w[k] & 0xffff0000u;
+      g[2 * k] *= ((int)lo > 0) ? 1.f : neg;
+      g[2 * k + 1] *= ((int)hi > 0) ? 1.f : neg;
+    }
+  }
+}
+
+// Sum NV x 8 per-thread values over the threads of the block that share a channel group; adds to dst[v*vstride + ch].
+// sh: [kNT/32][NV][min(c, 256)] floats (c <= 256: warps of a block cover the same channel groups) or unused.
+template <int NV>
+__device__ __forceinline__ void block_reduce_add32(float (&acc)[NV][8], float* sh, const Strip32& s, float* dst, int c,
+                                                   int vstride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (s.cg < 32) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float x = acc[v][j];
+        for (int off = 16; off >= s.cg; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        acc[v][j] = x;
+      }
+  }
+  if (c <= 256) {
+    // lanes < min(cg, 32) of every warp hold that warp's totals of channel group (warp's first group + lane)
+    const int ngl = s.cg < 32 ? s.cg : 32;
+    if (lane < ngl) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sh[(warp * NV + v) * c + s.g * 8 + j] = acc[v][j];
+    }
+    __syncthreads();
+    // warps covering the same groups: cg <= 32 -> all 8 warps; cg == 32 (c = 256) -> each warp is one pixel, all groups
+    for (int i = threadIdx.x; i < NV * c; i += kNT) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kNT / 32; ++w) t += sh[w * NV * c + i];
+      const int v = i / c, ch = i - v * c;
+      atomicAdd(dst + (size_t)v * vstride + ch, t);
+    }
+  } else {
+    // wide layers (c > 256, not on the SMSUT path): one atomic per thread and value
+    if (s.cg >= 32 || lane < s.cg) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dst + (size_t)v * vstride + s.g * 8 + j, acc[v][j]);
+    }
+  }
+}
+
+template <bool HAS_B, bool HAS_ACT>
 __global__ void __launch_bounds__(kNT, 3)
-in_bwd_reduce_kernel(const void* __restrict__ dout, const void* __restrict__ out, const void* __restrict__ xa,
-                     const float* __restrict__ stats_a, const void* __restrict__ xb,
-                     const float* __restrict__ stats_b, float* __restrict__ red, int hw, int c, int splits, int act,
-                     float slope) {
+in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
+                     const float* __restrict__ stats_a, const uint4* __restrict__ xb,
+                     const float* __restrict__ stats_b, float* __restrict__ red, int hw, int c, int splits, float neg) {
   pdl_prologue();
   extern __shared__ float sh[];
-  const Strip s = make_strip(c, hw, splits);
+  const Strip32 s = make_strip32(c, hw, splits);
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
@@ -251,41 +336,45 @@ in_bwd_reduce_kernel(const void* __restrict__ dout, const void* __restrict__ out
   float acc[3][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
-  const size_t base = (size_t)n * hw * c + ch0;
-  const bool has_act = act != SMSUT_ACT_NONE;
-  for (long long p = s.p0 + s.lane0; p < s.p1; p += (long long)kUB * s.nlanes) {
-    uint4 qd[kUB], qo[kUB], qa[kUB], qb[kUB];
+  // uint4 index of (pixel p, group g) = p * cg + g
+  size_t idx = ((size_t)n * hw + s.p0 + s.lane0) * s.cg + s.g;
+  const int step = s.nl * s.cg;
+  constexpr int U = 2;
+  int it = 0;
+  auto body = [&](const uint4& qd, const uint4& qo, const uint4& qa, const uint4& qb) {
+    float g[8], v[8];
+    load_g<HAS_ACT>(qd, qo, neg, g);
+    unpack8(qa, v);
 #pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      const long long pp = p + (long long)u * s.nlanes;
-      const bool ok = pp < s.p1;
-      const size_t off = base + (size_t)pp * c;
-      qd[u] = ok ? ldg16(dout, off) : zero4();          // g = 0 beyond the strip: contributes nothing
-      qo[u] = (ok && has_act) ? ldg16(out, off) : zero4();
-      qa[u] = ok ? ldg16(xa, off) : zero4();
-      if (HAS_B) qb[u] = ok ? ldg16(xb, off) : zero4();
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += g[j];
+      acc[1][j] = fmaf(g[j], v[j] - ma[j], acc[1][j]);
+    }
+    if (HAS_B) {
+      unpack8(qb, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g[j], v[j] - mb[j], acc[2][j]);
+    }
+  };
+  for (; it + U <= s.count; it += U, idx += (size_t)U * step) {
+    uint4 qd[U], qo[U], qa[U], qb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      qd[u] = dout[idx + (size_t)u * step];
+      if (HAS_ACT) qo[u] = out[idx + (size_t)u * step];
+      qa[u] = xa[idx + (size_t)u * step];
+      if (HAS_B) qb[u] = xb[idx + (size_t)u * step];
     }
 #pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      float g[8], v[8];
-      unpack8(qd[u], g);
-      if (has_act) {
-        unpack8(qo[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
-      }
-      unpack8(qa[u], v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] += g[j];
-        acc[1][j] = fmaf(g[j], v[j] - ma[j], acc[1][j]);
-      }
-      if (HAS_B) {
-        unpack8(qb[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g[j], v[j] - mb[j], acc[2][j]);
-      }
-    }
+    for (int u = 0; u < U; ++u) body(qd[u], qo[u], qa[u], qb[u]);
+  }
+  for (; it < s.count; ++it, idx += step) {
+    uint4 qo = zero4(), qb = zero4();
+    const uint4 qd = dout[idx];
+    if (HAS_ACT) qo = out[idx];
+    const uint4 qa = xa[idx];
+    if (HAS_B) qb = xb[idx];
+    body(qd, qo, qa, qb);
   }
   {
     float m[8], r[8];
@@ -298,20 +387,20 @@ in_bwd_reduce_kernel(const void* __restrict__ dout, const void* __restrict__ out
       for (int j = 0; j < 8; ++j) acc[2][j] *= r[j];
     }
   }
-  block_reduce_add<3>(acc, sh, s, red + (size_t)n * 3 * c, c, c);
+  block_reduce_add32<3>(acc, sh, s, red + (size_t)n * 3 * c, c, c);
 }
 
 // pass 2: dx = A*g + B*x + C per channel with A = gamma*rstd, B = -A*rstd*mean(g xhat), C = -A*mean(g) - B*mean
-template <bool HAS_B, bool HAS_RES>
+template <bool HAS_B, bool HAS_RES, bool HAS_ACT>
 __global__ void __launch_bounds__(kNT, 3)
-in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out, const void* __restrict__ xa,
-                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a, void* __restrict__ dxa,
-                    float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const void* __restrict__ xb,
-                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b, void* __restrict__ dxb,
-                    float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, void* __restrict__ dres,
-                    const float* __restrict__ red, int hw, int c, int cp, int splits, int act, float slope) {
+in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
+                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a, uint4* __restrict__ dxa,
+                    float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const uint4* __restrict__ xb,
+                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b, uint4* __restrict__ dxb,
+                    float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, uint4* __restrict__ dres,
+                    const float* __restrict__ red, int hw, int c, int cp, int splits, float neg) {
   pdl_prologue();
-  const Strip s = make_strip(c, hw, splits);
+  const Strip32 s = make_strip32(c, hw, splits);
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
@@ -351,44 +440,44 @@ in_bwd_apply_kernel(const void* __restrict__ dout, const void* __restrict__ out,
       }
     }
   }
-  const size_t base = (size_t)n * hw * c + ch0;
-  const bool has_act = act != SMSUT_ACT_NONE;
-  for (long long p = s.p0 + s.lane0; p < s.p1; p += (long long)kUB * s.nlanes) {
-    uint4 qd[kUB], qo[kUB], qa[kUB], qb[kUB];
+  size_t idx = ((size_t)n * hw + s.p0 + s.lane0) * s.cg + s.g;
+  const int step = s.nl * s.cg;
+  constexpr int U = 2;
+  int it = 0;
+  auto body = [&](const uint4& qd, const uint4& qo, const uint4& qa, const uint4& qb, size_t at) {
+    float g[8], v[8], o[8];
+    load_g<HAS_ACT>(qd, qo, neg, g);
+    if (HAS_RES) dres[at] = pack8(g);
+    unpack8(qa, v);
 #pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      const long long pp = p + (long long)u * s.nlanes;
-      const bool ok = pp < s.p1;
-      const size_t off = base + (size_t)pp * c;
-      qd[u] = ok ? ldg16(dout, off) : zero4();
-      qo[u] = (ok && has_act) ? ldg16(out, off) : zero4();
-      qa[u] = ok ? ldg16(xa, off) : zero4();
-      if (HAS_B) qb[u] = ok ? ldg16(xb, off) : zero4();
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(Aa[j], g[j], fmaf(Ba[j], v[j], Ca[j]));
+    dxa[at] = pack8(o);
+    if (HAS_B) {
+      unpack8(qb, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(Ab[j], g[j], fmaf(Bb[j], v[j], Cb[j]));
+      dxb[at] = pack8(o);
+    }
+  };
+  for (; it + U <= s.count; it += U, idx += (size_t)U * step) {
+    uint4 qd[U], qo[U], qa[U], qb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      qd[u] = dout[idx + (size_t)u * step];
+      if (HAS_ACT) qo[u] = out[idx + (size_t)u * step];
+      qa[u] = xa[idx + (size_t)u * step];
+      if (HAS_B) qb[u] = xb[idx + (size_t)u * step];
     }
 #pragma unroll
-    for (int u = 0; u < kUB; ++u) {
-      const long long pp = p + (long long)u * s.nlanes;
-      if (pp >= s.p1) break;
-      const size_t off = base + (size_t)pp * c;
-      float g[8], v[8], o[8];
-      unpack8(qd[u], g);
-      if (has_act) {
-        unpack8(qo[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= act_grad(v[j], act, slope);
-      }
-      if (HAS_RES) stg16(dres, off, pack8(g));
-      unpack8(qa[u], v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(Aa[j], g[j], fmaf(Ba[j], v[j], Ca[j]));
-      stg16(dxa, off, pack8(o));
-      if (HAS_B) {
-        unpack8(qb[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(Ab[j], g[j], fmaf(Bb[j], v[j], Cb[j]));
-        stg16(dxb, off, pack8(o));
-      }
-    }
+    for (int u = 0; u < U; ++u) body(qd[u], qo[u], qa[u], qb[u], idx + (size_t)u * step);
+  }
+  for (; it < s.count; ++it, idx += step) {
+    uint4 qo = zero4(), qb = zero4();
+    const uint4 qd = dout[idx];
+    if (HAS_ACT) qo = out[idx];
+    const uint4 qa = xa[idx];
+    if (HAS_B) qb = xb[idx];
+    body(qd, qo, qa, qb, idx);
   }
 }
 
@@ -612,12 +701,15 @@ extern "C" int smsut_in_bwd_reduce(const void* dout, const void* out, const void
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  if (xb != nullptr)
-    launch_pdl(in_bwd_reduce_kernel<true>, dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st, 
-        dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
-  else
-    launch_pdl(in_bwd_reduce_kernel<false>, dim3(n, splits), kNT, 3 * c * sizeof(float), (cudaStream_t)st, 
-        dout, out, xa, stats_a, xb, stats_b, red, hw, c, splits, act, slope);
+  SMSUT_CHECK(act == SMSUT_ACT_NONE || act == SMSUT_ACT_LRELU || act == SMSUT_ACT_RELU, -1, "in_bwd: unsupported activation");
+  const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
+  const size_t shm = c <= 256 ? (size_t)(kNT / 32) * 3 * c * sizeof(float) : 0;
+#define IN_BWD_RED(HB, HA)                                                                                        \
+  launch_pdl(in_bwd_reduce_kernel<HB, HA>, dim3(n, splits), kNT, shm, (cudaStream_t)st, (const uint4*)dout,        \
+             (const uint4*)out, (const uint4*)xa, stats_a, (const uint4*)xb, stats_b, red, hw, c, splits, neg)
+  if (xb != nullptr) { if (act != SMSUT_ACT_NONE) IN_BWD_RED(true, true); else IN_BWD_RED(true, false); }
+  else { if (act != SMSUT_ACT_NONE) IN_BWD_RED(false, true); else IN_BWD_RED(false, false); }
+#undef IN_BWD_RED
   count_launch();
   return launch_status("in_bwd_reduce_kernel");
 }
@@ -630,12 +722,17 @@ extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void*
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-#define IN_BWD_APPLY(HB, HR)                                                                                       \
-  launch_pdl(in_bwd_apply_kernel<HB, HR>, dim3(n, splits), kNT, 0, (cudaStream_t)st,                                        \
-      dout, out, xa, stats_a, gamma_a, dxa, dgamma_a, dbeta_a, xb, stats_b, gamma_b, dxb, dgamma_b, dbeta_b, dres, red, \
-      hw, c, cp, splits, act, slope)
+  SMSUT_CHECK(act == SMSUT_ACT_NONE || act == SMSUT_ACT_LRELU || act == SMSUT_ACT_RELU, -1, "in_bwd: unsupported activation");
+  const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
+#define IN_BWD_APPLY2(HB, HR, HA)                                                                                  \
+  launch_pdl(in_bwd_apply_kernel<HB, HR, HA>, dim3(n, splits), kNT, 0, (cudaStream_t)st, (const uint4*)dout,       \
+             (const uint4*)out, (const uint4*)xa, stats_a, gamma_a, (uint4*)dxa, dgamma_a, dbeta_a, (const uint4*)xb, \
+             stats_b, gamma_b, (uint4*)dxb, dgamma_b, dbeta_b, (uint4*)dres, red, hw, c, cp, splits, neg)
+#define IN_BWD_APPLY(HB, HR) \
+  do { if (act != SMSUT_ACT_NONE) IN_BWD_APPLY2(HB, HR, true); else IN_BWD_APPLY2(HB, HR, false); } while (0)
   if (xb != nullptr) { if (dres != nullptr) IN_BWD_APPLY(true, true); else IN_BWD_APPLY(true, false); }
   else { if (dres != nullptr) IN_BWD_APPLY(false, true); else IN_BWD_APPLY(false, false); }
+#undef IN_BWD_APPLY2
 #undef IN_BWD_APPLY
   count_launch();
   return launch_status("in_bwd_apply_kernel");
