@@ -6,3 +6,12 @@ trainer API.  The directory name is not a Python identifier; imp
 from . import _lib  # noqa: F401  (fails loudly when libsmsut_b200.so is missing)
 
 __all__ = ["_lib"]
+
+# Branch streams (ops.parallel_branch) make some leaf gradients arrive from another stream than the one their
+# AccumulateGrad node was created on; the engine synchronises them correctly, the warning is only advice.
+try:
+    import torch.autograd.graph as _ag
+    if hasattr(_ag, "set_warn_on_accumulate_grad_stream_mismatch"):
+        _ag.set_warn_on_accumulate_grad_stream_mismatch(False)
+except Exception:      # pragma: no cover
+    pass

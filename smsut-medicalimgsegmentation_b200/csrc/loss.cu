@@ -421,36 +421,39 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
   for (int i = lane; i < c; i += 32) dx[(size_t)row * c + i] = f2bf((g[i] - yy[i] * k) * inv);
 }
 
-// PatchNCE: one warp per query row; c must be a multiple of 32 and <= 512
+// PatchNCE: one 4-warp block per query row, each warp owns a quarter of the negatives; c must be a multiple of 32
+// and <= 512.  (One warp per row left 7 warps per SM walking 128 negatives one after the other: 130-175 us for a
+// 34 MFLOP problem.)  kJ negatives per step: their dot products and butterfly reductions are independent streams.
 template <bool BWD>
 __global__ void __launch_bounds__(128)
 patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float* __restrict__ loss_rows,
                 float* __restrict__ out, const float* __restrict__ gscale, float scale, float* __restrict__ dq,
                 int groups, int np, int c, float inv_t) {
   pdl_prologue();
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  __shared__ float sh_m[4], sh_s[4];
+  __shared__ float sh_acc[BWD ? 4 * 512 : 4];
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = groups * np;
-  if (row >= rows) return;
   const int grp = row / np, self = row - grp * np;
   constexpr int kMaxPer = 16;
+  constexpr int kJ = 8;
   const int per = c >> 5;
+  const int jq = (np + 3) / 4;
+  const int jb = warp * jq, je = (jb + jq < np) ? jb + jq : np;
   float qv[kMaxPer];
   for (int i = 0; i < per; ++i) qv[i] = q[(size_t)row * c + lane + 32 * i];
-  // positive logit
+  // positive logit (every warp: 2 KB of L1-resident loads)
   float pos = 0.f;
   for (int i = 0; i < per; ++i) pos = fmaf(qv[i], k[(size_t)row * c + lane + 32 * i], pos);
   pos = warp_sum(pos) * inv_t;
-  // pass 1: online log-sum-exp over [pos, negatives].  kJ negatives per step: their dot products and butterfly
-  // reductions are independent instruction streams (one negative at a time is a 128-long chain of dependent
-  // shuffle reductions: 150 us for a 34 MFLOP problem)
-  constexpr int kJ = 8;
-  float m = pos, s = 1.f;
-  for (int j0 = 0; j0 < np; j0 += kJ) {
+  // pass 1: online log-sum-exp over this warp's negatives (warp 0 also counts the positive)
+  float m = warp == 0 ? pos : -3.0e38f, s = warp == 0 ? 1.f : 0.f;
+  for (int j0 = jb; j0 < je; j0 += kJ) {
     float d[kJ];
 #pragma unroll
     for (int u = 0; u < kJ; ++u) {
-      const int j = j0 + u < np ? j0 + u : np - 1;
+      const int j = j0 + u < je ? j0 + u : je - 1;
       const float* kr = k + ((size_t)grp * np + j) * c;
       float a = 0.f;
       for (int i = 0; i < per; ++i) a = fmaf(qv[i], kr[lane + 32 * i], a);
@@ -463,32 +466,38 @@ patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float*
 #pragma unroll
     for (int u = 0; u < kJ; ++u) {
       const int j = j0 + u;
-      if (j >= np) break;
+      if (j >= je) break;
       const float dj = j == self ? -10.f * inv_t : d[u] * inv_t;
       const float mn = fmaxf(m, dj);
       s = s * __expf(m - mn) + __expf(dj - mn);
       m = mn;
     }
   }
-  const float lse = m + __logf(s);
+  if (lane == 0) { sh_m[warp] = m; sh_s[warp] = s; }
+  __syncthreads();
+  float mg = fmaxf(fmaxf(sh_m[0], sh_m[1]), fmaxf(sh_m[2], sh_m[3]));
+  float sg = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) sg += sh_s[w] * __expf(sh_m[w] - mg);
+  const float lse = mg + __logf(sg);
   if (!BWD) {
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
       loss_rows[row] = lse - pos;
       atomicAdd(out, scale * (lse - pos) / (float)rows);
     }
     return;
   }
-  // pass 2: dq = coef * inv_t * ( sum_{j != self} p_j k_j + (p_pos - 1) k_row )
+  // pass 2: dq = coef * inv_t * ( sum_{j != self} p_j k_j + (p_pos - 1) k_row ), each warp its own negatives
   const float coef = (gscale ? gscale[0] : 1.f) * scale / (float)rows * inv_t;
   float acc[kMaxPer];
   const float ppos = __expf(pos - lse);
-  for (int i = 0; i < per; ++i) acc[i] = (ppos - 1.f) * k[(size_t)row * c + lane + 32 * i];
+  for (int i = 0; i < per; ++i) acc[i] = warp == 0 ? (ppos - 1.f) * k[(size_t)row * c + lane + 32 * i] : 0.f;
   constexpr int kJ2 = 4;
-  for (int j0 = 0; j0 < np; j0 += kJ2) {
+  for (int j0 = jb; j0 < je; j0 += kJ2) {
     float d[kJ2];
 #pragma unroll
     for (int u = 0; u < kJ2; ++u) {
-      const int j = j0 + u < np ? j0 + u : np - 1;
+      const int j = j0 + u < je ? j0 + u : je - 1;
       const float* kr = k + ((size_t)grp * np + j) * c;
       float a = 0.f;
       for (int i = 0; i < per; ++i) a = fmaf(qv[i], kr[lane + 32 * i], a);
@@ -501,13 +510,16 @@ patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float*
 #pragma unroll
     for (int u = 0; u < kJ2; ++u) {
       const int j = j0 + u;
-      if (j >= np || j == self) continue;
+      if (j >= je || j == self) continue;
       const float pj = __expf(d[u] * inv_t - lse);
       const float* kr = k + ((size_t)grp * np + j) * c;
       for (int i = 0; i < per; ++i) acc[i] = fmaf(pj, kr[lane + 32 * i], acc[i]);
     }
   }
-  for (int i = 0; i < per; ++i) dq[(size_t)row * c + lane + 32 * i] = coef * acc[i];
+  for (int i = 0; i < per; ++i) sh_acc[warp * 512 + lane + 32 * i] = acc[i];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += 128)
+    dq[(size_t)row * c + ch] = coef * (sh_acc[ch] + sh_acc[512 + ch] + sh_acc[1024 + ch] + sh_acc[1536 + ch]);
 }
 
 static inline int grid_for(long long total, int per_block = 256) {
@@ -678,7 +690,7 @@ extern "C" int smsut_patchnce_fwd(const float* q, const float* k, float* loss_ro
                                   int32_t np, int32_t c, float inv_t, float scale, smsut_stream_t st) {
   SMSUT_CHECK(c % 32 == 0 && c <= 512, -1, "PatchNCE feature dim must be a multiple of 32 and <= 512");
   const int rows = groups * np;
-  launch_pdl(patchnce_kernel<false>, (rows + 3) / 4, 128, 0, (cudaStream_t)st, q, k, loss_rows, out, nullptr, scale, nullptr,
+  launch_pdl(patchnce_kernel<false>, rows, 128, 0, (cudaStream_t)st, q, k, loss_rows, out, nullptr, scale, nullptr,
                                                                       groups, np, c, inv_t);
   count_launch();
   return launch_status("patchnce_fwd_kernel");
@@ -687,7 +699,7 @@ extern "C" int smsut_patchnce_bwd(const float* q, const float* k, const float* g
                                   int32_t groups, int32_t np, int32_t c, float inv_t, smsut_stream_t st) {
   SMSUT_CHECK(c % 32 == 0 && c <= 512, -1, "PatchNCE feature dim must be a multiple of 32 and <= 512");
   const int rows = groups * np;
-  launch_pdl(patchnce_kernel<true>, (rows + 3) / 4, 128, 0, (cudaStream_t)st, q, k, nullptr, nullptr, gscale, scale, dq,
+  launch_pdl(patchnce_kernel<true>, rows, 128, 0, (cudaStream_t)st, q, k, nullptr, nullptr, gscale, scale, dq,
                                                                      groups, np, c, inv_t);
   count_launch();
   return launch_status("patchnce_bwd_kernel");
