@@ -564,6 +564,20 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
   int stages = (int)((200u * 1024u) / p.stage_bytes);
   if (stages > 6) stages = 6;
+  {
+    // more tiles than SMs: leave room for a second (third) CTA per SM, whose main loop then covers this one's
+    // prologue and epilogue, as long as >= 3 stages remain
+    static int per_sm_knob = -1;
+    if (per_sm_knob < 0) {
+      const char* e = getenv("SMSUT_TC_CTAS_PER_SM");
+      per_sm_knob = e ? atoi(e) : 2;
+    }
+    const long long ctas = (long long)m_tiles * (a->ncols_pad / bn);
+    if (per_sm_knob > 1 && ctas > device_sm_count()) {
+      int s2 = (int)((220u * 1024u / per_sm_knob - 2048u) / p.stage_bytes);
+      if (s2 >= 3 && s2 < stages) stages = s2;
+    }
+  }
   if (stages > ns) stages = ns;
   if (stages < 1) stages = 1;
   p.stages = stages;

@@ -121,8 +121,10 @@ class UGAN(nn.Module):
         if m is None:
             m = torch.zeros(x.size(0), self.n_modal, device=x.device)
         x = x.float()
-        # the segmentation half runs on a branch stream beside the translation half (they share only weights)
-        with ops.parallel_branch(0) as br:
+        # the segmentation half runs on a branch stream beside the translation half (they share only weights); a
+        # forward that itself runs inside a branch (the cycle pass of the trainer) uses another stream, so that the
+        # backward of the first pass's segmentation half is not queued behind the second pass's
+        with ops.parallel_branch(0 if ops.current_branch() is None else 3) as br:
             seg_out, seg_ens = self.seg_encoder.forward_nhwc(Fn.ImageInputFn.apply(x))
             seg_out = self.enc5.forward_nhwc([seg_out])
             seg = self.seg_decoder(to_nchw(seg_out), seg_ens)

@@ -134,7 +134,13 @@ def side_run(fn, keep):
 
 
 _branch_streams = {}
+_branch_stack = []        # ids of the parallel_branch blocks the calling thread is currently inside (forward only)
 branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]
+
+
+def current_branch():
+    """id of the innermost active parallel_branch block, or None on the forking (main) stream"""
+    return _branch_stack[-1] if _branch_stack else None
 
 
 class parallel_branch:
@@ -150,6 +156,7 @@ class parallel_branch:
         self.on = branch_parallel[0] and torch.cuda.is_available()
 
     def __enter__(self):
+        _branch_stack.append(self.k)
         if not self.on:
             return self
         self.main = torch.cuda.current_stream()
@@ -164,6 +171,7 @@ class parallel_branch:
         return self
 
     def __exit__(self, *a):
+        _branch_stack.pop()
         if self.on:
             self.ctx.__exit__(*a)
 

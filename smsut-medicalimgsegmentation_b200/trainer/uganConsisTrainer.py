@@ -71,6 +71,21 @@ class UGANConsisTrainer(UGANShp0Trainer):
         # generator forward shared by the D phase (detached) and the G phase
         y_fake, x_fake, feat_x_pool, sample_ids = self.net(x_real, vec_ot, sample_ids=sample_ids)
 
+        # ---------------- the cycle pass of the G phase (L157-168) needs only x_fake and G's weights: it runs on a
+        # branch stream beside the whole D phase (forward, gradient penalty, backward, Adam step)
+        if isinstance(lambda_semi, torch.Tensor):
+            lambda_semi = lambda_semi.reshape(())      # device scalar: one captured graph serves every epoch
+        with ops.parallel_branch(4) as b_cyc:
+            g_loss_seg = self.loss(y_fake[:bs], y_real)
+            y_rec, x_rec, feat_f_pool, _ = self.net(x_fake, vec_to, sample_ids=sample_ids)
+            g_loss_rec = Fn.L1MeanFn.apply(x_rec.contiguous(), x_real)
+            if use_semi:
+                g_loss_semi = self.consistency_loss(y_rec, y_fake)
+            else:
+                g_loss_semi = torch.zeros((), device=x_real.device)
+            g_loss_nce = self.nce_loss(feat_x_pool, feat_f_pool)
+            g_partial = lambda_rec * g_loss_rec + lambda_seg * g_loss_seg + lambda_semi * g_loss_semi + 1.0 * g_loss_nce
+
         # ---------------- D phase (L129-146): the three discriminator passes are independent chains of small
         # kernels -> real on the current stream, fake and interpolated on branch streams (ops.parallel_branch)
         x_fake_d = x_fake.detach()
@@ -98,33 +113,16 @@ class UGANConsisTrainer(UGANShp0Trainer):
         self.d_optimizer.step()
 
         # ---------------- G phase (L151-180); D's parameters are constants here
-        with ops.parallel_branch(1) as b_adv:       # D(G(x)) beside the cycle forward of G
-            for p in self.d_optimizer.params:
-                p.requires_grad_(False)
-            out_src, out_cls = self.D(x_fake)
-            for p in self.d_optimizer.params:
-                p.requires_grad_(True)
-            g_loss_fake = Fn.MeanFn.apply(out_src, -1.0)
-            g_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_trg)
-        g_loss_seg = self.loss(y_fake[:bs], y_real)
+        for p in self.d_optimizer.params:
+            p.requires_grad_(False)
+        out_src, out_cls = self.D(x_fake)
+        for p in self.d_optimizer.params:
+            p.requires_grad_(True)
+        g_loss_fake = Fn.MeanFn.apply(out_src, -1.0)
+        g_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_trg)
+        b_cyc.join(g_partial, g_loss_seg, g_loss_rec, g_loss_semi, g_loss_nce)
 
-        y_rec, x_rec, feat_f_pool, _ = self.net(x_fake, vec_to, sample_ids=sample_ids)
-        g_loss_rec = Fn.L1MeanFn.apply(x_rec.contiguous(), x_real)
-
-        if use_semi:
-            g_loss_semi = self.consistency_loss(y_rec, y_fake)
-        else:
-            g_loss_semi = torch.zeros((), device=x_real.device)
-        if isinstance(lambda_semi, torch.Tensor):
-            lambda_semi = lambda_semi.reshape(())      # device scalar: one captured graph serves every epoch
-
-        g_loss_nce = self.nce_loss(feat_x_pool, feat_f_pool)
-        b_adv.join(g_loss_fake, g_loss_cls)
-
-        g_loss = g_loss_fake + lambda_rec * g_loss_rec + lambda_cls * g_loss_cls + \
-            lambda_seg * g_loss_seg + \
-            lambda_semi * g_loss_semi + \
-            1.0 * g_loss_nce
+        g_loss = g_loss_fake + lambda_cls * g_loss_cls + g_partial
         self.optimizer.zero_grad()
         with Fn.accumulate_param_grads():
             g_loss.backward()
