@@ -56,6 +56,7 @@ class accumulate_param_grads:
     def __exit__(self, *a):
         _accumulate[0] = self.prev
         ops.side_streams_enable(False)
+        ops.branch_join_all()
         ops.side_join()
         ops.WgradScratch.flush_all()       # after the block every .grad is complete (tap-major scratch folded in)
 

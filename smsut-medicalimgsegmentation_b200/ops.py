@@ -187,6 +187,18 @@ class parallel_branch:
                 t.record_stream(cur)
 
 
+def branch_join_all():
+    """the current stream waits for every branch stream of its device (end of a backward pass: autograd only orders
+    streams where a gradient tensor crosses them, but parameter gradients are also written in place -- InstanceNorm
+    gamma / beta atomics, the wgrad scratch -- by kernels whose Functions hand autograd `None`)"""
+    if not torch.cuda.is_available():
+        return
+    cur = torch.cuda.current_stream()
+    for (dev, _k), st in _branch_streams.items():
+        if dev == cur.device_index and st != cur:
+            cur.wait_stream(st)
+
+
 def side_join():
     """the current stream waits for every side kernel issued since the last join"""
     if _Side.used:
@@ -311,6 +323,10 @@ class WgradScratch:
         arr = (UnpackEntry * len(entries))(*entries)
         self.table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self.n = len(entries)
+        # the zero fill above ran on whatever stream the first weight-gradient call came from; wgrad kernels of other
+        # branch streams must not overtake it (first iteration only, never during capture: the warm-up builds it)
+        if dev.type == "cuda" and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.synchronize(dev)
 
     def view_for(self, weight, out):
         """the scratch view of `weight` if `out` is its flat-gradient view, else None"""

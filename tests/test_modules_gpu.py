@@ -108,7 +108,7 @@ def test_unet_parity(pkg, size, n):
                                 loss_ref=lref.item(), grads_vs_fp32_oracle=g, grads_vs_bf16_emulation=ge,
                                 grad_cosine_vs_fp32=cos_fp32, grad_cosine_vs_bf16_emulation=cos_emu,
                                 argmax_agree_on_margin=agree, margin_excluded_frac=1 - mask.float().mean().item()))
-    assert r_emu < 1.5e-2, r_emu
+    assert r_emu < 1.5e-2, ("logits vs bf16 emulation", r_emu)
     assert r_fwd < 3e-2
     assert abs(loss.item() - lref.item()) < 1e-2 * abs(lref.item())
     assert agree > 0.995
@@ -233,7 +233,7 @@ def test_unet_free_running_loss_trajectory(pkg):
         traj.append((loss, ref.item()))
         worst = max(worst, abs(loss - ref.item()) / abs(ref.item()))
     report("unet_trajectory", dict(worst_rel=worst, trajectory=traj))
-    assert worst < 1.5e-2, worst
+    assert worst < 1.5e-2, ("worst loss deviation over the trajectory", worst, traj)
     assert traj[-1][0] < 0.7 * traj[0][0], "the loss did not go down"
 
 
