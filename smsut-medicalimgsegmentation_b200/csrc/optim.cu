@@ -111,44 +111,43 @@ __global__ void pack_weights_kernel(const smsut_pack_entry* __restrict__ table) 
   const int taps = e.kh * e.kw;
   __nv_bfloat16* f = reinterpret_cast<__nv_bfloat16*>(e.fprop);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(e.dgrad);
-  const long long tid = (long long)blockIdx.y * blockDim.x + threadIdx.x;
-  const long long nth = (long long)gridDim.y * blockDim.x;
+  // every weight has < 2^31 elements: 32-bit index arithmetic (the 64-bit divisions of the first version made this
+  // launch 29 us for 25 MB of traffic); blockIdx.y strides over output rows, threads over the row
   if (!e.transposed) {
     // fprop: [cout_pad][taps][cin_pad]
-    const long long nf = (long long)e.cout_pad * taps * e.cin_pad;
-    for (long long i = tid; i < nf; i += nth) {
-      const int ci = (int)(i % e.cin_pad);
-      const int t = (int)((i / e.cin_pad) % taps);
-      const int co = (int)(i / ((long long)e.cin_pad * taps));
-      const float v = (co < e.cout && ci < e.cin) ? e.w[((size_t)co * e.cin + ci) * taps + t] : 0.f;
-      f[i] = f2bf(v);
+    const int rowf = taps * e.cin_pad;
+    for (int co = blockIdx.y; co < e.cout_pad; co += gridDim.y) {
+      const float* wr = e.w + (size_t)co * e.cin * taps;
+      for (int i = threadIdx.x; i < rowf; i += blockDim.x) {
+        const int t = i / e.cin_pad, ci = i - t * e.cin_pad;
+        f[(size_t)co * rowf + i] = f2bf((co < e.cout && ci < e.cin) ? wr[ci * taps + t] : 0.f);
+      }
     }
     if (d != nullptr) {
       // dgrad: [cin_pad][taps (flipped)][cout_pad]
-      const long long nd = (long long)e.cin_pad * taps * e.cout_pad;
-      for (long long i = tid; i < nd; i += nth) {
-        const int co = (int)(i % e.cout_pad);
-        const int t = (int)((i / e.cout_pad) % taps);
-        const int ci = (int)(i / ((long long)e.cout_pad * taps));
-        const float v = (co < e.cout && ci < e.cin) ? e.w[((size_t)co * e.cin + ci) * taps + (taps - 1 - t)] : 0.f;
-        d[i] = f2bf(v);
+      const int rowd = taps * e.cout_pad;
+      for (int ci = blockIdx.y; ci < e.cin_pad; ci += gridDim.y) {
+        for (int i = threadIdx.x; i < rowd; i += blockDim.x) {
+          const int t = i / e.cout_pad, co = i - t * e.cout_pad;
+          d[(size_t)ci * rowd + i] =
+              f2bf((co < e.cout && ci < e.cin) ? e.w[((size_t)co * e.cin + ci) * taps + (taps - 1 - t)] : 0.f);
+        }
       }
     }
   } else {
     // ConvTranspose2d weight (cin, cout, kh, kw): fprop rows (t, co) x cin ; dgrad rows ci x (t, co)
-    const long long n = (long long)taps * e.cout * e.cin;
-    for (long long i = tid; i < n; i += nth) {
-      const int ci = (int)(i % e.cin);
-      const int co = (int)((i / e.cin) % e.cout);
-      const int t = (int)(i / ((long long)e.cin * e.cout));
-      f[i] = f2bf(e.w[((size_t)ci * e.cout + co) * taps + t]);
+    const int rows = taps * e.cout;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+      const int t = r / e.cout, co = r - t * e.cout;
+      for (int ci = threadIdx.x; ci < e.cin; ci += blockDim.x)
+        f[(size_t)r * e.cin + ci] = f2bf(e.w[((size_t)ci * e.cout + co) * taps + t]);
     }
     if (d != nullptr) {
-      for (long long i = tid; i < n; i += nth) {
-        const int co = (int)(i % e.cout);
-        const int t = (int)((i / e.cout) % taps);
-        const int ci = (int)(i / ((long long)e.cout * taps));
-        d[i] = f2bf(e.w[((size_t)ci * e.cout + co) * taps + t]);
+      for (int ci = blockIdx.y; ci < e.cin; ci += gridDim.y) {
+        for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+          const int t = i / e.cout, co = i - t * e.cout;
+          d[(size_t)ci * rows + i] = f2bf(e.w[((size_t)ci * e.cout + co) * taps + t]);
+        }
       }
     }
   }
@@ -203,12 +202,20 @@ extern "C" int smsut_poly_lr_tick(float* iter_state, float* lr_out, float base_l
 __global__ void unpack_wgrads_kernel(const smsut_unpack_entry* __restrict__ table) {
   pdl_prologue();
   const smsut_unpack_entry e = table[blockIdx.x];
-  const long long mc = (long long)e.rows * e.cols;
-  const long long tid = (long long)blockIdx.y * blockDim.x + threadIdx.x;
-  const long long nth = (long long)gridDim.y * blockDim.x;
-  for (long long i = tid; i < mc; i += nth) {
-    float* dst = e.grad + i * e.taps;
-    for (int t = 0; t < e.taps; ++t) dst[t] += e.scratch[(size_t)t * mc + i];
+  const int mc = e.rows * e.cols, taps = e.taps;
+  const int nth = gridDim.y * blockDim.x;
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < mc; i += nth) {
+    float* dst = e.grad + (size_t)i * taps;
+    const float* src = e.scratch + i;
+    if (taps == 9) {
+      float v[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) v[t] = src[(size_t)t * mc];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) dst[t] += v[t];
+    } else {
+      for (int t = 0; t < taps; ++t) dst[t] += src[(size_t)t * mc];
+    }
   }
 }
 

@@ -155,15 +155,26 @@ class UGANConsisTrainer(UGANShp0Trainer):
     def prepare_batch(self, x_real1, y_real, modal_org1, x_real2, modal_org2, mj):
         """Host-side assembly of L110-127: concatenate the labelled and unlabelled halves, build the modality
         difference vectors and move everything to the device."""
-        x_real = torch.cat([x_real1, x_real2], dim=0)
+        dev = self.device
         modal_org = torch.cat([modal_org1, modal_org2], dim=0)
         modal_trg = torch.zeros_like(modal_org).fill_(mj)
         vec_org = self.label2onehot(modal_org, cfg.n_modal)
         vec_trg = self.label2onehot(modal_trg, cfg.n_modal)
-        dev = self.device
-        return (x_real.to(dev, non_blocking=True), y_real.to(dev, non_blocking=True),
-                modal_org.to(dev, non_blocking=True), modal_trg.to(dev, non_blocking=True),
-                (vec_trg - vec_org).to(dev, non_blocking=True), (vec_org - vec_trg).to(dev, non_blocking=True))
+        if torch.device(dev).type != 'cuda':
+            x_real = torch.cat([x_real1, x_real2], dim=0)
+            return (x_real.to(dev), y_real.to(dev), modal_org.to(dev), modal_trg.to(dev), (vec_trg - vec_org).to(dev),
+                    (vec_org - vec_trg).to(dev))
+        # asynchronous copies straight from the (pinned) loader tensors: no host-side concatenation of the slices, and
+        # the few-byte modality tensors go through the caching pinned allocator so that nothing blocks the host
+        b1, b2 = x_real1.shape[0], x_real2.shape[0]
+        x_real = torch.empty((b1 + b2, *x_real1.shape[1:]), dtype=x_real1.dtype, device=dev)
+        x_real[:b1].copy_(x_real1, non_blocking=True)
+        x_real[b1:].copy_(x_real2, non_blocking=True)
+
+        def small(t):
+            return t.pin_memory().to(dev, non_blocking=True)
+        return (x_real, y_real.to(dev, non_blocking=True), small(modal_org), small(modal_trg),
+                small(vec_trg - vec_org), small(vec_org - vec_trg))
 
     def train_epoch(self, lb_loader, ul_loader, meter, num_iter=None):
         self.net.train()
