@@ -208,6 +208,11 @@ int smsut_softmax_mse_bwd(const float* zs, const float* zt, const float* gscale,
                           smsut_stream_t stream);
 /* argmax over channels -> int64 (n,h,w)  (trainer/uganConsisTrainer.py:52, trainer/baseTrainer.py:230) */
 int smsut_argmax_c(const float* logits, int64_t* out, int64_t npix, int32_t c, smsut_stream_t stream);
+/* validation metric path (trainer/baseTrainer.py:207-252, trainer/uganShp0Trainer.py:250-287, misc/utils.py:180-203):
+ * conf[label * c + argmax(logits)] += 1 over npix pixels (logits fp32 (npix, c) NHWC-flattened, labels int64; labels
+ * outside [0, c) are ignored; ties go to the first maximum like torch.argmax); conf: c*c uint64 counters, accumulated */
+int smsut_confusion_counts(const float* logits, const int64_t* labels, uint64_t* conf, int64_t npix, int32_t c,
+                           smsut_stream_t stream);
 /* out[0] += scale * sum|a-b| ; dA = gscale*scale*sign(a-b) */
 int smsut_l1_fwd(const float* a, const float* b, float* out, int64_t count, float scale, smsut_stream_t stream);
 int smsut_l1_bwd(const float* a, const float* b, const float* gscale, float scale, float* da, int64_t count,

@@ -97,6 +97,7 @@ _PROTOS = {
     "smsut_softmax_mse_fwd": [P, P, P, c_int64, c_int, P],
     "smsut_softmax_mse_bwd": [P, P, P, P, c_int64, c_int, P],
     "smsut_argmax_c": [P, P, c_int64, c_int, P],
+    "smsut_confusion_counts": [P, P, P, c_int64, c_int, P],
     "smsut_l1_fwd": [P, P, P, c_int64, c_float, P],
     "smsut_l1_bwd": [P, P, P, c_float, P, c_int64, P],
     "smsut_sum_f32": [P, P, c_int64, c_float, P],

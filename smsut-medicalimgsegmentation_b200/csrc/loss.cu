@@ -230,6 +230,30 @@ __global__ void argmax_kernel(const float* __restrict__ logits, long long* __res
   }
 }
 
+// Validation metric path (trainer/baseTrainer.py:207-252, misc/utils.py:180-203): confusion counts of
+// argmax(logits) against the labels, conf[label][prediction] += 1, accumulated per block in shared memory.
+// Dice_k = 2 conf[k][k] / (row_k + col_k): identical integers to the reference's per-organ numpy / medpy counts.
+template <int C>
+__global__ void __launch_bounds__(256) confusion_kernel(const float* __restrict__ logits,
+                                                        const long long* __restrict__ labels,
+                                                        unsigned long long* __restrict__ conf, long long npix) {
+  pdl_prologue();
+  __shared__ unsigned int sh[C * C];
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+    float z[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) z[c] = logits[i * C + c];
+    const int pred = argmax_first<C>(z);
+    const long long y = labels[i];
+    if (y >= 0 && y < C) atomicAdd(&sh[(int)y * C + pred], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (sh[i]) atomicAdd(conf + i, (unsigned long long)sh[i]);
+}
+
 __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                      float* __restrict__ out, long long count, float scale) {
   pdl_prologue();
@@ -594,6 +618,15 @@ extern "C" int smsut_argmax_c(const float* logits, int64_t* out, int64_t npix, i
   DISPATCH_C(c, (launch_pdl(argmax_kernel<C_>, grid, 256, 0, (cudaStream_t)st, logits, (long long*)out, npix)));
   count_launch();
   return launch_status("argmax_kernel");
+}
+extern "C" int smsut_confusion_counts(const float* logits, const int64_t* labels, uint64_t* conf, int64_t npix, int32_t c,
+                                      smsut_stream_t st) {
+  SMSUT_CHECK(logits && labels && conf && npix > 0, -1, "bad confusion args");
+  const int grid = grid_for(npix, 2048);
+  DISPATCH_C(c, (launch_pdl(confusion_kernel<C_>, grid, 256, 0, (cudaStream_t)st, logits, (const long long*)labels,
+                            (unsigned long long*)conf, npix)));
+  count_launch();
+  return launch_status("confusion_kernel");
 }
 extern "C" int smsut_l1_fwd(const float* a, const float* b, float* out, int64_t count, float scale, smsut_stream_t st) {
   launch_pdl(l1_fwd_kernel, grid_for(count, 1024), 256, 0, (cudaStream_t)st, a, b, out, count, scale);

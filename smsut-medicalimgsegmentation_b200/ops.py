@@ -134,6 +134,7 @@ def side_run(fn, keep):
 
 
 _branch_streams = {}
+_branch_used = []         # branch streams forked since the last branch_join_all()
 _branch_stack = []        # ids of the parallel_branch blocks the calling thread is currently inside (forward only)
 branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]
 
@@ -165,6 +166,8 @@ class parallel_branch:
         if st is None:
             st = _branch_streams[key] = torch.cuda.Stream(device=self.main.device)
         self.stream = st
+        if st not in _branch_used:
+            _branch_used.append(st)
         st.wait_stream(self.main)
         self.ctx = torch.cuda.stream(st)
         self.ctx.__enter__()
@@ -191,12 +194,13 @@ def branch_join_all():
     """the current stream waits for every branch stream of its device (end of a backward pass: autograd only orders
     streams where a gradient tensor crosses them, but parameter gradients are also written in place -- InstanceNorm
     gamma / beta atomics, the wgrad scratch -- by kernels whose Functions hand autograd `None`)"""
-    if not torch.cuda.is_available():
+    if not _branch_used:
         return
     cur = torch.cuda.current_stream()
-    for (dev, _k), st in _branch_streams.items():
-        if dev == cur.device_index and st != cur:
+    for st in _branch_used:     # only the streams forked since the last join (others are not part of a capture)
+        if st.device_index == cur.device_index and st != cur:
             cur.wait_stream(st)
+    del _branch_used[:]
 
 
 def side_join():
@@ -756,6 +760,14 @@ def argmax_c(logits):
     out = torch.empty(npix, dtype=torch.int64, device=logits.device)
     call("smsut_argmax_c", _p(_chk(logits, F32, "argmax logits")), _p(out), npix, c, _stream())
     return out
+
+
+def confusion_counts(logits, labels, conf):
+    """conf[label, argmax(logits)] += 1; logits fp32 (npix, c), labels int64 (npix,), conf int64 (c, c) accumulated"""
+    npix, c = _chk(logits, F32, "confusion logits").shape
+    assert labels.dtype == torch.int64 and labels.numel() == npix and conf.dtype == torch.int64 and conf.numel() == c * c
+    call("smsut_confusion_counts", _p(logits), _p(labels.contiguous()), _p(conf), npix, c, _stream())
+    return conf
 
 
 def l1_fwd(a, b, out, scale):

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from .. import config as cfg
+from .. import ops
 from ..data_loader import syntheticLoader as synlod
 from ..misc.loss import DiceAndCrossEntropyLoss
 
@@ -93,8 +94,7 @@ class BaseTrainer(object):
         like baseTrainer.py:214-219); the confusion counts stay on the device."""
         self.net.eval()
         n_cls = cfg.n_label + 1
-        inter = torch.zeros(n_cls, device=self.device)
-        denom = torch.zeros(n_cls, device=self.device)
+        conf = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=self.device)     # conf[label, prediction]
         with torch.no_grad():
             for img, msk, mdl, inm in loader:
                 b, c, h, w = img.shape
@@ -103,11 +103,12 @@ class BaseTrainer(object):
                 img = img.to(self.device, non_blocking=True)
                 msk = msk.to(self.device, non_blocking=True)
                 out = self.segment(img)[:b]
-                pred = torch.argmax(out, dim=1)
-                for k in range(1, n_cls):
-                    p, g = pred == k, msk == k
-                    inter[k] += (p & g).sum()
-                    denom[k] += p.sum() + g.sum()
+                # fp32 logits as (pixels, classes): zero-copy for the channels-last tensors the networks return
+                logits = out.permute(0, 2, 3, 1).reshape(-1, n_cls)
+                ops.confusion_counts(logits if logits.is_contiguous() else logits.contiguous(), msk.reshape(-1), conf)
+        self.confusion = conf
+        inter = conf.diagonal().double()
+        denom = (conf.sum(0) + conf.sum(1)).double()
         dice = (2 * inter[1:] / denom[1:].clamp_min(1)).mean().item()
         self.net.train()
         return dice

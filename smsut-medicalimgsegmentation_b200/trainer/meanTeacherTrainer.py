@@ -63,9 +63,11 @@ class MeanTeacherTrainer(BaseTrainer):
         bs = msk.shape[0]
         ops.arena_begin(img.device)
         self.lr_sched.tick()
+        with ops.parallel_branch(5) as b_ema:        # the teacher's forward runs beside the student's
+            with torch.no_grad():
+                ema_outputs = self.ema(img[bs:] + noise)
         out = self.net(img)
-        with torch.no_grad():
-            ema_outputs = self.ema(img[bs:] + noise)
+        b_ema.join(ema_outputs)
         sample_loss = self.loss(out[:bs], msk)
         if self.iter < self.semi_from_iter:
             semi_loss = torch.zeros((), dtype=torch.float32, device=img.device)

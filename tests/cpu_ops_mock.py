@@ -345,6 +345,14 @@ def argmax_c(logits):
     return logits.argmax(1)
 
 
+def confusion_counts(logits, labels, conf):
+    c = logits.shape[1]
+    pred = logits.argmax(1)
+    ok = (labels >= 0) & (labels < c)
+    conf.view(-1).index_add_(0, (labels[ok] * c + pred[ok]), torch.ones_like(pred[ok]))
+    return conf
+
+
 def l1_fwd(a, b, out, scale):
     out += scale * (a - b).abs().sum()
 

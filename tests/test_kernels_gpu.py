@@ -521,3 +521,22 @@ def test_conv_fused_instance_norm_statistics(ops, cins, cout, h, n):
     y, st = ops.conv_fprop([nhwc(x) for x in xs], pw, want_stats=True)
     yf = y.float()
     assert rel(st[:, 0], yf.sum((1, 2))) < 1e-4 and rel(st[:, 1], (yf * yf).sum((1, 2))) < 1e-4
+
+
+def test_confusion_counts_bit_exact(ops):
+    """validation metric path: conf[label, argmax] counts equal torch's, ties go to the first maximum, labels outside
+    [0, C) are ignored, repeated calls accumulate"""
+    torch.manual_seed(21)
+    npix, c = 3 * 97 * 101, 5
+    logits = torch.randn(npix, c, device=DEV)
+    logits[::7] = logits[::7].round()            # plenty of exact ties
+    logits[::11, 1] = logits[::11, 3]
+    labels = torch.randint(-1, c + 1, (npix,), device=DEV)
+    conf = torch.zeros(c, c, dtype=torch.int64, device=DEV)
+    ops.confusion_counts(logits, labels, conf)
+    ops.confusion_counts(logits, labels, conf)
+    pred = logits.argmax(1)
+    ok = (labels >= 0) & (labels < c)
+    ref = torch.zeros(c * c, dtype=torch.int64, device=DEV)
+    ref.index_add_(0, labels[ok] * c + pred[ok], torch.ones_like(pred[ok]))
+    assert torch.equal(conf.view(-1), 2 * ref)
