@@ -144,6 +144,26 @@ __global__ void __launch_bounds__(kNT, 4) in_stats_kernel(const void* __restrict
   block_reduce_add<2>(acc, sh, s, stats + (size_t)n * 2 * c, c, c);
 }
 
+struct Strip32 {
+  int cg, g, lane0, nl;     // channel groups of 8, this thread's group, its first pixel in the strip, pixel stride
+  int p0, count;            // first pixel of the block's strip, number of pixels this THREAD visits
+};
+
+__device__ __forceinline__ Strip32 make_strip32(int c, int hw, int splits) {
+  Strip32 s;
+  s.cg = c >> 3;
+  s.g = threadIdx.x % s.cg;
+  s.lane0 = threadIdx.x / s.cg;
+  s.nl = kNT / s.cg;
+  const int per = (hw + splits - 1) / splits;
+  s.p0 = blockIdx.y * per;
+  int p1 = s.p0 + per;
+  if (p1 > hw) p1 = hw;
+  const int span = p1 - s.p0 - s.lane0;
+  s.count = span > 0 ? (span + s.nl - 1) / s.nl : 0;
+  return s;
+}
+
 template <bool HAS_B, bool HAS_RES>
 __global__ void __launch_bounds__(kNT, 4)
 in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
@@ -177,46 +197,57 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
       }
     }
   }
-  const size_t base = (size_t)n * hw * c + ch0;
+  // 32-bit strip walk (see Strip32): full steps of U pixels without bounds checks, then a tail
+  const Strip32 t = make_strip32(c, hw, splits);
+  const uint4* pa = reinterpret_cast<const uint4*>(xa);
+  const uint4* pb = reinterpret_cast<const uint4*>(xb);
+  const uint4* pr = reinterpret_cast<const uint4*>(res);
+  uint4* po = reinterpret_cast<uint4*>(out);
+  size_t idx = ((size_t)n * hw + t.p0 + t.lane0) * t.cg + t.g;
+  const int step = t.nl * t.cg;
   constexpr int U = (HAS_B || HAS_RES) ? 2 : kUS;
-  for (long long p = s.p0 + s.lane0; p < s.p1; p += (long long)U * s.nlanes) {
+  auto body = [&](const uint4& qa, const uint4& qb, const uint4& qr, size_t at) {
+    float v[8], o[8];
+    unpack8(qa, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sa[j], ta[j]);
+    if (HAS_B) {
+      unpack8(qb, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sb[j], o[j]);
+    }
+    if (HAS_RES) {
+      unpack8(qr, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += v[j];
+    }
+    if (act == SMSUT_ACT_LRELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = lrelu(o[j], slope);
+    } else if (act == SMSUT_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    po[at] = pack8(o);
+  };
+  int it = 0;
+  for (; it + U <= t.count; it += U, idx += (size_t)U * step) {
     uint4 qa[U], qb[U], qr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long pp = p + (long long)u * s.nlanes;
-      const bool ok = pp < s.p1;
-      const size_t off = base + (size_t)pp * c;
-      qa[u] = ok ? ldg16(xa, off) : zero4();
-      if (HAS_B) qb[u] = ok ? ldg16(xb, off) : zero4();
-      if (HAS_RES) qr[u] = ok ? ldg16(res, off) : zero4();
+      qa[u] = pa[idx + (size_t)u * step];
+      if (HAS_B) qb[u] = pb[idx + (size_t)u * step];
+      if (HAS_RES) qr[u] = pr[idx + (size_t)u * step];
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long pp = p + (long long)u * s.nlanes;
-      if (pp >= s.p1) break;
-      float v[8], o[8];
-      unpack8(qa[u], v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sa[j], ta[j]);
-      if (HAS_B) {
-        unpack8(qb[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(v[j], sb[j], o[j]);
-      }
-      if (HAS_RES) {
-        unpack8(qr[u], v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += v[j];
-      }
-      if (act == SMSUT_ACT_LRELU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = lrelu(o[j], slope);
-      } else if (act == SMSUT_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-      }
-      stg16(out, base + (size_t)pp * c, pack8(o));
-    }
+    for (int u = 0; u < U; ++u) body(qa[u], qb[u], qr[u], idx + (size_t)u * step);
+  }
+  for (; it < t.count; ++it, idx += step) {
+    uint4 qb = zero4(), qr = zero4();
+    const uint4 qa = pa[idx];
+    if (HAS_B) qb = pb[idx];
+    if (HAS_RES) qr = pr[idx];
+    body(qa, qb, qr, idx);
   }
 }
 
@@ -231,26 +262,6 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
 // per-load bounds predicates, plus a 12 k-instruction unrolled block reduction.  This version walks the strip with
 // 32-bit counters and pointer increments, keeps the bounds check out of the main loop (full steps + a tail), tests
 // the activation sign on the packed bf16 bits, and reduces a block through shuffles + one shared-memory pass.
-struct Strip32 {
-  int cg, g, lane0, nl;     // channel groups of 8, this thread's group, its first pixel in the strip, pixel stride
-  int p0, count;            // first pixel of the block's strip, number of pixels this THREAD visits
-};
-
-__device__ __forceinline__ Strip32 make_strip32(int c, int hw, int splits) {
-  Strip32 s;
-  s.cg = c >> 3;
-  s.g = threadIdx.x % s.cg;
-  s.lane0 = threadIdx.x / s.cg;
-  s.nl = kNT / s.cg;
-  const int per = (hw + splits - 1) / splits;
-  s.p0 = blockIdx.y * per;
-  int p1 = s.p0 + per;
-  if (p1 > hw) p1 = hw;
-  const int span = p1 - s.p0 - s.lane0;
-  s.count = span > 0 ? (span + s.nl - 1) / s.nl : 0;
-  return s;
-}
-
 // g = dout * act'(out) for 8 packed bf16: the sign test works on the raw bits (out > 0  <=>  bits in (0, 0x8000))
 template <bool HAS_ACT>
 __device__ __forceinline__ void load_g(const uint4& qd, const uint4& qo, float neg, float* g) {
