@@ -45,8 +45,11 @@ class accumulate_param_grads:
     parameters' existing `.grad` tensors (the flat gradient buffer of optim.py) and autograd is handed `None`:
     no zero-fill + add pair per parameter.  Outside it the Functions return fresh gradient tensors as usual."""
 
-    def __init__(self, side_streams=True):
+    def __init__(self, side_streams=True, join=True):
+        """join=False leaves the side / branch streams of this backward running (no wait, no scratch flush): a later
+        `accumulate_param_grads()` block -- or the optimizer step -- completes the gradients"""
         self.side = side_streams
+        self.join = join
 
     def __enter__(self):
         self.prev = _accumulate[0]
@@ -56,6 +59,8 @@ class accumulate_param_grads:
     def __exit__(self, *a):
         _accumulate[0] = self.prev
         ops.side_streams_enable(False)
+        if not self.join:
+            return
         ops.branch_join_all()
         ops.side_join()
         ops.WgradScratch.flush_all()       # after the block every .grad is complete (tap-major scratch folded in)

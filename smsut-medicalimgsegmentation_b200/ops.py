@@ -63,6 +63,7 @@ def arena_begin(device, nbytes=48 << 20):
     _Arena.buf.zero_()
     _Arena.off = 0
     _Arena.active = True
+    del _branch_used[:]       # a new iteration: branch streams are (re)forked from here on
 
 
 def arena_end():
@@ -134,7 +135,7 @@ def side_run(fn, keep):
 
 
 _branch_streams = {}
-_branch_used = []         # branch streams forked since the last branch_join_all()
+_branch_used = []         # branch streams forked since the iteration began (arena_begin)
 _branch_stack = []        # ids of the parallel_branch blocks the calling thread is currently inside (forward only)
 branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]
 
@@ -197,10 +198,9 @@ def branch_join_all():
     if not _branch_used:
         return
     cur = torch.cuda.current_stream()
-    for st in _branch_used:     # only the streams forked since the last join (others are not part of a capture)
+    for st in _branch_used:     # only the streams forked in this iteration (others are not part of a capture)
         if st.device_index == cur.device_index and st != cur:
             cur.wait_stream(st)
-    del _branch_used[:]
 
 
 def side_join():
