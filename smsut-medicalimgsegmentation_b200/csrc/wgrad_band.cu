@@ -260,12 +260,17 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   p.taps = a->ksize * a->ksize;
   SMSUT_CHECK(a->dw != nullptr, -1, "null dw");
 
-  // row segments: ONE balanced wave of co-resident CTAs (up to 3 per SM), at least 8 rows each (every segment
+  // row segments: ONE balanced wave of co-resident CTAs (up to 2 per SM), at least 8 rows each (every segment
   // re-reads 2r halo rows and pays a full-accumulator atomic epilogue)
   const int sms = device_sm_count();
   const int base = a->n * p.wtiles * p.xchunks * p.dchunks;
   int per_sm = (int)((227u * 1024u) / (smem + 1024));
-  if (per_sm > 3) per_sm = 3;
+  static int per_sm_knob = -1;
+  if (per_sm_knob < 0) {
+    const char* e = getenv("SMSUT_WGRAD_BAND_PER_SM");
+    per_sm_knob = e && atoi(e) > 0 ? atoi(e) : 2;   // side-stream kernel: SM-time over latency (3 -> 12.36, 2 -> 12.14 ms/step)
+  }
+  if (per_sm > per_sm_knob) per_sm = per_sm_knob;
   if (per_sm < 1) per_sm = 1;
   int segs = (per_sm * sms) / base;
   if (segs < 1) segs = 1;

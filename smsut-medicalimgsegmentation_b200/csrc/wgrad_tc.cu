@@ -14,6 +14,7 @@
 // Reference semantics: aten::convolution_backward(weight) behind every nn.Conv2d / nn.ConvTranspose2d of
 // network/blocks.py:10-16,41.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/smsut_b200.h"
@@ -321,7 +322,14 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   p.stages = stages;
 
   // split-K over pixel tiles
-  int target = 2 * device_sm_count();
+  // CTAs over the whole launch.  These kernels run on side streams beside the dgrad chain, so SM-time matters more than
+  // latency: every CTA pays a full-accumulator reduction epilogue, fewer and longer CTAs leave the SMs to the others.
+  static int target_knob = -1;
+  if (target_knob < 0) {
+    const char* e = getenv("SMSUT_WGRAD_TARGET");
+    target_knob = e && atoi(e) > 0 ? atoi(e) : (device_sm_count() + 2) / 3;   // measured: 296 -> 13.0 ms/step, 48 -> 12.3
+  }
+  int target = target_knob;
   int splits = target / (ngroups * mblocks);
   if (splits < 1) splits = 1;
   if (splits > p.tiles_total) splits = p.tiles_total;

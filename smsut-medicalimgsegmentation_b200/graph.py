@@ -17,7 +17,10 @@ class GraphedStep:
     def __init__(self, step_fn, example_inputs, warmup=3, refresh=None):
         self.step_fn = step_fn
         self.static_in = [t.clone() if isinstance(t, torch.Tensor) else t for t in example_inputs]
-        s = torch.cuda.Stream()
+        # the capture stream carries the critical path: same (high) priority as the branch streams, above the wgrad
+        # side streams
+        from . import ops
+        s = torch.cuda.Stream(priority=ops._BRANCH_PRIORITY)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -28,7 +31,7 @@ class GraphedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=s):
             self.static_out = step_fn(*self.static_in)
         self.launches_per_replay = _lib.launch_count() - before
 

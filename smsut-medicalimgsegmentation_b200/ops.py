@@ -122,7 +122,8 @@ def side_run(fn, keep):
     main = torch.cuda.current_stream()
     pool = _Side.streams.get(main.device_index)
     if pool is None:
-        pool = [torch.cuda.Stream(device=main.device) for _ in range(_Side.n_streams)]
+        # lowest priority: the dgrad / norm chain on the forking streams is the critical path
+        pool = [torch.cuda.Stream(device=main.device, priority=0) for _ in range(_Side.n_streams)]
         _Side.streams[main.device_index] = pool
     s = pool[_Side.nxt % len(pool)]
     _Side.nxt += 1
@@ -135,6 +136,7 @@ def side_run(fn, keep):
 
 
 _branch_streams = {}
+_BRANCH_PRIORITY = int(os.environ.get("SMSUT_BRANCH_PRIORITY", "-1"))   # above the wgrad side streams (0 = lowest)
 _branch_used = []         # branch streams forked since the iteration began (arena_begin)
 _branch_stack = []        # ids of the parallel_branch blocks the calling thread is currently inside (forward only)
 branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]
@@ -165,7 +167,7 @@ class parallel_branch:
         key = (self.main.device_index, self.k)
         st = _branch_streams.get(key)
         if st is None:
-            st = _branch_streams[key] = torch.cuda.Stream(device=self.main.device)
+            st = _branch_streams[key] = torch.cuda.Stream(device=self.main.device, priority=_BRANCH_PRIORITY)
         self.stream = st
         if st not in _branch_used:
             _branch_used.append(st)
