@@ -504,7 +504,15 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   const int sms = device_sm_count();
   const size_t smem_need = ((p.w_bytes + 1023u) & ~1023u) + (size_t)p.nslots * p.slot_bytes + 2048;
   int per_sm = (int)((227u * 1024u) / smem_need);
-  const int reg_cap = (a->ncols_pad >> 4) == 2 ? 2 : 3;
+  int reg_cap = (a->ncols_pad >> 4) == 2 ? 2 : 3;
+  {
+    static int knob = -1;
+    if (knob < 0) {
+      const char* e = getenv("SMSUT_BAND_PER_SM");
+      knob = e && atoi(e) > 0 ? atoi(e) : 0;
+    }
+    if (knob > 0 && reg_cap > knob) reg_cap = knob;
+  }
   if (per_sm > reg_cap) per_sm = reg_cap;
   if (per_sm < 1) per_sm = 1;
   const int strips = a->n * p.wtiles;

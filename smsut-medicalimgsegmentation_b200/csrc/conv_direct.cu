@@ -104,6 +104,26 @@ __global__ void __launch_bounds__(128) direct_fprop_kernel(const DirectParams p)
   }
   if (!active) return;
   const size_t obase = (size_t)pix * p.y_ld;
+  if (CT >= 8 && !p.y_f32 && !p.accumulate && co0 + CT <= p.y_ld && ((obase + co0) & 7) == 0) {
+    // bf16 output, whole CT-channel run inside the pixel: 128-bit stores instead of CT two-byte stores
+    float v[CT];
+#pragma unroll
+    for (int o = 0; o < CT; ++o) {
+      const int co = co0 + o;
+      float t = acc[o];
+      if (co < p.cout) {
+        if (p.bias) t += p.bias[co];
+        t = apply_act(t, p.act, p.slope);
+      } else {
+        t = 0.f;
+      }
+      v[o] = t;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + obase + co0);
+#pragma unroll
+    for (int o = 0; o < CT; o += 8) dst[o >> 3] = pack8(v + o);
+    return;
+  }
 #pragma unroll
   for (int o = 0; o < CT; ++o) {
     const int co = co0 + o;
@@ -201,7 +221,23 @@ __global__ void __launch_bounds__(128) direct_dgrad_kernel(const DirectParams p)
         if (ox >= p.wo) continue;
         const size_t base = (((size_t)n * p.ho + oy) * p.wo + ox) * p.y_ld + c0;
         const float* wrow = ws + (size_t)(ky * p.kw + kx) * cn * CT;
-        for (int c = 0; c < cn; ++c) {
+        int c = 0;
+        if (!p.y_f32 && ((base | (size_t)p.y_ld) & 7) == 0) {
+          // bf16 gradient with 16-byte aligned channel runs: 8 channels per 128-bit load (the scalar loop below issued
+          // 64 two-byte loads per pixel on D's stem: 85 us for 67 MFLOP)
+          for (; c + 8 <= cn; c += 8) {
+            const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.y) + base + c);
+            float gv[8];
+            unpack8(q, gv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float* wv = wrow + (size_t)(c + k) * CT;
+#pragma unroll
+              for (int o = 0; o < CT; ++o) acc[o] = fmaf(gv[k], wv[o], acc[o]);
+            }
+          }
+        }
+        for (; c < cn; ++c) {
           const float gv = load_act(p.y, base + c, p.y_f32);
           const float* wv = wrow + (size_t)c * CT;
 #pragma unroll
