@@ -61,6 +61,7 @@ struct ConvTcParams {
   int dbg_rowshift;        // experiment: load the A tile one pixel to the left and start the descriptor one row later
   float* stats;            // fused InstanceNorm statistics [n][2][ncols_pad] of the stored values (optional)
   int fast;                // plain epilogue: bf16, one destination, every column valid, no bias / act / accumulate
+  int ksplit;              // > 1: the K steps are split over a (1,1,ksplit) cluster, partial tiles reduced through DSMEM
   KStep steps[kMaxSteps];
 };
 
@@ -113,6 +114,58 @@ __device__ __forceinline__ void store_chunk<float>(float* dst, const float* v, i
   }
 }
 
+
+// Plain-epilogue body for one 16-column chunk held in v[] (fp32): optional accumulate into / split of the bf16
+// destination(s), two 128-bit stores, and the InstanceNorm statistics of the stored values (one shuffle
+// reduce-scatter per chunk; a warp's 32 pixels belong to one image: host-checked).
+__device__ __forceinline__ void tc_fast_chunk(const ConvTcParams& p, float (&v)[16], int col, size_t pix, bool row_ok,
+                                              int lane, int n_w) {
+  __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0;
+  __nv_bfloat16* out1 = p.split > 0 ? reinterpret_cast<__nv_bfloat16*>(p.out1) + p.coff1 - p.split : out0;
+  const int ld1 = p.split > 0 ? p.ld1 : p.ld0;
+  uint4* dst = (p.split > 0 && col >= p.split) ? reinterpret_cast<uint4*>(out1 + pix * (size_t)ld1 + col)
+                                               : reinterpret_cast<uint4*>(out0 + pix * (size_t)p.ld0 + col);
+  if (p.accumulate && row_ok) {
+    float o[8];
+    const uint4 q0 = dst[0], q1 = dst[1];
+    unpack8(q0, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += o[k];
+    unpack8(q1, o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[8 + k] += o[k];
+  }
+  uint32_t w32[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
+  if (row_ok) {
+    dst[0] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+    dst[1] = make_uint4(w32[4], w32[5], w32[6], w32[7]);
+  }
+  if (p.stats != nullptr) {
+    float vals[32];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float lo = row_ok ? __uint_as_float(w32[k] << 16) : 0.f;
+      const float hi = row_ok ? __uint_as_float(w32[k] & 0xffff0000u) : 0.f;
+      vals[2 * k] = lo; vals[2 * k + 1] = hi;
+      vals[16 + 2 * k] = lo * lo; vals[16 + 2 * k + 1] = hi * hi;
+    }
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+      const bool upper = (lane & step) != 0;
+#pragma unroll
+      for (int k = 0; k < step; ++k) {
+        const float send = upper ? vals[k] : vals[k + step];
+        const float keep = upper ? vals[k + step] : vals[k];
+        vals[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+      }
+    }
+    // lane l: l < 16 -> sum of channel l, else sum of squares of channel l - 16 (image of the warp's first row)
+    if (n_w < p.n) atomicAdd(p.stats + ((size_t)n_w * 2 + (lane >> 4)) * p.ncols + col + (lane & 15), vals[0]);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -138,6 +191,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int h0 = th_i * p.th;
   const int w0 = tw_i * p.tw;
   const int col0 = blockIdx.y * p.bn;
+  // split-K over the cluster: CTA `kr` of the (1, 1, ksplit) cluster owns K steps [ks_begin, ks_end)
+  const int kr = p.ksplit > 1 ? (int)blockIdx.z : 0;
+  const int ks_begin = p.ksplit > 1 ? (kr * p.nsteps) / p.ksplit : 0;
+  const int ks_end = p.ksplit > 1 ? ((kr + 1) * p.nsteps) / p.ksplit : p.nsteps;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -166,7 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       uint8_t* ring = smem_raw + (smem_base - smem_u32(smem_raw));
-      for (int i = 0; i < p.nsteps; ++i) {
+      for (int i = ks_begin; i < ks_end; ++i) {
         const KStep st = p.steps[i];
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         mbar_arrive_expect_tx_e(&full_bar[stage], p.a_bytes + p.b_bytes, el);
@@ -191,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const uint32_t el = elect_one_u32();
     int stage = 0;
     uint32_t phase = 0;
-    for (int i = 0; i < p.nsteps; ++i) {
+    for (int i = ks_begin; i < ks_end; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       uint32_t a_lo = base_lo + (uint32_t)stage * stage_u;
@@ -201,10 +258,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int k = 0; k < 4; ++k) {
         if (k < kk)
           umma_bf16_e(tmem_base, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
-                      (i | k) != 0 ? 1u : 0u, el);
+                      (i != ks_begin || k != 0) ? 1u : 0u, el);
       }
       umma_commit_e(&empty_bar[stage], el);
-      if (i == p.nsteps - 1) umma_commit_e(&tmem_full_bar, el);
+      if (i == ks_end - 1) umma_commit_e(&tmem_full_bar, el);
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
   } else {
@@ -221,64 +278,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tc_fence_after();
 
     const int nchunks = p.bn >> 4;
-    if (p.fast) {
-      // common case: two 128-bit stores per 16 columns; the InstanceNorm statistics of the stored values leave the
-      // warp through one shuffle reduce-scatter per chunk (a warp's 32 pixels belong to one image: host-checked)
-      __nv_bfloat16* out0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + p.coff0;
-      __nv_bfloat16* out1 = p.split > 0 ? reinterpret_cast<__nv_bfloat16*>(p.out1) + p.coff1 - p.split : out0;
-      const int ld1 = p.split > 0 ? p.ld1 : p.ld0;
-      const size_t pix = ((size_t)n * p.h + h) * p.w + w;
+    if (p.ksplit > 1) {
+      // split-K, phase A: this CTA's partial tile -> its own shared memory as [chunk][row][16] fp32 (the stage ring
+      // is free: every MMA that read it has completed before tmem_full fired)
+      float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
       for (int j = 0; j < nchunks; ++j) {
         uint32_t raw[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
         tmem_ld_wait();
-        const int col = col0 + j * 16;
-        uint4* dst = (p.split > 0 && col >= p.split) ? reinterpret_cast<uint4*>(out1 + pix * (size_t)ld1 + col)
-                                                     : reinterpret_cast<uint4*>(out0 + pix * (size_t)p.ld0 + col);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          stg[(size_t)(j * 128 + r) * 4 + k] =
+              make_float4(__uint_as_float(raw[4 * k]), __uint_as_float(raw[4 * k + 1]), __uint_as_float(raw[4 * k + 2]),
+                          __uint_as_float(raw[4 * k + 3]));
+      }
+    } else if (p.fast) {
+      const size_t pix = ((size_t)n * p.h + h) * p.w + w;
+      const int n_w = n0 + (q * 32) / (p.tw * p.th);
+      for (int j = 0; j < nchunks; ++j) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
+        tmem_ld_wait();
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) v[k] = __uint_as_float(raw[k]);
-        if (p.accumulate && row_ok) {
-          float o[8];
-          const uint4 q0 = dst[0], q1 = dst[1];
-          unpack8(q0, o);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] += o[k];
-          unpack8(q1, o);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[8 + k] += o[k];
-        }
-        uint32_t w32[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) w32[k] = pack_bf16x2(v[2 * k], v[2 * k + 1]);
-        if (row_ok) {
-          dst[0] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
-          dst[1] = make_uint4(w32[4], w32[5], w32[6], w32[7]);
-        }
-        if (p.stats != nullptr) {
-          float vals[32];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float lo = row_ok ? __uint_as_float(w32[k] << 16) : 0.f;
-            const float hi = row_ok ? __uint_as_float(w32[k] & 0xffff0000u) : 0.f;
-            vals[2 * k] = lo; vals[2 * k + 1] = hi;
-            vals[16 + 2 * k] = lo * lo; vals[16 + 2 * k + 1] = hi * hi;
-          }
-#pragma unroll
-          for (int step = 16; step >= 1; step >>= 1) {
-            const bool upper = (lane & step) != 0;
-#pragma unroll
-            for (int k = 0; k < step; ++k) {
-              const float send = upper ? vals[k] : vals[k + step];
-              const float keep = upper ? vals[k + step] : vals[k];
-              vals[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-            }
-          }
-          // lane l: l < 16 -> sum of channel l, else sum of squares of channel l - 16 (image of the warp's first row)
-          const int n_w = n0 + (q * 32) / (p.tw * p.th);
-          if (n_w < p.n)
-            atomicAdd(p.stats + ((size_t)n_w * 2 + (lane >> 4)) * p.ncols + col0 + j * 16 + (lane & 15), vals[0]);
-        }
+        tc_fast_chunk(p, v, col0 + j * 16, pix, row_ok, lane, n_w);
       }
     } else
     for (int j = 0; j < nchunks; ++j) {
@@ -331,6 +355,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   }
 
+  if (p.ksplit > 1) {
+    // split-K, phase B: reduce-scatter of the partial tiles through distributed shared memory.  CTA kr of the cluster
+    // finishes the chunks j = kr, kr + ksplit, ...: it sums the ksplit partials of those 16 columns (its own and the
+    // peers', read with ld.shared::cluster) and runs the plain epilogue on them.
+    cluster_sync_all();                 // every CTA's partial tile is in its shared memory
+    if (warp >= 2) {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const int wl = r % p.tw, hl = (r / p.tw) % p.th, nl = r / (p.tw * p.th);
+      const int n = n0 + nl, h = h0 + hl, w = w0 + wl;
+      const bool row_ok = (n < p.n) && (h < p.h) && (w < p.w);
+      const size_t pix = ((size_t)n * p.h + h) * p.w + w;
+      const int n_w = n0 + (q * 32) / (p.tw * p.th);
+      const int nchunks = p.bn >> 4;
+      for (int j = kr; j < nchunks; j += p.ksplit) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = 0.f;
+        const uint32_t local = smem_base + (uint32_t)((j * 128 + r) * 64);
+        for (int c = 0; c < p.ksplit; ++c) {
+          const uint32_t ra = dsmem_addr(local, (uint32_t)c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 t = dsmem_ld_f4(ra + 16u * k);
+            v[4 * k] += t.x; v[4 * k + 1] += t.y; v[4 * k + 2] += t.z; v[4 * k + 3] += t.w;
+          }
+        }
+        tc_fast_chunk(p, v, col0 + j * 16, pix, row_ok, lane, n_w);
+      }
+    }
+    cluster_sync_all();                 // no CTA leaves (or frees its shared memory) while a peer still reads it
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -548,6 +604,37 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
       if ((int64_t)m_tiles * (a->ncols_pad / c) >= 120 || c <= 64) break;
     }
   }
+  // Deep layers: a handful of output tiles (32 at 16x16) each with a long K loop (36-72 steps of a narrow N tile).
+  // Optional (SMSUT_TC_KSPLIT=2|4): take the widest N tile instead and split K over a (1, 1, ksplit) thread-block
+  // cluster; the partial tiles meet in distributed shared memory (reduce-scatter: CTA k finishes every ksplit-th
+  // 16-column chunk).  Only with the plain epilogue, and only when the whole cluster grid still fits one wave.
+  // MEASURED on B200 and OFF by default: 256->256 @ 16x16 takes 24.6 us split 4-way against 18.4 us un-split
+  // (128->256: 22.6 vs 13.0): the 128 KB reduce-scatter through DSMEM (~20 B/cycle/SM) costs more than the shorter
+  // K loop saves.
+  int ksplit = 1;
+  if (a->bn <= 0 && conv_tc_plain_epilogue(a)) {
+    static int knob = -1;
+    if (knob < 0) {
+      const char* e = getenv("SMSUT_TC_KSPLIT");
+      knob = e ? atoi(e) : 0;
+    }
+    const int sms = device_sm_count();
+    if (knob > 1 && (int64_t)m_tiles * (a->ncols_pad / bn) <= sms) {
+      const int cands[4] = {256, 128, 64, 32};
+      for (int i = 0; i < 4 && ksplit == 1; ++i) {
+        const int c = cands[i];
+        if (c > a->ncols_pad || a->ncols_pad % c != 0) continue;
+        const int ctas = m_tiles * (a->ncols_pad / c);
+        for (int k = knob > 4 ? 4 : knob; k > 1; k >>= 1) {
+          if (ctas * k <= sms && ns >= 3 * k && (c >> 4) >= k) {
+            bn = c;
+            ksplit = k;
+            break;
+          }
+        }
+      }
+    }
+  }
   SMSUT_CHECK(bn % 16 == 0 && bn >= 16 && bn <= 256 && a->ncols_pad % bn == 0, -1, "bad N tile %d for %d columns", bn,
               a->ncols_pad);
   p.bn = bn;
@@ -581,7 +668,9 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   if (stages > ns) stages = ns;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+  size_t smem = (size_t)stages * p.stage_bytes;
+  if (ksplit > 1 && smem < (size_t)bn * 512u) smem = (size_t)bn * 512u;      // split-K staging [chunk][128][16] fp32
+  smem += 1024;
 
   p.mode = a->kind == SMSUT_TC_CONVT_FWD ? 1 : 0;
   p.out0 = a->out0; p.ld0 = a->out0_ld; p.coff0 = a->out0_coff;
@@ -606,8 +695,13 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   if (!a->out_f32)
     SMSUT_CHECK(a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 || a->ncols < 16, -1, "bf16 output pitch/offset must be multiples of 8");
 
-  dim3 grid((unsigned)m_tiles, (unsigned)(a->ncols_pad / bn));
-  launch_pdl(conv_tc_kernel, grid, kThreads, smem, stream, maps[0], maps[1], maps[2], maps[3], map_w, p);
+  p.ksplit = ksplit;
+  dim3 grid((unsigned)m_tiles, (unsigned)(a->ncols_pad / bn), (unsigned)ksplit);
+  if (ksplit > 1)
+    launch_cluster_z(conv_tc_kernel, grid, kThreads, smem, stream, (unsigned)ksplit, maps[0], maps[1], maps[2], maps[3],
+                     map_w, p);
+  else
+    launch_pdl(conv_tc_kernel, grid, kThreads, smem, stream, maps[0], maps[1], maps[2], maps[3], map_w, p);
   count_launch();
   return launch_status("conv_tc_kernel");
 }

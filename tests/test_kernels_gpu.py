@@ -540,3 +540,33 @@ def test_confusion_counts_bit_exact(ops):
     ref = torch.zeros(c * c, dtype=torch.int64, device=DEV)
     ref.index_add_(0, labels[ok] * c + pred[ok], torch.ones_like(pred[ok]))
     assert torch.equal(conf.view(-1), 2 * ref)
+
+
+def test_conv_tc_cluster_split_k(ops, monkeypatch):
+    """opt-in split-K over a thread-block cluster with a DSMEM reduce-scatter (SMSUT_TC_KSPLIT): same results as the
+    un-split kernel, fused statistics included.  (The knob is read once per process: run in a subprocess.)"""
+    import os
+    import subprocess
+    import sys
+    code = """
+import sys, torch
+sys.path.insert(0, '.')
+import __graft_entry__ as g; g.load_package()
+from smsut_b200 import ops
+import torch.nn.functional as F
+torch.manual_seed(3)
+for cin, cout, h, n in ((256, 256, 16, 16), (128, 256, 16, 16), (256, 256, 8, 16)):
+    x = torch.randn(n, cin, h, h, device='cuda').to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3, device='cuda') * (2.0 / (cin * 9)) ** 0.5).to(torch.bfloat16).float()
+    pw = ops.PackedWeight(w); ops.PackTable([pw]).refresh()
+    y, st = ops.conv_fprop([x.permute(0, 2, 3, 1).contiguous()], pw, want_stats=True)
+    ref = F.conv2d(x.float(), w, padding=1)
+    got = y.permute(0, 3, 1, 2).float()
+    assert ((got - ref).norm() / ref.norm()).item() < 1e-2
+    yf = y.float()
+    assert ((st[:, 0] - yf.sum((1, 2))).norm() / yf.sum((1, 2)).norm()).item() < 1e-4
+print('ok')
+"""
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SMSUT_TC_KSPLIT="4"), capture_output=True,
+                       text=True, timeout=300, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
