@@ -166,6 +166,8 @@ __device__ __forceinline__ void tc_fast_chunk(const ConvTcParams& p, float (&v)[
   }
 }
 
+// KSPLIT: compiled with the cluster split-K path (opt-in, see conv_tc_impl); the default instantiation carries none of it
+template <bool KSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
@@ -192,9 +194,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int w0 = tw_i * p.tw;
   const int col0 = blockIdx.y * p.bn;
   // split-K over the cluster: CTA `kr` of the (1, 1, ksplit) cluster owns K steps [ks_begin, ks_end)
-  const int kr = p.ksplit > 1 ? (int)blockIdx.z : 0;
-  const int ks_begin = p.ksplit > 1 ? (kr * p.nsteps) / p.ksplit : 0;
-  const int ks_end = p.ksplit > 1 ? ((kr + 1) * p.nsteps) / p.ksplit : p.nsteps;
+  const bool split = KSPLIT && p.ksplit > 1;
+  const int kr = split ? (int)blockIdx.z : 0;
+  const int ks_begin = split ? (kr * p.nsteps) / p.ksplit : 0;
+  const int ks_end = split ? ((kr + 1) * p.nsteps) / p.ksplit : p.nsteps;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
@@ -278,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tc_fence_after();
 
     const int nchunks = p.bn >> 4;
-    if (p.ksplit > 1) {
+    if (split) {
       // split-K, phase A: this CTA's partial tile -> its own shared memory as [chunk][row][16] fp32 (the stage ring
       // is free: every MMA that read it has completed before tmem_full fired)
       float4* stg = reinterpret_cast<float4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
@@ -355,7 +358,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   }
 
-  if (p.ksplit > 1) {
+  if (split) {
     // split-K, phase B: reduce-scatter of the partial tiles through distributed shared memory.  CTA kr of the cluster
     // finishes the chunks j = kr, kr + ksplit, ...: it sums the ksplit partials of those 16 columns (its own and the
     // peers', read with ld.shared::cluster) and runs the plain epilogue on them.
@@ -518,7 +521,8 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SMSUT_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
 
@@ -698,10 +702,10 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   p.ksplit = ksplit;
   dim3 grid((unsigned)m_tiles, (unsigned)(a->ncols_pad / bn), (unsigned)ksplit);
   if (ksplit > 1)
-    launch_cluster_z(conv_tc_kernel, grid, kThreads, smem, stream, (unsigned)ksplit, maps[0], maps[1], maps[2], maps[3],
+    launch_cluster_z(conv_tc_kernel<true>, grid, kThreads, smem, stream, (unsigned)ksplit, maps[0], maps[1], maps[2], maps[3],
                      map_w, p);
   else
-    launch_pdl(conv_tc_kernel, grid, kThreads, smem, stream, maps[0], maps[1], maps[2], maps[3], map_w, p);
+    launch_pdl(conv_tc_kernel<false>, grid, kThreads, smem, stream, maps[0], maps[1], maps[2], maps[3], map_w, p);
   count_launch();
   return launch_status("conv_tc_kernel");
 }
