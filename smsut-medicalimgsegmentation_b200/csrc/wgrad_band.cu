@@ -37,6 +37,7 @@ struct WgradBandParams {
   uint32_t x_pitch, d_pitch, x_layout, d_layout;
   uint32_t tmem_cols;
   int dbg_noepi;   // development: skip the atomics (SMSUT_WGRAD_NOEPI=1)
+  int stack;       // N-stacked issue: one UMMA covers all vertical taps of an x row (see the MMA issuer)
   int tap_major;   // dw is the tap-major scratch [tap][cout_total][cin_total]: lanes = contiguous channels
   int cout_total;
   float* dw;
@@ -131,6 +132,59 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t grp_u = ((uint32_t)p.tx_per_group * p.x_pitch) >> 4;   // next group of horizontal taps
     const int kchunks = p.kchunks, groups = p.groups;
     const uint32_t el = elect_one_u32();
+    if (p.stack) {
+      // N-stacked issue.  ncu / the UMMA model: one UMMA per (row, 16-pixel K chunk, vertical tap) with N = dcc = 16
+      // reads its 4 KB A tile for 16 columns of work, and two co-resident CTAs then saturate the tensor pipe's smem
+      // read port long before HBM.  Walk the X rows instead: x row j meets the dy rows j-KS+1 .. j, which sit in
+      // consecutive slots of the dy ring, so ONE UMMA with B = those slots side by side (N-blocks LBO = slot stride)
+      // accumulates every vertical tap at once: N = KS * dcc, a third of the instructions and A reads.  D column
+      // block b holds vertical tap ty = KS-1-b.  The block an x row touches for the first time (rows 0..KS-1) gets its
+      // own UMMA with accumulate = 0; a window that wraps around the ring is issued in two pieces.
+      const uint64_t b_hi_st = make_smem_desc(0, p.d_slot_bytes, 8u * p.d_pitch, p.d_layout) & 0xFFFFFFFFFFFF0000ull;
+      const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((128u >> 4) << 24);
+      const int dcc = p.dcc;
+      int xslot = 0, dslot_w = 0;
+      uint32_t xphase = 0, dphase_w = 0;
+      for (int j = 0; j < nrows_in; ++j) {
+        mbar_wait(&x_full[xslot], xphase);
+        if (j < nrows) {
+          mbar_wait(&d_full[dslot_w], dphase_w);
+          if (++dslot_w == nslots) { dslot_w = 0; dphase_w ^= 1u; }
+        }
+        tc_fence_after();
+        const int blk_lo = KS - 1 - j > 0 ? KS - 1 - j : 0;
+        const int blk_hi = nrows + KS - 2 - j < KS - 1 ? nrows + KS - 2 - j : KS - 1;
+        if (blk_lo <= blk_hi) {
+          const int i_lo = j - KS + 1 + blk_lo;                 // dy row of block blk_lo
+          const bool fresh = j <= KS - 1;                     // block blk_lo (dy row 0) is touched for the first time
+          const uint32_t a0 = x_base + (uint32_t)xslot * xslot_u;
+          for (int k = 0; k < kchunks; ++k) {
+            const uint64_t adesc = a_hi | (uint64_t)((a0 + k * xk_u) & 0x3FFFu);
+            int b = blk_lo, i = i_lo;
+            if (fresh) {
+              const uint32_t bs = d_base + (uint32_t)(i % nslots) * dslot_u + k * dk_u;
+              umma_bf16_e(tmem_base + (uint32_t)(b * dcc), adesc, b_hi | (uint64_t)(bs & 0x3FFFu),
+                          idesc0 | ((uint32_t)(dcc >> 3) << 17), k != 0 ? 1u : 0u, el);
+              ++b; ++i;
+            }
+            while (b <= blk_hi) {
+              const int s0 = i % nslots;
+              int nb = blk_hi - b + 1;
+              if (nb > nslots - s0) nb = nslots - s0;          // up to the end of the ring
+              const uint32_t bs = d_base + (uint32_t)s0 * dslot_u + k * dk_u;
+              umma_bf16_e(tmem_base + (uint32_t)(b * dcc), adesc, b_hi_st | (uint64_t)(bs & 0x3FFFu),
+                          idesc0 | ((uint32_t)((nb * dcc) >> 3) << 17), 1u, el);
+              b += nb; i += nb;
+            }
+          }
+        }
+        umma_commit_e(&x_empty[xslot], el);
+        const int i_rel = j - KS + 1;                        // dy row no later x row needs
+        if (i_rel >= 0 && i_rel < nrows) umma_commit_e(&d_empty[i_rel % nslots], el);
+        if (j == nrows_in - 1) umma_commit_e(&acc_full, el);
+        if (++xslot == nslots) { xslot = 0; xphase ^= 1u; }
+      }
+    } else {
     int rows_ready = 0, ready_slot = 0, base_slot = 0, dslot = 0;
     uint32_t ready_phase = 0, dphase = 0;
     for (int i = 0; i < nrows; ++i) {
@@ -163,6 +217,7 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (++base_slot == nslots) base_slot = 0;
       if (++dslot == nslots) { dslot = 0; dphase ^= 1u; }
     }
+    }
   } else {
     // ===================== epilogue: D_{ty,g}[(tx, ci)][co] -> atomics into dW[co][ci_off + ci][ty][tx] ==========
     const int q = warp & 3;
@@ -178,7 +233,7 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       tmem_ld_wait();
       const int col = j * 16;
       const int region = col / p.dcc, co0 = dch * p.dcc + (col - region * p.dcc);
-      const int ty = region / p.groups, g = region - ty * p.groups;
+      const int ty = p.stack ? KS - 1 - region : region / p.groups, g = p.stack ? 0 : region - (region / p.groups) * p.groups;
       const int tx = g * p.tx_per_group + txl;
       if (txl >= p.tx_per_group || tx >= KS || ci >= p.c_valid) continue;
       const int tap = ty * KS + tx;
@@ -251,6 +306,12 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   uint32_t tc = 32;
   while ((int)tc < cols) tc <<= 1;
   p.tmem_cols = tc;
+  {
+    const char* e = getenv("SMSUT_WGRAD_STACK");
+    // opt-in: measured SLOWER on B200 (16->16 @ 256x256: 88 us stacked vs 57 us; whole step 13.3 vs 12.1 ms) -- an
+    // MN-major B operand gathered from three row slots 4 KB apart evidently costs more than the saved instructions
+    p.stack = (p.groups == 1 && a->ksize * p.dcc <= 256 && e && e[0] == '1') ? 1 : 0;
+  }
   p.dw = a->dw;
   p.tap_major = a->dw_layout == 1 ? 1 : 0;
   p.cout_total = a->cout_total;
