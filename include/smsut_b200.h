@@ -154,6 +154,17 @@ int smsut_in_bwd2_reduce(const void* u, const void* dy, const void* x, const flo
 int smsut_in_bwd2_apply(const void* u, const void* dy, const void* x, const float* stats, const float* gamma,
                         const float* red2, void* g_dy, void* g_x, float* dgamma, int32_t n, int32_t hw, int32_t c,
                         smsut_stream_t stream);
+/* BatchNorm2d (network/blocks.py:19-26 get_norm('batch'); default norm of network/unet.py:14) on the kernels above:
+ * out[j] = mean over the n rows of rows[n][k][c] for every j (batch statistics = pooled per-sample sums; the
+ * backward pools `red` the same way between smsut_in_bwd_reduce and smsut_in_bwd_apply) */
+int smsut_bn_pool(const float* rows, float* out, int32_t n, int32_t k, int32_t c, smsut_stream_t stream);
+/* running_mean/var <- (1-momentum)*running + momentum*{batch mean, UNBIASED batch var} (torch.nn.BatchNorm2d) from a
+ * pooled statistics table; only the first c_params channels carry parameters */
+int smsut_bn_running_update(const float* pooled_stats, int32_t n, int32_t hw, int32_t c, int32_t c_params,
+                            float momentum, float* running_mean, float* running_var, smsut_stream_t stream);
+/* eval mode: stats[n][2][c] such that smsut_in_apply normalises with the running estimates */
+int smsut_bn_eval_stats(const float* running_mean, const float* running_var, float* stats, int32_t n, int32_t hw,
+                        int32_t c, int32_t c_params, smsut_stream_t stream);
 /* elementwise LeakyReLU family on bf16: y = act(x) ; dx = dy*act'(ref) (+ add) ; plain add */
 int smsut_act_fwd(const void* x, void* y, int64_t count, int32_t act, float slope, smsut_stream_t stream);
 int smsut_act_bwd(const void* dy, const void* ref, const void* add, void* dx, int64_t count, int32_t act, float slope,

@@ -160,13 +160,47 @@ def lrelu(x):
     return F.leaky_relu(x, SLOPE)
 
 
-def basic_block(x, sd, p):
+class Style:
+    """norm / activation choice of a network (network/blocks.py:19-34 get_norm / get_act).  The trainers all use
+    ('instance', 'lrelu'); ('batch', 'relu') is the default of the UNet / Encoder / Decoder signatures
+    (network/unet.py:14).  BatchNorm keeps its running estimates in `sd` under the nn.BatchNorm2d buffer names."""
+
+    def __init__(self, norm="instance", act="lrelu", training=True, momentum=0.1):
+        self.norm_type, self.act_type, self.training, self.momentum = norm, act, training, momentum
+
+    def norm(self, x, sd, p):
+        if self.norm_type == "instance":
+            return inorm(x, sd, p)
+        # nn.BatchNorm2d(C): batch statistics + running-estimate update in training, running estimates in eval
+        return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
+                            self.training, self.momentum, EPS)
+
+    def act(self, x):
+        return lrelu(x) if self.act_type == "lrelu" else F.relu(x)
+
+
+DEFAULT_STYLE = Style()
+
+
+def add_bn_buffers(sd):
+    """running_mean / running_var / num_batches_tracked entries of nn.BatchNorm2d for every affine norm in `sd`."""
+    out = dict(sd)
+    for k, v in sd.items():
+        if v.dim() == 1 and k.endswith(".bias") and k[:-4] + "weight" in sd and sd[k[:-4] + "weight"].dim() == 1:
+            p = k[:-4]
+            out[p + "running_mean"] = torch.zeros_like(v)
+            out[p + "running_var"] = torch.ones_like(v)
+            out[p + "num_batches_tracked"] = torch.zeros((), dtype=torch.int64, device=v.device)
+    return out
+
+
+def basic_block(x, sd, p, st=DEFAULT_STYLE):
     # network/blocks.py:66-80
-    y = lrelu(inorm(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1."))
-    y = inorm(F.conv2d(y, sd[p + "conv2.weight"], padding=1), sd, p + "bn2.")
+    y = st.act(st.norm(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1."))
+    y = st.norm(F.conv2d(y, sd[p + "conv2.weight"], padding=1), sd, p + "bn2.")
     if p + "shortcut1.weight" in sd:
-        x = inorm(F.conv2d(x, sd[p + "shortcut1.weight"]), sd, p + "shortcut2.")
-    return lrelu(y + x)
+        x = st.norm(F.conv2d(x, sd[p + "shortcut1.weight"]), sd, p + "shortcut2.")
+    return st.act(y + x)
 
 
 def bottle_block(x, sd, p):
@@ -180,22 +214,23 @@ def bottle_block(x, sd, p):
     return lrelu(y + ident)
 
 
-def unet_forward(sd, x, taps=None):
+def unet_forward(sd, x, taps=None, style=DEFAULT_STYLE):
     """network/unet.py:29-32 -> blocks.Encoder.forward (blocks.py:138-153) + blocks.Decoder.forward (:168-174)."""
     t = taps if taps is not None else {}
-    x = lrelu(inorm(F.conv2d(x, sd["encoder.pre_conv.weight"], padding=2), sd, "encoder.pre_bn."))
+    st = style
+    x = st.act(st.norm(F.conv2d(x, sd["encoder.pre_conv.weight"], padding=2), sd, "encoder.pre_bn."))
     t["encoder.pre"] = x
     skips = []
     for i in range(1, 5):
-        x = basic_block(x, sd, f"encoder.layer{i}.")
+        x = basic_block(x, sd, f"encoder.layer{i}.", st)
         t[f"encoder.layer{i}"] = x
         skips.append(x)
         x = F.max_pool2d(x, 2, 2)
-    x = basic_block(x, sd, "encoder.layer5.")
+    x = basic_block(x, sd, "encoder.layer5.", st)
     t["encoder.layer5"] = x
     for i in (4, 3, 2, 1):
         up = F.conv_transpose2d(x, sd[f"decoder.up{i}.up.weight"], stride=2)
-        x = basic_block(torch.cat([up, skips[i - 1]], 1), sd, f"decoder.layer{i}.")
+        x = basic_block(torch.cat([up, skips[i - 1]], 1), sd, f"decoder.layer{i}.", st)
         t[f"decoder.layer{i}"] = x
     return F.conv2d(x, sd["decoder.fc.weight"])
 

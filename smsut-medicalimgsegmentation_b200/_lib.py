@@ -78,6 +78,9 @@ _PROTOS = {
                            c_float, P],
     "smsut_in_bwd2_reduce": [P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_in_bwd2_apply": [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P],
+    "smsut_bn_pool": [P, P, c_int, c_int, c_int, P],
+    "smsut_bn_running_update": [P, c_int, c_int, c_int, c_int, c_float, P, P, P],
+    "smsut_bn_eval_stats": [P, P, P, c_int, c_int, c_int, c_int, P],
     "smsut_act_fwd": [P, P, c_int64, c_int, c_float, P],
     "smsut_act_bwd": [P, P, P, P, c_int64, c_int, c_float, P],
     "smsut_add_bf16": [P, P, P, c_int64, P],

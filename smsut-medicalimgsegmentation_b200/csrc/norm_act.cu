@@ -772,6 +772,74 @@ extern "C" int smsut_in_bwd2_apply(const void* u, const void* dy, const void* x,
   return launch_status("in_bwd2_apply_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// BatchNorm2d on top of the InstanceNorm kernels (network/blocks.py:19-26 get_norm('batch'), the default of
+// network/unet.py:14): batch statistics are the per-sample sums averaged over the samples, so the same apply /
+// backward kernels run on a (n, k, c) table whose n rows all hold the batch mean of the per-sample rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_pool_kernel(const float* rows, float* out, int n, int kc) {  // out may alias rows (column-private)
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kc) return;
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) s += rows[(size_t)j * kc + i];
+  s /= (float)n;
+  for (int j = 0; j < n; ++j) out[(size_t)j * kc + i] = s;
+}
+
+// running_mean / running_var momentum update from pooled statistics (row 0 of the table): PyTorch semantics,
+// unbiased variance in the running estimate (count = n*hw).
+__global__ void bn_running_kernel(const float* __restrict__ pooled, int c, int cp, float inv_hw, float unbias,
+                                  float momentum, float* __restrict__ rmean, float* __restrict__ rvar) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cp) return;
+  const float m = pooled[i] * inv_hw;
+  const float var = fmaxf(pooled[c + i] * inv_hw - m * m, 0.f);
+  rmean[i] = (1.f - momentum) * rmean[i] + momentum * m;
+  rvar[i] = (1.f - momentum) * rvar[i] + momentum * var * unbias;
+}
+
+// eval mode: a statistics table that makes the apply kernel normalise with the running estimates
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar,
+                                     float* __restrict__ stats, int n, int c, int cp, float hw) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int j = i / c, ch = i - j * c;
+  const float m = ch < cp ? rmean[ch] : 0.f, v = ch < cp ? rvar[ch] : 0.f;
+  stats[(size_t)j * 2 * c + ch] = m * hw;
+  stats[(size_t)j * 2 * c + c + ch] = (v + m * m) * hw;
+}
+
+extern "C" int smsut_bn_pool(const float* rows, float* out, int32_t n, int32_t k, int32_t c, smsut_stream_t st) {
+  SMSUT_CHECK(n > 0 && k > 0 && c > 0, -1, "bn_pool: empty table");
+  const int kc = k * c;
+  launch_pdl(bn_pool_kernel, dim3((kc + 127) / 128), 128, 0, (cudaStream_t)st, rows, out, n, kc);
+  count_launch();
+  return launch_status("bn_pool_kernel");
+}
+
+extern "C" int smsut_bn_running_update(const float* pooled, int32_t n, int32_t hw, int32_t c, int32_t cp,
+                                       float momentum, float* running_mean, float* running_var, smsut_stream_t st) {
+  SMSUT_CHECK(n > 0 && hw > 0 && cp > 0 && cp <= c, -1, "bn_running_update: bad sizes");
+  const double count = (double)n * hw;
+  const float unbias = count > 1.0 ? (float)(count / (count - 1.0)) : 1.f;
+  launch_pdl(bn_running_kernel, dim3((cp + 127) / 128), 128, 0, (cudaStream_t)st, pooled, c, cp, 1.f / (float)hw, unbias,
+             momentum, running_mean, running_var);
+  count_launch();
+  return launch_status("bn_running_kernel");
+}
+
+extern "C" int smsut_bn_eval_stats(const float* running_mean, const float* running_var, float* stats, int32_t n,
+                                   int32_t hw, int32_t c, int32_t cp, smsut_stream_t st) {
+  SMSUT_CHECK(n > 0 && hw > 0 && cp > 0 && cp <= c, -1, "bn_eval_stats: bad sizes");
+  launch_pdl(bn_eval_stats_kernel, dim3((n * c + 127) / 128), 128, 0, (cudaStream_t)st, running_mean, running_var, stats, n,
+             c, cp, (float)hw);
+  count_launch();
+  return launch_status("bn_eval_stats_kernel");
+}
+
 extern "C" int smsut_colsum_bf16(const void* x, int32_t rows, int32_t c, float* out, smsut_stream_t st) {
   int rc = check_nc(1, rows, c);
   if (rc) return rc;

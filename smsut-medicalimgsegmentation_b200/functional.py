@@ -306,6 +306,9 @@ class DirectConvFn(Function):
 # ----------------------------------------------------------------------------------------------
 # InstanceNorm + activation + residual
 # ----------------------------------------------------------------------------------------------
+BN_OFF, BN_TRAIN, BN_EVAL = 0, 1, 2     # INActFn `batch` modes: InstanceNorm / BatchNorm training / BatchNorm eval
+
+
 class LReluBwdFn(Function):
     """g = dy * act'(ref)  (ref = the activation's output; piecewise linear => second derivative is zero)"""
 
@@ -340,13 +343,13 @@ class INActFn(Function):
     """out = act( IN(xa; ga, ba) [+ IN(xb; gb, bb)] [+ res] )  (network/blocks.py:66-80, 99-117)"""
 
     @staticmethod
-    def forward(ctx, xa, ga, ba, xb, gb, bb, res, act, c_params, sa=None, sb=None):
+    def forward(ctx, xa, ga, ba, xb, gb, bb, res, act, c_params, sa=None, sb=None, batch=BN_OFF):
         if sa is None:
             sa = ops.in_stats(xa)
         if xb is not None and sb is None:
             sb = ops.in_stats(xb)
         out = ops.in_apply(xa, sa, ga, ba, xb, sb, gb, bb, res=res, act=act, slope=SLOPE, c_params=c_params)
-        ctx.act, ctx.cp, ctx.has_res = act, c_params, res is not None
+        ctx.act, ctx.cp, ctx.has_res, ctx.batch = act, c_params, res is not None, batch
         ctx.save_for_backward(xa, sa, ga, xb, sb, gb, out, ba, bb)
         return out
 
@@ -356,7 +359,12 @@ class INActFn(Function):
         dout = _c(dout)
         act, cp = ctx.act, ctx.cp
         want_res = ctx.has_res and ctx.needs_input_grad[6]
+        if ctx.batch == BN_EVAL:
+            raise NotImplementedError("backward through BatchNorm2d in eval mode (running statistics) is not on the path")
         if torch.is_grad_enabled():
+            if ctx.batch != BN_OFF:
+                raise NotImplementedError("double backward through BatchNorm2d is not on the path (the WGAN-GP "
+                                          "discriminator uses InstanceNorm)")
             assert cp is None or cp == xa.shape[3]
             g = LReluBwdFn.apply(dout, out, act) if act != ACT_NONE else dout
             dxa = INBwdFn.apply(g, xa, sa, ga)
@@ -364,7 +372,7 @@ class INActFn(Function):
             dga = dba = dgb = dbb = None
             if not _inputs_only_global[0]:
                 _, dga, dba, _, dgb, dbb, _ = ops.in_bwd(dout.detach(), out, xa, sa, ga, xb, sb, gb, False, act, SLOPE, cp)
-            return dxa, dga, dba, dxb, dgb, dbb, (g if want_res else None), None, None, None, None
+            return dxa, dga, dba, dxb, dgb, dbb, (g if want_res else None), None, None, None, None, None
         targets = None
         need = ctx.needs_input_grad
         if not (need[1] or need[2] or need[4] or need[5]):
@@ -375,13 +383,35 @@ class INActFn(Function):
             if tg[0] is not None and tg[1] is not None and (xb is None or (tg[2] is not None and tg[3] is not None)):
                 targets = tg
         dxa, dga, dba, dxb, dgb, dbb, dres = ops.in_bwd(dout, out, xa, sa, ga, xb, sb, gb, want_res, act, SLOPE, cp,
-                                                        targets=targets)
-        return dxa, dga, dba, dxb, dgb, dbb, dres, None, None, None, None
+                                                        targets=targets, batch=ctx.batch == BN_TRAIN)
+        return dxa, dga, dba, dxb, dgb, dbb, dres, None, None, None, None, None
+
+
+def _bn_stats(x, norm, stats):
+    """Statistics table for a BatchNorm2d layer (network/blocks.py:19-26, norm_type='batch'): training = the
+    per-sample sums pooled over the batch (+ the running-estimate update of torch.nn.BatchNorm2d), eval = a table
+    built from the running estimates.  Returns (table, mode)."""
+    n, h, w, c = x.shape
+    with torch.no_grad():
+        if norm.training or not norm.track_running_stats:
+            pooled = ops.bn_pool(stats if stats is not None else ops.in_stats(x))
+            if norm.training and norm.track_running_stats:
+                norm.num_batches_tracked.add_(1)
+                if norm.momentum is None:
+                    raise NotImplementedError("BatchNorm2d(momentum=None) (cumulative average) is not on the path")
+                ops.bn_running_update(pooled, h * w, norm.running_mean, norm.running_var, norm.momentum)
+            return pooled, BN_TRAIN
+        return ops.bn_eval_stats(norm.running_mean, norm.running_var, n, h * w, c), BN_EVAL
 
 
 def in_act(xa, norm_a, xb=None, norm_b=None, res=None, act=ACT_LRELU, c_params=None, stats_a=None, stats_b=None):
+    batch = BN_OFF
+    if getattr(norm_a, "smsut_batch_norm", False):
+        stats_a, batch = _bn_stats(xa, norm_a, stats_a)
+        if xb is not None:
+            stats_b, _ = _bn_stats(xb, norm_b, stats_b)
     return INActFn.apply(xa, norm_a.weight, norm_a.bias, xb, norm_b.weight if norm_b is not None else None,
-                         norm_b.bias if norm_b is not None else None, res, act, c_params, stats_a, stats_b)
+                         norm_b.bias if norm_b is not None else None, res, act, c_params, stats_a, stats_b, batch)
 
 
 # ----------------------------------------------------------------------------------------------

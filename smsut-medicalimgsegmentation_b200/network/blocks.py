@@ -115,6 +115,24 @@ class InstanceNorm2d(nn.InstanceNorm2d):
         return to_nchw(Fn.INActFn.apply(xin, self.weight, self.bias, None, None, None, None, ACT_NONE, cp))
 
 
+class BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d(C) (affine, running statistics, momentum 0.1, eps 1e-5: `get_norm(..., 'batch')`, the default
+    norm of the reference's UNet / Encoder / Decoder signatures) on the InstanceNorm kernels: the batch statistics
+    are the per-sample sums pooled over the batch (Fn._bn_stats), so forward and backward reuse the fused
+    norm + activation + residual kernels.  Same parameters and buffers as torch's (state_dict compatible)."""
+    smsut_batch_norm = True
+
+    def __init__(self, num_features, **kw):
+        super().__init__(num_features, **kw)
+        if not self.affine or abs(self.eps - 1e-5) > 1e-12:
+            raise NotImplementedError("the kernels implement BatchNorm2d(affine=True, eps=1e-5)")
+
+    def forward(self, x):
+        xin = to_nhwc(x)
+        cp = self.num_features if xin.shape[3] != self.num_features else None
+        return to_nchw(Fn.in_act(xin, self, act=ACT_NONE, c_params=cp))
+
+
 class LeakyReLU(nn.LeakyReLU):
     def forward(self, x):
         return to_nchw(_LReluFn.apply(to_nhwc(x), _act_code(self)))
@@ -171,8 +189,7 @@ def get_norm(channels, norm_type):
     if norm_type == 'instance':
         return InstanceNorm2d(channels, affine=True)
     elif norm_type == 'batch':
-        raise NotImplementedError("norm_type='batch' is not on the SMSUT hot path (every trainer passes 'instance'); "
-                                  "there is deliberately no PyTorch fallback")
+        return BatchNorm2d(channels)
     else:
         raise NotImplementedError
 

@@ -594,16 +594,40 @@ def in_apply(xa, sa, ga, ba, xb=None, sb=None, gb=None, bb=None, res=None, act=A
     return out
 
 
+def bn_pool(rows):
+    """(n, k, c) fp32 table -> the same shape with every row = the mean over n (BatchNorm = pooled InstanceNorm sums)"""
+    n, k, c = _chk(rows, F32, "bn_pool rows").shape
+    out = torch.empty_like(rows)
+    call("smsut_bn_pool", _p(rows), _p(out), n, k, c, _stream())
+    return out
+
+
+def bn_running_update(pooled, hw, running_mean, running_var, momentum):
+    n, _, c = pooled.shape
+    call("smsut_bn_running_update", _p(pooled), n, hw, c, running_mean.numel(), float(momentum),
+         _p(_chk(running_mean, F32, "running_mean")), _p(_chk(running_var, F32, "running_var")), _stream())
+
+
+def bn_eval_stats(running_mean, running_var, n, hw, c):
+    stats = torch.empty((n, 2, c), dtype=F32, device=running_mean.device)
+    call("smsut_bn_eval_stats", _p(_chk(running_mean, F32, "running_mean")), _p(_chk(running_var, F32, "running_var")),
+         _p(stats), n, hw, c, running_mean.numel(), _stream())
+    return stats
+
+
 def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=ACT_NONE, slope=0.01, c_params=None,
-           targets=None):
+           targets=None, batch=False):
     """returns dxa, dgamma_a, dbeta_a, dxb, dgamma_b, dbeta_b, dres.  `targets` = (dga, dba, dgb, dbb) fp32 tensors the
-    parameter gradients are accumulated INTO (the flat .grad views); they are then returned as None."""
+    parameter gradients are accumulated INTO (the flat .grad views); they are then returned as None.
+    batch: BatchNorm -- the reductions are pooled over the samples between the two passes."""
     n, h, w, c = xa.shape
     cp = c if c_params is None else c_params
     dev = xa.device
     red = zeros((n, 3, c), dev)
     call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(xb), _p(sb), _p(red), n, h * w, c, act, slope,
          _stream())
+    if batch:
+        call("smsut_bn_pool", _p(red), _p(red), n, 3, c, _stream())
     dxa = torch.empty_like(xa)
     dxb = torch.empty_like(xa) if xb is not None else None
     dres = torch.empty_like(xa) if want_res else None

@@ -189,27 +189,47 @@ def in_apply(xa, sa, ga, ba, xb=None, sb=None, gb=None, bb=None, res=None, act=0
     return _act(o, act, slope).to(_AD.t)
 
 
-def _in_bwd_one(g, x, stats, gamma, c):
+def _in_bwd_one(g, x, stats, gamma, c, batch=False):
     hw = x.shape[1] * x.shape[2]
     m, r = _mean_rstd(stats, hw)
     xh = (x.float() - m) * r
-    mg = g.mean((1, 2), keepdim=True)
-    mgx = (g * xh).mean((1, 2), keepdim=True)
+    dims = (0, 1, 2) if batch else (1, 2)     # BatchNorm: the two reductions are pooled over the samples as well
+    mg = g.mean(dims, keepdim=True)
+    mgx = (g * xh).mean(dims, keepdim=True)
     dx = _gam(gamma, c) * r * (g - mg - xh * mgx)
     return dx, (g * xh).sum((0, 1, 2)), g.sum((0, 1, 2))
 
 
+def bn_pool(rows):
+    return rows.mean(0, keepdim=True).expand_as(rows).contiguous()
+
+
+def bn_running_update(pooled, hw, running_mean, running_var, momentum):
+    n, _, c = pooled.shape
+    cp = running_mean.numel()
+    m = pooled[0, 0, :cp] / hw
+    var = (pooled[0, 1, :cp] / hw - m * m).clamp_min(0)
+    count = n * hw
+    running_mean.mul_(1 - momentum).add_(momentum * m)
+    running_var.mul_(1 - momentum).add_(momentum * var * (count / (count - 1) if count > 1 else 1.0))
+
+
+def bn_eval_stats(running_mean, running_var, n, hw, c):
+    m, v = _pad_c(running_mean.float(), c), _pad_c(running_var.float(), c)
+    return torch.stack([m * hw, (v + m * m) * hw], 0)[None].expand(n, 2, c).contiguous()
+
+
 def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=0, slope=0.01, c_params=None,
-           targets=None):
+           targets=None, batch=False):
     c = xa.shape[3]
     cp = c if c_params is None else c_params
     g = dout.float()
     if act != 0:
         g = g * _act_grad(out.float(), act, slope)
-    dxa, dga, dba = _in_bwd_one(g, xa, sa, ga, c)
+    dxa, dga, dba = _in_bwd_one(g, xa, sa, ga, c, batch)
     dxb = dgb = dbb = None
     if xb is not None:
-        dxb, dgb, dbb = _in_bwd_one(g, xb, sb, gb, c)
+        dxb, dgb, dbb = _in_bwd_one(g, xb, sb, gb, c, batch)
         dxb, dgb, dbb = dxb.to(_AD.t), dgb[:cp].clone(), dbb[:cp].clone()
     dres = g.to(_AD.t) if want_res else None
     if targets is not None:

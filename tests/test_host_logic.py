@@ -198,3 +198,41 @@ def test_mean_teacher_steps_match_oracle(exact):
             assert rel(p, sd[k]) < 1e-3, (it, k)
         for k, p in tr.ema.named_parameters():
             assert rel(p, ema[k]) < 1e-3, (it, k)
+
+
+def test_unet_batchnorm_relu_matches_oracle(exact):
+    """get_norm('batch') / get_act('relu') (the UNet signature's defaults, network/unet.py:14): training passes with
+    running-estimate updates, then eval; state_dict carries nn.BatchNorm2d's buffers."""
+    from smsut_b200.misc.loss import DiceAndCrossEntropyLoss
+    from smsut_b200.network.unet import UNet
+    net = UNet(1, 5, 16)
+    sd = O.add_bn_buffers(O.make_weights(O.unet_shapes(), 11))
+    assert set(net.state_dict()) == set(sd)
+    net.load_state_dict(sd)
+    ref_sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+              for k, v in sd.items()}
+    crit = DiceAndCrossEntropyLoss(0.5, 0.5, batch_dice=True)
+    net.train()
+    for seed in (21, 22):
+        x, y = O.synthetic_batch(2, 48, seed)
+        net.zero_grad()
+        for v in ref_sd.values():
+            v.grad = None
+        out = net(x)
+        ref = O.unet_forward(ref_sd, x, style=O.Style("batch", "relu", training=True))
+        assert rel(out, ref) < 1e-5
+        crit(out, y).backward()
+        O.dice_ce_loss(ref, y).backward()
+        for k, p in net.named_parameters():
+            assert rel(p.grad, ref_sd[k].grad) < 2e-4, k
+    for k, v in net.state_dict().items():
+        if "running" in k:
+            assert rel(v, ref_sd[k]) < 1e-5, k
+        if "num_batches" in k:
+            assert int(v) == 2
+    net.eval()
+    x, _ = O.synthetic_batch(2, 48, 23)
+    with torch.no_grad():
+        out = net(x)
+    ref = O.unet_forward(ref_sd, x, style=O.Style("batch", "relu", training=False))
+    assert rel(out, ref) < 1e-5

@@ -245,6 +245,45 @@ def test_instance_norm_fwd_bwd(ops, c, h, n):
         assert rel(g_, l_.grad) < 2e-2
 
 
+@pytest.mark.parametrize("c,cp,h,n", [(16, 16, 64, 3), (16, 8, 32, 4), (128, 128, 16, 5)])
+def test_batch_norm_on_pooled_statistics(ops, c, cp, h, n):
+    """nn.BatchNorm2d (training: batch statistics + running-estimate update; eval: running estimates) from the
+    InstanceNorm kernels + smsut_bn_pool / smsut_bn_running_update / smsut_bn_eval_stats.  cp < c: the stem's
+    8 channels in a 16-channel tensor."""
+    torch.manual_seed(16)
+    x = rnd(n, cp, h, h) * 1.7 + 0.4
+    x[1] *= 2.5                                     # samples with different statistics
+    x = bf(x).float()
+    xp = F.pad(x, (0, 0, 0, 0, 0, c - cp))
+    g, b = torch.randn(cp, device=DEV), torch.randn(cp, device=DEV)
+    bn = torch.nn.BatchNorm2d(cp).to(DEV)
+    with torch.no_grad():
+        bn.weight.copy_(g); bn.bias.copy_(b)
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    a = nhwc(xp)
+    pooled = ops.bn_pool(ops.in_stats(a))
+    assert torch.equal(pooled[0], pooled[n - 1])
+    ops.bn_running_update(pooled, h * h, rm, rv, 0.1)
+    out = ops.in_apply(a, pooled, g, b, act=ops.ACT_RELU, c_params=cp if cp != c else None)
+    xr = x.clone().requires_grad_(True)
+    ref = F.relu(bn(xr))
+    assert rel(nchw(out)[:, :cp], ref) < 1e-2
+    assert nchw(out)[:, cp:].abs().max().item() == 0 if cp < c else True
+    assert rel(rm, bn.running_mean) < 1e-4 and rel(rv, bn.running_var) < 1e-4
+    dout = rnd(n, cp, h, h)
+    ref.backward(dout)
+    dxa, dga, dba, *_ = ops.in_bwd(nhwc(F.pad(dout, (0, 0, 0, 0, 0, c - cp))), out, a, pooled, g, act=ops.ACT_RELU,
+                                   c_params=cp if cp != c else None, batch=True)
+    assert rel(nchw(dxa)[:, :cp], xr.grad) < 2e-2
+    assert rel(dga, bn.weight.grad) < 2e-2 and rel(dba, bn.bias.grad) < 2e-2
+    # eval mode
+    bn.eval()
+    st = ops.bn_eval_stats(bn.running_mean, bn.running_var, n, h * h, c)
+    out_e = ops.in_apply(a, st, g, b, act=ops.ACT_NONE, c_params=cp if cp != c else None)
+    assert rel(nchw(out_e)[:, :cp], bn(x)) < 1e-2
+
+
 @pytest.mark.parametrize("c,h,n", [(16, 32, 2), (64, 16, 3)])
 def test_instance_norm_double_backward(ops, c, h, n):
     torch.manual_seed(7)

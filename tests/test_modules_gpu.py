@@ -119,6 +119,51 @@ def test_unet_parity(pkg, size, n):
     assert cos_fp32 > 0.9 and cos_emu > 0.93, (cos_fp32, cos_emu)
 
 
+def test_unet_batchnorm_relu_parity(pkg):
+    """UNet with the signature's default norm / activation (network/unet.py:14: BatchNorm2d + ReLU): two training
+    steps' worth of forward / backward (running estimates move twice), then an eval forward, vs the fp32 oracle."""
+    from smsut_b200.misc.loss import DiceAndCrossEntropyLoss
+    from smsut_b200.network.unet import UNet
+    sd = to_dev(O.add_bn_buffers(O.make_weights(O.unet_shapes(), 11)))
+    net = UNet(1, 5, 16).to(DEV)
+    net.load_state_dict(sd)
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+            for k, v in sd.items()}
+    crit = DiceAndCrossEntropyLoss(0.5, 0.5, batch_dice=True)
+    rep = {}
+    net.train()
+    for it, seed in enumerate((21, 22)):
+        x, y = O.synthetic_batch(4, 128, seed, device=DEV)
+        net.zero_grad()
+        for v in leaf.values():
+            v.grad = None
+        out = net(x)
+        ref = O.unet_forward(leaf, x, style=O.Style("batch", "relu", training=True))
+        loss, lref = crit(out, y), O.dice_ce_loss(ref, y)
+        loss.backward()
+        lref.backward()
+        g = grad_report(net.named_parameters(), {k: v.grad for k, v in leaf.items()})
+        cos = cosine(list(net.named_parameters()), {k: v.grad for k, v in leaf.items()})
+        rep[f"train{it}"] = dict(logits_rel=rel(out, ref), loss=loss.item(), loss_ref=lref.item(), grads=g, grad_cosine=cos)
+        assert rel(out, ref) < 3e-2
+        assert abs(loss.item() - lref.item()) < 1e-2 * abs(lref.item())
+        gv = sorted(g.values())
+        assert gv[len(gv) // 2] < 0.25 and cos > 0.9, (gv[len(gv) // 2], cos)
+    bufs = {k: rel(v, leaf[k]) for k, v in net.state_dict().items() if "running" in k}
+    rep["running_estimates_rel_max"] = max(bufs.values())
+    assert max(bufs.values()) < 2e-2, max(bufs, key=bufs.get)
+    assert all(int(v) == 2 for k, v in net.state_dict().items() if "num_batches" in k)
+    net.eval()
+    x, _ = O.synthetic_batch(4, 128, 23, device=DEV)
+    with torch.no_grad():
+        out = net(x)
+    ref = O.unet_forward(leaf, x, style=O.Style("batch", "relu", training=False)).detach()
+    mask = margin_mask(ref)
+    rep["eval"] = dict(logits_rel=rel(out, ref), argmax_agree_on_margin=(out.argmax(1) == ref.argmax(1))[mask].float().mean().item())
+    report("unet_batchnorm", rep)
+    assert rep["eval"]["logits_rel"] < 3e-2 and rep["eval"]["argmax_agree_on_margin"] > 0.995
+
+
 def test_ugannce_parity(pkg):
     from smsut_b200.network.ugan import UGANnce
     sd = to_dev(O.make_weights(O.ugan_shapes(), 4))

@@ -129,3 +129,30 @@ def test_schedules_and_helpers():
     img, lab = O.synthetic_batch(2, 64, 0)
     assert img.shape == (2, 1, 64, 64) and img.min() >= -1 and img.max() <= 1 and set(lab.unique().tolist()) <= {0, 1, 2, 3, 4}
     assert 0.5 < (lab == 0).float().mean() < 0.95
+
+
+def test_unet_batchnorm_relu_matches_reference_fixture():
+    """UNet's default norm / activation (network/unet.py:14: batch norm + ReLU): two training passes (running
+    estimates updated twice) and an eval pass against the real reference's outputs."""
+    f = load("unet_bn")
+    sd = leaf(O.make_weights(O.unet_shapes(), 11))
+    sd = O.add_bn_buffers(sd)
+    st = O.Style("batch", "relu", training=True)
+    for it, seed in enumerate((21, 22)):
+        x, y = O.synthetic_batch(2, 48, seed)
+        for v in sd.values():
+            v.grad = None
+        out = O.unet_forward(sd, x, style=st)
+        assert close(out.detach(), f[f"logits{it}"], 1e-5)
+        loss = O.dice_ce_loss(out, y)
+        assert abs(loss.item() - float(f[f"loss{it}"])) < 1e-6
+        loss.backward()
+        check_grad_norms(f, f"gn{it}.", {k: v for k, v in sd.items() if v.requires_grad})
+    assert close(sd["decoder.fc.weight"].grad, f["fc_grad"]) and close(sd["encoder.pre_conv.weight"].grad, f["pre_grad"])
+    bufs = [k for k in f if k.startswith("buf.")]
+    assert len(bufs) == 2 * 28
+    for k in bufs:
+        assert close(sd[k[4:]], f[k], 1e-5), k
+    x, _ = O.synthetic_batch(2, 48, 23)
+    out = O.unet_forward(sd, x, style=O.Style("batch", "relu", training=False))
+    assert close(out.detach(), f["logits_eval"], 1e-5)
