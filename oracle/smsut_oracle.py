@@ -508,3 +508,62 @@ def mean_teacher_step(sd, ema, opt_state, x, y, noise, lr, it, lambda_semi, warm
     sgd_update(sd, grads, opt_state, lr)
     ema_update(ema, sd, ema_alpha(it, warm=warm))
     return float(seg.detach()), float(semi.detach())
+
+
+def cross_pse_step(sd1, sd2, st1, st2, x, y, lr, lambda_semi):
+    """trainer/crossPseTrainer.py:96-131 (cross pseudo supervision): two U-Nets on the same 2*bs slices; Dice+CE of
+    each on the labelled half, plus lambda * Dice+CE of each net's unlabelled-half logits against the OTHER net's
+    argmax; one backward, two SGD steps.  Updates both nets in place; returns the four losses and both grad dicts."""
+    bs = y.shape[0]
+    l1, l2 = _leaf(sd1), _leaf(sd2)
+    out1, out2 = unet_forward(l1, x), unet_forward(l2, x)
+    s1, s2 = dice_ce_loss(out1[:bs], y), dice_ce_loss(out2[:bs], y)
+    pred1, pred2 = torch.argmax(out1[bs:], 1).detach(), torch.argmax(out2[bs:], 1).detach()
+    c1, c2 = dice_ce_loss(out1[bs:], pred2), dice_ce_loss(out2[bs:], pred1)
+    total = s1 + s2 + lambda_semi * c1 + lambda_semi * c2
+    gs = torch.autograd.grad(total, list(l1.values()) + list(l2.values()))
+    g1, g2 = dict(zip(l1, gs[:len(l1)])), dict(zip(l2, gs[len(l1):]))
+    sgd_update(sd1, g1, st1, lr)
+    sgd_update(sd2, g2, st2, lr)
+    return dict(seg1=float(s1.detach()), seg2=float(s2.detach()), semi1=float(c1.detach()), semi2=float(c2.detach())), g1, g2
+
+
+def ugan_shape_step(G, D, g_state, d_state, x_real, y_real, modal_org, mj, alpha, lr, lambda_shp=None,
+                    lambdas=(1.0, 10.0, 10.0, 10.0)):
+    """One iteration (n_critic = 1) of UGANTrainer.train_epoch (trainer/uganTrainer.py:159-196: labelled slices only,
+    `UGAN` generator without the PatchNCE head, shape loss Dice+CE(y_rec, y_real) weighted lambda_shp) or, with
+    lambda_shp=None, of UGANShp0Trainer.train_epoch (trainer/uganShp0Trainer.py:180-217, the same without the
+    shape term).  Draws (target modality, alpha) injected.  Updates G, D and both optimiser states in place."""
+    lambda_cls, lambda_rec, lambda_gp, lambda_seg = lambdas
+    dev = x_real.device
+    n_modal = D["conv_cls.weight"].shape[0]
+    modal_trg, vec_ot, vec_to = _modal_vectors(modal_org, mj, n_modal, dev)
+    Dl = _leaf(D)
+    out_src, out_cls = discriminator_forward(Dl, x_real)
+    d_real, d_cls = -out_src.mean(), F.cross_entropy(out_cls, modal_org)
+    with torch.no_grad():
+        _, x_fake0 = ugannce_forward(G, x_real, vec_ot, val_phase=True)
+    d_fake = discriminator_forward(Dl, x_fake0)[0].mean()
+    x_hat = (alpha * x_real + (1 - alpha) * x_fake0).requires_grad_(True)
+    d_gp = gradient_penalty(discriminator_forward(Dl, x_hat)[0], x_hat)
+    d_loss = d_real + d_fake + lambda_cls * d_cls + lambda_gp * d_gp
+    d_grads = dict(zip(Dl, torch.autograd.grad(d_loss, list(Dl.values()))))
+    adam_update(D, d_grads, d_state, lr)
+
+    Gl = _leaf(G)
+    y_fake, x_fake = ugannce_forward(Gl, x_real, vec_ot, val_phase=True)
+    out_src, out_cls = discriminator_forward(D, x_fake)
+    g_fake, g_cls = -out_src.mean(), F.cross_entropy(out_cls, modal_trg)
+    g_seg = dice_ce_loss(y_fake, y_real)
+    y_rec, x_rec = ugannce_forward(Gl, x_fake, vec_to, val_phase=True)
+    g_rec = (x_real - x_rec).abs().mean()
+    g_loss = g_fake + lambda_rec * g_rec + lambda_cls * g_cls + lambda_seg * g_seg
+    losses = dict(D_real=d_real, D_fake=d_fake, D_cls=d_cls, D_gp=d_gp, G_fake=g_fake, G_rec=g_rec, G_cls=g_cls, G_seg=g_seg)
+    if lambda_shp is not None:
+        g_shp = dice_ce_loss(y_rec, y_real)
+        g_loss = g_loss + lambda_shp * g_shp
+        losses["G_shp"] = g_shp
+    used = {k: v for k, v in Gl.items() if not k.startswith("netF.")}
+    g_grads = dict(zip(used, torch.autograd.grad(g_loss, list(used.values()))))
+    sgd_update({k: G[k] for k in used}, g_grads, g_state, lr)
+    return {k: float(v.detach()) for k, v in losses.items()}, d_grads, g_grads

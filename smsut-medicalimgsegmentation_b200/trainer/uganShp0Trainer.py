@@ -1,8 +1,11 @@
 # -*- coding: utf-8 -*-
 """Counterpart of the reference's trainer/uganShp0Trainer.py: hyper-parameters (:37-50), build_network (:52-74),
 G/D checkpoints (:76-107), label2onehot / create_vectors (:109-120), denorm (:122-125), gradient_penalty
-(:127-134) and the device-side validate path (:250-287)."""
+(:127-134), the labelled-only GAN iteration (:136-235; shared with trainer/uganTrainer.py, which adds the shape
+loss) and the device-side validate path (:250-287)."""
 import os
+import random
+import time
 from os.path import join as pjoin
 
 import numpy as np
@@ -11,6 +14,8 @@ import torch.nn as nn
 
 from .. import config as cfg
 from .. import functional as Fn
+from .. import ops
+from ..network.blocks import refresh_packs
 from ..network.patchnce import PatchNCELoss
 from ..network.ugan import Discriminator, UGANnce
 from ..optim import SGD, Adam, PolyLR
@@ -99,3 +104,122 @@ class UGANShp0Trainer(BaseTrainer):
     def segment(self, img):
         seg, _ = self.net(img, val_phase=True)
         return seg
+
+    def translate(self, x, m):
+        """(seg, tsl) of the generator.  The reference's own loop unpacks two values from UGANnce.forward, which
+        returns four outside val_phase (network/ugan.py:195), so uganShp0Trainer.py:180 can only ever have run with
+        the two-output form: that is what is computed here."""
+        return self.net(x, m, val_phase=True)
+
+    SHP_LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_shp')
+
+    def shape_train_step(self, x_real, y_real, modal_org, modal_trg, vec_ot, vec_to, alpha, lambda_shp=None):
+        """One iteration (n_critic = 1) of uganShp0Trainer.py:162-217 on labelled device tensors, or, with
+        `lambda_shp` (host float or device scalar), of uganTrainer.py:141-196 whose G loss adds
+        lambda_shp * Dice+CE(y_rec, y_real).  As in UGANConsisTrainer.train_step, one generator forward serves the D
+        phase (detached) and the G phase, the cycle pass runs on a branch stream beside the D phase, and D's weight
+        gradients are not computed in the G phase.  Returns the losses ordered like SHP_LOSS_KEYS (G_shp = 0 without
+        the shape term) as one device vector."""
+        lambda_cls, lambda_gp = self.lambda_cls, self.lambda_gp
+        lambda_seg, lambda_rec = self.lambda_seg, self.lambda_rec
+        ops.arena_begin(x_real.device)
+        self.lr_sched.tick()
+        y_fake, x_fake = self.translate(x_real, vec_ot)
+        if isinstance(lambda_shp, torch.Tensor):
+            lambda_shp = lambda_shp.reshape(())
+        with ops.parallel_branch(4) as b_cyc:
+            g_loss_seg = self.loss(y_fake, y_real)
+            y_rec, x_rec = self.translate(x_fake, vec_to)
+            g_loss_rec = Fn.L1MeanFn.apply(x_rec.contiguous(), x_real)
+            g_partial = lambda_rec * g_loss_rec + lambda_seg * g_loss_seg
+            if lambda_shp is not None:
+                g_loss_shp = self.loss(y_rec, y_real)
+                g_partial = g_partial + lambda_shp * g_loss_shp
+            else:
+                g_loss_shp = torch.zeros((), device=x_real.device)
+
+        x_fake_d = x_fake.detach()
+        refresh_packs(self.D)
+        with ops.parallel_branch(1) as b_fake:
+            out_src_f, _ = self.D(x_fake_d)
+            d_loss_fake = Fn.MeanFn.apply(out_src_f, 1.0)
+        with ops.parallel_branch(2) as b_hat:
+            x_hat = ops.lerp_rows(alpha, x_real, x_fake_d.contiguous()).requires_grad_(True)
+            out_src_h, _ = self.D(x_hat)
+            d_loss_gp = self.gradient_penalty(out_src_h, x_hat)
+        out_src, out_cls = self.D(x_real)
+        d_loss_real = Fn.MeanFn.apply(out_src, -1.0)
+        d_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_org)
+        b_fake.join(d_loss_fake)
+        b_hat.join(d_loss_gp)
+        d_loss = d_loss_real + d_loss_fake + lambda_cls * d_loss_cls + lambda_gp * d_loss_gp
+        self.d_optimizer.zero_grad()
+        with Fn.accumulate_param_grads():
+            d_loss.backward()
+        if getattr(self, 'parallel', None) is not None:
+            self.parallel.all_reduce_grads(self.d_optimizer)
+        self.d_optimizer.step()
+
+        for p in self.d_optimizer.params:
+            p.requires_grad_(False)
+        out_src, out_cls = self.D(x_fake)
+        for p in self.d_optimizer.params:
+            p.requires_grad_(True)
+        g_loss_fake = Fn.MeanFn.apply(out_src, -1.0)
+        g_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_trg)
+        b_cyc.join(g_partial, g_loss_seg, g_loss_rec, g_loss_shp)
+        g_loss = g_loss_fake + lambda_cls * g_loss_cls + g_partial
+        self.optimizer.zero_grad()
+        with Fn.accumulate_param_grads():
+            g_loss.backward()
+        if getattr(self, 'parallel', None) is not None:
+            self.parallel.all_reduce_grads(self.optimizer)
+        self.optimizer.step()
+        ops.arena_end()
+        return torch.stack([d_loss_real.detach(), d_loss_fake.detach(), d_loss_cls.detach(), d_loss_gp.detach(),
+                            g_loss_fake.detach(), g_loss_rec.detach(), g_loss_cls.detach(), g_loss_seg.detach(),
+                            g_loss_shp.detach()])
+
+    def epoch_lambda_shp(self):
+        return None                     # uganShp0Trainer: no shape term
+
+    def train_epoch(self, lb_loader, ul_loader, meter, num_iter=None):
+        """uganShp0Trainer.py:136-235 / uganTrainer.py:115-215: labelled slices only, one target modality per
+        iteration (random.randint), alpha ~ N(0,1) per slice."""
+        self.net.train()
+        self.D.train()
+        lambda_shp = self.epoch_lambda_shp()
+        print(f'\nlambda_seg: {self.lambda_seg}' + ('.' if lambda_shp is None else f', lambda_shp: {lambda_shp}.'))
+        itr = iter(lb_loader)
+        tic = time.time()
+        losses = None
+        for i in range(self.n_critic * (num_iter or cfg.num_iter_per_epoch)):
+            try:
+                x_real, y_real, modal_org, _ = next(itr)
+            except StopIteration:
+                itr = iter(lb_loader)
+                x_real, y_real, modal_org, _ = next(itr)
+            mj = random.randint(0, cfg.n_modal - 1)
+            modal_trg = torch.zeros_like(modal_org).fill_(mj)
+            vec_org = self.label2onehot(modal_org, cfg.n_modal)
+            vec_trg = self.label2onehot(modal_trg, cfg.n_modal)
+            dev = self.device
+            alpha = torch.randn(x_real.size(0), device=dev)
+            losses = self.shape_train_step(x_real.to(dev, non_blocking=True), y_real.to(dev, non_blocking=True),
+                                           modal_org.to(dev), modal_trg.to(dev), (vec_trg - vec_org).to(dev),
+                                           (vec_org - vec_trg).to(dev), alpha, lambda_shp)
+            if (i + 1) % (self.n_critic * self.log_step) == 0:
+                log = 'Iter: %d/%d(%d), elapsed: %.2fs,' % (i, self.n_critic * cfg.num_iter_per_epoch, self.iter,
+                                                            time.time() - tic)
+                tic = time.time()
+                for k, v in zip(self.SHP_LOSS_KEYS, losses.tolist()):
+                    if k != 'G_shp' or lambda_shp is not None:
+                        log += ' %s: %.4f,' % (k, v)
+                print(log, flush=True)
+            lr_ = self.lr_sched.host_lr(self.iter + 1)
+            for opt in (self.optimizer, self.d_optimizer):
+                for param_group in opt.param_groups:
+                    param_group['lr'] = lr_
+                opt._lr_host = lr_
+            self.iter += 1
+        return losses

@@ -236,3 +236,69 @@ def test_unet_batchnorm_relu_matches_oracle(exact):
         out = net(x)
     ref = O.unet_forward(ref_sd, x, style=O.Style("batch", "relu", training=False))
     assert rel(out, ref) < 1e-5
+
+
+def test_cross_pse_trainer_steps_match_oracle(exact):
+    """crossPseTrainer: two networks, cross pseudo-labels through the fused loss's argmax"""
+    from types import SimpleNamespace
+    from smsut_b200.trainer.crossPseTrainer import crossPseTrainer
+    tr = crossPseTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=64))
+    sd1, sd2 = O.make_weights(O.unet_shapes(), 31), O.make_weights(O.unet_shapes(), 32)
+    tr.net.load_state_dict(sd1)
+    tr.net2.load_state_dict(sd2)
+    st1, st2 = {}, {}
+    for it in range(3):
+        x1, y = O.synthetic_batch(2, 64, 41 + it)
+        x2, _ = O.synthetic_batch(2, 64, 51 + it)
+        x = torch.cat([x1, x2])
+        got = tr.train_step(x, y, 0.05).tolist()
+        ref, _, _ = O.cross_pse_step(sd1, sd2, st1, st2, x, y, O.poly_lr(1e-2, max(it - 1, 0), 30000), 0.05)
+        for v, k in zip(got, ("seg1", "seg2", "semi1", "semi2")):
+            # the cross losses see argmax pseudo-labels: after an update, rounding-level weight differences flip
+            # the label of the odd near-tied pixel, which moves the loss by more than rounding error
+            tol = 1e-4 if it == 0 or k.startswith("seg") else 2e-3
+            assert abs(v - ref[k]) < tol * max(1.0, abs(ref[k])), (it, k, v, ref[k])
+        for net, sd in ((tr.net, sd1), (tr.net2, sd2)):
+            for k, p in net.named_parameters():
+                assert rel(p, sd[k]) < 1e-3, (it, k)
+
+
+@pytest.mark.parametrize("lambda_shp", [3.5, None])
+def test_ugan_shape_trainer_step_matches_oracle(exact, lambda_shp):
+    """UGANTrainer (shape loss) / the UGANShp0Trainer iteration on the `UGAN` generator, teacher-forced across D's Adam
+    step like test_full_ugan_consis_step_matches_oracle."""
+    from types import SimpleNamespace
+    from smsut_b200.trainer.uganTrainer import UGANTrainer
+    size = 64
+    tr = UGANTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=size))
+    shapes = {k: v for k, v in O.ugan_shapes().items() if not k.startswith("netF.")}
+    G, D = O.make_weights(shapes, 61), O.make_weights(O.disc_shapes(size), 62)
+    assert set(tr.net.state_dict()) == set(G)
+    tr.net.load_state_dict(G)
+    tr.D.load_state_dict(D)
+    x, y = O.synthetic_batch(3, size, 63)
+    modal_org, mj = torch.full((3,), 1), 3
+    modal_trg = torch.full_like(modal_org, mj)
+    vo, vt = tr.label2onehot(modal_org, 4), tr.label2onehot(modal_trg, 4)
+    alpha = torch.randn(3, generator=torch.Generator().manual_seed(64))
+    got = tr.shape_train_step(x, y, modal_org, modal_trg, vt - vo, vo - vt, alpha, lambda_shp).tolist()
+    # the oracle's D phase from the same start ...
+    D0 = {k: v.clone() for k, v in D.items()}
+    G0 = {k: v.clone() for k, v in G.items()}
+    ref, d_grads, _ = O.ugan_shape_step(G0, D0, {}, {}, x, y, modal_org, mj, alpha.view(-1, 1, 1, 1), 1e-2, lambda_shp)
+    for k, p in tr.D.named_parameters():
+        assert rel(p.grad, d_grads[k]) < 3e-3, k     # dominated by the double backward of a GP term of O(1e3)
+    for v, k in list(zip(got, tr.SHP_LOSS_KEYS))[:4]:
+        assert abs(v - ref[k]) < 2e-4 * max(1.0, abs(ref[k])), (k, v, ref[k])
+    # ... and its G phase against the trainer's updated discriminator (teacher forcing)
+    import unittest.mock as um
+    Dt = {k: v.detach().clone() for k, v in tr.D.state_dict().items()}
+    with um.patch.object(O, "adam_update", lambda *a, **k: None):
+        ref2, _, g_grads = O.ugan_shape_step(G, Dt, {}, {}, x, y, modal_org, mj, alpha.view(-1, 1, 1, 1), 1e-2, lambda_shp)
+    for v, k in list(zip(got, tr.SHP_LOSS_KEYS))[4:]:
+        if k in ref2:
+            assert abs(v - ref2[k]) < 2e-4 * max(1.0, abs(ref2[k])), (k, v, ref2[k])
+    assert ("G_shp" in ref2) == (lambda_shp is not None)
+    for k, p in tr.net.named_parameters():
+        assert rel(p.grad, g_grads[k]) < 8e-2, k
+        assert rel(p, G[k]) < 8e-2, k

@@ -156,3 +156,49 @@ def test_unet_batchnorm_relu_matches_reference_fixture():
     x, _ = O.synthetic_batch(2, 48, 23)
     out = O.unet_forward(sd, x, style=O.Style("batch", "relu", training=False))
     assert close(out.detach(), f["logits_eval"], 1e-5)
+
+
+def _norms(f, prefix):
+    return dict(zip(str(f[prefix + "names"]).split(","), f[prefix + "norms"].tolist()))
+
+
+def test_cross_pseudo_supervision_steps_match_reference_fixture():
+    """two consecutive crossPseTrainer iterations (trainer/crossPseTrainer.py:96-131) with SGD momentum carried over"""
+    f = load("siblings")
+    sd1, sd2 = O.make_weights(O.unet_shapes(), 31), O.make_weights(O.unet_shapes(), 32)
+    st1, st2 = {}, {}
+    for it in range(2):
+        x1, y = O.synthetic_batch(2, 64, 41 + it)
+        x2, _ = O.synthetic_batch(2, 64, 51 + it)
+        losses, g1, g2 = O.cross_pse_step(sd1, sd2, st1, st2, torch.cat([x1, x2]), y, 1e-2, 0.05)
+        got = [losses[k] for k in ("seg1", "seg2", "semi1", "semi2")]
+        assert np.allclose(got, f[f"cps{it}.losses"], rtol=2e-4 if it == 0 else 2e-3, atol=1e-5), (it, got)
+        for g, name in ((g1, "g1"), (g2, "g2")):
+            for k, ref in _norms(f, f"cps{it}.{name}.").items():
+                assert abs(g[k].norm().item() - ref) < (1e-3 if it == 0 else 2e-2) * max(ref, 1e-3), (it, name, k)
+        for sd, name in ((sd1, "sum1"), (sd2, "sum2")):
+            s = np.array([v.double().sum().item() for v in sd.values()])
+            assert np.allclose(s, f[f"cps{it}.{name}"], rtol=1e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize("name,lambda_shp", [("shp", 3.5), ("shp0", None)])
+def test_ugan_shape_step_matches_reference_fixture(name, lambda_shp):
+    """one UGANTrainer iteration (trainer/uganTrainer.py:159-196, shape loss) / UGANShp0Trainer iteration
+    (trainer/uganShp0Trainer.py:180-217) on the reference's `UGAN` generator (no PatchNCE head)"""
+    f = load("siblings")
+    shapes = {k: v for k, v in O.ugan_shapes().items() if not k.startswith("netF.")}
+    G, D = O.make_weights(shapes, 61), O.make_weights(O.disc_shapes(64), 62)
+    x, y = O.synthetic_batch(3, 64, 63)
+    losses, d_grads, g_grads = O.ugan_shape_step(G, D, {}, {}, x, y, torch.full((3,), 1), 3,
+                                                 torch.as_tensor(f[f"{name}.alpha"]), 1e-2, lambda_shp=lambda_shp)
+    keys = ["D_real", "D_fake", "D_cls", "D_gp", "G_fake", "G_rec", "G_cls", "G_seg"] + (["G_shp"] if lambda_shp else [])
+    for k, ref in zip(keys, f[f"{name}.losses"]):
+        assert abs(losses[k] - ref) < 1e-4 * max(1.0, abs(ref)), (k, losses[k], ref)
+    for k, ref in _norms(f, f"{name}.dgn.").items():
+        assert abs(d_grads[k].norm().item() - ref) < 1e-3 * max(ref, 1e-3), k
+    for k, ref in _norms(f, f"{name}.ggn.").items():
+        assert abs(g_grads[k].norm().item() - ref) < 5e-2 * max(ref, 1e-3), k
+    gsum = np.array([v.double().sum().item() for v in G.values()])
+    assert np.allclose(gsum, f[f"{name}.G_checksum"], rtol=2e-2, atol=0.5)
+    dsum = np.array([v.double().sum().item() for v in D.values()])
+    assert np.abs(dsum - f[f"{name}.D_checksum"]).max() < 0.5      # Adam: lr * sign(g) on near-zero gradients
