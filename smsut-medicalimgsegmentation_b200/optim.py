@@ -78,8 +78,29 @@ class _FlatOptimizer:
             self.lr_dev.fill_(lr)
             self._lr_host = lr
 
+    # resume state (an extension: the reference saves weights only, trainer/uganShp0Trainer.py:94-107): the flat
+    # optimizer buffers in parameter order, copied in place so captured graphs keep their addresses
+    _STATE = ()
+
+    def state_dict(self):
+        sd = {k: getattr(self, k).detach().cpu().clone() for k in self._STATE}
+        sd['lr'] = float(self.lr_dev.item())
+        sd['numel'] = int(self.flat.numel())
+        return sd
+
+    def load_state_dict(self, sd):
+        if int(sd['numel']) != self.flat.numel():
+            raise ValueError(f"optimizer state holds {sd['numel']} elements, this network has {self.flat.numel()}")
+        with torch.no_grad():
+            for k in self._STATE:
+                getattr(self, k).copy_(sd[k])
+            self.lr_dev.fill_(float(sd['lr']))
+        self.param_groups[0]['lr'] = self._lr_host = float(sd['lr'])
+
 
 class SGD(_FlatOptimizer):
+    _STATE = ('mom',)
+
     def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
         super().__init__(params, lr)
         self.momentum, self.weight_decay = momentum, weight_decay
@@ -92,6 +113,8 @@ class SGD(_FlatOptimizer):
 
 
 class Adam(_FlatOptimizer):
+    _STATE = ('m', 'v', 'state')
+
     def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         super().__init__(params, lr)
         self.betas, self.eps, self.weight_decay = tuple(betas), eps, weight_decay
@@ -122,3 +145,10 @@ class PolyLR:
 
     def host_lr(self, it):
         return self.base * (1.0 - max(it - 1, 0) / self.max_iter) ** self.power
+
+    def state_dict(self):
+        return dict(iter_state=self.iter_state.detach().cpu().clone())
+
+    def load_state_dict(self, sd):
+        with torch.no_grad():
+            self.iter_state.copy_(sd['iter_state'])

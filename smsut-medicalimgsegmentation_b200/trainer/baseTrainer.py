@@ -65,6 +65,39 @@ class BaseTrainer(object):
         path = pjoin(self.expr_root, model_idx, 'ckpt', f'{which_ckpt}.ckpt')
         self.net.load_state_dict(torch.load(path, map_location='cpu'))
 
+    # ---- resume state: an extension.  The reference checkpoints weights only, so a
+    # restarted run loses SGD momentum, Adam moments, the LR schedule position and the EMA teacher.
+    def _stateful(self):
+        """name -> object with state_dict()/load_state_dict(): every network, optimizer and schedule the trainer owns"""
+        out = {}
+        for name, obj in vars(self).items():
+            if name in ('loss', 'parallel'):
+                continue
+            if hasattr(obj, 'state_dict') and hasattr(obj, 'load_state_dict'):
+                out[name] = obj
+        return out
+
+    def save_state(self, prefix='resume'):
+        path = pjoin(self.expr_root, self.model_idx, 'ckpt', f'{prefix}.state')
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        state = {k: ({n: t.detach().cpu() if isinstance(t, torch.Tensor) else t for n, t in o.state_dict().items()})
+                 for k, o in self._stateful().items()}
+        state['__counters__'] = dict(epoch=self.epoch, iter=self.iter)
+        torch.save(state, path)
+        self.info(f'Save training state to {path}.')
+        return path
+
+    def load_state(self, path):
+        state = torch.load(path, map_location='cpu')
+        objs = self._stateful()
+        missing = sorted(set(objs) - set(state))
+        if missing:
+            raise KeyError(f'training state {path} lacks {missing}')
+        for k, o in objs.items():
+            o.load_state_dict(state[k])
+        ops.param_generation[0] += 1        # master weights changed outside an optimizer step: refresh the bf16 packs
+        self.epoch, self.iter = state['__counters__']['epoch'], state['__counters__']['iter']
+
     def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None):
         train_lb_loader = synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size)
         train_ul_loader = synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size)

@@ -302,3 +302,40 @@ def test_ugan_shape_trainer_step_matches_oracle(exact, lambda_shp):
     for k, p in tr.net.named_parameters():
         assert rel(p.grad, g_grads[k]) < 8e-2, k
         assert rel(p, G[k]) < 8e-2, k
+
+
+def test_resume_state_round_trip(exact, tmp_path):
+    """save_state / load_state (extension): a fresh trainer restored from the state file
+    continues exactly like the original -- weights, EMA teacher, SGD momentum, LR-schedule position, counters."""
+    from types import SimpleNamespace
+    from smsut_b200.trainer.meanTeacherTrainer import MeanTeacherTrainer
+
+    def batch(it):
+        x1, y = O.synthetic_batch(2, 64, 40 + it)
+        x2, _ = O.synthetic_batch(2, 64, 50 + it)
+        noise = torch.clamp(torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(it)) * 0.01, -0.02, 0.02)
+        return torch.cat([x1, x2]), y, noise
+
+    def make():
+        tr = MeanTeacherTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=64))
+        tr.semi_from_iter = 1
+        tr.expr_root = str(tmp_path)
+        return tr
+
+    a = make()
+    a.net.load_state_dict(O.make_weights(O.unet_shapes(), 31))
+    a.ema.load_state_dict(O.make_weights(O.unet_shapes(), 32))
+    for it in range(2):
+        a.train_step(*batch(it), 0.8)
+    path = a.save_state()
+    want = a.train_step(*batch(2), 0.8)
+    b = make()                      # fresh random weights, zero momentum, schedule at 0
+    b.load_state(path)
+    assert b.iter == 2
+    got = b.train_step(*batch(2), 0.8)
+    assert torch.equal(got, want)
+    for (k, p), (_, q) in zip(a.net.named_parameters(), b.net.named_parameters()):
+        assert torch.equal(p, q), k
+    for (k, p), (_, q) in zip(a.ema.named_parameters(), b.ema.named_parameters()):
+        assert torch.equal(p, q), k
+    assert torch.equal(a.optimizer.mom, b.optimizer.mom) and torch.equal(a.lr_sched.iter_state, b.lr_sched.iter_state)
