@@ -134,17 +134,21 @@ int smsut_in_apply(const void* xa, const float* stats_a, const float* gamma_a, c
                    const void* xb, const float* stats_b, const float* gamma_b, const float* beta_b,
                    const void* res, void* out, int32_t n, int32_t hw, int32_t c, int32_t c_params, int32_t act,
                    float slope, smsut_stream_t stream);
-/* backward, pass 1: g = dout * act'(out);  red[n][c] = {sum g, sum g*xhat_a, sum g*xhat_b} (zeroed by caller) */
-int smsut_in_bwd_reduce(const void* dout, const void* out, const void* xa, const float* stats_a, const void* xb,
-                        const float* stats_b, float* red, int32_t n, int32_t hw, int32_t c, int32_t act, float slope,
-                        smsut_stream_t stream);
+/* backward, pass 1: g = dout * act'(out);  red[n][c] = {sum g, sum g*xhat_a, sum g*xhat_b} (zeroed by caller).
+ * out == NULL (with an activation): the sign of the activation's input is recomputed from xa / xb with the forward's
+ * own expression (gamma / beta of every branch required) instead of read from `out` -- valid whenever the forward
+ * had no residual input; saves one streamed tensor.  gamma / beta may be NULL otherwise. */
+int smsut_in_bwd_reduce(const void* dout, const void* out, const void* xa, const float* stats_a, const float* gamma_a,
+                        const float* beta_a, const void* xb, const float* stats_b, const float* gamma_b,
+                        const float* beta_b, float* red, int32_t n, int32_t hw, int32_t c, int32_t c_params,
+                        int32_t act, float slope, smsut_stream_t stream);
 /* backward, pass 2: dxa = gamma_a*rstd_a*(g - mean g - xhat_a*mean(g xhat_a)); same for b; dres = g (optional);
- * dgamma/dbeta accumulated (atomics) into fp32 parameter gradients */
+ * dgamma/dbeta accumulated (atomics) into fp32 parameter gradients.  out == NULL as above (beta_a / beta_b required). */
 int smsut_in_bwd_apply(const void* dout, const void* out, const void* xa, const float* stats_a, const float* gamma_a,
-                       void* dxa, float* dgamma_a, float* dbeta_a, const void* xb, const float* stats_b,
-                       const float* gamma_b, void* dxb, float* dgamma_b, float* dbeta_b, void* dres,
-                       const float* red, int32_t n, int32_t hw, int32_t c, int32_t c_params, int32_t act, float slope,
-                       smsut_stream_t stream);
+                       const float* beta_a, void* dxa, float* dgamma_a, float* dbeta_a, const void* xb,
+                       const float* stats_b, const float* gamma_b, const float* beta_b, void* dxb, float* dgamma_b,
+                       float* dbeta_b, void* dres, const float* red, int32_t n, int32_t hw, int32_t c,
+                       int32_t c_params, int32_t act, float slope, smsut_stream_t stream);
 /* double backward of InstanceNorm (WGAN-GP, trainer/uganShp0Trainer.py:127-134):
  * given u = cotangent of dx, with dx = IN_bwd(dy; x, gamma):
  *   pass 1: red2[n][c] = {sum u, sum dy, sum u*xhat, sum dy*xhat, sum u*dy}

@@ -29,7 +29,8 @@ def timed(fn):
     return ms / reps * 1e3
 
 
-print(f"{'level':>10} | stats  apply1 apply2  bwd1(red+app)  bwd2(red+app)   [us]   | GB/s: apply2 bwd2")
+print(f"{'level':>10} | stats  apply1 apply2  bwd1(red+app)  bwd2(red+app)  bwd1r  bwd2r [us]   | GB/s: apply2 bwd2 bwd2r"
+      "   (bwdNr: activation sign recomputed from x instead of read from out)")
 for h, c in ((256, 16), (128, 32), (64, 64), (32, 128), (16, 256)):
     x = torch.randn(16, h, h, c, device="cuda").to(torch.bfloat16)
     xb = torch.randn(16, h, h, c, device="cuda").to(torch.bfloat16)
@@ -44,5 +45,7 @@ for h, c in ((256, 16), (128, 32), (64, 64), (32, 128), (16, 256)):
     t_a2 = timed(lambda: ops.in_apply(x, st, ga, ba, xb, stb, ga, ba, act=ops.ACT_LRELU))
     t_b1 = timed(lambda: ops.in_bwd(d, out1, x, st, ga, act=ops.ACT_LRELU))
     t_b2 = timed(lambda: ops.in_bwd(d, out2, x, st, ga, xb, stb, ga, act=ops.ACT_LRELU))
-    print(f"{h:4d}x{c:<4d} | {t_s:6.1f} {t_a1:6.1f} {t_a2:6.1f} {t_b1:14.1f} {t_b2:14.1f}          | {3 * nb / t_a2 / 1e3:6.0f} {10 * nb / t_b2 / 1e3:6.0f}",
-          flush=True)
+    t_b1r = timed(lambda: ops.in_bwd(d, out1, x, st, ga, act=ops.ACT_LRELU, betas=(ba, None)))
+    t_b2r = timed(lambda: ops.in_bwd(d, out2, x, st, ga, xb, stb, ga, act=ops.ACT_LRELU, betas=(ba, ba)))
+    print(f"{h:4d}x{c:<4d} | {t_s:6.1f} {t_a1:6.1f} {t_a2:6.1f} {t_b1:14.1f} {t_b2:14.1f} {t_b1r:6.1f} {t_b2r:6.1f}       | "
+          f"{3 * nb / t_a2 / 1e3:6.0f} {10 * nb / t_b2 / 1e3:6.0f} {8 * nb / t_b2r / 1e3:6.0f}", flush=True)

@@ -73,8 +73,8 @@ _PROTOS = {
     "smsut_head1x1_bwd": [P, P, P, P, P, P, P, c_int64, c_int, c_int, P],
     "smsut_in_stats": [P, c_int, c_int, c_int, P, P],
     "smsut_in_apply": [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
-    "smsut_in_bwd_reduce": [P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_float, P],
-    "smsut_in_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
+    "smsut_in_bwd_reduce": [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
+    "smsut_in_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
                            c_float, P],
     "smsut_in_bwd2_reduce": [P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_in_bwd2_apply": [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P],

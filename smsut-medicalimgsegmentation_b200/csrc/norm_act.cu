@@ -97,6 +97,11 @@ __device__ __forceinline__ void load_mean_rstd(const float* stats, int n, int c,
   }
 }
 
+// shift of the folded affine form  y = x * (gamma * rstd) + in_shift(beta, mean, gamma * rstd).  One definition for
+// the forward and the backward kernels: the backward recomputes the pre-activation's sign from x instead of reading
+// the activation's output, and must land on the same side of zero as the forward did.
+__device__ __forceinline__ float in_shift(float beta, float mean, float scale) { return fmaf(-mean, scale, beta); }
+
 __device__ __forceinline__ float act_grad(float out, int act, float slope) {
   if (act == SMSUT_ACT_LRELU) return out > 0.f ? 1.f : slope;
   if (act == SMSUT_ACT_RELU) return out > 0.f ? 1.f : 0.f;
@@ -184,7 +189,7 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
       const bool ok = ch0 + j < cp;
       const float g = ok ? gamma_a[ch0 + j] : 0.f, b = ok ? beta_a[ch0 + j] : 0.f;
       sa[j] = g * r[j];
-      ta[j] = b - m[j] * sa[j];
+      ta[j] = in_shift(b, m[j], sa[j]);
     }
     if (HAS_B) {
       load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
@@ -193,7 +198,7 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
         const bool ok = ch0 + j < cp;
         const float g = ok ? gamma_b[ch0 + j] : 0.f, b = ok ? beta_b[ch0 + j] : 0.f;
         sb[j] = g * r[j];
-        ta[j] += b - m[j] * sb[j];      // both shifts folded into one
+        ta[j] += in_shift(b, m[j], sb[j]);      // both shifts folded into one
       }
     }
   }
@@ -277,6 +282,19 @@ __device__ __forceinline__ void load_g(const uint4& qd, const uint4& qo, float n
   }
 }
 
+// the same from the recomputed pre-activation  pre = xa*sa + ta [+ xb*sb]  (exactly the forward's expression)
+template <bool HAS_B>
+__device__ __forceinline__ void load_g_recomputed(const uint4& qd, const float* va, const float* vb, const float* sa,
+                                                  const float* ta, const float* sb, float neg, float* g) {
+  unpack8(qd, g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float pre = fmaf(va[j], sa[j], ta[j]);
+    if (HAS_B) pre = fmaf(vb[j], sb[j], pre);
+    g[j] *= pre > 0.f ? 1.f : neg;
+  }
+}
+
 // Sum NV x 8 per-thread values over the threads of the block that share a channel group; adds to dst[v*vstride + ch].
 // sh: [kNT/32][NV][min(c, 256)] floats (c <= 256: warps of a block cover the same channel groups) or unused.
 template <int NV>
@@ -322,19 +340,46 @@ __device__ __forceinline__ void block_reduce_add32(float (&acc)[NV][8], float* s
   }
 }
 
-template <bool HAS_B, bool HAS_ACT>
-__global__ void __launch_bounds__(kNT, 3)
+// RECOMP: `out` is not read; the activation's sign comes from the pre-activation recomputed from xa / xb (possible
+// whenever the forward had no residual input), which removes one of the 3 (4) streamed tensors.
+template <bool HAS_B, bool HAS_ACT, bool RECOMP, int MINB>
+__global__ void __launch_bounds__(kNT, MINB)
 in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
-                     const float* __restrict__ stats_a, const uint4* __restrict__ xb,
-                     const float* __restrict__ stats_b, float* __restrict__ red, int hw, int c, int splits, float neg) {
+                     const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                     const float* __restrict__ beta_a, const uint4* __restrict__ xb,
+                     const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
+                     const float* __restrict__ beta_b, float* __restrict__ red, int hw, int c, int cp, int splits,
+                     float neg) {
   pdl_prologue();
   extern __shared__ float sh[];
   const Strip32 s = make_strip32(c, hw, splits);
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
-  float ma[8], mb[8];
-  {
+  // !RECOMP: ma / mb = the means (centred accumulation).  RECOMP: ma = sa, mb = sb, ta = the folded affine form of
+  // the forward; the sums are accumulated raw and centred once at the end (sum g (x - m) = sum g x - m sum g).
+  float ma[8], mb[8], ta[8];
+  if (RECOMP) {
+    float m[8], r[8];
+    load_mean_rstd(stats_a, n, c, ch0, inv_hw, m, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool ok = ch0 + j < cp;
+      const float g = ok ? gamma_a[ch0 + j] : 0.f, b = ok ? beta_a[ch0 + j] : 0.f;
+      ma[j] = g * r[j];
+      ta[j] = in_shift(b, m[j], ma[j]);
+    }
+    if (HAS_B) {
+      load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = ch0 + j < cp;
+        const float g = ok ? gamma_b[ch0 + j] : 0.f, b = ok ? beta_b[ch0 + j] : 0.f;
+        mb[j] = g * r[j];
+        ta[j] += in_shift(b, m[j], mb[j]);
+      }
+    }
+  } else {
     const float* s0 = stats_a + (size_t)n * 2 * c + ch0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) ma[j] = s0[j] * inv_hw;
@@ -353,18 +398,25 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
   constexpr int U = 2;
   int it = 0;
   auto body = [&](const uint4& qd, const uint4& qo, const uint4& qa, const uint4& qb) {
-    float g[8], v[8];
-    load_g<HAS_ACT>(qd, qo, neg, g);
+    float g[8], v[8], w[8];
     unpack8(qa, v);
+    if (HAS_B) unpack8(qb, w);
+    if (RECOMP) {
+      load_g_recomputed<HAS_B>(qd, v, w, ma, ta, mb, neg, g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += g[j];
-      acc[1][j] = fmaf(g[j], v[j] - ma[j], acc[1][j]);
-    }
-    if (HAS_B) {
-      unpack8(qb, v);
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g[j];
+        acc[1][j] = fmaf(g[j], v[j], acc[1][j]);
+        if (HAS_B) acc[2][j] = fmaf(g[j], w[j], acc[2][j]);
+      }
+    } else {
+      load_g<HAS_ACT>(qd, qo, neg, g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[2][j] = fmaf(g[j], v[j] - mb[j], acc[2][j]);
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += g[j];
+        acc[1][j] = fmaf(g[j], v[j] - ma[j], acc[1][j]);
+        if (HAS_B) acc[2][j] = fmaf(g[j], w[j] - mb[j], acc[2][j]);
+      }
     }
   };
   for (; it + U <= s.count; it += U, idx += (size_t)U * step) {
@@ -372,7 +424,7 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       qd[u] = dout[idx + (size_t)u * step];
-      if (HAS_ACT) qo[u] = out[idx + (size_t)u * step];
+      if (HAS_ACT && !RECOMP) qo[u] = out[idx + (size_t)u * step];
       qa[u] = xa[idx + (size_t)u * step];
       if (HAS_B) qb[u] = xb[idx + (size_t)u * step];
     }
@@ -382,7 +434,7 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
   for (; it < s.count; ++it, idx += step) {
     uint4 qo = zero4(), qb = zero4();
     const uint4 qd = dout[idx];
-    if (HAS_ACT) qo = out[idx];
+    if (HAS_ACT && !RECOMP) qo = out[idx];
     const uint4 qa = xa[idx];
     if (HAS_B) qb = xb[idx];
     body(qd, qo, qa, qb);
@@ -391,23 +443,26 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
     float m[8], r[8];
     load_mean_rstd(stats_a, n, c, ch0, inv_hw, m, r);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[1][j] *= r[j];
+    for (int j = 0; j < 8; ++j) acc[1][j] = (RECOMP ? fmaf(-m[j], acc[0][j], acc[1][j]) : acc[1][j]) * r[j];
     if (HAS_B) {
       load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[2][j] *= r[j];
+      for (int j = 0; j < 8; ++j) acc[2][j] = (RECOMP ? fmaf(-m[j], acc[0][j], acc[2][j]) : acc[2][j]) * r[j];
     }
   }
   block_reduce_add32<3>(acc, sh, s, red + (size_t)n * 3 * c, c, c);
 }
 
 // pass 2: dx = A*g + B*x + C per channel with A = gamma*rstd, B = -A*rstd*mean(g xhat), C = -A*mean(g) - B*mean
-template <bool HAS_B, bool HAS_RES, bool HAS_ACT>
-__global__ void __launch_bounds__(kNT, 3)
+// RECOMP as in the reduce kernel: A = gamma * rstd is the forward's scale, so only the folded shift `ta` is extra.
+template <bool HAS_B, bool HAS_RES, bool HAS_ACT, bool RECOMP, int MINB>
+__global__ void __launch_bounds__(kNT, MINB)
 in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
-                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a, uint4* __restrict__ dxa,
+                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                    const float* __restrict__ beta_a, uint4* __restrict__ dxa,
                     float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const uint4* __restrict__ xb,
-                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b, uint4* __restrict__ dxb,
+                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
+                    const float* __restrict__ beta_b, uint4* __restrict__ dxb,
                     float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, uint4* __restrict__ dres,
                     const float* __restrict__ red, int hw, int c, int cp, int splits, float neg) {
   pdl_prologue();
@@ -415,7 +470,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
   const int n = blockIdx.x;
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
-  float Aa[8], Ba[8], Ca[8], Ab[8], Bb[8], Cb[8];
+  float Aa[8], Ba[8], Ca[8], Ab[8], Bb[8], Cb[8], ta[8];
   const float* r0 = red + (size_t)n * 3 * c + ch0;
   {
     float m[8], r[8];
@@ -426,6 +481,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
       const float A = (ok ? gamma_a[ch0 + j] : 0.f) * r[j];
       const float B = -A * r[j] * (r0[c + j] * inv_hw);
       Aa[j] = A; Ba[j] = B; Ca[j] = -A * (r0[j] * inv_hw) - B * m[j];
+      if (RECOMP) ta[j] = in_shift(ok ? beta_a[ch0 + j] : 0.f, m[j], A);
     }
     if (HAS_B) {
       load_mean_rstd(stats_b, n, c, ch0, inv_hw, m, r);
@@ -435,6 +491,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
         const float A = (ok ? gamma_b[ch0 + j] : 0.f) * r[j];
         const float B = -A * r[j] * (r0[2 * c + j] * inv_hw);
         Ab[j] = A; Bb[j] = B; Cb[j] = -A * (r0[j] * inv_hw) - B * m[j];
+        if (RECOMP) ta[j] += in_shift(ok ? beta_b[ch0 + j] : 0.f, m[j], A);
       }
     }
   }
@@ -456,17 +513,18 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
   constexpr int U = 2;
   int it = 0;
   auto body = [&](const uint4& qd, const uint4& qo, const uint4& qa, const uint4& qb, size_t at) {
-    float g[8], v[8], o[8];
-    load_g<HAS_ACT>(qd, qo, neg, g);
-    if (HAS_RES) dres[at] = pack8(g);
+    float g[8], v[8], w[8], o[8];
     unpack8(qa, v);
+    if (HAS_B) unpack8(qb, w);
+    if (RECOMP) load_g_recomputed<HAS_B>(qd, v, w, Aa, ta, Ab, neg, g);
+    else load_g<HAS_ACT>(qd, qo, neg, g);
+    if (HAS_RES) dres[at] = pack8(g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(Aa[j], g[j], fmaf(Ba[j], v[j], Ca[j]));
     dxa[at] = pack8(o);
     if (HAS_B) {
-      unpack8(qb, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(Ab[j], g[j], fmaf(Bb[j], v[j], Cb[j]));
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(Ab[j], g[j], fmaf(Bb[j], w[j], Cb[j]));
       dxb[at] = pack8(o);
     }
   };
@@ -475,7 +533,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       qd[u] = dout[idx + (size_t)u * step];
-      if (HAS_ACT) qo[u] = out[idx + (size_t)u * step];
+      if (HAS_ACT && !RECOMP) qo[u] = out[idx + (size_t)u * step];
       qa[u] = xa[idx + (size_t)u * step];
       if (HAS_B) qb[u] = xb[idx + (size_t)u * step];
     }
@@ -485,7 +543,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
   for (; it < s.count; ++it, idx += step) {
     uint4 qo = zero4(), qb = zero4();
     const uint4 qd = dout[idx];
-    if (HAS_ACT) qo = out[idx];
+    if (HAS_ACT && !RECOMP) qo = out[idx];
     const uint4 qa = xa[idx];
     if (HAS_B) qb = xb[idx];
     body(qd, qo, qa, qb, idx);
@@ -706,44 +764,79 @@ extern "C" int smsut_in_apply(const void* xa, const float* stats_a, const float*
   return launch_status("in_apply_kernel");
 }
 
+// two-branch recomputed-sign kernels: 2 blocks / SM without register spills, or 3 with ~250 B of spills
+// (SMSUT_IN_RECOMP_MINB=2|3; measured on B200: see DESIGN.md)
+static bool recomp_two_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SMSUT_IN_RECOMP_MINB");
+    v = e ? atoi(e) : 2;
+  }
+  return v == 2;
+}
+
 extern "C" int smsut_in_bwd_reduce(const void* dout, const void* out, const void* xa, const float* stats_a,
-                                   const void* xb, const float* stats_b, float* red, int32_t n, int32_t hw, int32_t c,
-                                   int32_t act, float slope, smsut_stream_t st) {
+                                   const float* gamma_a, const float* beta_a, const void* xb, const float* stats_b,
+                                   const float* gamma_b, const float* beta_b, float* red, int32_t n, int32_t hw,
+                                   int32_t c, int32_t cp, int32_t act, float slope, smsut_stream_t st) {
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
   SMSUT_CHECK(act == SMSUT_ACT_NONE || act == SMSUT_ACT_LRELU || act == SMSUT_ACT_RELU, -1, "in_bwd: unsupported activation");
+  // out == NULL with an activation: the sign is recomputed from xa / xb, which needs the forward's affine parameters
+  const bool recomp = act != SMSUT_ACT_NONE && out == nullptr;
+  SMSUT_CHECK(!recomp || (gamma_a && beta_a && (xb == nullptr || (gamma_b && beta_b))), -1,
+              "in_bwd_reduce: out == NULL needs gamma / beta of every branch");
   const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
   const size_t shm = c <= 256 ? (size_t)(kNT / 32) * 3 * c * sizeof(float) : 0;
-#define IN_BWD_RED(HB, HA)                                                                                        \
-  launch_pdl(in_bwd_reduce_kernel<HB, HA>, dim3(n, splits), kNT, shm, (cudaStream_t)st, (const uint4*)dout,        \
-             (const uint4*)out, (const uint4*)xa, stats_a, (const uint4*)xb, stats_b, red, hw, c, splits, neg)
-  if (xb != nullptr) { if (act != SMSUT_ACT_NONE) IN_BWD_RED(true, true); else IN_BWD_RED(true, false); }
-  else { if (act != SMSUT_ACT_NONE) IN_BWD_RED(false, true); else IN_BWD_RED(false, false); }
+#define IN_BWD_RED(HB, HA, RC, MB)                                                                                 \
+  launch_pdl(in_bwd_reduce_kernel<HB, HA, RC, MB>, dim3(n, splits), kNT, shm, (cudaStream_t)st, (const uint4*)dout, \
+             (const uint4*)out, (const uint4*)xa, stats_a, gamma_a, beta_a, (const uint4*)xb, stats_b, gamma_b,    \
+             beta_b, red, hw, c, cp, splits, neg)
+  if (xb != nullptr) {
+    if (recomp) { if (recomp_two_blocks()) IN_BWD_RED(true, true, true, 2); else IN_BWD_RED(true, true, true, 3); }
+    else if (act != SMSUT_ACT_NONE) IN_BWD_RED(true, true, false, 3);
+    else IN_BWD_RED(true, false, false, 3);
+  } else {
+    if (recomp) IN_BWD_RED(false, true, true, 3);
+    else if (act != SMSUT_ACT_NONE) IN_BWD_RED(false, true, false, 3);
+    else IN_BWD_RED(false, false, false, 3);
+  }
 #undef IN_BWD_RED
   count_launch();
   return launch_status("in_bwd_reduce_kernel");
 }
 
 extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void* xa, const float* stats_a,
-                                  const float* gamma_a, void* dxa, float* dgamma_a, float* dbeta_a, const void* xb,
-                                  const float* stats_b, const float* gamma_b, void* dxb, float* dgamma_b,
-                                  float* dbeta_b, void* dres, const float* red, int32_t n, int32_t hw, int32_t c,
-                                  int32_t cp, int32_t act, float slope, smsut_stream_t st) {
+                                  const float* gamma_a, const float* beta_a, void* dxa, float* dgamma_a,
+                                  float* dbeta_a, const void* xb, const float* stats_b, const float* gamma_b,
+                                  const float* beta_b, void* dxb, float* dgamma_b, float* dbeta_b, void* dres,
+                                  const float* red, int32_t n, int32_t hw, int32_t c, int32_t cp, int32_t act,
+                                  float slope, smsut_stream_t st) {
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
   SMSUT_CHECK(act == SMSUT_ACT_NONE || act == SMSUT_ACT_LRELU || act == SMSUT_ACT_RELU, -1, "in_bwd: unsupported activation");
+  const bool recomp = act != SMSUT_ACT_NONE && out == nullptr;
+  SMSUT_CHECK(!recomp || (beta_a && (xb == nullptr || beta_b)), -1, "in_bwd_apply: out == NULL needs beta of every branch");
   const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
-#define IN_BWD_APPLY2(HB, HR, HA)                                                                                  \
-  launch_pdl(in_bwd_apply_kernel<HB, HR, HA>, dim3(n, splits), kNT, 0, (cudaStream_t)st, (const uint4*)dout,       \
-             (const uint4*)out, (const uint4*)xa, stats_a, gamma_a, (uint4*)dxa, dgamma_a, dbeta_a, (const uint4*)xb, \
-             stats_b, gamma_b, (uint4*)dxb, dgamma_b, dbeta_b, (uint4*)dres, red, hw, c, cp, splits, neg)
-#define IN_BWD_APPLY(HB, HR) \
-  do { if (act != SMSUT_ACT_NONE) IN_BWD_APPLY2(HB, HR, true); else IN_BWD_APPLY2(HB, HR, false); } while (0)
+#define IN_BWD_APPLY3(HB, HR, HA, RC)                                                                              \
+  do { if (HB && RC && recomp_two_blocks()) IN_BWD_APPLY4(HB, HR, HA, RC, 2); else IN_BWD_APPLY4(HB, HR, HA, RC, 3); } while (0)
+#define IN_BWD_APPLY4(HB, HR, HA, RC, MB)                                                                          \
+  launch_pdl(in_bwd_apply_kernel<HB, HR, HA, RC, MB>, dim3(n, splits), kNT, 0, (cudaStream_t)st, (const uint4*)dout, \
+             (const uint4*)out, (const uint4*)xa, stats_a, gamma_a, beta_a, (uint4*)dxa, dgamma_a, dbeta_a,        \
+             (const uint4*)xb, stats_b, gamma_b, beta_b, (uint4*)dxb, dgamma_b, dbeta_b, (uint4*)dres, red, hw, c, \
+             cp, splits, neg)
+#define IN_BWD_APPLY(HB, HR)                                        \
+  do {                                                              \
+    if (recomp) IN_BWD_APPLY3(HB, HR, true, true);                  \
+    else if (act != SMSUT_ACT_NONE) IN_BWD_APPLY3(HB, HR, true, false); \
+    else IN_BWD_APPLY3(HB, HR, false, false);                       \
+  } while (0)
   if (xb != nullptr) { if (dres != nullptr) IN_BWD_APPLY(true, true); else IN_BWD_APPLY(true, false); }
   else { if (dres != nullptr) IN_BWD_APPLY(false, true); else IN_BWD_APPLY(false, false); }
-#undef IN_BWD_APPLY2
+#undef IN_BWD_APPLY4
+#undef IN_BWD_APPLY3
 #undef IN_BWD_APPLY
   count_launch();
   return launch_status("in_bwd_apply_kernel");

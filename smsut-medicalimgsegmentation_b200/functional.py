@@ -6,6 +6,7 @@ kernels.  First-order backwards use the fused kernels.  When autograd runs a bac
 of the `*BwdFn` Functions below, whose own backwards are the hand-derived second-order kernels
 (smsut_in_bwd2_*, conv fprop/wgrad of the cotangent, avg-pool forward of the cotangent ...).
 """
+import os
 import threading
 
 import torch
@@ -306,6 +307,7 @@ class DirectConvFn(Function):
 # ----------------------------------------------------------------------------------------------
 # InstanceNorm + activation + residual
 # ----------------------------------------------------------------------------------------------
+RECOMPUTE_SIGN = [os.environ.get("SMSUT_IN_BWD_RECOMPUTE", "1") != "0"]   # A/B knob for the InstanceNorm backward
 BN_OFF, BN_TRAIN, BN_EVAL = 0, 1, 2     # INActFn `batch` modes: InstanceNorm / BatchNorm training / BatchNorm eval
 
 
@@ -382,8 +384,10 @@ class INActFn(Function):
                   _target(bb) if xb is not None else None]
             if tg[0] is not None and tg[1] is not None and (xb is None or (tg[2] is not None and tg[3] is not None)):
                 targets = tg
+        # no residual input in the forward: the sign of the activation's input is a function of xa / xb alone
+        betas = (ba, bb) if (not ctx.has_res and RECOMPUTE_SIGN[0]) else None
         dxa, dga, dba, dxb, dgb, dbb, dres = ops.in_bwd(dout, out, xa, sa, ga, xb, sb, gb, want_res, act, SLOPE, cp,
-                                                        targets=targets, batch=ctx.batch == BN_TRAIN)
+                                                        targets=targets, batch=ctx.batch == BN_TRAIN, betas=betas)
         return dxa, dga, dba, dxb, dgb, dbb, dres, None, None, None, None, None
 
 

@@ -616,16 +616,22 @@ def bn_eval_stats(running_mean, running_var, n, hw, c):
 
 
 def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=ACT_NONE, slope=0.01, c_params=None,
-           targets=None, batch=False):
+           targets=None, batch=False, betas=None):
     """returns dxa, dgamma_a, dbeta_a, dxb, dgamma_b, dbeta_b, dres.  `targets` = (dga, dba, dgb, dbb) fp32 tensors the
     parameter gradients are accumulated INTO (the flat .grad views); they are then returned as None.
-    batch: BatchNorm -- the reductions are pooled over the samples between the two passes."""
+    batch: BatchNorm -- the reductions are pooled over the samples between the two passes.
+    betas = (beta_a, beta_b | None): the forward had no residual input, so the kernels recompute the activation's
+    sign from xa / xb instead of streaming `out` (one tensor less in each pass)."""
     n, h, w, c = xa.shape
     cp = c if c_params is None else c_params
     dev = xa.device
+    ba = bb = None
+    if betas is not None and act != ACT_NONE:
+        ba, bb = betas
+        out = None
     red = zeros((n, 3, c), dev)
-    call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(xb), _p(sb), _p(red), n, h * w, c, act, slope,
-         _stream())
+    call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(xb), _p(sb), _p(gb), _p(bb),
+         _p(red), n, h * w, c, cp, act, slope, _stream())
     if batch:
         call("smsut_bn_pool", _p(red), _p(red), n, 3, c, _stream())
     dxa = torch.empty_like(xa)
@@ -638,8 +644,8 @@ def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act
         pg = zeros((4, cp), dev)
         t = [pg[0], pg[1], pg[2] if xb is not None else None, pg[3] if xb is not None else None]
         ret = t
-    call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(dxa), _p(t[0]), _p(t[1]), _p(xb), _p(sb),
-         _p(gb), _p(dxb), _p(t[2]), _p(t[3]), _p(dres), _p(red), n, h * w, c, cp, act, slope, _stream())
+    call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(dxa), _p(t[0]), _p(t[1]), _p(xb),
+         _p(sb), _p(gb), _p(bb), _p(dxb), _p(t[2]), _p(t[3]), _p(dres), _p(red), n, h * w, c, cp, act, slope, _stream())
     return dxa, ret[0], ret[1], dxb, ret[2], ret[3], dres
 
 

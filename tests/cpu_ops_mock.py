@@ -220,12 +220,21 @@ def bn_eval_stats(running_mean, running_var, n, hw, c):
 
 
 def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act=0, slope=0.01, c_params=None,
-           targets=None, batch=False):
+           targets=None, batch=False, betas=None):
     c = xa.shape[3]
     cp = c if c_params is None else c_params
     g = dout.float()
     if act != 0:
-        g = g * _act_grad(out.float(), act, slope)
+        if betas is not None:       # the kernels' recomputed-sign mode: the mask comes from xa / xb, not from `out`
+            hw = xa.shape[1] * xa.shape[2]
+            m, r = _mean_rstd(sa, hw)
+            pre = (xa.float() - m) * r * _gam(ga, c) + _gam(betas[0], c)
+            if xb is not None:
+                m, r = _mean_rstd(sb, hw)
+                pre = pre + (xb.float() - m) * r * _gam(gb, c) + _gam(betas[1], c)
+            g = g * _act_grad(pre, act, slope)
+        else:
+            g = g * _act_grad(out.float(), act, slope)
     dxa, dga, dba = _in_bwd_one(g, xa, sa, ga, c, batch)
     dxb = dgb = dbb = None
     if xb is not None:

@@ -243,6 +243,28 @@ def test_instance_norm_fwd_bwd(ops, c, h, n):
     for g_, l_ in zip(got, leaves):
         g_ = nchw(g_) if g_.dim() == 4 else g_
         assert rel(g_, l_.grad) < 2e-2
+    # no residual in the forward: the backward may recompute the activation's sign from xa / xb instead of reading
+    # `out` (betas=...).  Both modes must use the SAME mask: one flipped element would move dx by ~3e-3 relative and
+    # dbeta (= sum g) by ~1e-3, while the different summation order of the two modes moves them by ~1e-6
+    for act in (ops.ACT_LRELU, ops.ACT_RELU):
+        o1 = ops.in_apply(a, sa, ga, ba, act=act)
+        r_out = ops.in_bwd(nhwc(dout), o1, a, sa, ga, act=act)
+        r_rec = ops.in_bwd(nhwc(dout), o1, a, sa, ga, act=act, betas=(ba, None))
+        assert rel(r_rec[0], r_out[0]) < 2e-4 and rel(r_rec[1], r_out[1]) < 1e-5 and rel(r_rec[2], r_out[2]) < 1e-5
+        o2 = ops.in_apply(a, sa, ga, ba, b2, sb, gb, bb, act=act)
+        r_out = ops.in_bwd(nhwc(dout), o2, a, sa, ga, b2, sb, gb, act=act)
+        r_rec = ops.in_bwd(nhwc(dout), o2, a, sa, ga, b2, sb, gb, act=act, betas=(ba, bb))
+        assert rel(r_rec[0], r_out[0]) < 2e-4 and rel(r_rec[3], r_out[3]) < 2e-4
+        for i in (1, 2, 4, 5):
+            assert rel(r_rec[i], r_out[i]) < 1e-5, i
+    leaves = [t.clone().requires_grad_(True) for t in (xa, ga, ba, xb, gb, bb)]
+    ref3 = F.leaky_relu(in_ref(*leaves[0:3]) + in_ref(*leaves[3:6]), 0.01)
+    ref3.backward(dout)
+    o2 = ops.in_apply(a, sa, ga, ba, b2, sb, gb, bb, act=ops.ACT_LRELU)
+    got = ops.in_bwd(nhwc(dout), None, a, sa, ga, b2, sb, gb, act=ops.ACT_LRELU, betas=(ba, bb))
+    for g_, l_ in zip(got[:6], leaves):
+        g_ = nchw(g_) if g_.dim() == 4 else g_
+        assert rel(g_, l_.grad) < 2e-2
 
 
 @pytest.mark.parametrize("c,cp,h,n", [(16, 16, 64, 3), (16, 8, 32, 4), (128, 128, 16, 5)])
