@@ -111,8 +111,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    bs = 2                              # bounded sample: 2 labelled + 2 unlabelled slices per step
-    steps, warmup = min(args.steps, 6), min(args.warmup, 1)
+    bs = 4                              # bounded sample: 4 labelled + 4 unlabelled slices per step (~1.3 s on 16 cores)
+    steps, warmup = min(args.steps, 8), min(max(args.warmup, 1), 2)
     rate, sec, threads = cpu_step_rate(bs, steps, warmup)
     sample = f"{steps} timed iterations (after {warmup} warm-up) of the full uganConsis step at {bs}+{bs} 256x256 slices"
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
@@ -315,10 +315,10 @@ def run_ours(args):
                                    "together > L2), CUDA events around the replay on its stream; peak = burst "
                                    f"({how}); 8 of the 13 classes are HBM-bound (SURVEY.md section 8d): see gbs / ideal_us",
                             "per_class": per}
-        rate, sec, threads = cpu_step_rate(2, 1, 0)
+        rate, sec, threads = cpu_step_rate(4, 6, 1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "1 iteration of the oracle's full uganConsis step at 2+2 256x256 slices "
-                                          f"({sec:.1f} s), fp32, torch CPU"}
+                                "sample": "6 timed iterations (after 1 warm-up) of the oracle's full uganConsis step at "
+                                          f"4+4 256x256 slices ({sec:.2f} s each), fp32, torch CPU, {threads} threads"}
     if par.rank == 0:
         print(json.dumps(line), flush=True)
     if par.world > 1:

@@ -17,6 +17,7 @@ ga, ba = torch.ones(16, device="cuda"), torch.zeros(16, device="cuda")
 for _ in range(2):
     st, stb = ops.in_stats(x), ops.in_stats(xb)
     out = ops.in_apply(x, st, ga, ba, xb, stb, ga, ba, act=ops.ACT_LRELU)
-    r = ops.in_bwd(d, out, x, st, ga, xb, stb, ga, act=ops.ACT_LRELU)
+    r = ops.in_bwd(d, out, x, st, ga, xb, stb, ga, act=ops.ACT_LRELU)                   # mask read from `out`
+    r = ops.in_bwd(d, out, x, st, ga, xb, stb, ga, act=ops.ACT_LRELU, betas=(ba, ba))   # mask recomputed from x
 torch.cuda.synchronize()
 print("ok")

@@ -395,7 +395,7 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
   // uint4 index of (pixel p, group g) = p * cg + g
   size_t idx = ((size_t)n * hw + s.p0 + s.lane0) * s.cg + s.g;
   const int step = s.nl * s.cg;
-  constexpr int U = 2;
+  constexpr int U = MINB == 2 ? 4 : 2;      // 2-resident variants have the registers for deeper load batches
   int it = 0;
   auto body = [&](const uint4& qd, const uint4& qo, const uint4& qa, const uint4& qb) {
     float g[8], v[8], w[8];
@@ -510,7 +510,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
   }
   size_t idx = ((size_t)n * hw + s.p0 + s.lane0) * s.cg + s.g;
   const int step = s.nl * s.cg;
-  constexpr int U = 2;
+  constexpr int U = MINB == 2 ? 4 : 2;      // 2-resident variants have the registers for deeper load batches
   int it = 0;
   auto body = [&](const uint4& qd, const uint4& qo, const uint4& qa, const uint4& qb, size_t at) {
     float g[8], v[8], w[8], o[8];
@@ -706,15 +706,18 @@ __global__ void __launch_bounds__(kNT) colsum_kernel(const void* __restrict__ x,
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static int pick_splits(int n, int hw, int c) {
-  // ~8 blocks per SM overall (two waves at 4 resident blocks), each block streaming >= 16 KB
+static int pick_splits(int n, int hw, int c, int blocks_per_sm = 8) {
+  // `blocks_per_sm` blocks per SM over the whole grid = two waves of the kernel's resident blocks (8 for the 4-resident
+  // forward kernels; measured with scripts/in_bench.py: 4 for the statistics kernel and for the 2-resident two-branch
+  // recomputed-sign backward kernels, 93 -> 81 us per pair at 256x256x16), each block streaming >= 16 KB
   const long long bytes = (long long)hw * c * 2;
   long long s = bytes / (16 * 1024);
-  static int bps = 0;
-  if (bps == 0) {
-    const char* e = getenv("SMSUT_IN_BPS");      // development knob: blocks per SM over the whole grid
-    bps = e && atoi(e) > 0 ? atoi(e) : 8;
+  static int knob = -1;
+  if (knob < 0) {
+    const char* e = getenv("SMSUT_IN_BPS");      // development knob: overrides every kernel's choice
+    knob = e && atoi(e) > 0 ? atoi(e) : 0;
   }
+  const int bps = knob > 0 ? knob : blocks_per_sm;
   const long long want = ((long long)bps * device_sm_count() + n - 1) / n;
   if (s > want) s = want;
   if (s < 1) s = 1;
@@ -741,7 +744,7 @@ using namespace smsut;
 extern "C" int smsut_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float* stats, smsut_stream_t st) {
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
-  const int splits = pick_splits(n, hw, c);
+  const int splits = pick_splits(n, hw, c, 4);
   launch_pdl(in_stats_kernel, dim3(n, splits), kNT, 2 * c * sizeof(float), (cudaStream_t)st, x, stats, hw, c, splits);
   count_launch();
   return launch_status("in_stats_kernel");
@@ -781,10 +784,10 @@ extern "C" int smsut_in_bwd_reduce(const void* dout, const void* out, const void
                                    int32_t c, int32_t cp, int32_t act, float slope, smsut_stream_t st) {
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
-  const int splits = pick_splits(n, hw, c);
   SMSUT_CHECK(act == SMSUT_ACT_NONE || act == SMSUT_ACT_LRELU || act == SMSUT_ACT_RELU, -1, "in_bwd: unsupported activation");
   // out == NULL with an activation: the sign is recomputed from xa / xb, which needs the forward's affine parameters
   const bool recomp = act != SMSUT_ACT_NONE && out == nullptr;
+  const int splits = pick_splits(n, hw, c, recomp && xb != nullptr && recomp_two_blocks() ? 4 : 8);
   SMSUT_CHECK(!recomp || (gamma_a && beta_a && (xb == nullptr || (gamma_b && beta_b))), -1,
               "in_bwd_reduce: out == NULL needs gamma / beta of every branch");
   const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
@@ -815,9 +818,9 @@ extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void*
                                   float slope, smsut_stream_t st) {
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
-  const int splits = pick_splits(n, hw, c);
   SMSUT_CHECK(act == SMSUT_ACT_NONE || act == SMSUT_ACT_LRELU || act == SMSUT_ACT_RELU, -1, "in_bwd: unsupported activation");
   const bool recomp = act != SMSUT_ACT_NONE && out == nullptr;
+  const int splits = pick_splits(n, hw, c, recomp && xb != nullptr && recomp_two_blocks() ? 4 : 8);
   SMSUT_CHECK(!recomp || (beta_a && (xb == nullptr || beta_b)), -1, "in_bwd_apply: out == NULL needs beta of every branch");
   const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
 #define IN_BWD_APPLY3(HB, HR, HA, RC)                                                                              \
