@@ -46,16 +46,20 @@ class accumulate_param_grads:
     parameters' existing `.grad` tensors (the flat gradient buffer of optim.py) and autograd is handed `None`:
     no zero-fill + add pair per parameter.  Outside it the Functions return fresh gradient tensors as usual."""
 
-    def __init__(self, side_streams=True, join=True):
+    def __init__(self, side_streams=True, join=True, flush=True, side_group=0):
         """join=False leaves the side / branch streams of this backward running (no wait, no scratch flush): a later
-        `accumulate_param_grads()` block -- or the optimizer step -- completes the gradients"""
+        `accumulate_param_grads()` block -- or the optimizer step -- completes the gradients.  flush=False joins but
+        leaves the tap-major scratch to the optimizer step (another network's weight-gradient kernels may still be
+        in flight, and flush_all would fold THEIR scratch too).  side_group: see ops.side_streams_enable."""
         self.side = side_streams
         self.join = join
+        self.flush = flush
+        self.group = side_group
 
     def __enter__(self):
         self.prev = _accumulate[0]
         _accumulate[0] = True
-        ops.side_streams_enable(self.side)     # wgrad kernels run beside the dgrad chain (ops._Side)
+        ops.side_streams_enable(self.side, self.group)     # wgrad kernels run beside the dgrad chain (ops._Side)
 
     def __exit__(self, *a):
         _accumulate[0] = self.prev
@@ -64,7 +68,8 @@ class accumulate_param_grads:
             return
         ops.branch_join_all()
         ops.side_join()
-        ops.WgradScratch.flush_all()       # after the block every .grad is complete (tap-major scratch folded in)
+        if self.flush:
+            ops.WgradScratch.flush_all()       # after the block every .grad is complete (tap-major scratch folded in)
 
 
 def _target(param):

@@ -104,13 +104,38 @@ class _Side:
     n_streams = int(os.environ.get("SMSUT_SIDE_STREAMS", "2"))
     streams = {}        # device index -> [streams]
     active = False
+    group = 0
     nxt = 0
     held = []
     used = []
 
 
-def side_streams_enable(on=True):
+def side_streams_enable(on=True, group=0):
+    """group: which pool of side streams the following weight-gradient kernels use.  Two backward passes that are in
+    flight at the same time (the generator's cycle-pass backward beside the discriminator phase) use different pools,
+    so that joining one does not wait for the other's queue."""
     _Side.active = bool(on) and _Side.n_streams > 0
+    _Side.group = group
+
+
+def pending_detach():
+    """Hand the bookkeeping of everything forked so far (side streams with weight-gradient kernels in flight, the
+    tensors they read, the branch streams used) to the caller and start afresh: the next join then only waits for
+    work issued after this call.  `pending_attach` gives it back before the join that must cover it."""
+    st = (_Side.used, _Side.held, list(_branch_used))
+    _Side.used, _Side.held = [], []
+    del _branch_used[:]
+    return st
+
+
+def pending_attach(st):
+    for s in st[0]:
+        if s not in _Side.used:
+            _Side.used.append(s)
+    _Side.held.extend(st[1])
+    for b in st[2]:
+        if b not in _branch_used:
+            _branch_used.append(b)
 
 
 def side_run(fn, keep):
@@ -120,11 +145,11 @@ def side_run(fn, keep):
         fn()
         return
     main = torch.cuda.current_stream()
-    pool = _Side.streams.get(main.device_index)
+    pool = _Side.streams.get((main.device_index, _Side.group))
     if pool is None:
         # lowest priority: the dgrad / norm chain on the forking streams is the critical path
         pool = [torch.cuda.Stream(device=main.device, priority=0) for _ in range(_Side.n_streams)]
-        _Side.streams[main.device_index] = pool
+        _Side.streams[(main.device_index, _Side.group)] = pool
     s = pool[_Side.nxt % len(pool)]
     _Side.nxt += 1
     s.wait_stream(main)

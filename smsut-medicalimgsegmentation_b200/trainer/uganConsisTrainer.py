@@ -33,6 +33,9 @@ from .. import ops
 from ..network.blocks import refresh_packs
 from .uganShp0Trainer import UGANShp0Trainer
 
+# stage the generator's backward so that the cycle pass's half runs beside the discriminator phase (train_step)
+SPLIT_G_BACKWARD = [os.environ.get("SMSUT_SPLIT_G_BACKWARD", "1") != "0"]
+
 LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
 
 
@@ -70,14 +73,25 @@ class UGANConsisTrainer(UGANShp0Trainer):
 
         # generator forward shared by the D phase (detached) and the G phase
         y_fake, x_fake, feat_x_pool, sample_ids = self.net(x_real, vec_ot, sample_ids=sample_ids)
+        split = SPLIT_G_BACKWARD[0]
 
         # ---------------- the cycle pass of the G phase (L157-168) needs only x_fake and G's weights: it runs on a
-        # branch stream beside the whole D phase (forward, gradient penalty, backward, Adam step)
+        # branch stream beside the whole D phase (forward, gradient penalty, backward, Adam step).
+        # g_loss = [adversarial + classification terms, which need the UPDATED discriminator]
+        #        + g_partial [cycle L1, segmentation, consistency, PatchNCE: functions of G alone].
+        # Gradients add, so with `split` the backward of g_partial starts as soon as the cycle forward is done --
+        # through the whole cycle pass down to d g_partial / d x_fake and through the first pass's segmentation
+        # half -- beside the D phase; only the first pass's translation half waits for the discriminator (it is
+        # back-propagated ONCE, with both contributions to d/d x_fake summed).  That takes the cycle-pass backward,
+        # half of the generator's backward work, off the serial path behind the D phase.
         if isinstance(lambda_semi, torch.Tensor):
             lambda_semi = lambda_semi.reshape(())      # device scalar: one captured graph serves every epoch
+        if split:
+            self.optimizer.zero_grad()                 # before the fork: stage A accumulates into G's gradients
+        x_fake_c = x_fake.detach().requires_grad_(True) if split else x_fake
         with ops.parallel_branch(4) as b_cyc:
             g_loss_seg = self.loss(y_fake[:bs], y_real)
-            y_rec, x_rec, feat_f_pool, _ = self.net(x_fake, vec_to, sample_ids=sample_ids)
+            y_rec, x_rec, feat_f_pool, _ = self.net(x_fake_c, vec_to, sample_ids=sample_ids)
             g_loss_rec = Fn.L1MeanFn.apply(x_rec.contiguous(), x_real)
             if use_semi:
                 g_loss_semi = self.consistency_loss(y_rec, y_fake)
@@ -85,6 +99,11 @@ class UGANConsisTrainer(UGANShp0Trainer):
                 g_loss_semi = torch.zeros((), device=x_real.device)
             g_loss_nce = self.nce_loss(feat_x_pool, feat_f_pool)
             g_partial = lambda_rec * g_loss_rec + lambda_seg * g_loss_seg + lambda_semi * g_loss_semi + 1.0 * g_loss_nce
+            if split:
+                with Fn.accumulate_param_grads(join=False, side_group=1):
+                    g_partial.backward()
+                dx_fake_cyc = x_fake_c.grad
+        stage_a = ops.pending_detach() if split else None   # the D phase joins only what it forks itself
 
         # ---------------- D phase (L129-146): the three discriminator passes are independent chains of small
         # kernels -> real on the current stream, fake and interpolated on branch streams (ops.parallel_branch)
@@ -106,7 +125,8 @@ class UGANConsisTrainer(UGANShp0Trainer):
 
         d_loss = d_loss_real + d_loss_fake + lambda_cls * d_loss_cls + lambda_gp * d_loss_gp
         self.d_optimizer.zero_grad()
-        with Fn.accumulate_param_grads():   # wgrad kernels add straight into the flat gradient buffer
+        # flush=False: G's weight-gradient scratch is being written by stage A; d_optimizer.step() folds D's own
+        with Fn.accumulate_param_grads(flush=not split):   # wgrad kernels add straight into the flat gradient buffer
             d_loss.backward()
         if self.parallel is not None:
             self.parallel.all_reduce_grads(self.d_optimizer)
@@ -122,10 +142,17 @@ class UGANConsisTrainer(UGANShp0Trainer):
         g_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_trg)
         b_cyc.join(g_partial, g_loss_seg, g_loss_rec, g_loss_semi, g_loss_nce)
 
-        g_loss = g_loss_fake + lambda_cls * g_loss_cls + g_partial
-        self.optimizer.zero_grad()
-        with Fn.accumulate_param_grads():
-            g_loss.backward()
+        if split:
+            ops.pending_attach(stage_a)
+            if dx_fake_cyc.is_cuda:
+                dx_fake_cyc.record_stream(torch.cuda.current_stream())
+            with Fn.accumulate_param_grads():
+                torch.autograd.backward([g_loss_fake + lambda_cls * g_loss_cls, x_fake], [None, dx_fake_cyc])
+        else:
+            g_loss = g_loss_fake + lambda_cls * g_loss_cls + g_partial
+            self.optimizer.zero_grad()
+            with Fn.accumulate_param_grads():
+                g_loss.backward()
         if self.parallel is not None:
             self.parallel.all_reduce_grads(self.optimizer)
         self.optimizer.step()
