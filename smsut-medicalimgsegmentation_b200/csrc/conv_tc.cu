@@ -62,6 +62,12 @@ struct ConvTcParams {
   float* stats;            // fused InstanceNorm statistics [n][2][ncols_pad] of the stored values (optional)
   int fast;                // plain epilogue: bf16, one destination, every column valid, no bias / act / accumulate
   int ksplit;              // > 1: the K steps are split over a (1,1,ksplit) cluster, partial tiles reduced through DSMEM
+  // vertical-tap sharing (3x3, tile inside one image): a K step is one (dx, source, chunk); its A box holds th + 2 rows
+  // fetched ONCE, the three vertical taps are UMMA descriptors started vt_row16 (16-byte units) = one image row apart,
+  // and the stage carries the three taps' weight tiles (K coordinates vt_kstride apart)
+  int vt;
+  uint32_t vt_row16;
+  int vt_kstride;
   KStep steps[kMaxSteps];
 };
 
@@ -229,12 +235,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int i = ks_begin; i < ks_end; ++i) {
         const KStep st = p.steps[i];
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        mbar_arrive_expect_tx_e(&full_bar[stage], p.a_bytes + p.b_bytes, el);
+        mbar_arrive_expect_tx_e(&full_bar[stage], p.a_bytes + (p.vt ? 3u : 1u) * p.b_bytes, el);
         void* a_dst = ring + (size_t)stage * p.stage_bytes;
-        void* b_dst = (uint8_t*)a_dst + p.a_bytes;
+        uint8_t* b_dst = (uint8_t*)a_dst + p.a_bytes;
         const CUtensorMap* m = st.map == 0 ? &map_a0 : (st.map == 1 ? &map_a1 : (st.map == 2 ? &map_a2 : &map_a3));
         tma_load_4d_e(a_dst, m, &full_bar[stage], st.c0, w0 + st.dx - (p.dbg_rowshift ? 1 : 0), h0 + st.dy, n0, el);
         tma_load_2d_e(b_dst, &map_w, &full_bar[stage], st.k, col0, el);
+        if (p.vt) {
+          tma_load_2d_e(b_dst + p.b_bytes, &map_w, &full_bar[stage], st.k + p.vt_kstride, col0, el);
+          tma_load_2d_e(b_dst + 2 * p.b_bytes, &map_w, &full_bar[stage], st.k + 2 * p.vt_kstride, col0, el);
+        }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -262,6 +272,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (k < kk)
           umma_bf16_e(tmem_base, desc_hi | (uint64_t)(a_lo + 2u * k), desc_hi | (uint64_t)(b_lo + 2u * k), idesc,
                       (i != ks_begin || k != 0) ? 1u : 0u, el);
+      }
+      if (p.vt) {
+        // the other two vertical taps of this (dx, chunk): same stage, A one / two image rows further down
+        const uint32_t b_u = p.b_bytes >> 4;
+#pragma unroll
+        for (int j = 1; j < 3; ++j) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < kk)
+              umma_bf16_e(tmem_base, desc_hi | (uint64_t)(a_lo + (uint32_t)j * p.vt_row16 + 2u * k),
+                          desc_hi | (uint64_t)(b_lo + (uint32_t)j * b_u + 2u * k), idesc, 1u, el);
+          }
+        }
       }
       umma_commit_e(&empty_bar[stage], el);
       if (i == ks_end - 1) umma_commit_e(&tmem_full_bar, el);
@@ -500,6 +523,19 @@ static bool conv_tc_fuses_stats(const smsut_conv_tc_args* a) {
   return tn == 1 || (th * tw) % 32 == 0;
 }
 
+// N tile: the widest of 256..16 dividing the column count that still gives ~a wave of CTAs (or <= 64)
+static int default_bn(int m_tiles, int ncols_pad) {
+  const int cands[5] = {256, 128, 64, 32, 16};
+  int bn = 16;
+  for (int i = 0; i < 5; ++i) {
+    const int c = cands[i];
+    if (c > ncols_pad || ncols_pad % c != 0) continue;
+    bn = c;
+    if ((int64_t)m_tiles * (ncols_pad / c) >= 120 || c <= 64) break;
+  }
+  return bn;
+}
+
 static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a != nullptr, -1, "null args");
   SMSUT_CHECK(a->nsrc == 1 || a->nsrc == 2, -1, "nsrc must be 1 or 2");
@@ -552,13 +588,44 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   if (a->kind == SMSUT_TC_CONV || a->kind == SMSUT_TC_CONVT_FWD) {
     const int ks = a->kind == SMSUT_TC_CONV ? a->ksize : 1;
     SMSUT_CHECK(ks == 1 || ks == 3 || ks == 5, -1, "ksize must be 1, 3 or 5");
+    // vertical-tap sharing: 3x3, the 128-pixel tile lies inside one image and its rows are whole 8-pixel groups, so
+    // that "one image row further down" is a whole number of swizzle atoms (SMSUT_TC_VT=0 switches it off)
+    // Measured on B200 (scripts/conv_classes.py, us per launch at 16 slices, off -> on): 256->256 @16x16 19.0 -> 15.0,
+    // 128->256 13.5 -> 11.4, 64->128 @32x32 13.1 -> 11.6, 256->128 21.3 -> 19.6; but 64->64 @64x64 19.5 -> 25.5 (th = 2:
+    // the halo doubles the rows fetched and the 56 KB stage leaves no room for the second CTA per SM) and a 256-wide
+    // N tile leaves a single stage.  Hence: th >= 4 and at least two stages.  SMSUT_TC_VT=0 off, =2 wherever legal.
+    const char* vt_env = getenv("SMSUT_TC_VT");      // read per call: the parity tests run both settings in one process
+    const int vt_knob = vt_env ? atoi(vt_env) : 1;
+    p.vt = (vt_knob && a->kind == SMSUT_TC_CONV && ks == 3 && p.tn == 1 && p.tw % 8 == 0 && p.th + 2 <= 256) ? 1 : 0;
+    if (p.vt && vt_knob != 2) {
+      const int bn0 = a->bn > 0 ? a->bn : default_bn(m_tiles, a->ncols_pad);
+      const size_t stage = (size_t)(p.th + 2) * p.tw * cc * 2 + 3u * (size_t)bn0 * cc * 2;
+      if (p.th < 4 || 2 * stage > 200u * 1024u) p.vt = 0;
+    }
     for (int s = 0; s < a->nsrc; ++s) {
       rc = make_act_map(&maps[s], a->src[s], a->src_c[s], a->w, a->h, a->n, a->src_ld[s],
-                        (int64_t)a->src_ld[s] * a->w, (int64_t)a->src_ld[s] * a->w * a->h, cc, p.tw, p.th, p.tn);
+                        (int64_t)a->src_ld[s] * a->w, (int64_t)a->src_ld[s] * a->w * a->h, cc, p.tw,
+                        p.vt ? p.th + 2 : p.th, p.tn);
       if (rc) return rc;
     }
     const int r = ks / 2;
     int t = 0;
+    if (p.vt) {
+      p.vt_row16 = (uint32_t)(p.tw * cc * 2) >> 4;
+      p.vt_kstride = 3 * ctot;
+      for (int dx = -1; dx <= 1; ++dx) {
+        int coff = 0;
+        for (int s = 0; s < a->nsrc; ++s) {
+          for (int c0 = 0; c0 < a->src_c[s]; c0 += cc) {
+            SMSUT_CHECK(ns < kMaxSteps, -6, "too many K steps");
+            KStep& st = p.steps[ns++];
+            st.map = (int8_t)s; st.dy = -1; st.dx = (int8_t)dx; st.c0 = (int16_t)c0;
+            st.k = (dx + 1) * ctot + coff + c0;      // tap (dy = -1, dx); taps (0, dx), (+1, dx) are vt_kstride apart
+          }
+          coff += a->src_c[s];
+        }
+      }
+    } else
     for (int dy = -r; dy <= r; ++dy)
       for (int dx = -r; dx <= r; ++dx, ++t) {
         int coff = 0;
@@ -598,16 +665,7 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
 
   // N tile
   int bn = a->bn;
-  if (bn <= 0) {
-    const int cands[5] = {256, 128, 64, 32, 16};
-    bn = 16;
-    for (int i = 0; i < 5; ++i) {
-      const int c = cands[i];
-      if (c > a->ncols_pad || a->ncols_pad % c != 0) continue;
-      bn = c;
-      if ((int64_t)m_tiles * (a->ncols_pad / c) >= 120 || c <= 64) break;
-    }
-  }
+  if (bn <= 0) bn = default_bn(m_tiles, a->ncols_pad);
   // Deep layers: a handful of output tiles (32 at 16x16) each with a long K loop (36-72 steps of a narrow N tile).
   // Optional (SMSUT_TC_KSPLIT=2|4): take the widest N tile instead and split K over a (1, 1, ksplit) thread-block
   // cluster; the partial tiles meet in distributed shared memory (reduce-scatter: CTA k finishes every ksplit-th
@@ -650,9 +708,9 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   rc = make_mat_map(&map_w, a->wpack, ktot, a->ncols_pad, ktot, cc, bn);
   if (rc) return rc;
 
-  p.a_bytes = (uint32_t)kTileM * cc * 2;
+  p.a_bytes = (uint32_t)(p.vt ? (p.th + 2) * p.tw : kTileM) * cc * 2;
   p.b_bytes = (uint32_t)bn * cc * 2;
-  p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023u) & ~1023u);
+  p.stage_bytes = (p.a_bytes + (p.vt ? 3u : 1u) * p.b_bytes + 1023u) & ~1023u;
   int stages = (int)((200u * 1024u) / p.stage_bytes);
   if (stages > 6) stages = 6;
   {

@@ -85,6 +85,35 @@ def test_conv_tc_fprop_dgrad_wgrad(ops, cins, cout, h, n, ks):
     assert rel(dw, dw_ref) < 1e-2
 
 
+VT_CASES = [([32], 64, 64, 2), ([64], 64, 64, 3), ([64, 64], 64, 64, 2), ([64], 128, 32, 2), ([128, 128], 128, 32, 2),
+            ([128], 256, 16, 2), ([256], 256, 16, 3), ([16], 32, 64, 2), ([32, 16], 48, 32, 2), ([256], 256, 8, 4)]
+
+
+@pytest.mark.parametrize("cins,cout,h,n", VT_CASES)
+def test_conv_tc_vertical_tap_sharing(ops, monkeypatch, cins, cout, h, n):
+    """SMSUT_TC_VT=1: a K step of conv_tc_kernel is one (dx, source, chunk) whose A box of th + 2 rows is fetched once
+    and serves the three vertical taps through descriptor offsets.  Same results as the one-box-per-tap path
+    (different accumulation order only) and as the fp32 statement; 8x8 (tile spans two images) must fall back."""
+    torch.manual_seed(21)
+    cin = sum(cins)
+    xs = [rnd(n, c, h, h) for c in cins]
+    wt = rnd(cout, cin, 3, 3, scale=(2.0 / (cin * 9)) ** 0.5)
+    pw = make_pack(ops, wt)
+    x_cat, dy = torch.cat(xs, 1), rnd(n, cout, h, h)
+    y_ref = F.conv2d(x_cat, wt, padding=1)
+    dx_ref = torch.nn.grad.conv2d_input(x_cat.shape, wt, dy, padding=1)
+    got = {}
+    for vt in ("0", "2", "1"):          # off / wherever legal / the default rule (th >= 4, >= 2 stages)
+        monkeypatch.setenv("SMSUT_TC_VT", vt)
+        y, st = ops.conv_fprop([nhwc(x) for x in xs], pw, want_stats=True)
+        dxs = ops.conv_dgrad(nhwc(dy), pw, splits=cins)
+        got[vt] = (nchw(y), torch.cat([nchw(d) for d in dxs], 1), st)
+        assert rel(got[vt][0], y_ref) < 1e-2 and rel(got[vt][1], dx_ref) < 1e-2, vt
+    for vt in ("1", "2"):
+        assert rel(got[vt][0], got["0"][0]) < 2e-3 and rel(got[vt][1], got["0"][1]) < 2e-3
+        assert rel(got[vt][2], got["0"][2]) < 1e-3
+
+
 @pytest.mark.parametrize("cins,cout,h,n,ks", [([16], 16, 256, 1, 3), ([16, 16], 16, 128, 2, 3), ([32], 64, 64, 2, 3),
                                               ([64, 64], 64, 64, 2, 3), ([128], 256, 16, 2, 3), ([256], 256, 8, 4, 3),
                                               ([64], 32, 64, 2, 1)])
