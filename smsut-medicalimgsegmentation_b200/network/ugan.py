@@ -114,7 +114,18 @@ class UGAN(nn.Module):
                                    tranposed=True, use_tanh=False)
         _kaiming_init(self)
 
-    def _branches(self, x, m):
+    def _seg_half(self, xin):
+        seg_out, seg_ens = self.seg_encoder.forward_nhwc(xin)
+        seg_out = self.enc5.forward_nhwc([seg_out])
+        return self.seg_decoder(to_nchw(seg_out), seg_ens)
+
+    def _branches(self, x, m, seg_rows=None, seg_rest=True):
+        """seg_rows = r: the segmentation half runs as two independent sub-batches -- slices [:r] with an autograd
+        graph, slices [r:] without one (or not at all when seg_rest is False) -- and `seg` is returned as the pair.
+        Every layer of the generator is per-sample (InstanceNorm), so the values equal the full-batch forward; the
+        trainer uses it where only the labelled slices' logits are differentiated (uganConsisTrainer.py:151-155:
+        g_loss_seg = loss(y_fake[:bs], y_real); the other slices' logits are only argmax targets), which halves that
+        branch's backward instead of pushing zeros through it."""
         if x.shape[1] != 1:
             raise NotImplementedError("the path translates single-channel slices (cfg.img_channels = 1)")
         refresh_packs(self)
@@ -124,16 +135,28 @@ class UGAN(nn.Module):
         # the segmentation half runs on a branch stream beside the translation half (they share only weights); a
         # forward that itself runs inside a branch (the cycle pass of the trainer) uses another stream, so that the
         # backward of the first pass's segmentation half is not queued behind the second pass's
-        with ops.parallel_branch(0 if ops.current_branch() is None else 3) as br:
-            seg_out, seg_ens = self.seg_encoder.forward_nhwc(Fn.ImageInputFn.apply(x))
-            seg_out = self.enc5.forward_nhwc([seg_out])
-            seg = self.seg_decoder(to_nchw(seg_out), seg_ens)
+        if seg_rows is None:
+            with ops.parallel_branch(0 if ops.current_branch() is None else 3) as br:
+                seg = self._seg_half(Fn.ImageInputFn.apply(x))
+            joins = [(br, seg)]
+        else:
+            xin = Fn.ImageInputFn.apply(x)            # before the forks: both sub-batches read it
+            with ops.parallel_branch(0 if ops.current_branch() is None else 3) as br:
+                seg_a = self._seg_half(xin[:seg_rows])
+            joins, seg_b = [(br, seg_a)], None
+            if seg_rest:
+                with ops.parallel_branch(6) as br2:
+                    with torch.no_grad():
+                        seg_b = self._seg_half(xin[seg_rows:])
+                joins.append((br2, seg_b))
+            seg = (seg_a, seg_b)
 
         tsl_in = _TslInputFn.apply(x, m)
         tsl_out, tsl_ens = self.tsl_encoder.forward_nhwc(tsl_in)
         tsl_out_1 = self.enc5.forward_nhwc([tsl_out])
         tsl = self.tsl_decoder(to_nchw(tsl_out_1), tsl_ens)
-        br.join(seg)
+        for b, t in joins:
+            b.join(t)
         return seg, tsl, tsl_out_1
 
     def forward(self, x, m=None):
@@ -161,8 +184,10 @@ class UGANnce(UGAN):
                                    tranposed=True, use_tanh=False)
         _kaiming_init(self)
 
-    def forward(self, x, m=None, sample_ids=None, val_phase=False):
-        seg, tsl, tsl_out_1 = self._branches(x, m)
+    def forward(self, x, m=None, sample_ids=None, val_phase=False, seg_rows=None, seg_rest=True):
+        """seg_rows / seg_rest (extension, see UGAN._branches): `seg` comes back as (seg[:r] with graph, seg[r:]
+        without graph or None)."""
+        seg, tsl, tsl_out_1 = self._branches(x, m, seg_rows, seg_rest)
         if val_phase:
             return seg, tsl
         feats = [to_nchw(tsl_out_1)]

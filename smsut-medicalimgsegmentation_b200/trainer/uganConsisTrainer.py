@@ -36,6 +36,9 @@ from .uganShp0Trainer import UGANShp0Trainer
 # stage the generator's backward so that the cycle pass's half runs beside the discriminator phase (train_step)
 SPLIT_G_BACKWARD = [os.environ.get("SMSUT_SPLIT_G_BACKWARD", "1") != "0"]
 
+# run the first pass's segmentation half as labelled (with graph) + unlabelled (no graph) sub-batches (train_step)
+SPLIT_SEG_ROWS = [os.environ.get("SMSUT_SPLIT_SEG_ROWS", "1") != "0"]
+
 LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
 
 
@@ -72,8 +75,15 @@ class UGANConsisTrainer(UGANShp0Trainer):
         self.lr_sched.tick()
 
         # generator forward shared by the D phase (detached) and the G phase
-        y_fake, x_fake, feat_x_pool, sample_ids = self.net(x_real, vec_ot, sample_ids=sample_ids)
         split = SPLIT_G_BACKWARD[0]
+        if SPLIT_SEG_ROWS[0]:
+            # only the labelled slices' logits are differentiated (L153: loss(y_fake[:bs], y_real)); the unlabelled ones
+            # are argmax targets of the consistency loss (needed only when it is on): no autograd graph for them
+            (y_fake_lb, y_fake_ul), x_fake, feat_x_pool, sample_ids = self.net(
+                x_real, vec_ot, sample_ids=sample_ids, seg_rows=bs, seg_rest=bool(use_semi))
+        else:
+            y_fake, x_fake, feat_x_pool, sample_ids = self.net(x_real, vec_ot, sample_ids=sample_ids)
+            y_fake_lb, y_fake_ul = y_fake[:bs], None
 
         # ---------------- the cycle pass of the G phase (L157-168) needs only x_fake and G's weights: it runs on a
         # branch stream beside the whole D phase (forward, gradient penalty, backward, Adam step).
@@ -90,10 +100,12 @@ class UGANConsisTrainer(UGANShp0Trainer):
             self.optimizer.zero_grad()                 # before the fork: stage A accumulates into G's gradients
         x_fake_c = x_fake.detach().requires_grad_(True) if split else x_fake
         with ops.parallel_branch(4) as b_cyc:
-            g_loss_seg = self.loss(y_fake[:bs], y_real)
+            g_loss_seg = self.loss(y_fake_lb, y_real)
             y_rec, x_rec, feat_f_pool, _ = self.net(x_fake_c, vec_to, sample_ids=sample_ids)
             g_loss_rec = Fn.L1MeanFn.apply(x_rec.contiguous(), x_real)
             if use_semi:
+                if y_fake_ul is not None:
+                    y_fake = torch.cat([y_fake_lb.detach(), y_fake_ul], dim=0)
                 g_loss_semi = self.consistency_loss(y_rec, y_fake)
             else:
                 g_loss_semi = torch.zeros((), device=x_real.device)
