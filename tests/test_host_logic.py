@@ -339,3 +339,31 @@ def test_resume_state_round_trip(exact, tmp_path):
     for (k, p), (_, q) in zip(a.ema.named_parameters(), b.ema.named_parameters()):
         assert torch.equal(p, q), k
     assert torch.equal(a.optimizer.mom, b.optimizer.mom) and torch.equal(a.lr_sched.iter_state, b.lr_sched.iter_state)
+
+
+def test_fit_validate_and_reference_format_checkpoints(exact, tmp_path, monkeypatch):
+    """`-p train` path of BaseTrainer (trainer/baseTrainer.py:125-201): fit = train_epoch + validate_epoch + best/last
+    checkpoints.  The checkpoints are the reference's format -- a plain state_dict of fp32 OIHW tensors without a
+    `module.` prefix (trainer/uganShp0Trainer.py:94-107) -- and load back into a fresh trainer (`-p test`)."""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    args = SimpleNamespace(fold=0, expr_name="t", input_size=32)
+    tr = UnetTrainer('train', args)
+    tr.expr_root = str(tmp_path)
+    tr.fit('inTurn', max_epoch=1, iters_per_epoch=2)
+    assert tr.iter == 2 and tr.epoch == 1
+    ck = torch.load(os.path.join(str(tmp_path), '000', 'ckpt', 'last.ckpt'))
+    assert set(ck) == set(O.unet_shapes()) and all(v.dtype == torch.float32 and v.device.type == 'cpu' for v in ck.values())
+    assert {k: tuple(v.shape) for k, v in ck.items()} == {k: tuple(v) for k, v in O.unet_shapes().items()}
+    assert os.path.exists(os.path.join(str(tmp_path), '000', 'ckpt', 'best.ckpt'))
+    te = UnetTrainer('test', args)
+    te.expr_root = str(tmp_path)
+    te.load_model('000', 'last')
+    for (k, p), (_, q) in zip(tr.net.state_dict().items(), te.net.state_dict().items()):
+        assert torch.equal(p.cpu(), q.cpu()), k
+    # the oracle evaluates the checkpoint to the same logits as the restored network
+    x, _ = O.synthetic_batch(2, 32, 5)
+    with torch.no_grad():
+        assert rel(te.net(x), O.unet_forward(ck, x)) < 1e-5
