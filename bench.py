@@ -28,6 +28,26 @@ from types import SimpleNamespace
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+
+class _StdoutToStderr:
+    """stdout carries exactly ONE JSON line, but libraries write to file descriptor 1 behind Python's back (NCCL prints
+    "NCCL version ..." at communicator creation): point fd 1 at stderr for the whole run and give it back only for
+    the result line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(text, flush=True)
+        os.dup2(2, 1)
+
+
+_OUT = None
+
 FLOP_PER_SLICE = 1.0763e11      # reference-as-executed conv+GEMM FLOPs per slice (SURVEY.md section 8d)
 METRIC, UNIT = "train slices/sec (256x256)", "slices/s"
 
@@ -123,7 +143,7 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _OUT.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -320,7 +340,7 @@ def run_ours(args):
                                 "sample": "6 timed iterations (after 1 warm-up) of the oracle's full uganConsis step at "
                                           f"4+4 256x256 slices ({sec:.2f} s each), fp32, torch CPU, {threads} threads"}
     if par.rank == 0:
-        print(json.dumps(line), flush=True)
+        _OUT.emit(json.dumps(line))
     if par.world > 1:
         # tearing down a NCCL communicator that live CUDA graphs still reference can block at exit: everything is
         # measured and printed, so synchronise, agree that every rank is done, and leave without the teardown
@@ -338,6 +358,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     a = ap.parse_args()
+    _OUT = _StdoutToStderr()
     if a.impl == "reference":
         run_reference(a)
     else:

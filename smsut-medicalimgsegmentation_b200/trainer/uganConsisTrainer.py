@@ -39,6 +39,9 @@ SPLIT_G_BACKWARD = [os.environ.get("SMSUT_SPLIT_G_BACKWARD", "1") != "0"]
 # run the first pass's segmentation half as labelled (with graph) + unlabelled (no graph) sub-batches (train_step)
 SPLIT_SEG_ROWS = [os.environ.get("SMSUT_SPLIT_SEG_ROWS", "1") != "0"]
 
+# D(x_real) and D(G(x).detach()) of the D phase as one 2B-slice pass (train_step); measured: see DESIGN.md
+BATCH_D_REAL_FAKE = [os.environ.get("SMSUT_BATCH_D", "0") != "0"]
+
 LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
 
 
@@ -121,18 +124,26 @@ class UGANConsisTrainer(UGANShp0Trainer):
         # kernels -> real on the current stream, fake and interpolated on branch streams (ops.parallel_branch)
         x_fake_d = x_fake.detach()
         refresh_packs(self.D)       # before the fork: all three passes read the bf16 weight copies this launch writes
-        with ops.parallel_branch(1) as b_fake:
-            out_src_f, _ = self.D(x_fake_d)
-            d_loss_fake = Fn.MeanFn.apply(out_src_f, 1.0)
         with ops.parallel_branch(2) as b_hat:
             x_hat = ops.lerp_rows(alpha, x_real, x_fake_d.contiguous()).requires_grad_(True)
             out_src_h, _ = self.D(x_hat)
             d_loss_gp = self.gradient_penalty(out_src_h, x_hat)
-
-        out_src, out_cls = self.D(x_real)
-        d_loss_real = Fn.MeanFn.apply(out_src, -1.0)
-        d_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_org)
-        b_fake.join(d_loss_fake)
+        if BATCH_D_REAL_FAKE[0]:
+            # D(x_real) and D(G(x).detach()) as ONE pass over 2B slices: every layer of D is per-sample (InstanceNorm),
+            # so the values are those of two passes; the discriminator's kernels are far smaller than the machine
+            nb = x_real.shape[0]
+            out_src, out_cls = self.D(torch.cat([x_real, x_fake_d], dim=0))
+            d_loss_real = Fn.MeanFn.apply(out_src[:nb].contiguous(), -1.0)
+            d_loss_fake = Fn.MeanFn.apply(out_src[nb:].contiguous(), 1.0)
+            d_loss_cls = Fn.CERowsFn.apply(out_cls[:nb].contiguous(), modal_org)
+        else:
+            with ops.parallel_branch(1) as b_fake:
+                out_src_f, _ = self.D(x_fake_d)
+                d_loss_fake = Fn.MeanFn.apply(out_src_f, 1.0)
+            out_src, out_cls = self.D(x_real)
+            d_loss_real = Fn.MeanFn.apply(out_src, -1.0)
+            d_loss_cls = Fn.CERowsFn.apply(out_cls.contiguous(), modal_org)
+            b_fake.join(d_loss_fake)
         b_hat.join(d_loss_gp)
 
         d_loss = d_loss_real + d_loss_fake + lambda_cls * d_loss_cls + lambda_gp * d_loss_gp
