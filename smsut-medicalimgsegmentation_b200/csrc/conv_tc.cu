@@ -596,7 +596,8 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
     // N tile leaves a single stage.  Hence: th >= 4 and at least two stages.  SMSUT_TC_VT=0 off, =2 wherever legal.
     const char* vt_env = getenv("SMSUT_TC_VT");      // read per call: the parity tests run both settings in one process
     const int vt_knob = vt_env ? atoi(vt_env) : 1;
-    p.vt = (vt_knob && a->kind == SMSUT_TC_CONV && ks == 3 && p.tn == 1 && p.tw % 8 == 0 && p.th + 2 <= 256) ? 1 : 0;
+    p.vt = (vt_knob && a->kind == SMSUT_TC_CONV && ks == 3 && p.tn == 1 && p.tw % 8 == 0 && p.th + 2 <= 256 &&
+            p.th + 2 <= a->h) ? 1 : 0;      // the halo box never exceeds the image height
     if (p.vt && vt_knob != 2) {
       const int bn0 = a->bn > 0 ? a->bn : default_bn(m_tiles, a->ncols_pad);
       const size_t stage = (size_t)(p.th + 2) * p.tw * cc * 2 + 3u * (size_t)bn0 * cc * 2;
