@@ -72,3 +72,98 @@ def test_two_rank_unet_step_equals_single_process_on_concatenated_batch(tmp_path
     for it in range(2):
         avg = 0.5 * (res[0][1][it] + res[1][1][it])
         assert abs(avg - ref_losses[it]) < 1e-4, (it, avg, ref_losses[it])
+
+
+def _gan_inputs(rank, bs=2, size=64):
+    from oracle import smsut_oracle as O
+    x1, y = O.synthetic_batch(bs, size, 11 + 10 * rank)
+    x2, _ = O.synthetic_batch(bs, size, 12 + 10 * rank)
+    alpha = torch.randn(2 * bs, generator=torch.Generator().manual_seed(3 + rank))
+    return x1, y, x2, alpha
+
+
+def _gan_worker(rank, world, port, outdir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), SMSUT_ALLOW_CPU_TEST_DOUBLE="1")
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    torch.set_num_threads(2)
+    import __graft_entry__ as g
+    g.load_package()
+    from types import SimpleNamespace
+
+    import cpu_ops_mock
+    from oracle import smsut_oracle as O
+    from smsut_b200.parallel import DataParallelContext
+    from smsut_b200.trainer.uganConsisTrainer import UGANConsisTrainer
+    size, bs = 64, 2
+    with cpu_ops_mock.installed(exact=True):
+        par = DataParallelContext(backend="gloo")
+        tr = UGANConsisTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=size))
+        tr.parallel = par
+        tr.net.load_state_dict(O.make_weights(O.ugan_shapes(), 7 + rank))        # replicas differ until the broadcast
+        tr.D.load_state_dict(O.make_weights(O.disc_shapes(size), 8 + rank))
+        par.broadcast_params(tr.optimizer, tr.d_optimizer)
+        x1, y, x2, alpha = _gan_inputs(rank)
+        ids = [torch.randperm(16, generator=torch.Generator().manual_seed(0))]
+        batch = tr.prepare_batch(x1, y, torch.full((bs,), 1), x2, torch.full((bs,), 3), 2)
+        losses = tr.train_step(*batch, alpha, ids, 0.7, True)
+        w = float(world)
+        torch.save(dict(losses=losses.tolist(),
+                        D={k: v.detach().clone() for k, v in tr.D.state_dict().items()},
+                        G={k: v.detach().clone() for k, v in tr.net.state_dict().items()},
+                        d_grads={k: p.grad.detach().clone() / w for k, p in tr.D.named_parameters()},
+                        g_grads={k: p.grad.detach().clone() / w for k, p in tr.net.named_parameters()}),
+                   os.path.join(outdir, f"gan{rank}.pt"))
+        par.close()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_ugan_consis_step_equals_single_process_on_global_batch(tmp_path):
+    """The headline path at world_size 2 (gloo, fp32 test double): per-rank 2 labelled + 2 unlabelled slices, the two
+    flat-gradient all-reduces and the Dice-statistic all-reduces inside both Dice/CE losses (segmentation and
+    consistency) -- including the staged generator backward, whose first stage runs before the D phase -- against the
+    oracle's single-process iteration on the global batch [lb0, lb1, ul0, ul1] (what nn.DataParallel computes).
+    Teacher-forced across D's Adam step like tests/test_host_logic.py."""
+    sys.path.insert(0, ROOT)
+    from oracle import smsut_oracle as O
+    ctx = mp.get_context("spawn")
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_gan_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(500)
+        assert p.exitcode == 0
+    res = [torch.load(os.path.join(str(tmp_path), f"gan{r}.pt")) for r in range(2)]
+
+    def rel(a, b):
+        return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+    size, bs = 64, 2
+    ins = [_gan_inputs(r) for r in range(2)]
+    x = torch.cat([ins[0][0], ins[1][0], ins[0][2], ins[1][2]])
+    y = torch.cat([ins[0][1], ins[1][1]])
+    modal = torch.cat([torch.full((2 * bs,), 1), torch.full((2 * bs,), 3)])
+    alpha = torch.cat([ins[0][3][:bs], ins[1][3][:bs], ins[0][3][bs:], ins[1][3][bs:]]).view(-1, 1, 1, 1)
+    ids = [torch.randperm(16, generator=torch.Generator().manual_seed(0))]
+    G, D = O.make_weights(O.ugan_shapes(), 7), O.make_weights(O.disc_shapes(size), 8)      # rank 0's weights
+    ref, d_grads = O.ugan_d_phase(G, D, {}, x, modal, 2, alpha, ids, 1e-2)
+    # replicas stay identical, and their averaged D gradient is the global-batch gradient
+    for k in D:
+        assert rel(res[0]["D"][k], res[1]["D"][k]) < 1e-6, k
+    # the GP double backward dominates these gradients (O(1e3 - 1e4) values).  Convolutions over 4 and over 8 slices round
+    # differently; an fp32-rounding-level difference flips the LeakyReLU mask of the odd near-zero pre-activation near
+    # D's output, which moves that sample's input gradient -- and with it every layer's GP gradient -- by a fraction of
+    # a percent (measured: median 2.6e-3, max 6.9e-3; a missing all-reduce or a wrong 1/W would be off by 50-100 %)
+    d_rel = sorted(rel(res[0]["d_grads"][k], d_grads[k]) for k in D)
+    assert d_rel[len(d_rel) // 2] < 1e-2 and d_rel[-1] < 3e-2, (d_rel[len(d_rel) // 2], d_rel[-1])
+    Dt = {k: v.clone() for k, v in res[0]["D"].items()}                                    # teacher-force the G phase
+    g_ref, g_grads = O.ugan_g_phase(G, Dt, {}, x, y, modal, 2, ids, 1e-2, 1000, 0.7, nce_batch=2 * 8)      # PatchNCELoss(cfg.batch_size * world): the groups stay the per-rank ones
+    ref.update(g_ref)
+    keys = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
+    for i, k in enumerate(keys):
+        avg = 0.5 * (res[0]["losses"][i] + res[1]["losses"][i])      # means and (global Dice + local CE) both average
+        assert abs(avg - ref[k]) < 5e-4 * max(1.0, abs(ref[k])), (k, avg, ref[k])
+    for k in g_grads:
+        assert rel(res[0]["G"][k], res[1]["G"][k]) < 1e-6, k
+        assert rel(res[0]["g_grads"][k], g_grads[k]) < 8e-2, k
