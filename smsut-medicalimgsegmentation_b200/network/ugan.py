@@ -119,7 +119,7 @@ class UGAN(nn.Module):
         seg_out = self.enc5.forward_nhwc([seg_out])
         return self.seg_decoder(to_nchw(seg_out), seg_ens)
 
-    def _branches(self, x, m, seg_rows=None, seg_rest=True):
+    def _branches(self, x, m, seg_rows=None, seg_rest=True, want_seg=True):
         """seg_rows = r: the segmentation half runs as two independent sub-batches -- slices [:r] with an autograd
         graph, slices [r:] without one (or not at all when seg_rest is False) -- and `seg` is returned as the pair.
         Every layer of the generator is per-sample (InstanceNorm), so the values equal the full-batch forward; the
@@ -135,7 +135,9 @@ class UGAN(nn.Module):
         # the segmentation half runs on a branch stream beside the translation half (they share only weights); a
         # forward that itself runs inside a branch (the cycle pass of the trainer) uses another stream, so that the
         # backward of the first pass's segmentation half is not queued behind the second pass's
-        if seg_rows is None:
+        if not want_seg:
+            seg, joins = None, []       # the caller discards the logits (cycle pass while the consistency loss is off)
+        elif seg_rows is None:
             with ops.parallel_branch(0 if ops.current_branch() is None else 3) as br:
                 seg = self._seg_half(Fn.ImageInputFn.apply(x))
             joins = [(br, seg)]
@@ -184,10 +186,10 @@ class UGANnce(UGAN):
                                    tranposed=True, use_tanh=False)
         _kaiming_init(self)
 
-    def forward(self, x, m=None, sample_ids=None, val_phase=False, seg_rows=None, seg_rest=True):
+    def forward(self, x, m=None, sample_ids=None, val_phase=False, seg_rows=None, seg_rest=True, want_seg=True):
         """seg_rows / seg_rest (extension, see UGAN._branches): `seg` comes back as (seg[:r] with graph, seg[r:]
-        without graph or None)."""
-        seg, tsl, tsl_out_1 = self._branches(x, m, seg_rows, seg_rest)
+        without graph or None).  want_seg=False: the segmentation half is not run and `seg` is None."""
+        seg, tsl, tsl_out_1 = self._branches(x, m, seg_rows, seg_rest, want_seg)
         if val_phase:
             return seg, tsl
         feats = [to_nchw(tsl_out_1)]

@@ -104,7 +104,10 @@ class UGANConsisTrainer(UGANShp0Trainer):
         x_fake_c = x_fake.detach().requires_grad_(True) if split else x_fake
         with ops.parallel_branch(4) as b_cyc:
             g_loss_seg = self.loss(y_fake_lb, y_real)
-            y_rec, x_rec, feat_f_pool, _ = self.net(x_fake_c, vec_to, sample_ids=sample_ids)
+            # y_rec only feeds the consistency loss (L162-168): while that is off (iter < semi_from_iter) the cycle
+            # pass's segmentation half is not run at all (the reference computes it and drops it)
+            y_rec, x_rec, feat_f_pool, _ = self.net(x_fake_c, vec_to, sample_ids=sample_ids,
+                                                    want_seg=bool(use_semi) or not SPLIT_SEG_ROWS[0])
             g_loss_rec = Fn.L1MeanFn.apply(x_rec.contiguous(), x_real)
             if use_semi:
                 if y_fake_ul is not None:
