@@ -167,3 +167,98 @@ def test_two_rank_ugan_consis_step_equals_single_process_on_global_batch(tmp_pat
     for k in g_grads:
         assert rel(res[0]["G"][k], res[1]["G"][k]) < 1e-6, k
         assert rel(res[0]["g_grads"][k], g_grads[k]) < 8e-2, k
+
+
+def _semi_worker(rank, world, port, outdir, which):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), SMSUT_ALLOW_CPU_TEST_DOUBLE="1")
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    torch.set_num_threads(2)
+    import __graft_entry__ as g
+    g.load_package()
+    from types import SimpleNamespace
+
+    import cpu_ops_mock
+    from oracle import smsut_oracle as O
+    from smsut_b200.parallel import DataParallelContext
+    args = SimpleNamespace(fold=0, expr_name=None, input_size=64)
+    with cpu_ops_mock.installed(exact=True):
+        par = DataParallelContext(backend="gloo")
+        if which == "mean_teacher":
+            from smsut_b200.trainer.meanTeacherTrainer import MeanTeacherTrainer
+            tr = MeanTeacherTrainer('train', args)
+            tr.semi_from_iter = 1
+            nets = dict(net=tr.net, ema=tr.ema)
+            opts = [tr.optimizer]
+        else:
+            from smsut_b200.trainer.crossPseTrainer import crossPseTrainer
+            tr = crossPseTrainer('train', args)
+            nets = dict(net=tr.net, net2=tr.net2)
+            opts = [tr.optimizer1, tr.optimizer2]
+        tr.parallel = par
+        for i, n in enumerate(nets.values()):
+            n.load_state_dict(O.make_weights(O.unet_shapes(), 31 + i))          # same weights on both ranks
+        par.broadcast_params(*opts)
+        losses = []
+        for it in range(2):
+            x1, y = O.synthetic_batch(2, 64, 40 + it + 100 * rank)
+            x2, _ = O.synthetic_batch(2, 64, 50 + it + 100 * rank)
+            x = torch.cat([x1, x2])
+            if which == "mean_teacher":
+                noise = torch.clamp(torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(it + 10 * rank)) * 0.01,
+                                    -0.02, 0.02)
+                losses.append(tr.train_step(x, y, noise, 0.8).tolist())
+            else:
+                losses.append(tr.train_step(x, y, 0.05).tolist())
+        torch.save(dict(losses=losses, nets={k: {n: v.detach().clone() for n, v in m.state_dict().items()}
+                                             for k, m in nets.items()}), os.path.join(outdir, f"{which}{rank}.pt"))
+        par.close()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("which", ["mean_teacher", "cross_pse"])
+def test_two_rank_semi_supervised_steps_equal_single_process_on_global_batch(tmp_path, which):
+    """config 4 (mean teacher: gradient + Dice-statistic all-reduce, EMA update local and identical on every rank) and
+    the cross-pseudo-supervision trainer (two networks, four Dice/CE losses) at world_size 2 on gloo vs the oracle's
+    single-process steps on the global batch [lb0, lb1, ul0, ul1]."""
+    sys.path.insert(0, ROOT)
+    from oracle import smsut_oracle as O
+    ctx = mp.get_context("spawn")
+    port = 29700 + os.getpid() % 90 + (0 if which == "mean_teacher" else 100)
+    procs = [ctx.Process(target=_semi_worker, args=(r, 2, port, str(tmp_path), which)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(500)
+        assert p.exitcode == 0
+    res = [torch.load(os.path.join(str(tmp_path), f"{which}{r}.pt")) for r in range(2)]
+
+    def rel(a, b):
+        return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+    sd1, sd2 = O.make_weights(O.unet_shapes(), 31), O.make_weights(O.unet_shapes(), 32)
+    st1, st2 = {}, {}
+    for it in range(2):
+        xs1, ys, xs2 = [], [], []
+        for r in range(2):
+            x1, y = O.synthetic_batch(2, 64, 40 + it + 100 * r)
+            x2, _ = O.synthetic_batch(2, 64, 50 + it + 100 * r)
+            xs1.append(x1); ys.append(y); xs2.append(x2)
+        x, y = torch.cat(xs1 + xs2), torch.cat(ys)
+        lr = O.poly_lr(1e-2, max(it - 1, 0), 30000)
+        if which == "mean_teacher":
+            noise = torch.cat([torch.clamp(torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(it + 10 * r))
+                                           * 0.01, -0.02, 0.02) for r in range(2)])
+            ref = O.mean_teacher_step(sd1, sd2, st1, x, y, noise, lr, it, 0.8, warm=1)
+        else:
+            d, _, _ = O.cross_pse_step(sd1, sd2, st1, st2, x, y, lr, 0.05)
+            ref = [d[k] for k in ("seg1", "seg2", "semi1", "semi2")]
+        for i, v in enumerate(ref):
+            avg = 0.5 * (res[0]["losses"][it][i] + res[1]["losses"][it][i])
+            tol = 1e-4 if it == 0 else 2e-3     # iteration 1 sees argmax pseudo-labels / rounding of updated weights
+            assert abs(avg - float(v)) < tol * max(1.0, abs(float(v))), (it, i, avg, float(v))
+    names = list(res[0]["nets"])
+    for name, sd in zip(names, (sd1, sd2)):
+        for k in sd:
+            assert rel(res[0]["nets"][name][k], res[1]["nets"][name][k]) < 1e-6, (name, k)
+            assert rel(res[0]["nets"][name][k], sd[k]) < 2e-3, (name, k)
