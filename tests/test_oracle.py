@@ -202,3 +202,25 @@ def test_ugan_shape_step_matches_reference_fixture(name, lambda_shp):
     assert np.allclose(gsum, f[f"{name}.G_checksum"], rtol=2e-2, atol=0.5)
     dsum = np.array([v.double().sum().item() for v in D.values()])
     assert np.abs(dsum - f[f"{name}.D_checksum"]).max() < 0.5      # Adam: lr * sign(g) on near-zero gradients
+
+
+def test_mean_teacher_steps_match_reference_fixture():
+    """three meanTeacherTrainer iterations (trainer/meanTeacherTrainer.py:95-153) starting at iter 99: the consistency
+    loss and the EMA decay switch on at iter 100 (config 4 of BASELINE.json)"""
+    f = load("mean_teacher")
+    sd, ema = O.make_weights(O.unet_shapes(), 71), O.make_weights(O.unet_shapes(), 72)
+    st = {}
+    for k in range(3):
+        it = 99 + k
+        x1, y = O.synthetic_batch(2, 64, 81 + k)
+        x2, _ = O.synthetic_batch(2, 64, 91 + k)
+        noise = torch.clamp(torch.randn(2, 1, 64, 64, generator=torch.Generator().manual_seed(k)) * 0.01, -0.02, 0.02)
+        seg, semi = O.mean_teacher_step(sd, ema, st, torch.cat([x1, x2]), y, noise, O.poly_lr(1e-2, it - 1, 30000), it, 0.8)
+        assert abs(seg - f[f"losses{k}"][0]) < 1e-5 * (1 + k * 20) and abs(semi - f[f"losses{k}"][1]) < 1e-6 * (1 + k * 20)
+        assert (semi == 0.0) == (it < 100)
+        for name, d in (("net", sd), ("ema", ema)):
+            norms = np.array([v.double().norm().item() for v in d.values()])
+            sums = np.array([v.double().sum().item() for v in d.values()])
+            assert np.allclose(norms, f[f"{name}_norm{k}"], rtol=1e-4, atol=1e-5), (k, name)
+            assert np.allclose(sums, f[f"{name}_sum{k}"], rtol=1e-3, atol=2e-3), (k, name)
+    assert close(sd["decoder.fc.weight"], f["fc"], 1e-4) and close(ema["decoder.fc.weight"], f["ema_fc"], 1e-4)
