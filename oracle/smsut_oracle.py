@@ -567,3 +567,29 @@ def ugan_shape_step(G, D, g_state, d_state, x_real, y_real, modal_org, mj, alpha
     g_grads = dict(zip(used, torch.autograd.grad(g_loss, list(used.values()))))
     sgd_update({k: G[k] for k in used}, g_grads, g_state, lr)
     return {k: float(v.detach()) for k, v in losses.items()}, d_grads, g_grads
+
+
+def mo_matrix(prd_npys, gt_npys, n_modal=4, n_label=4):
+    """Modality-organ Dice matrix of misc/utils.py:180-203 (get_mo_matrix) in numpy.  prd_npys / gt_npys: dicts
+    '<modality index>_<patient>' -> (slices, H, W) integer label volumes.  The per-volume score is
+    medpy.metric.binary.dc (medpy is not installed here; its published definition: 2 |p & g| / (|p| + |g|) over the
+    boolean masks, 0.0 when both are empty), averaged over the volumes of a modality; last row / column = means."""
+    import numpy as np
+    matrix = np.zeros((n_modal, n_label))
+    n = np.zeros((n_modal, 1))
+    for k in gt_npys.keys():
+        m = int(k.split('_')[0])
+        p, g = np.asarray(prd_npys[k]), np.asarray(gt_npys[k])
+        for i in range(n_label):
+            j = i + 1
+            a, b = (p == j), (g == j)
+            denom = float(a.sum() + b.sum())
+            matrix[m][i] += 2.0 * float((a & b).sum()) / denom if denom > 0 else 0.0
+        n[m] += 1
+    n[n == 0] += 1e-8
+    matrix /= n
+    full = np.zeros((n_modal + 1, n_label + 1))
+    full[:n_modal, :n_label] = matrix
+    full[-1, :] = np.mean(full[0:n_modal], axis=0)
+    full[:, -1] = np.mean(full[:, 0:n_label], axis=1)
+    return full

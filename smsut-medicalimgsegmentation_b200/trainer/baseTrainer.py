@@ -107,13 +107,43 @@ class BaseTrainer(object):
             tic = time.time()
             self.train_epoch(train_lb_loader, train_ul_loader, None, num_iter=iters_per_epoch)
             self.epoch += 1
-            dice = self.validate_epoch(test_loader)
+            self.validate_epoch(test_loader)
+            dice = self.validate_dice()[0]['dice']        # the reference's model-selection metric (baseTrainer.py:176-180)
             self.info('[TRN/TST] Epoch: %d(%d)/%d, elapsed: %.2fs, dice: %.4f' %
                       (epoch, best_epoch, cfg.max_epoch, time.time() - tic, dice))
             if dice >= best:
                 best, best_epoch = dice, epoch
                 self.save_model(prefix='best')
         self.save_model(prefix='last')
+
+    def validate_dice(self, volume_confusion=None):
+        """The reference's selection metric (baseTrainer.py:246-252 -> misc/utils.py:180-203 get_mo_matrix): Dice per
+        volume and organ, averaged over the volumes of a modality, then over organs / modalities; from the per-volume
+        confusion counts of the last validate_epoch instead of medpy on host volumes.  medpy.metric.dc(p, g) =
+        2 |p & g| / (|p| + |g|), and 0 when both are empty.  Returns (dict like the reference's, matrix)."""
+        confs = self.volume_confusion if volume_confusion is None else volume_confusion
+        n_modal, n_label = cfg.n_modal, cfg.n_label
+        matrix = np.zeros((n_modal, n_label))
+        n = np.zeros((n_modal, 1))
+        for key, cv in confs.items():
+            m = key.split('_')[0]
+            m = int(m) if m.isdigit() else cfg.Modality[m].value
+            c = cv.cpu().numpy().astype(np.float64)
+            inter, size_p, size_g = np.diag(c), c.sum(0), c.sum(1)
+            for i in range(n_label):
+                j = i + 1
+                denom = size_p[j] + size_g[j]
+                matrix[m][i] += 2.0 * inter[j] / denom if denom > 0 else 0.0
+            n[m] += 1
+        n[n == 0] += 1e-8
+        matrix /= n
+        full = np.zeros((n_modal + 1, n_label + 1))
+        full[:n_modal, :n_label] = matrix
+        full[-1, :] = np.mean(full[0:n_modal], axis=0)
+        full[:, -1] = np.mean(full[:, 0:n_label], axis=1)
+        dices = {f'dice_{i}': full[i, -1] for i in range(n_modal)}
+        dices['dice'] = full[-1, -1]
+        return dices, full
 
     @abc.abstractmethod
     def train_epoch(self, lb_loader, ul_loader, meter, num_iter=None):
@@ -128,6 +158,7 @@ class BaseTrainer(object):
         self.net.eval()
         n_cls = cfg.n_label + 1
         conf = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=self.device)     # conf[label, prediction]
+        vol_conf = {}
         with torch.no_grad():
             for img, msk, mdl, inm in loader:
                 b, c, h, w = img.shape
@@ -138,8 +169,23 @@ class BaseTrainer(object):
                 out = self.segment(img)[:b]
                 # fp32 logits as (pixels, classes): zero-copy for the channels-last tensors the networks return
                 logits = out.permute(0, 2, 3, 1).reshape(-1, n_cls)
-                ops.confusion_counts(logits if logits.is_contiguous() else logits.contiguous(), msk.reshape(-1), conf)
+                logits = logits if logits.is_contiguous() else logits.contiguous()
+                ops.confusion_counts(logits, msk.reshape(-1), conf)
+                # per-volume counts for the modality-organ matrix: slices are named '<modality>_<patient>_<z>'
+                # (baseTrainer.py:241); consecutive slices of one volume share one accumulator
+                if inm is None:
+                    continue                # unnamed slices: only the global counts
+                i0 = 0
+                keys = ['_'.join(str(nm).split('_')[:2]) for nm in inm][:b]
+                for i in range(1, b + 1):
+                    if i == b or keys[i] != keys[i0]:
+                        cv = vol_conf.get(keys[i0])
+                        if cv is None:
+                            cv = vol_conf[keys[i0]] = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=self.device)
+                        ops.confusion_counts(logits[i0 * h * w:i * h * w], msk[i0:i].reshape(-1), cv)
+                        i0 = i
         self.confusion = conf
+        self.volume_confusion = vol_conf
         inter = conf.diagonal().double()
         denom = (conf.sum(0) + conf.sum(1)).double()
         dice = (2 * inter[1:] / denom[1:].clamp_min(1)).mean().item()

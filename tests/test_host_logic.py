@@ -367,3 +367,54 @@ def test_fit_validate_and_reference_format_checkpoints(exact, tmp_path, monkeypa
     x, _ = O.synthetic_batch(2, 32, 5)
     with torch.no_grad():
         assert rel(te.net(x), O.unet_forward(ck, x)) < 1e-5
+
+
+def test_validation_modality_organ_matrix_matches_oracle(exact, monkeypatch):
+    """validate_epoch + validate_dice: the modality-organ Dice matrix of get_mo_matrix
+    (misc/utils.py:180-203) from per-volume confusion counts, incl. a ragged last batch (padded to cfg.batch_size) and
+    a volume that spans two batches."""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    monkeypatch.setattr(cfg, "batch_size", 4)
+    tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=32))
+    sd = O.make_weights(O.unet_shapes(), 5)
+    tr.net.load_state_dict(sd)
+    # modality 0: volumes a (4 slices) and b (6 slices: one full batch + a ragged batch of 2); modality 2: volume c (4)
+    layout = [(0, 'a', 4), (0, 'b', 4), (0, 'b', 2), (2, 'c', 4)]
+    batches, z0 = [], {}
+    for bi, (m, pid, n) in enumerate(layout):
+        img, lab = O.synthetic_batch(n, 32, 300 + bi)
+        s = z0.get((m, pid), 0)
+        names = [f"{m}_{pid}_{s + z}" for z in range(n)]
+        z0[(m, pid)] = s + n
+        batches.append((img, lab, torch.full((n,), m), names))
+    dice = tr.validate_epoch(batches)
+    dices, matrix = tr.validate_dice()
+    prd, gt = {}, {}
+    for img, lab, mdl, names in batches:
+        pred = O.unet_forward(sd, img).argmax(1)
+        key = '_'.join(names[0].split('_')[:2])
+        prd[key] = torch.cat([prd[key], pred]) if key in prd else pred
+        gt[key] = torch.cat([gt[key], lab]) if key in gt else lab
+    ref = O.mo_matrix({k: v.numpy() for k, v in prd.items()}, {k: v.numpy() for k, v in gt.items()})
+    assert matrix.shape == (5, 5) and abs(matrix - ref).max() < 1e-12
+    assert abs(dices['dice'] - ref[-1, -1]) < 1e-12 and abs(dices['dice_2'] - ref[2, -1]) < 1e-12
+    assert dices['dice_1'] == 0.0 and sorted(tr.volume_confusion) == ['0_a', '0_b', '2_c']
+    assert int(tr.confusion.sum()) == 14 * 32 * 32 and 0.0 <= dice <= 1.0
+    assert int(sum(v.sum() for v in tr.volume_confusion.values())) == 14 * 32 * 32
+
+
+def test_validate_epoch_without_slice_names(exact, monkeypatch):
+    """loaders that yield no names (inm=None): global counts only, as tests/test_modules_gpu.py uses it"""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    monkeypatch.setattr(cfg, "batch_size", 4)
+    tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=32))
+    batches = []
+    for i, n in enumerate((4, 3)):
+        x, y = O.synthetic_batch(n, 32, 70 + i)
+        batches.append((x, y, torch.zeros(n, dtype=torch.int64), None))
+    dice = tr.validate_epoch(batches)
+    assert int(tr.confusion.sum()) == 7 * 32 * 32 and tr.volume_confusion == {} and 0.0 <= dice <= 1.0
