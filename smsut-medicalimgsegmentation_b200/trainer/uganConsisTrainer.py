@@ -240,6 +240,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
         ul_itr = iter(ul_loader)
         tic = time.time()
         losses = None
+        fixed = None        # the epoch's first labelled batch: the fixed slices of the sample grid (L83-90)
         for i in range(n_critic * (num_iter or cfg.num_iter_per_epoch)):
             try:
                 x_real1, y_real, modal_org1, _ = next(lb_itr)
@@ -252,6 +253,8 @@ class UGANConsisTrainer(UGANShp0Trainer):
                 ul_itr = iter(ul_loader)
                 x_real2, _, modal_org2, _ = next(ul_itr)
 
+            if fixed is None:
+                fixed = (x_real1, modal_org1)
             mj = random.randint(0, cfg.n_modal - 1)
             batch = self.prepare_batch(x_real1, y_real, modal_org1, x_real2, modal_org2, mj)
             alpha, sample_ids = self.draw(batch[0].size(0))
@@ -272,6 +275,9 @@ class UGANConsisTrainer(UGANShp0Trainer):
                     param_group['lr'] = lr_
                 opt._lr_host = lr_
             self.iter += 1
+        if getattr(self, 'save_samples', False) and fixed is not None:      # L205-214 (off by default: an image file per epoch)
+            self.sample_translations(*fixed, save_path=os.path.join(self.expr_root, self.model_idx, 'sample',
+                                                                    f'train-{self.epoch + 1}-images.png'))
         return losses
 
 

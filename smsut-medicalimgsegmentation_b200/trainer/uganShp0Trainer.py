@@ -91,6 +91,34 @@ class UGANShp0Trainer(BaseTrainer):
         out = (x + 1.) / 2.
         return out.clamp_(0, 1)
 
+    def sample_translations(self, x_fixed, modal_org, save_path=None):
+        """The per-epoch debug grid of uganShp0Trainer.py:219-228 / uganConsisTrainer.py:205-214: the fixed slices next
+        to their translation into every modality, concatenated along the width and de-normalised to [0, 1]
+        ((B, 1, H, (n_modal + 1) * W) fp32 on the host).  save_path: also written as one image (nrow=1, padding=0
+        like save_image) when PIL is importable."""
+        was_training = self.net.training
+        self.net.eval()
+        with torch.no_grad():
+            x_fixed = x_fixed.to(self.device)
+            vec_fixed_org = self.label2onehot(modal_org, cfg.n_modal).to(self.device)
+            x_fake_list = [x_fixed.float()]
+            for vec_fixed in self.create_vectors(vec_fixed_org, cfg.n_modal):
+                _, x_fake = self.translate(x_fixed, vec_fixed - vec_fixed_org)
+                x_fake_list.append(x_fake.float())
+            grid = self.denorm(torch.cat(x_fake_list, dim=3).cpu())
+        self.net.train(was_training)
+        if save_path is not None:
+            try:
+                from PIL import Image
+            except ImportError:
+                Image = None
+            if Image is not None:
+                os.makedirs(os.path.dirname(save_path) or '.', exist_ok=True)
+                rows = (grid[:, 0] * 255.0 + 0.5).clamp(0, 255).to(torch.uint8)       # save_image's quantisation
+                Image.fromarray(torch.cat(list(rows), dim=0).numpy()).save(save_path)
+                print(f'[*] Saved real and fake images into {save_path}.')
+        return grid
+
     def gradient_penalty(self, y, x):
         """mean_b (|| d sum(y) / d x_b ||_2 - 1)^2 with a differentiable first-order pass: the backward of every
         op of D emits its hand-written second-order kernels (functional.py)."""

@@ -418,3 +418,28 @@ def test_validate_epoch_without_slice_names(exact, monkeypatch):
         batches.append((x, y, torch.zeros(n, dtype=torch.int64), None))
     dice = tr.validate_epoch(batches)
     assert int(tr.confusion.sum()) == 7 * 32 * 32 and tr.volume_confusion == {} and 0.0 <= dice <= 1.0
+
+
+def test_translation_sample_grid_matches_oracle(exact, tmp_path):
+    """per-epoch sample grid (uganConsisTrainer.py:205-214): [x, G(x -> modality 0), ..., G(x -> modality 3)] along the
+    width, de-normalised"""
+    size = 64
+    tr, G, D = _consis_trainer(size)
+    x, _ = O.synthetic_batch(2, size, 17)
+    modal = torch.tensor([1, 3])
+    path = os.path.join(str(tmp_path), 'sample', 'train-1-images.png')
+    grid = tr.sample_translations(x, modal, save_path=path)
+    assert grid.shape == (2, 1, size, 5 * size) and grid.min() >= 0 and grid.max() <= 1
+    org = O.label2onehot(modal, 4)
+    cols = [x]
+    for j in range(4):
+        trg = O.label2onehot(torch.full((2,), j), 4)
+        cols.append(O.ugannce_forward(G, x, trg - org, val_phase=True)[1])
+    ref = ((torch.cat(cols, dim=3) + 1) / 2).clamp(0, 1)
+    assert rel(grid, ref) < 1e-4          # saturated tanh outputs: fp32 rounding of a sign-like head
+    try:
+        import PIL  # noqa: F401
+        assert os.path.exists(path)
+    except ImportError:
+        pass
+    assert tr.net.training
