@@ -443,3 +443,27 @@ def test_translation_sample_grid_matches_oracle(exact, tmp_path):
     except ImportError:
         pass
     assert tr.net.training
+
+
+def test_consis_train_epoch_loop_and_sample_file(exact, tmp_path, monkeypatch):
+    """the epoch loop around train_step (loader cycling, random draws, LR mirror, iteration counter, sample grid)"""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.data_loader import syntheticLoader as synlod
+    from smsut_b200.trainer.uganConsisTrainer import UGANConsisTrainer
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    tr = UGANConsisTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=64))
+    tr.expr_root, tr.save_samples, tr.semi_from_iter = str(tmp_path), True, 1
+    lb = synlod.get_loader(None, 'train', 0, 2, size=64, pool_batches=1)       # one batch each: the loaders must cycle
+    ul = synlod.get_loader(None, 'val', 0, 2, size=64, pool_batches=1)
+    w0 = tr.net.seg_decoder.fc.weight.detach().clone()
+    losses = tr.train_epoch(lb, ul, None, num_iter=2)
+    assert tr.iter == 2 and losses.shape == (10,) and torch.isfinite(losses).all()
+    assert losses[8] > 0                                                        # consistency loss on from iter 1
+    assert not torch.equal(w0, tr.net.seg_decoder.fc.weight)
+    assert abs(tr.optimizer.param_groups[0]['lr'] - O.poly_lr(1e-2, 1, cfg.max_epoch * cfg.num_iter_per_epoch)) < 1e-12
+    try:
+        import PIL  # noqa: F401
+        assert os.path.exists(os.path.join(str(tmp_path), '000', 'sample', 'train-1-images.png'))
+    except ImportError:
+        pass
