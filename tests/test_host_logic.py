@@ -467,3 +467,29 @@ def test_consis_train_epoch_loop_and_sample_file(exact, tmp_path, monkeypatch):
         assert os.path.exists(os.path.join(str(tmp_path), '000', 'sample', 'train-1-images.png'))
     except ImportError:
         pass
+
+
+def test_ugan_and_cross_pse_epoch_loops(exact, tmp_path, monkeypatch):
+    """train_epoch of UGANTrainer (lambda_shp ramp of uganTrainer.py:122-123, labelled-only loop) and crossPseTrainer"""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.data_loader import syntheticLoader as synlod
+    from smsut_b200.trainer.crossPseTrainer import crossPseTrainer
+    from smsut_b200.trainer.uganTrainer import UGANTrainer
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    args = SimpleNamespace(fold=0, expr_name=None, input_size=64)
+    lb = synlod.get_loader(None, 'train', 0, 2, size=64, pool_batches=1)
+    ul = synlod.get_loader(None, 'val', 0, 2, size=64, pool_batches=1)
+    tr = UGANTrainer('train', args)
+    assert tr.epoch_lambda_shp() == 0.0
+    tr.epoch = 4
+    assert tr.epoch_lambda_shp() == 2.0                    # epoch * (10 / 20), capped at lambda_seg
+    tr.epoch = 100
+    assert tr.epoch_lambda_shp() == 10.0
+    tr.epoch = 4
+    losses = tr.train_epoch(lb, ul, None, num_iter=2)
+    assert tr.iter == 2 and losses.shape == (9,) and torch.isfinite(losses).all() and losses[8] > 0
+    cp = crossPseTrainer('train', args)
+    losses = cp.train_epoch(lb, ul, None, num_iter=2)
+    assert cp.iter == 2 and losses.shape == (4,) and torch.isfinite(losses).all()
+    assert abs(cp.optimizer2.param_groups[0]['lr'] - O.poly_lr(1e-2, 1, cfg.max_epoch * cfg.num_iter_per_epoch)) < 1e-12
