@@ -493,3 +493,24 @@ def test_ugan_and_cross_pse_epoch_loops(exact, tmp_path, monkeypatch):
     losses = cp.train_epoch(lb, ul, None, num_iter=2)
     assert cp.iter == 2 and losses.shape == (4,) and torch.isfinite(losses).all()
     assert abs(cp.optimizer2.param_groups[0]['lr'] - O.poly_lr(1e-2, 1, cfg.max_epoch * cfg.num_iter_per_epoch)) < 1e-12
+
+
+@pytest.mark.parametrize("module", ["unetTrainer", "meanTeacherTrainer", "crossPseTrainer", "uganConsisTrainer", "uganTrainer"])
+def test_cli_train_then_test_entry_points(exact, tmp_path, monkeypatch, capsys, module):
+    """`python trainer/<x>Trainer.py -p train -f 0` then `-p test -f 0 -i 000 -wh last` (the reference's entry points,
+    e.g. trainer/unetTrainer.py:150-171), through the modules' own __main__ blocks on the CPU test double."""
+    import runpy
+    from smsut_b200 import config as cfg
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    monkeypatch.setattr(cfg, "input_size", 32)
+    monkeypatch.setattr(cfg, "expr_root", str(tmp_path))
+    name = f"smsut_b200.trainer.{module}"
+    monkeypatch.setattr(sys, "argv", [module + ".py", "-p", "train", "-f", "0", "-nm", "cli", "--epochs", "1", "--iters", "1"])
+    sys.modules.pop(name, None)
+    runpy.run_module(name, run_name="__main__")
+    ckpts = ["last_G.ckpt", "last_D.ckpt"] if module.startswith("ugan") else ["last.ckpt"]     # uganShp0Trainer.py:94-107
+    for c in ckpts:
+        assert os.path.exists(os.path.join(str(tmp_path), "cli", "000", "ckpt", c)), c
+    monkeypatch.setattr(sys, "argv", [module + ".py", "-p", "test", "-f", "0", "-nm", "cli", "-i", "000", "-wh", "last"])
+    runpy.run_module(name, run_name="__main__")
+    assert "dice:" in capsys.readouterr().out
