@@ -306,6 +306,22 @@ typedef struct smsut_unpack_entry {
 } smsut_unpack_entry;
 int smsut_unpack_wgrads(const smsut_unpack_entry* table, int32_t n, smsut_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Deterministic accumulation (SMSUT_DETERMINISTIC=1).  The reference's reductions (InstanceNorm sums over H*W,
+ * network/blocks.py:22-23; aten::convolution_backward(weight); the batch-wide Dice statistics, misc/loss.py:52-63;
+ * the scalar loss means, trainer/uganConsisTrainer.py:129-177) are cross-CTA sums; the library forms them with fp32
+ * atomics, whose order changes run to run.  For every accumulator address inside a registered range the kernels add
+ * into a 64-bit fixed-point (Q31.32) shadow instead -- integer addition is associative, so any arrival order, even
+ * from concurrent streams, gives bit-identical totals -- and smsut_det_resolve folds the shadow into the fp32
+ * destination (dst[i] += shadow[i] * 2^-32; shadow[i] = 0).  Unregistered destinations keep the fp32 atomics.
+ * `shadow` holds bytes/4 int64 values (2x the bytes of the range) and must be zero before the first accumulation.
+ * ---------------------------------------------------------------------------------------------- */
+int smsut_det_register(const void* base, size_t bytes, void* shadow);
+int smsut_det_unregister(const void* base);
+int smsut_det_ranges(void);                       /* number of live registrations */
+void* smsut_det_shadow(const void* p);            /* shadow address of an accumulator address, or NULL */
+int smsut_det_resolve(float* dst, int64_t count, smsut_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,6 +124,9 @@ _PROTOS = {
     "smsut_poly_lr_tick": [P, P, c_float, c_float, c_float, P],
     "smsut_pack_weights": [P, c_int, P],
     "smsut_unpack_wgrads": [P, c_int, P],
+    "smsut_det_register": [P, C.c_size_t, P],
+    "smsut_det_unregister": [P],
+    "smsut_det_resolve": [P, c_int64, P],
 }
 
 
@@ -141,6 +144,10 @@ def _load():
     lib.smsut_last_error.argtypes = []
     lib.smsut_abi_version.restype = c_int
     lib.smsut_launch_count.restype = c_int64
+    lib.smsut_det_ranges.restype = c_int
+    lib.smsut_det_ranges.argtypes = []
+    lib.smsut_det_shadow.restype = c_void_p
+    lib.smsut_det_shadow.argtypes = [c_void_p]
     for name, argtypes in _PROTOS.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -166,4 +173,5 @@ def launch_count():
 
 
 def exported_names():
-    return ["smsut_last_error", "smsut_abi_version", "smsut_launch_count"] + list(_PROTOS)
+    return ["smsut_last_error", "smsut_abi_version", "smsut_launch_count", "smsut_det_ranges", "smsut_det_shadow"] + \
+        list(_PROTOS)

@@ -140,6 +140,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
 
 // ---------------------------------------------------------------------------------------------
+// Deterministic accumulation (SMSUT_DETERMINISTIC=1, det.cu).
+// Every cross-CTA reduction of the library (InstanceNorm statistics, weight-gradient partials, loss sums, parameter
+// gradients of the norm layers) is an fp32 atomic whose order changes from run to run.  In deterministic mode the
+// destination buffers have a registered 64-bit fixed-point shadow (Q31.32): partial sums are converted and added
+// with INTEGER atomics, which are associative, so any arrival order -- including concurrent kernels on different
+// streams -- gives bit-identical totals; smsut_det_resolve folds a shadow into its fp32 destination.  The host
+// launcher looks the shadow up (det_shadow) and hands the kernel a second base pointer; nullptr = plain fp32 atomics.
+// ---------------------------------------------------------------------------------------------
+long long* det_shadow(const void* p);   // host: shadow address of a registered accumulator address, or nullptr
+
+__device__ __forceinline__ void acc_add(float* dst, long long* q, float v) {
+  if (q != nullptr)
+    atomicAdd(reinterpret_cast<unsigned long long*>(q), (unsigned long long)__double2ll_rn((double)v * 4294967296.0));
+  else
+    atomicAdd(dst, v);
+}
+// the same for element `idx` of an accumulator array and its (optional) shadow array
+__device__ __forceinline__ void acc_add_at(float* base, long long* base_q, size_t idx, float v) {
+  acc_add(base + idx, base_q != nullptr ? base_q + idx : nullptr, v);
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

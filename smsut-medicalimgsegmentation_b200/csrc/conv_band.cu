@@ -52,6 +52,7 @@ struct BandParams {
   int act; float slope;
   int accumulate, out_f32;
   float* stats;            // fused InstanceNorm statistics [n][2][ncols_pad] (optional)
+  long long* stats_q;      // its fixed-point shadow in deterministic mode (common.cuh), else nullptr
   int fast;                // epilogue fast path (see band_epilogue_fast)
   long long* trace;        // development: per-row clock64 stamps of CTA 0 (SMSUT_BAND_TRACE=1)
 };
@@ -182,7 +183,7 @@ __device__ __forceinline__ void band_epilogue_fast(const BandParams& p, uint64_t
         vals[16 + k] = s2[j][k];
       }
       const float tot = warp_reduce_scatter32(vals, lane);
-      atomicAdd(p.stats + ((size_t)n * 2 + (lane >> 4)) * p.ncols_pad + j * 16 + (lane & 15), tot);
+      acc_add_at(p.stats, p.stats_q, ((size_t)n * 2 + (lane >> 4)) * p.ncols_pad + j * 16 + (lane & 15), tot);
     }
   }
 }
@@ -427,7 +428,7 @@ conv_band_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
       for (int j = 0; j < nchunks && j < 4; ++j) {
         const int col = j * 16 + (lane & 15);
         if (col < p.ncols)
-          atomicAdd(p.stats + ((size_t)n * 2 + (lane >> 4)) * p.ncols_pad + col, st_acc[j]);
+          acc_add_at(p.stats, p.stats_q, ((size_t)n * 2 + (lane >> 4)) * p.ncols_pad + col, st_acc[j]);
       }
     }
   }
@@ -537,6 +538,7 @@ int conv_band_try(const smsut_conv_tc_args* a, cudaStream_t stream) {
   if (a->stats != nullptr) {
     SMSUT_CHECK(conv_band_fuses_stats(a), -1, "stats requested for a shape that does not fuse them");
     p.stats = a->stats;
+    p.stats_q = det_shadow(a->stats);
   }
   SMSUT_CHECK(a->out0 != nullptr, -1, "null output");
   if (p.split > 0) SMSUT_CHECK(p.split % 16 == 0, -1, "split must be a multiple of 16");

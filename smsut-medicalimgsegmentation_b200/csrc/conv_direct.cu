@@ -261,6 +261,7 @@ __global__ void __launch_bounds__(128) direct_dgrad_kernel(const DirectParams p)
 // ---------------------------------------------------------------------------------------------
 constexpr int kWgOPT = 4;
 __global__ void __launch_bounds__(256) direct_wgrad_kernel(const DirectParams p, float* dw, float* dbias,
+                                                           long long* dw_q, long long* dbias_q,
                                                            int rows_per_block) {
   pdl_prologue();
   const int taps = p.kh * p.kw;
@@ -312,7 +313,7 @@ __global__ void __launch_bounds__(256) direct_wgrad_kernel(const DirectParams p,
   }
 #pragma unroll
   for (int j = 0; j < kWgOPT; ++j)
-    if (oidx[j] < nout && acc[j] != 0.f) atomicAdd(dw + oidx[j], acc[j]);
+    if (oidx[j] < nout && acc[j] != 0.f) acc_add_at(dw, dw_q, oidx[j], acc[j]);
 
   if (dbias != nullptr && blockIdx.y == 0) {
     for (int c = threadIdx.x; c < p.cout; c += blockDim.x) {
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(256) direct_wgrad_kernel(const DirectParams p,
         const size_t dybase = (size_t)r * p.wo * p.y_ld;
         for (int ox = 0; ox < p.wo; ++ox) s += load_act(p.y, dybase + (size_t)ox * p.y_ld + c, p.y_f32);
       }
-      atomicAdd(dbias + c, s);
+      acc_add_at(dbias, dbias_q, c, s);
     }
   }
 }
@@ -334,9 +335,9 @@ template <int COUT>
 __global__ void __launch_bounds__(256)
 head1x1_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
                    const float* __restrict__ w, uint4* __restrict__ dx, float* __restrict__ dw,
-                   float* __restrict__ db, long long npix) {
+                   float* __restrict__ db, long long* dw_q, long long* db_q, long long npix) {
   pdl_prologue();
-  __shared__ float sh[COUT * 17];
+  __shared__ float sh[8][COUT * 17];      // per-warp slots, summed in warp order (no shared-memory float atomics)
   float wr[COUT][16], aw[COUT][16], ab[COUT];
 #pragma unroll
   for (int o = 0; o < COUT; ++o) {
@@ -344,7 +345,6 @@ head1x1_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ dy, co
 #pragma unroll
     for (int c = 0; c < 16; ++c) { wr[o][c] = w[o * 16 + c]; aw[o][c] = 0.f; }
   }
-  for (int i = threadIdx.x; i < COUT * 17; i += blockDim.x) sh[i] = 0.f;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
     float xv[16], g[COUT], d[16];
     unpack8(x[2 * p], xv);
@@ -370,16 +370,19 @@ head1x1_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ dy, co
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const float v = warp_sum(aw[o][c]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&sh[o * 17 + c], v);
+      if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][o * 17 + c] = v;
     }
     const float v = warp_sum(ab[o]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sh[o * 17 + 16], v);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5][o * 17 + 16] = v;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < COUT * 17; i += blockDim.x) {
     const int o = i / 17, c = i - o * 17;
-    if (c < 16) { if (dw) atomicAdd(dw + o * 16 + c, sh[i]); }
-    else if (db) atomicAdd(db + o, sh[i]);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sh[w][i];
+    if (c < 16) { if (dw) acc_add_at(dw, dw_q, o * 16 + c, t); }
+    else if (db) acc_add_at(db, db_q, o, t);
   }
 }
 
@@ -468,7 +471,7 @@ static int direct_wgrad(const smsut_conv_direct_args* a, float* dw, float* dbias
   int rows_per_block = (int)((total_rows + want_blocks - 1) / want_blocks);
   if (rows_per_block < 1) rows_per_block = 1;
   dim3 grid((unsigned)((total_rows + rows_per_block - 1) / rows_per_block), (unsigned)chunks);
-  launch_pdl(direct_wgrad_kernel, grid, 256, 0, stream, p, dw, dbias, rows_per_block);
+  launch_pdl(direct_wgrad_kernel, grid, 256, 0, stream, p, dw, dbias, det_shadow(dw), det_shadow(dbias), rows_per_block);
   count_launch();
   return launch_status("direct_wgrad_kernel");
 }
@@ -483,7 +486,7 @@ extern "C" int smsut_head1x1_bwd(const void* x, const float* dy, const float* y,
   const long long cap = 4LL * device_sm_count();
   if (blocks > cap) blocks = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
-#define HEAD_CASE(C) case C: launch_pdl(head1x1_bwd_kernel<C>, (unsigned)blocks, 256, 0, st, (const uint4*)x, dy, y, w, (uint4*)dx, dw, db, npix); break;
+#define HEAD_CASE(C) case C: launch_pdl(head1x1_bwd_kernel<C>, (unsigned)blocks, 256, 0, st, (const uint4*)x, dy, y, w, (uint4*)dx, dw, db, det_shadow(dw), det_shadow(db), npix); break;
   switch (cout) { HEAD_CASE(1) HEAD_CASE(2) HEAD_CASE(3) HEAD_CASE(4) HEAD_CASE(5) HEAD_CASE(6) HEAD_CASE(7) HEAD_CASE(8) }
 #undef HEAD_CASE
   count_launch();

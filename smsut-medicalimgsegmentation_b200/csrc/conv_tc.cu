@@ -60,6 +60,7 @@ struct ConvTcParams {
   int accumulate, out_f32;
   int dbg_rowshift;        // experiment: load the A tile one pixel to the left and start the descriptor one row later
   float* stats;            // fused InstanceNorm statistics [n][2][ncols_pad] of the stored values (optional)
+  long long* stats_q;      // its fixed-point shadow in deterministic mode (common.cuh), else nullptr
   int fast;                // plain epilogue: bf16, one destination, every column valid, no bias / act / accumulate
   int ksplit;              // > 1: the K steps are split over a (1,1,ksplit) cluster, partial tiles reduced through DSMEM
   // vertical-tap sharing (3x3, tile inside one image): a K step is one (dx, source, chunk); its A box holds th + 2 rows
@@ -168,7 +169,7 @@ __device__ __forceinline__ void tc_fast_chunk(const ConvTcParams& p, float (&v)[
       }
     }
     // lane l: l < 16 -> sum of channel l, else sum of squares of channel l - 16 (image of the warp's first row)
-    if (n_w < p.n) atomicAdd(p.stats + ((size_t)n_w * 2 + (lane >> 4)) * p.ncols + col + (lane & 15), vals[0]);
+    if (n_w < p.n) acc_add_at(p.stats, p.stats_q, ((size_t)n_w * 2 + (lane >> 4)) * p.ncols + col + (lane & 15), vals[0]);
   }
 }
 
@@ -754,6 +755,7 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   if (a->stats != nullptr) {
     SMSUT_CHECK(conv_tc_fuses_stats(a), -1, "stats requested for a shape conv_tc_kernel does not fuse them for");
     p.stats = a->stats;
+    p.stats_q = det_shadow(a->stats);
   }
   if (!a->out_f32)
     SMSUT_CHECK(a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 || a->ncols < 16, -1, "bf16 output pitch/offset must be multiples of 8");

@@ -54,7 +54,7 @@ __device__ __forceinline__ int argmax_first(const float* z) {
 template <int C>
 __global__ void __launch_bounds__(256)
 dice_ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
-                   const float* __restrict__ label_logits, float* __restrict__ acc, long long npix) {
+                   const float* __restrict__ label_logits, float* __restrict__ acc, long long* acc_q, long long npix) {
   pdl_prologue();
   __shared__ float sh[32];
   float tp[C], fp[C], fn[C], ce = 0.f;
@@ -102,12 +102,12 @@ dice_ce_fwd_kernel(const float* __restrict__ logits, const long long* __restrict
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     float r;
-    r = block_sum(tp[c], sh); if (threadIdx.x == 0) atomicAdd(acc + c, r);
-    r = block_sum(fp[c], sh); if (threadIdx.x == 0) atomicAdd(acc + C + c, r);
-    r = block_sum(fn[c], sh); if (threadIdx.x == 0) atomicAdd(acc + 2 * C + c, r);
+    r = block_sum(tp[c], sh); if (threadIdx.x == 0) acc_add_at(acc, acc_q, c, r);
+    r = block_sum(fp[c], sh); if (threadIdx.x == 0) acc_add_at(acc, acc_q, C + c, r);
+    r = block_sum(fn[c], sh); if (threadIdx.x == 0) acc_add_at(acc, acc_q, 2 * C + c, r);
   }
   const float r = block_sum(ce, sh);
-  if (threadIdx.x == 0) atomicAdd(acc + 3 * C, r);
+  if (threadIdx.x == 0) acc_add_at(acc, acc_q, 3 * C, r);
 }
 
 __global__ void dice_ce_finish_kernel(const float* __restrict__ acc, float* __restrict__ loss, float inv_npix, int c,
@@ -193,7 +193,7 @@ dice_ce_bwd_kernel(const float* __restrict__ logits, const long long* __restrict
 // (trainer/meanTeacherTrainer.py:124-130).  The teacher logits are constants.
 template <int C, bool BWD>
 __global__ void __launch_bounds__(256)
-softmax_mse_kernel(const float* __restrict__ zs, const float* __restrict__ zt, float* __restrict__ out,
+softmax_mse_kernel(const float* __restrict__ zs, const float* __restrict__ zt, float* __restrict__ out, long long* out_q,
                    const float* __restrict__ gscale, float scale, float* __restrict__ dzs, long long npix) {
   pdl_prologue();
   __shared__ float sh[32];
@@ -215,7 +215,7 @@ softmax_mse_kernel(const float* __restrict__ zs, const float* __restrict__ zt, f
   }
   if (!BWD) {
     const float r = block_sum(acc, sh);
-    if (threadIdx.x == 0) atomicAdd(out, r * scale);
+    if (threadIdx.x == 0) acc_add(out, out_q, r * scale);
   }
 }
 
@@ -255,14 +255,15 @@ __global__ void __launch_bounds__(256) confusion_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                     float* __restrict__ out, long long count, float scale) {
+                                                     float* __restrict__ out, long long* out_q, long long count,
+                                                     float scale) {
   pdl_prologue();
   __shared__ float sh[32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     s += fabsf(a[i] - b[i]);
   const float r = block_sum(s, sh);
-  if (threadIdx.x == 0) atomicAdd(out, r * scale);
+  if (threadIdx.x == 0) acc_add(out, out_q, r * scale);
 }
 __global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                               const float* __restrict__ gscale, float scale, float* __restrict__ da, long long count) {
@@ -274,14 +275,14 @@ __global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restri
   }
 }
 __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ x, float* __restrict__ out,
-                                                  long long count, float scale) {
+                                                  long long* out_q, long long count, float scale) {
   pdl_prologue();
   __shared__ float sh[32];
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
     s += x[i];
   const float r = block_sum(s, sh);
-  if (threadIdx.x == 0) atomicAdd(out, r * scale);
+  if (threadIdx.x == 0) acc_add(out, out_q, r * scale);
 }
 __global__ void fill_kernel(float* __restrict__ x, long long count, float v) {
   pdl_prologue();
@@ -315,7 +316,7 @@ __global__ void lerp_rows_kernel(const float* __restrict__ alpha, const float* _
 
 // small-row cross entropy (rows <= a few hundred, c <= 8): one block
 __global__ void ce_rows_fwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
-                                   float* __restrict__ out, int rows, int c, float scale) {
+                                   float* __restrict__ out, long long* out_q, int rows, int c, float scale) {
   pdl_prologue();
   __shared__ float sh[32];
   float s = 0.f;
@@ -328,7 +329,7 @@ __global__ void ce_rows_fwd_kernel(const float* __restrict__ logits, const long 
     s += m + logf(e) - z[target[r]];
   }
   const float t = block_sum(s, sh);
-  if (threadIdx.x == 0) atomicAdd(out, t * scale / (float)rows);
+  if (threadIdx.x == 0) acc_add(out, out_q, t * scale / (float)rows);
 }
 __global__ void ce_rows_bwd_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
                                    const float* __restrict__ gscale, float scale, float* __restrict__ dlogits,
@@ -358,12 +359,13 @@ __global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ 
   const float r = block_sum(s, sh);
   if (threadIdx.x == 0) norm[blockIdx.x] = sqrtf(r);
 }
-__global__ void gp_loss_kernel(const float* __restrict__ norm, float* __restrict__ out, int b, float scale) {
+__global__ void gp_loss_kernel(const float* __restrict__ norm, float* __restrict__ out, long long* out_q, int b,
+                               float scale) {
   pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float s = 0.f;
   for (int i = 0; i < b; ++i) s += (norm[i] - 1.f) * (norm[i] - 1.f);
-  atomicAdd(out, scale * s / (float)b);
+  acc_add(out, out_q, scale * s / (float)b);
 }
 __global__ void gp_bwd_kernel(const float* __restrict__ g, const float* __restrict__ norm,
                               const float* __restrict__ gscale, float scale, float* __restrict__ u, int b,
@@ -451,8 +453,8 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 template <bool BWD>
 __global__ void __launch_bounds__(128)
 patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float* __restrict__ loss_rows,
-                float* __restrict__ out, const float* __restrict__ gscale, float scale, float* __restrict__ dq,
-                int groups, int np, int c, float inv_t) {
+                float* __restrict__ out, long long* out_q, const float* __restrict__ gscale, float scale,
+                float* __restrict__ dq, int groups, int np, int c, float inv_t) {
   pdl_prologue();
   __shared__ float sh_m[4], sh_s[4];
   __shared__ float sh_acc[BWD ? 4 * 512 : 4];
@@ -507,7 +509,7 @@ patchnce_kernel(const float* __restrict__ q, const float* __restrict__ k, float*
   if (!BWD) {
     if (threadIdx.x == 0) {
       loss_rows[row] = lse - pos;
-      atomicAdd(out, scale * (lse - pos) / (float)rows);
+      acc_add(out, out_q, scale * (lse - pos) / (float)rows);
     }
     return;
   }
@@ -573,7 +575,7 @@ extern "C" int smsut_dice_ce_fwd(const float* logits, const int64_t* labels, con
   SMSUT_CHECK((labels != nullptr) != (label_logits != nullptr), -1, "exactly one of labels / label_logits");
   const int grid = grid_for(npix / 4);
   DISPATCH_C(c, (launch_pdl(dice_ce_fwd_kernel<C_>, grid, 256, 0, (cudaStream_t)st, logits, (const long long*)labels,
-                                                                           label_logits, acc, npix)));
+                                                                           label_logits, acc, det_shadow(acc), npix)));
   count_launch();
   return launch_status("dice_ce_fwd_kernel");
 }
@@ -599,7 +601,7 @@ extern "C" int smsut_softmax_mse_fwd(const float* zs, const float* zt, float* ou
                                      smsut_stream_t st) {
   const int grid = grid_for(npix);
   const float scale = 1.f / ((float)npix * (float)c);
-  DISPATCH_C(c, (launch_pdl(softmax_mse_kernel<C_, false>, grid, 256, 0, (cudaStream_t)st, zs, zt, out, nullptr, scale,
+  DISPATCH_C(c, (launch_pdl(softmax_mse_kernel<C_, false>, grid, 256, 0, (cudaStream_t)st, zs, zt, out, det_shadow(out), nullptr, scale,
                                                                                  nullptr, npix)));
   count_launch();
   return launch_status("softmax_mse_fwd_kernel");
@@ -608,7 +610,7 @@ extern "C" int smsut_softmax_mse_bwd(const float* zs, const float* zt, const flo
                                      int32_t c, smsut_stream_t st) {
   const int grid = grid_for(npix);
   const float scale = 1.f / ((float)npix * (float)c);
-  DISPATCH_C(c, (launch_pdl(softmax_mse_kernel<C_, true>, grid, 256, 0, (cudaStream_t)st, zs, zt, nullptr, gscale, scale, dzs,
+  DISPATCH_C(c, (launch_pdl(softmax_mse_kernel<C_, true>, grid, 256, 0, (cudaStream_t)st, zs, zt, nullptr, nullptr, gscale, scale, dzs,
                                                                                 npix)));
   count_launch();
   return launch_status("softmax_mse_bwd_kernel");
@@ -629,7 +631,7 @@ extern "C" int smsut_confusion_counts(const float* logits, const int64_t* labels
   return launch_status("confusion_kernel");
 }
 extern "C" int smsut_l1_fwd(const float* a, const float* b, float* out, int64_t count, float scale, smsut_stream_t st) {
-  launch_pdl(l1_fwd_kernel, grid_for(count, 1024), 256, 0, (cudaStream_t)st, a, b, out, count, scale);
+  launch_pdl(l1_fwd_kernel, grid_for(count, 1024), 256, 0, (cudaStream_t)st, a, b, out, det_shadow(out), count, scale);
   count_launch();
   return launch_status("l1_fwd_kernel");
 }
@@ -640,7 +642,7 @@ extern "C" int smsut_l1_bwd(const float* a, const float* b, const float* gscale,
   return launch_status("l1_bwd_kernel");
 }
 extern "C" int smsut_sum_f32(const float* x, float* out, int64_t count, float scale, smsut_stream_t st) {
-  launch_pdl(sum_kernel, grid_for(count, 1024), 256, 0, (cudaStream_t)st, x, out, count, scale);
+  launch_pdl(sum_kernel, grid_for(count, 1024), 256, 0, (cudaStream_t)st, x, out, det_shadow(out), count, scale);
   count_launch();
   return launch_status("sum_kernel");
 }
@@ -668,7 +670,7 @@ extern "C" int smsut_lerp_rows_f32(const float* alpha, const float* x, const flo
 }
 extern "C" int smsut_ce_rows_fwd(const float* logits, const int64_t* target, float* out, int32_t rows, int32_t c,
                                  float scale, smsut_stream_t st) {
-  launch_pdl(ce_rows_fwd_kernel, 1, 256, 0, (cudaStream_t)st, logits, (const long long*)target, out, rows, c, scale);
+  launch_pdl(ce_rows_fwd_kernel, 1, 256, 0, (cudaStream_t)st, logits, (const long long*)target, out, det_shadow(out), rows, c, scale);
   count_launch();
   return launch_status("ce_rows_fwd_kernel");
 }
@@ -682,7 +684,7 @@ extern "C" int smsut_ce_rows_bwd(const float* logits, const int64_t* target, con
 extern "C" int smsut_gp_fwd(const float* g, float* norm, float* out, int32_t b, int64_t per, float scale,
                             smsut_stream_t st) {
   launch_pdl(gp_norm_kernel, b, 256, 0, (cudaStream_t)st, g, norm, per);
-  launch_pdl(gp_loss_kernel, 1, 32, 0, (cudaStream_t)st, norm, out, b, scale);
+  launch_pdl(gp_loss_kernel, 1, 32, 0, (cudaStream_t)st, norm, out, det_shadow(out), b, scale);
   count_launch(); count_launch();
   return launch_status("gp_fwd kernels");
 }
@@ -723,7 +725,7 @@ extern "C" int smsut_patchnce_fwd(const float* q, const float* k, float* loss_ro
                                   int32_t np, int32_t c, float inv_t, float scale, smsut_stream_t st) {
   SMSUT_CHECK(c % 32 == 0 && c <= 512, -1, "PatchNCE feature dim must be a multiple of 32 and <= 512");
   const int rows = groups * np;
-  launch_pdl(patchnce_kernel<false>, rows, 128, 0, (cudaStream_t)st, q, k, loss_rows, out, nullptr, scale, nullptr,
+  launch_pdl(patchnce_kernel<false>, rows, 128, 0, (cudaStream_t)st, q, k, loss_rows, out, det_shadow(out), nullptr, scale, nullptr,
                                                                       groups, np, c, inv_t);
   count_launch();
   return launch_status("patchnce_fwd_kernel");
@@ -732,7 +734,7 @@ extern "C" int smsut_patchnce_bwd(const float* q, const float* k, const float* g
                                   int32_t groups, int32_t np, int32_t c, float inv_t, smsut_stream_t st) {
   SMSUT_CHECK(c % 32 == 0 && c <= 512, -1, "PatchNCE feature dim must be a multiple of 32 and <= 512");
   const int rows = groups * np;
-  launch_pdl(patchnce_kernel<true>, rows, 128, 0, (cudaStream_t)st, q, k, nullptr, nullptr, gscale, scale, dq,
+  launch_pdl(patchnce_kernel<true>, rows, 128, 0, (cudaStream_t)st, q, k, nullptr, nullptr, nullptr, gscale, scale, dq,
                                                                      groups, np, c, inv_t);
   count_launch();
   return launch_status("patchnce_bwd_kernel");

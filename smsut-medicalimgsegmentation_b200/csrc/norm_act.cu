@@ -40,41 +40,6 @@ __device__ __forceinline__ Strip make_strip(int c, int hw, int splits) {
   return s;
 }
 
-// Reduce NV values across threads that share a channel group and add them to dst[v * vstride + g*8 + j].
-template <int NV>
-__device__ __forceinline__ void block_reduce_add(float (&acc)[NV][8], float* sh, const Strip& s, float* dst, int c,
-                                                 size_t vstride) {
-  // sh: [NV][c] floats
-  for (int i = threadIdx.x; i < NV * c; i += kNT) sh[i] = 0.f;
-  __syncthreads();
-  if (s.cg <= 16) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float x = acc[v][j];
-        for (int off = 16; off >= s.cg; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-        acc[v][j] = x;
-      }
-    if ((threadIdx.x & 31) < s.cg) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(&sh[v * c + s.g * 8 + j], acc[v][j]);
-    }
-  } else {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sh[v * c + s.g * 8 + j], acc[v][j]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NV * c; i += kNT) {
-    const int v = i / c, ch = i - v * c;
-    atomicAdd(dst + v * vstride + ch, sh[i]);
-  }
-}
-
 __device__ __forceinline__ uint4 ldg16(const void* base, size_t elem_off) {
   return *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem_off);
 }
@@ -108,6 +73,73 @@ __device__ __forceinline__ float act_grad(float out, int act, float slope) {
   return 1.f;
 }
 
+struct Strip32 {
+  int cg, g, lane0, nl;     // channel groups of 8, this thread's group, its first pixel in the strip, pixel stride
+  int p0, count;            // first pixel of the block's strip, number of pixels this THREAD visits
+};
+
+__device__ __forceinline__ Strip32 make_strip32(int c, int hw, int splits) {
+  Strip32 s;
+  s.cg = c >> 3;
+  s.g = threadIdx.x % s.cg;
+  s.lane0 = threadIdx.x / s.cg;
+  s.nl = kNT / s.cg;
+  const int per = (hw + splits - 1) / splits;
+  s.p0 = blockIdx.y * per;
+  int p1 = s.p0 + per;
+  if (p1 > hw) p1 = hw;
+  const int span = p1 - s.p0 - s.lane0;
+  s.count = span > 0 ? (span + s.nl - 1) / s.nl : 0;
+  return s;
+}
+
+// Sum NV x 8 per-thread values over the threads of the block that share a channel group; adds to dst[v*vstride + ch].
+// sh: [kNT/32][NV][min(c, 256)] floats (c <= 256: warps of a block cover the same channel groups) or unused.
+// Deterministic inside the block: per-warp slots summed in warp order (no shared-memory float atomics); the one global
+// add per block and value goes through acc_add (fixed-point shadow `dst_q` in deterministic mode, else nullptr).
+template <int NV, typename StripT>
+__device__ __forceinline__ void block_reduce_add32(float (&acc)[NV][8], float* sh, const StripT& s, float* dst,
+                                                   long long* dst_q, int c, int vstride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (s.cg < 32) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float x = acc[v][j];
+        for (int off = 16; off >= s.cg; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        acc[v][j] = x;
+      }
+  }
+  if (c <= 256) {
+    // lanes < min(cg, 32) of every warp hold that warp's totals of channel group (warp's first group + lane)
+    const int ngl = s.cg < 32 ? s.cg : 32;
+    if (lane < ngl) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sh[(warp * NV + v) * c + s.g * 8 + j] = acc[v][j];
+    }
+    __syncthreads();
+    // warps covering the same groups: cg <= 32 -> all 8 warps; cg == 32 (c = 256) -> each warp is one pixel, all groups
+    for (int i = threadIdx.x; i < NV * c; i += kNT) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kNT / 32; ++w) t += sh[w * NV * c + i];
+      const int v = i / c, ch = i - v * c;
+      acc_add_at(dst, dst_q, (size_t)v * vstride + ch, t);
+    }
+  } else {
+    // wide layers (c > 256, not on the SMSUT path): one atomic per thread and value
+    if (s.cg >= 32 || lane < s.cg) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_add_at(dst, dst_q, (size_t)v * vstride + s.g * 8 + j, acc[v][j]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
@@ -118,8 +150,8 @@ constexpr int kUB = 2;  // backward kernels (3-4 tensors per pixel)
 
 __device__ __forceinline__ uint4 zero4() { return make_uint4(0u, 0u, 0u, 0u); }
 
-__global__ void __launch_bounds__(kNT, 4) in_stats_kernel(const void* __restrict__ x, float* __restrict__ stats, int hw,
-                                                          int c, int splits) {
+__global__ void __launch_bounds__(kNT, 4) in_stats_kernel(const void* __restrict__ x, float* __restrict__ stats,
+                                                          long long* stats_q, int hw, int c, int splits) {
   pdl_prologue();
   extern __shared__ float sh[];
   const Strip s = make_strip(c, hw, splits);
@@ -146,27 +178,7 @@ __global__ void __launch_bounds__(kNT, 4) in_stats_kernel(const void* __restrict
       }
     }
   }
-  block_reduce_add<2>(acc, sh, s, stats + (size_t)n * 2 * c, c, c);
-}
-
-struct Strip32 {
-  int cg, g, lane0, nl;     // channel groups of 8, this thread's group, its first pixel in the strip, pixel stride
-  int p0, count;            // first pixel of the block's strip, number of pixels this THREAD visits
-};
-
-__device__ __forceinline__ Strip32 make_strip32(int c, int hw, int splits) {
-  Strip32 s;
-  s.cg = c >> 3;
-  s.g = threadIdx.x % s.cg;
-  s.lane0 = threadIdx.x / s.cg;
-  s.nl = kNT / s.cg;
-  const int per = (hw + splits - 1) / splits;
-  s.p0 = blockIdx.y * per;
-  int p1 = s.p0 + per;
-  if (p1 > hw) p1 = hw;
-  const int span = p1 - s.p0 - s.lane0;
-  s.count = span > 0 ? (span + s.nl - 1) / s.nl : 0;
-  return s;
+  block_reduce_add32<2>(acc, sh, s, stats + (size_t)n * 2 * c, stats_q ? stats_q + (size_t)n * 2 * c : nullptr, c, c);
 }
 
 template <bool HAS_B, bool HAS_RES>
@@ -295,51 +307,6 @@ __device__ __forceinline__ void load_g_recomputed(const uint4& qd, const float* 
   }
 }
 
-// Sum NV x 8 per-thread values over the threads of the block that share a channel group; adds to dst[v*vstride + ch].
-// sh: [kNT/32][NV][min(c, 256)] floats (c <= 256: warps of a block cover the same channel groups) or unused.
-template <int NV>
-__device__ __forceinline__ void block_reduce_add32(float (&acc)[NV][8], float* sh, const Strip32& s, float* dst, int c,
-                                                   int vstride) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (s.cg < 32) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float x = acc[v][j];
-        for (int off = 16; off >= s.cg; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-        acc[v][j] = x;
-      }
-  }
-  if (c <= 256) {
-    // lanes < min(cg, 32) of every warp hold that warp's totals of channel group (warp's first group + lane)
-    const int ngl = s.cg < 32 ? s.cg : 32;
-    if (lane < ngl) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sh[(warp * NV + v) * c + s.g * 8 + j] = acc[v][j];
-    }
-    __syncthreads();
-    // warps covering the same groups: cg <= 32 -> all 8 warps; cg == 32 (c = 256) -> each warp is one pixel, all groups
-    for (int i = threadIdx.x; i < NV * c; i += kNT) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kNT / 32; ++w) t += sh[w * NV * c + i];
-      const int v = i / c, ch = i - v * c;
-      atomicAdd(dst + (size_t)v * vstride + ch, t);
-    }
-  } else {
-    // wide layers (c > 256, not on the SMSUT path): one atomic per thread and value
-    if (s.cg >= 32 || lane < s.cg) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(dst + (size_t)v * vstride + s.g * 8 + j, acc[v][j]);
-    }
-  }
-}
-
 // RECOMP: `out` is not read; the activation's sign comes from the pre-activation recomputed from xa / xb (possible
 // whenever the forward had no residual input), which removes one of the 3 (4) streamed tensors.
 template <bool HAS_B, bool HAS_ACT, bool RECOMP, int MINB>
@@ -348,8 +315,8 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
                      const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
                      const float* __restrict__ beta_a, const uint4* __restrict__ xb,
                      const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
-                     const float* __restrict__ beta_b, float* __restrict__ red, int hw, int c, int cp, int splits,
-                     float neg) {
+                     const float* __restrict__ beta_b, float* __restrict__ red, long long* red_q, int hw, int c, int cp,
+                     int splits, float neg) {
   pdl_prologue();
   extern __shared__ float sh[];
   const Strip32 s = make_strip32(c, hw, splits);
@@ -450,7 +417,7 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
       for (int j = 0; j < 8; ++j) acc[2][j] = (RECOMP ? fmaf(-m[j], acc[0][j], acc[2][j]) : acc[2][j]) * r[j];
     }
   }
-  block_reduce_add32<3>(acc, sh, s, red + (size_t)n * 3 * c, c, c);
+  block_reduce_add32<3>(acc, sh, s, red + (size_t)n * 3 * c, red_q ? red_q + (size_t)n * 3 * c : nullptr, c, c);
 }
 
 // pass 2: dx = A*g + B*x + C per channel with A = gamma*rstd, B = -A*rstd*mean(g xhat), C = -A*mean(g) - B*mean
@@ -464,7 +431,8 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
                     const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
                     const float* __restrict__ beta_b, uint4* __restrict__ dxb,
                     float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, uint4* __restrict__ dres,
-                    const float* __restrict__ red, int hw, int c, int cp, int splits, float neg) {
+                    const float* __restrict__ red, long long* dga_q, long long* dba_q, long long* dgb_q,
+                    long long* dbb_q, int hw, int c, int cp, int splits, float neg) {
   pdl_prologue();
   const Strip32 s = make_strip32(c, hw, splits);
   const int n = blockIdx.x;
@@ -500,11 +468,11 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (ch0 + j >= cp) continue;
-      if (dgamma_a) atomicAdd(dgamma_a + ch0 + j, r0[c + j]);
-      if (dbeta_a) atomicAdd(dbeta_a + ch0 + j, r0[j]);
+      if (dgamma_a) acc_add_at(dgamma_a, dga_q, ch0 + j, r0[c + j]);
+      if (dbeta_a) acc_add_at(dbeta_a, dba_q, ch0 + j, r0[j]);
       if (HAS_B) {
-        if (dgamma_b) atomicAdd(dgamma_b + ch0 + j, r0[2 * c + j]);
-        if (dbeta_b) atomicAdd(dbeta_b + ch0 + j, r0[j]);
+        if (dgamma_b) acc_add_at(dgamma_b, dgb_q, ch0 + j, r0[2 * c + j]);
+        if (dbeta_b) acc_add_at(dbeta_b, dbb_q, ch0 + j, r0[j]);
       }
     }
   }
@@ -560,7 +528,8 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kNT)
 in_bwd2_reduce_kernel(const void* __restrict__ u, const void* __restrict__ dy, const void* __restrict__ x,
-                      const float* __restrict__ stats, float* __restrict__ red2, int hw, int c, int splits) {
+                      const float* __restrict__ stats, float* __restrict__ red2, long long* red2_q, int hw, int c,
+                      int splits) {
   pdl_prologue();
   extern __shared__ float sh[];
   const Strip s = make_strip(c, hw, splits);
@@ -589,14 +558,14 @@ in_bwd2_reduce_kernel(const void* __restrict__ u, const void* __restrict__ dy, c
       acc[4][j] = fmaf(uu[j], dd[j], acc[4][j]);
     }
   }
-  block_reduce_add<5>(acc, sh, s, red2 + (size_t)n * 5 * c, c, c);
+  block_reduce_add32<5>(acc, sh, s, red2 + (size_t)n * 5 * c, red2_q ? red2_q + (size_t)n * 5 * c : nullptr, c, c);
 }
 
 __global__ void __launch_bounds__(kNT)
 in_bwd2_apply_kernel(const void* __restrict__ u, const void* __restrict__ dy, const void* __restrict__ x,
                      const float* __restrict__ stats, const float* __restrict__ gamma,
                      const float* __restrict__ red2, void* __restrict__ g_dy, void* __restrict__ g_x,
-                     float* __restrict__ dgamma, int hw, int c, int splits) {
+                     float* __restrict__ dgamma, long long* dgamma_q, int hw, int c, int splits) {
   pdl_prologue();
   const Strip s = make_strip(c, hw, splits);
   const int n = blockIdx.x;
@@ -617,7 +586,7 @@ in_bwd2_apply_kernel(const void* __restrict__ u, const void* __restrict__ dy, co
   if (dgamma != nullptr && blockIdx.y == 0 && s.lane0 == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      atomicAdd(dgamma + ch0 + j, r[j] * (float)hw * (e[j] - mu[j] * md[j] - b[j] * cu[j]));
+      acc_add_at(dgamma, dgamma_q, ch0 + j, r[j] * (float)hw * (e[j] - mu[j] * md[j] - b[j] * cu[j]));
   }
   const size_t base = (size_t)n * hw * c + ch0;
   for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
@@ -686,8 +655,8 @@ __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict_
 }
 
 // column sums of a (rows, c) bf16 matrix (bias gradients of the netF Linear layers)
-__global__ void __launch_bounds__(kNT) colsum_kernel(const void* __restrict__ x, float* __restrict__ out, int rows,
-                                                     int c, int splits) {
+__global__ void __launch_bounds__(kNT) colsum_kernel(const void* __restrict__ x, float* __restrict__ out,
+                                                     long long* out_q, int rows, int c, int splits) {
   pdl_prologue();
   extern __shared__ float sh[];
   const Strip s = make_strip(c, rows, splits);
@@ -700,7 +669,7 @@ __global__ void __launch_bounds__(kNT) colsum_kernel(const void* __restrict__ x,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
   }
-  block_reduce_add<1>(acc, sh, s, out, c, c);
+  block_reduce_add32<1>(acc, sh, s, out, out_q, c, c);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -725,6 +694,9 @@ static int pick_splits(int n, int hw, int c, int blocks_per_sm = 8) {
   return (int)s;
 }
 
+// shared memory of block_reduce_add32: per-warp slots for c <= 256
+static size_t red_smem(int nv, int c) { return c <= 256 ? (size_t)(kNT / 32) * nv * c * sizeof(float) : 0; }
+
 static int check_nc(int n, int hw, int c) {
   SMSUT_CHECK(n > 0 && hw > 0 && c >= 8 && (c & 7) == 0 && kNT % (c >> 3) == 0, -1,
               "instance-norm kernels need C in {8,16,...,2048} dividing 2048 (got n=%d hw=%d c=%d)", n, hw, c);
@@ -745,7 +717,8 @@ extern "C" int smsut_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, f
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c, 4);
-  launch_pdl(in_stats_kernel, dim3(n, splits), kNT, 2 * c * sizeof(float), (cudaStream_t)st, x, stats, hw, c, splits);
+  launch_pdl(in_stats_kernel, dim3(n, splits), kNT, red_smem(2, c), (cudaStream_t)st, x, stats, det_shadow(stats), hw, c,
+             splits);
   count_launch();
   return launch_status("in_stats_kernel");
 }
@@ -791,11 +764,12 @@ extern "C" int smsut_in_bwd_reduce(const void* dout, const void* out, const void
   SMSUT_CHECK(!recomp || (gamma_a && beta_a && (xb == nullptr || (gamma_b && beta_b))), -1,
               "in_bwd_reduce: out == NULL needs gamma / beta of every branch");
   const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
-  const size_t shm = c <= 256 ? (size_t)(kNT / 32) * 3 * c * sizeof(float) : 0;
+  const size_t shm = red_smem(3, c);
+  long long* red_q = det_shadow(red);
 #define IN_BWD_RED(HB, HA, RC, MB)                                                                                 \
   launch_pdl(in_bwd_reduce_kernel<HB, HA, RC, MB>, dim3(n, splits), kNT, shm, (cudaStream_t)st, (const uint4*)dout, \
              (const uint4*)out, (const uint4*)xa, stats_a, gamma_a, beta_a, (const uint4*)xb, stats_b, gamma_b,    \
-             beta_b, red, hw, c, cp, splits, neg)
+             beta_b, red, red_q, hw, c, cp, splits, neg)
   if (xb != nullptr) {
     if (recomp) { if (recomp_two_blocks()) IN_BWD_RED(true, true, true, 2); else IN_BWD_RED(true, true, true, 3); }
     else if (act != SMSUT_ACT_NONE) IN_BWD_RED(true, true, false, 3);
@@ -828,8 +802,8 @@ extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void*
 #define IN_BWD_APPLY4(HB, HR, HA, RC, MB)                                                                          \
   launch_pdl(in_bwd_apply_kernel<HB, HR, HA, RC, MB>, dim3(n, splits), kNT, 0, (cudaStream_t)st, (const uint4*)dout, \
              (const uint4*)out, (const uint4*)xa, stats_a, gamma_a, beta_a, (uint4*)dxa, dgamma_a, dbeta_a,        \
-             (const uint4*)xb, stats_b, gamma_b, beta_b, (uint4*)dxb, dgamma_b, dbeta_b, (uint4*)dres, red, hw, c, \
-             cp, splits, neg)
+             (const uint4*)xb, stats_b, gamma_b, beta_b, (uint4*)dxb, dgamma_b, dbeta_b, (uint4*)dres, red,        \
+             det_shadow(dgamma_a), det_shadow(dbeta_a), det_shadow(dgamma_b), det_shadow(dbeta_b), hw, c, cp, splits, neg)
 #define IN_BWD_APPLY(HB, HR)                                        \
   do {                                                              \
     if (recomp) IN_BWD_APPLY3(HB, HR, true, true);                  \
@@ -850,8 +824,8 @@ extern "C" int smsut_in_bwd2_reduce(const void* u, const void* dy, const void* x
   int rc = check_nc(n, hw, c);
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
-  launch_pdl(in_bwd2_reduce_kernel, dim3(n, splits), kNT, 5 * c * sizeof(float), (cudaStream_t)st, u, dy, x, stats, red2, hw,
-                                                                                          c, splits);
+  launch_pdl(in_bwd2_reduce_kernel, dim3(n, splits), kNT, red_smem(5, c), (cudaStream_t)st, u, dy, x, stats, red2,
+             det_shadow(red2), hw, c, splits);
   count_launch();
   return launch_status("in_bwd2_reduce_kernel");
 }
@@ -863,7 +837,7 @@ extern "C" int smsut_in_bwd2_apply(const void* u, const void* dy, const void* x,
   if (rc) return rc;
   const int splits = pick_splits(n, hw, c);
   launch_pdl(in_bwd2_apply_kernel, dim3(n, splits), kNT, 0, (cudaStream_t)st, u, dy, x, stats, gamma, red2, g_dy, g_x, dgamma,
-                                                                      hw, c, splits);
+             det_shadow(dgamma), hw, c, splits);
   count_launch();
   return launch_status("in_bwd2_apply_kernel");
 }
@@ -940,7 +914,7 @@ extern "C" int smsut_colsum_bf16(const void* x, int32_t rows, int32_t c, float* 
   int rc = check_nc(1, rows, c);
   if (rc) return rc;
   const int splits = pick_splits(1, rows, c);
-  launch_pdl(colsum_kernel, dim3(1, splits), kNT, c * sizeof(float), (cudaStream_t)st, x, out, rows, c, splits);
+  launch_pdl(colsum_kernel, dim3(1, splits), kNT, red_smem(1, c), (cudaStream_t)st, x, out, det_shadow(out), rows, c, splits);
   count_launch();
   return launch_status("colsum_kernel");
 }

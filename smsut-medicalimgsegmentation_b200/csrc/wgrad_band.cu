@@ -41,6 +41,7 @@ struct WgradBandParams {
   int tap_major;   // dw is the tap-major scratch [tap][cout_total][cin_total]: lanes = contiguous channels
   int cout_total;
   float* dw;
+  long long* dw_q;         // fixed-point shadow of dw in deterministic mode (common.cuh), else nullptr
   int cout, cin_total, ci_off, c_valid, taps;
 };
 
@@ -243,7 +244,7 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (co < p.cout && !p.dbg_noepi) {
           float* dst = p.tap_major ? p.dw + ((size_t)tap * p.cout_total + co) * p.cin_total + p.ci_off + ci
                                    : p.dw + ((size_t)co * p.cin_total + p.ci_off + ci) * p.taps + tap;
-          atomicAdd(dst, __uint_as_float(raw[k]));
+          acc_add(dst, p.dw_q != nullptr ? p.dw_q + (dst - p.dw) : nullptr, __uint_as_float(raw[k]));
         }
       }
     }
@@ -313,6 +314,7 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
     p.stack = (p.groups == 1 && a->ksize * p.dcc <= 256 && e && e[0] == '1') ? 1 : 0;
   }
   p.dw = a->dw;
+  p.dw_q = det_shadow(a->dw);
   p.tap_major = a->dw_layout == 1 ? 1 : 0;
   p.cout_total = a->cout_total;
   p.cout = a->dy_c < a->cout_total ? a->dy_c : a->cout_total;

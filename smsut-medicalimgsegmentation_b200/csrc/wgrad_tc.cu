@@ -52,6 +52,7 @@ struct WgradParams {
   int tap_major;   // dw is the tap-major scratch [tap][m_full][nc]
   int m_full;      // rows of the full weight matrix (tap-major addressing)
   float* dw;
+  long long* dw_q;         // fixed-point shadow of dw in deterministic mode (common.cuh), else nullptr
   int m_total, m_off, nc, c_off, taps, c_valid;
   BBlock blocks[kWgMaxBlocks];
 };
@@ -178,7 +179,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       if (p.tap_major) {
         // 16 contiguous floats of row m in the tap-major scratch: four 128-bit reductions
         float* dst = p.dw + ((size_t)blk.tap * p.m_full + (p.m_off + m)) * p.nc + p.c_off + c;
-        if (c + 16 <= p.c_valid && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        long long* dq = p.dw_q != nullptr ? p.dw_q + (dst - p.dw) : nullptr;     // deterministic mode: fixed-point shadow
+        if (dq == nullptr && c + 16 <= p.c_valid && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(raw[i])),
@@ -188,14 +190,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (c + i < p.c_valid) atomicAdd(dst + i, __uint_as_float(raw[i]));
+            if (c + i < p.c_valid) acc_add(dst + i, dq != nullptr ? dq + i : nullptr, __uint_as_float(raw[i]));
         }
         continue;
       }
       float* dst = p.dw + ((size_t)(p.m_off + m) * p.nc + p.c_off + c) * p.taps + blk.tap;
 #pragma unroll
       for (int i = 0; i < 16; ++i)
-        if (c + i < p.c_valid) atomicAdd(dst + (size_t)i * p.taps, __uint_as_float(raw[i]));
+        if (c + i < p.c_valid)
+          acc_add(dst + (size_t)i * p.taps, p.dw_q != nullptr ? p.dw_q + (dst - p.dw) + (size_t)i * p.taps : nullptr,
+                  __uint_as_float(raw[i]));
     }
   }
 
@@ -337,6 +341,7 @@ static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
 
   p.dw = a->dw;
+  p.dw_q = det_shadow(a->dw);
   p.tap_major = a->dw_layout == 1 ? 1 : 0;
   SMSUT_CHECK(a->dw != nullptr, -1, "null dw");
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;

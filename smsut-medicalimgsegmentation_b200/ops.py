@@ -49,18 +49,65 @@ param_generation = [0]
 # ----------------------------------------------------------------------------------------------
 # zero-initialised scratch (statistics, reduction buffers, loss accumulators)
 # ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------
+# deterministic mode (SMSUT_DETERMINISTIC=1, csrc/det.cu): every accumulator the kernels reduce into with atomics gets
+# a registered 64-bit fixed-point shadow; integer atomics are order-independent, `resolve` folds the shadow into the
+# fp32 tensor before its first reader.  Two runs of a step -- eager or graph replay, any stream schedule -- are then
+# bit-identical, which turns "is it a race or is it atomics noise?" into an equality test.
+# ----------------------------------------------------------------------------------------------
+DET = [os.environ.get("SMSUT_DETERMINISTIC", "0") == "1"]
+
+
+def set_deterministic(on=True):
+    """Switch deterministic accumulation on / off for accumulators allocated FROM NOW ON (arena, optimizers built
+    afterwards); call it before constructing trainers / optimizers."""
+    DET[0] = bool(on)
+    if _Arena.buf is not None:      # rebuilt (with / without its shadow) at the next arena_begin
+        if _Arena.shadow is not None:
+            call("smsut_det_unregister", _p(_Arena.buf))
+        _Arena.buf = _Arena.shadow = None
+
+
+def det_register(t):
+    """Allocate, register and return the fixed-point shadow of the fp32 accumulator tensor `t` (contiguous)."""
+    shadow = torch.zeros(t.numel(), dtype=torch.int64, device=t.device)
+    call("smsut_det_register", _p(t), t.numel() * 4, _p(shadow))
+    return shadow
+
+
+def det_unregister(ptr):
+    _lib.lib.smsut_det_unregister(C.c_void_p(ptr))
+
+
+def resolve(t):
+    """Fold the pending fixed-point partial sums of accumulator `t` into it (no-op outside deterministic mode and
+    for unregistered tensors).  Launched on the current stream, right after the kernels that accumulate into `t`."""
+    if DET[0] and t is not None and t.numel() > 0:
+        call("smsut_det_resolve", _p(t), t.numel(), _stream())
+    return t
+
+
 class _Arena:
     """One buffer cleared by ONE memset at the start of a training iteration; the hundreds of small zeroed
     accumulators of the iteration are slices of it (each would otherwise be its own fill launch)."""
     buf = None
+    shadow = None      # deterministic mode: int64 fixed-point shadow of `buf` (one value per fp32 slot)
     off = 0
     active = False
 
 
 def arena_begin(device, nbytes=48 << 20):
     if _Arena.buf is None or _Arena.buf.device != torch.device(device) or _Arena.buf.numel() != nbytes:
+        if _Arena.shadow is not None:
+            call("smsut_det_unregister", _p(_Arena.buf))
+            _Arena.shadow = None
         _Arena.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        if DET[0] and _Arena.buf.is_cuda:
+            _Arena.shadow = torch.zeros(nbytes // 4, dtype=torch.int64, device=device)
+            call("smsut_det_register", _p(_Arena.buf), nbytes, _p(_Arena.shadow))
     _Arena.buf.zero_()
+    if _Arena.shadow is not None:
+        _Arena.shadow.zero_()
     _Arena.off = 0
     _Arena.active = True
     del _branch_used[:]       # a new iteration: branch streams are (re)forked from here on
@@ -89,7 +136,17 @@ def zeros(shape, device, dtype=F32):
         t.set_(_Arena.buf.untyped_storage(), _Arena.off // item, tuple(shape), tuple(reversed(strides)))
         _Arena.off += (nbytes + 255) // 256 * 256
         return t
-    return torch.zeros(shape, dtype=dtype, device=device)
+    t = torch.zeros(shape, dtype=dtype, device=device)
+    if DET[0] and dtype == F32 and t.is_cuda and t.numel() > 0:
+        # outside an iteration's arena: a shadow of its own, unregistered when the tensor dies
+        shadow = det_register(t)
+        weakref.finalize(t, _det_release, t.data_ptr(), shadow)
+    return t
+
+
+def _det_release(ptr, shadow):
+    det_unregister(ptr)
+    del shadow
 
 
 # ----------------------------------------------------------------------------------------------
@@ -322,12 +379,15 @@ class WgradScratch:
     smsut_unpack_wgrads launch per network -- folds the scratch into the OIHW gradient and clears it."""
     owners = weakref.WeakSet()
 
-    def __init__(self, params, grad_views):
+    def __init__(self, params, grad_views, grad_flat=None):
         """params: the network's parameters; grad_views[i]: the flat-gradient view of params[i].  The scratch is built
-        on first use: the conv modules create their PackedWeight (which marks a weight as tensor-core) lazily."""
+        on first use: the conv modules create their PackedWeight (which marks a weight as tensor-core) lazily.
+        grad_flat: the flat gradient buffer the views live in (deterministic mode: its shadow is folded in by flush)."""
         self.params, self.grads = list(params), list(grad_views)
+        self.grad_flat = grad_flat
         self.dirty = False
         self.flat = None
+        self.shadow = None
         self.views = {}
         for p in self.params:
             p._smsut_scratch_owner = weakref.ref(self)
@@ -342,6 +402,7 @@ class WgradScratch:
         dev = items[0][0].device
         sizes = [(p.numel() + 3) // 4 * 4 for p, _ in items]
         self.flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
+        self.shadow = det_register(self.flat) if DET[0] and self.flat.is_cuda else None
         entries, off = [], 0
         for (p, g), sz in zip(items, sizes):
             taps, rows, cols = p._smsut_tc
@@ -374,9 +435,20 @@ class WgradScratch:
         self.dirty = True
         return ent[0]
 
+    def discard(self):
+        """drop pending weight gradients (optimizer.zero_grad)"""
+        if self.flat is not None and self.dirty:
+            self.flat.zero_()
+            if self.shadow is not None:
+                self.shadow.zero_()
+        self.dirty = False
+
     def flush(self):
+        if self.grad_flat is not None:
+            resolve(self.grad_flat)       # deterministic mode: atomically accumulated parameter gradients
         if self.flat is None or not self.dirty:
             return
+        resolve(self.flat)
         call("smsut_unpack_wgrads", _p(self.table), self.n, _stream())
         self.flat.zero_()
         self.dirty = False
@@ -441,7 +513,7 @@ def conv_fprop(xs, pw, bias=None, act=ACT_NONE, out_f32=False, want_stats=False)
     call("smsut_conv_tc", C.byref(a), _stream())
     if not want_stats:
         return y
-    return y, (stats if stats is not None else in_stats(y))
+    return y, (resolve(stats) if stats is not None else in_stats(y))
 
 
 def conv_dgrad(dy, pw, splits=None):
@@ -485,7 +557,7 @@ def wgrad_tc(kind, ksize, n, h, w, x, x_c, dy, dy_c, dw, cin_total, ci_off, cout
 def conv_wgrad(xs, dy, pw, out=None):
     """fp32 OIHW weight gradient of conv_fprop, accumulated (atomics) into `out` or a fresh zeroed tensor."""
     n, h, w, _ = xs[0].shape
-    dw = out if out is not None else torch.zeros_like(pw.weight, dtype=F32)
+    dw = out if out is not None else zeros(tuple(pw.weight.shape), pw.weight.device)
     scratch = _wgrad_scratch(pw.weight, out)
     dst = scratch if scratch is not None else dw
 
@@ -501,6 +573,7 @@ def conv_wgrad(xs, dy, pw, out=None):
         side_run(launch, (list(xs), dy))
     else:
         launch()
+        resolve(dw)
     return dw
 
 
@@ -522,7 +595,7 @@ def convt_dgrad(dy, pw):
 
 def convt_wgrad(x, dy, pw, out=None):
     n, h, w, c = x.shape
-    dw = out if out is not None else torch.zeros_like(pw.weight, dtype=F32)
+    dw = out if out is not None else zeros(tuple(pw.weight.shape), pw.weight.device)
     scratch = _wgrad_scratch(pw.weight, out)
     dst = scratch if scratch is not None else dw
     if out is not None:
@@ -530,6 +603,7 @@ def convt_wgrad(x, dy, pw, out=None):
                                   tap_major=scratch is not None), (x, dy))
     else:
         wgrad_tc(TC_CONVT_FWD, 1, n, h, w, x, c, dy, pw.cout, dst, pw.cin, 0, pw.cout)
+        resolve(dw)
     return dw
 
 
@@ -578,19 +652,25 @@ def head1x1_bwd(x, dy, y, weight, want_dx, dw=None, db=None, want_bias=False):
     n, h, w, c = _chk(x, BF16, "head x").shape
     cout = weight.shape[0]
     dx = torch.empty_like(x) if want_dx else None
-    dw = dw if dw is not None else torch.zeros_like(weight, dtype=F32)
-    if want_bias and db is None:
-        db = torch.zeros(cout, dtype=F32, device=x.device)
+    fresh_w, fresh_b = dw is None, want_bias and db is None
+    dw = dw if dw is not None else zeros(tuple(weight.shape), x.device)
+    if fresh_b:
+        db = zeros(cout, x.device)
     call("smsut_head1x1_bwd", _p(x), _p(_chk(dy, F32, "head dy")), _p(y), _p(weight), _p(dx), _p(dw), _p(db), n * h * w, c,
          cout, _stream())
+    if fresh_w:
+        resolve(dw)
+    if fresh_b:
+        resolve(db)
     return dx, dw, db
 
 
 def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias, dw=None, db=None):
     side = dw is not None and (db is not None or not want_bias)     # accumulating into the flat gradient buffer
-    dw = dw if dw is not None else torch.zeros_like(weight, dtype=F32)
-    if want_bias and db is None:
-        db = torch.zeros(weight.shape[0], dtype=F32, device=weight.device)
+    fresh_w, fresh_b = dw is None, want_bias and db is None
+    dw = dw if dw is not None else zeros(tuple(weight.shape), weight.device)
+    if fresh_b:
+        db = zeros(weight.shape[0], weight.device)
     if not want_bias:
         db = None
     a = _direct_args(x, weight, dy, stride, pad, None, ACT_NONE, 0.0, False)
@@ -598,6 +678,10 @@ def conv_direct_wgrad(x, dy, weight, stride, pad, want_bias, dw=None, db=None):
         side_run(lambda: call("smsut_conv_direct_wgrad", C.byref(a), _p(dw), _p(db), _stream()), (x, dy, a))
     else:
         call("smsut_conv_direct_wgrad", C.byref(a), _p(dw), _p(db), _stream())
+        if fresh_w:
+            resolve(dw)
+        if fresh_b and db is not None:
+            resolve(db)
     return dw, db
 
 
@@ -608,7 +692,7 @@ def in_stats(x):
     n, h, w, c = _chk(x, BF16, "in_stats x").shape
     stats = zeros((n, 2, c), x.device)
     call("smsut_in_stats", _p(x), n, h * w, c, _p(stats), _stream())
-    return stats
+    return resolve(stats)
 
 
 def in_apply(xa, sa, ga, ba, xb=None, sb=None, gb=None, bb=None, res=None, act=ACT_NONE, slope=0.01, c_params=None):
@@ -657,11 +741,13 @@ def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act
     red = zeros((n, 3, c), dev)
     call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(xb), _p(sb), _p(gb), _p(bb),
          _p(red), n, h * w, c, cp, act, slope, _stream())
+    resolve(red)
     if batch:
         call("smsut_bn_pool", _p(red), _p(red), n, 3, c, _stream())
     dxa = torch.empty_like(xa)
     dxb = torch.empty_like(xa) if xb is not None else None
     dres = torch.empty_like(xa) if want_res else None
+    pg = None
     if targets is not None:
         t = list(targets)
         ret = [None, None, None, None]
@@ -671,6 +757,8 @@ def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act
         ret = t
     call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(dxa), _p(t[0]), _p(t[1]), _p(xb),
          _p(sb), _p(gb), _p(bb), _p(dxb), _p(t[2]), _p(t[3]), _p(dres), _p(red), n, h * w, c, cp, act, slope, _stream())
+    if pg is not None:
+        resolve(pg)
     return dxa, ret[0], ret[1], dxb, ret[2], ret[3], dres
 
 
@@ -679,11 +767,12 @@ def in_bwd2(u, dy, x, stats, gamma):
     n, h, w, c = x.shape
     red2 = zeros((n, 5, c), x.device)
     call("smsut_in_bwd2_reduce", _p(u), _p(dy), _p(x), _p(stats), _p(red2), n, h * w, c, _stream())
+    resolve(red2)
     g_dy, g_x = torch.empty_like(x), torch.empty_like(x)
-    dgamma = torch.zeros(c, dtype=F32, device=x.device)
+    dgamma = zeros(c, x.device)
     call("smsut_in_bwd2_apply", _p(u), _p(dy), _p(x), _p(stats), _p(gamma), _p(red2), _p(g_dy), _p(g_x), _p(dgamma), n,
          h * w, c, _stream())
-    return g_dy, g_x, dgamma
+    return g_dy, g_x, resolve(dgamma)
 
 
 def act_fwd(x, act, slope=0.01):
@@ -706,9 +795,9 @@ def add_bf16(a, b):
 
 def colsum(x):
     rows, c = x.shape
-    out = torch.zeros(c, dtype=F32, device=x.device)
+    out = zeros(c, x.device)
     call("smsut_colsum_bf16", _p(_chk(x, BF16, "colsum x")), rows, c, _p(out), _stream())
-    return out
+    return resolve(out)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -785,6 +874,7 @@ def dice_ce_fwd(logits, labels, label_logits, acc):
     npix, c = logits.shape
     call("smsut_dice_ce_fwd", _p(_chk(logits, F32, "dice logits")), _p(labels), _p(label_logits), _p(acc), npix, c,
          _stream())
+    resolve(acc)
 
 
 def dice_ce_finish(acc, npix_total, c, w_dc, w_ce):
@@ -804,6 +894,7 @@ def dice_ce_bwd(logits, labels, label_logits, acc, gscale, scale, npix_total, w_
 def softmax_mse_fwd(zs, zt, out):
     npix, c = zs.shape
     call("smsut_softmax_mse_fwd", _p(_chk(zs, F32, "mse zs")), _p(_chk(zt, F32, "mse zt")), _p(out), npix, c, _stream())
+    resolve(out)
 
 
 def softmax_mse_bwd(zs, zt, gscale):
@@ -829,6 +920,7 @@ def confusion_counts(logits, labels, conf):
 
 def l1_fwd(a, b, out, scale):
     call("smsut_l1_fwd", _p(_chk(a, F32, "l1 a")), _p(_chk(b, F32, "l1 b")), _p(out), a.numel(), scale, _stream())
+    resolve(out)
 
 
 def l1_bwd(a, b, gscale, scale):
@@ -839,6 +931,7 @@ def l1_bwd(a, b, gscale, scale):
 
 def sum_f32(x, out, scale):
     call("smsut_sum_f32", _p(_chk(x, F32, "sum x")), _p(out), x.numel(), scale, _stream())
+    resolve(out)
 
 
 def fill_f32(x, value):
@@ -868,6 +961,7 @@ def lerp_rows(alpha, x, y):
 def ce_rows_fwd(logits, target, out, scale):
     rows, c = logits.shape
     call("smsut_ce_rows_fwd", _p(_chk(logits, F32, "ce logits")), _p(target), _p(out), rows, c, scale, _stream())
+    resolve(out)
 
 
 def ce_rows_bwd(logits, target, gscale, scale):
@@ -882,6 +976,7 @@ def gp_fwd(g, out, scale):
     per = g.numel() // b
     norm = torch.empty(b, dtype=F32, device=g.device)
     call("smsut_gp_fwd", _p(_chk(g, F32, "gp g")), _p(norm), _p(out), b, per, scale, _stream())
+    resolve(out)
     return norm
 
 
@@ -925,6 +1020,7 @@ def patchnce_fwd(q, k, groups, np_, inv_t, out, scale):
     loss_rows = torch.empty(rows, dtype=F32, device=q.device)
     call("smsut_patchnce_fwd", _p(_chk(q, F32, "nce q")), _p(_chk(k, F32, "nce k")), _p(loss_rows), _p(out), groups,
          np_, c, inv_t, scale, _stream())
+    resolve(out)
     return loss_rows
 
 

@@ -47,22 +47,42 @@ class _FlatOptimizer:
                 p.grad = self.grad[off:off + n].view(p.shape)
                 off += sz
         # tap-major scratch for the tensor-core weight gradients (ops.WgradScratch); folded into `grad` by finish_grads()
-        self.wgrad_scratch = ops.WgradScratch(self.params, [p.grad for p in self.params])
+        # deterministic mode: the parameter gradients the kernels accumulate with atomics (norm gamma / beta, direct
+        # convs) go through a fixed-point shadow of the flat gradient, folded in by finish_grads()
+        self.grad_shadow = ops.det_register(self.grad) if ops.DET[0] and self.grad.is_cuda else None
+        self.wgrad_scratch = ops.WgradScratch(self.params, [p.grad for p in self.params], grad_flat=self.grad)
         self.param_groups = [dict(params=self.params, lr=lr)]
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self._lr_host = float(lr)
         self.grad_scale = 1.0      # 1/world_size after a summing all-reduce of `grad`
 
+    def _detached(self):
+        """parameters whose .grad no longer aliases the flat gradient buffer (net.zero_grad(set_to_none=True),
+        optimizer-unaware code assigning p.grad, ...)"""
+        lo = self.grad.data_ptr()
+        hi = lo + self.grad.numel() * 4
+        return [p for p in self.params if p.grad is None or not (lo <= p.grad.data_ptr() < hi)]
+
     def zero_grad(self, set_to_none=False):
         self.grad.zero_()
-        for p in self.params:    # autograd may have swapped a .grad tensor in: re-attach the flat views
-            if p.grad is None or p.grad.data_ptr() < self.grad.data_ptr() or \
-                    p.grad.data_ptr() >= self.grad.data_ptr() + self.grad.numel() * 4:
-                self._reattach()
-                break
+        if self.grad_shadow is not None:
+            self.grad_shadow.zero_()
+        self.wgrad_scratch.discard()     # a backward without a step must not leak into the next one
+        if self._detached():             # autograd may have swapped a .grad tensor in: re-attach the flat views
+            self._reattach()
 
     def finish_grads(self):
-        """fold the tensor-core weight-gradient scratch into the flat gradient (no-op when nothing is pending)"""
+        """complete the flat gradient: adopt gradients that landed in foreign .grad tensors, fold the tensor-core
+        weight-gradient scratch and (deterministic mode) the fixed-point shadow in (no-op when nothing is pending)"""
+        stray = self._detached()
+        if stray:
+            # the fused step reads only the flat buffer: a detached .grad would silently train on zeros
+            held = [(p, p.grad) for p in stray]
+            self._reattach()
+            with torch.no_grad():
+                for p, g in held:
+                    if g is not None:
+                        p.grad.add_(g.to(p.grad.dtype).view_as(p.grad))
         self.wgrad_scratch.flush()
 
     def _reattach(self):
