@@ -168,6 +168,13 @@ class Style:
     def __init__(self, norm="instance", act="lrelu", training=True, momentum=0.1):
         self.norm_type, self.act_type, self.training, self.momentum = norm, act, training, momentum
 
+    # hooks of the per-layer parity protocol; no-ops here, see RecordingStyle
+    def tap(self, key, x):
+        return x
+
+    def pool(self, x, key=None):
+        return F.max_pool2d(x, 2, 2)
+
     def norm(self, x, sd, p):
         if self.norm_type == "instance":
             return inorm(x, sd, p)
@@ -175,8 +182,57 @@ class Style:
         return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
                             self.training, self.momentum, EPS)
 
-    def act(self, x):
+    def act(self, x, key=None):
         return lrelu(x) if self.act_type == "lrelu" else F.relu(x)
+
+
+class RecordingStyle(Style):
+    """Style that (i) records every tapped tensor (block inputs / outputs, retained for .grad), every activation's
+    mask (pre-activation > 0) and every max-pool's argmax under the block's key, and (ii) optionally FORCES masks and
+    pool indices taken from another run.  LeakyReLU / ReLU / max-pool are the only non-smooth ops of the path: with
+    their selections forced, the network is the same piecewise-linear-in-the-selections function on both sides, so a
+    gradient comparison measures arithmetic, not which side of a kink a bf16-rounded value fell on.
+    forced_masks / forced_pool: dict key -> bool mask (NCHW) / int64 indices as returned by max_pool2d(return_indices),
+    or a list consumed in call order when keys are not known."""
+
+    def __init__(self, norm="instance", act="lrelu", training=True, momentum=0.1, forced_masks=None, forced_pool=None):
+        super().__init__(norm, act, training, momentum)
+        self.taps, self.masks, self.pools = {}, {}, {}
+        self.forced_masks, self.forced_pool = forced_masks, forced_pool
+        self._n = 0
+
+    def tap(self, key, x):
+        if x.requires_grad:
+            x.retain_grad()
+        self.taps[key] = x
+        return x
+
+    def _forced(self, table, key):
+        if table is None:
+            return None
+        if isinstance(table, dict):
+            return table.get(key)
+        return table.pop(0) if table else None
+
+    def act(self, x, key=None):
+        key = key if key is not None else f"act{self._n}"
+        self._n += 1
+        m = self._forced(self.forced_masks, key)
+        if m is None:
+            m = x > 0
+        self.masks[key] = m.detach()
+        neg = SLOPE if self.act_type == "lrelu" else 0.0
+        return torch.where(m, x, x * neg)
+
+    def pool(self, x, key=None):
+        key = key if key is not None else f"pool{self._n}"
+        idx = self._forced(self.forced_pool, key)
+        if idx is None:
+            y, idx = F.max_pool2d(x, 2, 2, return_indices=True)
+            self.pools[key] = idx
+            return y
+        self.pools[key] = idx
+        return x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
 
 
 DEFAULT_STYLE = Style()
@@ -194,74 +250,83 @@ def add_bn_buffers(sd):
     return out
 
 
-def basic_block(x, sd, p, st=DEFAULT_STYLE):
-    # network/blocks.py:66-80
-    y = st.act(st.norm(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1."))
+def basic_block(x, sd, p, st=DEFAULT_STYLE, tag=None):
+    # network/blocks.py:66-80.  tag: key prefix of the parity hooks (defaults to the state_dict prefix; enc5 is
+    # called once per branch with the same weights and needs distinct keys)
+    k = p if tag is None else tag
+    x = st.tap(k + "in", x)
+    y = st.act(st.norm(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1."), k + "act1")
     y = st.norm(F.conv2d(y, sd[p + "conv2.weight"], padding=1), sd, p + "bn2.")
     if p + "shortcut1.weight" in sd:
         x = st.norm(F.conv2d(x, sd[p + "shortcut1.weight"]), sd, p + "shortcut2.")
-    return st.act(y + x)
+    return st.tap(k + "out", st.act(y + x, k + "act2"))
 
 
-def bottle_block(x, sd, p):
+def bottle_block(x, sd, p, st=DEFAULT_STYLE):
     # network/blocks.py:99-117 (stride 2): both branches see avg_pool2d
+    x = st.tap(p + "in", x)
     ident = F.avg_pool2d(x, 2)
-    y = lrelu(inorm(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1."))
+    y = st.act(inorm(F.conv2d(x, sd[p + "conv1.weight"], padding=1), sd, p + "bn1."), p + "act1")
     y = F.avg_pool2d(y, 2)
     y = inorm(F.conv2d(y, sd[p + "conv2.weight"], padding=1), sd, p + "bn2.")
     if p + "downsample.0.weight" in sd:
         ident = inorm(F.conv2d(ident, sd[p + "downsample.0.weight"]), sd, p + "downsample.1.")
-    return lrelu(y + ident)
+    return st.tap(p + "out", st.act(y + ident, p + "act2"))
 
 
 def unet_forward(sd, x, taps=None, style=DEFAULT_STYLE):
     """network/unet.py:29-32 -> blocks.Encoder.forward (blocks.py:138-153) + blocks.Decoder.forward (:168-174)."""
     t = taps if taps is not None else {}
     st = style
-    x = st.act(st.norm(F.conv2d(x, sd["encoder.pre_conv.weight"], padding=2), sd, "encoder.pre_bn."))
-    t["encoder.pre"] = x
+    x = st.tap("encoder.pre.in", x)
+    x = st.act(st.norm(F.conv2d(x, sd["encoder.pre_conv.weight"], padding=2), sd, "encoder.pre_bn."), "encoder.pre.act")
+    t["encoder.pre"] = st.tap("encoder.pre.out", x)
     skips = []
     for i in range(1, 5):
         x = basic_block(x, sd, f"encoder.layer{i}.", st)
         t[f"encoder.layer{i}"] = x
         skips.append(x)
-        x = F.max_pool2d(x, 2, 2)
+        x = st.pool(x, f"encoder.pool{i}")
     x = basic_block(x, sd, "encoder.layer5.", st)
     t["encoder.layer5"] = x
     for i in (4, 3, 2, 1):
-        up = F.conv_transpose2d(x, sd[f"decoder.up{i}.up.weight"], stride=2)
+        up = st.tap(f"decoder.up{i}.out", F.conv_transpose2d(st.tap(f"decoder.up{i}.in", x),
+                                                             sd[f"decoder.up{i}.up.weight"], stride=2))
         x = basic_block(torch.cat([up, skips[i - 1]], 1), sd, f"decoder.layer{i}.", st)
         t[f"decoder.layer{i}"] = x
-    return F.conv2d(x, sd["decoder.fc.weight"])
+    return st.tap("decoder.fc.out", F.conv2d(st.tap("decoder.fc.in", x), sd["decoder.fc.weight"]))
 
 
-def ugan_encoder(sd, p, x, t):
+def ugan_encoder(sd, p, x, t, st=DEFAULT_STYLE):
     # network/ugan.py:39-55
-    x = lrelu(inorm(F.conv2d(x, sd[p + "pre.0.weight"], padding=2), sd, p + "pre.1."))
-    t[p + "pre"] = x
+    x = st.tap(p + "pre.in", x)
+    x = st.act(inorm(F.conv2d(x, sd[p + "pre.0.weight"], padding=2), sd, p + "pre.1."), p + "pre.act")
+    t[p + "pre"] = st.tap(p + "pre.out", x)
     skips = []
     for i in range(1, 5):
-        x = basic_block(x, sd, f"{p}enc{i}.")
+        x = basic_block(x, sd, f"{p}enc{i}.", st)
         t[f"{p}enc{i}"] = x
         skips.append(x)
-        x = F.max_pool2d(x, 2, 2)
+        x = st.pool(x, f"{p}pool{i}")
     skips.reverse()
     return x, skips
 
 
-def ugan_decoder(sd, p, e5, skips, transposed, use_tanh, t):
+def ugan_decoder(sd, p, e5, skips, transposed, use_tanh, t, st=DEFAULT_STYLE):
     # network/ugan.py:76-83, network/blocks.py:37-50
     x = e5
     for k, i in enumerate((4, 3, 2, 1)):
+        x = st.tap(f"{p}up{i}.in", x)
         if transposed:
             up = F.conv_transpose2d(x, sd[f"{p}up{i}.up.weight"], stride=2)
         else:
             up = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
             up = F.conv2d(up, sd[f"{p}up{i}.up.1.weight"])
-        x = basic_block(torch.cat([up, skips[k]], 1), sd, f"{p}dec{i}.")
+        up = st.tap(f"{p}up{i}.out", up)
+        x = basic_block(torch.cat([up, skips[k]], 1), sd, f"{p}dec{i}.", st)
         t[f"{p}dec{i}"] = x
-    out = F.conv2d(x, sd[p + "fc.weight"], sd[p + "fc.bias"])
-    return torch.tanh(out) if use_tanh else out
+    out = F.conv2d(st.tap(p + "fc.in", x), sd[p + "fc.weight"], sd[p + "fc.bias"])
+    return st.tap(p + "fc.out", torch.tanh(out) if use_tanh else out)
 
 
 def l2_normalize(x):
@@ -276,7 +341,7 @@ def patch_sample(sd, feat, ids):
     return l2_normalize(F.linear(h, sd["netF.mlp_0.2.weight"], sd["netF.mlp_0.2.bias"]))
 
 
-def ugannce_forward(sd, x, m=None, sample_ids=None, val_phase=False, taps=None):
+def ugannce_forward(sd, x, m=None, sample_ids=None, val_phase=False, taps=None, style=DEFAULT_STYLE):
     """network/ugan.py:153-195.  `sample_ids` must be given when features are wanted (the reference draws
     torch.randperm(H*W)[:64] itself, ugan.py:321-322; the oracle takes the draw as an input)."""
     t = taps if taps is not None else {}
@@ -284,29 +349,33 @@ def ugannce_forward(sd, x, m=None, sample_ids=None, val_phase=False, taps=None):
     if m is None:
         m = torch.zeros(x.size(0), n_modal, device=x.device)
     planes = m.view(m.size(0), m.size(1), 1, 1).repeat(1, 1, x.size(2), x.size(3))
-    tsl_out, tsl_skips = ugan_encoder(sd, "tsl_encoder.", torch.cat([x, planes], 1), t)
-    tsl_e5 = basic_block(tsl_out, sd, "enc5.")
+    st = style
+    tsl_out, tsl_skips = ugan_encoder(sd, "tsl_encoder.", torch.cat([x, planes], 1), t, st)
+    tsl_e5 = basic_block(tsl_out, sd, "enc5.", st, tag="tsl.enc5.")
     t["tsl.enc5"] = tsl_e5
-    tsl = ugan_decoder(sd, "tsl_decoder.", tsl_e5, tsl_skips, False, True, t)
-    seg_out, seg_skips = ugan_encoder(sd, "seg_encoder.", x, t)
-    seg_e5 = basic_block(seg_out, sd, "enc5.")
+    tsl = ugan_decoder(sd, "tsl_decoder.", tsl_e5, tsl_skips, False, True, t, st)
+    seg_out, seg_skips = ugan_encoder(sd, "seg_encoder.", x, t, st)
+    seg_e5 = basic_block(seg_out, sd, "enc5.", st, tag="seg.enc5.")
     t["seg.enc5"] = seg_e5
-    seg = ugan_decoder(sd, "seg_decoder.", seg_e5, seg_skips, True, False, t)
+    seg = ugan_decoder(sd, "seg_decoder.", seg_e5, seg_skips, True, False, t, st)
     if val_phase:
         return seg, tsl
     return seg, tsl, [patch_sample(sd, tsl_e5, sample_ids[0])], sample_ids
 
 
-def discriminator_forward(sd, x, taps=None):
+def discriminator_forward(sd, x, taps=None, style=DEFAULT_STYLE):
     """network/ugan.py:225-229."""
     t = taps if taps is not None else {}
-    out = lrelu(F.conv2d(x, sd["main.0.weight"], sd["main.0.bias"], stride=2, padding=1))
-    t["main.0"] = out
+    st = style
+    x = st.tap("main.0.in", x)
+    out = st.act(F.conv2d(x, sd["main.0.weight"], sd["main.0.bias"], stride=2, padding=1), "main.0.act")
+    t["main.0"] = st.tap("main.0.out", out)
     i = 2
     while f"main.{i}.conv1.weight" in sd:
-        out = bottle_block(out, sd, f"main.{i}.")
+        out = bottle_block(out, sd, f"main.{i}.", st)
         t[f"main.{i}"] = out
         i += 1
+    out = st.tap("heads.in", out)
     out_src = F.conv2d(out, sd["conv_src.weight"], padding=1)
     out_cls = F.conv2d(out, sd["conv_cls.weight"])
     return out_src, out_cls.view(out_cls.size(0), out_cls.size(1))

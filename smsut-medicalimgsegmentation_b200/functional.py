@@ -413,14 +413,23 @@ def _bn_stats(x, norm, stats):
         return ops.bn_eval_stats(norm.running_mean, norm.running_var, n, h * w, c), BN_EVAL
 
 
+# Parity instrumentation (tests/parity_layers.py): when a list is installed here, every fused norm + activation call
+# appends (norm module, activation output).  The sign of that output is the LeakyReLU / ReLU mask the kernels used;
+# the per-layer parity protocol forces the oracle onto the same masks.
+ACT_TAPS = [None]
+
+
 def in_act(xa, norm_a, xb=None, norm_b=None, res=None, act=ACT_LRELU, c_params=None, stats_a=None, stats_b=None):
     batch = BN_OFF
     if getattr(norm_a, "smsut_batch_norm", False):
         stats_a, batch = _bn_stats(xa, norm_a, stats_a)
         if xb is not None:
             stats_b, _ = _bn_stats(xb, norm_b, stats_b)
-    return INActFn.apply(xa, norm_a.weight, norm_a.bias, xb, norm_b.weight if norm_b is not None else None,
-                         norm_b.bias if norm_b is not None else None, res, act, c_params, stats_a, stats_b, batch)
+    out = INActFn.apply(xa, norm_a.weight, norm_a.bias, xb, norm_b.weight if norm_b is not None else None,
+                        norm_b.bias if norm_b is not None else None, res, act, c_params, stats_a, stats_b, batch)
+    if ACT_TAPS[0] is not None and act != ACT_NONE:
+        ACT_TAPS[0].append((norm_a, out))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

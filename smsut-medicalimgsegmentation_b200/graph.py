@@ -35,9 +35,47 @@ class GraphedStep:
             self.static_out = step_fn(*self.static_in)
         self.launches_per_replay = _lib.launch_count() - before
 
+    def accepts(self, inputs):
+        """True if `inputs` have the shapes / dtypes the graph was captured for (a ragged last batch does not)"""
+        if len(inputs) != len(self.static_in):
+            return False
+        for dst, src in zip(self.static_in, inputs):
+            if isinstance(dst, torch.Tensor):
+                if not isinstance(src, torch.Tensor) or src.shape != dst.shape or src.dtype != dst.dtype:
+                    return False
+            elif dst != src:
+                return False
+        return True
+
     def __call__(self, *inputs):
         for dst, src in zip(self.static_in, inputs):
             if isinstance(dst, torch.Tensor) and src is not dst:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        # the replay ended with optimizer steps the host-side bookkeeping has not seen: mark the bf16 weight copies
+        # stale so that an eager forward after it (validation, sampling) repacks them
+        from . import ops
+        ops.param_generation[0] += 1
         return self.static_out
+
+
+class StateSnapshot:
+    """Clones of a trainer's live state tensors (weights, optimizer moments, schedules, running statistics); restore()
+    copies them back IN PLACE, so buffers captured in a CUDA graph keep their addresses.  Capturing a step inside a
+    training run costs warm-up iterations on the example batch: the snapshot makes the capture side-effect free."""
+
+    def __init__(self, tensors):
+        seen, self.pairs = set(), []
+        for t in tensors:
+            if not isinstance(t, torch.Tensor) or t.numel() == 0:
+                continue
+            key = (t.data_ptr(), t.numel(), t.dtype)
+            if key in seen:
+                continue
+            seen.add(key)
+            self.pairs.append((t, t.detach().clone()))
+
+    def restore(self):
+        with torch.no_grad():
+            for t, c in self.pairs:
+                t.copy_(c)

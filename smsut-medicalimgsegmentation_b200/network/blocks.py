@@ -62,6 +62,8 @@ class Conv2d(nn.Conv2d):
         assert len(xs) == 1
         y = Fn.DirectConvFn.apply(xs[0], self.weight, self.bias, self.stride[0], self.padding[0], self.fused_act,
                                   self.out_pad, self.out_f32)
+        if Fn.ACT_TAPS[0] is not None and self.fused_act in (ACT_LRELU, ACT_RELU):
+            Fn.ACT_TAPS[0].append((self, y))        # parity instrumentation: the fused activation's output
         return (y, None) if with_stats else y
 
     def forward(self, x):

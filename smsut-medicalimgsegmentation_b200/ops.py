@@ -72,6 +72,9 @@ def det_register(t):
     """Allocate, register and return the fixed-point shadow of the fp32 accumulator tensor `t` (contiguous)."""
     shadow = torch.zeros(t.numel(), dtype=torch.int64, device=t.device)
     call("smsut_det_register", _p(t), t.numel() * 4, _p(shadow))
+    # the registry holds raw addresses: drop the entry when the accumulator dies (its memory may be handed to an
+    # unrelated tensor); the finalizer keeps the shadow alive exactly as long as the accumulator
+    weakref.finalize(t, _det_release, t.data_ptr(), shadow)
     return shadow
 
 
@@ -138,9 +141,7 @@ def zeros(shape, device, dtype=F32):
         return t
     t = torch.zeros(shape, dtype=dtype, device=device)
     if DET[0] and dtype == F32 and t.is_cuda and t.numel() > 0:
-        # outside an iteration's arena: a shadow of its own, unregistered when the tensor dies
-        shadow = det_register(t)
-        weakref.finalize(t, _det_release, t.data_ptr(), shadow)
+        det_register(t)      # outside an iteration's arena: a shadow of its own, unregistered when the tensor dies
     return t
 
 

@@ -27,6 +27,9 @@ class FlatParams:
                 p.data = self.flat[off:off + n].view(p.shape)
                 off += sz
 
+    def live_tensors(self):
+        return [self.flat]
+
 
 class _FlatOptimizer:
     def __init__(self, params, lr):
@@ -91,6 +94,13 @@ class _FlatOptimizer:
             n = p.numel()
             p.grad = self.grad[off:off + n].view(p.shape)
             off += (n + 3) // 4 * 4
+
+    def live_tensors(self):
+        """every device buffer a step mutates (graph.StateSnapshot)"""
+        out = [self.flat, self.grad, self.lr_dev] + [getattr(self, k) for k in self._STATE]
+        if self.grad_shadow is not None:
+            out.append(self.grad_shadow)
+        return out
 
     def _sync_lr(self):
         lr = float(self.param_groups[0]['lr'])
@@ -159,6 +169,9 @@ class PolyLR:
         self.iter_state = torch.zeros(1, dtype=torch.float32, device=dev)
         for o in self.opts[1:]:
             o.lr_dev = self.opts[0].lr_dev    # one shared device scalar
+
+    def live_tensors(self):
+        return [self.iter_state]
 
     def tick(self):
         ops.poly_lr_tick(self.iter_state, self.opts[0].lr_dev, self.base, float(self.max_iter), self.power)

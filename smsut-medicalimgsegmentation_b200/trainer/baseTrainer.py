@@ -37,6 +37,44 @@ class BaseTrainer(object):
         self.loss = DiceAndCrossEntropyLoss(weight_ce=cfg.weight_ce, weight_dc=cfg.weight_dc, batch_dice=True)
         self.epoch = 0
         self.iter = 0
+        self._graphs = {}       # lazily captured CUDA graphs of the iteration, keyed by its host-side mode switches
+
+    # ---- CUDA graph behind the epoch loops: `fit` runs the iteration the benchmark measures -------------------------
+    def graph_enabled(self):
+        """The epoch loops replay ONE captured CUDA graph per iteration (forward, backward, optimizer steps, LR tick:
+        graph.py) -- the eager iteration pays ~1 300 host launches.  SMSUT_GRAPH=0 keeps the eager iteration."""
+        return torch.device(self.device).type == 'cuda' and os.environ.get('SMSUT_GRAPH', '1') != '0'
+
+    def _live_tensors(self):
+        out = []
+        for obj in vars(self).values():
+            if isinstance(obj, torch.nn.Module):
+                out += list(obj.state_dict().values())
+            elif hasattr(obj, 'live_tensors'):
+                out += obj.live_tensors()
+            elif isinstance(obj, torch.Tensor):
+                out.append(obj)
+        return out
+
+    def graphed(self, key, fn, inputs):
+        """The captured graph of `fn(*inputs)` (device tensors only) for mode `key`, captured at first use with the
+        given inputs as the example batch.  The capture's warm-up iterations run on a snapshot: weights, optimizer
+        state, schedules and counters are put back afterwards, so training continues as if nothing had run.
+        Returns None when the inputs do not match the captured shapes (ragged batch): run that iteration eagerly."""
+        from ..graph import GraphedStep, StateSnapshot
+        g = self._graphs.get(key)
+        if g is None:
+            snap = StateSnapshot(self._live_tensors())
+            counters = (self.iter, self.epoch)
+            rng = torch.cuda.get_rng_state(self.device), torch.get_rng_state()
+            g = GraphedStep(fn, list(inputs))
+            snap.restore()
+            self.iter, self.epoch = counters
+            torch.cuda.set_rng_state(rng[0], self.device)
+            torch.set_rng_state(rng[1])
+            ops.param_generation[0] += 1
+            self._graphs[key] = g
+        return g if g.accepts(inputs) else None
 
     @staticmethod
     def sigmoid_rampup(current, rampup_length):

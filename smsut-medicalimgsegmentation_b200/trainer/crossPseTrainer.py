@@ -46,6 +46,8 @@ class crossPseTrainer(BaseTrainer):
         """One iteration of crossPseTrainer.py:96-131 on device tensors: img = cat(labelled, unlabelled)
         (2*bs,1,H,W), msk (bs,H,W).  Returns (seg1, seg2, semi1, semi2) as one device vector."""
         bs = msk.shape[0]
+        if isinstance(lambda_semi, torch.Tensor):
+            lambda_semi = lambda_semi.reshape(())      # device scalar: one captured graph serves every epoch
         ops.arena_begin(img.device)
         self.lr_sched.tick()
         with ops.parallel_branch(5) as b2:          # the two networks share nothing until the cross losses
@@ -78,6 +80,7 @@ class crossPseTrainer(BaseTrainer):
         ul_itr = iter(ul_loader)
         lambda_semi = self.lambda_semi * self.sigmoid_rampup(self.epoch, cfg.max_epoch)
         losses = None
+        lam_dev = torch.zeros(1, device=self.device)
         for i in range(num_iter or cfg.num_iter_per_epoch):
             try:
                 img1, msk, mdl1, _ = next(lb_itr)
@@ -91,7 +94,15 @@ class crossPseTrainer(BaseTrainer):
                 img2, _, mdl2, _ = next(ul_itr)
             img = torch.cat([img1, img2], dim=0).to(self.device, non_blocking=True)
             msk = msk.to(self.device, non_blocking=True)
-            losses = self.train_step(img, msk, lambda_semi)
+            step = None
+            if self.graph_enabled():
+                lam_dev.fill_(float(lambda_semi))
+                step = self.graphed('cross_pse', self.train_step, [img, msk, lam_dev])
+            if step is not None:
+                losses = step(img, msk, lam_dev)
+                self.iter += 1
+            else:
+                losses = self.train_step(img, msk, lambda_semi)
             if (i + 1) % self.log_step == 0:
                 s1, s2, c1, c2 = losses.tolist()
                 self.info('Iter %d, global_iter: %d, crossPse1_loss: %.4f, crossPse2_loss: %.4f, '

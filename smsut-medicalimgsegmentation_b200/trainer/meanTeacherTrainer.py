@@ -50,17 +50,24 @@ class MeanTeacherTrainer(BaseTrainer):
 
     def update_ema_variable(self):
         # alpha = min(1 - 1/(iter+1), 0.99), 0 while iter < 100; ONE fused launch over the flat buffers
-        if self.iter < self.semi_from_iter:
-            self.alpha = 0
-        else:
-            self.alpha = min(1 - 1 / (self.iter + 1), self.ema_decay)
+        self.alpha = self.host_alpha()
         self.alpha_dev.fill_(float(self.alpha))
         ops.ema_update(self.ema_flat.flat, self.optimizer.flat, self.alpha_dev)
 
-    def train_step(self, img, msk, noise, lambda_semi):
+    def host_alpha(self):
+        # alpha = min(1 - 1/(iter+1), 0.99), 0 while iter < 100 (meanTeacherTrainer.py:63-69)
+        return 0 if self.iter < self.semi_from_iter else min(1 - 1 / (self.iter + 1), self.ema_decay)
+
+    def train_step(self, img, msk, noise, lambda_semi, alpha=None, use_semi=None):
         """One iteration of meanTeacherTrainer.py:95-153: img = cat(labelled, unlabelled) (2*bs,1,H,W); `noise` is the
-        clamped N(0, 0.01^2) perturbation of the teacher's input (drawn outside, L106)."""
+        clamped N(0, 0.01^2) perturbation of the teacher's input (drawn outside, L106).  alpha (device scalar) /
+        use_semi: the iteration-dependent EMA coefficient and consistency switch handed in from outside (the captured
+        graph of train_epoch); by default both follow self.iter."""
         bs = msk.shape[0]
+        if use_semi is None:
+            use_semi = self.iter >= self.semi_from_iter
+        if isinstance(lambda_semi, torch.Tensor):
+            lambda_semi = lambda_semi.reshape(())
         ops.arena_begin(img.device)
         self.lr_sched.tick()
         with ops.parallel_branch(5) as b_ema:        # the teacher's forward runs beside the student's
@@ -69,7 +76,7 @@ class MeanTeacherTrainer(BaseTrainer):
         out = self.net(img)
         b_ema.join(ema_outputs)
         sample_loss = self.loss(out[:bs], msk)
-        if self.iter < self.semi_from_iter:
+        if not use_semi:
             semi_loss = torch.zeros((), dtype=torch.float32, device=img.device)
         else:
             semi_loss = Fn.SoftmaxMSEFn.apply(_flat_logits(out[bs:]), _flat_logits(ema_outputs))
@@ -80,7 +87,10 @@ class MeanTeacherTrainer(BaseTrainer):
         if self.parallel is not None:
             self.parallel.all_reduce_grads(self.optimizer)
         self.optimizer.step()
-        self.update_ema_variable()
+        if alpha is None:
+            self.update_ema_variable()
+        else:
+            ops.ema_update(self.ema_flat.flat, self.optimizer.flat, alpha)
         ops.arena_end()
         self.iter += 1
         return torch.stack([sample_loss.detach(), semi_loss.detach()])
@@ -91,6 +101,7 @@ class MeanTeacherTrainer(BaseTrainer):
         ul_itr = iter(ul_loader)
         lambda_semi = self.lambda_semi * self.sigmoid_rampup(self.epoch, self.epoch_rampup)
         losses = None
+        lam_dev = torch.zeros(1, device=self.device)
         for i in range(num_iter or cfg.num_iter_per_epoch):
             try:
                 img1, msk, mdl1, _ = next(lb_itr)
@@ -105,7 +116,20 @@ class MeanTeacherTrainer(BaseTrainer):
             img = torch.cat([img1, img2], dim=0).to(self.device, non_blocking=True)
             msk = msk.to(self.device, non_blocking=True)
             noise = torch.clamp(torch.randn_like(img[cfg.batch_size:]) * 0.01, -0.02, 0.02)
-            losses = self.train_step(img, msk, noise, lambda_semi)
+            step = None
+            if self.graph_enabled():
+                use_semi = self.iter >= self.semi_from_iter
+                self.alpha = self.host_alpha()
+                self.alpha_dev.fill_(float(self.alpha))
+                lam_dev.fill_(float(lambda_semi))
+                inputs = [img, msk, noise, lam_dev, self.alpha_dev]
+                step = self.graphed(('mean_teacher', bool(use_semi)),
+                                    lambda *a: self.train_step(*a, use_semi=use_semi), inputs)
+            if step is not None:
+                losses = step(*inputs)
+                self.iter += 1
+            else:
+                losses = self.train_step(img, msk, noise, lambda_semi)
             if (i + 1) % self.log_step == 0:
                 seg, semi = losses.tolist()
                 self.info('Iter %d, global_iter: %d, semi_loss: %.4f, seg_loss: %.4f, lambda_semi: %f self.alpha: %f' %

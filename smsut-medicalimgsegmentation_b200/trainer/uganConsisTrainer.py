@@ -240,6 +240,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
         ul_itr = iter(ul_loader)
         tic = time.time()
         losses = None
+        lam_dev = torch.zeros(1, device=self.device)
         fixed = None        # the epoch's first labelled batch: the fixed slices of the sample grid (L83-90)
         for i in range(n_critic * (num_iter or cfg.num_iter_per_epoch)):
             try:
@@ -258,7 +259,19 @@ class UGANConsisTrainer(UGANShp0Trainer):
             mj = random.randint(0, cfg.n_modal - 1)
             batch = self.prepare_batch(x_real1, y_real, modal_org1, x_real2, modal_org2, mj)
             alpha, sample_ids = self.draw(batch[0].size(0))
-            losses = self.train_step(*batch, alpha, sample_ids, lambda_semi, self.iter >= self.semi_from_iter)
+            use_semi = self.iter >= self.semi_from_iter
+            step = None
+            if self.graph_enabled():
+                # one captured graph per state of the consistency switch (iter < / >= semi_from_iter); the epoch's
+                # lambda_semi and the learning rate are device scalars, so the graphs serve the whole run
+                lam_dev.fill_(float(lambda_semi))
+                inputs = [*batch, alpha, sample_ids[0], lam_dev]
+                step = self.graphed(('consis', bool(use_semi)),
+                                    lambda *a: self.train_step(*a[:7], [a[7]], a[8], use_semi), inputs)
+            if step is not None:
+                losses = step(*inputs)
+            else:
+                losses = self.train_step(*batch, alpha, sample_ids, lambda_semi, use_semi)
 
             if (i + 1) % (n_critic * self.log_step) == 0:
                 vals = losses.tolist()      # the only device->host sync of the loop

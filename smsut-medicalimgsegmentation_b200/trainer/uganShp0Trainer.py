@@ -221,6 +221,7 @@ class UGANShp0Trainer(BaseTrainer):
         itr = iter(lb_loader)
         tic = time.time()
         losses = None
+        lam_dev = torch.zeros(1, device=self.device)
         for i in range(self.n_critic * (num_iter or cfg.num_iter_per_epoch)):
             try:
                 x_real, y_real, modal_org, _ = next(itr)
@@ -233,9 +234,22 @@ class UGANShp0Trainer(BaseTrainer):
             vec_trg = self.label2onehot(modal_trg, cfg.n_modal)
             dev = self.device
             alpha = torch.randn(x_real.size(0), device=dev)
-            losses = self.shape_train_step(x_real.to(dev, non_blocking=True), y_real.to(dev, non_blocking=True),
-                                           modal_org.to(dev), modal_trg.to(dev), (vec_trg - vec_org).to(dev),
-                                           (vec_org - vec_trg).to(dev), alpha, lambda_shp)
+            batch = [x_real.to(dev, non_blocking=True), y_real.to(dev, non_blocking=True), modal_org.to(dev),
+                     modal_trg.to(dev), (vec_trg - vec_org).to(dev), (vec_org - vec_trg).to(dev), alpha]
+            step = None
+            if self.graph_enabled():
+                # lambda_shp (uganTrainer.py:122-123, per epoch) rides in a device scalar; None = no shape term
+                if lambda_shp is not None:
+                    lam_dev.fill_(float(lambda_shp))
+                    inputs = batch + [lam_dev]
+                    step = self.graphed('shape', self.shape_train_step, inputs)
+                else:
+                    inputs = batch
+                    step = self.graphed('shp0', self.shape_train_step, inputs)
+            if step is not None:
+                losses = step(*inputs)
+            else:
+                losses = self.shape_train_step(*batch, lambda_shp)
             if (i + 1) % (self.n_critic * self.log_step) == 0:
                 log = 'Iter: %d/%d(%d), elapsed: %.2fs,' % (i, self.n_critic * cfg.num_iter_per_epoch, self.iter,
                                                             time.time() - tic)

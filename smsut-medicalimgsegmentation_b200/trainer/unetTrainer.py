@@ -61,7 +61,12 @@ class UnetTrainer(BaseTrainer):
                 img, msk, mdl, _ = next(lb_itr)
             img = img.to(self.device, non_blocking=True)
             msk = msk.to(self.device, non_blocking=True)
-            loss = self.train_step(img, msk)
+            step = self.graphed('unet', self.train_step, [img, msk]) if self.graph_enabled() else None
+            if step is not None:
+                loss = step(img, msk)
+                self.iter += 1
+            else:
+                loss = self.train_step(img, msk)
             for param_group in self.optimizer.param_groups:   # host mirror of the device-side schedule
                 param_group['lr'] = self.optimizer._lr_host = self.lr_sched.host_lr(self.iter)
         return loss
