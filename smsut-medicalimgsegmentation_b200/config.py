@@ -36,4 +36,6 @@ weight_decay = 1e-3
 
 nce_layers = [5]
 
-expr_root = './smsut-out'
+import os as _os
+
+expr_root = _os.environ.get('SMSUT_EXPR_ROOT', './smsut-out')      # the reference's expr_root (config.py:46); env override for tests

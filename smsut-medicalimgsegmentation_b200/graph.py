@@ -52,6 +52,7 @@ class GraphedStep:
             if isinstance(dst, torch.Tensor) and src is not dst:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        self.replays = getattr(self, 'replays', 0) + 1
         # the replay ended with optimizer steps the host-side bookkeeping has not seen: mark the bf16 weight copies
         # stale so that an eager forward after it (validation, sampling) repacks them
         from . import ops

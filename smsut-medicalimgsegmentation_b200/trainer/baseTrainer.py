@@ -29,7 +29,10 @@ class BaseTrainer(object):
             expr_name = self.__class__.__name__
         else:
             expr_name = args.expr_name
-        self.expr_root, self.model_idx = pjoin(cfg.expr_root, expr_name), '000'
+        # the run directory <expr_root>/<NNN> is allocated like the reference's init_train_env (baseTrainer.py:74-77:
+        # NNN = number of entries already under expr_root), but lazily -- at the first save / fit -- so that building a
+        # trainer has no side effects on disk
+        self.expr_root, self._model_idx = pjoin(cfg.expr_root, expr_name), None
         self.modality = 'all'
         self.input_size = getattr(args, 'input_size', None) or cfg.input_size
         self.net = None
@@ -76,6 +79,21 @@ class BaseTrainer(object):
             self._graphs[key] = g
         return g if g.accepts(inputs) else None
 
+    @property
+    def model_idx(self):
+        if self._model_idx is None:
+            if self.phase != 'train':
+                raise RuntimeError("no run id yet: pass -i <model_id> / call load_model(model_idx, which_ckpt)")
+            os.makedirs(self.expr_root, exist_ok=True)
+            self._model_idx = str(len(os.listdir(self.expr_root))).rjust(3, '0')
+            os.makedirs(pjoin(self.expr_root, self._model_idx), exist_ok=True)
+            self.info(f'Create train environment in {pjoin(self.expr_root, self._model_idx)}.')
+        return self._model_idx
+
+    @model_idx.setter
+    def model_idx(self, value):
+        self._model_idx = value
+
     @staticmethod
     def sigmoid_rampup(current, rampup_length):
         """Exponential rampup from https://arxiv.org/abs/1610.02242"""
@@ -102,6 +120,7 @@ class BaseTrainer(object):
     def load_model(self, model_idx, which_ckpt):
         path = pjoin(self.expr_root, model_idx, 'ckpt', f'{which_ckpt}.ckpt')
         self.net.load_state_dict(torch.load(path, map_location='cpu'))
+        self._model_idx = model_idx
 
     # ---- resume state: an extension.  The reference checkpoints weights only, so a
     # restarted run loses SGD momentum, Adam moments, the LR schedule position and the EMA teacher.
@@ -136,14 +155,37 @@ class BaseTrainer(object):
         ops.param_generation[0] += 1        # master weights changed outside an optimizer step: refresh the bf16 packs
         self.epoch, self.iter = state['__counters__']['epoch'], state['__counters__']['iter']
 
-    def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None):
-        train_lb_loader = synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size)
-        train_ul_loader = synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size)
-        test_loader = synlod.get_loader(None, 'test', 0, cfg.batch_size, size=self.input_size, pool_batches=4)
+    def make_loaders(self, loader_type):
+        """(labelled, unlabelled, test) loaders of baseTrainer.py:125-136.  'inTurn' / 'base' read the PNG slice tree
+        under cfg.base_root (data_loader/inTurnLoader.py, baseLoader.py); when no dataset is there (this repository
+        ships none: CHAOS / Synapse are not redistributable) the synthetic abdominal slices are used instead -- LOUDLY,
+        a run on them is a smoke run, not a trained model.  'synthetic' asks for them explicitly."""
+        if loader_type not in ('inTurn', 'base', 'synthetic'):
+            raise NotImplementedError(loader_type)
+        root = getattr(cfg, 'base_root', None)
+        if loader_type != 'synthetic' and root and os.path.isdir(root):
+            from ..data_loader import baseLoader as bslod, inTurnLoader as inlod
+            lod = inlod if loader_type == 'inTurn' else bslod
+            aug = getattr(cfg, 'data_aug', None)
+            return (lod.get_loader(root, 'train', self.fold, cfg.batch_size, aug, device=self.device),
+                    lod.get_loader(root, 'val', self.fold, cfg.batch_size, aug, device=self.device),
+                    lod.get_loader(root, 'test', 0, cfg.batch_size, device=self.device))
+        if loader_type != 'synthetic':
+            self.info(f'*** WARNING: no dataset under cfg.base_root = {root!r}: fit({loader_type!r}) falls back to '
+                      'SYNTHETIC abdominal-like slices (data_loader/syntheticLoader.py). The checkpoints of this run '
+                      'are NOT a model trained on CHAOS / Synapse data. ***')
+        return (synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size),
+                synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size),
+                synlod.get_loader(None, 'test', 0, cfg.batch_size, size=self.input_size, pool_batches=4))
+
+    def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None, loaders=None):
+        """loaders: optional (labelled, unlabelled, test) loaders injected by the caller instead of make_loaders"""
+        train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
         best, best_epoch = -1.0, -1
         for epoch in range(max_epoch or cfg.max_epoch):
             tic = time.time()
             self.train_epoch(train_lb_loader, train_ul_loader, None, num_iter=iters_per_epoch)
+            self._write_timing(time.time() - tic, iters_per_epoch or cfg.num_iter_per_epoch)
             self.epoch += 1
             self.validate_epoch(test_loader)
             dice = self.validate_dice()[0]['dice']        # the reference's model-selection metric (baseTrainer.py:176-180)
@@ -153,6 +195,25 @@ class BaseTrainer(object):
                 best, best_epoch = dice, epoch
                 self.save_model(prefix='best')
         self.save_model(prefix='last')
+
+    def _write_timing(self, epoch_s, iters):
+        """SMSUT_TIMING=<path>: per-epoch iteration timing as JSON (tests/test_parity_layers_gpu.py checks that the
+        epoch loop runs at the benchmarked speed).  steady_ms_per_iter = device time of the last epoch's final
+        iterations (after graph capture), measured by train_epoch with CUDA events when it keeps them."""
+        path = os.environ.get('SMSUT_TIMING')
+        if not path:
+            return
+        import json
+        ev = getattr(self, '_iter_events', None)
+        steady = None
+        if ev and len(ev) >= 8:
+            torch.cuda.synchronize()
+            tail = ev[len(ev) // 2:]
+            steady = tail[0].elapsed_time(tail[-1]) / (len(tail) - 1)
+        replays = sum(getattr(g, 'replays', 0) for g in self._graphs.values())
+        with open(path, 'w') as f:
+            json.dump(dict(epoch_s=epoch_s, iters=iters, ms_per_iter_wall=epoch_s * 1e3 / max(iters, 1),
+                           steady_ms_per_iter=steady, graph_replays=replays, graphs=len(self._graphs)), f)
 
     def validate_dice(self, volume_confusion=None):
         """The reference's selection metric (baseTrainer.py:246-252 -> misc/utils.py:180-203 get_mo_matrix): Dice per

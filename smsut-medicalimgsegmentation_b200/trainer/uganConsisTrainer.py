@@ -241,6 +241,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
         tic = time.time()
         losses = None
         lam_dev = torch.zeros(1, device=self.device)
+        timing = self._iter_events = [] if os.environ.get('SMSUT_TIMING') and torch.cuda.is_available() else None
         fixed = None        # the epoch's first labelled batch: the fixed slices of the sample grid (L83-90)
         for i in range(n_critic * (num_iter or cfg.num_iter_per_epoch)):
             try:
@@ -272,6 +273,10 @@ class UGANConsisTrainer(UGANShp0Trainer):
                 losses = step(*inputs)
             else:
                 losses = self.train_step(*batch, alpha, sample_ids, lambda_semi, use_semi)
+            if timing is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                timing.append(e)
 
             if (i + 1) % (n_critic * self.log_step) == 0:
                 vals = losses.tolist()      # the only device->host sync of the loop

@@ -62,6 +62,7 @@ class UGANShp0Trainer(BaseTrainer):
         D_path = pjoin(self.expr_root, model_idx, 'ckpt', f'{which_ckpt}_D.ckpt')
         self.net.load_state_dict(torch.load(G_path, map_location='cpu'))
         self.D.load_state_dict(torch.load(D_path, map_location='cpu'))
+        self._model_idx = model_idx
         print(f'[*] Load G and D from {G_path}.')
 
     def save_model(self, prefix):

@@ -288,3 +288,45 @@ def test_headline_config_step_parity(pkg):
         tol = 0.12 if k == "D_gp" else (0.08 if k in ("D_fake", "G_cls", "G_fake") else 3e-2)
         assert abs(v - r) < tol * max(1.0, abs(r)), (k, v, r)
     assert cos_d > 0.8 and cos_g > 0.5, (cos_d, cos_g)
+
+
+# --------------------------------------------------------------------------------------------------
+# the drop-in entry points on the GPU: `-p train` replays the captured graph, `-p test` reloads the checkpoints
+# --------------------------------------------------------------------------------------------------
+def test_cli_train_runs_the_graph_and_checkpoints_round_trip(pkg, tmp_path):
+    """`python trainer/uganConsisTrainer.py -p train -f 0 --epochs 1 --iters 24` then `-p test -i 000` through the
+    module's own __main__ on the B200 (SURVEY.md section 8b entry points; a7 fit, N3 checkpoints): fit -> train_epoch
+    must run the captured CUDA graph (the iteration the benchmark times), the epoch's steady-state iteration time is
+    asserted, and the reference-format checkpoints (uganShp0Trainer.py:94-107) load back into fresh networks, oracle
+    weights included."""
+    import subprocess
+    import time
+    env = dict(os.environ, SMSUT_EXPR_ROOT=str(tmp_path), SMSUT_TIMING=os.path.join(str(tmp_path), "timing.json"))
+    pkgdir = os.path.join(ROOT, "smsut-medicalimgsegmentation_b200")
+    script = os.path.join(pkgdir, "trainer", "uganConsisTrainer.py")
+    t0 = time.time()
+    r = subprocess.run([sys.executable, script, "-p", "train", "-f", "0", "-nm", "cli", "--epochs", "1", "--iters", "24"],
+                       cwd=pkgdir, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    timing = json.load(open(env["SMSUT_TIMING"]))
+    report("cli_train", dict(timing=timing, wall_s=time.time() - t0, stdout_tail=r.stdout[-1500:]))
+    assert timing["graph_replays"] >= 20, timing            # the epoch loop replayed the graph, not the eager step
+    assert timing["steady_ms_per_iter"] < 13.0, timing      # the benchmarked iteration: 11 ms + host batch copies
+    for c in ("last_G.ckpt", "last_D.ckpt", "best_G.ckpt", "best_D.ckpt"):
+        assert os.path.exists(os.path.join(str(tmp_path), "cli", "000", "ckpt", c)), c
+    r = subprocess.run([sys.executable, script, "-p", "test", "-f", "0", "-nm", "cli", "-i", "000", "-wh", "last"],
+                       cwd=pkgdir, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dice:" in r.stdout, r.stderr[-3000:]
+    # reference format: plain state_dicts without a `module.` prefix, loadable by the reference's modules (key set
+    # and shapes of the state_dict contract) and by the oracle
+    G = torch.load(os.path.join(str(tmp_path), "cli", "000", "ckpt", "last_G.ckpt"), map_location="cpu")
+    D = torch.load(os.path.join(str(tmp_path), "cli", "000", "ckpt", "last_D.ckpt"), map_location="cpu")
+    assert {k: tuple(v.shape) for k, v in G.items()} == {k: tuple(v) for k, v in O.ugan_shapes().items()}
+    assert {k: tuple(v.shape) for k, v in D.items()} == {k: tuple(v) for k, v in O.disc_shapes(256).items()}
+    x, _ = O.synthetic_batch(2, 256, 5, device=DEV)
+    from smsut_b200.network.ugan import UGANnce
+    net = UGANnce(1, 5, 4, 16).to(DEV)
+    net.load_state_dict(G)
+    seg, tsl = net(x, val_phase=True)
+    rseg, rtsl = O.ugannce_forward(to_dev(G), x, val_phase=True)
+    assert PL.rel(seg, rseg) < 4e-2 and torch.isfinite(tsl).all(), PL.rel(seg, rseg)
