@@ -322,6 +322,26 @@ int smsut_det_ranges(void);                       /* number of live registration
 void* smsut_det_shadow(const void* p);            /* shadow address of an accumulator address, or NULL */
 int smsut_det_resolve(float* dst, int64_t count, smsut_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Input pipeline: gather + joint augmentation + normalisation of one batch in one launch.
+ * Replaces, per slice, the reference's host-side chain  JointRotate -> JointElasticDeform -> JointRandomResizedCrop
+ * (data_loader/externalTransforms.py:46-101) -> [RandomGammaCorrection] -> ToTensor + Normalize(0.5, 0.5) /
+ * MaskToTensor (data_loader/baseLoader.py:87-112), applied by BalanceDataset.__getitem__
+ * (data_loader/balanceLoader.py:66-76) in DataLoader workers.
+ *   images / labels : the resident u8 dataset, (slices, h, w) each
+ *   index           : int64 [n] slice ids of the batch (the InTurn sampler's draw, data_loader/inTurnLoader.py:15-60)
+ *   params          : fp32 [n][SMSUT_AUG_PARAM_FLOATS], per slice:
+ *                     rot_on, m00, m01, m02, m10, m11, m12   inverse rotation, source = M (x+.5, y+.5, 1) - .5
+ *                     ela_on                                  apply the elastic deformation
+ *                     crop_on, top, left, height, width       crop box resized to (h, w)
+ *                     gamma_on, gamma                         RandomGammaCorrection (image only)
+ *                     points, coef[2][5][5]                   cubic B-spline coefficients of the control displacements
+ *   x_out (n,1,h,w) fp32 in [-1, 1];  y_out (n,h,w) int64.   h * w <= 100 KiB (the plane lives in shared memory).
+ * ---------------------------------------------------------------------------------------------- */
+#define SMSUT_AUG_PARAM_FLOATS 66
+int smsut_augment_batch(const uint8_t* images, const uint8_t* labels, const int64_t* index, const float* params,
+                        float* x_out, int64_t* y_out, int32_t n, int32_t h, int32_t w, smsut_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -124,6 +124,7 @@ _PROTOS = {
     "smsut_poly_lr_tick": [P, P, c_float, c_float, c_float, P],
     "smsut_pack_weights": [P, c_int, P],
     "smsut_unpack_wgrads": [P, c_int, P],
+    "smsut_augment_batch": [P, P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_det_register": [P, C.c_size_t, P],
     "smsut_det_unregister": [P],
     "smsut_det_resolve": [P, c_int64, P],

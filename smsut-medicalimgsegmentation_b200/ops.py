@@ -395,7 +395,7 @@ class WgradScratch:
         WgradScratch.owners.add(self)
 
     def _build(self):
-        self.flush()
+        self._flush_scratch()     # NOT flush(): folding the gradient's fixed-point shadow mid-backward would split a sum
         items = [(p, g) for p, g in zip(self.params, self.grads) if getattr(p, "_smsut_tc", None) is not None]
         self.views = {}
         if not items:
@@ -447,6 +447,9 @@ class WgradScratch:
     def flush(self):
         if self.grad_flat is not None:
             resolve(self.grad_flat)       # deterministic mode: atomically accumulated parameter gradients
+        self._flush_scratch()
+
+    def _flush_scratch(self):
         if self.flat is None or not self.dirty:
             return
         resolve(self.flat)
