@@ -2,6 +2,7 @@
 """Module-level constants of the hot path; same names and values as the reference's config.py (the values are
 the contract: config.py:7-11 modalities, :23-33 training constants, :36-37 network, :49 input size, :57 batch,
 :74-78 optimiser and NCE layers).  Dataset roots and augmentation settings are out of scope (synthetic data)."""
+import os as _os
 from enum import Enum
 
 
@@ -28,14 +29,29 @@ base_width = 16
 input_size = 256
 mod_type = ('ct, t1in, t1out, t2')
 
+# Data loader (config.py:44-72): the processed PNG dataset root ('***/bimod' in the reference: a placeholder) and the
+# joint augmentation of the training loaders, applied on the GPU (data_loader/externalTransforms.py)
+base_root = _os.environ.get('SMSUT_BASE_ROOT', '***/bimod')
+png_root = base_root
+split_yaml = 'semi-1910.yaml'
 batch_size = 8
 num_workers = 6
+data_aug = dict(
+    rotate=True,
+    rotate_degrees=15,
+    resizeCrop=True,
+    resizeCrop_size=input_size,
+    elasticDeform=True,
+    elasticDeform_sigmas=(9., 13.),
+    elasticDeform_points=3,
+    colorJitter=False,
+    gammaCorrect=False,
+    gammaCorrect_gammas=(0.7, 1.5),
+)
 
 lr = 1e-2
 weight_decay = 1e-3
 
 nce_layers = [5]
-
-import os as _os
 
 expr_root = _os.environ.get('SMSUT_EXPR_ROOT', './smsut-out')      # the reference's expr_root (config.py:46); env override for tests

@@ -870,6 +870,22 @@ def build_tsl_input(x, m, c_pad):
     return y
 
 
+def augment_batch(images, labels, index, params):
+    """images / labels: the resident u8 dataset (slices, h, w); index int64 (n,); params fp32 (n, 66): see
+    smsut_augment_batch.  Returns (x fp32 (n,1,h,w) in [-1,1], y int64 (n,h,w))."""
+    if images.device.type != "cuda":
+        raise _lib.SmsutError("augment_batch: SMSUT kernels need CUDA tensors (there is no CPU fallback)")
+    slices, h, w = images.shape
+    assert images.dtype == torch.uint8 and labels.dtype == torch.uint8 and labels.shape == images.shape
+    assert images.is_contiguous() and labels.is_contiguous()
+    n = index.numel()
+    assert index.dtype == torch.int64 and params.dtype == F32 and tuple(params.shape) == (n, 66) and params.is_contiguous()
+    x = torch.empty((n, 1, h, w), dtype=F32, device=images.device)
+    y = torch.empty((n, h, w), dtype=torch.int64, device=images.device)
+    call("smsut_augment_batch", _p(images), _p(labels), _p(index), _p(params), _p(x), _p(y), n, h, w, _stream())
+    return x, y
+
+
 # ----------------------------------------------------------------------------------------------
 # losses
 # ----------------------------------------------------------------------------------------------

@@ -215,6 +215,56 @@ class BaseTrainer(object):
             json.dump(dict(epoch_s=epoch_s, iters=iters, ms_per_iter_wall=epoch_s * 1e3 / max(iters, 1),
                            steady_ms_per_iter=steady, graph_replays=replays, graphs=len(self._graphs)), f)
 
+    # ---- `-p pseudo` (baseTrainer.py:320-378): predictions of the test split written out as images -----------------
+    @staticmethod
+    def colorize(img):
+        """label map -> RGB with the reference's palette (baseTrainer.py:322-329)"""
+        colors = [(255, 0, 0), (0, 255, 0), (0, 0, 255), (255, 255, 0)]
+        h, w = img.shape
+        color_img = np.zeros((h, w, 3))
+        for i in range(1, 5):
+            color_img[img == i, :] = colors[i - 1][:]
+        return color_img
+
+    def pseudo_loader(self, loader_type):
+        if loader_type != 'inTurn':
+            raise NotImplementedError(loader_type)
+        return self.make_loaders('inTurn')[2]
+
+    def saving_pseudo(self, loader_type, expr_root, loader=None):
+        """baseTrainer.py:320-378: segment every slice of the test loader and save `<name>pse.jpg` (prediction),
+        `<name>gt.jpg` (label), `<name>ori.jpg` (input) under <expr_root>/pseudo.  The forward + argmax run on the
+        kernels; only the image files are host work.  Returns the number of slices written."""
+        from PIL import Image
+        self.net.eval()
+        pred_root = pjoin(expr_root, 'pseudo')
+        os.makedirs(pred_root, exist_ok=True)
+        loader = loader if loader is not None else self.pseudo_loader(loader_type)
+        self.info(f'Predict and save in {pred_root}.')
+        count = 0
+        with torch.no_grad():
+            for img, msk, mdl, inm in loader:
+                b = img.shape[0]
+                count += b
+                img = img.to(self.device, non_blocking=True)
+                out = self.segment(img)
+                logits = out.permute(0, 2, 3, 1).reshape(-1, out.shape[1])
+                pred = ops.argmax_c(logits if logits.is_contiguous() else logits.contiguous())
+                pred = pred.view(b, *out.shape[2:]).cpu().numpy()
+                img_np, msk_np = img.reshape(b, *img.shape[2:]).cpu().numpy(), msk.cpu().numpy()
+                for i in range(b):
+                    self._save_pseudo_item(pred_root, inm[i], pred[i], msk_np[i], img_np[i], None)
+        self.net.train()
+        print(count)
+        return count
+
+    def _save_pseudo_item(self, pred_root, name, pred, msk, img, fake):
+        from PIL import Image
+        Image.fromarray(self.colorize(pred).astype(np.uint8)).save(pjoin(pred_root, name + 'pse.jpg'))
+        Image.fromarray(self.colorize(msk).astype(np.uint8)).save(pjoin(pred_root, name + 'gt.jpg'))
+        # (a + 1) * 255 on a [-1, 1] image, then mode 'F' -> 'RGB' (clips at 255): the reference's own arithmetic
+        Image.fromarray(((img + 1) * 255).astype(np.float32)).convert('RGB').save(pjoin(pred_root, name + 'ori.jpg'))
+
     def validate_dice(self, volume_confusion=None):
         """The reference's selection metric (baseTrainer.py:246-252 -> misc/utils.py:180-203 get_mo_matrix): Dice per
         volume and organ, averaged over the volumes of a modality, then over organs / modalities; from the per-volume

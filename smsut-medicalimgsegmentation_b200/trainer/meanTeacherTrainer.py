@@ -159,5 +159,9 @@ if __name__ == '__main__':
         trainer = MeanTeacherTrainer('test', args)
         trainer.load_model(args.model_id or '000', args.which_ckpt)
         print('dice: %.4f' % trainer.validate_epoch(synlod.get_loader(None, 'test', 0, cfg.batch_size, pool_batches=4)))
+    elif args.phase == 'pseudo':
+        trainer = MeanTeacherTrainer('pseudo', args)
+        trainer.load_model(args.model_id or '000', args.which_ckpt)
+        trainer.saving_pseudo('inTurn', os.path.join(trainer.expr_root, args.model_id or '000'))
     else:
         raise NotImplementedError

@@ -229,6 +229,52 @@ class UGANConsisTrainer(UGANShp0Trainer):
         return (x_real, y_real.to(dev, non_blocking=True), small(modal_org), small(modal_trg),
                 small(vec_trg - vec_org), small(vec_org - vec_trg))
 
+    # volumes whose slices the reference keeps (uganConsisTrainer.py:290): "selected visualization samples"
+    pseudo_volumes = ('ct_028', 't1in_037', 't1out_015', 't2_032')
+
+    def saving_pseudo(self, loader_type, expr_root, loader=None):
+        """uganConsisTrainer.py:216-306: like BaseTrainer.saving_pseudo, plus `<name>fk.jpg` -- the slice next to its
+        translation into every modality (B, 1, H, (n_modal + 1) W) -- and only for the volumes in `pseudo_volumes`
+        (None: every volume).  Returns (slices seen, slices written)."""
+        from PIL import Image
+        self.net.eval()
+        pred_root = os.path.join(expr_root, 'pseudo')
+        os.makedirs(pred_root, exist_ok=True)
+        loader = loader if loader is not None else self.pseudo_loader(loader_type)
+        self.info(f'Predict and save in {pred_root}.')
+        count = written = 0
+        volumes = getattr(cfg, 'pseudo_volumes', self.pseudo_volumes)      # cfg.pseudo_volumes = None: keep every volume
+        with torch.no_grad():
+            for img, msk, mdl, inm in loader:
+                b = img.shape[0]
+                count += b
+                img = img.to(self.device, non_blocking=True)
+                vec_fixed_org = self.label2onehot(mdl, cfg.n_modal).to(self.device)
+                x_fake_list = [img.float()]
+                for vec_fixed in self.create_vectors(vec_fixed_org, cfg.n_modal):
+                    _, x_fake = self.translate(img, vec_fixed - vec_fixed_org)
+                    x_fake_list.append(x_fake.float())
+                img_fake = torch.cat(x_fake_list, dim=3)
+                out = self.segment(img)
+                logits = out.permute(0, 2, 3, 1).reshape(-1, out.shape[1])
+                pred = ops.argmax_c(logits if logits.is_contiguous() else logits.contiguous())
+                pred = pred.view(b, *out.shape[2:]).cpu().numpy()
+                img_np, msk_np = img.reshape(b, *img.shape[2:]).cpu().numpy(), msk.cpu().numpy()
+                fk = ((img_fake.cpu() + 1.) / 2 * 255).numpy()
+                for i in range(b):
+                    mod, pid = str(inm[i]).split('_')[:2]
+                    if volumes is not None and mod + '_' + pid not in volumes:
+                        continue
+                    written += 1
+                    Image.fromarray(self.colorize(pred[i]).astype(np.uint8)).save(os.path.join(pred_root, inm[i] + 'pse.jpg'))
+                    Image.fromarray(self.colorize(msk_np[i]).astype(np.uint8)).save(os.path.join(pred_root, inm[i] + 'gt.jpg'))
+                    # `((a + 1) * 255).astype(uint8)` wraps above 255: the reference's own arithmetic (L283-287)
+                    Image.fromarray(((img_np[i] + 1) * 255).astype(np.uint8)).save(os.path.join(pred_root, inm[i] + 'ori.jpg'))
+                    Image.fromarray(fk[i, 0].astype(np.uint8)).save(os.path.join(pred_root, inm[i] + 'fk.jpg'))
+        self.net.train()
+        print(count)
+        return count, written
+
     def train_epoch(self, lb_loader, ul_loader, meter, num_iter=None):
         self.net.train()
         self.D.train()
@@ -323,5 +369,9 @@ if __name__ == '__main__':
         trainer = UGANConsisTrainer('test', args)
         trainer.load_model(args.model_id or '000', args.which_ckpt)
         print('dice: %.4f' % trainer.validate_epoch(synlod.get_loader(None, 'test', 0, cfg.batch_size, pool_batches=4)))
+    elif args.phase == 'pseudo':
+        trainer = UGANConsisTrainer('pseudo', args)
+        trainer.load_model(args.model_id or '000', args.which_ckpt)
+        trainer.saving_pseudo('inTurn', os.path.join(trainer.expr_root, args.model_id or '000'))
     else:
         raise NotImplementedError

@@ -122,7 +122,12 @@ def run_layer(Fn, layer, sd, act_dtype=BF16):
     free = list(st_free.masks.values())
     nflip = sum(int((crop(a, b.shape[1]) != b).sum()) for a, b in zip(masks, free))
     ntot = sum(b.numel() for b in free)
-    res = dict(fwd=rel(y_cmp, yr), dx=[], params={}, flips=(nflip / ntot if ntot else 0.0))
+    yr_d = yr.detach().float()
+    res = dict(fwd=rel(y_cmp, yr), dx=[], params={}, flips=(nflip / ntot if ntot else 0.0),
+               # tail of the forward error: largest element error in units of the reference's RMS (a halo / tile-edge
+               # bug would put a few elements far outside what bf16 rounding of large activations explains)
+               fwd_max_over_rms=((y_cmp.reshape(yr_d.shape) - yr_d).abs().max() / (yr_d.pow(2).mean().sqrt() + 1e-30)).item(),
+               ref_max_over_rms=(yr_d.abs().max() / (yr_d.pow(2).mean().sqrt() + 1e-30)).item())
     for leaf, x, g in zip(leaves, xs_r, gx):
         if g is None:
             continue

@@ -514,3 +514,34 @@ def test_cli_train_then_test_entry_points(exact, tmp_path, monkeypatch, capsys, 
     monkeypatch.setattr(sys, "argv", [module + ".py", "-p", "test", "-f", "0", "-nm", "cli", "-i", "000", "-wh", "last"])
     runpy.run_module(name, run_name="__main__")
     assert "dice:" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("module", ["unetTrainer", "uganConsisTrainer"])
+def test_cli_pseudo_entry_point(exact, tmp_path, monkeypatch, capsys, module):
+    """`-p pseudo -i 000` (uganConsisTrainer.py:329-332 -> saving_pseudo, baseTrainer.py:320-378 /
+    uganConsisTrainer.py:216-306): prediction / label / input images of the test split, plus the translation strip
+    for the GAN trainer, written under <run>/pseudo."""
+    import runpy
+    from PIL import Image
+    from smsut_b200 import config as cfg
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    monkeypatch.setattr(cfg, "input_size", 32)
+    monkeypatch.setattr(cfg, "expr_root", str(tmp_path))
+    name = f"smsut_b200.trainer.{module}"
+    monkeypatch.setattr(sys, "argv", [module + ".py", "-p", "train", "-f", "0", "-nm", "cli", "--epochs", "1", "--iters", "1"])
+    sys.modules.pop(name, None)
+    runpy.run_module(name, run_name="__main__")
+    monkeypatch.setattr(cfg, "pseudo_volumes", None, raising=False)      # the synthetic volumes are not the four named ones
+    monkeypatch.setattr(sys, "argv", [module + ".py", "-p", "pseudo", "-f", "0", "-nm", "cli", "-i", "000", "-wh", "last"])
+    runpy.run_module(name, run_name="__main__")
+    out = os.path.join(str(tmp_path), "cli", "000", "pseudo")
+    files = sorted(os.listdir(out))
+    kinds = ("pse.jpg", "gt.jpg", "ori.jpg") + (("fk.jpg",) if module == "uganConsisTrainer" else ())
+    assert len(files) == 8 * len(kinds)            # 4 test batches of 2 slices
+    for k in kinds:
+        assert sum(f.endswith(k) for f in files) == 8
+    pse = Image.open(os.path.join(out, [f for f in files if f.endswith("pse.jpg")][0]))
+    assert pse.size == (32, 32) and pse.mode == "RGB"
+    if module == "uganConsisTrainer":
+        fk = Image.open(os.path.join(out, [f for f in files if f.endswith("fk.jpg")][0]))
+        assert fk.size == (32 * (cfg.n_modal + 1), 32)

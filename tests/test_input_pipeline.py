@@ -1,0 +1,254 @@
+"""Input pipeline: sampler / dataset / parameter-draw host logic on the CPU (pinned to golden
+index streams produced by the reference's own sampler classes), and the fused GPU augmentation kernel against a torch
+`grid_sample` statement of the same three resampling stages."""
+import json
+import math
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _write_dataset(root, size=32, per_patient=5, patients=(("ct", ["001", "002"]), ("t1in", ["003"]), ("t1out", ["004"]),
+                                                           ("t2", ["005", "006"]))):
+    """a tiny PNG tree in the reference's layout + split file (baseLoader.py:31-48)"""
+    import yaml
+    from PIL import Image
+    rng = np.random.RandomState(0)
+    split = {}
+    for m, pids in patients:
+        for pid in pids:
+            for sub in ("images", "labels"):
+                os.makedirs(os.path.join(root, m, pid, sub), exist_ok=True)
+            for z in range(per_patient):
+                img = (rng.rand(size, size) * 255).astype(np.uint8)
+                lab = (rng.rand(size, size) * 5).astype(np.uint8).clip(0, 4)
+                name = f"{m}_{pid}_{z:03d}.png"
+                Image.fromarray(img).save(os.path.join(root, m, pid, "images", name))
+                Image.fromarray(lab).save(os.path.join(root, m, pid, "labels", name))
+        split[m] = {"train": [list(pids)], "val": [list(pids)], "test": list(pids)}
+    with open(os.path.join(root, "semi-1910.yaml"), "w") as f:
+        yaml.safe_dump(split, f)
+
+
+def test_inturn_samplers_match_reference_streams(pkg):
+    from smsut_b200.data_loader.inTurnLoader import InTurnTestBatchSampler, InTurnTrainBatchSampler
+    cases = json.load(open(os.path.join(HERE, "golden", "inturn_sampler.json")))
+    assert len(cases) == 5
+    for c in cases:
+        samples, n = [], 0
+        for s in c["sizes"]:
+            samples.append(list(range(n, n + s)))
+            n += s
+        random.seed(c["seed"])
+        sampler = InTurnTrainBatchSampler([list(x) for x in samples], c["batch_size"], c["shuffle"])
+        assert len(sampler) == c["train_len"]
+        for want in c["epochs"]:
+            assert [list(b) for b in sampler] == want
+        test = InTurnTestBatchSampler([list(x) for x in samples], c["batch_size"])
+        assert [list(b) for b in test] == c["test"] and len(test) == c["test_len"]
+
+
+def test_parameter_draws(pkg):
+    from smsut_b200.data_loader import externalTransforms as extt
+    random.seed(0)
+    np.random.seed(0)
+    # rotation about the centre: the centre maps to itself, a quarter turn maps corners onto corners
+    m = extt.inverse_rotation(30.0, 64, 48)
+    cx, cy = 24.0, 32.0
+    assert abs(m[0] * cx + m[1] * cy + m[2] - cx) < 1e-9 and abs(m[3] * cx + m[4] * cy + m[5] - cy) < 1e-9
+    assert abs(m[0] * m[4] - m[1] * m[3] - 1.0) < 1e-12                      # a rotation
+    # crop parameters: inside the image, area / aspect in range (torchvision RandomResizedCrop.get_params)
+    for _ in range(500):
+        i, j, h, w = extt.JointRandomResizedCrop.get_params(256, 256, (0.6, 1.0), (3 / 4, 4 / 3))
+        assert 0 <= i <= 256 - h and 0 <= j <= 256 - w and 0.59 * 65536 <= h * w <= 65536 + 512
+        assert 3 / 4 - 0.02 <= w / h <= 4 / 3 + 0.02
+    # B-spline coefficients interpolate the control values: (c[i-1] + 4 c[i] + c[i+1]) / 6 == v[i] with mirrored ends
+    for n in (3, 4, 5):
+        v = np.random.randn(2, n, n)
+        c = extt.bspline_coefficients(v).astype(np.float64)
+        pad = np.pad(c, ((0, 0), (1, 1), (1, 1)), mode="reflect")
+        rows = (pad[:, :-2, 1:-1] + 4 * pad[:, 1:-1, 1:-1] + pad[:, 2:, 1:-1]) / 6
+        padr = np.pad(rows, ((0, 0), (0, 0), (1, 1)), mode="reflect")
+        back = (padr[:, :, :-2] + 4 * rows + padr[:, :, 2:]) / 6
+        assert np.abs(back - v).max() < 1e-5
+    # the composed draw packs into the kernel's parameter record
+    comp = extt.JointCompose([extt.JointRotate(15), extt.JointElasticDeform((9., 13.), 3, p=1.0),
+                              extt.JointRandomResizedCrop(256)])
+    rec = comp.draw(256, 256)
+    out = np.zeros(extt.PARAM_FLOATS, dtype=np.float32)
+    extt.pack_params(rec, out)
+    assert out[0] == 1 and out[7] == 1 and out[8] == 1 and out[13] == 0 and out[15] == 3
+    assert np.abs(out[16:16 + 18]).max() > 0 and np.abs(out[16 + 18:]).max() == 0
+    with pytest.raises(NotImplementedError):
+        extt.JointCompose([extt.JointRandomResizedCrop(256), extt.JointRotate(15)])      # order of baseLoader.py:93-100
+
+
+def test_parse_aug_and_config(pkg):
+    from smsut_b200 import config as cfg
+    from smsut_b200.data_loader import baseLoader as bslod
+    from smsut_b200.data_loader import externalTransforms as extt
+    assert bslod.parse_aug(None) is None and bslod.parse_aug({}) is None
+    comp = bslod.parse_aug(cfg.data_aug)              # the reference's defaults (config.py:57-68)
+    assert [type(t) for t in comp.transforms] == [extt.JointRotate, extt.JointElasticDeform, extt.JointRandomResizedCrop]
+    assert comp.transforms[0].degrees == (-15, 15) and comp.transforms[1].points == 3
+    with pytest.raises(NotImplementedError):
+        bslod.parse_aug(dict(cfg.data_aug, colorJitter=True))
+
+
+# --------------------------------------------------------------------------------------------------
+# torch statement of the three stages (float coordinates as the kernel defines them, sampling by grid_sample)
+# --------------------------------------------------------------------------------------------------
+def _grid_sample_u8(src, sy, sx, mode, zeros=True, box=None):
+    """src (h, w) u8, absolute source coordinates sy / sx (h, w) -> u8 via torch grid_sample (align_corners=False)"""
+    h, w = src.shape
+    if box is not None:                      # crop, then resize: sampling clamps to the crop box
+        i, j, ch, cw = box
+        src = src[i:i + ch, j:j + cw]
+        sy, sx = sy - i, sx - j
+        h, w = ch, cw
+    gx = (sx + 0.5) * 2.0 / w - 1.0
+    gy = (sy + 0.5) * 2.0 / h - 1.0
+    grid = torch.stack([gx, gy], -1)[None]
+    out = F.grid_sample(src[None, None].float(), grid, mode=mode, padding_mode="zeros" if zeros else "border",
+                        align_corners=False)[0, 0]
+    return torch.floor(out + 0.5).clamp(0, 255).to(torch.uint8) if mode == "bilinear" else out.to(torch.uint8)
+
+
+def _bspline_field(coef, n, size, dev):
+    """dense displacement along one axis pair from (n, n) B-spline coefficients (mirror), evaluated in torch"""
+    def basis(t):
+        return torch.stack([(1 - 3 * t + 3 * t ** 2 - t ** 3) / 6, (4 - 6 * t ** 2 + 3 * t ** 3) / 6,
+                            (1 + 3 * t + 3 * t ** 2 - 3 * t ** 3) / 6, t ** 3 / 6], -1)
+
+    def mirror(i):
+        period = 2 * (n - 1)
+        i = i % period
+        return torch.where(i < n, i, period - i)
+    u = torch.arange(size, device=dev, dtype=torch.float32) * ((n - 1) / (size - 1))
+    f = torch.floor(u)
+    w = basis(u - f)                                                  # (size, 4)
+    idx = mirror(f.long()[:, None] - 1 + torch.arange(4, device=dev)[None])      # (size, 4)
+    c = coef[idx]                                                     # rows gathered: (size, 4, n)
+    c = c[:, :, idx]                                                  # (size_y, 4, size_x, 4)
+    return torch.einsum("ya,yaxb,xb->yx", w, c, w)
+
+
+def _reference_pipeline(img, msk, p, dev):
+    """one slice through rotate -> elastic -> resized crop -> normalise, per parameter record p (66 floats)"""
+    h, w = img.shape
+    yy, xx = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32),
+                            torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+    if p[0]:
+        sx = p[1] * (xx + 0.5) + p[2] * (yy + 0.5) + p[3] - 0.5
+        sy = p[4] * (xx + 0.5) + p[5] * (yy + 0.5) + p[6] - 0.5
+        img, msk = _grid_sample_u8(img, sy, sx, "bilinear"), _grid_sample_u8(msk, sy, sx, "nearest")
+    if p[7]:
+        n = int(p[15])
+        coef = torch.tensor(p[16:16 + 2 * n * n], device=dev).view(2, n, n)
+        dy, dx = _bspline_field(coef[0], n, h, dev), _bspline_field(coef[1], n, h, dev)
+        img, msk = _grid_sample_u8(img, yy + dy, xx + dx, "nearest"), _grid_sample_u8(msk, yy + dy, xx + dx, "nearest")
+    if p[8]:
+        i, j, ch, cw = (int(v) for v in p[9:13])
+        sy = i + (yy + 0.5) * (ch / h) - 0.5
+        sx = j + (xx + 0.5) * (cw / w) - 0.5
+        img = _grid_sample_u8(img, sy, sx, "bilinear", zeros=False, box=(i, j, ch, cw))
+        msk = _grid_sample_u8(msk, sy, sx, "nearest", zeros=False, box=(i, j, ch, cw))
+    x = img.float()
+    if p[13]:
+        x = torch.floor((255 + 1 - 1e-3) * (x / 255) ** float(p[14]))
+    return (x / 255 - 0.5) / 0.5, msk.long()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [256, 64])
+def test_augment_kernel_matches_grid_sample_statement(pkg, size):
+    from smsut_b200 import ops
+    from smsut_b200.data_loader import externalTransforms as extt
+    dev = "cuda"
+    random.seed(5)
+    np.random.seed(5)
+    g = torch.Generator().manual_seed(5)
+    # smooth-ish images (bilinear on pure noise would make every rounding tie visible) and blocky labels
+    base = F.interpolate(torch.rand(12, 1, size // 8, size // 8, generator=g), size=(size, size), mode="bilinear")[:, 0]
+    images = (base * 255).round().to(torch.uint8).to(dev).contiguous()
+    labels = (F.interpolate(torch.rand(12, 1, size // 16, size // 16, generator=g), size=(size, size))[:, 0] * 5).long() \
+        .clamp(0, 4).to(torch.uint8).to(dev).contiguous()
+    sigma = (9. * size / 256, 13. * size / 256)
+    stages = [
+        extt.JointCompose([]),                                                                   # normalise only
+        extt.JointCompose([extt.JointRotate(15)]),
+        extt.JointCompose([extt.JointElasticDeform(sigma, 3, p=1.0)]),
+        extt.JointCompose([extt.JointRandomResizedCrop(size)]),
+        extt.JointCompose([extt.RandomGammaCorrection((0.7, 1.5), p=1.0)]),
+        extt.JointCompose([extt.JointRotate(15), extt.JointElasticDeform(sigma, 3, p=1.0),
+                           extt.JointRandomResizedCrop(size), extt.RandomGammaCorrection((0.7, 1.5), p=1.0)]),
+    ]
+    report = {}
+    for si, comp in enumerate(stages):
+        index = torch.tensor([3, 0, 11, 7, 7, 1, 5, 9], dtype=torch.int64)
+        params = torch.zeros((len(index), extt.PARAM_FLOATS))
+        for r in range(len(index)):
+            extt.pack_params(comp.draw(size, size), params[r].numpy())
+        x, y = ops.augment_batch(images, labels, index.to(dev), params.to(dev))
+        assert x.shape == (8, 1, size, size) and y.shape == (8, size, size) and y.dtype == torch.int64
+        img_bad = msk_bad = big = 0
+        for r in range(len(index)):
+            xr, yr = _reference_pipeline(images[index[r]], labels[index[r]], params[r].tolist(), dev)
+            d = ((x[r, 0] - xr).abs() * 127.5).round()                # difference in u8 steps
+            img_bad += int((d > 0).sum())
+            big += int((d > 1).sum()) if si in (0, 1, 3) else 0        # single resampling stage: never more than 1 step
+            msk_bad += int((y[r] != yr).sum())
+        tot = len(index) * size * size
+        report[si] = (img_bad / tot, msk_bad / tot)
+        if si == 0:
+            assert img_bad == 0 and msk_bad == 0                      # pure gather + normalise: exact
+        # the two sides evaluate the same coordinate formulas in different float orders: a coordinate that lands within
+        # an ulp of a rounding boundary may resolve differently (one u8 step for bilinear, a neighbour for nearest);
+        # chained stages carry such a pixel into the next stage
+        assert img_bad / tot < (2e-3 if si < 5 else 2e-2), (si, report)
+        assert msk_bad / tot < (2e-3 if si < 5 else 2e-2), (si, report)
+        assert big == 0, (si, big)
+    os.makedirs(os.path.join(os.path.dirname(HERE), "gpurun_out"), exist_ok=True)
+    json.dump(report, open(os.path.join(os.path.dirname(HERE), "gpurun_out", f"parity_augment_{size}.json"), "w"))
+
+
+@pytest.mark.gpu
+def test_loaders_on_a_png_tree(pkg, tmp_path):
+    """baseLoader / inTurnLoader over a tiny PNG tree in the reference's layout: one modality per batch, the tuple the
+    trainers consume, test-phase batches equal the decoded files exactly, and a trainer epoch runs on them."""
+    from smsut_b200 import config as cfg
+    from smsut_b200.data_loader import baseLoader as bslod
+    from smsut_b200.data_loader import inTurnLoader as inlod
+    root = str(tmp_path / "bimod")
+    _write_dataset(root, size=64, per_patient=6)
+    random.seed(1)
+    loader = inlod.get_loader(root, "train", 0, 4, cfg.data_aug and dict(cfg.data_aug, resizeCrop_size=64,
+                                                                         elasticDeform_sigmas=(2., 3.)))
+    batches = list(loader)
+    assert len(batches) == len(loader) > 0
+    for img, msk, mdl, names in batches:
+        assert img.is_cuda and img.shape == (4, 1, 64, 64) and img.dtype == torch.float32 and img.abs().max() <= 1
+        assert msk.shape == (4, 64, 64) and msk.dtype == torch.int64 and int(msk.max()) <= 4
+        assert len(torch.unique(mdl)) == 1 and not mdl.is_cuda            # one modality per batch (baseTrainer.py:222)
+        assert all(n.startswith(cfg.Modality(int(mdl[0])).name + "_") for n in names)
+    test = inlod.get_loader(root, "test", 0, 4)
+    from PIL import Image
+    seen = 0
+    for img, msk, mdl, names in test:
+        for k, n in enumerate(names):
+            m, pid, _ = n.split("_")
+            ref = np.asarray(Image.open(os.path.join(root, m, pid, "images", n + ".png")), dtype=np.float32)
+            lab = np.asarray(Image.open(os.path.join(root, m, pid, "labels", n + ".png")))
+            assert np.array_equal(img[k, 0].cpu().numpy(), ((ref / 255 - 0.5) / 0.5).astype(np.float32))
+            assert np.array_equal(msk[k].cpu().numpy(), lab.astype(np.int64))
+            seen += 1
+    assert seen == 36
+    base = bslod.get_loader(root, "train", 0, 4, None, modal="ct")
+    assert len(base) == 3 and all(int(b[2][0]) == 0 for b in base)            # 12 ct slices, drop_last

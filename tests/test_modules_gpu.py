@@ -89,8 +89,14 @@ def test_unet_parity(pkg, size, n):
     g = grad_report(net.named_parameters(), {k: v.grad for k, v in leaf.items()})
     mask = margin_mask(ref.detach())
     agree = (out.argmax(1) == ref.argmax(1))[mask].float().mean().item()
-    report(f"unet_{size}", dict(logits_rel=r_fwd, loss=loss.item(), loss_ref=lref.item(), grads=g,
-                                argmax_agree_on_margin=agree, margin_excluded_frac=1 - mask.float().mean().item()))
+    # where does the argmax become EXACT?  smallest top-2 margin (in units of the logits' RMS) above which no pixel
+    # disagrees, and the share of pixels below it
+    refd = ref.detach()
+    top2 = refd.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1]) / refd.pow(2).mean().sqrt()
+    bad = out.argmax(1) != refd.argmax(1)
+    exact_from = margin[bad].max().item() if bad.any() else 0.0
+    exact_excluded = (margin <= exact_from).float().mean().item()
     # the same module tree with every kernel replaced by its bf16-emulating PyTorch statement: isolates kernel
     # errors from the (inherent) effect of bf16 activation storage
     kgrads = {k: p.grad.clone() for k, p in net.named_parameters()}
@@ -107,11 +113,16 @@ def test_unet_parity(pkg, size, n):
     report(f"unet_{size}", dict(logits_rel=r_fwd, logits_rel_vs_bf16_emulation=r_emu, loss=loss.item(),
                                 loss_ref=lref.item(), grads_vs_fp32_oracle=g, grads_vs_bf16_emulation=ge,
                                 grad_cosine_vs_fp32=cos_fp32, grad_cosine_vs_bf16_emulation=cos_emu,
-                                argmax_agree_on_margin=agree, margin_excluded_frac=1 - mask.float().mean().item()))
+                                argmax_agree_on_margin=agree, margin_excluded_frac=1 - mask.float().mean().item(),
+                                argmax_exact_above_margin_rms=exact_from, argmax_exact_excluded_frac=exact_excluded))
     assert r_emu < 1.5e-2, ("logits vs bf16 emulation", r_emu)
     assert r_fwd < 3e-2
     assert abs(loss.item() - lref.item()) < 1e-2 * abs(lref.item())
-    assert agree > 0.995
+    assert agree > 0.998, agree
+    # "argmax masks bit-exact wherever the logit margin exceeds the tolerance": every pixel whose margin exceeds
+    # `exact_from` logit-RMS agrees; the accumulated bf16 error of 27 layers has a heavy tail (a few pixels are off by
+    # ten times the RMS error), so that margin is ~0.2 RMS rather than the 2e-2 of the mean error
+    assert exact_from < 0.35 and exact_excluded < 0.35, (exact_from, exact_excluded)
     # per-tensor gradient deviations are dominated by LeakyReLU mask flips of near-zero bf16 pre-activations
     # (DESIGN.md section 4): bound the median and require the update direction to agree
     gv = sorted(g.values())
@@ -166,25 +177,40 @@ def test_unet_batchnorm_relu_parity(pkg):
 
 def test_ugannce_parity(pkg):
     from smsut_b200.network.ugan import UGANnce
-    sd = to_dev(O.make_weights(O.ugan_shapes(), 4))
-    sd["tsl_decoder.fc.weight"] *= 0.05       # keep tanh out of saturation (sign-like heads flip on bf16 noise)
+    from smsut_b200 import functional as Fn
+    sd = to_dev(O.make_weights(O.ugan_shapes(), 4))        # the real kaiming-scale weights, heads included
     net = UGANnce(1, 5, 4, 16).to(DEV)
     net.load_state_dict(sd)
     x, _ = O.synthetic_batch(2, 256, 4, device=DEV)
     m = torch.tensor([[1., 0, -1, 0], [0, 1., -1, 0]], device=DEV)
     ids = [torch.randperm(256, generator=torch.Generator().manual_seed(0))[:64].to(DEV)]
+    Fn.ACT_TAPS[0] = []
     seg, tsl, feats, _ = net(x, m, sample_ids=ids)
+    taps, Fn.ACT_TAPS[0] = Fn.ACT_TAPS[0], None
     leaf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    rseg, rtsl, rfeats, _ = O.ugannce_forward(leaf, x, m, sample_ids=ids)
+    st = O.RecordingStyle()
+    rseg, rtsl, rfeats, _ = O.ugannce_forward(leaf, x, m, sample_ids=ids, style=st)
     r = dict(seg=rel(seg, rseg), tsl=rel(tsl, rtsl), feat=rel(feats[0], rfeats[0]))
+    # The translation head is tanh(1x1 conv) with ONE output channel: at kaiming scale its pre-activation has a
+    # standard deviation of ~5, a third of the outputs sit in saturation and the rest follow the pre-activation's
+    # ABSOLUTE error (tanh is 1-Lipschitz), so the output's relative error (0.17) says little.  What the kernels owe
+    # is (a) the pre-activation within the accumulated bf16 tolerance and (b) |tanh(a) - tanh(b)| <= |a - b|.
+    d1 = [t for mod, t in taps if mod is net.tsl_decoder.dec1.bn2][0]              # the head's input (NHWC bf16)
+    w, b = sd["tsl_decoder.fc.weight"], sd["tsl_decoder.fc.bias"]
+    z = torch.nn.functional.conv2d(d1.permute(0, 3, 1, 2).float(), w, b)
+    rz = torch.nn.functional.conv2d(st.taps["tsl_decoder.fc.in"].detach(), w, b)
+    r["tsl_preactivation"] = rel(z, rz)
+    r["tsl_saturated_frac"] = (rtsl.abs() > 0.99).float().mean().item()
+    assert rel(tsl, torch.tanh(z)) < 1e-5                       # the fused head kernel on its own input: exact
+    assert ((tsl.float() - rtsl).abs() <= (z - rz).abs() + 1e-6).all()
+    assert r["tsl_preactivation"] < 4e-2, r
     w = torch.randn_like(rseg)
     (seg * w).mean().add(tsl.mean()).add((feats[0] ** 3).sum()).backward()
     (rseg * w).mean().add(rtsl.mean()).add((rfeats[0] ** 3).sum()).backward()
     g = grad_report(net.named_parameters(), {k: v.grad for k, v in leaf.items()})
     cos = cosine(list(net.named_parameters()), {k: v.grad for k, v in leaf.items()})
     report("ugannce", dict(outputs=r, grads=g, grad_cosine_vs_fp32=cos))
-    # the 1-channel tanh head sums 16 cancelling terms: its relative error is ~4x that of its input activations
-    assert r['seg'] < 4e-2 and r['feat'] < 5e-2 and r['tsl'] < 0.2, r
+    assert r['seg'] < 3e-2 and r['feat'] < 5e-2 and r['tsl'] < 0.25, r
     assert len(net(x, val_phase=True)) == 2
     assert cos > 0.8, cos
 
@@ -266,7 +292,8 @@ def test_ugan_consis_step_parity(pkg, use_semi):
     assert cos_d > 0.5 and cos_g > 0.4, (cos_d, cos_g)      # observed over 10 runs: cos_d 0.88-0.96, cos_g 0.595-0.874
 
 
-def test_unet_free_running_loss_trajectory(pkg):
+@pytest.mark.parametrize("size", [128, 256])
+def test_unet_free_running_loss_trajectory(pkg, size):
     """SGD-only U-Net path, 200 free-running steps against the fp32 oracle (BASELINE.json north_star: "loss
     trajectories over 200 steps within 1%"; SURVEY 7.2 item 7: this path is well conditioned, unlike the GAN step).
     Both sides run free (no teacher forcing), so the comparison is between two chaotic trajectories: the order of
@@ -274,24 +301,35 @@ def test_unet_free_running_loss_trajectory(pkg):
     LeakyReLU masks.  Measured over 14 runs on B200 (scripts/poison_probe.py): mean deviation 0.36-1.7 % (median
     0.55 %), worst single step 1.5-4.5 % (at the tail, where the loss has fallen from 3.12 to 0.026), first 40 steps
     <= 1.8 %.  The bounds below are that spread with margin, not a tighter claim."""
+    from smsut_b200 import ops
     from smsut_b200.trainer.unetTrainer import UnetTrainer
-    tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=128))
-    sd = to_dev(O.make_weights(O.unet_shapes(), 21))
-    tr.net.load_state_dict(sd)
-    st, traj = {}, []
-    for it in range(200):
-        x, y = O.synthetic_batch(4, 128, 30 + it % 8, device=DEV)
-        loss = tr.train_step(x, y).item()
-        ref, _ = O.unet_step(sd, st, x, y, O.poly_lr(1e-2, max(it - 1, 0), 30000))
-        traj.append((loss, ref.item()))
+    # deterministic accumulation: the kernel path's trajectory is then ONE reproducible sequence (round 1 bounded the
+    # run-to-run spread of the atomics instead), so the bounds below are the measured values with a small margin
+    ops.set_deterministic(True)
+    try:
+        tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=size))
+        sd = to_dev(O.make_weights(O.unet_shapes(), 21))
+        tr.net.load_state_dict(sd)
+        st, traj = {}, []
+        for it in range(200):
+            x, y = O.synthetic_batch(4, size, 30 + it % 8, device=DEV)
+            loss = tr.train_step(x, y).item()
+            ref, _ = O.unet_step(sd, st, x, y, O.poly_lr(1e-2, max(it - 1, 0), 30000))
+            traj.append((loss, ref.item()))
+    finally:
+        ops.set_deterministic(False)
     dev = [abs(a - b) / abs(b) for a, b in traj]
     worst, mean_dev, early = max(dev), sum(dev) / len(dev), max(dev[:40])
-    report("unet_trajectory", dict(worst_rel=worst, mean_rel=mean_dev, worst_rel_first_40=early, steps=len(traj),
-                                   trajectory=traj))
-    assert early < 3e-2, ("worst loss deviation over the first 40 steps", early)
-    assert mean_dev < 3e-2, ("mean loss deviation over the trajectory", mean_dev)
-    assert worst < 8e-2, ("worst loss deviation over the trajectory", worst)
-    assert traj[-1][0] < 0.7 * traj[0][0], "the loss did not go down"
+    report(f"unet_trajectory_{size}", dict(worst_rel=worst, mean_rel=mean_dev, worst_rel_first_40=early, steps=len(traj),
+                                           trajectory=traj))
+    # north_star: "loss trajectories over 200 steps within 1%".  Measured (B200, deterministic mode): the first 40
+    # steps stay within 0.5 %; over all 200 steps the loss falls 160x (3.09 -> 0.019) and the two free-running
+    # optimisations drift apart to a mean of 1.5 % / a worst step of 3.3 % at 256x256 -- the 1 % holds for the part of
+    # the trajectory where the loss is not yet dominated by its last digits, not for the tail.
+    assert early < 1e-2, ("worst loss deviation over the first 40 steps", early)
+    assert mean_dev < 2.5e-2, ("mean loss deviation over the trajectory", mean_dev)
+    assert worst < 5e-2, ("worst loss deviation over the trajectory", worst)
+    assert traj[-1][0] < 0.05 * traj[0][0], "the loss did not go down"
 
 
 def test_inference_sweep_matches_oracle_argmax(pkg):
@@ -309,45 +347,10 @@ def test_inference_sweep_matches_oracle_argmax(pkg):
             assert mask.float().mean() > 0.7
 
 
-def test_cuda_graph_replay_equals_eager_step(pkg):
-    """The captured iteration (forward, double backward, both optimizer steps, LR tick) replayed from a given
-    state gives the same losses and weights as the eager iteration from that state.  (One step only: the
-    free-running GAN is chaotic, atomics alone make two eager runs drift apart after a few steps.)"""
-    size, bs = 128, 2
-    x1, y = O.synthetic_batch(bs, size, 11)
-    x2, _ = O.synthetic_batch(bs, size, 12)
-    mod1, mod2 = torch.full((bs,), 0), torch.full((bs,), 2)
-    lam = torch.full((1,), 0.5, device=DEV)
-    tr, G, D = _trainer(size)
-    gen = torch.Generator(device=DEV).manual_seed(5)
-    batch = tr.prepare_batch(x1, y, mod1, x2, mod2, 1)
-    hw = (size // 16) ** 2
-    a0, i0 = torch.randn(2 * bs, device=DEV, generator=gen), torch.randperm(hw, device=DEV, generator=gen)[:64]
-    a1, i1 = torch.randn(2 * bs, device=DEV, generator=gen), torch.randperm(hw, device=DEV, generator=gen)[:64]
-
-    def reset():
-        tr.net.load_state_dict(G)
-        tr.D.load_state_dict(D)
-        for t in (tr.optimizer.mom, tr.d_optimizer.m, tr.d_optimizer.v, tr.d_optimizer.state, tr.lr_sched.iter_state):
-            t.zero_()
-        tr.optimizer.lr_dev.fill_(1e-2)
-
-    step = tr.graphed_step([*batch, a0, i0, lam], use_semi=True)      # 3 warm-up iterations, then capture
-    assert step.launches_per_replay > 500
-    reset()
-    lg = step(*batch, a1, i1, lam).clone()
-    dg = tr.d_optimizer.grad.clone()
-    reset()
-    le = tr.train_step(*batch, a1, [i1], lam, True).clone()
-    de = tr.d_optimizer.grad.clone()
-    reset()
-    le2 = tr.train_step(*batch, a1, [i1], lam, True).clone()      # eager twice: the run-to-run spread of fp32 atomics
-    spread = rel(le2, le)
-    report("graph_vs_eager", dict(eager=le.tolist(), eager_again=le2.tolist(), graph=lg.tolist(),
-                                  d_grad_rel=rel(dg, de), eager_vs_eager=spread))
-    # same kernels, same inputs: only the order of fp32 atomics differs, but D_gp ~ 5e3 and D's Adam step
-    # (lr * sign(g) on near-zero gradients) amplify that; the graph must sit within the eager-vs-eager spread
-    assert rel(lg, le) < max(5 * spread, 3e-2), (lg.tolist(), le.tolist(), spread)
+# test_cuda_graph_replay_equals_eager_step moved to tests/test_parity_layers_gpu.py
+# (test_deterministic_mode_graph_equals_eager_bitwise): with order-independent accumulation the captured graph's replay,
+# two eager runs and the stream-free schedule are compared BITWISE per loss, per gradient and per weight, instead of by
+# the norm of a loss vector that D_gp dominates.
 
 
 def test_validate_epoch_dice_from_confusion_counts(pkg):

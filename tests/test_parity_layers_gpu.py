@@ -43,7 +43,12 @@ def to_dev(sd):
 #    4.5e-2 on the whole tensor; the image channel's slice of the same tensor is at 3e-3.
 #  * netF: PatchSampleF is ONE fused Function of five reference ops (gather, Linear, ReLU, Linear, L2 normalise:
 #    network/ugan.py:316-334) whose backward hands bf16 cotangents from stage to stage; its d/dx is measured 2.6e-2.
-LOOSER = {("tsl_encoder.pre", "tsl_encoder.pre.0.weight"): 6e-2, ("netF", "dx"): 3.5e-2}
+#    The same planes put a large per-(sample, channel) constant under the image-dependent part of the stem's conv
+#    output; the bf16 rounding of that stored tensor scales with the constant, InstanceNorm then removes the constant
+#    but not the rounding: this stem's forward error is 8.6e-3 where every other layer has 4e-3, and the gradient of
+#    its norm's gamma is measured 2.5e-2.
+LOOSER = {("tsl_encoder.pre", "tsl_encoder.pre.0.weight"): 6e-2, ("tsl_encoder.pre", "tsl_encoder.pre.1.weight"): 3.5e-2,
+          ("netF", "dx"): 3.5e-2}
 
 
 def _assert_layers(res, name):
