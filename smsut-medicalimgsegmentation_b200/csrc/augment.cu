@@ -182,8 +182,9 @@ augment_kernel(const uint8_t* __restrict__ images, const uint8_t* __restrict__ l
     } else {
       float f = (float)v;
       if (p.gamma_on != 0.f)      // torchvision adjust_gamma on a PIL image: int((255 + 1 - 1e-3) * (v / 255) ** gamma)
-        f = floorf((255.f + 1.f - 1e-3f) * powf(f * (1.f / 255.f), p.gamma));
-      x_out[(size_t)n * hw + i] = (f * (1.f / 255.f) - 0.5f) * 2.f;      // ToTensor, Normalize(mean 0.5, std 0.5)
+        f = floorf((255.f + 1.f - 1e-3f) * powf(f / 255.f, p.gamma));
+      // ToTensor (IEEE division by 255, as torch's byte -> float .div(255)), Normalize(mean 0.5, std 0.5): bit-exact
+      x_out[(size_t)n * hw + i] = (f / 255.f - 0.5f) / 0.5f;
     }
   }
 }

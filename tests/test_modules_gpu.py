@@ -192,18 +192,20 @@ def test_ugannce_parity(pkg):
     rseg, rtsl, rfeats, _ = O.ugannce_forward(leaf, x, m, sample_ids=ids, style=st)
     r = dict(seg=rel(seg, rseg), tsl=rel(tsl, rtsl), feat=rel(feats[0], rfeats[0]))
     # The translation head is tanh(1x1 conv) with ONE output channel: at kaiming scale its pre-activation has a
-    # standard deviation of ~5, a third of the outputs sit in saturation and the rest follow the pre-activation's
-    # ABSOLUTE error (tanh is 1-Lipschitz), so the output's relative error (0.17) says little.  What the kernels owe
-    # is (a) the pre-activation within the accumulated bf16 tolerance and (b) |tanh(a) - tanh(b)| <= |a - b|.
+    # standard deviation of ~5 and is a sum of 16 cancelling terms (relative error 0.11 for an input error of 0.027), a
+    # third of the outputs sit in saturation and the rest follow the pre-activation's ABSOLUTE error (tanh is
+    # 1-Lipschitz), so the output's relative error (0.17) says little.  What the kernels owe is (a) the head's input
+    # within the accumulated bf16 tolerance, (b) the fused head exact on that input, (c) |tanh(a) - tanh(b)| <= |a - b|.
     d1 = [t for mod, t in taps if mod is net.tsl_decoder.dec1.bn2][0]              # the head's input (NHWC bf16)
     w, b = sd["tsl_decoder.fc.weight"], sd["tsl_decoder.fc.bias"]
     z = torch.nn.functional.conv2d(d1.permute(0, 3, 1, 2).float(), w, b)
     rz = torch.nn.functional.conv2d(st.taps["tsl_decoder.fc.in"].detach(), w, b)
-    r["tsl_preactivation"] = rel(z, rz)
+    r["tsl_head_input"] = rel(d1.permute(0, 3, 1, 2), st.taps["tsl_decoder.fc.in"])
+    r["tsl_preactivation"] = rel(z, rz)         # 16 -> 1 projection with cancelling terms: ~4x the input's error
     r["tsl_saturated_frac"] = (rtsl.abs() > 0.99).float().mean().item()
     assert rel(tsl, torch.tanh(z)) < 1e-5                       # the fused head kernel on its own input: exact
     assert ((tsl.float() - rtsl).abs() <= (z - rz).abs() + 1e-6).all()
-    assert r["tsl_preactivation"] < 4e-2, r
+    assert r["tsl_head_input"] < 3e-2, r         # what reaches the head after 27 bf16-stored layers
     w = torch.randn_like(rseg)
     (seg * w).mean().add(tsl.mean()).add((feats[0] ** 3).sum()).backward()
     (rseg * w).mean().add(rtsl.mean()).add((rfeats[0] ** 3).sum()).backward()
@@ -326,9 +328,11 @@ def test_unet_free_running_loss_trajectory(pkg, size):
     # steps stay within 0.5 %; over all 200 steps the loss falls 160x (3.09 -> 0.019) and the two free-running
     # optimisations drift apart to a mean of 1.5 % / a worst step of 3.3 % at 256x256 -- the 1 % holds for the part of
     # the trajectory where the loss is not yet dominated by its last digits, not for the tail.
-    assert early < 1e-2, ("worst loss deviation over the first 40 steps", early)
-    assert mean_dev < 2.5e-2, ("mean loss deviation over the trajectory", mean_dev)
-    assert worst < 5e-2, ("worst loss deviation over the trajectory", worst)
+    # 128x128 (measured: mean 0.20 %, worst 0.91 %, first 40 steps 0.20 %) meets the 1 % of the north star outright.
+    b_mean, b_worst, b_early = (5e-3, 1.5e-2, 5e-3) if size == 128 else (2.5e-2, 5e-2, 1e-2)
+    assert early < b_early, ("worst loss deviation over the first 40 steps", early)
+    assert mean_dev < b_mean, ("mean loss deviation over the trajectory", mean_dev)
+    assert worst < b_worst, ("worst loss deviation over the trajectory", worst)
     assert traj[-1][0] < 0.05 * traj[0][0], "the loss did not go down"
 
 
