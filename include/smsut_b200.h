@@ -149,6 +149,15 @@ int smsut_in_bwd_apply(const void* dout, const void* out, const void* xa, const 
                        const float* stats_b, const float* gamma_b, const float* beta_b, void* dxb, float* dgamma_b,
                        float* dbeta_b, void* dres, const float* red, int32_t n, int32_t hw, int32_t c,
                        int32_t c_params, int32_t act, float slope, smsut_stream_t stream);
+/* both passes in ONE launch (reduce, a barrier over the CTAs of a sample, apply; the second pass re-reads its strip from
+ * L2): same arguments as the pair above plus `counters`, n zeroed 32-bit words.  Falls back to the two kernels when
+ * the grid cannot be co-resident (more samples than resident CTAs) or SMSUT_IN_FUSED=0.  red[n][3][c] zeroed by the
+ * caller as for smsut_in_bwd_reduce. */
+int smsut_in_bwd_fused(const void* dout, const void* out, const void* xa, const float* stats_a, const float* gamma_a,
+                       const float* beta_a, void* dxa, float* dgamma_a, float* dbeta_a, const void* xb,
+                       const float* stats_b, const float* gamma_b, const float* beta_b, void* dxb, float* dgamma_b,
+                       float* dbeta_b, void* dres, float* red, void* counters, int32_t n, int32_t hw, int32_t c,
+                       int32_t c_params, int32_t act, float slope, smsut_stream_t stream);
 /* double backward of InstanceNorm (WGAN-GP, trainer/uganShp0Trainer.py:127-134):
  * given u = cotangent of dx, with dx = IN_bwd(dy; x, gamma):
  *   pass 1: red2[n][c] = {sum u, sum dy, sum u*xhat, sum dy*xhat, sum u*dy}

@@ -76,6 +76,8 @@ _PROTOS = {
     "smsut_in_bwd_reduce": [P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_float, P],
     "smsut_in_bwd_apply": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
                            c_float, P],
+    "smsut_in_bwd_fused": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
+                           c_float, P],
     "smsut_in_bwd2_reduce": [P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_in_bwd2_apply": [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_bn_pool": [P, P, c_int, c_int, c_int, P],

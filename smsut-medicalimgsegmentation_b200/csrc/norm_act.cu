@@ -78,14 +78,14 @@ struct Strip32 {
   int p0, count;            // first pixel of the block's strip, number of pixels this THREAD visits
 };
 
-__device__ __forceinline__ Strip32 make_strip32(int c, int hw, int splits) {
+__device__ __forceinline__ Strip32 make_strip32(int c, int hw, int splits, int split_idx) {
   Strip32 s;
   s.cg = c >> 3;
   s.g = threadIdx.x % s.cg;
   s.lane0 = threadIdx.x / s.cg;
   s.nl = kNT / s.cg;
   const int per = (hw + splits - 1) / splits;
-  s.p0 = blockIdx.y * per;
+  s.p0 = split_idx * per;
   int p1 = s.p0 + per;
   if (p1 > hw) p1 = hw;
   const int span = p1 - s.p0 - s.lane0;
@@ -215,7 +215,7 @@ in_apply_kernel(const void* __restrict__ xa, const float* __restrict__ stats_a, 
     }
   }
   // 32-bit strip walk (see Strip32): full steps of U pixels without bounds checks, then a tail
-  const Strip32 t = make_strip32(c, hw, splits);
+  const Strip32 t = make_strip32(c, hw, splits, blockIdx.y);
   const uint4* pa = reinterpret_cast<const uint4*>(xa);
   const uint4* pb = reinterpret_cast<const uint4*>(xb);
   const uint4* pr = reinterpret_cast<const uint4*>(res);
@@ -309,18 +309,17 @@ __device__ __forceinline__ void load_g_recomputed(const uint4& qd, const float* 
 
 // RECOMP: `out` is not read; the activation's sign comes from the pre-activation recomputed from xa / xb (possible
 // whenever the forward had no residual input), which removes one of the 3 (4) streamed tensors.
+// `n` = sample, `split` = which strip of the sample this CTA streams (the stand-alone kernel takes them from
+// blockIdx.x / .y, the fused kernel below from blockIdx.y / .x)
 template <bool HAS_B, bool HAS_ACT, bool RECOMP, int MINB>
-__global__ void __launch_bounds__(kNT, MINB)
-in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
-                     const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
-                     const float* __restrict__ beta_a, const uint4* __restrict__ xb,
-                     const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
-                     const float* __restrict__ beta_b, float* __restrict__ red, long long* red_q, int hw, int c, int cp,
-                     int splits, float neg) {
-  pdl_prologue();
-  extern __shared__ float sh[];
-  const Strip32 s = make_strip32(c, hw, splits);
-  const int n = blockIdx.x;
+__device__ __forceinline__ void
+in_bwd_reduce_body(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
+                   const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                   const float* __restrict__ beta_a, const uint4* __restrict__ xb,
+                   const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
+                   const float* __restrict__ beta_b, float* __restrict__ red, long long* red_q, int hw, int c, int cp,
+                   int splits, float neg, int n, int split, float* sh) {
+  const Strip32 s = make_strip32(c, hw, splits, split);
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
   // !RECOMP: ma / mb = the means (centred accumulation).  RECOMP: ma = sa, mb = sb, ta = the folded affine form of
@@ -420,26 +419,54 @@ in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ o
   block_reduce_add32<3>(acc, sh, s, red + (size_t)n * 3 * c, red_q ? red_q + (size_t)n * 3 * c : nullptr, c, c);
 }
 
+template <bool HAS_B, bool HAS_ACT, bool RECOMP, int MINB>
+__global__ void __launch_bounds__(kNT, MINB)
+in_bwd_reduce_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
+                     const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                     const float* __restrict__ beta_a, const uint4* __restrict__ xb,
+                     const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
+                     const float* __restrict__ beta_b, float* __restrict__ red, long long* red_q, int hw, int c, int cp,
+                     int splits, float neg) {
+  pdl_prologue();
+  extern __shared__ float sh[];
+  in_bwd_reduce_body<HAS_B, HAS_ACT, RECOMP, MINB>(dout, out, xa, stats_a, gamma_a, beta_a, xb, stats_b, gamma_b, beta_b,
+                                                   red, red_q, hw, c, cp, splits, neg, blockIdx.x, blockIdx.y, sh);
+}
+
 // pass 2: dx = A*g + B*x + C per channel with A = gamma*rstd, B = -A*rstd*mean(g xhat), C = -A*mean(g) - B*mean
 // RECOMP as in the reduce kernel: A = gamma * rstd is the forward's scale, so only the folded shift `ta` is extra.
-template <bool HAS_B, bool HAS_RES, bool HAS_ACT, bool RECOMP, int MINB>
-__global__ void __launch_bounds__(kNT, MINB)
-in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
-                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
-                    const float* __restrict__ beta_a, uint4* __restrict__ dxa,
-                    float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const uint4* __restrict__ xb,
-                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
-                    const float* __restrict__ beta_b, uint4* __restrict__ dxb,
-                    float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, uint4* __restrict__ dres,
-                    const float* __restrict__ red, long long* dga_q, long long* dba_q, long long* dgb_q,
-                    long long* dbb_q, int hw, int c, int cp, int splits, float neg) {
-  pdl_prologue();
-  const Strip32 s = make_strip32(c, hw, splits);
-  const int n = blockIdx.x;
+// FRESH: `red` was accumulated by other CTAs of THIS launch (fused kernel): read it past L1 (ld.global.cg), or from
+// the fixed-point shadow `red_q` in deterministic mode (the fp32 copy is only written by smsut_det_resolve)
+template <bool HAS_B, bool HAS_RES, bool HAS_ACT, bool RECOMP, int MINB, bool FRESH>
+__device__ __forceinline__ void
+in_bwd_apply_body(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
+                  const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                  const float* __restrict__ beta_a, uint4* __restrict__ dxa,
+                  float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const uint4* __restrict__ xb,
+                  const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
+                  const float* __restrict__ beta_b, uint4* __restrict__ dxb,
+                  float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, uint4* __restrict__ dres,
+                  const float* red, const long long* red_q, long long* dga_q, long long* dba_q, long long* dgb_q,
+                  long long* dbb_q, int hw, int c, int cp, int splits, float neg, int n, int split) {
+  const Strip32 s = make_strip32(c, hw, splits, split);
   const int ch0 = s.g * 8;
   const float inv_hw = 1.f / (float)hw;
   float Aa[8], Ba[8], Ca[8], Ab[8], Bb[8], Cb[8], ta[8];
-  const float* r0 = red + (size_t)n * 3 * c + ch0;
+  float r0[3 * 8];      // {sum g, sum g xhat_a, sum g xhat_b} of this thread's 8 channels
+  {
+    const size_t base = (size_t)n * 3 * c + ch0;
+#pragma unroll
+    for (int v = 0; v < (HAS_B ? 3 : 2); ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (FRESH && red_q != nullptr)
+          r0[v * 8 + j] = (float)((double)__ldcg(red_q + base + (size_t)v * c + j) * (1.0 / 4294967296.0));
+        else if (FRESH)
+          r0[v * 8 + j] = __ldcg(red + base + (size_t)v * c + j);
+        else
+          r0[v * 8 + j] = red[base + (size_t)v * c + j];
+      }
+  }
   {
     float m[8], r[8];
     load_mean_rstd(stats_a, n, c, ch0, inv_hw, m, r);
@@ -447,7 +474,7 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
     for (int j = 0; j < 8; ++j) {
       const bool ok = ch0 + j < cp;
       const float A = (ok ? gamma_a[ch0 + j] : 0.f) * r[j];
-      const float B = -A * r[j] * (r0[c + j] * inv_hw);
+      const float B = -A * r[j] * (r0[8 + j] * inv_hw);
       Aa[j] = A; Ba[j] = B; Ca[j] = -A * (r0[j] * inv_hw) - B * m[j];
       if (RECOMP) ta[j] = in_shift(ok ? beta_a[ch0 + j] : 0.f, m[j], A);
     }
@@ -457,21 +484,21 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
       for (int j = 0; j < 8; ++j) {
         const bool ok = ch0 + j < cp;
         const float A = (ok ? gamma_b[ch0 + j] : 0.f) * r[j];
-        const float B = -A * r[j] * (r0[2 * c + j] * inv_hw);
+        const float B = -A * r[j] * (r0[16 + j] * inv_hw);
         Ab[j] = A; Bb[j] = B; Cb[j] = -A * (r0[j] * inv_hw) - B * m[j];
         if (RECOMP) ta[j] += in_shift(ok ? beta_b[ch0 + j] : 0.f, m[j], A);
       }
     }
   }
   // parameter gradients: one block per sample adds its (n, c) sums
-  if (blockIdx.y == 0 && s.lane0 == 0) {
+  if (split == 0 && s.lane0 == 0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       if (ch0 + j >= cp) continue;
-      if (dgamma_a) acc_add_at(dgamma_a, dga_q, ch0 + j, r0[c + j]);
+      if (dgamma_a) acc_add_at(dgamma_a, dga_q, ch0 + j, r0[8 + j]);
       if (dbeta_a) acc_add_at(dbeta_a, dba_q, ch0 + j, r0[j]);
       if (HAS_B) {
-        if (dgamma_b) acc_add_at(dgamma_b, dgb_q, ch0 + j, r0[2 * c + j]);
+        if (dgamma_b) acc_add_at(dgamma_b, dgb_q, ch0 + j, r0[16 + j]);
         if (dbeta_b) acc_add_at(dbeta_b, dbb_q, ch0 + j, r0[j]);
       }
     }
@@ -516,6 +543,68 @@ in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ ou
     if (HAS_B) qb = xb[idx];
     body(qd, qo, qa, qb, idx);
   }
+}
+
+template <bool HAS_B, bool HAS_RES, bool HAS_ACT, bool RECOMP, int MINB>
+__global__ void __launch_bounds__(kNT, MINB)
+in_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
+                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                    const float* __restrict__ beta_a, uint4* __restrict__ dxa,
+                    float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const uint4* __restrict__ xb,
+                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
+                    const float* __restrict__ beta_b, uint4* __restrict__ dxb,
+                    float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, uint4* __restrict__ dres,
+                    const float* __restrict__ red, long long* dga_q, long long* dba_q, long long* dgb_q,
+                    long long* dbb_q, int hw, int c, int cp, int splits, float neg) {
+  pdl_prologue();
+  in_bwd_apply_body<HAS_B, HAS_RES, HAS_ACT, RECOMP, MINB, false>(
+      dout, out, xa, stats_a, gamma_a, beta_a, dxa, dgamma_a, dbeta_a, xb, stats_b, gamma_b, beta_b, dxb, dgamma_b, dbeta_b,
+      dres, red, nullptr, dga_q, dba_q, dgb_q, dbb_q, hw, c, cp, splits, neg, blockIdx.x, blockIdx.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused backward: ONE launch instead of the reduce / apply pair.  grid = (splits, n): the CTAs of a sample are adjacent
+// in launch order.  Each CTA streams its strip once for the reductions (pass 1), the CTAs of the sample meet at a
+// counter barrier, then each CTA streams the SAME strip again for dx (pass 2) -- the strip is 50-200 KB per tensor and
+// was read microseconds earlier, so pass 2 is served from L2 instead of HBM.  The launcher keeps the whole grid
+// co-resident (<= occupancy x SMs), which is what makes the spin barrier safe; other streams' kernels only delay it.
+// Not for BatchNorm: its reductions are pooled over the samples between the passes (two-kernel path).
+// ---------------------------------------------------------------------------------------------
+template <bool HAS_B, bool HAS_RES, bool HAS_ACT, bool RECOMP, int MINB>
+__global__ void __launch_bounds__(kNT, MINB)
+in_bwd_fused_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ out, const uint4* __restrict__ xa,
+                    const float* __restrict__ stats_a, const float* __restrict__ gamma_a,
+                    const float* __restrict__ beta_a, uint4* __restrict__ dxa,
+                    float* __restrict__ dgamma_a, float* __restrict__ dbeta_a, const uint4* __restrict__ xb,
+                    const float* __restrict__ stats_b, const float* __restrict__ gamma_b,
+                    const float* __restrict__ beta_b, uint4* __restrict__ dxb,
+                    float* __restrict__ dgamma_b, float* __restrict__ dbeta_b, uint4* __restrict__ dres,
+                    float* red, long long* red_q, unsigned int* counters, long long* dga_q, long long* dba_q,
+                    long long* dgb_q, long long* dbb_q, int hw, int c, int cp, int splits, float neg) {
+  pdl_prologue();
+  extern __shared__ float sh[];
+  const int n = blockIdx.y, split = blockIdx.x;
+  in_bwd_reduce_body<HAS_B, HAS_ACT, RECOMP, MINB>(dout, out, xa, stats_a, gamma_a, beta_a, xb, stats_b, gamma_b, beta_b,
+                                                   red, red_q, hw, c, cp, splits, neg, n, split, sh);
+  // barrier over the `splits` CTAs of sample n: the sums are complete once every CTA has added its share
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counters + n, 1u);
+    unsigned int spins = 0;
+    while (atomicAdd(counters + n, 0u) < (unsigned int)splits) {
+      __nanosleep(40);
+      if (++spins > (1u << 26)) {
+        printf("smsut: in_bwd_fused barrier timed out (sample %d split %d of %d)\n", n, split, splits);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  in_bwd_apply_body<HAS_B, HAS_RES, HAS_ACT, RECOMP, MINB, true>(
+      dout, out, xa, stats_a, gamma_a, beta_a, dxa, dgamma_a, dbeta_a, xb, stats_b, gamma_b, beta_b, dxb, dgamma_b, dbeta_b,
+      dres, red, red_q, dga_q, dba_q, dgb_q, dbb_q, hw, c, cp, splits, neg, n, split);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -817,6 +906,79 @@ extern "C" int smsut_in_bwd_apply(const void* dout, const void* out, const void*
 #undef IN_BWD_APPLY
   count_launch();
   return launch_status("in_bwd_apply_kernel");
+}
+
+// InstanceNorm backward in ONE call: the fused kernel when the whole grid can be co-resident (see
+// in_bwd_fused_kernel), else the reduce / apply pair.  `counters`: n zeroed 32-bit words (the per-sample barrier).
+extern "C" int smsut_in_bwd_fused(const void* dout, const void* out, const void* xa, const float* stats_a,
+                                  const float* gamma_a, const float* beta_a, void* dxa, float* dgamma_a,
+                                  float* dbeta_a, const void* xb, const float* stats_b, const float* gamma_b,
+                                  const float* beta_b, void* dxb, float* dgamma_b, float* dbeta_b, void* dres,
+                                  float* red, void* counters, int32_t n, int32_t hw, int32_t c, int32_t cp, int32_t act,
+                                  float slope, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  SMSUT_CHECK(act == SMSUT_ACT_NONE || act == SMSUT_ACT_LRELU || act == SMSUT_ACT_RELU, -1, "in_bwd: unsupported activation");
+  SMSUT_CHECK(red != nullptr && counters != nullptr, -1, "in_bwd_fused: red / counters missing");
+  const bool recomp = act != SMSUT_ACT_NONE && out == nullptr;
+  SMSUT_CHECK(!recomp || (gamma_a && beta_a && (xb == nullptr || (gamma_b && beta_b))), -1,
+              "in_bwd_fused: out == NULL needs gamma / beta of every branch");
+  static int knob = -1;
+  if (knob < 0) {
+    const char* e = getenv("SMSUT_IN_FUSED");
+    knob = e ? atoi(e) : 1;
+  }
+  const float neg = act == SMSUT_ACT_LRELU ? slope : 0.f;
+  const size_t shm = red_smem(3, c);
+  long long* red_q = det_shadow(red);
+  const bool two = recomp && xb != nullptr && recomp_two_blocks();      // the 2-resident register budget (see above)
+  int launched = 0;
+#define IN_FUSED(HB, HR, HA, RC, MB)                                                                                  \
+  do {                                                                                                                \
+    static int per_sm = -1;                                                                                           \
+    if (per_sm < 0) {                                                                                                 \
+      int nb = 0;                                                                                                     \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, in_bwd_fused_kernel<HB, HR, HA, RC, MB>, kNT, 24 * 1024) != \
+          cudaSuccess)                                                                                                \
+        nb = 0;                                                                                                       \
+      per_sm = nb;                                                                                                    \
+    }                                                                                                                 \
+    const long long cap = (long long)per_sm * device_sm_count();                                                      \
+    if (knob && shm <= 24 * 1024 && cap >= n) {                                                                       \
+      int splits = pick_splits(n, hw, c, MB == 2 ? 4 : 8);                                                            \
+      if ((long long)splits * n > cap) splits = (int)(cap / n);                                                       \
+      launch_pdl(in_bwd_fused_kernel<HB, HR, HA, RC, MB>, dim3(splits, n), kNT, shm, (cudaStream_t)st,                \
+                 (const uint4*)dout, (const uint4*)out, (const uint4*)xa, stats_a, gamma_a, beta_a, (uint4*)dxa,      \
+                 dgamma_a, dbeta_a, (const uint4*)xb, stats_b, gamma_b, beta_b, (uint4*)dxb, dgamma_b, dbeta_b,       \
+                 (uint4*)dres, red, red_q, (unsigned int*)counters, det_shadow(dgamma_a), det_shadow(dbeta_a),        \
+                 det_shadow(dgamma_b), det_shadow(dbeta_b), hw, c, cp, splits, neg);                                  \
+      launched = 1;                                                                                                   \
+    }                                                                                                                 \
+  } while (0)
+#define IN_FUSED_A(HB, HR)                                                                  \
+  do {                                                                                      \
+    if (recomp) { if (two) IN_FUSED(HB, HR, true, true, 2); else IN_FUSED(HB, HR, true, true, 3); } \
+    else if (act != SMSUT_ACT_NONE) IN_FUSED(HB, HR, true, false, 3);                       \
+    else IN_FUSED(HB, HR, false, false, 3);                                                 \
+  } while (0)
+  if (xb != nullptr) { if (dres != nullptr) IN_FUSED_A(true, true); else IN_FUSED_A(true, false); }
+  else { if (dres != nullptr) IN_FUSED_A(false, true); else IN_FUSED_A(false, false); }
+#undef IN_FUSED_A
+#undef IN_FUSED
+  if (launched) {
+    count_launch();
+    return launch_status("in_bwd_fused_kernel");
+  }
+  // not co-residable (more samples than resident blocks) or switched off: the two-kernel path
+  rc = smsut_in_bwd_reduce(dout, out, xa, stats_a, gamma_a, beta_a, xb, stats_b, gamma_b, beta_b, red, n, hw, c, cp, act,
+                           slope, st);
+  if (rc) return rc;
+  if (red_q != nullptr) {
+    rc = smsut_det_resolve(red, (int64_t)n * 3 * c, st);
+    if (rc) return rc;
+  }
+  return smsut_in_bwd_apply(dout, out, xa, stats_a, gamma_a, beta_a, dxa, dgamma_a, dbeta_a, xb, stats_b, gamma_b, beta_b,
+                            dxb, dgamma_b, dbeta_b, dres, red, n, hw, c, cp, act, slope, st);
 }
 
 extern "C" int smsut_in_bwd2_reduce(const void* u, const void* dy, const void* x, const float* stats, float* red2,

@@ -743,11 +743,6 @@ def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act
         ba, bb = betas
         out = None
     red = zeros((n, 3, c), dev)
-    call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(xb), _p(sb), _p(gb), _p(bb),
-         _p(red), n, h * w, c, cp, act, slope, _stream())
-    resolve(red)
-    if batch:
-        call("smsut_bn_pool", _p(red), _p(red), n, 3, c, _stream())
     dxa = torch.empty_like(xa)
     dxb = torch.empty_like(xa) if xb is not None else None
     dres = torch.empty_like(xa) if want_res else None
@@ -759,8 +754,21 @@ def in_bwd(dout, out, xa, sa, ga, xb=None, sb=None, gb=None, want_res=False, act
         pg = zeros((4, cp), dev)
         t = [pg[0], pg[1], pg[2] if xb is not None else None, pg[3] if xb is not None else None]
         ret = t
-    call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(dxa), _p(t[0]), _p(t[1]), _p(xb),
-         _p(sb), _p(gb), _p(bb), _p(dxb), _p(t[2]), _p(t[3]), _p(dres), _p(red), n, h * w, c, cp, act, slope, _stream())
+    if not batch:
+        # InstanceNorm: both passes in one launch (the second one re-reads its strip from L2)
+        counters = zeros(n, dev)
+        call("smsut_in_bwd_fused", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(dxa), _p(t[0]), _p(t[1]), _p(xb),
+             _p(sb), _p(gb), _p(bb), _p(dxb), _p(t[2]), _p(t[3]), _p(dres), _p(red), _p(counters), n, h * w, c, cp, act,
+             slope, _stream())
+    else:
+        # BatchNorm: the reductions are pooled over the samples between the two passes
+        call("smsut_in_bwd_reduce", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(xb), _p(sb), _p(gb), _p(bb),
+             _p(red), n, h * w, c, cp, act, slope, _stream())
+        resolve(red)
+        call("smsut_bn_pool", _p(red), _p(red), n, 3, c, _stream())
+        call("smsut_in_bwd_apply", _p(dout), _p(out), _p(xa), _p(sa), _p(ga), _p(ba), _p(dxa), _p(t[0]), _p(t[1]), _p(xb),
+             _p(sb), _p(gb), _p(bb), _p(dxb), _p(t[2]), _p(t[3]), _p(dres), _p(red), n, h * w, c, cp, act, slope,
+             _stream())
     if pg is not None:
         resolve(pg)
     return dxa, ret[0], ret[1], dxb, ret[2], ret[3], dres
