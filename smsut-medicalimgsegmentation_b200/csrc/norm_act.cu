@@ -944,7 +944,9 @@ extern "C" int smsut_in_bwd_fused(const void* dout, const void* out, const void*
       per_sm = nb;                                                                                                    \
     }                                                                                                                 \
     const long long cap = (long long)per_sm * device_sm_count();                                                      \
-    if (knob && shm <= 24 * 1024 && cap >= n) {                                                                       \
+    const long long sample_bytes = (long long)hw * c * 2;                                                            \
+    const bool pick = knob == 1 || (knob == 2 && sample_bytes <= 256 * 1024) || (knob == 3 && sample_bytes > 256 * 1024); \
+    if (pick && shm <= 24 * 1024 && cap >= n) {                                                                       \
       int splits = pick_splits(n, hw, c, MB == 2 ? 4 : 8);                                                            \
       if ((long long)splits * n > cap) splits = (int)(cap / n);                                                       \
       launch_pdl(in_bwd_fused_kernel<HB, HR, HA, RC, MB>, dim3(splits, n), kNT, shm, (cudaStream_t)st,                \
