@@ -636,6 +636,7 @@ class PatchSampleFn(Function):
         y = ops.conv_fprop([h], pw2, bias=b2, out_f32=True)    # fp32
         q, norm = ops.l2norm_fwd(y.view(r, -1))
         ctx.pw = (pw1, pw2)
+        ctx.biases = (b1, b2)
         ctx.fshape = tuple(feat.shape)
         ctx.save_for_backward(ids, x4, h, q, norm, w1, w2)
         return q
@@ -646,18 +647,24 @@ class PatchSampleFn(Function):
         pw1, pw2 = ctx.pw
         r = q.shape[0]
         dy = ops.l2norm_bwd(_c(dq), q, norm).view(1, x4.shape[1], x4.shape[2], -1)      # bf16
-        dw2 = ops.conv_wgrad([h], dy, pw2)
-        db2 = ops.colsum(dy.view(r, -1))
+        # parameter gradients go straight into the flat .grad views inside accumulate_param_grads (autograd gets None):
+        # an AccumulateGrad node runs on the stream its parameter was FIRST used on -- the main stream, for netF -- and
+        # would make that stream wait for this backward (it held the whole discriminator phase back by 1.7 ms)
+        b1, b2 = ctx.biases
+        tw1, tb1, tw2, tb2 = _target(w1), _target(b1), _target(w2), _target(b2)
+        dw2 = ops.conv_wgrad([h], dy, pw2, out=tw2.view(pw2.weight.shape) if tw2 is not None else None)
+        db2 = ops.colsum(dy.view(r, -1), out=tb2)
         dh = ops.conv_dgrad(dy, pw2)[0]
         dh = ops.act_bwd(dh, h, act=ACT_RELU)
-        dw1 = ops.conv_wgrad([x4], dh, pw1)
-        db1 = ops.colsum(dh.view(r, -1))
+        dw1 = ops.conv_wgrad([x4], dh, pw1, out=tw1.view(pw1.weight.shape) if tw1 is not None else None)
+        db1 = ops.colsum(dh.view(r, -1), out=tb1)
         dfeat = None
         if ctx.needs_input_grad[0]:
             drows = ops.conv_dgrad(dh, pw1)[0].view(r, -1)
             dfeat = torch.zeros(ctx.fshape, dtype=BF16, device=dq.device)
             ops.scatter_rows_add(drows, ids, dfeat)
-        return dfeat, None, None, dw1.view_as(w1), db1, None, dw2.view_as(w2), db2
+        return (dfeat, None, None, _ret(dw1.view_as(w1), tw1), _ret(db1, tb1), None, _ret(dw2.view_as(w2), tw2),
+                _ret(db2, tb2))
 
 
 class PatchNCEFn(Function):

@@ -6,6 +6,8 @@ the LR tick into ONE graph, so the host cost of an iteration is a handful of asy
 The iteration's inputs (slices, labels, modality vectors, alpha, patch ids, lambda_semi) live in static device
 buffers that are refreshed before each replay.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -30,10 +32,15 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        dot = os.environ.get("SMSUT_GRAPH_DOT")      # development: dump the captured graph (nodes + dependency edges)
+        if dot:
+            self.graph.enable_debug_mode()
         before = _lib.launch_count()
         with torch.cuda.graph(self.graph, stream=s):
             self.static_out = step_fn(*self.static_in)
         self.launches_per_replay = _lib.launch_count() - before
+        if dot:
+            self.graph.debug_dump(dot)
 
     def accepts(self, inputs):
         """True if `inputs` have the shapes / dtypes the graph was captured for (a ragged last batch does not)"""

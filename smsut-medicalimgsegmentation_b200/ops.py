@@ -805,11 +805,14 @@ def add_bf16(a, b):
     return out
 
 
-def colsum(x):
+def colsum(x, out=None):
+    """column sums of a (rows, c) bf16 matrix, accumulated INTO `out` (fp32, e.g. a flat-gradient view) when given"""
     rows, c = x.shape
-    out = zeros(c, x.device)
-    call("smsut_colsum_bf16", _p(_chk(x, BF16, "colsum x")), rows, c, _p(out), _stream())
-    return resolve(out)
+    fresh = out is None
+    if fresh:
+        out = zeros(c, x.device)
+    call("smsut_colsum_bf16", _p(_chk(x, BF16, "colsum x")), rows, c, _p(_chk(out, F32, "colsum out")), _stream())
+    return resolve(out) if fresh else out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -276,8 +276,8 @@ def add_bf16(a, b):
     return (a.float() + b.float()).to(_AD.t)
 
 
-def colsum(x):
-    return x.float().sum(0)
+def colsum(x, out=None):
+    return _acc(out, x.float().sum(0))
 
 
 def maxpool2_fwd(x):
