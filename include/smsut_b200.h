@@ -258,8 +258,10 @@ int smsut_ce_rows_fwd(const float* logits, const int64_t* target, float* out, in
 int smsut_ce_rows_bwd(const float* logits, const int64_t* target, const float* gscale, float scale, float* dlogits,
                       int32_t rows, int32_t c, smsut_stream_t stream);
 /* WGAN-GP: norm[b] = ||g_b||_2 over `per` elements (fp32 g); out[0] += scale*mean((norm-1)^2);
+ * norm2: b zeroed floats of scratch (the squared norms are accumulated by several blocks per sample);
  * backward: u = gscale*scale*2*(norm-1)/(B*norm) * g  (cotangent of g) */
-int smsut_gp_fwd(const float* g, float* norm, float* out, int32_t b, int64_t per, float scale, smsut_stream_t stream);
+int smsut_gp_fwd(const float* g, float* norm, float* norm2, float* out, int32_t b, int64_t per, float scale,
+                 smsut_stream_t stream);
 int smsut_gp_bwd(const float* g, const float* norm, const float* gscale, float scale, float* u, int32_t b, int64_t per,
                  smsut_stream_t stream);
 /* PatchNCE: gather rows of a (n, hw, c) bf16 feature map at `ids` -> (n*nids, c) bf16 and its adjoint */

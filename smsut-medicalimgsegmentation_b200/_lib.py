@@ -112,7 +112,7 @@ _PROTOS = {
     "smsut_lerp_rows_f32": [P, P, P, P, c_int, c_int64, P],
     "smsut_ce_rows_fwd": [P, P, P, c_int, c_int, c_float, P],
     "smsut_ce_rows_bwd": [P, P, P, c_float, P, c_int, c_int, P],
-    "smsut_gp_fwd": [P, P, P, c_int, c_int64, c_float, P],
+    "smsut_gp_fwd": [P, P, P, P, c_int, c_int64, c_float, P],
     "smsut_gp_bwd": [P, P, P, c_float, P, c_int, c_int64, P],
     "smsut_gather_rows": [P, P, P, c_int, c_int, c_int, c_int, P],
     "smsut_scatter_rows_add": [P, P, P, c_int, c_int, c_int, c_int, P],

@@ -386,6 +386,111 @@ head1x1_bwd_kernel(const uint4* __restrict__ x, const float* __restrict__ dy, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The discriminator's stem (network/ugan.py:202: Conv2d(1, 16, 4, stride 2, padding 1) + bias) has its own backward
+// kernels: the generic ones above ran 60-110 us on it (17 MB of traffic), three to eight times per iteration, and the
+// timeline of the captured step showed them ON the critical path of the discriminator phase (the weight gradient
+// held D's Adam step back by 0.8 ms).  x / dx: (N, H, W, 1) fp32; dy: (N, H/2, W/2, 16) bf16.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStemRows = 8;      // output rows per CTA
+
+// dW[co][0][ky][kx] += sum_p dy[p][co] x[2 oy - 1 + ky][2 ox - 1 + kx];  dbias[co] += sum_p dy[p][co]
+// 256 threads = 16 (co) x 16 (tap); one output row at a time is staged in shared memory (dy row as fp32, the four
+// input rows it touches with a zero halo) and every thread walks the row with two conflict-free LDS per FMA.
+__global__ void __launch_bounds__(256) stem4x4_wgrad_kernel(const float* __restrict__ x, const uint4* __restrict__ dy,
+                                                            float* dw, float* dbias, long long* dw_q, long long* db_q,
+                                                            int n_rows_total, int h, int w, int ho, int wo) {
+  pdl_prologue();
+  extern __shared__ float sm[];
+  const int xs = w + 4;                 // row pitch: == 4 (mod 32) for w % 32 == 0 -> the 16 taps hit 16 banks
+  float* x_s = sm;                      // [4][xs], column c holds input column c - 1
+  float* dy_s = sm + 4 * xs;            // [wo][16]
+  const int t = threadIdx.x, co = t >> 4, tap = t & 15, ky = tap >> 2, kx = tap & 3;
+  float acc = 0.f, accb = 0.f;
+  const int row0 = blockIdx.x * kStemRows;
+  for (int r = row0; r < row0 + kStemRows && r < n_rows_total; ++r) {
+    const int n = r / ho, oy = r - n * ho;
+    __syncthreads();
+    for (int i = t; i < 4 * xs; i += 256) {
+      const int rr = i / xs, c = i - rr * xs;
+      const int iy = 2 * oy - 1 + rr, ix = c - 1;
+      x_s[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? x[((size_t)n * h + iy) * w + ix] : 0.f;
+    }
+    const uint4* drow = dy + ((size_t)n * ho + oy) * wo * 2;
+    for (int i = t; i < wo * 2; i += 256) {
+      float v[8];
+      unpack8(drow[i], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dy_s[i * 8 + j] = v[j];
+    }
+    __syncthreads();
+    const float* xr = x_s + ky * xs + kx;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f;
+    int ox = 0;
+    for (; ox + 1 < wo; ox += 2) {
+      const float d0 = dy_s[ox * 16 + co], d1 = dy_s[ox * 16 + 16 + co];
+      a0 = fmaf(d0, xr[2 * ox], a0);
+      a1 = fmaf(d1, xr[2 * ox + 2], a1);
+      b0 += d0 + d1;
+    }
+    for (; ox < wo; ++ox) {
+      const float d0 = dy_s[ox * 16 + co];
+      a0 = fmaf(d0, xr[2 * ox], a0);
+      b0 += d0;
+    }
+    acc += a0 + a1;
+    accb += b0;
+  }
+  acc_add_at(dw, dw_q, (size_t)co * 16 + tap, acc);
+  if (dbias != nullptr && tap == 0) acc_add_at(dbias, db_q, (size_t)co, accb);
+}
+
+// dx[n][iy][ix] = sum_{co, ky, kx} dy[n][(iy + 1 - ky) / 2][(ix + 1 - kx) / 2][co] w[co][ky][kx]  (valid, even terms):
+// one thread per input pixel, 2 x 2 output pixels x 16 channels = 64 FMAs; weights in shared memory.
+__global__ void __launch_bounds__(256) stem4x4_dgrad_kernel(const uint4* __restrict__ dy, const float* __restrict__ wt,
+                                                            float* __restrict__ dx, long long npix, int h, int w, int ho,
+                                                            int wo) {
+  pdl_prologue();
+  __shared__ float w_s[16 * 16];        // [ky*4 + kx][co]
+  for (int i = threadIdx.x; i < 256; i += 256) {
+    const int co = i >> 4, tap = i & 15;
+    w_s[tap * 16 + co] = wt[i];
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= npix) return;
+  const int ix = (int)(pix % w);
+  const long long t = pix / w;
+  const int iy = (int)(t % h), n = (int)(t / h);
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int ky = ((iy + 1) & 1) + 2 * a;
+    const int oy = (iy + 1 - ky) >> 1;
+    if (iy + 1 - ky < 0 || oy >= ho) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int kx = ((ix + 1) & 1) + 2 * b;
+      const int ox = (ix + 1 - kx) >> 1;
+      if (ix + 1 - kx < 0 || ox >= wo) continue;
+      const uint4* g = dy + (((size_t)n * ho + oy) * wo + ox) * 2;
+      float v[16];
+      unpack8(g[0], v);
+      unpack8(g[1], v + 8);
+      const float* wr = w_s + (ky * 4 + kx) * 16;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc = fmaf(v[c], wr[c], acc);
+    }
+  }
+  dx[pix] = acc;
+}
+
+static bool is_disc_stem(const DirectParams& p) {
+  return p.kh == 4 && p.kw == 4 && p.stride == 2 && p.pad == 1 && p.cin == 1 && p.cout == 16 && p.x_ld == 1 && p.x_f32 &&
+         p.y_ld == 16 && !p.y_f32 && !p.accumulate && (p.w & 31) == 0 && p.ho * 2 == p.h && p.wo * 2 == p.w &&
+         (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;
+}
+
 static int fill_params(const smsut_conv_direct_args* a, DirectParams* p) {
   SMSUT_CHECK(a != nullptr, -1, "null args");
   SMSUT_CHECK(a->n > 0 && a->h > 0 && a->w > 0 && a->cin > 0 && a->cout > 0 && a->stride > 0, -1, "bad conv dims");
@@ -441,6 +546,12 @@ static int direct_dgrad(const smsut_conv_direct_args* a, cudaStream_t stream) {
   const long long npix = (long long)p.n * p.h * p.w;
   const int taps = p.kh * p.kw;
   const int cw = p.cin > p.x_ld ? p.cin : p.x_ld;
+  if (is_disc_stem(p)) {
+    launch_pdl(stem4x4_dgrad_kernel, dim3((unsigned)((npix + 255) / 256)), 256, 0, stream, (const uint4*)p.y, p.wt,
+               (float*)const_cast<void*>(p.x), npix, p.h, p.w, p.ho, p.wo);
+    count_launch();
+    return launch_status("stem4x4_dgrad_kernel");
+  }
   if (cw <= 1) {
     p.cch = pick_cch(taps, 1, p.cout);
     dim3 grid((unsigned)((npix + 127) / 128), 1);
@@ -463,6 +574,17 @@ static int direct_wgrad(const smsut_conv_direct_args* a, float* dw, float* dbias
   int rc = fill_params(a, &p);
   if (rc) return rc;
   SMSUT_CHECK(dw != nullptr, -1, "null dw");
+  if (is_disc_stem(p)) {
+    const int rows = p.n * p.ho;
+    const size_t smem = (size_t)(4 * (p.w + 4) + p.wo * 16) * sizeof(float);
+    if (smem <= 48 * 1024) {
+      launch_pdl(stem4x4_wgrad_kernel, dim3((unsigned)((rows + kStemRows - 1) / kStemRows)), 256, smem, stream,
+                 (const float*)p.x, (const uint4*)p.y, dw, dbias, det_shadow(dw), det_shadow(dbias), rows, p.h, p.w, p.ho,
+                 p.wo);
+      count_launch();
+      return launch_status("stem4x4_wgrad_kernel");
+    }
+  }
   const int nout = p.cout * p.cin * p.kh * p.kw;
   const long long total_rows = (long long)p.n * p.ho;
   const int chunks = (nout + 256 * kWgOPT - 1) / (256 * kWgOPT);

@@ -348,23 +348,33 @@ __global__ void ce_rows_bwd_kernel(const float* __restrict__ logits, const long 
   }
 }
 
-// gradient penalty: one block per sample
-__global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ g, float* __restrict__ norm,
-                                                      long long per) {
+// gradient penalty: the squared norms are summed by (sample, split) blocks (one block per sample left 16 blocks walking
+// 65 536 elements each: 57 us on the critical path of the discriminator phase), the loss kernel takes the roots
+__global__ void __launch_bounds__(256) gp_norm_kernel(const float* __restrict__ g, float* norm2, long long* norm2_q,
+                                                      long long per, int splits) {
   pdl_prologue();
   __shared__ float sh[32];
   const float* p = g + (size_t)blockIdx.x * per;
+  const long long chunk = (per + splits - 1) / splits;
+  const long long i0 = (long long)blockIdx.y * chunk;
+  long long i1 = i0 + chunk;
+  if (i1 > per) i1 = per;
   float s = 0.f;
-  for (long long i = threadIdx.x; i < per; i += blockDim.x) s = fmaf(p[i], p[i], s);
+  for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) s = fmaf(p[i], p[i], s);
   const float r = block_sum(s, sh);
-  if (threadIdx.x == 0) norm[blockIdx.x] = sqrtf(r);
+  if (threadIdx.x == 0) acc_add_at(norm2, norm2_q, blockIdx.x, r);
 }
-__global__ void gp_loss_kernel(const float* __restrict__ norm, float* __restrict__ out, long long* out_q, int b,
-                               float scale) {
+// norm[i] = sqrt(norm2[i]); out[0] += scale * mean_i (norm_i - 1)^2
+__global__ void gp_loss_kernel(const float* __restrict__ norm2, float* __restrict__ norm, float* __restrict__ out,
+                               long long* out_q, int b, float scale) {
   pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float s = 0.f;
-  for (int i = 0; i < b; ++i) s += (norm[i] - 1.f) * (norm[i] - 1.f);
+  for (int i = 0; i < b; ++i) {
+    const float nr = sqrtf(norm2[i]);
+    norm[i] = nr;
+    s += (nr - 1.f) * (nr - 1.f);
+  }
   acc_add(out, out_q, scale * s / (float)b);
 }
 __global__ void gp_bwd_kernel(const float* __restrict__ g, const float* __restrict__ norm,
@@ -681,11 +691,22 @@ extern "C" int smsut_ce_rows_bwd(const float* logits, const int64_t* target, con
   count_launch();
   return launch_status("ce_rows_bwd_kernel");
 }
-extern "C" int smsut_gp_fwd(const float* g, float* norm, float* out, int32_t b, int64_t per, float scale,
+extern "C" int smsut_gp_fwd(const float* g, float* norm, float* norm2, float* out, int32_t b, int64_t per, float scale,
                             smsut_stream_t st) {
-  launch_pdl(gp_norm_kernel, b, 256, 0, (cudaStream_t)st, g, norm, per);
-  launch_pdl(gp_loss_kernel, 1, 32, 0, (cudaStream_t)st, norm, out, det_shadow(out), b, scale);
-  count_launch(); count_launch();
+  SMSUT_CHECK(g && norm && norm2 && out && b > 0 && per > 0, -1, "gp_fwd: bad arguments");
+  long long splits = per / 2048;
+  if (splits < 1) splits = 1;
+  if (splits > 32) splits = 32;
+  long long* q = det_shadow(norm2);
+  launch_pdl(gp_norm_kernel, dim3((unsigned)b, (unsigned)splits), 256, 0, (cudaStream_t)st, g, norm2, q, (long long)per,
+             (int)splits);
+  count_launch();
+  if (q != nullptr) {
+    const int rc = smsut_det_resolve(norm2, b, st);
+    if (rc) return rc;
+  }
+  launch_pdl(gp_loss_kernel, 1, 32, 0, (cudaStream_t)st, (const float*)norm2, norm, out, det_shadow(out), b, scale);
+  count_launch();
   return launch_status("gp_fwd kernels");
 }
 extern "C" int smsut_gp_bwd(const float* g, const float* norm, const float* gscale, float scale, float* u, int32_t b,

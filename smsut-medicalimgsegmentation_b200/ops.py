@@ -220,6 +220,10 @@ def side_run(fn, keep):
 
 _branch_streams = {}
 _BRANCH_PRIORITY = int(os.environ.get("SMSUT_BRANCH_PRIORITY", "-1"))   # above the wgrad side streams (0 = lowest)
+# Branches 3 / 4 carry the generator's cycle pass and its early backward ("stage A" of UGANConsisTrainer.train_step):
+# their result is needed only at the end of the iteration, while the discriminator phase beside them is the critical
+# path -- so they run at the side streams' priority (kernel nodes of a captured graph keep their stream's priority).
+_BRANCH_PRIORITIES = {3: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "0")), 4: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "0"))}
 _branch_used = []         # branch streams forked since the iteration began (arena_begin)
 _branch_stack = []        # ids of the parallel_branch blocks the calling thread is currently inside (forward only)
 branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]
@@ -250,7 +254,8 @@ class parallel_branch:
         key = (self.main.device_index, self.k)
         st = _branch_streams.get(key)
         if st is None:
-            st = _branch_streams[key] = torch.cuda.Stream(device=self.main.device, priority=_BRANCH_PRIORITY)
+            st = _branch_streams[key] = torch.cuda.Stream(device=self.main.device,
+                                                          priority=_BRANCH_PRIORITIES.get(self.k, _BRANCH_PRIORITY))
         self.stream = st
         if st not in _branch_used:
             _branch_used.append(st)
@@ -1006,7 +1011,8 @@ def gp_fwd(g, out, scale):
     b = g.shape[0]
     per = g.numel() // b
     norm = torch.empty(b, dtype=F32, device=g.device)
-    call("smsut_gp_fwd", _p(_chk(g, F32, "gp g")), _p(norm), _p(out), b, per, scale, _stream())
+    norm2 = zeros(b, g.device)
+    call("smsut_gp_fwd", _p(_chk(g, F32, "gp g")), _p(norm), _p(norm2), _p(out), b, per, scale, _stream())
     resolve(out)
     return norm
 

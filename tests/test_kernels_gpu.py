@@ -239,6 +239,27 @@ def test_conv_direct(ops, cin, cout, k, stride, pad, h, x_f32, bias):
         assert rel(db, dy.sum((0, 2, 3))) < 1e-4
 
 
+def test_discriminator_stem_backward_kernels(ops):
+    """the specialised backward of D's stem (Conv2d(1, 16, 4, s2, p1) + bias, network/ugan.py:202): dgrad to the fp32
+    image and wgrad / dbias from bf16 gradients, vs torch.nn.grad on the same (bf16-exact) values; also a second size"""
+    for n, h in ((4, 256), (3, 64)):
+        torch.manual_seed(7)
+        x = rnd(n, 1, h, h)
+        wt = torch.randn(16, 1, 4, 4, device=DEV) * 0.25
+        dy = torch.randn(n, 16, h // 2, h // 2, device=DEV).bfloat16().float()
+        dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
+        xin = x.permute(0, 2, 3, 1).contiguous()
+        dx = ops.conv_direct_dgrad(dyn, wt, (n, h, h, 1), torch.float32, 2, 1)
+        assert rel(nchw(dx), torch.nn.grad.conv2d_input(x.shape, wt, dy, stride=2, padding=1)) < 1e-5
+        dw, db = ops.conv_direct_wgrad(xin, dyn, wt, 2, 1, want_bias=True)
+        assert rel(dw, torch.nn.grad.conv2d_weight(x, wt.shape, dy, stride=2, padding=1)) < 1e-4
+        assert rel(db, dy.sum((0, 2, 3))) < 1e-4
+        dw2 = torch.zeros_like(wt)
+        ops.conv_direct_wgrad(xin, dyn, wt, 2, 1, want_bias=False, dw=dw2)          # accumulate form, no bias
+        ops.conv_direct_wgrad(xin, dyn, wt, 2, 1, want_bias=False, dw=dw2)
+        assert rel(dw2, 2 * dw) < 1e-5
+
+
 def in_ref(x, g, b):
     return F.instance_norm(x, weight=g, bias=b, eps=1e-5)
 
