@@ -220,10 +220,12 @@ def side_run(fn, keep):
 
 _branch_streams = {}
 _BRANCH_PRIORITY = int(os.environ.get("SMSUT_BRANCH_PRIORITY", "-1"))   # above the wgrad side streams (0 = lowest)
-# Branches 3 / 4 carry the generator's cycle pass and its early backward ("stage A" of UGANConsisTrainer.train_step):
-# their result is needed only at the end of the iteration, while the discriminator phase beside them is the critical
-# path -- so they run at the side streams' priority (kernel nodes of a captured graph keep their stream's priority).
-_BRANCH_PRIORITIES = {3: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "0")), 4: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "0"))}
+# Branches 3 / 4 carry the generator's cycle pass and its early backward ("stage A" of UGANConsisTrainer.train_step).
+# Kernel nodes of a captured graph keep their stream's priority; running stage A BELOW the discriminator phase
+# (SMSUT_STAGE_A_PRIORITY=0) measured slower (10.46 vs 10.30 ms / step): its kernels are what fills the SMs the
+# discriminator's small kernels leave idle, and the final backward waits for it anyway.
+_BRANCH_PRIORITIES = {3: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "-1")),
+                      4: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "-1"))}
 _branch_used = []         # branch streams forked since the iteration began (arena_begin)
 _branch_stack = []        # ids of the parallel_branch blocks the calling thread is currently inside (forward only)
 branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]
