@@ -485,6 +485,50 @@ __global__ void __launch_bounds__(256) stem4x4_dgrad_kernel(const uint4* __restr
   dx[pix] = acc;
 }
 
+// y[n][oy][ox][co] = act( bias[co] + sum_{ky,kx} x[n][2 oy - 1 + ky][2 ox - 1 + kx] w[co][ky][kx] ): one thread per
+// output pixel, its 4 x 4 patch in registers (fp32 image), 16 x 16 weights in shared memory, two 128-bit stores.
+__global__ void __launch_bounds__(256) stem4x4_fprop_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                            const float* __restrict__ bias, uint4* __restrict__ y,
+                                                            long long npix, int h, int w, int ho, int wo, int act,
+                                                            float slope) {
+  pdl_prologue();
+  __shared__ float w_s[16 * 16];        // [tap][co]
+  __shared__ float b_s[16];
+  {
+    const int i = threadIdx.x, co = i >> 4, tap = i & 15;
+    w_s[tap * 16 + co] = wt[i];
+    if (i < 16) b_s[i] = bias != nullptr ? bias[i] : 0.f;
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (pix >= npix) return;
+  const int ox = (int)(pix % wo);
+  const long long t = pix / wo;
+  const int oy = (int)(t % ho), n = (int)(t / ho);
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = b_s[c];
+#pragma unroll
+  for (int ky = 0; ky < 4; ++ky) {
+    const int iy = 2 * oy - 1 + ky;
+    if (iy < 0 || iy >= h) continue;
+    const float* xr = x + ((size_t)n * h + iy) * w;
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx) {
+      const int ix = 2 * ox - 1 + kx;
+      if (ix < 0 || ix >= w) continue;
+      const float v = xr[ix];
+      const float* wr = w_s + (ky * 4 + kx) * 16;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = fmaf(v, wr[c], acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = apply_act(acc[c], act, slope);
+  y[2 * pix] = pack8(acc);
+  y[2 * pix + 1] = pack8(acc + 8);
+}
+
 static bool is_disc_stem(const DirectParams& p) {
   return p.kh == 4 && p.kw == 4 && p.stride == 2 && p.pad == 1 && p.cin == 1 && p.cout == 16 && p.x_ld == 1 && p.x_f32 &&
          p.y_ld == 16 && !p.y_f32 && !p.accumulate && (p.w & 31) == 0 && p.ho * 2 == p.h && p.wo * 2 == p.w &&
@@ -519,6 +563,12 @@ static int direct_fprop(const smsut_conv_direct_args* a, cudaStream_t stream) {
   const long long npix = (long long)p.n * p.ho * p.wo;
   const int taps = p.kh * p.kw;
   const int cw = p.cout > p.y_ld ? p.cout : p.y_ld;  // channels to write (incl. zero padding)
+  if (is_disc_stem(p)) {
+    launch_pdl(stem4x4_fprop_kernel, dim3((unsigned)((npix + 255) / 256)), 256, 0, stream, (const float*)p.x, p.wt, p.bias,
+               (uint4*)p.y, npix, p.h, p.w, p.ho, p.wo, p.act, p.slope);
+    count_launch();
+    return launch_status("stem4x4_fprop_kernel");
+  }
   if (npix * p.cout <= 4096 && p.y_ld == p.cout && p.cin >= 32) {
     const long long warps = npix * p.cout;
     launch_pdl(direct_fprop_small_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, stream, p);

@@ -225,7 +225,11 @@ _BRANCH_PRIORITY = int(os.environ.get("SMSUT_BRANCH_PRIORITY", "-1"))   # above 
 # (SMSUT_STAGE_A_PRIORITY=0) measured slower (10.46 vs 10.30 ms / step): its kernels are what fills the SMs the
 # discriminator's small kernels leave idle, and the final backward waits for it anyway.
 _BRANCH_PRIORITIES = {3: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "-1")),
-                      4: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "-1"))}
+                      4: int(os.environ.get("SMSUT_STAGE_A_PRIORITY", "-1")),
+                      # branches 1 / 2: D(G(x)) and the interpolated pass with the gradient penalty's double backward --
+                      # the longest dependent chain of the iteration (140 small kernels)
+                      1: int(os.environ.get("SMSUT_D_PRIORITY", "-1")),
+                      2: int(os.environ.get("SMSUT_D_PRIORITY", "-1"))}
 _branch_used = []         # branch streams forked since the iteration began (arena_begin)
 _branch_stack = []        # ids of the parallel_branch blocks the calling thread is currently inside (forward only)
 branch_parallel = [os.environ.get("SMSUT_BRANCH_STREAMS", "1") != "0"]

@@ -249,6 +249,11 @@ def test_discriminator_stem_backward_kernels(ops):
         dy = torch.randn(n, 16, h // 2, h // 2, device=DEV).bfloat16().float()
         dyn = dy.permute(0, 2, 3, 1).contiguous().bfloat16()
         xin = x.permute(0, 2, 3, 1).contiguous()
+        b = torch.randn(16, device=DEV)
+        y = ops.conv_direct_fprop(xin, wt, 2, 1, bias=b, act=2, slope=0.01, out_c=16)      # bias + LeakyReLU fused
+        assert y.dtype == torch.bfloat16 and rel(nchw(y), F.leaky_relu(F.conv2d(x, wt, b, stride=2, padding=1), 0.01)) < 5e-3
+        y0 = ops.conv_direct_fprop(xin, wt, 2, 1, out_c=16)                                 # the cotangent form: no bias / act
+        assert rel(nchw(y0), F.conv2d(x, wt, None, stride=2, padding=1)) < 5e-3
         dx = ops.conv_direct_dgrad(dyn, wt, (n, h, h, 1), torch.float32, 2, 1)
         assert rel(nchw(dx), torch.nn.grad.conv2d_input(x.shape, wt, dy, stride=2, padding=1)) < 1e-5
         dw, db = ops.conv_direct_wgrad(xin, dyn, wt, 2, 1, want_bias=True)
