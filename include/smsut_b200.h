@@ -167,6 +167,10 @@ int smsut_in_bwd2_reduce(const void* u, const void* dy, const void* x, const flo
 int smsut_in_bwd2_apply(const void* u, const void* dy, const void* x, const float* stats, const float* gamma,
                         const float* red2, void* g_dy, void* g_x, float* dgamma, int32_t n, int32_t hw, int32_t c,
                         smsut_stream_t stream);
+/* the double backward in ONE launch (same design as smsut_in_bwd_fused); counters: n zeroed 32-bit words */
+int smsut_in_bwd2_fused(const void* u, const void* dy, const void* x, const float* stats, const float* gamma, float* red2,
+                        void* counters, void* g_dy, void* g_x, float* dgamma, int32_t n, int32_t hw, int32_t c,
+                        smsut_stream_t stream);
 /* BatchNorm2d (network/blocks.py:19-26 get_norm('batch'); default norm of network/unet.py:14) on the kernels above:
  * out[j] = mean over the n rows of rows[n][k][c] for every j (batch statistics = pooled per-sample sums; the
  * backward pools `red` the same way between smsut_in_bwd_reduce and smsut_in_bwd_apply) */

@@ -78,6 +78,7 @@ _PROTOS = {
                            c_float, P],
     "smsut_in_bwd_fused": [P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int,
                            c_float, P],
+    "smsut_in_bwd2_fused": [P, P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_in_bwd2_reduce": [P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_in_bwd2_apply": [P, P, P, P, P, P, P, P, P, c_int, c_int, c_int, P],
     "smsut_bn_pool": [P, P, c_int, c_int, c_int, P],

@@ -696,6 +696,107 @@ in_bwd2_apply_kernel(const void* __restrict__ u, const void* __restrict__ dy, co
   }
 }
 
+// Both passes of the double backward in ONE launch (grid = (splits, n), counter barrier over the CTAs of a sample, the
+// sums read back past L1 or from the fixed-point shadow): the gradient penalty's double-backward chain is 140 dependent
+// kernels of which 28 were these pairs, and on that chain every link costs ~25 us inside the captured iteration.
+__global__ void __launch_bounds__(kNT)
+in_bwd2_fused_kernel(const void* __restrict__ u, const void* __restrict__ dy, const void* __restrict__ x,
+                     const float* __restrict__ stats, const float* __restrict__ gamma, float* red2, long long* red2_q,
+                     unsigned int* counters, void* __restrict__ g_dy, void* __restrict__ g_x, float* dgamma,
+                     long long* dgamma_q, int hw, int c, int splits) {
+  pdl_prologue();
+  extern __shared__ float sh[];
+  const int n = blockIdx.y, split = blockIdx.x;
+  Strip s;
+  s.cg = c >> 3;
+  s.g = threadIdx.x % s.cg;
+  s.lane0 = threadIdx.x / s.cg;
+  s.nlanes = kNT / s.cg;
+  {
+    const long long per = ((long long)hw + splits - 1) / splits;
+    s.p0 = (long long)split * per;
+    s.p1 = s.p0 + per;
+    if (s.p1 > hw) s.p1 = hw;
+  }
+  const int ch0 = s.g * 8;
+  const float inv_hw = 1.f / (float)hw;
+  float m[8], r[8];
+  load_mean_rstd(stats, n, c, ch0, inv_hw, m, r);
+  const size_t base = (size_t)n * hw * c + ch0;
+  {
+    float acc[5][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = acc[4][j] = 0.f;
+    for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+      const size_t off = base + (size_t)p * c;
+      float uu[8], dd[8], xx[8];
+      unpack8(ldg16(u, off), uu);
+      unpack8(ldg16(dy, off), dd);
+      unpack8(ldg16(x, off), xx);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xx[j] - m[j]) * r[j];
+        acc[0][j] += uu[j];
+        acc[1][j] += dd[j];
+        acc[2][j] = fmaf(uu[j], xh, acc[2][j]);
+        acc[3][j] = fmaf(dd[j], xh, acc[3][j]);
+        acc[4][j] = fmaf(uu[j], dd[j], acc[4][j]);
+      }
+    }
+    block_reduce_add32<5>(acc, sh, s, red2 + (size_t)n * 5 * c, red2_q ? red2_q + (size_t)n * 5 * c : nullptr, c, c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counters + n, 1u);
+    unsigned int spins = 0;
+    while (atomicAdd(counters + n, 0u) < (unsigned int)splits) {
+      __nanosleep(40);
+      if (++spins > (1u << 26)) {
+        printf("smsut: in_bwd2_fused barrier timed out (sample %d split %d of %d)\n", n, split, splits);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  float mu[8], md[8], cu[8], b[8], e[8], gr[8];
+  {
+    const size_t rb = (size_t)n * 5 * c + ch0;
+    float t[5];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int v = 0; v < 5; ++v)
+        t[v] = red2_q != nullptr ? (float)((double)__ldcg(red2_q + rb + (size_t)v * c + j) * (1.0 / 4294967296.0))
+                                 : __ldcg(red2 + rb + (size_t)v * c + j);
+      mu[j] = t[0] * inv_hw; md[j] = t[1] * inv_hw; cu[j] = t[2] * inv_hw; b[j] = t[3] * inv_hw; e[j] = t[4] * inv_hw;
+      gr[j] = gamma[ch0 + j] * r[j];
+    }
+  }
+  if (dgamma != nullptr && split == 0 && s.lane0 == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      acc_add_at(dgamma, dgamma_q, ch0 + j, r[j] * (float)hw * (e[j] - mu[j] * md[j] - b[j] * cu[j]));
+  }
+  for (long long p = s.p0 + s.lane0; p < s.p1; p += s.nlanes) {
+    const size_t off = base + (size_t)p * c;
+    float uu[8], dd[8], xx[8], o1[8], o2[8];
+    unpack8(ldg16(u, off), uu);
+    unpack8(ldg16(dy, off), dd);
+    unpack8(ldg16(x, off), xx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xx[j] - m[j]) * r[j];
+      o1[j] = gr[j] * (uu[j] - mu[j] - xh * cu[j]);
+      o2[j] = -gr[j] * r[j] *
+              (xh * (e[j] - mu[j] * md[j] - 3.f * b[j] * cu[j]) + cu[j] * (dd[j] - md[j]) + b[j] * (uu[j] - mu[j]));
+    }
+    stg16(g_dy, off, pack8(o1));
+    stg16(g_x, off, pack8(o2));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // elementwise
 // ---------------------------------------------------------------------------------------------
@@ -1004,6 +1105,43 @@ extern "C" int smsut_in_bwd2_apply(const void* u, const void* dy, const void* x,
              det_shadow(dgamma), hw, c, splits);
   count_launch();
   return launch_status("in_bwd2_apply_kernel");
+}
+
+// double backward in one call: fused kernel when the grid can be co-resident, else the pair.  counters: n zeroed words
+extern "C" int smsut_in_bwd2_fused(const void* u, const void* dy, const void* x, const float* stats, const float* gamma,
+                                   float* red2, void* counters, void* g_dy, void* g_x, float* dgamma, int32_t n, int32_t hw,
+                                   int32_t c, smsut_stream_t st) {
+  int rc = check_nc(n, hw, c);
+  if (rc) return rc;
+  SMSUT_CHECK(red2 != nullptr && counters != nullptr, -1, "in_bwd2_fused: red2 / counters missing");
+  static int knob = -1, per_sm = -1;
+  if (knob < 0) {
+    const char* e = getenv("SMSUT_IN_FUSED");
+    knob = e ? atoi(e) : 1;
+  }
+  const size_t shm = red_smem(5, c);
+  if (per_sm < 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, in_bwd2_fused_kernel, kNT, 40 * 1024) != cudaSuccess) nb = 0;
+    per_sm = nb;
+  }
+  const long long cap = (long long)per_sm * device_sm_count();
+  long long* red2_q = det_shadow(red2);
+  if (knob && shm <= 40 * 1024 && cap >= n) {
+    int splits = pick_splits(n, hw, c);
+    if ((long long)splits * n > cap) splits = (int)(cap / n);
+    launch_pdl(in_bwd2_fused_kernel, dim3(splits, n), kNT, shm, (cudaStream_t)st, u, dy, x, stats, gamma, red2, red2_q,
+               (unsigned int*)counters, g_dy, g_x, dgamma, det_shadow(dgamma), hw, c, splits);
+    count_launch();
+    return launch_status("in_bwd2_fused_kernel");
+  }
+  rc = smsut_in_bwd2_reduce(u, dy, x, stats, red2, n, hw, c, st);
+  if (rc) return rc;
+  if (red2_q != nullptr) {
+    rc = smsut_det_resolve(red2, (int64_t)n * 5 * c, st);
+    if (rc) return rc;
+  }
+  return smsut_in_bwd2_apply(u, dy, x, stats, gamma, red2, g_dy, g_x, dgamma, n, hw, c, st);
 }
 
 // ---------------------------------------------------------------------------------------------

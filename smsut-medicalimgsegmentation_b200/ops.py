@@ -789,12 +789,11 @@ def in_bwd2(u, dy, x, stats, gamma):
     """double backward of plain InstanceNorm: returns g_dy, g_x, dgamma"""
     n, h, w, c = x.shape
     red2 = zeros((n, 5, c), x.device)
-    call("smsut_in_bwd2_reduce", _p(u), _p(dy), _p(x), _p(stats), _p(red2), n, h * w, c, _stream())
-    resolve(red2)
+    counters = zeros(n, x.device)
     g_dy, g_x = torch.empty_like(x), torch.empty_like(x)
     dgamma = zeros(c, x.device)
-    call("smsut_in_bwd2_apply", _p(u), _p(dy), _p(x), _p(stats), _p(gamma), _p(red2), _p(g_dy), _p(g_x), _p(dgamma), n,
-         h * w, c, _stream())
+    call("smsut_in_bwd2_fused", _p(u), _p(dy), _p(x), _p(stats), _p(gamma), _p(red2), _p(counters), _p(g_dy), _p(g_x),
+         _p(dgamma), n, h * w, c, _stream())
     return g_dy, g_x, resolve(dgamma)
 
 
