@@ -1127,7 +1127,9 @@ extern "C" int smsut_in_bwd2_fused(const void* u, const void* dy, const void* x,
   }
   const long long cap = (long long)per_sm * device_sm_count();
   long long* red2_q = det_shadow(red2);
-  if (knob && shm <= 40 * 1024 && cap >= n) {
+  const long long sample_bytes = (long long)hw * c * 2;
+  const bool pick = knob == 1 || (knob == 2 && sample_bytes <= 256 * 1024) || (knob == 3 && sample_bytes > 256 * 1024);
+  if (pick && shm <= 40 * 1024 && cap >= n) {
     int splits = pick_splits(n, hw, c);
     if ((long long)splits * n > cap) splits = (int)(cap / n);
     launch_pdl(in_bwd2_fused_kernel, dim3(splits, n), kNT, shm, (cudaStream_t)st, u, dy, x, stats, gamma, red2, red2_q,
