@@ -280,6 +280,11 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
       if (a->ksize * a->x_c > 128) return 0;
     }
   }
+  {
+    // development (timing bound only, WRONG results): how much of the iteration is this kernel?  scripts/gpu_ab.sh
+    const char* e = getenv("SMSUT_DBG_SKIP_WGRAD_BAND");
+    if (e && e[0] == '1') return 1;
+  }
   WgradBandParams p;
   memset(&p, 0, sizeof(p));
   { const char* e = getenv("SMSUT_WGRAD_NOEPI"); p.dbg_noepi = (e && e[0] == '1') ? 1 : 0; }

@@ -261,6 +261,44 @@ def test_discriminator_layers(pkg):
     assert e2e["max_forced"] < 3e-2, e2e["max_forced"]      # 12 layers: the accumulated error stays at 2e-2 (1.8-2.1e-2 measured)
 
 
+def test_discriminator_gradient_penalty_forced_selections(pkg):
+    """The D phase's hardest path: WGAN-GP (trainer/uganShp0Trainer.py:127-134) -- a first-order backward with
+    create_graph and the double backward through every conv / InstanceNorm / LeakyReLU / avg-pool of D (the hand-derived
+    second-order kernels) -- end to end against the oracle evaluated on the SAME LeakyReLU selections.  With the
+    selections forced the comparison is arithmetic only, so the gates can be tight where the free-running step test
+    (tests/test_modules_gpu.py::test_ugan_consis_step_parity) has to allow for mask flips: a dropped term of d_loss, a
+    wrong lambda or a missing contribution to the double backward moves these numbers by tens of percent."""
+    from smsut_b200 import functional as Fn
+    from smsut_b200.network.ugan import Discriminator
+    from smsut_b200.trainer.uganShp0Trainer import UGANShp0Trainer
+    sd = to_dev(O.make_weights(O.disc_shapes(256), 5))
+    D = Discriminator(256, 4, 16, max_width=256).to(DEV)
+    D.load_state_dict(sd)
+    x, _ = O.synthetic_batch(4, 256, 6, device=DEV)
+    x_hat0 = x + 0.1 * torch.randn(x.shape, generator=torch.Generator().manual_seed(9)).to(DEV)
+
+    def ours():
+        xh = x_hat0.clone().requires_grad_(True)
+        s, c = D(xh)
+        gp = UGANShp0Trainer.gradient_penalty(None, s, xh)
+        return [s, c, gp.reshape(1)], 10 * gp + s.mean() + c.pow(2).mean()
+
+    def oracle(leaf, style):
+        xh = x_hat0.clone().requires_grad_(True)
+        s, c = O.discriminator_forward(leaf, xh, style=style)
+        gp = O.gradient_penalty(s, xh)
+        return [s, c, gp.reshape(1)], 10 * gp + s.mean() + c.pow(2).mean()
+    e2e = _forced_end_to_end(Fn, D, "disc", {}, ours, oracle, sd)
+    a = torch.cat([p.grad.flatten().float() for _, p in D.named_parameters()])
+    report("forced_discriminator_gp", e2e)
+    vals = sorted(e2e["grads_vs_forced_oracle"].values())
+    free = sorted(e2e["grads_vs_free_oracle"].values())
+    assert abs(e2e["outputs"][2]) < 5e-2, e2e["outputs"]                      # the penalty itself
+    assert vals[len(vals) // 2] < 3e-2 and vals[-1] < 0.1, (vals[len(vals) // 2], vals[-1])
+    assert vals[len(vals) // 2] < 0.5 * free[len(free) // 2], (vals[len(vals) // 2], free[len(free) // 2])
+    assert torch.isfinite(a).all()
+
+
 # --------------------------------------------------------------------------------------------------
 # deterministic mode: bit-identical iterations, graph replay == eager, stream schedule does not matter
 # --------------------------------------------------------------------------------------------------
