@@ -214,11 +214,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 static uint32_t layout_for_chunk(int cc) { return cc == 64 ? 2u : (cc == 32 ? 4u : 6u); }
 
 int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream);
+int wgrad_hmma_try(const smsut_wgrad_tc_args* a, cudaStream_t stream);
 
 static int wgrad_tc_impl(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   SMSUT_CHECK(a != nullptr, -1, "null args");
   if (a->dw != nullptr && a->x_c % 16 == 0 && a->dy_c % 16 == 0) {
-    const int rb = wgrad_band_try(a, stream);     // wide, narrow-channel layers: rows fetched once, taps by descriptor
+    // wide, narrow-channel layers: warp-level MMAs over shared-memory row rings (wgrad_hmma.cu); SMSUT_WGRAD_HMMA=0
+    // falls through to the tcgen05 band kernel (rows fetched once by TMA, taps by descriptor arithmetic)
+    int rb = wgrad_hmma_try(a, stream);
+    if (rb != 0) return rb < 0 ? rb : 0;
+    rb = wgrad_band_try(a, stream);
     if (rb != 0) return rb < 0 ? rb : 0;
   }
   SMSUT_CHECK(a->kind == SMSUT_TC_CONV || a->kind == SMSUT_TC_CONVT_FWD, -1, "wgrad kind must be CONV or CONVT_FWD");

@@ -141,6 +141,32 @@ def test_wgrad_tap_major_scratch(ops, cins, cout, h, n, ks):
     assert rel(grad - 0.5, 2 * dw_ref) < 1e-2
 
 
+@pytest.mark.parametrize("cin,cout,h,w,n,ks,live", [
+    (16, 16, 256, 256, 2, 3, 16), (32, 16, 128, 128, 2, 3, 32), (16, 32, 128, 128, 3, 3, 16), (32, 32, 40, 128, 2, 3, 32),
+    (16, 64, 24, 128, 2, 3, 16), (16, 16, 64, 256, 1, 5, 5), (16, 16, 32, 128, 2, 5, 1), (32, 32, 128, 128, 2, 1, 32),
+    (16, 32, 17, 128, 5, 1, 16), (32, 64, 16, 256, 2, 1, 32), (16, 16, 512, 512, 1, 3, 8)])
+def test_wgrad_warp_mma_kernel(ops, cin, cout, h, w, n, ks, live):
+    """wgrad_hmma_kernel (the wide, narrow-channel layers: W % 128 == 0, 16 / 32 input channels) on every template
+    instance, ragged row segments, non-square images, zero-padded input channels (`live` of `cin` exist in the weight)
+    and both destination layouts, vs torch.nn.grad.conv2d_weight on the same bf16-exact values."""
+    torch.manual_seed(13)
+    x = rnd(n, cin, h, w)
+    x[:, live:] = 0
+    dy = rnd(n, cout, h, w)
+    wt = rnd(cout, live, ks, ks, scale=0.1)
+    pw = make_pack(ops, wt)
+    assert pw.cin_pad == cin
+    dw_ref = torch.nn.grad.conv2d_weight(x[:, :live], wt.shape, dy, padding=ks // 2)
+    dw = ops.conv_wgrad([nhwc(x)], nhwc(dy), pw)                      # OIHW destination
+    assert rel(dw, dw_ref) < 5e-3, rel(dw, dw_ref)
+    grad = torch.zeros_like(wt)
+    sc = ops.WgradScratch([wt], [grad])
+    ops.conv_wgrad([nhwc(x)], nhwc(dy), pw, out=grad)                 # tap-major scratch, folded by unpack_wgrads
+    ops.side_join()
+    sc.flush()
+    assert rel(grad, dw_ref) < 5e-3, rel(grad, dw_ref)
+
+
 def test_convt_wgrad_tap_major_scratch(ops):
     x = rnd(2, 64, 32, 32, seed=6)
     wt = rnd(64, 32, 2, 2, scale=0.1)
