@@ -28,6 +28,7 @@ namespace smsut {
 void count_launch();
 
 constexpr int kHmMaxWarps = 16;
+constexpr int kHmMaxDepth = 6;
 
 struct WgradHmmaParams {
   const __nv_bfloat16* x;
@@ -39,6 +40,7 @@ struct WgradHmmaParams {
   int wtiles, segs, rows_per_seg;
   int jobs, pg, nwarps;          // jobs = (dy_c / 16) * ks; pixel groups; warps = jobs * pg
   int xs_slots, ds_slots;        // ring depths
+  int depth;                     // rows staged ahead of the one being multiplied (1..kHmMaxDepth)
   int x_pitch, d_pitch;          // bytes per pixel in shared memory (channels * 2 + 16)
   int x_row_bytes, d_row_bytes;  // bytes per ring slot
   int tap_major, cout_total, cout, cin_total, ci_off, c_valid, taps;
@@ -50,6 +52,18 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// wait until at most `n` of the most recently committed groups are still in flight (n is a small runtime value)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+  switch (n) {
+    case 0: cp_async_wait<0>(); break;
+    case 1: cp_async_wait<1>(); break;
+    case 2: cp_async_wait<2>(); break;
+    case 3: cp_async_wait<3>(); break;
+    case 4: cp_async_wait<4>(); break;
+    case 5: cp_async_wait<5>(); break;
+    default: cp_async_wait<6>(); break;
+  }
+}
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -126,18 +140,20 @@ __global__ void __launch_bounds__(kHmMaxWarps * 32, 1) wgrad_hmma_kernel(const W
   //   B (x):    m0 (px 0-7, ci 0-7) m1 (px 8-15, ci 0-7) m2 (px 0-7, ci 8-15) m3 (px 8-15, ci 8-15)
   const uint32_t b_lane = (uint32_t)(((mi & 1) * 8 + r8) * p.x_pitch + ((mi >> 1) * 8) * 2);
 
-  // prologue: x rows h0-R .. h0+R (the first window) and dy row h0; then one row ahead
-  for (int j = 0; j < 2 * R + 1; ++j) stage_x(h0 - R + j, j % p.xs_slots);
-  stage_d(h0, 0);
-  cp_async_commit();
-  for (int i = 0; i < nrows; ++i) {
-    // prefetch what row i + 1 needs: x row h0 + i + 1 + R and dy row h0 + i + 1
-    if (i + 1 < nrows) {
-      stage_x(h0 + i + 1 + R, (i + 1 + 2 * R) % p.xs_slots);
-      stage_d(h0 + i + 1, (i + 1) % p.ds_slots);
+  // One cp.async group per output row: group g carries what row g adds to the rings (x row h0 + g + R, dy row h0 + g;
+  // group 0 also the first window's x rows h0-R .. h0+R-1).  `depth` groups stay in flight ahead of the row being
+  // multiplied: one row of lookahead left the loop waiting a full DRAM round trip per row (65 us per launch).
+  const int D = p.depth;
+  for (int j = 0; j < 2 * R; ++j) stage_x(h0 - R + j, j % p.xs_slots);
+  for (int g = 0; g < D; ++g) {
+    if (g < nrows) {
+      stage_x(h0 + g + R, (g + 2 * R) % p.xs_slots);
+      stage_d(h0 + g, g % p.ds_slots);
     }
     cp_async_commit();
-    cp_async_wait<1>();            // everything but the group just committed has landed
+  }
+  for (int i = 0; i < nrows; ++i) {
+    cp_async_wait_dyn(D - 1);      // groups 0 .. i have landed (D - 1 newer ones may still be in flight)
     __syncthreads();
     if (active) {
       const uint32_t d_row = d_ring_s + (uint32_t)((i % p.ds_slots) * p.d_row_bytes) + a_lane;
@@ -157,7 +173,12 @@ __global__ void __launch_bounds__(kHmMaxWarps * 32, 1) wgrad_hmma_kernel(const W
         }
       }
     }
-    __syncthreads();               // the slots this row read are overwritten by the next iteration's prefetch
+    __syncthreads();               // every warp is done with row i: its oldest slots may be refilled
+    if (i + D < nrows) {
+      stage_x(h0 + i + D + R, (i + D + 2 * R) % p.xs_slots);
+      stage_d(h0 + i + D, (i + D) % p.ds_slots);
+    }
+    cp_async_commit();
   }
   cp_async_wait<0>();
   __syncthreads();
@@ -230,12 +251,15 @@ int wgrad_hmma_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   if (p.pg < 1) p.pg = 1;
   if (p.pg > 8) p.pg = 8;
   p.nwarps = p.jobs * p.pg;
-  p.xs_slots = 2 * p.r + 2;
-  p.ds_slots = 2;
   p.x_pitch = a->x_c * 2 + 16;
   p.d_pitch = a->dy_c * 2 + 16;
   p.x_row_bytes = ((128 + 2 * p.r) * p.x_pitch + 127) & ~127;
   p.d_row_bytes = (128 * p.d_pitch + 127) & ~127;
+  // lookahead: as deep as ~100 KB of rings allow (two CTAs per SM)
+  p.depth = kHmMaxDepth;
+  while (p.depth > 1 && (size_t)(2 * p.r + p.depth) * p.x_row_bytes + (size_t)p.depth * p.d_row_bytes > 100u * 1024u) --p.depth;
+  p.xs_slots = 2 * p.r + p.depth;      // rows i .. i + 2r in use + depth - 1 staged ahead, refilled after the row's barrier
+  p.ds_slots = p.depth;
   p.tap_major = a->dw_layout == 1 ? 1 : 0;
   p.cout_total = a->cout_total;
   p.cout = a->dy_c < a->cout_total ? a->dy_c : a->cout_total;
