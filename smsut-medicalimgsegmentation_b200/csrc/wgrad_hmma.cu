@@ -7,7 +7,10 @@
 // (wgrad_band.cu) has to feed that shape through M = 128 / N >= 16 UMMAs that are 37 % occupied and all issued by one
 // thread -- 24 of them per 128-pixel row -- and measured 36-69 us per launch; skipping it altogether shortened the
 // captured iteration from 10.2 to 8.9 ms, which makes it the most expensive kernel family of the step.  Here every
-// warp of the CTA issues its own m16n8k16 bf16 MMAs (fp32 accumulate), so the issue rate scales with the warps:
+// warp of the CTA issues its own m16n8k16 bf16 MMAs (fp32 accumulate), so the issue rate scales with the warps.
+// RESULT: correct on every shape (tests/test_kernels_gpu.py::test_wgrad_warp_mma_kernel) but SLOWER than the tcgen05
+// kernel -- the warp-level MMA path of sm_100 is too slow for 4.8 GFLOP per launch (see wgrad_hmma_try) -- so it is
+// opt-in and kept as a measured negative result.
 //
 //   CTA   = one strip: 128 pixels x R rows of one image (the grid is one wave of two CTAs per SM)
 //   warp  = one "job" (16 output channels, one vertical tap ky) x one pixel group (chunks c = g, g + PG, ...)
@@ -230,12 +233,13 @@ int wgrad_hmma_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   if (a->x_ld % 8 != 0 || a->dy_ld % 8 != 0) return 0;
   if ((reinterpret_cast<uintptr_t>(a->x) & 15) != 0 || (reinterpret_cast<uintptr_t>(a->dy) & 15) != 0) return 0;
   {
-    static int knob = -1;
-    if (knob < 0) {
-      const char* e = getenv("SMSUT_WGRAD_HMMA");      // 0: keep the tcgen05 band kernel (A/B, development)
-      knob = e ? atoi(e) : 1;
-    }
-    if (!knob) return 0;
+    // OPT-IN (SMSUT_WGRAD_HMMA=1; read per call so that the parity test can switch it).  Measured on B200 and NOT the
+    // default: 64.9 us against 58.0 us of the tcgen05 band kernel for 16->16 @ 256x256 x 16 slices (88 vs 56 us for
+    // 32->32 @ 128x128), 10.8 vs 10.2 ms per captured iteration.  Deeper cp.async lookahead changed nothing: the
+    // kernel is bound by the legacy warp-level MMA path itself, which on sm_100 sustains only ~70-150 TFLOP/s --
+    // 4.8 GFLOP per launch cannot finish under ~35 us there, while HBM would allow 10 us.
+    const char* e = getenv("SMSUT_WGRAD_HMMA");
+    if (!(e && e[0] == '1')) return 0;
   }
   WgradHmmaParams p;
   memset(&p, 0, sizeof(p));

@@ -145,10 +145,11 @@ def test_wgrad_tap_major_scratch(ops, cins, cout, h, n, ks):
     (16, 16, 256, 256, 2, 3, 16), (32, 16, 128, 128, 2, 3, 32), (16, 32, 128, 128, 3, 3, 16), (32, 32, 40, 128, 2, 3, 32),
     (16, 64, 24, 128, 2, 3, 16), (16, 16, 64, 256, 1, 5, 5), (16, 16, 32, 128, 2, 5, 1), (32, 32, 128, 128, 2, 1, 32),
     (16, 32, 17, 128, 5, 1, 16), (32, 64, 16, 256, 2, 1, 32), (16, 16, 512, 512, 1, 3, 8)])
-def test_wgrad_warp_mma_kernel(ops, cin, cout, h, w, n, ks, live):
+def test_wgrad_warp_mma_kernel(ops, monkeypatch, cin, cout, h, w, n, ks, live):
     """wgrad_hmma_kernel (the wide, narrow-channel layers: W % 128 == 0, 16 / 32 input channels) on every template
     instance, ragged row segments, non-square images, zero-padded input channels (`live` of `cin` exist in the weight)
     and both destination layouts, vs torch.nn.grad.conv2d_weight on the same bf16-exact values."""
+    monkeypatch.setenv("SMSUT_WGRAD_HMMA", "1")          # opt-in kernel (measured slower than the tcgen05 band kernel)
     torch.manual_seed(13)
     x = rnd(n, cin, h, w)
     x[:, live:] = 0
