@@ -389,14 +389,18 @@ def parity_check(torch, tr, par, host_batch, bs, dev):
             def flat_of(named, grads):
                 return torch.cat([grads[k].flatten().float() for k, _ in named])
 
-            def mine(named, opt):
+            def mine(named, flat):
                 off, parts = 0, []
                 for _, p_ in named:
                     n = p_.numel()
-                    parts.append(opt[off:off + n])
+                    parts.append(flat[off:off + n])
                     off += (n + 3) // 4 * 4
                 return torch.cat(parts) / W
-            dn, gn = list(tr.D.named_parameters()), list(tr.net.named_parameters())
+
+            def in_flat_order(net, opt):      # (name, parameter) in the optimizer's flat-buffer order
+                names = {id(p_): k for k, p_ in net.named_parameters()}
+                return [(names[id(p_)], p_) for p_ in opt.params]
+            dn, gn = in_flat_order(tr.D, tr.d_optimizer), in_flat_order(tr.net, tr.optimizer)
             a_d, b_d = mine(dn, d_sum), flat_of(dn, d_grads)
             a_g, b_g = mine(gn, g_sum), flat_of(gn, g_grads)
             cos = lambda a, b: float(a @ b / (a.norm() * b.norm() + 1e-30))

@@ -391,12 +391,16 @@ class WgradScratch:
     smsut_unpack_wgrads launch per network -- folds the scratch into the OIHW gradient and clears it."""
     owners = weakref.WeakSet()
 
-    def __init__(self, params, grad_views, grad_flat=None):
+    def __init__(self, params, grad_views, grad_flat=None, n_early=0, early_offset=None):
         """params: the network's parameters; grad_views[i]: the flat-gradient view of params[i].  The scratch is built
         on first use: the conv modules create their PackedWeight (which marks a weight as tensor-core) lazily.
         grad_flat: the flat gradient buffer the views live in (deterministic mode: its shadow is folded in by flush)."""
         self.params, self.grads = list(params), list(grad_views)
         self.grad_flat = grad_flat
+        # the last n_early parameters form the "early bucket" (optim._FlatOptimizer): flush(part=...) can complete the
+        # two parts of the gradient separately
+        self.n_early, self.early_offset = n_early, early_offset
+        self.n_late_entries, self.scratch_split = 0, 0
         self.dirty = False
         self.flat = None
         self.shadow = None
@@ -416,6 +420,9 @@ class WgradScratch:
         self.flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
         self.shadow = det_register(self.flat) if DET[0] and self.flat.is_cuda else None
         entries, off = [], 0
+        early_ids = {id(p) for p in self.params[len(self.params) - self.n_early:]} if self.n_early else set()
+        self.n_late_entries = sum(1 for p, _ in items if id(p) not in early_ids)
+        self.scratch_split = sum(sz for (p, _), sz in zip(items, sizes) if id(p) not in early_ids)
         for (p, g), sz in zip(items, sizes):
             taps, rows, cols = p._smsut_tc
             view = self.flat[off:off + p.numel()].view(taps, rows, cols)
@@ -455,23 +462,42 @@ class WgradScratch:
                 self.shadow.zero_()
         self.dirty = False
 
-    def flush(self):
-        if self.grad_flat is not None:
-            resolve(self.grad_flat)       # deterministic mode: atomically accumulated parameter gradients
-        self._flush_scratch()
+    def flush(self, part='all'):
+        """part: 'all', or 'early' / 'late' = only the early bucket's parameters / only the others"""
+        if self.grad_flat is not None:       # deterministic mode: atomically accumulated parameter gradients
+            if part == 'all' or not self.n_early:
+                resolve(self.grad_flat)
+            elif part == 'early':
+                resolve(self.grad_flat[self.early_offset:])
+            elif self.early_offset > 0:
+                resolve(self.grad_flat[:self.early_offset])
+        self._flush_scratch(part if self.n_early else 'all')
 
-    def _flush_scratch(self):
+    def _flush_scratch(self, part='all'):
         if self.flat is None or not self.dirty:
             return
-        resolve(self.flat)
-        call("smsut_unpack_wgrads", _p(self.table), self.n, _stream())
-        self.flat.zero_()
-        self.dirty = False
+        entry = ctypes_sizeof_unpack_entry()
+        if part == 'all':
+            first, count, lo, hi = 0, self.n, 0, self.flat.numel()
+        elif part == 'late':
+            first, count, lo, hi = 0, self.n_late_entries, 0, self.scratch_split
+        else:
+            first, count, lo, hi = self.n_late_entries, self.n - self.n_late_entries, self.scratch_split, self.flat.numel()
+        if count > 0:
+            resolve(self.flat[lo:hi])
+            call("smsut_unpack_wgrads", C.c_void_p(self.table.data_ptr() + first * entry), count, _stream())
+            self.flat[lo:hi].zero_()
+        if part != 'early':
+            self.dirty = False       # 'early' leaves the late part pending
 
     @staticmethod
     def flush_all():
         for o in list(WgradScratch.owners):
             o.flush()
+
+
+def ctypes_sizeof_unpack_entry():
+    return C.sizeof(UnpackEntry)
 
 
 def _wgrad_scratch(weight, out):

@@ -32,8 +32,16 @@ class FlatParams:
 
 
 class _FlatOptimizer:
-    def __init__(self, params, lr):
+    def __init__(self, params, lr, early=None):
+        """early: optional list of parameters whose gradients are complete EARLY in the iteration (before the rest of the
+        backward has run).  They are laid out as the tail of the flat buffers -- [late ..., early ...] -- so that their
+        gradients are one contiguous range that a data-parallel run can all-reduce while the remaining backward is
+        still running (parallel.DataParallelContext.all_reduce_early)."""
         self.params = [p for p in params]
+        if early:
+            ids = {id(p) for p in early}
+            self.params = [p for p in self.params if id(p) not in ids] + [p for p in self.params if id(p) in ids]
+        self.n_early = len(early) if early else 0
         if not self.params:
             raise ValueError("optimizer got an empty parameter list")
         dev = self.params[0].device
@@ -42,18 +50,23 @@ class _FlatOptimizer:
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         off = 0
+        self.early_offset = total      # first element of the early bucket in the flat buffers
         with torch.no_grad():
-            for p, sz in zip(self.params, sizes):
+            for i, (p, sz) in enumerate(zip(self.params, sizes)):
+                if self.n_early and i == len(self.params) - self.n_early:
+                    self.early_offset = off
                 n = p.numel()
                 self.flat[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat[off:off + n].view(p.shape)
                 p.grad = self.grad[off:off + n].view(p.shape)
                 off += sz
+        self.early_done = False        # the early bucket of this iteration has already been completed (and reduced)
         # tap-major scratch for the tensor-core weight gradients (ops.WgradScratch); folded into `grad` by finish_grads()
         # deterministic mode: the parameter gradients the kernels accumulate with atomics (norm gamma / beta, direct
         # convs) go through a fixed-point shadow of the flat gradient, folded in by finish_grads()
         self.grad_shadow = ops.det_register(self.grad) if ops.DET[0] and self.grad.is_cuda else None
-        self.wgrad_scratch = ops.WgradScratch(self.params, [p.grad for p in self.params], grad_flat=self.grad)
+        self.wgrad_scratch = ops.WgradScratch(self.params, [p.grad for p in self.params], grad_flat=self.grad,
+                                              n_early=self.n_early, early_offset=self.early_offset)
         self.param_groups = [dict(params=self.params, lr=lr)]
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
         self._lr_host = float(lr)
@@ -67,6 +80,7 @@ class _FlatOptimizer:
         return [p for p in self.params if p.grad is None or not (lo <= p.grad.data_ptr() < hi)]
 
     def zero_grad(self, set_to_none=False):
+        self.early_done = False
         self.grad.zero_()
         if self.grad_shadow is not None:
             self.grad_shadow.zero_()
@@ -86,7 +100,16 @@ class _FlatOptimizer:
                 for p, g in held:
                     if g is not None:
                         p.grad.add_(g.to(p.grad.dtype).view_as(p.grad))
-        self.wgrad_scratch.flush()
+        self.wgrad_scratch.flush(part='late' if self.early_done else 'all')
+
+    def finish_early_grads(self):
+        """complete the gradients of the early bucket (fold its part of the tensor-core scratch and of the fixed-point
+        shadow in); the final finish_grads() then only completes the rest"""
+        if not self.n_early or self.early_done:
+            return False
+        self.wgrad_scratch.flush(part='early')
+        self.early_done = True
+        return True
 
     def _reattach(self):
         off = 0
@@ -131,8 +154,8 @@ class _FlatOptimizer:
 class SGD(_FlatOptimizer):
     _STATE = ('mom',)
 
-    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0):
-        super().__init__(params, lr)
+    def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, early=None):
+        super().__init__(params, lr, early=early)
         self.momentum, self.weight_decay = momentum, weight_decay
         self.mom = torch.zeros_like(self.flat)
 

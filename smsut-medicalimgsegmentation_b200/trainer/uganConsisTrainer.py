@@ -42,6 +42,9 @@ SPLIT_SEG_ROWS = [os.environ.get("SMSUT_SPLIT_SEG_ROWS", "1") != "0"]
 # D(x_real) and D(G(x).detach()) of the D phase as one 2B-slice pass (train_step); measured: see DESIGN.md
 BATCH_D_REAL_FAKE = [os.environ.get("SMSUT_BATCH_D", "0") != "0"]
 
+# data-parallel runs: all-reduce the early gradient bucket beside the discriminator phase (train_step)
+EARLY_ALLREDUCE = [os.environ.get("SMSUT_EARLY_ALLREDUCE", "1") != "0"]
+
 LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
 
 
@@ -122,6 +125,14 @@ class UGANConsisTrainer(UGANShp0Trainer):
                     g_partial.backward()
                 dx_fake_cyc = x_fake_c.grad
         stage_a = ops.pending_detach() if split else None   # the D phase joins only what it forks itself
+        if split and self.parallel is not None and EARLY_ALLREDUCE[0]:
+            # overlap: the segmentation halves and netF have their complete gradient once stage A is through -- their
+            # bucket is all-reduced on a communication stream while the discriminator phase and the rest of the
+            # generator's backward run; the final all_reduce_grads() handles the other half
+            producers = list(stage_a[0]) + list(stage_a[2])
+            if b_cyc.on:
+                producers.append(b_cyc.stream)
+            self.parallel.all_reduce_early(self.optimizer, producers)
 
         # ---------------- D phase (L129-146): the three discriminator passes are independent chains of small
         # kernels -> real on the current stream, fake and interpolated on branch streams (ops.parallel_branch)

@@ -53,7 +53,10 @@ class UGANShp0Trainer(BaseTrainer):
         # data parallelism is one process per GPU (parallel.py), not nn.DataParallel: nothing to wrap here
         if self.phase == 'train':
             beta1, beta2 = self.beta1, self.beta2
-            self.optimizer = SGD(self.net.parameters(), lr=cfg.lr, momentum=0.9, weight_decay=cfg.weight_decay)
+            # early bucket: the segmentation halves and netF get their whole gradient in the generator's early backward
+            # stage (UGANConsisTrainer.train_step) -- a data-parallel run reduces them beside the discriminator phase
+            early = [p for n, p in self.net.named_parameters() if n.startswith(('seg_encoder.', 'seg_decoder.', 'netF.'))]
+            self.optimizer = SGD(self.net.parameters(), lr=cfg.lr, momentum=0.9, weight_decay=cfg.weight_decay, early=early)
             self.d_optimizer = Adam(self.D.parameters(), cfg.lr, [beta1, beta2], weight_decay=cfg.weight_decay)
             self.lr_sched = PolyLR([self.optimizer, self.d_optimizer], cfg.lr, cfg.max_epoch * cfg.num_iter_per_epoch)
 

@@ -354,7 +354,8 @@ def test_deterministic_mode_graph_equals_eager_bitwise(pkg):
             if opt is None:
                 return ""
             names, off = [], 0
-            for (name, p_) in net.named_parameters():
+            pname = {id(p_): k for k, p_ in net.named_parameters()}
+            for name, p_ in ((pname[id(q)], q) for q in opt.params):          # the flat buffers' own order
                 n = p_.numel()
                 c = int((d[off:off + n] > 0).sum())
                 if c:
