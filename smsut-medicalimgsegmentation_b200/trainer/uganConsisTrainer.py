@@ -42,8 +42,12 @@ SPLIT_SEG_ROWS = [os.environ.get("SMSUT_SPLIT_SEG_ROWS", "1") != "0"]
 # D(x_real) and D(G(x).detach()) of the D phase as one 2B-slice pass (train_step); measured: see DESIGN.md
 BATCH_D_REAL_FAKE = [os.environ.get("SMSUT_BATCH_D", "0") != "0"]
 
-# data-parallel runs: all-reduce the early gradient bucket beside the discriminator phase (train_step)
-EARLY_ALLREDUCE = [os.environ.get("SMSUT_EARLY_ALLREDUCE", "1") != "0"]
+# data-parallel runs: all-reduce the early gradient bucket (segmentation halves + netF) on a communication stream beside
+# the discriminator phase (train_step).  Built, correct (2-rank gloo test, NCCL parity check of bench.py) and MEASURED
+# SLOWER on 2 x B200: 10.76 ms / step with the overlapped bucket against 10.31 ms with one all-reduce after the backward
+# (N = 1: 10.22 ms) -- the collective's CTAs sit on SMs through the busiest window of the iteration, and every NCCL call
+# shares one stream, so the discriminator's all-reduce queues behind it.  Off by default (SMSUT_EARLY_ALLREDUCE=1).
+EARLY_ALLREDUCE = [os.environ.get("SMSUT_EARLY_ALLREDUCE", "0") != "0"]
 
 LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
 

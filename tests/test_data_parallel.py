@@ -82,9 +82,9 @@ def _gan_inputs(rank, bs=2, size=64):
     return x1, y, x2, alpha
 
 
-def _gan_worker(rank, world, port, outdir):
+def _gan_worker(rank, world, port, outdir, early="0"):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
-                      MASTER_PORT=str(port), SMSUT_ALLOW_CPU_TEST_DOUBLE="1")
+                      MASTER_PORT=str(port), SMSUT_ALLOW_CPU_TEST_DOUBLE="1", SMSUT_EARLY_ALLREDUCE=early)
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     torch.set_num_threads(2)
     import __graft_entry__ as g
@@ -118,17 +118,19 @@ def _gan_worker(rank, world, port, outdir):
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_ugan_consis_step_equals_single_process_on_global_batch(tmp_path):
+@pytest.mark.parametrize("early", ["0", "1"])
+def test_two_rank_ugan_consis_step_equals_single_process_on_global_batch(tmp_path, early):
     """The headline path at world_size 2 (gloo, fp32 test double): per-rank 2 labelled + 2 unlabelled slices, the two
     flat-gradient all-reduces and the Dice-statistic all-reduces inside both Dice/CE losses (segmentation and
     consistency) -- including the staged generator backward, whose first stage runs before the D phase -- against the
     oracle's single-process iteration on the global batch [lb0, lb1, ul0, ul1] (what nn.DataParallel computes).
-    Teacher-forced across D's Adam step like tests/test_host_logic.py."""
+    Teacher-forced across D's Adam step like tests/test_host_logic.py.  early = "1": the opt-in overlapped all-reduce of
+    the early gradient bucket (SMSUT_EARLY_ALLREDUCE, trainer/uganConsisTrainer.py) must give the same step."""
     sys.path.insert(0, ROOT)
     from oracle import smsut_oracle as O
     ctx = mp.get_context("spawn")
-    port = 29900 + os.getpid() % 90
-    procs = [ctx.Process(target=_gan_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    port = 29900 + os.getpid() % 90 + (100 if early == "1" else 0)
+    procs = [ctx.Process(target=_gan_worker, args=(r, 2, port, str(tmp_path), early)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
