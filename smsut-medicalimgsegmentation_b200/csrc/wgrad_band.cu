@@ -38,6 +38,8 @@ struct WgradBandParams {
   uint32_t tmem_cols;
   int dbg_noepi;   // development: skip the atomics (SMSUT_WGRAD_NOEPI=1)
   int stack;       // N-stacked issue: one UMMA covers all vertical taps of an x row (see the MMA issuer)
+  int multi;       // one MMA-issuing warp per vertical tap (see the kernel)
+  int m64;         // M = 64 UMMAs (16-channel x chunks, KS <= 3): 4 horizontal-tap blocks instead of 8 -> half the A bytes
   int tap_major;   // dw is the tap-major scratch [tap][cout_total][cin_total]: lanes = contiguous channels
   int cout_total;
   float* dw;
@@ -75,17 +77,22 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const int nrows = h_end - h_begin;
   const int nrows_in = nrows + 2 * p.r;
   const int nslots = p.nslots;
+  // MMA-issuing warps: one per vertical tap (warps 1 .. KS; warps 2.. are the epilogue warps, idle until the strip ends).
+  // A UMMA of this kernel is tiny (N = 16..64 columns, K = 16 pixels) and one thread issues ~1 per 75 cycles
+  // (descriptor arithmetic + the issue itself): with a single issuer the 8 * KS UMMAs of a 128-pixel row take longer
+  // than the row's HBM time.  The vertical taps own disjoint accumulators, so each gets its own in-order issuer.
+  const int ni = p.multi ? KS : 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
     tma_prefetch_desc(&map_dy);
     for (int s = 0; s < nslots; ++s) {
       mbar_init(&x_full[s], 1);
-      mbar_init(&x_empty[s], 1);
+      mbar_init(&x_empty[s], (uint32_t)ni);      // every issuing warp releases every row slot once per use
       mbar_init(&d_full[s], 1);
-      mbar_init(&d_empty[s], 1);
+      mbar_init(&d_empty[s], (uint32_t)ni);
     }
-    mbar_init(&acc_full, 1);
+    mbar_init(&acc_full, (uint32_t)ni);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -119,12 +126,12 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || (p.multi && warp <= KS)) {
+    // ===================== MMA issuer(s) =====================
     // A = x slot, MN-major, M = (tx, ci): M-blocks of xcc channels one pixel row apart (LBO = pitch);
     // B = dy slot, MN-major, N = dcc;  K = pixels (16 per UMMA)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(p.dcc >> 3) << 17) | ((128u >> 4) << 24);
+                           ((uint32_t)(p.dcc >> 3) << 17) | (((p.m64 ? 64u : 128u) >> 4) << 24);
     const uint64_t a_hi = make_smem_desc(0, p.x_pitch, 8u * p.x_pitch, p.x_layout) & 0xFFFFFFFFFFFF0000ull;
     const uint64_t b_hi = make_smem_desc(0, 0, 8u * p.d_pitch, p.d_layout) & 0xFFFFFFFFFFFF0000ull;
     const uint32_t x_base = smem_base >> 4, d_base = (smem_base + p.d_base_off) >> 4;
@@ -185,6 +192,34 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         if (j == nrows_in - 1) umma_commit_e(&acc_full, el);
         if (++xslot == nslots) { xslot = 0; xphase ^= 1u; }
       }
+    } else if (p.multi) {
+      // issuer of vertical tap ty: dy row i meets x row i + ty (ring slot (i + ty) % nslots); it waits for exactly those
+      // two rows, accumulates into its own TMEM columns and releases both slots.  x rows j < ty are never read by this
+      // issuer: it arrives for them up front so that every slot sees `ni` arrivals per use.
+      const int ty = warp - 1;
+      if (el) for (int j = 0; j < ty; ++j) mbar_arrive(&x_empty[j]);
+      int xslot = ty, dslot = 0;
+      uint32_t xphase = 0, dphase = 0;
+      for (int i = 0; i < nrows; ++i) {
+        mbar_wait(&x_full[xslot], xphase);
+        mbar_wait(&d_full[dslot], dphase);
+        tc_fence_after();
+        const uint32_t b0 = d_base + (uint32_t)dslot * dslot_u;
+        const uint32_t a0 = x_base + (uint32_t)xslot * xslot_u;
+        for (int g = 0; g < groups; ++g) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((ty * groups + g) * p.dcc);
+          const uint32_t ag = a0 + (uint32_t)g * grp_u;
+#pragma unroll 4
+          for (int k = 0; k < kchunks; ++k)
+            umma_bf16_e(d_tmem, a_hi | (uint64_t)((ag + k * xk_u) & 0x3FFFu),
+                        b_hi | (uint64_t)((b0 + k * dk_u) & 0x3FFFu), idesc, (i | k) != 0 ? 1u : 0u, el);
+        }
+        umma_commit_e(&x_empty[xslot], el);
+        umma_commit_e(&d_empty[dslot], el);
+        if (i == nrows - 1) umma_commit_e(&acc_full, el);
+        if (++xslot == nslots) { xslot = 0; xphase ^= 1u; }
+        if (++dslot == nslots) { dslot = 0; dphase ^= 1u; }
+      }
     } else {
     int rows_ready = 0, ready_slot = 0, base_slot = 0, dslot = 0;
     uint32_t ready_phase = 0, dphase = 0;
@@ -219,11 +254,15 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (++dslot == nslots) { dslot = 0; dphase ^= 1u; }
     }
     }
-  } else {
+  }
+  if (warp >= 2) {
     // ===================== epilogue: D_{ty,g}[(tx, ci)][co] -> atomics into dW[co][ci_off + ci][ty][tx] ==========
+    // M = 128: accumulator row (tx, ci) = TMEM lane.  M = 64 (cta_group::1): row m sits in lane (m & 15) + 32 * (m >> 4),
+    // i.e. lanes 0..15 of warp quarter q hold horizontal tap q's 16 channels and lanes 16..31 hold nothing
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int txl = row / p.xcc, cil = row - txl * p.xcc;
+    const int txl = p.m64 ? (lane < 16 ? q : p.tx_per_group) : row / p.xcc;
+    const int cil = p.m64 ? (lane & 15) : row - txl * p.xcc;
     const int ci = xch * p.xcc + cil;
     mbar_wait(&acc_full, 0);
     tc_fence_after();
@@ -295,7 +334,16 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   p.tw = tw; p.kchunks = tw / 16; p.wtiles = a->w / tw;
   p.xcc = chunk_of(a->x_c); p.dcc = chunk_of(a->dy_c);
   p.xchunks = a->x_c / p.xcc; p.dchunks = a->dy_c / p.dcc;
-  p.tx_per_group = 128 / p.xcc;
+  {
+    // M = 64 for the 16-channel chunks of the 1x1 / 3x3 layers: the MN-major A operand of a UMMA is M x 16 pixels, and
+    // with M = 128 = 8 horizontal-tap blocks only KS of them are taps -- the tensor pipe's shared-memory reads of A
+    // (4 KB per UMMA, 24 UMMAs per 128-pixel row) bound the kernel.  M = 64 halves them.  SMSUT_WGRAD_M64=0: off.
+    const char* e = getenv("SMSUT_WGRAD_M64");      // read per call: the parity tests run both settings in one process
+    // Measured (B200, us per launch alone, M = 128 -> 64): 16->16 @256^2 53.5 -> 51.4, but 16->32 @128^2 35.7 -> 41.5
+    // (a 1-SM UMMA with M = 64 exposes the shared-memory read latency of A): only with 16 dy channels, or =2 everywhere.
+    p.m64 = (p.xcc == 16 && a->ksize * p.xcc <= 64 && !(e && e[0] == '0') && (p.dcc == 16 || (e && e[0] == '2'))) ? 1 : 0;
+  }
+  p.tx_per_group = (p.m64 ? 64 : 128) / p.xcc;
   p.groups = (a->ksize + p.tx_per_group - 1) / p.tx_per_group;
   p.x_pitch = (uint32_t)p.xcc * 2u; p.d_pitch = (uint32_t)p.dcc * 2u;
   p.x_layout = layout_for(p.xcc); p.d_layout = layout_for(p.dcc);
@@ -316,7 +364,9 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
     const char* e = getenv("SMSUT_WGRAD_STACK");
     // opt-in: measured SLOWER on B200 (16->16 @ 256x256: 88 us stacked vs 57 us; whole step 13.3 vs 12.1 ms) -- an
     // MN-major B operand gathered from three row slots 4 KB apart evidently costs more than the saved instructions
-    p.stack = (p.groups == 1 && a->ksize * p.dcc <= 256 && e && e[0] == '1') ? 1 : 0;
+    const char* em = getenv("SMSUT_WGRAD_MULTI");      // read per call (tests run both)
+    p.multi = (a->ksize > 1 && !(em && em[0] == '0')) ? 1 : 0;
+    p.stack = (p.groups == 1 && !p.m64 && !p.multi && a->ksize * p.dcc <= 256 && e && e[0] == '1') ? 1 : 0;
   }
   p.dw = a->dw;
   p.dw_q = det_shadow(a->dw);

@@ -168,6 +168,37 @@ def test_wgrad_warp_mma_kernel(ops, monkeypatch, cin, cout, h, w, n, ks, live):
     assert rel(grad, dw_ref) < 5e-3, rel(grad, dw_ref)
 
 
+@pytest.mark.parametrize("m64,multi", [("2", "1"), ("0", "1"), ("2", "0"), ("0", "0")])
+@pytest.mark.parametrize("cin,cout,h,w,n,ks,live", [
+    (16, 16, 256, 256, 2, 3, 16), (16, 32, 128, 128, 3, 3, 16), (16, 64, 24, 128, 2, 3, 16), (16, 16, 40, 128, 2, 3, 8),
+    (16, 32, 17, 128, 5, 1, 16), (16, 16, 64, 256, 1, 5, 5), (16, 16, 3, 128, 2, 5, 1), (32, 16, 128, 128, 2, 3, 32),
+    (32, 64, 2, 128, 2, 3, 32), (16, 16, 512, 512, 1, 3, 16)])
+def test_wgrad_band_kernel_variants(ops, monkeypatch, m64, multi, cin, cout, h, w, n, ks, live):
+    """wgrad_band_kernel with M = 64 UMMAs (16-channel x chunks of the 1x1 / 3x3 layers: accumulator rows in TMEM lanes
+    0..15 of each warp quarter) and with M = 128 (SMSUT_WGRAD_M64=0; 32-channel chunks and 5x5 always), with one
+    MMA-issuing warp per vertical tap and with a single issuer (SMSUT_WGRAD_MULTI=0), ragged and very short row
+    segments, zero-padded input channels, both destination layouts, vs torch.nn.grad.conv2d_weight."""
+    monkeypatch.setenv("SMSUT_WGRAD_M64", m64)
+    monkeypatch.setenv("SMSUT_WGRAD_MULTI", multi)
+    monkeypatch.delenv("SMSUT_WGRAD_HMMA", raising=False)
+    torch.manual_seed(17)
+    x = rnd(n, cin, h, w)
+    x[:, live:] = 0
+    dy = rnd(n, cout, h, w)
+    wt = rnd(cout, live, ks, ks, scale=0.1)
+    pw = make_pack(ops, wt)
+    assert pw.cin_pad == cin
+    dw_ref = torch.nn.grad.conv2d_weight(x[:, :live], wt.shape, dy, padding=ks // 2)
+    dw = ops.conv_wgrad([nhwc(x)], nhwc(dy), pw)                      # OIHW destination
+    assert rel(dw, dw_ref) < 5e-3, rel(dw, dw_ref)
+    grad = torch.zeros_like(wt)
+    sc = ops.WgradScratch([wt], [grad])
+    ops.conv_wgrad([nhwc(x)], nhwc(dy), pw, out=grad)                 # tap-major scratch, folded by unpack_wgrads
+    ops.side_join()
+    sc.flush()
+    assert rel(grad, dw_ref) < 5e-3, rel(grad, dw_ref)
+
+
 def test_convt_wgrad_tap_major_scratch(ops):
     x = rnd(2, 64, 32, 32, seed=6)
     wt = rnd(64, 32, 2, 2, scale=0.1)
