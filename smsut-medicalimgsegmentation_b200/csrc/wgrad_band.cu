@@ -39,12 +39,14 @@ struct WgradBandParams {
   int dbg_noepi;   // development: skip the atomics (SMSUT_WGRAD_NOEPI=1)
   int stack;       // N-stacked issue: one UMMA covers all vertical taps of an x row (see the MMA issuer)
   int multi;       // one MMA-issuing warp per vertical tap (see the kernel)
+  int csize;       // > 1: (csize, 1, 1) thread-block cluster whose CTAs sum their accumulators through DSMEM before the atomics
   int m64;         // M = 64 UMMAs (16-channel x chunks, KS <= 3): 4 horizontal-tap blocks instead of 8 -> half the A bytes
   int tap_major;   // dw is the tap-major scratch [tap][cout_total][cin_total]: lanes = contiguous channels
   int cout_total;
   float* dw;
   long long* dw_q;         // fixed-point shadow of dw in deterministic mode (common.cuh), else nullptr
   int cout, cin_total, ci_off, c_valid, taps;
+  long long* trace;        // development: clock stamps (SMSUT_WGRAD_TRACE=1), see wgrad_band_try
 };
 
 template <int KS>
@@ -82,6 +84,11 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   // (descriptor arithmetic + the issue itself): with a single issuer the 8 * KS UMMAs of a 128-pixel row take longer
   // than the row's HBM time.  The vertical taps own disjoint accumulators, so each gets its own in-order issuer.
   const int ni = p.multi ? KS : 1;
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 1024 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[512 + blockIdx.x * 4 + 0] = (long long)t;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -113,6 +120,8 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       uint32_t xph = 0, dph = 0;
       for (int j = 0; j < nrows_in; ++j) {
         mbar_wait(&x_empty[xs], xph ^ 1u);
+        if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && j < 64)
+          p.trace[j * 8 + 0] = clock64();
         mbar_arrive_expect_tx_e(&x_full[xs], (uint32_t)(p.tw + 2 * p.r) * p.x_pitch, el);
         tma_load_4d_e(smem_al + (size_t)xs * p.x_slot_bytes, &map_x, &x_full[xs], xch * p.xcc, w0 - p.r, h_begin - p.r + j,
                       n, el);
@@ -201,9 +210,13 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       int xslot = ty, dslot = 0;
       uint32_t xphase = 0, dphase = 0;
       for (int i = 0; i < nrows; ++i) {
+        const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && i < 64 &&
+                        (ty == 0 || ty == KS - 1);
+        if (tr) p.trace[i * 8 + (ty == 0 ? 1 : 4)] = clock64();
         mbar_wait(&x_full[xslot], xphase);
         mbar_wait(&d_full[dslot], dphase);
         tc_fence_after();
+        if (tr) p.trace[i * 8 + (ty == 0 ? 2 : 5)] = clock64();
         const uint32_t b0 = d_base + (uint32_t)dslot * dslot_u;
         const uint32_t a0 = x_base + (uint32_t)xslot * xslot_u;
         for (int g = 0; g < groups; ++g) {
@@ -217,6 +230,7 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         umma_commit_e(&x_empty[xslot], el);
         umma_commit_e(&d_empty[dslot], el);
         if (i == nrows - 1) umma_commit_e(&acc_full, el);
+        if (tr) p.trace[i * 8 + (ty == 0 ? 3 : 6)] = clock64();
         if (++xslot == nslots) { xslot = 0; xphase ^= 1u; }
         if (++dslot == nslots) { dslot = 0; dphase ^= 1u; }
       }
@@ -266,7 +280,24 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const int ci = xch * p.xcc + cil;
     mbar_wait(&acc_full, 0);
     tc_fence_after();
+    if (p.trace != nullptr && threadIdx.x == 64 && blockIdx.x < 1024 && blockIdx.y == 0 && blockIdx.z == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      p.trace[512 + blockIdx.x * 4 + 1] = (long long)t;       // main loop done, epilogue starts
+    }
     const int nch = (KS * p.groups * p.dcc) >> 4;
+    if (p.csize > 1) {
+      // cluster reduction, phase A: this CTA's accumulators -> its own shared memory as S[column][128 rows] fp32 (the
+      // row rings are dead: every MMA that read them completed before acc_full fired)
+      float* S = reinterpret_cast<float*>(smem_al);
+      for (int j = 0; j < nch; ++j) {
+        uint32_t raw[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) S[(size_t)(j * 16 + k) * 128 + row] = __uint_as_float(raw[k]);
+      }
+    } else
     for (int j = 0; j < nch; ++j) {
       uint32_t raw[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 16), raw);
@@ -289,8 +320,50 @@ wgrad_band_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
   }
 
+  if (p.csize > 1) {
+    // Phase B.  Every CTA of the wave adds its accumulators to the SAME KS x KS x Cin x Cout addresses: ~300 CTAs x 2 304
+    // fp32 atomics on 2 304 addresses for a 16 -> 16 layer, and the kernel is not complete until they have drained
+    // through the L2 atomic units -- measured 16-28 us of a 50-100 us launch (SMSUT_WGRAD_NOEPI=1).  The CTAs of a
+    // cluster therefore sum their partial tiles first: CTA `rank` finishes every csize-th column (its own and the
+    // peers' copies, read with ld.shared::cluster) and issues the atomics for it -- csize times fewer of them.
+    cluster_sync_all();
+    if (warp >= 2) {
+      const int ew = warp - 2;
+      const int rank = (int)cluster_ctarank();
+      const int ncols = KS * p.groups * p.dcc;
+      for (int col = rank + p.csize * ew; col < ncols; col += p.csize * 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t local = smem_base + (uint32_t)((col * 128 + lane * 4) * 4);
+        for (int c = 0; c < p.csize; ++c) {
+          const float4 t = dsmem_ld_f4(dsmem_addr(local, (uint32_t)c));
+          v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+        }
+        const int region = col / p.dcc, co = blockIdx.z * p.dcc + (col - region * p.dcc);
+        const int ty = region / p.groups, g = region - ty * p.groups;
+        if (co >= p.cout || p.dbg_noepi) continue;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int rw = lane * 4 + r4;
+          const int txl = p.m64 ? ((rw & 31) < 16 ? (rw >> 5) : p.tx_per_group) : rw / p.xcc;
+          const int cil = p.m64 ? (rw & 15) : rw - txl * p.xcc;
+          const int ci = blockIdx.y * p.xcc + cil, tx = g * p.tx_per_group + txl;
+          if (txl >= p.tx_per_group || tx >= KS || ci >= p.c_valid) continue;
+          const int tap = ty * KS + tx;
+          float* dst = p.tap_major ? p.dw + ((size_t)tap * p.cout_total + co) * p.cin_total + p.ci_off + ci
+                                   : p.dw + ((size_t)co * p.cin_total + p.ci_off + ci) * p.taps + tap;
+          acc_add(dst, p.dw_q != nullptr ? p.dw_q + (dst - p.dw) : nullptr, v[r4]);
+        }
+      }
+    }
+    cluster_sync_all();                 // no CTA leaves (or frees its shared memory) while a peer still reads it
+  }
   tc_fence_before();
   __syncthreads();
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 1024 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[512 + blockIdx.x * 4 + 2] = (long long)t;
+  }
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -386,7 +459,10 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   static int per_sm_knob = -1;
   if (per_sm_knob < 0) {
     const char* e = getenv("SMSUT_WGRAD_BAND_PER_SM");
-    per_sm_knob = e && atoi(e) > 0 ? atoi(e) : 2;   // side-stream kernel: SM-time over latency (3 -> 12.36, 2 -> 12.14 ms/step)
+    // side-stream kernel: SM-time over latency.  Single issuer: 3 -> 12.36, 2 -> 12.14 ms / step.  With one issuing warp
+    // per vertical tap the tensor pipe's shared-memory reads bound the main loop, so a second CTA per SM adds nothing to
+    // it but doubles the set-up, the atomics of the epilogue and the shared memory held: 2 -> 10.02, 1 -> 9.85 ms / step
+    per_sm_knob = e && atoi(e) > 0 ? atoi(e) : 1;
   }
   if (per_sm > per_sm_knob) per_sm = per_sm_knob;
   if (per_sm < 1) per_sm = 1;
@@ -411,6 +487,36 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
   if (rc) return rc;
 
   dim3 grid((unsigned)(a->n * p.wtiles * p.segs), (unsigned)p.xchunks, (unsigned)p.dchunks);
+  // cluster reduction of the accumulators before the atomics (see the kernel): clusters of 4 (2) CTAs along x when the
+  // staging tile fits the ring memory and the whole grid of clusters is still co-resident; SMSUT_WGRAD_CLUSTER=1: off
+  p.csize = 1;
+  {
+    static bool attrs_set = false;      // before the occupancy query: it must see the opt-in shared-memory size
+    if (!attrs_set) {
+      SMSUT_CUDA_OK(cudaFuncSetAttribute(wgrad_band_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SMSUT_CUDA_OK(cudaFuncSetAttribute(wgrad_band_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      SMSUT_CUDA_OK(cudaFuncSetAttribute(wgrad_band_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attrs_set = true;
+    }
+    const char* e = getenv("SMSUT_WGRAD_CLUSTER");      // read per call (tests run both)
+    const int want = e ? atoi(e) : 4;
+    const size_t stage = (size_t)a->ksize * p.groups * p.dcc * 128 * sizeof(float);
+    for (int c = want > 4 ? 4 : want; c > 1 && p.csize == 1; c >>= 1) {
+      if (grid.x % (unsigned)c != 0 || stage + 1024 > smem) continue;
+      int fit = 0;
+      if (a->ksize == 1) fit = max_active_clusters_x(wgrad_band_kernel<1>, dim3(kWbThreads), smem, (unsigned)c);
+      if (a->ksize == 3) fit = max_active_clusters_x(wgrad_band_kernel<3>, dim3(kWbThreads), smem, (unsigned)c);
+      if (a->ksize == 5) fit = max_active_clusters_x(wgrad_band_kernel<5>, dim3(kWbThreads), smem, (unsigned)c);
+      if ((long long)fit * c >= (long long)grid.x * grid.y * grid.z) p.csize = c;
+    }
+  }
+  static long long* trace_dev = nullptr;
+  const bool tracing = getenv("SMSUT_WGRAD_TRACE") != nullptr;
+  if (tracing) {
+    if (!trace_dev) cudaMalloc(&trace_dev, (512 + 4096) * sizeof(long long));
+    cudaMemsetAsync(trace_dev, 0, (512 + 4096) * sizeof(long long), stream);
+    p.trace = trace_dev;
+  }
   bool launched = false;
 #define WB_CASE(KS_)                                                                                               \
   if (!launched && a->ksize == KS_) {                                                                              \
@@ -419,12 +525,42 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
       SMSUT_CUDA_OK(cudaFuncSetAttribute(wgrad_band_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    launch_pdl(wgrad_band_kernel<KS_>, grid, kWbThreads, smem, stream, map_x, map_dy, p);                                  \
+    if (p.csize > 1)                                                                                               \
+      launch_cluster_x(wgrad_band_kernel<KS_>, grid, kWbThreads, smem, stream, (unsigned)p.csize, map_x, map_dy, p);   \
+    else                                                                                                           \
+      launch_pdl(wgrad_band_kernel<KS_>, grid, kWbThreads, smem, stream, map_x, map_dy, p);                          \
     launched = true;                                                                                               \
   }
   WB_CASE(1) WB_CASE(3) WB_CASE(5)
 #undef WB_CASE
   count_launch();
+  if (tracing) {
+    // development: per-row clock64 stamps of CTA 0 (producer; first and last issuer) and per-CTA globaltimer stamps
+    static long long host[512 + 4096];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(host, trace_dev, sizeof(host), cudaMemcpyDeviceToHost);
+    const long long t0 = host[0];
+    fprintf(stderr, "wgrad band trace ks=%d xcc=%d dcc=%d w=%d rows=%d slots=%d grid=%u,%u,%u smem=%zu m64=%d multi=%d\n", p.ks,
+            p.xcc, p.dcc, p.w, p.rows_per_seg, p.nslots, grid.x, grid.y, grid.z, smem, p.m64, p.multi);
+    fprintf(stderr, " row | tma slot free | ty0: top  ready  issued | tyL: top  ready  issued\n");
+    for (int i = 0; i < 64 && i < p.rows_per_seg + 2 * p.r; ++i)
+      fprintf(stderr, " %3d | %8lld | %8lld %8lld %8lld | %8lld %8lld %8lld\n", i, host[i * 8] - t0, host[i * 8 + 1] - t0,
+              host[i * 8 + 2] - t0, host[i * 8 + 3] - t0, host[i * 8 + 4] - t0, host[i * 8 + 5] - t0, host[i * 8 + 6] - t0);
+    const unsigned nc = grid.x < 1024 ? grid.x : 1024;
+    long long g0 = host[512];
+    for (unsigned c = 0; c < nc; ++c) if (host[512 + c * 4] < g0) g0 = host[512 + c * 4];
+    long long smax = 0, emax = 0, main_sum = 0, epi_sum = 0, epi_max = 0;
+    for (unsigned c = 0; c < nc; ++c) {
+      const long long st0 = host[512 + c * 4] - g0, ep = host[512 + c * 4 + 1] - g0, en = host[512 + c * 4 + 2] - g0;
+      if (st0 > smax) smax = st0;
+      if (en > emax) emax = en;
+      main_sum += ep - st0;
+      epi_sum += en - ep;
+      if (en - ep > epi_max) epi_max = en - ep;
+    }
+    fprintf(stderr, "CTAs %u: last start %lld ns, last end %lld ns; mean set-up + main loop %lld ns, mean epilogue %lld ns (max %lld)\n",
+            nc, smax, emax, main_sum / nc, epi_sum / nc, epi_max);
+  }
   int st = launch_status("wgrad_band_kernel");
   return st ? st : 1;
 }

@@ -166,6 +166,7 @@ class _Side:
     nxt = 0
     held = []
     used = []
+    defer = None        # list of (fn, keep, event) while weight-gradient launches are being deferred (defer_begin)
 
 
 def side_streams_enable(on=True, group=0):
@@ -196,6 +197,45 @@ def pending_attach(st):
             _branch_used.append(b)
 
 
+def defer_begin():
+    """From now on side_run() only QUEUES its launches (with an event that marks where their operands are ready); they
+    are issued by run_deferred().  Weight gradients are leaves of the dependency graph, so WHEN they run is free: the
+    trainer moves those of the generator's early backward out of the window it shares with the discriminator phase
+    (every SM busy) into the tail of the iteration (one latency-bound chain, SMs idle)."""
+    if _Side.active:
+        _Side.defer = []
+
+
+def defer_end():
+    """stop deferring; returns the queued launches for run_deferred()"""
+    items, _Side.defer = _Side.defer, None
+    return items or []
+
+
+def run_deferred(items, group=2):
+    """Issue the queued weight-gradient launches on side streams ordered after the CURRENT stream (so they start no
+    earlier than this point of the iteration) and after their own operands; the next side_join() waits for them."""
+    if not items:
+        return
+    main = torch.cuda.current_stream()
+    pool = _Side.streams.get((main.device_index, group))
+    if pool is None:
+        pool = [torch.cuda.Stream(device=main.device, priority=0) for _ in range(max(_Side.n_streams, 1))]
+        _Side.streams[(main.device_index, group)] = pool
+    started = set()
+    for i, (fn, keep, ev) in enumerate(items):
+        s = pool[i % len(pool)]
+        if i < len(pool) and id(s) not in started:
+            s.wait_stream(main)
+            started.add(id(s))
+        s.wait_event(ev)
+        with torch.cuda.stream(s):
+            fn()
+        if s not in _Side.used:
+            _Side.used.append(s)
+        _Side.held.append(keep)
+
+
 def side_run(fn, keep):
     """fn() on a side stream ordered after everything issued so far on the current stream (or inline when side
     streams are off).  `keep`: the tensors fn's kernels read."""
@@ -203,6 +243,11 @@ def side_run(fn, keep):
         fn()
         return
     main = torch.cuda.current_stream()
+    if _Side.defer is not None:
+        ev = torch.cuda.Event()
+        ev.record(main)
+        _Side.defer.append((fn, keep, ev))
+        return
     pool = _Side.streams.get((main.device_index, _Side.group))
     if pool is None:
         # lowest priority: the dgrad / norm chain on the forking streams is the critical path

@@ -48,6 +48,10 @@ BATCH_D_REAL_FAKE = [os.environ.get("SMSUT_BATCH_D", "0") != "0"]
 # (N = 1: 10.22 ms) -- the collective's CTAs sit on SMs through the busiest window of the iteration, and every NCCL call
 # shares one stream, so the discriminator's all-reduce queues behind it.  Off by default (SMSUT_EARLY_ALLREDUCE=1).
 EARLY_ALLREDUCE = [os.environ.get("SMSUT_EARLY_ALLREDUCE", "0") != "0"]
+# the weight-gradient kernels of stage A (the generator's early backward, beside the discriminator phase) are queued and
+# issued after the discriminator's backward instead: they then fill the SMs the latency-bound tail of the iteration
+# (D step -> D(G(x)) -> the first pass's translation-half backward) leaves idle (ops.defer_begin / run_deferred)
+DEFER_STAGE_A_WGRADS = [os.environ.get("SMSUT_DEFER_WGRAD", "1") != "0"]
 
 LOSS_KEYS = ('D_real', 'D_fake', 'D_cls', 'D_gp', 'G_fake', 'G_rec', 'G_cls', 'G_seg', 'G_semi', 'G_nce')
 
@@ -126,7 +130,10 @@ class UGANConsisTrainer(UGANShp0Trainer):
             g_partial = lambda_rec * g_loss_rec + lambda_seg * g_loss_seg + lambda_semi * g_loss_semi + 1.0 * g_loss_nce
             if split:
                 with Fn.accumulate_param_grads(join=False, side_group=1):
+                    if DEFER_STAGE_A_WGRADS[0] and not EARLY_ALLREDUCE[0]:
+                        ops.defer_begin()
                     g_partial.backward()
+                    deferred = ops.defer_end()
                 dx_fake_cyc = x_fake_c.grad
         stage_a = ops.pending_detach() if split else None   # the D phase joins only what it forks itself
         if split and self.parallel is not None and EARLY_ALLREDUCE[0]:
@@ -169,6 +176,12 @@ class UGANConsisTrainer(UGANShp0Trainer):
         # flush=False: G's weight-gradient scratch is being written by stage A; d_optimizer.step() folds D's own
         with Fn.accumulate_param_grads(flush=not split):   # wgrad kernels add straight into the flat gradient buffer
             d_loss.backward()
+        if split and deferred:
+            held = ops.pending_detach()                     # the D step's own join must not wait for them
+            ops.run_deferred(deferred)
+            late = ops.pending_detach()
+            ops.pending_attach(held)
+            stage_a = (stage_a[0] + late[0], stage_a[1] + late[1], stage_a[2] + late[2])
         if self.parallel is not None:
             self.parallel.all_reduce_grads(self.d_optimizer)
         self.d_optimizer.step()

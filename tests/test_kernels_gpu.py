@@ -168,18 +168,20 @@ def test_wgrad_warp_mma_kernel(ops, monkeypatch, cin, cout, h, w, n, ks, live):
     assert rel(grad, dw_ref) < 5e-3, rel(grad, dw_ref)
 
 
-@pytest.mark.parametrize("m64,multi", [("2", "1"), ("0", "1"), ("2", "0"), ("0", "0")])
+@pytest.mark.parametrize("m64,multi,cluster", [("2", "1", "4"), ("0", "1", "2"), ("2", "0", "4"), ("0", "0", "1"), ("1", "1", "1")])
 @pytest.mark.parametrize("cin,cout,h,w,n,ks,live", [
     (16, 16, 256, 256, 2, 3, 16), (16, 32, 128, 128, 3, 3, 16), (16, 64, 24, 128, 2, 3, 16), (16, 16, 40, 128, 2, 3, 8),
     (16, 32, 17, 128, 5, 1, 16), (16, 16, 64, 256, 1, 5, 5), (16, 16, 3, 128, 2, 5, 1), (32, 16, 128, 128, 2, 3, 32),
     (32, 64, 2, 128, 2, 3, 32), (16, 16, 512, 512, 1, 3, 16)])
-def test_wgrad_band_kernel_variants(ops, monkeypatch, m64, multi, cin, cout, h, w, n, ks, live):
+def test_wgrad_band_kernel_variants(ops, monkeypatch, m64, multi, cluster, cin, cout, h, w, n, ks, live):
     """wgrad_band_kernel with M = 64 UMMAs (16-channel x chunks of the 1x1 / 3x3 layers: accumulator rows in TMEM lanes
     0..15 of each warp quarter) and with M = 128 (SMSUT_WGRAD_M64=0; 32-channel chunks and 5x5 always), with one
-    MMA-issuing warp per vertical tap and with a single issuer (SMSUT_WGRAD_MULTI=0), ragged and very short row
-    segments, zero-padded input channels, both destination layouts, vs torch.nn.grad.conv2d_weight."""
+    MMA-issuing warp per vertical tap and with a single issuer (SMSUT_WGRAD_MULTI=0), with the accumulators of a
+    thread-block cluster summed through distributed shared memory before the atomics (SMSUT_WGRAD_CLUSTER=4 / 2) and
+    without (=1), ragged and very short row segments, zero-padded input channels, both destination layouts, vs torch.nn.grad.conv2d_weight."""
     monkeypatch.setenv("SMSUT_WGRAD_M64", m64)
     monkeypatch.setenv("SMSUT_WGRAD_MULTI", multi)
+    monkeypatch.setenv("SMSUT_WGRAD_CLUSTER", cluster)
     monkeypatch.delenv("SMSUT_WGRAD_HMMA", raising=False)
     torch.manual_seed(17)
     x = rnd(n, cin, h, w)
