@@ -357,6 +357,31 @@ int smsut_det_resolve(float* dst, int64_t count, smsut_stream_t stream);
 int smsut_augment_batch(const uint8_t* images, const uint8_t* labels, const int64_t* index, const float* params,
                         float* x_out, int64_t* y_out, int32_t n, int32_t h, int32_t w, smsut_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * coraNet losses (trainer/coraNetTrainer.py).  All tensors fp32 NHWC-flattened (npix, c),
+ * labels int64, accumulators zeroed by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+/* the (1 + nheads*nlab)-channel output -> nheads stacked (npix, 1 + nlab) tensors, head h = [channel 0, channels
+ * 1 + h*nlab .. (h+1)*nlab]: `torch.cat([out_back, out_h], dim=1)` of coraNetTrainer.py:279-297; the backward sums the
+ * background gradients of the heads */
+int smsut_heads_split_fwd(const float* z, float* heads, int64_t npix, int32_t nlab, int32_t nheads, smsut_stream_t stream);
+int smsut_heads_split_bwd(const float* dheads, float* dz, int64_t npix, int32_t nlab, int32_t nheads, smsut_stream_t stream);
+/* nn.CrossEntropyLoss(weight=cw[, reduction='none']) of coraNetTrainer.py:44-58: acc[0] += sum_p m_p cw[y_p] nll_p,
+ * acc[1] += sum_p cw[y_p], acc[2] += sum_p m_p  (cw == NULL: ones; mask == NULL: ones).  'mean' loss = acc[0] / acc[1];
+ * the masked certain-area loss `(CE_none * mask).sum() / (mask.sum() + 1e-16)` (:301-303) = acc[0] / (acc[2] + 1e-16).
+ * bwd: dz = gscale[0] * d(loss)/dz with the denominator chosen by mask_den */
+int smsut_wce_fwd(const float* z, const int64_t* y, const float* cw, const float* mask, float* acc, int64_t npix, int32_t c,
+                  smsut_stream_t stream);
+int smsut_wce_bwd(const float* z, const int64_t* y, const float* cw, const float* mask, const float* acc,
+                  const float* gscale, int32_t mask_den, float* dz, int64_t npix, int32_t c, smsut_stream_t stream);
+/* `(softmax_mse_loss(zs, zt) * m).sum() / (m.sum() + 1e-16)` of coraNetTrainer.py:137-149,331-337 with m = mask
+ * (invert = 0) or 1 - mask (invert = 1), mask (npix) broadcast over the classes: acc[0] += sum_p m_p sum_c (ps - pt)^2,
+ * acc[1] += sum_p m_p; bwd writes dzs (zt is a constant) */
+int smsut_softmax_mse_masked_fwd(const float* zs, const float* zt, const float* mask, int32_t invert, float* acc,
+                                 int64_t npix, int32_t c, smsut_stream_t stream);
+int smsut_softmax_mse_masked_bwd(const float* zs, const float* zt, const float* mask, int32_t invert, const float* acc,
+                                 const float* gscale, float* dzs, int64_t npix, int32_t c, smsut_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -579,6 +579,93 @@ def mean_teacher_step(sd, ema, opt_state, x, y, noise, lr, it, lambda_semi, warm
     return float(seg.detach()), float(semi.detach())
 
 
+# coraNet (trainer/coraNetTrainer.py).  The shipped config.py pairs n_label = 4 with the 2-class weight vectors of the
+# SAML configuration (config.py:82-88: `default_w = [1, 1]`, `w_con = [1, 5]`, `w_rad = [5, 1]`; the CHAOS vectors are
+# the commented alternatives) -- nn.CrossEntropyLoss(weight=2 values) raises on 5-class logits, so the trainer runs as
+# written only with matching vectors.  These are the CHAOS vectors of those comments.
+CORA_W = dict(default=[1.0, 1.0, 1.0, 1.0, 1.0], con=[1.0, 5.0, 5.0, 5.0, 5.0], rad=[5.0, 1.0, 1.0, 1.0, 1.0])
+
+
+def coranet_heads(out, n_label=4):
+    """coraNetTrainer.py:279-286: the (1 + 3 n_label)-channel output -> three (1 + n_label)-class heads that share the
+    background channel."""
+    back = out[:, :1]
+    return [torch.cat([back, out[:, 1 + h * n_label:1 + (h + 1) * n_label]], 1) for h in range(3)]
+
+
+def soft_dice_loss(x, y, batch_dice):
+    """misc/loss.py:39-63"""
+    p = F.softmax(x, 1)
+    oh = torch.zeros_like(p).scatter_(1, y.unsqueeze(1), 1.0)
+    dims = (0, 2, 3) if batch_dice else (2, 3)
+    tp = (p * oh).sum(dims); fp = (p * (1 - oh)).sum(dims); fn = ((1 - p) * oh).sum(dims)
+    dc = (2 * tp + 1e-5) / (2 * tp + fp + fn + 1e-5 + 1e-8)
+    return 1.0 - (dc[1:] if batch_dice else dc[:, 1:]).mean()
+
+
+def coranet_supervised(heads, y, w=CORA_W, weight_ce=0.5, weight_dc=0.5):
+    """coraNetTrainer.py:288-292 (and pre_epoch :485-488): (Dice+CE on head 0 + weighted CE on heads 1, 2) / 4"""
+    wt = lambda k: torch.tensor(w[k], dtype=heads[0].dtype, device=heads[0].device)
+    cedc = weight_dc * soft_dice_loss(heads[0], y, True) + weight_ce * F.cross_entropy(heads[0], y, weight=wt("default"))
+    con = F.cross_entropy(heads[1], y, weight=wt("con"))
+    rad = F.cross_entropy(heads[2], y, weight=wt("rad"))
+    return (cedc + con + rad) / 4, (cedc, con, rad)
+
+
+def coranet_unsupervised(heads, ema_heads, plab, mask, consistency_weight, w=CORA_W):
+    """coraNetTrainer.py:299-338: certain areas (pseudo label where heads 1 and 2 agreed: per-sample Dice + masked CE,
+    / 2) and uncertain areas (masked softmax-MSE against the EMA teacher's three heads, / 3)."""
+    wt = torch.tensor(w["default"], dtype=heads[0].dtype, device=heads[0].device)
+    dice2 = soft_dice_loss(heads[0], plab, False)
+    ce2 = (F.cross_entropy(heads[0], plab, weight=wt, reduction="none") * mask).sum() / (mask.sum() + 1e-16)
+    certain = (ce2 + dice2) / 2
+    inv = (1 - mask).unsqueeze(1)
+    consts = []
+    for hs, ht in zip(heads, ema_heads):
+        dist = (torch.softmax(hs, 1) - torch.softmax(ht, 1)) ** 2
+        consts.append(consistency_weight * ((dist * inv).sum() / (inv.sum() + 1e-16)))
+    return certain, sum(consts) / 3
+
+
+def coranet_pre_step(sd, ema, opt_state, img1, msk, lr, it):
+    """one iteration of pre_epoch (coraNetTrainer.py:436-499): only the labelled half reaches the loss"""
+    leaf = _leaf(sd)
+    heads = coranet_heads(unet_forward(leaf, img1))
+    loss, parts = coranet_supervised(heads, msk)
+    grads = dict(zip(leaf, torch.autograd.grad(loss, list(leaf.values()))))
+    sgd_update(sd, grads, opt_state, lr)
+    ema_update(ema, sd, ema_alpha(it))
+    return [float(loss.detach())] + [float(v.detach()) for v in parts], grads
+
+
+def coranet_train_step(sd, ema, opt_state, img1, msk, img2, plab2, mask, lr, it, consistency_weight, unsup_from=1000):
+    """one iteration of train_epoch (coraNetTrainer.py:244-352): supervised + certain + 0.1 * uncertain, the latter two
+    zeroed while it < 1000; SGD; EMA update."""
+    leaf = _leaf(sd)
+    sup, _ = coranet_supervised(coranet_heads(unet_forward(leaf, img1)), msk)
+    heads2 = coranet_heads(unet_forward(leaf, img2))
+    with torch.no_grad():
+        ema_heads = coranet_heads(unet_forward(ema, img2))
+    certain, uncertain = coranet_unsupervised(heads2, ema_heads, plab2, mask, consistency_weight)
+    if it < unsup_from:
+        certain, uncertain = torch.zeros((), device=img1.device), torch.zeros((), device=img1.device)
+    loss = sup + certain + uncertain * 0.1
+    grads = dict(zip(leaf, torch.autograd.grad(loss, list(leaf.values()), allow_unused=True)))
+    grads = {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in grads.items()}
+    sgd_update(sd, grads, opt_state, lr)
+    ema_update(ema, sd, ema_alpha(it))
+    return [float(sup.detach()), float(certain.detach()), float(uncertain.detach())], grads
+
+
+def coranet_pred_unlabel(sd, img):
+    """pred_unlabel (coraNetTrainer.py:177-226) on a batch: pseudo label = argmax of head 0, certainty mask = heads 1
+    and 2 agree"""
+    with torch.no_grad():
+        h = coranet_heads(unet_forward(sd, img))
+        p0, p1, p2 = (t.argmax(1) for t in h)
+    return p0, (p1 == p2).float()
+
+
 def cross_pse_step(sd1, sd2, st1, st2, x, y, lr, lambda_semi):
     """trainer/crossPseTrainer.py:96-131 (cross pseudo supervision): two U-Nets on the same 2*bs slices; Dice+CE of
     each on the labelled half, plus lambda * Dice+CE of each net's unlabelled-half logits against the OTHER net's

@@ -102,6 +102,12 @@ _PROTOS = {
     "smsut_dice_ce_bwd": [P, P, P, P, P, c_float, P, c_int64, c_int64, c_int, c_float, c_float, P],
     "smsut_softmax_mse_fwd": [P, P, P, c_int64, c_int, P],
     "smsut_softmax_mse_bwd": [P, P, P, P, c_int64, c_int, P],
+    "smsut_heads_split_fwd": [P, P, c_int64, c_int, c_int, P],
+    "smsut_heads_split_bwd": [P, P, c_int64, c_int, c_int, P],
+    "smsut_wce_fwd": [P, P, P, P, P, c_int64, c_int, P],
+    "smsut_wce_bwd": [P, P, P, P, P, P, c_int, P, c_int64, c_int, P],
+    "smsut_softmax_mse_masked_fwd": [P, P, P, c_int, P, c_int64, c_int, P],
+    "smsut_softmax_mse_masked_bwd": [P, P, P, c_int, P, P, P, c_int64, c_int, P],
     "smsut_argmax_c": [P, P, c_int64, c_int, P],
     "smsut_confusion_counts": [P, P, P, c_int64, c_int, P],
     "smsut_l1_fwd": [P, P, P, c_int64, c_float, P],

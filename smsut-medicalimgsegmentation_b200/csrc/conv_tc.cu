@@ -576,6 +576,10 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
 
   // channel chunk = largest of 64/32/16 dividing every source's channel count
   int cc = 64;
+  {
+    const char* e = getenv("SMSUT_TC_MAXCC");      // development: 32 / 16 = shorter K steps, more pipeline stages
+    if (e && (atoi(e) == 32 || atoi(e) == 16) && (ctot / atoi(e)) * 9 <= kMaxSteps) cc = atoi(e);
+  }
   for (int s = 0; s < a->nsrc; ++s)
     while (a->src_c[s] % cc != 0) cc >>= 1;
   p.cc = cc;

@@ -556,6 +556,57 @@ class SoftmaxMSEFn(Function):
         return ops.softmax_mse_bwd(zs, zt, _c(g).view(1)), None
 
 
+class HeadsSplitFn(Function):
+    """The three 5-class heads of coraNet's 13-channel output (trainer/coraNetTrainer.py:279-297): (npix, 1 + H*L) ->
+    (H, npix, 1 + L) with the background channel shared; backward sums its H gradients."""
+
+    @staticmethod
+    def forward(ctx, z, nlab, nheads):
+        ctx.dims = (nlab, nheads)
+        return ops.heads_split_fwd(z, nlab, nheads)
+
+    @staticmethod
+    def backward(ctx, d):
+        nlab, nheads = ctx.dims
+        return ops.heads_split_bwd(_c(d), nlab, nheads), None, None
+
+
+class WeightedCEFn(Function):
+    """nn.CrossEntropyLoss(weight=cw) on (npix, C) logits: 'mean' form sum w[y] nll / sum w[y] (mask None), or the
+    masked form `(CE(reduction='none') * mask).sum() / (mask.sum() + 1e-16)` (trainer/coraNetTrainer.py:44-58,301-303)"""
+
+    @staticmethod
+    def forward(ctx, z, y, cw, mask):
+        acc = ops.zeros(3, z.device)
+        ops.wce_fwd(z, y, cw, mask, acc)
+        ctx.save_for_backward(z, y, cw, mask, acc)
+        den = acc[2] + 1e-16 if mask is not None else acc[1]
+        return (acc[0] / den).view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        z, y, cw, mask, acc = ctx.saved_tensors
+        return ops.wce_bwd(z, y, cw, mask, acc, _c(g).view(1), mask is not None), None, None, None
+
+
+class SoftmaxMSEMaskedFn(Function):
+    """`(softmax_mse_loss(zs, zt) * m).sum() / (m.sum() + 1e-16)` with m = 1 - mask (invert) or mask, broadcast over the
+    classes (trainer/coraNetTrainer.py:137-149,331-337); gradient to zs only."""
+
+    @staticmethod
+    def forward(ctx, zs, zt, mask, invert):
+        acc = ops.zeros(2, zs.device)
+        ops.softmax_mse_masked_fwd(zs, zt, mask, invert, acc)
+        ctx.save_for_backward(zs, zt, mask, acc)
+        ctx.invert = invert
+        return (acc[0] / (acc[1] + 1e-16)).view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        zs, zt, mask, acc = ctx.saved_tensors
+        return ops.softmax_mse_masked_bwd(zs, zt, mask, ctx.invert, acc, _c(g).view(1)), None, None, None
+
+
 class L1MeanFn(Function):
     """mean |a - b| with gradient to a (g_loss_rec, trainer/uganConsisTrainer.py:162)"""
 

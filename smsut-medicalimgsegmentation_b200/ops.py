@@ -1015,6 +1015,52 @@ def softmax_mse_bwd(zs, zt, gscale):
     return d
 
 
+# ---- coraNet losses (csrc/coranet.cu; trainer/coraNetTrainer.py) --------------------------------------------------
+def heads_split_fwd(z, nlab, nheads):
+    """(npix, 1 + nheads*nlab) fp32 -> (nheads, npix, 1 + nlab): head h = [channel 0, channels 1 + h*nlab .. (h+1)*nlab]"""
+    npix, c = z.shape
+    assert c == 1 + nheads * nlab
+    out = torch.empty((nheads, npix, 1 + nlab), dtype=F32, device=z.device)
+    call("smsut_heads_split_fwd", _p(_chk(z, F32, "heads z")), _p(out), npix, nlab, nheads, _stream())
+    return out
+
+
+def heads_split_bwd(dheads, nlab, nheads):
+    npix = dheads.shape[1]
+    dz = torch.empty((npix, 1 + nheads * nlab), dtype=F32, device=dheads.device)
+    call("smsut_heads_split_bwd", _p(_chk(dheads, F32, "heads grad")), _p(dz), npix, nlab, nheads, _stream())
+    return dz
+
+
+def wce_fwd(z, y, cw, mask, acc):
+    """acc[0] += sum m*cw[y]*nll, acc[1] += sum cw[y], acc[2] += sum m (cw / mask None = ones)"""
+    npix, c = z.shape
+    call("smsut_wce_fwd", _p(_chk(z, F32, "wce z")), _p(y), _p(cw), _p(mask), _p(acc), npix, c, _stream())
+    resolve(acc)
+
+
+def wce_bwd(z, y, cw, mask, acc, gscale, mask_den):
+    d = torch.empty_like(z)
+    call("smsut_wce_bwd", _p(z), _p(y), _p(cw), _p(mask), _p(acc), _p(gscale), 1 if mask_den else 0, _p(d), z.shape[0],
+         z.shape[1], _stream())
+    return d
+
+
+def softmax_mse_masked_fwd(zs, zt, mask, invert, acc):
+    """acc[0] += sum_p m_p sum_c (softmax(zs) - softmax(zt))^2, acc[1] += sum_p m_p, m = 1 - mask if invert else mask"""
+    npix, c = zs.shape
+    call("smsut_softmax_mse_masked_fwd", _p(_chk(zs, F32, "mse zs")), _p(_chk(zt, F32, "mse zt")), _p(_chk(mask, F32, "mse mask")),
+         1 if invert else 0, _p(acc), npix, c, _stream())
+    resolve(acc)
+
+
+def softmax_mse_masked_bwd(zs, zt, mask, invert, acc, gscale):
+    d = torch.empty_like(zs)
+    call("smsut_softmax_mse_masked_bwd", _p(zs), _p(zt), _p(mask), 1 if invert else 0, _p(acc), _p(gscale), _p(d),
+         zs.shape[0], zs.shape[1], _stream())
+    return d
+
+
 def argmax_c(logits):
     npix, c = logits.shape
     out = torch.empty(npix, dtype=torch.int64, device=logits.device)

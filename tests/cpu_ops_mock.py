@@ -559,3 +559,47 @@ def softmax_mse_bwd(zs, zt, gscale):
         z = zs.detach().clone().requires_grad_(True)
         ((torch.softmax(z, 1) - torch.softmax(zt.detach(), 1)) ** 2).mean().backward()
     return z.grad * gscale
+
+
+# ---- coraNet losses ------------------------------------------------------------------------------------------------
+def heads_split_fwd(z, nlab, nheads):
+    return torch.stack([torch.cat([z[:, :1], z[:, 1 + h * nlab:1 + (h + 1) * nlab]], 1) for h in range(nheads)])
+
+
+def heads_split_bwd(dheads, nlab, nheads):
+    return torch.cat([dheads[:, :, 0].sum(0)[:, None]] + [dheads[h, :, 1:] for h in range(nheads)], 1)
+
+
+def _wce_terms(z, y, cw, mask):
+    c = z.shape[1]
+    w = (cw if cw is not None else torch.ones(c, dtype=z.dtype))[y]
+    m = mask if mask is not None else torch.ones_like(w)
+    return w, m
+
+
+def wce_fwd(z, y, cw, mask, acc):
+    w, m = _wce_terms(z, y, cw, mask)
+    nll = F.cross_entropy(z, y, reduction="none")
+    acc[0] += (m * w * nll).sum()
+    acc[1] += w.sum()
+    acc[2] += m.sum()
+
+
+def wce_bwd(z, y, cw, mask, acc, gscale, mask_den):
+    w, m = _wce_terms(z, y, cw, mask)
+    den = acc[2] + 1e-16 if mask_den else acc[1]
+    return gscale * (m * w)[:, None] * (torch.softmax(z, 1) - F.one_hot(y, z.shape[1]).to(z.dtype)) / den
+
+
+def softmax_mse_masked_fwd(zs, zt, mask, invert, acc):
+    m = 1 - mask if invert else mask
+    acc[0] += (((torch.softmax(zs, 1) - torch.softmax(zt, 1)) ** 2).sum(1) * m).sum()
+    acc[1] += m.sum()
+
+
+def softmax_mse_masked_bwd(zs, zt, mask, invert, acc, gscale):
+    m = 1 - mask if invert else mask
+    with torch.enable_grad():
+        z = zs.detach().clone().requires_grad_(True)
+        ((((torch.softmax(z, 1) - torch.softmax(zt.detach(), 1)) ** 2).sum(1) * m).sum() / (acc[1] + 1e-16)).backward()
+    return z.grad * gscale

@@ -224,3 +224,34 @@ def test_mean_teacher_steps_match_reference_fixture():
             assert np.allclose(norms, f[f"{name}_norm{k}"], rtol=1e-4, atol=1e-5), (k, name)
             assert np.allclose(sums, f[f"{name}_sum{k}"], rtol=1e-3, atol=2e-3), (k, name)
     assert close(sd["decoder.fc.weight"], f["fc"], 1e-4) and close(ema["decoder.fc.weight"], f["ema_fc"], 1e-4)
+
+
+def test_coranet_iterations_match_reference_fixture():
+    """coraNetTrainer (trainer/coraNetTrainer.py): a pre_epoch iteration (:461-499), pred_unlabel (:186-207) and two
+    train_epoch iterations (:264-352, before / after the iter-1000 switch) against tests/golden/coranet.npz, which
+    make_golden_coranet.py produced with the reference's UNet and the trainer's own loss class lifted from its source"""
+    f = load("coranet")
+    n_out = int(f["n_out"])
+    sd, ema = O.make_weights(O.unet_shapes(out_ch=n_out), 71), O.make_weights(O.unet_shapes(out_ch=n_out), 72)
+    st = {}
+
+    def check(tag, losses, grads, rtol_l, rtol_g):
+        assert np.allclose(losses, f[tag + ".losses"], rtol=rtol_l, atol=1e-6), (tag, losses, f[tag + ".losses"])
+        for k, ref in zip(str(f[tag + ".names"]).split(","), f[tag + ".gnorms"].tolist()):
+            assert abs(grads[k].norm().item() - ref) < rtol_g * max(ref, 1e-3), (tag, k, grads[k].norm().item(), ref)
+        s = np.array([v.double().sum().item() for k, v in sd.items() if k in dict.fromkeys(str(f[tag + ".names"]).split(","))])
+        assert np.allclose(s, f[tag + ".sum_net"], rtol=1e-3, atol=5e-2), tag
+        e = np.array([v.double().sum().item() for k, v in ema.items() if k in dict.fromkeys(str(f[tag + ".names"]).split(","))])
+        assert np.allclose(e, f[tag + ".sum_ema"], rtol=1e-3, atol=5e-2), tag
+
+    img1, msk = O.synthetic_batch(2, 64, 81)
+    losses, grads = O.coranet_pre_step(sd, ema, st, img1, msk, 1e-2, 200)
+    check("pre", losses, grads, 2e-5, 1e-3)
+    imgu, _ = O.synthetic_batch(2, 64, 83)
+    plab, mask = O.coranet_pred_unlabel(sd, imgu)
+    assert (plab.numpy() != f["pred.plab"]).mean() < 1e-3 and (mask.numpy() != f["pred.mask"]).mean() < 1e-3
+    plab, mask = torch.as_tensor(f["pred.plab"]).long(), torch.as_tensor(f["pred.mask"]).float()
+    for tag, it in (("trn_early", 300), ("trn_late", 1500)):
+        img1, msk = O.synthetic_batch(2, 64, 91 + it)
+        losses, grads = O.coranet_train_step(sd, ema, st, img1, msk, imgu, plab, mask, 1e-2, it, 0.3)
+        check(tag, losses, grads, 2e-3, 2e-2)
