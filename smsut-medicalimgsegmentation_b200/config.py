@@ -54,4 +54,16 @@ weight_decay = 1e-3
 
 nce_layers = [5]
 
+# coraNet (config.py:80-95).  The reference ships the 2-class SAML vectors (`default_w = [1, 1]`, `w_con = [1, 5]`,
+# `w_rad = [5, 1]`) next to n_label = 4, for which nn.CrossEntropyLoss(weight) raises on the 5-class heads; the CHAOS
+# vectors of its comments are the ones consistent with n_label = 4.  Plain lists here: the trainer puts them on its
+# device.
+thres = 0.5
+default_w = [1., 1., 1., 1., 1.]
+w_con = [1., 5., 5., 5., 5.]
+w_rad = [5., 1., 1., 1., 1.]
+pre_epoch = 100
+cora_epoch = 200
+pred_step = 10
+
 expr_root = _os.environ.get('SMSUT_EXPR_ROOT', './smsut-out')      # the reference's expr_root (config.py:46); env override for tests

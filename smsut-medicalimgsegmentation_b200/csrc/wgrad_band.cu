@@ -488,7 +488,11 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
 
   dim3 grid((unsigned)(a->n * p.wtiles * p.segs), (unsigned)p.xchunks, (unsigned)p.dchunks);
   // cluster reduction of the accumulators before the atomics (see the kernel): clusters of 4 (2) CTAs along x when the
-  // staging tile fits the ring memory and the whole grid of clusters is still co-resident; SMSUT_WGRAD_CLUSTER=1: off
+  // staging tile fits the ring memory and the whole grid of clusters is still co-resident.  Opt-in
+  // (SMSUT_WGRAD_CLUSTER=4 | 2): correct (tests) but MEASURED SLOWER on the step -- 9.845 ms off, 9.999 ms with
+  // clusters of 2, 9.934 ms with 4; per launch 32->32 @128^2 gains (52.7 -> 39.2 us) while 16->32 loses (30.8 -> 39.0)
+  // and 16->16 @256^2 is unchanged (53.2 -> 52.9): with one CTA per SM the atomics' drain is no longer what bounds the
+  // launch, and cluster launches lose the freedom to place CTAs on any free SM beside the other streams' kernels.
   p.csize = 1;
   {
     static bool attrs_set = false;      // before the occupancy query: it must see the opt-in shared-memory size
@@ -499,7 +503,7 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
       attrs_set = true;
     }
     const char* e = getenv("SMSUT_WGRAD_CLUSTER");      // read per call (tests run both)
-    const int want = e ? atoi(e) : 4;
+    const int want = e ? atoi(e) : 1;
     const size_t stage = (size_t)a->ksize * p.groups * p.dcc * 128 * sizeof(float);
     for (int c = want > 4 ? 4 : want; c > 1 && p.csize == 1; c >>= 1) {
       if (grid.x % (unsigned)c != 0 || stage + 1024 > smem) continue;

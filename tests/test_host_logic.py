@@ -6,6 +6,7 @@ test_kernels_gpu.py / test_modules_gpu.py.)"""
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch
 
@@ -198,6 +199,63 @@ def test_mean_teacher_steps_match_oracle(exact):
             assert rel(p, sd[k]) < 1e-3, (it, k)
         for k, p in tr.ema.named_parameters():
             assert rel(p, ema[k]) < 1e-3, (it, k)
+
+
+def test_coranet_steps_match_oracle(exact, tmp_path, monkeypatch):
+    """coraNetTrainer: a pre_epoch iteration, pred_unlabel, train_epoch iterations before / after the
+    iter-1000 switch and the pre_best -> fit checkpoint hand-over, on the fp32 test double vs the oracle (which
+    tests/test_oracle.py pins to the fixture made from the reference's own UNet and loss class)."""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.coraNetTrainer import PseudoLabelSet, coraNetTrainer
+    monkeypatch.setattr(cfg, "expr_root", str(tmp_path))
+    tr = coraNetTrainer('train', SimpleNamespace(fold=0, expr_name='cora', input_size=64, model_id=None))
+    n_out = 3 * cfg.n_label + 1
+    sd, ema = O.make_weights(O.unet_shapes(out_ch=n_out), 71), O.make_weights(O.unet_shapes(out_ch=n_out), 72)
+    assert set(tr.net.state_dict()) == set(sd)
+    tr.net.load_state_dict(sd)
+    tr.ema.load_state_dict(ema)
+    st = {}
+    tr.iter = 200
+    img1, msk = O.synthetic_batch(2, 64, 81)
+    got = tr.pre_step(img1, msk).tolist()
+    ref, _ = O.coranet_pre_step(sd, ema, st, img1, msk, 1e-2, 200)
+    assert np.allclose(got, ref, rtol=1e-4, atol=1e-5), (got, ref)
+    for k, p in tr.net.named_parameters():
+        assert rel(p, sd[k]) < 1e-3, k
+    for k, p in tr.ema.named_parameters():
+        assert rel(p, ema[k]) < 1e-3, k
+    # pseudo labels and certainty mask of a batch of unlabelled slices
+    imgu, labu = O.synthetic_batch(2, 64, 83)
+    new_loader, plab_dice = tr.pred_unlabel([(imgu, labu, torch.zeros(2, dtype=torch.long), None)])
+    plab, mask = O.coranet_pred_unlabel(sd, imgu)
+    assert isinstance(new_loader, PseudoLabelSet) and new_loader.num == 2 and 0.0 <= plab_dice <= 1.0
+    assert (new_loader.plab != plab).float().mean() < 1e-3 and (new_loader.mask != mask).float().mean() < 1e-3
+    fg_p, fg_l = plab > 0, labu > 0
+    ref_dice = np.mean([2.0 * (fg_p[i] & fg_l[i]).sum().item() / max((fg_p[i].sum() + fg_l[i].sum()).item(), 1) for i in range(2)])
+    assert abs(plab_dice - ref_dice) < 1e-6
+    # train iterations: before (certain / uncertain terms are zeros) and after iter 1000
+    for it in (300, 1500):
+        tr.iter = it
+        img1, msk = O.synthetic_batch(2, 64, 91 + it)
+        got = tr.train_step(img1, msk, imgu, plab, mask, 0.3).tolist()
+        ref, _ = O.coranet_train_step(sd, ema, st, img1, msk, imgu, plab, mask, 1e-2, it, 0.3)
+        assert np.allclose(got, ref, rtol=2e-4, atol=1e-5), (it, got, ref)
+        for k, p in tr.net.named_parameters():
+            assert rel(p, sd[k]) < 2e-3, (it, k)
+        for k, p in tr.ema.named_parameters():
+            assert rel(p, ema[k]) < 2e-3, (it, k)
+    # prefit writes pre_best / pre_ema_best, fit of a fresh trainer starts from them
+    loaders = ([(img1, msk, torch.zeros(2, dtype=torch.long), None)], [(imgu, labu, torch.zeros(2, dtype=torch.long), None)],
+               [(imgu, labu, torch.zeros(2, dtype=torch.long), ["0_1_0", "0_1_1"])])
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    tr.prefit('inTurn', pre_epoch=1, iters_per_epoch=1, loaders=loaders)
+    ck = os.path.join(str(tmp_path), 'cora', tr.model_idx, 'ckpt')
+    assert {'pre_best.ckpt', 'pre_ema_best.ckpt', 'pre_last.ckpt', 'pre_ema_last.ckpt'} <= set(os.listdir(ck))
+    tr2 = coraNetTrainer('train', SimpleNamespace(fold=0, expr_name='cora', input_size=64, model_id=tr.model_idx))
+    tr2.fit('inTurn', max_epoch=1, iters_per_epoch=2, loaders=loaders)
+    assert {'best.ckpt', 'last.ckpt'} <= set(os.listdir(os.path.join(str(tmp_path), 'cora', tr2.model_idx, 'ckpt')))
+    assert tr2.iter == 2 and tr2.epoch == 1
 
 
 def test_unet_batchnorm_relu_matches_oracle(exact):
@@ -545,3 +603,28 @@ def test_cli_pseudo_entry_point(exact, tmp_path, monkeypatch, capsys, module):
     if module == "uganConsisTrainer":
         fk = Image.open(os.path.join(out, [f for f in files if f.endswith("fk.jpg")][0]))
         assert fk.size == (32 * (cfg.n_modal + 1), 32)
+
+
+def test_cli_coranet_pretrain_train_test(exact, tmp_path, monkeypatch, capsys):
+    """coraNetTrainer's entry points (trainer/coraNetTrainer.py:746-776): `-p pretrain` (the reference's commented
+    `prefit` line as a phase of its own) writes pre_best / pre_ema_best, `-p train -i 000` starts from them, predicts
+    the pseudo labels and trains, `-p test -i 001` reloads the result."""
+    import runpy
+    from smsut_b200 import config as cfg
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    monkeypatch.setattr(cfg, "input_size", 32)
+    monkeypatch.setattr(cfg, "expr_root", str(tmp_path))
+    name = "smsut_b200.trainer.coraNetTrainer"
+    base = ["coraNetTrainer.py", "-f", "0", "-nm", "cli"]
+    monkeypatch.setattr(sys, "argv", base + ["-p", "pretrain", "--epochs", "1", "--iters", "1"])
+    sys.modules.pop(name, None)
+    runpy.run_module(name, run_name="__main__")
+    ck = os.path.join(str(tmp_path), "cli", "000", "ckpt")
+    assert {"pre_best.ckpt", "pre_ema_best.ckpt", "pre_last.ckpt", "pre_ema_last.ckpt"} <= set(os.listdir(ck))
+    monkeypatch.setattr(sys, "argv", base + ["-p", "train", "-i", "000", "--epochs", "1", "--iters", "1"])
+    runpy.run_module(name, run_name="__main__")
+    assert {"best.ckpt", "last.ckpt"} <= set(os.listdir(os.path.join(str(tmp_path), "cli", "001", "ckpt")))
+    assert "Pseudo label dice" in capsys.readouterr().out
+    monkeypatch.setattr(sys, "argv", base + ["-p", "test", "-i", "001", "-wh", "last"])
+    runpy.run_module(name, run_name="__main__")
+    assert "dice:" in capsys.readouterr().out

@@ -746,3 +746,66 @@ print('ok')
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SMSUT_TC_KSPLIT="4"), capture_output=True,
                        text=True, timeout=300, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+# ---- coraNet losses (csrc/coranet.cu; trainer/coraNetTrainer.py) ---------------------------------------------------
+@pytest.mark.parametrize("npix,nlab", [(4096, 4), (50001, 4), (777, 1)])
+def test_coranet_heads_split(ops, npix, nlab):
+    """(npix, 1 + 3L) -> three (npix, 1 + L) heads sharing channel 0 (`torch.cat([out_back, out_h], 1)`,
+    coraNetTrainer.py:279-286), bit-exact; the backward sums the three background gradients."""
+    z = torch.randn(npix, 1 + 3 * nlab, device=DEV)
+    h = ops.heads_split_fwd(z, nlab, 3)
+    ref = torch.stack([torch.cat([z[:, :1], z[:, 1 + k * nlab:1 + (k + 1) * nlab]], 1) for k in range(3)])
+    assert torch.equal(h, ref)
+    d = torch.randn_like(h)
+    dz = ops.heads_split_bwd(d, nlab, 3)
+    zr = z.clone().requires_grad_(True)
+    torch.stack([torch.cat([zr[:, :1], zr[:, 1 + k * nlab:1 + (k + 1) * nlab]], 1) for k in range(3)]).backward(d)
+    assert rel(dz, zr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("npix,c,weighted,masked", [(65536, 5, True, False), (65536, 5, False, True), (30011, 5, True, True),
+                                                     (4099, 2, True, True), (131072, 5, False, False)])
+def test_coranet_weighted_masked_ce(pkg, ops, npix, c, weighted, masked):
+    """nn.CrossEntropyLoss(weight) in 'mean' form and the masked `(CE_none * mask).sum() / (mask.sum() + 1e-16)` form
+    (coraNetTrainer.py:44-58,301-303), forward and backward, vs PyTorch fp32"""
+    from smsut_b200 import functional as Fn
+    torch.manual_seed(npix)
+    z = (torch.randn(npix, c, device=DEV) * 3).requires_grad_(True)
+    y = torch.randint(0, c, (npix,), device=DEV)
+    cw = (torch.rand(c, device=DEV) * 4 + 0.5) if weighted else None
+    mask = (torch.rand(npix, device=DEV) > 0.4).float() if masked else None
+    loss = Fn.WeightedCEFn.apply(z, y, cw, mask)
+    zr = z.detach().clone().requires_grad_(True)
+    if masked:
+        ref = (F.cross_entropy(zr, y, weight=cw, reduction="none") * mask).sum() / (mask.sum() + 1e-16)
+    else:
+        ref = F.cross_entropy(zr, y, weight=cw)
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item())), (loss.item(), ref.item())
+    (loss * 1.7).backward()
+    (ref * 1.7).backward()
+    assert rel(z.grad, zr.grad) < 1e-5
+    if masked:      # an empty mask gives 0 / 1e-16 = 0 and a zero gradient, like the reference's expression
+        z2 = z.detach().clone().requires_grad_(True)
+        l0 = Fn.WeightedCEFn.apply(z2, y, cw, torch.zeros_like(mask))
+        l0.backward()
+        assert l0.item() == 0.0 and z2.grad.abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("npix,c,invert", [(65536, 5, True), (30011, 5, False), (4099, 2, True)])
+def test_coranet_masked_softmax_mse(pkg, ops, npix, c, invert):
+    """`(softmax_mse_loss(zs, zt) * m).sum() / (m.sum() + 1e-16)`, m = (1 - mask) broadcast over the classes
+    (coraNetTrainer.py:137-149,327-337), forward and gradient to the student logits, vs PyTorch fp32"""
+    from smsut_b200 import functional as Fn
+    torch.manual_seed(npix + 1)
+    zs = (torch.randn(npix, c, device=DEV) * 2).requires_grad_(True)
+    zt = torch.randn(npix, c, device=DEV) * 2
+    mask = (torch.rand(npix, device=DEV) > 0.6).float()
+    loss = Fn.SoftmaxMSEMaskedFn.apply(zs, zt, mask, invert)
+    zr = zs.detach().clone().requires_grad_(True)
+    m = (1 - mask) if invert else mask
+    ref = (((torch.softmax(zr, 1) - torch.softmax(zt, 1)) ** 2) * m[:, None]).sum() / (m.sum() + 1e-16)
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1e-3, abs(ref.item())), (loss.item(), ref.item())
+    (loss * 0.3).backward()
+    (ref * 0.3).backward()
+    assert rel(zs.grad, zr.grad) < 1e-5

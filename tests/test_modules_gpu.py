@@ -415,6 +415,78 @@ def test_mean_teacher_step_parity(pkg, size, bs):
     report(f"mean_teacher_{size}", dict(losses=rows))
 
 
+@pytest.mark.parametrize("size,bs", [(128, 2), (256, 2)])
+def test_coranet_steps_parity(pkg, size, bs):
+    """coraNetTrainer (trainer/coraNetTrainer.py): a pre_epoch iteration, pred_unlabel and
+    train_epoch iterations before / after the iter-1000 switch on the kernels vs the fp32 oracle, teacher-forced per
+    iteration; then the same train iteration as a CUDA-graph replay vs eager."""
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.coraNetTrainer import coraNetTrainer
+    tr = coraNetTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=size, model_id=None))
+    n_out = 3 * cfg.n_label + 1
+    tr.net.load_state_dict(to_dev(O.make_weights(O.unet_shapes(out_ch=n_out), 71)))
+    tr.ema.load_state_dict(to_dev(O.make_weights(O.unet_shapes(out_ch=n_out), 72)))
+    rep = {}
+
+    def snap():
+        return ({k: v.detach().clone() for k, v in tr.net.state_dict().items()},
+                {k: v.detach().clone() for k, v in tr.ema.state_dict().items()})
+
+    tr.iter = 200
+    img1, msk = O.synthetic_batch(bs, size, 81, device=DEV)
+    sd, ema = snap()
+    got = tr.pre_step(img1, msk).tolist()
+    ref, grads = O.coranet_pre_step(sd, ema, {}, img1, msk, 1e-2, 200)
+    rep["pre"] = dict(got=got, ref=ref, grad_cosine=cosine(list(tr.net.named_parameters()), grads))
+    for v, r in zip(got, ref):
+        assert abs(v - r) < 3e-2 * max(1.0, abs(r)), ("pre", got, ref)
+    assert rep["pre"]["grad_cosine"] > 0.9, rep["pre"]
+    for k, p in tr.ema.named_parameters():
+        assert rel(p, ema[k]) < 1e-4, k                      # the EMA rule on fp32 masters
+
+    imgu, labu = O.synthetic_batch(bs, size, 83, device=DEV)
+    sd, ema = snap()
+    new_loader, plab_dice = tr.pred_unlabel([(imgu, labu, torch.zeros(bs, dtype=torch.long), None)])
+    plab, mask = O.coranet_pred_unlabel(sd, imgu)
+    rep["pred"] = dict(plab_disagree=(new_loader.plab != plab).float().mean().item(),
+                       mask_disagree=(new_loader.mask != mask).float().mean().item(), plab_dice=plab_dice)
+    assert rep["pred"]["plab_disagree"] < 2e-2 and rep["pred"]["mask_disagree"] < 4e-2, rep["pred"]
+
+    for it in (300, 1500):
+        tr.iter = it
+        img1, msk = O.synthetic_batch(bs, size, 91 + it, device=DEV)
+        sd, ema = snap()
+        got = tr.train_step(img1, msk, imgu, plab, mask, 0.3).tolist()
+        ref, grads = O.coranet_train_step(sd, ema, {}, img1, msk, imgu, plab, mask, 1e-2, it, 0.3)
+        cos = cosine(list(tr.net.named_parameters()), grads)
+        rep[f"train_{it}"] = dict(got=got, ref=ref, grad_cosine=cos)
+        for v, r in zip(got, ref):
+            assert abs(v - r) < 3e-2 * max(1.0, abs(r)) + 1e-4, (it, got, ref)
+        assert cos > 0.9, (it, cos)
+    assert rep["train_1500"]["ref"][1] > 0 and rep["train_1500"]["ref"][2] > 0
+
+    # the epoch loop replays the captured iteration: same losses as the eager step from the same state
+    from smsut_b200.graph import StateSnapshot
+    tr.iter = 1500
+    keep = StateSnapshot(tr._live_tensors())
+    eager = tr.train_step(img1, msk, imgu, plab, mask, 0.3).tolist()
+    keep.restore()
+    from smsut_b200 import ops as _ops
+    _ops.param_generation[0] += 1         # master weights changed outside an optimizer step: refresh the bf16 packs
+    tr.iter = 1500
+    cw = torch.full((1,), 0.3, device=DEV)
+    tr.alpha = tr.host_alpha()
+    tr.alpha_dev.fill_(float(tr.alpha))
+    inputs = [img1, msk, imgu, plab, mask, cw, tr.alpha_dev]
+    step = tr.graphed(('cora_train', True), lambda *a: tr.train_step(*a, use_unsup=True), inputs)
+    assert step is not None
+    graph = step(*inputs).tolist()
+    rep["graph_vs_eager"] = dict(eager=eager, graph=graph)
+    for a, b in zip(eager, graph):
+        assert abs(a - b) < 5e-3 * max(1.0, abs(a)), (eager, graph)
+    report(f"coranet_{size}", rep)
+
+
 def test_cross_pse_step_parity(pkg):
     """crossPseTrainer (crossPseTrainer.py:96-131) at 256x256 on the kernels vs the fp32
     oracle, teacher-forced per iteration (both sides start each iteration from the kernel path's weights)."""
