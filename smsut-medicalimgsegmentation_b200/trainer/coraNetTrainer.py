@@ -51,6 +51,7 @@ class DiceAndCrossEntropyLoss(nn.Module):
         self.weight_ce, self.weight_dc, self.batch_dice, self.reduc = weight_ce, weight_dc, batch_dice, reduc
         w = cfg.default_w if weight is None else weight
         self.register_buffer('weight', torch.as_tensor(w, dtype=torch.float32))
+        self.unit_weight = all(float(v) == 1.0 for v in w)      # decided on the host: forward() must stay capturable
 
     def forward(self, x, y, mask=None):
         """x: (B, C, H, W) logits or the (B*H*W, C) rows of a head; y: (B, H, W) labels; mask: (B, H, W) floats"""
@@ -58,7 +59,7 @@ class DiceAndCrossEntropyLoss(nn.Module):
         logits = x if x.dim() == 2 else _flat_logits(x)
         yy = y.reshape(-1)
         yy = yy if yy.dtype == torch.int64 else yy.long()
-        if self.batch_dice and mask is None and bool((self.weight == 1).all()):
+        if self.batch_dice and mask is None and self.unit_weight:
             return Fn.DiceCEFn.apply(logits, yy, None, self.weight_ce, self.weight_dc)      # one fused pass (misc/loss.py)
         loss = 0.
         if self.weight_dc != 0:
