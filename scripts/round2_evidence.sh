@@ -21,6 +21,11 @@ ncu --set full --clock-control none --import-source on -k regex:'conv_band_kerne
     python scripts/conv_ncu.py > gpurun_out/ncu_conv.log 2>&1
 ncu -i gpurun_out/conv_${tag}.ncu-rep --page raw --csv > gpurun_out/conv_${tag}_raw.csv 2>/dev/null
 rm -f gpurun_out/conv_${tag}.ncu-rep
+python scripts/wgrad_ncu.py > /dev/null 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:'wgrad_band_kernel' -o gpurun_out/wgrad_${tag} -f \
+    python scripts/wgrad_ncu.py > gpurun_out/ncu_wgrad.log 2>&1
+ncu -i gpurun_out/wgrad_${tag}.ncu-rep --page raw --csv > gpurun_out/wgrad_${tag}_raw.csv 2>/dev/null
+rm -f gpurun_out/wgrad_${tag}.ncu-rep
 python - <<PY
 import json
 d=json.load(open('gpurun_out/bench_${tag}_1gpu.json'))
