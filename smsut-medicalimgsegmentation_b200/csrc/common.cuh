@@ -393,6 +393,30 @@ __device__ __forceinline__ void tma_load_4d_e(void* dst, const CUtensorMap* m, u
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(elected)
       : "memory");
 }
+// multicast variants for thread-block clusters: the TMA write and its complete_tx land at the same CTA-relative offsets
+// in every CTA of `mask`; the commit arrives on the same-offset mbarrier of every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc_e(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 uint16_t mask, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;\n\t"
+      "}" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_e(uint64_t* bar, uint16_t mask, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "h"(mask), "r"(elected)
+      : "memory");
+}
 // elect.sync predicate as an integer (1 in exactly one lane of the converged warp)
 __device__ __forceinline__ uint32_t elect_one_u32() {
   uint32_t pred = 0;

@@ -63,6 +63,8 @@ struct ConvTcParams {
   long long* stats_q;      // its fixed-point shadow in deterministic mode (common.cuh), else nullptr
   int fast;                // plain epilogue: bf16, one destination, every column valid, no bias / act / accumulate
   int ksplit;              // > 1: the K steps are split over a (1,1,ksplit) cluster, partial tiles reduced through DSMEM
+  int mc;                  // > 1: (mc,1,1) cluster of M tiles sharing one weight tile: CTA r loads rows [r, r+1) * bn / mc of
+                           // every B tile and multicasts them to all mc CTAs (1 / mc of the weight traffic from L2)
   // vertical-tap sharing (3x3, tile inside one image): a K step is one (dx, source, chunk); its A box holds th + 2 rows
   // fetched ONCE, the three vertical taps are UMMA descriptors started vt_row16 (16-byte units) = one image row apart,
   // and the stage carries the three taps' weight tiles (K coordinates vt_kstride apart)
@@ -178,7 +180,8 @@ template <bool KSPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
-               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ ConvTcParams p) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_ws,
+               const __grid_constant__ ConvTcParams p) {
   pdl_trigger();   // the next kernel may be scheduled; this one waits for its predecessor after its own set-up
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[8];
@@ -202,6 +205,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int col0 = blockIdx.y * p.bn;
   // split-K over the cluster: CTA `kr` of the (1, 1, ksplit) cluster owns K steps [ks_begin, ks_end)
   const bool split = KSPLIT && p.ksplit > 1;
+  const bool mcast = KSPLIT && p.mc > 1;
+  const uint32_t mc_rank = mcast ? cluster_ctarank() : 0u;
+  const uint16_t mc_mask = (uint16_t)((1u << (mcast ? p.mc : 1)) - 1u);
   const int kr = split ? (int)blockIdx.z : 0;
   const int ks_begin = split ? (kr * p.nsteps) / p.ksplit : 0;
   const int ks_end = split ? ((kr + 1) * p.nsteps) / p.ksplit : p.nsteps;
@@ -211,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tma_prefetch_desc(&map_w);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], mcast ? (uint32_t)p.mc : 1u);      // multicast: every CTA of the cluster releases every stage
     }
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
@@ -224,6 +230,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  if (mcast) cluster_sync_all();      // the peers' barriers exist before anything is multicast to / arrives on them
   pdl_wait();      // barriers, TMEM and descriptors are ready: now the predecessor's results are needed
 
   if (warp == 0) {
@@ -241,10 +248,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         uint8_t* b_dst = (uint8_t*)a_dst + p.a_bytes;
         const CUtensorMap* m = st.map == 0 ? &map_a0 : (st.map == 1 ? &map_a1 : (st.map == 2 ? &map_a2 : &map_a3));
         tma_load_4d_e(a_dst, m, &full_bar[stage], st.c0, w0 + st.dx - (p.dbg_rowshift ? 1 : 0), h0 + st.dy, n0, el);
+        if (mcast) {
+          // this CTA's slice of the weight tile(s) -> the same place in every CTA of the cluster; the peers' slices
+          // arrive the same way and complete this stage's barrier (expect_tx counts the WHOLE tile)
+          const uint32_t sl_rows = (uint32_t)p.bn / (uint32_t)p.mc;
+          const uint32_t sl_off = mc_rank * (p.b_bytes / (uint32_t)p.mc);
+          const int row0 = col0 + (int)(mc_rank * sl_rows);
+          tma_load_2d_mc_e(b_dst + sl_off, &map_ws, &full_bar[stage], st.k, row0, mc_mask, el);
+          if (p.vt) {
+            tma_load_2d_mc_e(b_dst + p.b_bytes + sl_off, &map_ws, &full_bar[stage], st.k + p.vt_kstride, row0, mc_mask, el);
+            tma_load_2d_mc_e(b_dst + 2 * p.b_bytes + sl_off, &map_ws, &full_bar[stage], st.k + 2 * p.vt_kstride, row0,
+                             mc_mask, el);
+          }
+        } else {
         tma_load_2d_e(b_dst, &map_w, &full_bar[stage], st.k, col0, el);
         if (p.vt) {
           tma_load_2d_e(b_dst + p.b_bytes, &map_w, &full_bar[stage], st.k + p.vt_kstride, col0, el);
           tma_load_2d_e(b_dst + 2 * p.b_bytes, &map_w, &full_bar[stage], st.k + 2 * p.vt_kstride, col0, el);
+        }
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
@@ -287,7 +308,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
       }
-      umma_commit_e(&empty_bar[stage], el);
+      if (mcast) umma_commit_mc_e(&empty_bar[stage], mc_mask, el);      // the stage is free in EVERY CTA only when all released it
+      else umma_commit_e(&empty_bar[stage], el);
       if (i == ks_end - 1) umma_commit_e(&tmem_full_bar, el);
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
     }
@@ -414,6 +436,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     cluster_sync_all();                 // no CTA leaves (or frees its shared memory) while a peer still reads it
   }
+  if (mcast) cluster_sync_all();       // no CTA leaves while a peer's commit may still arrive on its barriers
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -765,12 +788,32 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
     SMSUT_CHECK(a->out0_ld % 8 == 0 && a->out0_coff % 8 == 0 || a->ncols < 16, -1, "bf16 output pitch/offset must be multiples of 8");
 
   p.ksplit = ksplit;
+  // Weight-tile multicast (SMSUT_TC_MCAST=2|4, opt-in).  Every M tile of a layer reads the SAME weight tile from L2: at
+  // 32x32 / 16x16 it is 55-66 % of a CTA's operand bytes (ncu: 113 MB L2->SM for a 9 MB input at 256->128 @32x32).  A
+  // (mc,1,1) cluster of M tiles loads it once: CTA r fetches rows [r, r+1) * bn / mc and multicasts them.
+  p.mc = 1;
+  CUtensorMap map_ws = map_w;
+  {
+    const char* e = getenv("SMSUT_TC_MCAST");      // read per call: the parity tests run both settings in one process
+    const int want = e ? atoi(e) : 0;
+    for (int c = want > 4 ? 4 : want; c > 1 && p.mc == 1 && ksplit == 1; c >>= 1) {
+      if (m_tiles % c != 0 || bn % (8 * c) != 0 || ns < 2) continue;
+      const int fit = max_active_clusters_x(conv_tc_kernel<true>, dim3(kThreads), smem, (unsigned)c);
+      if (fit < 1) continue;
+      rc = make_mat_map(&map_ws, a->wpack, ktot, a->ncols_pad, ktot, cc, bn / c);
+      if (rc) return rc;
+      p.mc = c;
+    }
+  }
   dim3 grid((unsigned)m_tiles, (unsigned)(a->ncols_pad / bn), (unsigned)ksplit);
   if (ksplit > 1)
     launch_cluster_z(conv_tc_kernel<true>, grid, kThreads, smem, stream, (unsigned)ksplit, maps[0], maps[1], maps[2], maps[3],
-                     map_w, p);
+                     map_w, map_ws, p);
+  else if (p.mc > 1)
+    launch_cluster_x(conv_tc_kernel<true>, grid, kThreads, smem, stream, (unsigned)p.mc, maps[0], maps[1], maps[2], maps[3],
+                     map_w, map_ws, p);
   else
-    launch_pdl(conv_tc_kernel<false>, grid, kThreads, smem, stream, maps[0], maps[1], maps[2], maps[3], map_w, p);
+    launch_pdl(conv_tc_kernel<false>, grid, kThreads, smem, stream, maps[0], maps[1], maps[2], maps[3], map_w, map_ws, p);
   count_launch();
   return launch_status("conv_tc_kernel");
 }

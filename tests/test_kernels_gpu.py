@@ -114,6 +114,34 @@ def test_conv_tc_vertical_tap_sharing(ops, monkeypatch, cins, cout, h, n):
         assert rel(got[vt][2], got["0"][2]) < 1e-3
 
 
+@pytest.mark.parametrize("mc", ["2", "4"])
+@pytest.mark.parametrize("cins,cout,h,n,ks", [([32], 64, 64, 2, 3), ([64, 64], 64, 64, 2, 3), ([64], 128, 32, 2, 3),
+                                              ([128, 128], 128, 32, 4, 3), ([128], 256, 16, 4, 3), ([256], 256, 16, 6, 3),
+                                              ([256], 256, 8, 4, 3), ([64], 32, 64, 2, 1), ([256], 128, 32, 2, 1)])
+def test_conv_tc_weight_multicast(ops, monkeypatch, mc, cins, cout, h, n, ks):
+    """SMSUT_TC_MCAST=2|4: a cluster of M tiles of conv_tc_kernel loads each weight tile once -- CTA r fetches its slice
+    of the rows and TMA-multicasts it into every CTA of the cluster; the stage is released by a multicast commit of
+    every CTA.  Same results (bitwise: same accumulation order) as the un-clustered kernel, with and without the
+    vertical-tap sharing, incl. shapes where the cluster does not divide the tiles (falls back)."""
+    torch.manual_seed(31)
+    cin = sum(cins)
+    xs = [rnd(n, c, h, h) for c in cins]
+    wt = rnd(cout, cin, ks, ks, scale=(2.0 / (cin * ks * ks)) ** 0.5)
+    pw = make_pack(ops, wt)
+    x_cat, dy = torch.cat(xs, 1), rnd(n, cout, h, h)
+    y_ref = F.conv2d(x_cat, wt, padding=ks // 2)
+    dx_ref = torch.nn.grad.conv2d_input(x_cat.shape, wt, dy, padding=ks // 2)
+    got = {}
+    for key in ("0", mc):
+        monkeypatch.setenv("SMSUT_TC_MCAST", key)
+        y, st = ops.conv_fprop([nhwc(x) for x in xs], pw, want_stats=True)
+        dxs = ops.conv_dgrad(nhwc(dy), pw, splits=cins)
+        got[key] = (nchw(y), torch.cat([nchw(d) for d in dxs], 1), st)
+        assert rel(got[key][0], y_ref) < 1e-2 and rel(got[key][1], dx_ref) < 1e-2, key
+    assert torch.equal(got[mc][0], got["0"][0]) and torch.equal(got[mc][1], got["0"][1])
+    assert rel(got[mc][2], got["0"][2]) < 1e-5
+
+
 @pytest.mark.parametrize("cins,cout,h,n,ks", [([16], 16, 256, 1, 3), ([16, 16], 16, 128, 2, 3), ([32], 64, 64, 2, 3),
                                               ([64, 64], 64, 64, 2, 3), ([128], 256, 16, 2, 3), ([256], 256, 8, 4, 3),
                                               ([64], 32, 64, 2, 1)])
