@@ -791,6 +791,11 @@ static int conv_tc_impl(const smsut_conv_tc_args* a, cudaStream_t stream) {
   // Weight-tile multicast (SMSUT_TC_MCAST=2|4, opt-in).  Every M tile of a layer reads the SAME weight tile from L2: at
   // 32x32 / 16x16 it is 55-66 % of a CTA's operand bytes (ncu: 113 MB L2->SM for a 9 MB input at 256->128 @32x32).  A
   // (mc,1,1) cluster of M tiles loads it once: CTA r fetches rows [r, r+1) * bn / mc and multicasts them.
+  // MEASURED on B200 and OFF by default: bit-identical results, but every class is 1-4 us SLOWER per launch (64->64 @64x64
+  // 19.5 -> 23.6 us, 256->128 @32x32 19.4 -> 20.5 / 21.3 us, 256->256 @16x16 15.4 -> 16.2 / 16.4 us with clusters of
+  // 2 / 4) and the step 10.34 / 10.42 ms against 9.78 ms: at 32-512 tiles of 10-20 us these launches are bound by their
+  // fixed latencies (launch, set-up, first TMA round trip, epilogue), not by L2->SM bandwidth, and a cluster adds two
+  // cluster barriers, lock-step stage release across its CTAs and gang scheduling.
   p.mc = 1;
   CUtensorMap map_ws = map_w;
   {

@@ -462,9 +462,12 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
     // side-stream kernel: SM-time over latency.  Single issuer: 3 -> 12.36, 2 -> 12.14 ms / step.  With one issuing warp
     // per vertical tap the tensor pipe's shared-memory reads bound the main loop, so a second CTA per SM adds nothing to
     // it but doubles the set-up, the atomics of the epilogue and the shared memory held: 2 -> 10.02, 1 -> 9.85 ms / step
-    per_sm_knob = e && atoi(e) > 0 ? atoi(e) : 1;
+    per_sm_knob = e && atoi(e) > 0 ? atoi(e) : 0;
   }
-  if (per_sm > per_sm_knob) per_sm = per_sm_knob;
+  // default: one CTA per SM where every vertical tap has its own issuer, two for the single-issuer 1x1 layers (ncu launch
+  // list: their launch went from 19.6 to 30.5 us with one)
+  const int per_sm_cap = per_sm_knob > 0 ? per_sm_knob : (p.multi ? 1 : 2);
+  if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   if (per_sm < 1) per_sm = 1;
   int segs = (per_sm * sms) / base;
   if (segs < 1) segs = 1;
