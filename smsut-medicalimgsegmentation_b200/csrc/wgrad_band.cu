@@ -464,9 +464,10 @@ int wgrad_band_try(const smsut_wgrad_tc_args* a, cudaStream_t stream) {
     // it but doubles the set-up, the atomics of the epilogue and the shared memory held: 2 -> 10.02, 1 -> 9.85 ms / step
     per_sm_knob = e && atoi(e) > 0 ? atoi(e) : 0;
   }
-  // default: one CTA per SM where every vertical tap has its own issuer, two for the single-issuer 1x1 layers (ncu launch
-  // list: their launch went from 19.6 to 30.5 us with one)
-  const int per_sm_cap = per_sm_knob > 0 ? per_sm_knob : (p.multi ? 1 : 2);
+  // default: one CTA per SM.  The single-issuer 1x1 layers are slower ALONE that way (ncu launch list: 19.6 -> 30.5 us per
+  // launch), but two CTAs per SM for them cost the step 9.92 ms against 9.85 ms: what the iteration pays for a side-stream
+  // kernel is the SM time and shared memory it takes from the other chains, not its own duration.
+  const int per_sm_cap = per_sm_knob > 0 ? per_sm_knob : 1;
   if (per_sm > per_sm_cap) per_sm = per_sm_cap;
   if (per_sm < 1) per_sm = 1;
   int segs = (per_sm * sms) / base;
