@@ -159,7 +159,9 @@ class _Side:
     (captured as parallel branches of the step's CUDA graph), so they fill the SMs the narrow dgrad / norm kernels
     of the critical path leave idle.  Their operands are held until the join, so the caching allocator cannot hand
     the memory to a later kernel of the main stream while a side kernel still reads it."""
-    n_streams = int(os.environ.get("SMSUT_SIDE_STREAMS", "2"))
+    # side streams per pool.  Measured on B200 (ms per 16-slice step, round-2 final build): 1 -> 10.65, 2 -> 9.91,
+    # 3 -> 9.88, 4 -> 9.79 (twice, on two boxes), 6 -> 9.85, 8 -> 9.83
+    n_streams = int(os.environ.get("SMSUT_SIDE_STREAMS", "4"))
     streams = {}        # device index -> [streams]
     active = False
     group = 0
