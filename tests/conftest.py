@@ -26,3 +26,19 @@ def pytest_collection_modifyitems(config, items):
 def pkg():
     import __graft_entry__ as g
     return g.load_package()
+
+
+@pytest.fixture(autouse=True)
+def _cpu_tests_start_from_a_fixed_rng_state(request):
+    """Every CPU test starts from the same torch / numpy / random state, so a test's draws do not depend on which tests
+    ran before it (an unseeded draw once put a pre-activation within rounding of zero in one suite order only).  The GPU
+    tests keep the generator state they were measured with."""
+    if "gpu" not in request.keywords:
+        import random
+
+        import numpy as np
+        import torch
+        torch.manual_seed(20261019)
+        np.random.seed(20261019)
+        random.seed(20261019)
+    yield

@@ -72,7 +72,7 @@ def test_ugannce_forward_backward_matches_oracle(exact):
     assert rel(seg, rseg) < 1e-4 and rel(tsl, rtsl) < 1e-4 and rel(feats[0], rfeats[0]) < 1e-4
     # val_phase arity
     assert len(net(x, val_phase=True)) == 2
-    w = torch.randn_like(rseg)
+    w = torch.randn(rseg.shape, generator=torch.Generator().manual_seed(1))
     (seg * w).sum().add(tsl.sum()).add((feats[0] ** 3).sum()).backward()
     (rseg * w).sum().add(rtsl.sum()).add((rfeats[0] ** 3).sum()).backward()
     for k, p in net.named_parameters():
@@ -86,7 +86,10 @@ def test_discriminator_gradient_penalty_double_backward(exact):
     sd = O.make_weights(O.disc_shapes(64), 5)
     D.load_state_dict(sd)
     x, _ = O.synthetic_batch(3, 64, 6)
-    x_hat = (x + 0.1 * torch.randn_like(x)).requires_grad_(True)
+    # seeded noise: about one draw in twelve puts a pre-activation within rounding of zero, where the test double and the
+    # oracle (same fp32 arithmetic, different summation order) pick different LeakyReLU sides (error 1e-3 instead of 1e-6)
+    noise = torch.randn(x.shape, generator=torch.Generator().manual_seed(0))
+    x_hat = (x + 0.1 * noise).requires_grad_(True)
     out_src, out_cls = D(x_hat)
     gp = UGANShp0Trainer.gradient_penalty(None, out_src, x_hat)
     (gp * 10 + out_src.mean() + out_cls.pow(2).mean()).backward()
