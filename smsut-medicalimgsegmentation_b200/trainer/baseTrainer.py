@@ -1,8 +1,8 @@
 # -*- coding: utf-8 -*-
 """Counterpart of the reference's trainer/baseTrainer.py restricted to what the hot path needs: construction
 (device, network, Dice+CE loss: baseTrainer.py:35-62), sigmoid_rampup (:64-72), save_model (:120-123), the epoch
-loop `fit` (:125-201) over synthetic loaders, and a device-side validate_epoch (:207-244).  Experiment folders,
-TensorBoard, medpy metrics and PNG datasets are out of scope."""
+loop `fit` (:125-201) with its train / test meters and [TRN] / [TST] log lines, and a device-side validate_epoch
+(:207-244).  TensorBoard and the medpy surface metrics are out of scope."""
 import abc
 import os
 import time
@@ -15,6 +15,7 @@ from .. import config as cfg
 from .. import ops
 from ..data_loader import syntheticLoader as synlod
 from ..misc.loss import DiceAndCrossEntropyLoss
+from ..misc.utils import Meter
 
 
 class BaseTrainer(object):
@@ -41,6 +42,7 @@ class BaseTrainer(object):
         self.epoch = 0
         self.iter = 0
         self._graphs = {}       # lazily captured CUDA graphs of the iteration, keyed by its host-side mode switches
+        self._meter_queue = []  # (meter, device scalar, modality, slices) noted since the last meter_flush
 
     # ---- CUDA graph behind the epoch loops: `fit` runs the iteration the benchmark measures -------------------------
     def graph_enabled(self):
@@ -78,6 +80,30 @@ class BaseTrainer(object):
             ops.param_generation[0] += 1
             self._graphs[key] = g
         return g if g.accepts(inputs) else None
+
+    # ---- the epoch meters of `fit` (baseTrainer.py:147-199, misc/utils.py:58-160) -----------------------------------
+    def meter_note(self, meter, loss, modal_id, n):
+        """`meter.accumulate(*meter.collect_loss_by(loss.item(), m, n))` of the reference's loops (unetTrainer.py:75-76,
+        uganConsisTrainer.py:157-158, ...) without its device->host sync per iteration: the scalar stays on the device
+        (as a copy: a graph replay overwrites its outputs) until meter_flush."""
+        if meter is not None:
+            self._meter_queue.append((meter, loss.detach().reshape(()).clone(), int(modal_id), int(n)))
+
+    def meter_flush(self):
+        """hand everything noted since the last flush to its meter: ONE device->host copy"""
+        queue, self._meter_queue = self._meter_queue, []
+        if queue:
+            values = torch.stack([t for _, t, _, _ in queue]).tolist()
+            for (meter, _, modal_id, n), v in zip(queue, values):
+                meter.accumulate(*meter.collect_loss_by(v, modal_id, n))
+
+    @staticmethod
+    def make_meters():
+        """(train meter, test meter) of baseTrainer.py:147-151"""
+        min_better_keys = [f'loss_{i}' for i in range(cfg.n_modal)] + ['loss']
+        max_better_keys = [f'dice_{i}' for i in range(cfg.n_modal)] + ['dice']
+        return (Meter(min_better_keys=min_better_keys, max_better_keys=[], alpha=cfg.exp_alpha),
+                Meter(min_better_keys=min_better_keys, max_better_keys=max_better_keys, alpha=1.))
 
     @property
     def model_idx(self):
@@ -181,20 +207,44 @@ class BaseTrainer(object):
     def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None, loaders=None):
         """loaders: optional (labelled, unlabelled, test) loaders injected by the caller instead of make_loaders"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
-        best, best_epoch = -1.0, -1
-        for epoch in range(max_epoch or cfg.max_epoch):
-            tic = time.time()
-            self.train_epoch(train_lb_loader, train_ul_loader, None, num_iter=iters_per_epoch)
+        train_meter, test_meter = self.make_meters()
+        best_epoch = -1
+        n_epoch = max_epoch or cfg.max_epoch
+        tic = time.time()
+        for epoch in range(n_epoch):
+            train_meter.reset_cur()
+            self.train_epoch(train_lb_loader, train_ul_loader, train_meter, num_iter=iters_per_epoch)
             self._write_timing(time.time() - tic, iters_per_epoch or cfg.num_iter_per_epoch)
             self.epoch += 1
-            self.validate_epoch(test_loader)
-            dice = self.validate_dice()[0]['dice']        # the reference's model-selection metric (baseTrainer.py:176-180)
-            self.info('[TRN/TST] Epoch: %d(%d)/%d, elapsed: %.2fs, dice: %.4f' %
-                      (epoch, best_epoch, cfg.max_epoch, time.time() - tic, dice))
-            if dice >= best:
-                best, best_epoch = dice, epoch
+            tic = self.log_train_stage(train_meter, epoch, best_epoch, n_epoch, tic)
+            tic = self.test_stage(test_loader, test_meter, epoch, n_epoch, tic)
+            if test_meter.cur_values['dice'] >= test_meter.best_values['dice']:
                 self.save_model(prefix='best')
+                best_epoch = epoch
         self.save_model(prefix='last')
+        self.meters = (train_meter, test_meter)
+
+    def log_train_stage(self, train_meter, epoch, best_epoch, n_epoch, tic, tag=''):
+        """the train logs of an epoch (baseTrainer.py:158-172, without the TensorBoard scalars); returns the new tic"""
+        self.meter_flush()
+        train_meter.update_cur()
+        opt = getattr(self, 'optimizer', None) or getattr(self, 'optimizer1')      # crossPseTrainer.py:185-188
+        self.info('')
+        self.info(f"lr: {opt.param_groups[0]['lr']}.")
+        self.info('[TRN] %sEpoch: %d(%d)/%d, elapsed: %.2fs,' % (tag, epoch, best_epoch, n_epoch, time.time() - tic)
+                  + str(train_meter))
+        return time.time()
+
+    def test_stage(self, test_loader, test_meter, epoch, n_epoch, tic, tag=''):
+        """the test stage of an epoch (baseTrainer.py:177-193): per-modality loss from validate_epoch, Dice from the
+        modality-organ matrix -- the reference's model-selection metric; returns the new tic"""
+        test_meter.reset_cur()
+        self.validate_epoch(test_loader, meter=test_meter)
+        v = self.validate_dice()[0]
+        test_meter.accumulate(v, {k: 1. for k in v.keys()})
+        test_meter.update_cur()
+        self.info('[TST] %sEpoch: %d/%d, elapsed: %.2fs,' % (tag, epoch, n_epoch, time.time() - tic) + str(test_meter))
+        return time.time()
 
     def _write_timing(self, epoch_s, iters):
         """SMSUT_TIMING=<path>: per-epoch iteration timing as JSON (tests/test_parity_layers_gpu.py checks that the
@@ -301,6 +351,10 @@ class BaseTrainer(object):
     def segment(self, img):
         return self.net(img)
 
+    def validation_loss(self, out, msk, b):
+        """the loss validate_epoch reports per batch: Dice + CE of the segmentation logits (baseTrainer.py:228)"""
+        return self.loss(out, msk)
+
     def validate_epoch(self, loader, npys=None, meter=None, save_path=None):
         """Mean foreground Dice of argmax predictions over the loader (pads a ragged last batch to cfg.batch_size
         like baseTrainer.py:214-219); the confusion counts stay on the device."""
@@ -316,6 +370,10 @@ class BaseTrainer(object):
                 img = img.to(self.device, non_blocking=True)
                 msk = msk.to(self.device, non_blocking=True)
                 out = self.segment(img)[:b]
+                if meter is not None:
+                    # baseTrainer.py:224-231: the batch's Dice+CE under the modality of its first slice, weighted with
+                    # img.size(0) -- the PADDED batch size for a ragged last batch, as in the reference
+                    self.meter_note(meter, self.validation_loss(out, msk, b), mdl[0].item(), img.size(0))
                 # fp32 logits as (pixels, classes): zero-copy for the channels-last tensors the networks return
                 logits = out.permute(0, 2, 3, 1).reshape(-1, n_cls)
                 logits = logits if logits.is_contiguous() else logits.contiguous()
@@ -333,6 +391,7 @@ class BaseTrainer(object):
                             cv = vol_conf[keys[i0]] = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=self.device)
                         ops.confusion_counts(logits[i0 * h * w:i * h * w], msk[i0:i].reshape(-1), cv)
                         i0 = i
+        self.meter_flush()
         self.confusion = conf
         self.volume_confusion = vol_conf
         inter = conf.diagonal().double()

@@ -20,6 +20,7 @@ import argparse
 import os
 import random
 import sys
+import time
 from os.path import join as pjoin
 
 if __package__ in (None, ""):
@@ -170,7 +171,13 @@ class coraNetTrainer(BaseTrainer):
 
     def segment(self, img):
         """validate_epoch / test / pseudo read head 0 (:715-733): channels 0 .. n_label of the output"""
-        return self.net(img)[:, :cfg.n_label + 1]
+        out = self.net(img)
+        self._val_out = [out]           # for validation_loss (a list: not part of the trainer's live tensors)
+        return out[:, :cfg.n_label + 1]
+
+    def validation_loss(self, out, msk, b):
+        """(:715-731) validate_epoch reports the three-head supervised loss, not head 0's Dice + CE alone"""
+        return self.supervised_loss(self._val_out.pop()[:b], msk)[0]
 
     def supervised_loss(self, out, msk):
         h = self.heads(out)
@@ -291,10 +298,14 @@ class coraNetTrainer(BaseTrainer):
                 self.iter += 1
             else:
                 losses = self.pre_step(img1, msk)
+            # (:457,494-495) the iteration's loss under the labelled batch's modality; the reference weights it with the
+            # size of its concatenated labelled + unlabelled batch
+            self.meter_note(meter, losses[0], mdl1[0].item(), 2 * img1.size(0))
             if (i + 1) % self.log_step == 0:
                 tl, cd, lc, lr_ = losses.tolist()
                 self.info(f'Iter %d, global_iter: %d, train_loss: %.4f cedc_loss: %.4f, loss_con: %.4f, loss_rad: %.4f' %
                           (i, self.iter, tl, cd, lc, lr_))
+        self.meter_flush()
         return losses
 
     def train_epoch(self, lb_loader, ul_loader, new_loader, meter=None, num_iter=None):
@@ -324,33 +335,37 @@ class coraNetTrainer(BaseTrainer):
                 self.iter += 1
             else:
                 losses = self.train_step(img1, msk, img2, plab2, mask, consistency_weight)
+            if meter is not None:       # (:283,344-351) supervised + certain + 0.1 uncertain
+                self.meter_note(meter, losses[0] + losses[1] + 0.1 * losses[2], mdl1[0].item(),
+                                img1.size(0) + img2.size(0))
             if (i + 1) % self.log_step == 0:
                 sup, cer, unc = losses.tolist()
                 self.info(f'Iter %d, global_iter: %d, supervised_loss: %.4f, certain_loss: %.4f, uncertain_loss: %f' %
                           (i, self.iter, sup, cer, unc))
             for param_group in self.optimizer.param_groups:
                 param_group['lr'] = self.optimizer._lr_host = self.lr_sched.host_lr(self.iter)
+        self.meter_flush()
         return losses
 
     # ---- the two training phases -------------------------------------------------------------------------------------
-    def _validate(self, test_loader):
-        self.validate_epoch(test_loader)
-        return self.validate_dice()[0]['dice']
-
     def prefit(self, loader_type='inTurn', pre_epoch=None, iters_per_epoch=None, loaders=None):
         """(:526-602) supervised pre-training; keeps `pre_best` / `pre_ema_best` on the validation Dice and writes
         `pre_last` / `pre_ema_last` at the end"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
-        best, best_epoch = -1.0, -1
-        for epoch in range(pre_epoch if pre_epoch is not None else cfg.pre_epoch):
-            self.pre_epoch(train_lb_loader, train_ul_loader, None, num_iter=iters_per_epoch)
+        train_meter, test_meter = self.make_meters()
+        best_epoch = -1
+        n_epoch = pre_epoch if pre_epoch is not None else cfg.pre_epoch
+        tic = time.time()
+        for epoch in range(n_epoch):
+            train_meter.reset_cur()
+            self.pre_epoch(train_lb_loader, train_ul_loader, train_meter, num_iter=iters_per_epoch)
             self.epoch += 1
-            dice = self._validate(test_loader)
-            self.info('[TRN/TST] pre Epoch: %d(%d)/%d, dice: %.4f' % (epoch, best_epoch, cfg.pre_epoch, dice))
-            if dice >= best:
-                best, best_epoch = dice, epoch
+            tic = self.log_train_stage(train_meter, epoch, best_epoch, n_epoch, tic, tag='pre ')
+            tic = self.test_stage(test_loader, test_meter, epoch, n_epoch, tic, tag='pre ')
+            if test_meter.cur_values['dice'] >= test_meter.best_values['dice']:
                 self.save_model(prefix='pre_best')
                 self.save_ema_model(prefix='pre_ema_best')
+                best_epoch = epoch
         self.save_model(prefix='pre_last')
         self.save_ema_model(prefix='pre_ema_last')
 
@@ -358,22 +373,25 @@ class coraNetTrainer(BaseTrainer):
         """(:604-690) loads `pre_best` / `pre_ema_best` of run `model_id`, predicts the pseudo labels (again every
         cfg.pred_step epochs) and trains; `best` on the validation Dice, `last` at the end"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
-        best, best_epoch = -1.0, -1
+        train_meter, test_meter = self.make_meters()
+        best_epoch = -1
         self.load_model(self.model_id, 'pre_best')
         self.load_ema_model(self.model_id, 'pre_ema_best')
         self.model_idx = None       # this run gets its own directory (the reference allocates it at construction)
         new_loader, plab_dice = self.pred_unlabel(train_ul_loader)
         n_epoch = max_epoch if max_epoch is not None else cfg.cora_epoch
+        tic = time.time()
         for epoch in range(n_epoch):
             if epoch % cfg.pred_step == 0:
                 new_loader, plab_dice = self.pred_unlabel(train_ul_loader)
-            self.train_epoch(train_lb_loader, train_ul_loader, new_loader, None, num_iter=iters_per_epoch)
+            train_meter.reset_cur()
+            self.train_epoch(train_lb_loader, train_ul_loader, new_loader, train_meter, num_iter=iters_per_epoch)
             self.epoch += 1
-            dice = self._validate(test_loader)
-            self.info('[TRN/TST] Epoch: %d(%d)/%d, dice: %.4f' % (epoch, best_epoch, n_epoch, dice))
-            if dice >= best:
-                best, best_epoch = dice, epoch
+            tic = self.log_train_stage(train_meter, epoch, best_epoch, n_epoch, tic)
+            tic = self.test_stage(test_loader, test_meter, epoch, n_epoch, tic)
+            if test_meter.cur_values['dice'] >= test_meter.best_values['dice']:
                 self.save_model(prefix='best')
+                best_epoch = epoch
         self.save_model(prefix='last')
 
 

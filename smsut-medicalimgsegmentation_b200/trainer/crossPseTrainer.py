@@ -103,6 +103,9 @@ class crossPseTrainer(BaseTrainer):
                 self.iter += 1
             else:
                 losses = self.train_step(img, msk, lambda_semi)
+            # crossPseTrainer.py:106-119: both networks' supervised losses go to the same meter
+            self.meter_note(meter, losses[0], mdl1[0].item(), img.size(0))
+            self.meter_note(meter, losses[1], mdl1[0].item(), img.size(0))
             if (i + 1) % self.log_step == 0:
                 s1, s2, c1, c2 = losses.tolist()
                 self.info('Iter %d, global_iter: %d, crossPse1_loss: %.4f, crossPse2_loss: %.4f, '
@@ -111,6 +114,7 @@ class crossPseTrainer(BaseTrainer):
             for opt in (self.optimizer1, self.optimizer2):
                 for param_group in opt.param_groups:
                     param_group['lr'] = opt._lr_host = lr_
+        self.meter_flush()
         return losses
 
 

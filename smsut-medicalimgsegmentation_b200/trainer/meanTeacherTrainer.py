@@ -130,12 +130,16 @@ class MeanTeacherTrainer(BaseTrainer):
                 self.iter += 1
             else:
                 losses = self.train_step(img, msk, noise, lambda_semi)
+            # meanTeacherTrainer.py:103,121: the supervised loss under the labelled batch's modality, weighted with the
+            # size of the concatenated batch
+            self.meter_note(meter, losses[0], mdl1[0].item(), img.size(0))
             if (i + 1) % self.log_step == 0:
                 seg, semi = losses.tolist()
                 self.info('Iter %d, global_iter: %d, semi_loss: %.4f, seg_loss: %.4f, lambda_semi: %f self.alpha: %f' %
                           (i, self.iter, semi, seg, lambda_semi, self.alpha))
             for param_group in self.optimizer.param_groups:
                 param_group['lr'] = self.optimizer._lr_host = self.lr_sched.host_lr(self.iter)
+        self.meter_flush()
         return losses
 
 

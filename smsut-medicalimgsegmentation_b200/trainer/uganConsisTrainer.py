@@ -347,6 +347,9 @@ class UGANConsisTrainer(UGANShp0Trainer):
                 losses = step(*inputs)
             else:
                 losses = self.train_step(*batch, alpha, sample_ids, lambda_semi, use_semi)
+            # uganConsisTrainer.py:96,112,157-158: the segmentation loss under the labelled batch's modality, weighted
+            # with cfg.batch_size
+            self.meter_note(meter, losses[LOSS_KEYS.index('G_seg')], modal_org1[0].item(), cfg.batch_size)
             if timing is not None:
                 e = torch.cuda.Event(enable_timing=True)
                 e.record()
@@ -370,6 +373,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
         if getattr(self, 'save_samples', False) and fixed is not None:      # L205-214 (off by default: an image file per epoch)
             self.sample_translations(*fixed, save_path=os.path.join(self.expr_root, self.model_idx, 'sample',
                                                                     f'train-{self.epoch + 1}-images.png'))
+        self.meter_flush()
         return losses
 
 

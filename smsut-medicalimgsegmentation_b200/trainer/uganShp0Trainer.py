@@ -254,6 +254,8 @@ class UGANShp0Trainer(BaseTrainer):
                 losses = step(*inputs)
             else:
                 losses = self.shape_train_step(*batch, lambda_shp)
+            # uganShp0Trainer.py:162,206-207: the segmentation loss under the batch's modality
+            self.meter_note(meter, losses[self.SHP_LOSS_KEYS.index('G_seg')], modal_org[0].item(), x_real.size(0))
             if (i + 1) % (self.n_critic * self.log_step) == 0:
                 log = 'Iter: %d/%d(%d), elapsed: %.2fs,' % (i, self.n_critic * cfg.num_iter_per_epoch, self.iter,
                                                             time.time() - tic)
@@ -268,4 +270,5 @@ class UGANShp0Trainer(BaseTrainer):
                     param_group['lr'] = lr_
                 opt._lr_host = lr_
             self.iter += 1
+        self.meter_flush()
         return losses

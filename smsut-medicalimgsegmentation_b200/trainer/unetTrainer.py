@@ -67,8 +67,10 @@ class UnetTrainer(BaseTrainer):
                 self.iter += 1
             else:
                 loss = self.train_step(img, msk)
+            self.meter_note(meter, loss, mdl[0].item(), img.size(0))      # unetTrainer.py:69-76
             for param_group in self.optimizer.param_groups:   # host mirror of the device-side schedule
                 param_group['lr'] = self.optimizer._lr_host = self.lr_sched.host_lr(self.iter)
+        self.meter_flush()
         return loss
 
 

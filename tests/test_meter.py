@@ -1,0 +1,199 @@
+"""misc/utils.py (the epoch Meter of BaseTrainer.fit, the modality-organ Dice matrix, directory / yaml helpers) against
+traces of the reference's own classes (tests/golden/meter.json, made by make_golden_meter.py from the reference's
+source), and the fit loop's use of them on the fp32 test double."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "meter.json")))
+
+
+def close(a, b, tol=1e-9):
+    assert set(a) == set(b), (sorted(a), sorted(b))
+    for k in a:
+        assert abs(a[k] - b[k]) <= tol * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
+@pytest.mark.parametrize("trace", GOLD["traces"], ids=lambda t: f"alpha{t['alpha']}")
+def test_meter_epochs_match_reference_trace(pkg, trace):
+    from smsut_b200.misc.utils import Meter
+    m = Meter(min_better_keys=trace["min_keys"], max_better_keys=trace["max_keys"], alpha=trace["alpha"])
+    assert list(m.configs.items()) == [(k, "min") for k in trace["min_keys"]] + [(k, "max") for k in trace["max_keys"]]
+    assert m.pre_values is None
+    for ep in trace["epochs"]:
+        m.reset_cur()
+        assert all(v == 0 for v in m.cur_values.values()) and all(v == 0 for v in m.n.values())
+        for c in ep["calls"]:
+            v, n = Meter.collect_loss_by(c["loss"], c["modal"], c["n"])
+            assert v == c["v"] and n == c["k"]
+            m.accumulate(v, n)
+        if ep["dice"] is not None:
+            m.accumulate(ep["dice"], {k: 1. for k in ep["dice"]})
+        m.update_cur(reset_best=ep["reset_best"])
+        close(m.cur_values, ep["cur"])
+        close(m.best_values, ep["best"])
+        close(m.pre_values, ep["pre"])
+        assert str(m) == ep["text"]
+
+
+@pytest.mark.parametrize("case", GOLD["dice"], ids=lambda c: f"b{len(c['modal'])}")
+def test_collect_dice_by_matches_reference(pkg, case):
+    from smsut_b200 import config as cfg
+    from smsut_b200.misc.utils import Meter
+    logits, gt = torch.tensor(case["logits"], dtype=torch.float32), torch.tensor(case["gt"])
+    a, n = Meter.collect_dice_by(logits, gt, torch.tensor(case["modal"]), cfg.n_modal)
+    close(a, case["a"], 1e-6)           # the reference sums float32 per-slice values
+    assert n == case["n"]
+
+
+@pytest.mark.parametrize("case", GOLD["mo"], ids=["seed0", "seed1"])
+def test_modality_organ_matrix_matches_reference(pkg, case):
+    from smsut_b200.misc.utils import get_all_matrix, get_mo_matrix
+    gt = {k: np.array(v) for k, v in case["gt"].items()}
+    prd = {k: np.array(v) for k, v in case["prd"].items()}
+    assert np.abs(get_mo_matrix(prd, gt) - np.array(case["matrix"])).max() < 1e-12
+    with pytest.raises(NotImplementedError):
+        get_all_matrix(prd, gt)
+
+
+def test_directory_yaml_and_label_volume_helpers(pkg, tmp_path, monkeypatch):
+    from smsut_b200 import config as cfg
+    from smsut_b200.misc import utils
+    a, b = tmp_path / "a", tmp_path / "a" / "b"
+    utils.maybe_mkdir(str(a), str(b))
+    utils.maybe_mkdir(str(a))                       # existing directories are left alone
+    assert a.is_dir() and b.is_dir()
+    with pytest.raises(FileNotFoundError):          # like os.mkdir: no parents
+        utils.maybe_mkdir(str(tmp_path / "x" / "y"))
+    split = {m: dict(train=["1"], val=["2"], test=["3", "4"] if m == "ct" else ["3"]) for m in cfg.Modality.__members__}
+    utils.write_yaml(split, str(tmp_path / cfg.split_yaml))
+    assert utils.read_yaml(str(tmp_path / cfg.split_yaml)) == split
+    rng = np.random.default_rng(0)
+    for m in cfg.Modality.__members__:
+        for p, z in (("3", 5), ("4", 2)):
+            os.makedirs(tmp_path / m / p, exist_ok=True)
+            np.save(tmp_path / m / p / f"{m}_{p}.npy", rng.integers(0, 5, size=(z, 8, 8)).astype(np.uint8))
+    n, vols = utils.get_label_npys(str(tmp_path), "all", "test")
+    assert n == 5 * 4 + 2 and set(vols) == {f"{m}_3" for m in cfg.Modality.__members__} | {"ct_4"}
+    n, vols = utils.get_label_npys(str(tmp_path), "t2", "test")
+    assert n == 5 and list(vols) == ["t2_3"] and vols["t2_3"].shape == (5, 8, 8)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the meters inside the epoch loop (fp32 test double of the kernel layer)
+# ----------------------------------------------------------------------------------------------------------------------
+sys.path.insert(0, HERE)
+import cpu_ops_mock                                   # noqa: E402
+from oracle import smsut_oracle as O                  # noqa: E402
+
+os.environ["SMSUT_ALLOW_CPU_TEST_DOUBLE"] = "1"
+
+
+@pytest.fixture()
+def exact(pkg):
+    with cpu_ops_mock.installed(exact=True) as ops:
+        yield ops
+
+
+def _loader(batches):
+    class L(list):
+        dataset = None
+    return L(batches)
+
+
+def test_fit_fills_the_reference_meters(exact, tmp_path, monkeypatch, capsys):
+    """BaseTrainer.fit (baseTrainer.py:147-199): the train meter holds the slice-weighted mean of the iterations' losses
+    per modality, the test meter the per-modality validation loss (weighted with the PADDED size of a ragged last batch,
+    as the reference does) and the modality-organ Dice; `best` follows the test meter; [TRN] / [TST] lines are logged."""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    size = 32
+    tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name="m", input_size=size))
+    tr.expr_root = str(tmp_path)
+    sd = O.make_weights(O.unet_shapes(), 3)
+    tr.net.load_state_dict(sd)
+    mods = [0, 2, 2, 3]
+    train = []
+    for i, m in enumerate(mods):
+        x, y = O.synthetic_batch(2, size, 40 + i)
+        train.append((x, y, torch.full((2,), m), [f"{m}_p_{z}" for z in range(2)]))
+    test = []
+    for i, (m, n) in enumerate(((0, 2), (0, 1), (3, 2))):          # a ragged batch of one slice
+        x, y = O.synthetic_batch(n, size, 60 + i)
+        test.append((x, y, torch.full((n,), m), [f"{m}_q{i}_{z}" for z in range(n)]))
+    tr.fit(loaders=(_loader(train), _loader(train), _loader(test)), max_epoch=2, iters_per_epoch=4)
+    train_meter, test_meter = tr.meters
+
+    # the same two epochs on the oracle: per-iteration losses, then the validation loss of the weights after each epoch
+    st, w = {}, dict(sd)
+    it = 0
+    for epoch in range(2):
+        sums, cnt = {}, {}
+        for (x, y, mdl, _) in train:
+            loss, _ = O.unet_step(w, st, x, y, O.poly_lr(1e-2, max(it - 1, 0), cfg.max_epoch * cfg.num_iter_per_epoch))
+            it += 1
+            for k in ("loss", f"loss_{int(mdl[0])}"):
+                sums[k] = sums.get(k, 0.0) + loss.item() * 2
+                cnt[k] = cnt.get(k, 0) + 2
+        means = {k: sums[k] / cnt[k] for k in sums}
+    # cfg.exp_alpha = 1: no smoothing, the meter holds the last epoch.  2e-3: eight free-running SGD steps of the fp32 test
+    # double and the oracle (test_host_logic.py allows the weights 1e-3 after three)
+    for k, v in means.items():
+        assert abs(train_meter.cur_values[k] - v) < 2e-3 * max(1.0, abs(v)), (k, train_meter.cur_values[k], v)
+    assert train_meter.cur_values["loss_1"] == 0 and train_meter.n["loss_1"] == 0
+    assert train_meter.n["loss"] == 8 and train_meter.n["loss_2"] == 4
+
+    sums, cnt = {}, {}
+    with torch.no_grad():
+        for (x, y, mdl, _) in test:
+            loss = O.dice_ce_loss(O.unet_forward({k: v for k, v in tr.net.state_dict().items()}, x), y).item()
+            for k in ("loss", f"loss_{int(mdl[0])}"):
+                sums[k] = sums.get(k, 0.0) + loss * cfg.batch_size          # padded size, baseTrainer.py:214-230
+                cnt[k] = cnt.get(k, 0) + cfg.batch_size
+    for k in sums:
+        assert abs(test_meter.cur_values[k] - sums[k] / cnt[k]) < 1e-5, (k, test_meter.cur_values[k], sums[k] / cnt[k])
+    dices = tr.validate_dice()[0]
+    for k, v in dices.items():
+        assert abs(test_meter.cur_values[k] - v) < 1e-12
+    assert test_meter.best_values["dice"] >= test_meter.cur_values["dice"]
+    assert test_meter.best_values["loss"] <= test_meter.cur_values["loss"]
+    out = capsys.readouterr().out
+    assert out.count("[TRN] Epoch:") == 2 and out.count("[TST] Epoch:") == 2
+    assert " loss_ct:" in out and " dice_t2:" in out and "lr: " in out
+    for c in ("best.ckpt", "last.ckpt"):
+        assert os.path.exists(os.path.join(str(tmp_path), "000", "ckpt", c))
+
+
+def test_consis_epoch_notes_the_segmentation_loss(exact, monkeypatch):
+    """UGANConsisTrainer.train_epoch (uganConsisTrainer.py:96,112,157-158): G_seg under the labelled batch's modality,
+    weighted with cfg.batch_size; one flush per epoch"""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.misc.utils import Meter
+    from smsut_b200.trainer.uganConsisTrainer import LOSS_KEYS, UGANConsisTrainer
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    size = 64
+    tr = UGANConsisTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=size))
+    lb, ul = [], []
+    for i, m in enumerate((1, 3)):
+        x, y = O.synthetic_batch(2, size, 80 + i)
+        lb.append((x, y, torch.full((2,), m), None))
+        x2, _ = O.synthetic_batch(2, size, 90 + i)
+        ul.append((x2, None, torch.full((2,), (m + 1) % 4), None))
+    seen = []
+    step = tr.train_step
+    monkeypatch.setattr(tr, "train_step", lambda *a, **k: seen.append(step(*a, **k)) or seen[-1])
+    meter = tr.make_meters()[0]
+    tr.train_epoch(_loader(lb), _loader(ul), meter, num_iter=2)
+    assert tr._meter_queue == [] and len(seen) == 2
+    seg = [float(s[LOSS_KEYS.index("G_seg")]) for s in seen]
+    assert abs(meter.cur_values["loss_1"] - seg[0] * 2) < 1e-6 and abs(meter.cur_values["loss_3"] - seg[1] * 2) < 1e-6
+    assert abs(meter.cur_values["loss"] - (seg[0] + seg[1]) * 2) < 1e-6 and meter.n["loss"] == 4
+    assert isinstance(meter, Meter) and meter.n["loss_0"] == 0
