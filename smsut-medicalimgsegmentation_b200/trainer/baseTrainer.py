@@ -2,7 +2,9 @@
 """Counterpart of the reference's trainer/baseTrainer.py restricted to what the hot path needs: construction
 (device, network, Dice+CE loss: baseTrainer.py:35-62), sigmoid_rampup (:64-72), save_model (:120-123), the epoch
 loop `fit` (:125-201) with its train / test meters and [TRN] / [TST] log lines, and a device-side validate_epoch
-(:207-244).  TensorBoard and the medpy surface metrics are out of scope."""
+(:207-244).  The run directory gets the reference's layout (ckpt / tb / result / sample, `train.log`, TensorBoard
+scalars of both meters: :81-98, :165-172, :187-193) except the copy of the working directory into `code/`.  The medpy
+surface metrics are out of scope."""
 import abc
 import os
 import time
@@ -21,6 +23,8 @@ from ..misc.utils import Meter
 class BaseTrainer(object):
     def __init__(self, phase, args=None):
         self.args = args
+        self.writer = None      # TensorBoard writer of the run (opened by fit)
+        self._log_file = None   # <run>/train.log once the run directory exists
         if not torch.cuda.is_available() and os.environ.get("SMSUT_ALLOW_CPU_TEST_DOUBLE") != "1":
             raise RuntimeError("the SMSUT B200 trainers need a CUDA device: there is no CPU fallback")
         self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
@@ -112,13 +116,26 @@ class BaseTrainer(object):
                 raise RuntimeError("no run id yet: pass -i <model_id> / call load_model(model_idx, which_ckpt)")
             os.makedirs(self.expr_root, exist_ok=True)
             self._model_idx = str(len(os.listdir(self.expr_root))).rjust(3, '0')
-            os.makedirs(pjoin(self.expr_root, self._model_idx), exist_ok=True)
-            self.info(f'Create train environment in {pjoin(self.expr_root, self._model_idx)}.')
+            model_root = pjoin(self.expr_root, self._model_idx)
+            for d in ('ckpt', 'tb', 'result', 'sample'):                 # init_train_env, baseTrainer.py:84-90
+                os.makedirs(pjoin(model_root, d), exist_ok=True)
+            self._log_file = open(pjoin(model_root, 'train.log'), 'a', encoding='utf-8')
+            self.info(f'Create train environment in {model_root}.')
         return self._model_idx
 
     @model_idx.setter
     def model_idx(self, value):
+        if value != self._model_idx:        # another run directory: its own train.log and TensorBoard files
+            self.close_run_logs()
         self._model_idx = value
+
+    def close_run_logs(self):
+        if self.writer is not None:
+            self.writer.close()
+            self.writer = None
+        if self._log_file is not None:
+            self._log_file.close()
+            self._log_file = None
 
     @staticmethod
     def sigmoid_rampup(current, rampup_length):
@@ -131,7 +148,31 @@ class BaseTrainer(object):
             return float(np.exp(-5.0 * phase * phase))
 
     def info(self, msg):
+        """console + <run>/train.log (the reference's FileLogger, baseTrainer.py:94-103)"""
         print(msg, flush=True)
+        if self._log_file is not None and not self._log_file.closed:
+            self._log_file.write(time.strftime('%Y-%m-%d %H:%M:%S') + f' - INFO: {msg}\n')
+            self._log_file.flush()
+
+    def open_writer(self):
+        """TensorBoard scalars under <run>/tb like baseTrainer.py:92 (SMSUT_TENSORBOARD=0 switches them off)"""
+        if self.writer is None and os.environ.get('SMSUT_TENSORBOARD', '1') != '0':
+            try:
+                from torch.utils.tensorboard import SummaryWriter
+            except ImportError as e:          # logging only: the training path does not depend on it
+                self.info(f'TensorBoard writer unavailable ({e}); scalars are not written.')
+                return None
+            self.writer = SummaryWriter(pjoin(self.expr_root, self.model_idx, 'tb'))
+        return self.writer
+
+    def write_scalars(self, stage, meter, epoch, lr=None):
+        """`<stage>/<key>` per meter key with modality names (baseTrainer.py:165-172, 187-193)"""
+        if self.writer is not None:
+            for k, v in meter.cur_values.items():
+                self.writer.add_scalar(f'{stage}/{Meter.display_key(k)}', v, epoch)
+            if lr is not None:
+                self.writer.add_scalar(f'{stage}/lr', lr, epoch)
+            self.writer.flush()
 
     @abc.abstractmethod
     def build_network(self):
@@ -208,6 +249,7 @@ class BaseTrainer(object):
         """loaders: optional (labelled, unlabelled, test) loaders injected by the caller instead of make_loaders"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
         train_meter, test_meter = self.make_meters()
+        self.open_writer()
         best_epoch = -1
         n_epoch = max_epoch or cfg.max_epoch
         tic = time.time()
@@ -230,9 +272,11 @@ class BaseTrainer(object):
         train_meter.update_cur()
         opt = getattr(self, 'optimizer', None) or getattr(self, 'optimizer1')      # crossPseTrainer.py:185-188
         self.info('')
-        self.info(f"lr: {opt.param_groups[0]['lr']}.")
+        lr = opt.param_groups[0]['lr']
+        self.info(f'lr: {lr}.')
         self.info('[TRN] %sEpoch: %d(%d)/%d, elapsed: %.2fs,' % (tag, epoch, best_epoch, n_epoch, time.time() - tic)
                   + str(train_meter))
+        self.write_scalars('train', train_meter, epoch, lr)
         return time.time()
 
     def test_stage(self, test_loader, test_meter, epoch, n_epoch, tic, tag=''):
@@ -244,6 +288,7 @@ class BaseTrainer(object):
         test_meter.accumulate(v, {k: 1. for k in v.keys()})
         test_meter.update_cur()
         self.info('[TST] %sEpoch: %d/%d, elapsed: %.2fs,' % (tag, epoch, n_epoch, time.time() - tic) + str(test_meter))
+        self.write_scalars('test', test_meter, epoch)
         return time.time()
 
     def _write_timing(self, epoch_s, iters):

@@ -353,6 +353,7 @@ class coraNetTrainer(BaseTrainer):
         `pre_last` / `pre_ema_last` at the end"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
         train_meter, test_meter = self.make_meters()
+        self.open_writer()
         best_epoch = -1
         n_epoch = pre_epoch if pre_epoch is not None else cfg.pre_epoch
         tic = time.time()
@@ -378,6 +379,7 @@ class coraNetTrainer(BaseTrainer):
         self.load_model(self.model_id, 'pre_best')
         self.load_ema_model(self.model_id, 'pre_ema_best')
         self.model_idx = None       # this run gets its own directory (the reference allocates it at construction)
+        self.open_writer()
         new_loader, plab_dice = self.pred_unlabel(train_ul_loader)
         n_epoch = max_epoch if max_epoch is not None else cfg.cora_epoch
         tic = time.time()

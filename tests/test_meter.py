@@ -197,3 +197,40 @@ def test_consis_epoch_notes_the_segmentation_loss(exact, monkeypatch):
     assert abs(meter.cur_values["loss_1"] - seg[0] * 2) < 1e-6 and abs(meter.cur_values["loss_3"] - seg[1] * 2) < 1e-6
     assert abs(meter.cur_values["loss"] - (seg[0] + seg[1]) * 2) < 1e-6 and meter.n["loss"] == 4
     assert isinstance(meter, Meter) and meter.n["loss_0"] == 0
+
+
+def test_run_directory_layout_train_log_and_tensorboard_scalars(exact, tmp_path, monkeypatch):
+    """init_train_env (baseTrainer.py:81-98) + the scalars of fit (:165-172, :187-193): <run>/{ckpt,tb,result,sample},
+    train.log with the epoch lines, `train/<key>`, `train/lr`, `test/<key>` per epoch with modality names"""
+    from types import SimpleNamespace
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    monkeypatch.setattr(cfg, "batch_size", 2)
+    tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name="tb", input_size=32))
+    tr.expr_root = str(tmp_path)
+    batches = []
+    for i, m in enumerate((0, 1)):
+        x, y = O.synthetic_batch(2, 32, 20 + i)
+        batches.append((x, y, torch.full((2,), m), [f"{m}_v_{z}" for z in range(2)]))
+    tr.fit(loaders=(_loader(batches), _loader(batches), _loader(batches)), max_epoch=2, iters_per_epoch=2)
+    run = os.path.join(str(tmp_path), "000")
+    assert sorted(os.listdir(run)) == ["ckpt", "result", "sample", "tb", "train.log"]
+    log = open(os.path.join(run, "train.log")).read()
+    assert log.count("[TRN] Epoch:") == 2 and log.count("[TST] Epoch:") == 2 and "Save model to" in log
+    tr.close_run_logs()
+    ea = EventAccumulator(os.path.join(run, "tb"))
+    ea.Reload()
+    tags = set(ea.Tags()["scalars"])
+    want = {f"train/loss_{n}" for n in cfg.Modality.__members__} | {"train/loss", "train/lr", "test/loss", "test/dice"} \
+        | {f"test/dice_{n}" for n in cfg.Modality.__members__} | {f"test/loss_{n}" for n in cfg.Modality.__members__}
+    assert tags == want, tags ^ want
+    train_meter, test_meter = tr.meters
+    ev = ea.Scalars("test/dice")
+    assert [e.step for e in ev] == [0, 1] and abs(ev[1].value - test_meter.cur_values["dice"]) < 1e-6
+    assert abs(ea.Scalars("train/loss_ct")[1].value - train_meter.cur_values["loss_0"]) < 1e-6
+    # a second run under the same experiment gets the next number (baseTrainer.py:83)
+    tr2 = UnetTrainer('train', SimpleNamespace(fold=0, expr_name="tb", input_size=32))
+    tr2.expr_root = str(tmp_path)
+    assert tr2.model_idx == "001" and os.path.isdir(os.path.join(str(tmp_path), "001", "tb"))
+    tr2.close_run_logs()
