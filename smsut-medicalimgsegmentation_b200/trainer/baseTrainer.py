@@ -222,11 +222,12 @@ class BaseTrainer(object):
         ops.param_generation[0] += 1        # master weights changed outside an optimizer step: refresh the bf16 packs
         self.epoch, self.iter = state['__counters__']['epoch'], state['__counters__']['iter']
 
-    def make_loaders(self, loader_type):
-        """(labelled, unlabelled, test) loaders of baseTrainer.py:125-136.  'inTurn' / 'base' read the PNG slice tree
-        under cfg.base_root (data_loader/inTurnLoader.py, baseLoader.py); when no dataset is there (this repository
-        ships none: CHAOS / Synapse are not redistributable) the synthetic abdominal slices are used instead -- LOUDLY,
-        a run on them is a smoke run, not a trained model.  'synthetic' asks for them explicitly."""
+    def make_loaders(self, loader_type, phases=('train', 'val', 'test')):
+        """(labelled, unlabelled, test) loaders of baseTrainer.py:125-136 (or the subset named by `phases`).  'inTurn' /
+        'base' read the PNG slice tree under cfg.base_root (data_loader/inTurnLoader.py, baseLoader.py); when no dataset
+        is there (this repository ships none: CHAOS / Synapse are not redistributable) the synthetic abdominal slices
+        are used instead -- LOUDLY, a run on them is a smoke run, not a trained model.  'synthetic' asks for them
+        explicitly."""
         if loader_type not in ('inTurn', 'base', 'synthetic'):
             raise NotImplementedError(loader_type)
         root = getattr(cfg, 'base_root', None)
@@ -234,16 +235,38 @@ class BaseTrainer(object):
             from ..data_loader import baseLoader as bslod, inTurnLoader as inlod
             lod = inlod if loader_type == 'inTurn' else bslod
             aug = getattr(cfg, 'data_aug', None)
-            return (lod.get_loader(root, 'train', self.fold, cfg.batch_size, aug, device=self.device),
-                    lod.get_loader(root, 'val', self.fold, cfg.batch_size, aug, device=self.device),
-                    lod.get_loader(root, 'test', 0, cfg.batch_size, device=self.device))
+            make = dict(train=lambda: lod.get_loader(root, 'train', self.fold, cfg.batch_size, aug, device=self.device),
+                        val=lambda: lod.get_loader(root, 'val', self.fold, cfg.batch_size, aug, device=self.device),
+                        test=lambda: lod.get_loader(root, 'test', 0, cfg.batch_size, device=self.device))
+            return tuple(make[ph]() for ph in phases)
         if loader_type != 'synthetic':
-            self.info(f'*** WARNING: no dataset under cfg.base_root = {root!r}: fit({loader_type!r}) falls back to '
-                      'SYNTHETIC abdominal-like slices (data_loader/syntheticLoader.py). The checkpoints of this run '
-                      'are NOT a model trained on CHAOS / Synapse data. ***')
-        return (synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size),
-                synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size),
-                synlod.get_loader(None, 'test', 0, cfg.batch_size, size=self.input_size, pool_batches=4))
+            self.info(f'*** WARNING: no dataset under cfg.base_root = {root!r}: {self.phase}({loader_type!r}) falls back '
+                      'to SYNTHETIC abdominal-like slices (data_loader/syntheticLoader.py). Checkpoints and scores of '
+                      'this run are NOT those of a model trained / tested on CHAOS / Synapse data. ***')
+        make = dict(train=lambda: synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size),
+                    val=lambda: synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size),
+                    test=lambda: synlod.get_loader(None, 'test', 0, cfg.batch_size, size=self.input_size, pool_batches=4))
+        return tuple(make[ph]() for ph in phases)
+
+    def test(self, loader_type, expr_root, loader=None):
+        """`-p test` (baseTrainer.py:254-318): segment the test split, collect the modality-organ Dice matrix (row =
+        modality, column = organ, last row / column = means) and write it to `<expr_root>/<modality>_trois_matrix.csv`.
+        The reference appends the ASSD matrix (medpy, after a connected-component clean-up) to the same file; that
+        block is not produced here.  Returns the matrix."""
+        if loader is None:
+            if loader_type != 'inTurn':
+                raise NotImplementedError(loader_type)
+            loader = self.make_loaders(loader_type, phases=('test',))[0]
+        self.info(f"Predict and score the test split ({pjoin(expr_root, 'result')}).")
+        self.validate_epoch(loader)
+        dices, matrix = self.validate_dice()
+        log = ''.join(','.join('%.4f' % v for v in row) + '\n' for row in matrix) + '\n'
+        os.makedirs(expr_root, exist_ok=True)
+        with open(pjoin(expr_root, f'{self.modality}_trois_matrix.csv'), 'w') as f:
+            f.write(log)
+        self.info(log)
+        self.info('dice: %.4f' % dices['dice'])
+        return matrix
 
     def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None, loaders=None):
         """loaders: optional (labelled, unlabelled, test) loaders injected by the caller instead of make_loaders"""
@@ -324,7 +347,7 @@ class BaseTrainer(object):
     def pseudo_loader(self, loader_type):
         if loader_type != 'inTurn':
             raise NotImplementedError(loader_type)
-        return self.make_loaders('inTurn')[2]
+        return self.make_loaders('inTurn', phases=('test',))[0]
 
     def saving_pseudo(self, loader_type, expr_root, loader=None):
         """baseTrainer.py:320-378: segment every slice of the test loader and save `<name>pse.jpg` (prediction),

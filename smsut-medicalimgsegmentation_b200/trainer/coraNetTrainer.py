@@ -424,7 +424,7 @@ if __name__ == '__main__':
         trainer.fit('inTurn', max_epoch=args.epochs, iters_per_epoch=args.iters)
     elif args.phase == 'test':
         trainer.load_model(args.model_id or '000', args.which_ckpt)
-        print('dice: %.4f' % trainer.validate_epoch(trainer.make_loaders('inTurn')[2]))
+        trainer.test('inTurn', pjoin(trainer.expr_root, args.model_id or '000'))
     elif args.phase == 'pseudo':
         trainer.load_model(args.model_id or '000', args.which_ckpt)
         trainer.saving_pseudo('inTurn', pjoin(trainer.expr_root, args.model_id or '000'))

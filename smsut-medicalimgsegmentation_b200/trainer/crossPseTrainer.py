@@ -134,10 +134,9 @@ if __name__ == '__main__':
         trainer = crossPseTrainer('train', args)
         trainer.fit('inTurn', max_epoch=args.epochs, iters_per_epoch=args.iters)
     elif args.phase == 'test':
-        from ..data_loader import syntheticLoader as synlod
         trainer = crossPseTrainer('test', args)
         trainer.load_model(args.model_id or '000', args.which_ckpt)
-        print('dice: %.4f' % trainer.validate_epoch(synlod.get_loader(None, 'test', 0, cfg.batch_size, pool_batches=4)))
+        trainer.test('inTurn', os.path.join(trainer.expr_root, args.model_id or '000'))
     elif args.phase == 'pseudo':
         trainer = crossPseTrainer('pseudo', args)
         trainer.load_model(args.model_id or '000', args.which_ckpt)

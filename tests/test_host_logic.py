@@ -574,7 +574,12 @@ def test_cli_train_then_test_entry_points(exact, tmp_path, monkeypatch, capsys, 
         assert os.path.exists(os.path.join(str(tmp_path), "cli", "000", "ckpt", c)), c
     monkeypatch.setattr(sys, "argv", [module + ".py", "-p", "test", "-f", "0", "-nm", "cli", "-i", "000", "-wh", "last"])
     runpy.run_module(name, run_name="__main__")
-    assert "dice:" in capsys.readouterr().out
+    out = capsys.readouterr().out
+    assert "dice:" in out
+    # BaseTrainer.test (baseTrainer.py:254-318): the modality-organ Dice matrix as <run>/all_trois_matrix.csv
+    rows = [r for r in open(os.path.join(str(tmp_path), "cli", "000", "all_trois_matrix.csv")).read().split("\n") if r]
+    assert len(rows) == cfg.n_modal + 1 and all(len(r.split(",")) == cfg.n_label + 1 for r in rows)
+    assert ("dice: " + rows[-1].split(",")[-1]) in out
 
 
 @pytest.mark.parametrize("module", ["unetTrainer", "uganConsisTrainer"])
