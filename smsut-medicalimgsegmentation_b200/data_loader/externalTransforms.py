@@ -22,6 +22,18 @@ PARAM_FLOATS = 66      # == SMSUT_AUG_PARAM_FLOATS (include/smsut_b200.h)
 MAX_POINTS = 5
 
 
+class MaskToTensor(object):
+    """label image -> int64 tensor (externalTransforms.py:12-20).  The GPU pipeline emits int64 labels itself; this is
+    for host-side callers of the reference's transform."""
+
+    def __call__(self, x):
+        import torch
+        return torch.from_numpy(np.array(x)).long()
+
+    def __repr__(self):
+        return self.__class__.__name__ + '()\n'
+
+
 class JointRotate(object):
     def __init__(self, degrees, resample=False, expand=False, center=None):
         if expand or center is not None:

@@ -18,6 +18,19 @@ def _flat_logits(x):
     return v.reshape(-1, x.shape[1])
 
 
+def get_tp_fp_fn_tn(output, gt, dims=(2, 3)):
+    """Soft true / false positive / negative sums of (B, C, H, W) probabilities `output` against (B, H, W) labels `gt`
+    over `dims` (loss.py:23-36).  The loss kernels compute the same sums inside their fused pass; this host-side form
+    is for callers of the reference's helper (misc/utils.py Meter.collect_dice_by)."""
+    with torch.no_grad():
+        onehot = torch.zeros_like(output).scatter_(1, gt.to(output.device).long().unsqueeze(1), 1)
+    tp = (output * onehot).sum(dim=dims)
+    fp = (output * (1. - onehot)).sum(dim=dims)
+    fn = ((1. - output) * onehot).sum(dim=dims)
+    tn = ((1. - output) * (1. - onehot)).sum(dim=dims)
+    return tp, fp, fn, tn
+
+
 class DiceAndCrossEntropyLoss(nn.Module):
     def __init__(self, weight_ce=1., weight_dc=1., batch_dice=False):
         super(DiceAndCrossEntropyLoss, self).__init__()

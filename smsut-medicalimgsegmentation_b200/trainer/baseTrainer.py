@@ -123,6 +123,20 @@ class BaseTrainer(object):
             self.info(f'Create train environment in {model_root}.')
         return self._model_idx
 
+    def init_train_env(self, expr_root=None):
+        """baseTrainer.py:81-98: allocate the run directory now (this class does it lazily, at the first save / fit, so
+        that building a trainer leaves nothing on disk); returns the run id"""
+        if expr_root is not None:
+            self.expr_root = expr_root
+        return self.model_idx
+
+    def register_experiment_args(self, path, filename='expriments.log'):
+        """baseTrainer.py:74-79: append the trainer class, its run directory and its arguments to <path>/<filename>"""
+        assert self.phase == 'train'
+        with open(pjoin(path, filename), 'a') as f:
+            f.write(self.__class__.__name__ + ', ' + pjoin(self.expr_root, self.model_idx) + '\n')
+            f.write(str(self.args) + '\n\n')
+
     @model_idx.setter
     def model_idx(self, value):
         if value != self._model_idx:        # another run directory: its own train.log and TensorBoard files

@@ -143,6 +143,9 @@ class MeanTeacherTrainer(BaseTrainer):
         return losses
 
 
+meanTeacherTrainer = MeanTeacherTrainer        # the reference's class name (meanTeacherTrainer.py:35)
+
+
 if __name__ == '__main__':
     parser = argparse.ArgumentParser()
     parser.add_argument('-p', '--phase', type=str, default='train')

@@ -35,3 +35,21 @@ for seed, sizes, bs, shuffle in ((1, (37, 20, 53, 16), 8, False), (2, (37, 20, 5
                       test=test, test_len=len(ns["InTurnTestBatchSampler"]([list(x) for x in samples], bs))))
 json.dump(cases, open(os.path.join(HERE, "inturn_sampler.json"), "w"))
 print("wrote", len(cases), "cases")
+
+# ---- data_loader/balanceLoader.py:80-109, lifted the same way -> tests/golden/balance_sampler.json ------------------
+SRC_B = "/root/reference/data_loader/balanceLoader.py"
+tree_b = ast.parse(open(SRC_B).read())
+wanted_b = [n for n in tree_b.body if isinstance(n, ast.ClassDef) and n.name == "ModalityBalanceBatchSampler"]
+exec(compile(ast.Module(body=wanted_b, type_ignores=[]), SRC_B, "exec"), ns)
+cases_b = []
+for seed, sizes, bs in ((1, (37, 20, 53, 16), 8), (2, (9, 9, 9, 9), 4), (3, (64, 8, 24, 40), 8), (4, (5, 17), 2), (5, (12, 12, 12, 12), 16)):
+    samples, n = [], 0
+    for s in sizes:
+        samples.append(list(range(n, n + s)))
+        n += s
+    random.seed(seed)
+    sampler = ns["ModalityBalanceBatchSampler"]([list(x) for x in samples], bs)
+    cases_b.append(dict(seed=seed, sizes=sizes, batch_size=bs, length=len(sampler),
+                        epochs=[[list(b) for b in sampler] for _ in range(3)]))      # cursors carry over between epochs
+json.dump(cases_b, open(os.path.join(HERE, "balance_sampler.json"), "w"))
+print("wrote", len(cases_b), "balance cases")

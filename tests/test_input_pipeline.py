@@ -55,6 +55,31 @@ def test_inturn_samplers_match_reference_streams(pkg):
         assert [list(b) for b in test] == c["test"] and len(test) == c["test_len"]
 
 
+def test_balance_sampler_matches_reference_streams(pkg):
+    """data_loader/balanceLoader.py:80-109 (no trainer builds it; kept importable): three passes with carried-over cursors"""
+    from smsut_b200.data_loader import balanceLoader
+    from smsut_b200.data_loader.baseLoader import BalanceDataset
+    assert balanceLoader.BalanceDataset is BalanceDataset
+    cases = json.load(open(os.path.join(HERE, "golden", "balance_sampler.json")))
+    assert len(cases) == 5
+    for c in cases:
+        samples, n = [], 0
+        for s in c["sizes"]:
+            samples.append(list(range(n, n + s)))
+            n += s
+        random.seed(c["seed"])
+        sampler = balanceLoader.ModalityBalanceBatchSampler([list(x) for x in samples], c["batch_size"])
+        assert len(sampler) == c["length"]
+        for want in c["epochs"]:
+            got = [list(b) for b in sampler]
+            assert got == want
+            assert all(len(b) == c["batch_size"] for b in got)
+    with pytest.raises(ValueError):
+        balanceLoader.get_loader("/nonexistent", "test", 0, 8)
+    with pytest.raises(AssertionError):
+        balanceLoader.get_loader("/nonexistent", "train", 0, 6)
+
+
 def test_parameter_draws(pkg):
     from smsut_b200.data_loader import externalTransforms as extt
     random.seed(0)

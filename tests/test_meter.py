@@ -234,3 +234,32 @@ def test_run_directory_layout_train_log_and_tensorboard_scalars(exact, tmp_path,
     tr2.expr_root = str(tmp_path)
     assert tr2.model_idx == "001" and os.path.isdir(os.path.join(str(tmp_path), "001", "tb"))
     tr2.close_run_logs()
+
+
+def test_reference_helper_names_are_importable(exact, tmp_path):
+    """names a caller of the reference's modules may import: the class name of meanTeacherTrainer.py:35, loss.py:23's
+    get_tp_fp_fn_tn, externalTransforms.py:12's MaskToTensor, init_train_env / register_experiment_args"""
+    from types import SimpleNamespace
+    from PIL import Image
+    from smsut_b200.data_loader.externalTransforms import MaskToTensor
+    from smsut_b200.misc.loss import get_tp_fp_fn_tn
+    from smsut_b200.trainer.meanTeacherTrainer import MeanTeacherTrainer, meanTeacherTrainer
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    assert meanTeacherTrainer is MeanTeacherTrainer
+    lab = np.arange(12, dtype=np.uint8).reshape(3, 4) % 5
+    t = MaskToTensor()(Image.fromarray(lab))
+    assert t.dtype == torch.int64 and torch.equal(t, torch.from_numpy(lab).long())
+    gen = torch.Generator().manual_seed(0)
+    prob = torch.softmax(torch.randn(2, 5, 6, 6, generator=gen), dim=1)
+    gt = torch.randint(0, 5, (2, 6, 6), generator=gen)
+    tp, fp, fn, tn = get_tp_fp_fn_tn(prob, gt)
+    onehot = torch.nn.functional.one_hot(gt, 5).permute(0, 3, 1, 2).float()
+    assert tp.shape == (2, 5) and torch.allclose(tp, (prob * onehot).sum((2, 3)))
+    assert torch.allclose(tp + fn, onehot.sum((2, 3))) and torch.allclose(tp + fp + fn + tn, torch.full((2, 5), 36.))
+    assert get_tp_fp_fn_tn(prob, gt, dims=(0, 2, 3))[0].shape == (5,)
+    tr = UnetTrainer('train', SimpleNamespace(fold=1, expr_name="e", input_size=32))
+    assert tr.init_train_env(str(tmp_path)) == "000" and os.path.isdir(os.path.join(str(tmp_path), "000", "sample"))
+    tr.register_experiment_args(str(tmp_path))
+    reg = open(os.path.join(str(tmp_path), "expriments.log")).read()
+    assert reg.startswith("UnetTrainer, " + os.path.join(str(tmp_path), "000")) and "fold=1" in reg
+    tr.close_run_logs()
