@@ -397,11 +397,20 @@ class BaseTrainer(object):
         # (a + 1) * 255 on a [-1, 1] image, then mode 'F' -> 'RGB' (clips at 255): the reference's own arithmetic
         Image.fromarray(((img + 1) * 255).astype(np.float32)).convert('RGB').save(pjoin(pred_root, name + 'ori.jpg'))
 
-    def validate_dice(self, volume_confusion=None):
+    def validate_dice(self, volume_confusion=None, gt_npys=None):
         """The reference's selection metric (baseTrainer.py:246-252 -> misc/utils.py:180-203 get_mo_matrix): Dice per
         volume and organ, averaged over the volumes of a modality, then over organs / modalities; from the per-volume
         confusion counts of the last validate_epoch instead of medpy on host volumes.  medpy.metric.dc(p, g) =
-        2 |p & g| / (|p| + |g|), and 0 when both are empty.  Returns (dict like the reference's, matrix)."""
+        2 |p & g| / (|p| + |g|), and 0 when both are empty.  Returns (dict like the reference's, matrix).
+
+        Called the reference's way, `validate_dice(prd_npys, gt_npys)` with host volumes, it returns the dict alone,
+        computed by misc.utils.get_mo_matrix."""
+        if gt_npys is not None:
+            from ..misc.utils import get_mo_matrix
+            mo = get_mo_matrix(volume_confusion, gt_npys)
+            dices = {f'dice_{i}': mo[i, -1] for i in range(cfg.n_modal)}
+            dices['dice'] = mo[-1, -1]
+            return dices
         confs = self.volume_confusion if volume_confusion is None else volume_confusion
         n_modal, n_label = cfg.n_modal, cfg.n_label
         matrix = np.zeros((n_modal, n_label))
@@ -439,9 +448,17 @@ class BaseTrainer(object):
 
     def validate_epoch(self, loader, npys=None, meter=None, save_path=None):
         """Mean foreground Dice of argmax predictions over the loader (pads a ragged last batch to cfg.batch_size
-        like baseTrainer.py:214-219); the confusion counts stay on the device."""
+        like baseTrainer.py:214-219); the confusion counts stay on the device (`confusion`, `volume_confusion`:
+        validate_dice() builds the modality-organ matrix from them).
+
+        Called the reference's way -- with `npys`, the {'<modality>_<patient>': (Z, H, W)} label volumes of
+        get_label_npys -- it ALSO copies the predicted label maps into host volumes of those shapes and returns the
+        reference's `(number of predicted slices, prediction volumes)` (baseTrainer.py:207-244)."""
         self.net.eval()
         n_cls = cfg.n_label + 1
+        prd_npys, n_prd_slic = None, 0
+        if npys is not None:
+            prd_npys = {k: np.zeros(v.shape, dtype=v.dtype) for k, v in npys.items()}
         conf = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=self.device)     # conf[label, prediction]
         vol_conf = {}
         with torch.no_grad():
@@ -460,6 +477,12 @@ class BaseTrainer(object):
                 logits = out.permute(0, 2, 3, 1).reshape(-1, n_cls)
                 logits = logits if logits.is_contiguous() else logits.contiguous()
                 ops.confusion_counts(logits, msk.reshape(-1), conf)
+                if prd_npys is not None:
+                    pred = ops.argmax_c(logits).view(b, h, w).cpu().numpy()
+                    for i in range(b):
+                        m_name, pid, z = str(inm[i]).split('_')
+                        prd_npys[f'{m_name}_{pid}'][int(z)] = pred[i]
+                        n_prd_slic += 1
                 # per-volume counts for the modality-organ matrix: slices are named '<modality>_<patient>_<z>'
                 # (baseTrainer.py:241); consecutive slices of one volume share one accumulator
                 if inm is None:
@@ -480,4 +503,4 @@ class BaseTrainer(object):
         denom = (conf.sum(0) + conf.sum(1)).double()
         dice = (2 * inter[1:] / denom[1:].clamp_min(1)).mean().item()
         self.net.train()
-        return dice
+        return dice if prd_npys is None else (n_prd_slic, prd_npys)

@@ -263,3 +263,38 @@ def test_reference_helper_names_are_importable(exact, tmp_path):
     reg = open(os.path.join(str(tmp_path), "expriments.log")).read()
     assert reg.startswith("UnetTrainer, " + os.path.join(str(tmp_path), "000")) and "fold=1" in reg
     tr.close_run_logs()
+
+
+def test_validate_epoch_and_dice_the_reference_way(exact, monkeypatch):
+    """baseTrainer.py:207-252 called as the reference's fit / test call it: validate_epoch(loader, npys) returns (number
+    of slices, prediction volumes), validate_dice(prd_npys, gt_npys) the Dice dict -- equal to the dict the device-side
+    confusion counts give, incl. a ragged last batch and a volume split over two batches"""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    monkeypatch.setattr(cfg, "batch_size", 4)
+    tr = UnetTrainer('train', SimpleNamespace(fold=0, expr_name=None, input_size=32))
+    sd = O.make_weights(O.unet_shapes(), 5)
+    tr.net.load_state_dict(sd)
+    layout = [('ct', 'a', 4), ('ct', 'b', 4), ('ct', 'b', 2), ('t1out', 'c', 3)]
+    batches, z0, gt = [], {}, {}
+    for bi, (m, pid, n) in enumerate(layout):
+        img, lab = O.synthetic_batch(n, 32, 500 + bi)
+        s = z0.get((m, pid), 0)
+        batches.append((img, lab, torch.full((n,), cfg.Modality[m].value), [f"{m}_{pid}_{s + z}" for z in range(n)]))
+        z0[(m, pid)] = s + n
+        key = f"{m}_{pid}"
+        gt[key] = np.concatenate([gt[key], lab.numpy()]) if key in gt else lab.numpy()
+    n_slices, prd = tr.validate_epoch(batches, gt)
+    assert n_slices == 13 and set(prd) == set(gt) and all(prd[k].shape == gt[k].shape for k in gt)
+    for img, lab, mdl, names in batches:
+        pred = O.unet_forward(sd, img).argmax(1).numpy()
+        for i, nm in enumerate(names):
+            m, pid, z = nm.split('_')
+            assert np.array_equal(prd[f"{m}_{pid}"][int(z)], pred[i]), nm
+    ref_way = tr.validate_dice(prd, gt)
+    device_way, matrix = tr.validate_dice()
+    assert set(ref_way) == set(device_way)
+    for k in ref_way:
+        assert abs(ref_way[k] - device_way[k]) < 1e-12, k
+    assert isinstance(tr.validate_epoch(batches), float)
