@@ -198,10 +198,13 @@ class BaseTrainer(object):
         torch.save({k: v.detach().cpu() for k, v in self.net.state_dict().items()}, path)
         self.info(f'Save model to {path}.')
 
-    def load_model(self, model_idx, which_ckpt):
+    def load_model(self, model_idx=None, which_ckpt='last'):
+        if model_idx is None:               # baseTrainer.py:112-117: default = this run's own checkpoint
+            model_idx = self.model_idx
         path = pjoin(self.expr_root, model_idx, 'ckpt', f'{which_ckpt}.ckpt')
         self.net.load_state_dict(torch.load(path, map_location='cpu'))
         self._model_idx = model_idx
+        self.info(f'Load model from {path}.')
 
     # ---- resume state: an extension.  The reference checkpoints weights only, so a
     # restarted run loses SGD momentum, Adam moments, the LR schedule position and the EMA teacher.
