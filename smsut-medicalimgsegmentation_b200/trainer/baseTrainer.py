@@ -307,7 +307,7 @@ class BaseTrainer(object):
         self.meters = (train_meter, test_meter)
 
     def log_train_stage(self, train_meter, epoch, best_epoch, n_epoch, tic, tag=''):
-        """the train logs of an epoch (baseTrainer.py:158-172, without the TensorBoard scalars); returns the new tic"""
+        """the train logs and scalars of an epoch (baseTrainer.py:158-172); returns the new tic"""
         self.meter_flush()
         train_meter.update_cur()
         opt = getattr(self, 'optimizer', None) or getattr(self, 'optimizer1')      # crossPseTrainer.py:185-188
