@@ -42,3 +42,14 @@ def _cpu_tests_start_from_a_fixed_rng_state(request):
         np.random.seed(20261019)
         random.seed(20261019)
     yield
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _gpu_test_files_start_from_a_fresh_process_rng_state():
+    """On a GPU box every test FILE starts from the generator state of a fresh process (torch's default seed, CPU and
+    CUDA generators): the files were measured one process each (scripts/gpu_tests.sh), and `pytest tests -m gpu` in ONE
+    process should feed the tests that draw without a seed the same inputs."""
+    import torch
+    if torch.cuda.is_available():
+        torch.manual_seed(67280421310721)       # c10::detail default_rng_seed_val
+    yield
