@@ -288,6 +288,7 @@ class BaseTrainer(object):
     def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None, loaders=None):
         """loaders: optional (labelled, unlabelled, test) loaders injected by the caller instead of make_loaders"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
+        self.info_loader_sizes(train_lb_loader, train_ul_loader, test_loader)
         train_meter, test_meter = self.make_meters()
         self.open_writer()
         best_epoch = -1
@@ -305,6 +306,13 @@ class BaseTrainer(object):
                 best_epoch = epoch
         self.save_model(prefix='last')
         self.meters = (train_meter, test_meter)
+
+    def info_loader_sizes(self, train_lb_loader, train_ul_loader, test_loader):
+        """baseTrainer.py:139-141"""
+        for what, loader in (('train labeled', train_lb_loader), ('train unlabel', train_ul_loader), ('test ', test_loader)):
+            dataset = getattr(loader, 'dataset', None)
+            if dataset is not None:
+                self.info(f'{what} images: {len(dataset)}')
 
     def log_train_stage(self, train_meter, epoch, best_epoch, n_epoch, tic, tag=''):
         """the train logs and scalars of an epoch (baseTrainer.py:158-172); returns the new tic"""

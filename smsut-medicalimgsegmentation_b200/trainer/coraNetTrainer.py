@@ -352,6 +352,7 @@ class coraNetTrainer(BaseTrainer):
         """(:526-602) supervised pre-training; keeps `pre_best` / `pre_ema_best` on the validation Dice and writes
         `pre_last` / `pre_ema_last` at the end"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
+        self.info_loader_sizes(train_lb_loader, train_ul_loader, test_loader)
         train_meter, test_meter = self.make_meters()
         self.open_writer()
         best_epoch = -1
@@ -374,6 +375,7 @@ class coraNetTrainer(BaseTrainer):
         """(:604-690) loads `pre_best` / `pre_ema_best` of run `model_id`, predicts the pseudo labels (again every
         cfg.pred_step epochs) and trains; `best` on the validation Dice, `last` at the end"""
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
+        self.info_loader_sizes(train_lb_loader, train_ul_loader, test_loader)
         train_meter, test_meter = self.make_meters()
         best_epoch = -1
         self.load_model(self.model_id, 'pre_best')
