@@ -168,6 +168,11 @@ def get_mo_matrix(prd_npys, gt_npys):
     return matrix
 
 
+def connected_components(pred):
+    raise NotImplementedError('the connected-component clean-up of `-p test` (utils.py:18-37) needs skimage (CPU '
+                              'evaluation extra, out of scope: DESIGN.md section 7)')
+
+
 def get_all_matrix(prd_npys, gt_npys):
     raise NotImplementedError('Hausdorff / ASSD and the connected-component clean-up of `-p test` need medpy and '
                               'skimage (CPU evaluation extras, out of scope: DESIGN.md section 7); get_mo_matrix / '

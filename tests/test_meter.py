@@ -53,12 +53,14 @@ def test_collect_dice_by_matches_reference(pkg, case):
 
 @pytest.mark.parametrize("case", GOLD["mo"], ids=["seed0", "seed1"])
 def test_modality_organ_matrix_matches_reference(pkg, case):
-    from smsut_b200.misc.utils import get_all_matrix, get_mo_matrix
+    from smsut_b200.misc.utils import connected_components, get_all_matrix, get_mo_matrix
     gt = {k: np.array(v) for k, v in case["gt"].items()}
     prd = {k: np.array(v) for k, v in case["prd"].items()}
     assert np.abs(get_mo_matrix(prd, gt) - np.array(case["matrix"])).max() < 1e-12
     with pytest.raises(NotImplementedError):
         get_all_matrix(prd, gt)
+    with pytest.raises(NotImplementedError):
+        connected_components(prd[next(iter(prd))])
 
 
 def test_directory_yaml_and_label_volume_helpers(pkg, tmp_path, monkeypatch):
