@@ -113,6 +113,18 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference / CPU arm: the oracle on host cores
 # ------------------------------------------------------------------------------------------------
+def cpu_model():
+    """the host CPU's model name (SURVEY.md section 8d asks the CPU arm to name it), '' if it cannot be read"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return ""
+
+
 def cpu_step_rate(bs, steps, warmup, threads=None):
     import torch
     from oracle import smsut_oracle as O
@@ -169,7 +181,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOADS["ugan_consis"], "per_gpu_slices": 2 * bs, "global_batch": 2 * bs,
                        "device": "host CPU"},
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                             "cpu": cpu_model()},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _OUT.emit(json.dumps(line))
@@ -568,7 +581,8 @@ def run_ugan_consis(args, torch, par):
         rate, sec, threads = cpu_step_rate(bs, 4, 1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "4 timed iterations (after 1 warm-up) of the oracle's full uganConsis step at "
-                                          f"{bs}+{bs} 256x256 slices ({sec:.2f} s each), fp32, torch CPU, {threads} threads"}
+                                          f"{bs}+{bs} 256x256 slices ({sec:.2f} s each), fp32, torch CPU, {threads} threads",
+                                "cpu": cpu_model()}
         if not args.no_context:
             del step
             tr._graphs.clear()
