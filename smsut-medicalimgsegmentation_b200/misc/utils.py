@@ -3,9 +3,10 @@
 directory / yaml helpers (utils.py:40-55), the epoch `Meter` of `BaseTrainer.fit` (utils.py:58-160), the label-volume
 loader (utils.py:163-177) and the modality-organ Dice matrix (utils.py:180-203).
 
-Not here, and why: `connected_components` / `get_all_matrix` (utils.py:18-37, 206-279) are the CPU post-processing and
-surface-distance extras of `-p test` built on skimage / medpy; the trainers compute the Dice
-matrix from device-side confusion counts instead (`BaseTrainer.validate_dice`)."""
+`connected_components` / `get_all_matrix` (utils.py:18-37, 206-279), the CPU post-processing and surface-distance
+extras of `-p test`, are restated on scipy.ndimage (skimage / medpy are not importable offline and the reference pins
+no version: those two are checked against brute-force statements, not against the libraries).  The trainers compute the
+Dice matrix from device-side confusion counts instead (`BaseTrainer.validate_dice`)."""
 import os
 from collections import OrderedDict
 from os.path import join as pjoin
@@ -169,11 +170,81 @@ def get_mo_matrix(prd_npys, gt_npys):
 
 
 def connected_components(pred):
-    raise NotImplementedError('the connected-component clean-up of `-p test` (utils.py:18-37) needs skimage (CPU '
-                              'evaluation extra, out of scope: DESIGN.md section 7)')
+    """The clean-up `-p test` applies to a predicted label map before the surface metric (utils.py:18-37): per label
+    1..cfg.n_modal (sic: the reference loops over the modality count, which equals the organ count on CHAOS), keep the
+    connected components that hold more than 10 % of that label's voxels.  skimage.measure.label(connectivity=2) is
+    restated with scipy.ndimage.label: neighbours within squared distance 2 (8-connected in 2-D, 18-connected in 3-D).
+    skimage is not importable offline, so this restatement is checked against a flood fill, not against skimage."""
+    from scipy import ndimage
+    pred = np.asarray(pred)
+    structure = ndimage.generate_binary_structure(pred.ndim, min(2, pred.ndim))
+    out = np.zeros_like(pred)
+    for i in range(cfg.n_modal):
+        labels, num = ndimage.label(pred == i + 1, structure=structure)
+        if num == 0:
+            continue
+        sizes = np.bincount(labels.ravel(), minlength=num + 1)
+        keep = sizes > 0.1 * sizes[1:].sum()
+        keep[0] = False
+        out += (keep[labels] * (i + 1)).astype(out.dtype)
+    return np.uint8(out)
+
+
+def _surface_distances(result, reference, voxelspacing=None, connectivity=1):
+    """distances from the border voxels of `result` to the nearest border voxel of `reference` (medpy.metric.binary:
+    border = object minus its erosion, Euclidean distance transform of the complement of the reference border)"""
+    from scipy import ndimage
+    result, reference = np.atleast_1d(np.asarray(result).astype(bool)), np.atleast_1d(np.asarray(reference).astype(bool))
+    if not result.any():
+        raise RuntimeError('The first supplied array does not contain any binary object.')
+    if not reference.any():
+        raise RuntimeError('The second supplied array does not contain any binary object.')
+    footprint = ndimage.generate_binary_structure(result.ndim, connectivity)
+    result_border = result ^ ndimage.binary_erosion(result, structure=footprint, iterations=1)
+    reference_border = reference ^ ndimage.binary_erosion(reference, structure=footprint, iterations=1)
+    dt = ndimage.distance_transform_edt(~reference_border, sampling=voxelspacing)
+    return dt[result_border]
+
+
+def assd(result, reference, voxelspacing=None, connectivity=1):
+    """medpy.metric.assd restated from its documentation (medpy is not importable offline; no version is pinned by the
+    reference): the mean of the two directed average surface distances"""
+    return float(np.mean((_surface_distances(result, reference, voxelspacing, connectivity).mean(),
+                          _surface_distances(reference, result, voxelspacing, connectivity).mean())))
+
+
+def _with_means(matrix):
+    n_modal, n_label = matrix.shape
+    full = np.zeros((n_modal + 1, n_label + 1))
+    full[:n_modal, :n_label] = matrix
+    full[-1, :] = full[:n_modal].mean(axis=0)
+    full[:, -1] = full[:, :n_label].mean(axis=1)
+    return full
 
 
 def get_all_matrix(prd_npys, gt_npys):
-    raise NotImplementedError('Hausdorff / ASSD and the connected-component clean-up of `-p test` need medpy and '
-                              'skimage (CPU evaluation extras, out of scope: DESIGN.md section 7); get_mo_matrix / '
-                              'BaseTrainer.validate_dice give the Dice matrix')
+    """(Dice, "Hausdorff", ASSD) modality-organ matrices of `-p test` (utils.py:206-279) on predictions cleaned by
+    connected_components (the volume, then every slice).  As in the reference the second matrix repeats the Dice
+    values (`t = s`), an organ missing from the prediction scores the largest ASSD seen so far in its volume, and an
+    organ missing from the LABELS of a volume raises (medpy's RuntimeError).  CPU evaluation: nothing here runs on the
+    device."""
+    n_modal, n_label = cfg.n_modal, cfg.n_label
+    dice, hd, sd = (np.zeros((n_modal, n_label)) for _ in range(3))
+    n = np.zeros((n_modal, 1))
+    for k, g in gt_npys.items():
+        m = cfg.Modality[k.split('_')[0]].value
+        p = connected_components(prd_npys[k])
+        for z in range(p.shape[0]):
+            p[z] = connected_components(p[z])
+        worst = 0
+        for j in range(1, n_label + 1):
+            predx, gx = p == j, np.asarray(g) == j
+            s = dice_coefficient(predx, gx)
+            r = worst if not predx.any() else assd(predx, gx)
+            worst = max(worst, r)
+            dice[m, j - 1] += s
+            hd[m, j - 1] += s
+            sd[m, j - 1] += r
+        n[m] += 1
+    n[n == 0] += 1e-8
+    return _with_means(dice / n), _with_means(hd / n), _with_means(sd / n)

@@ -265,24 +265,40 @@ class BaseTrainer(object):
                     test=lambda: synlod.get_loader(None, 'test', 0, cfg.batch_size, size=self.input_size, pool_batches=4))
         return tuple(make[ph]() for ph in phases)
 
-    def test(self, loader_type, expr_root, loader=None):
-        """`-p test` (baseTrainer.py:254-318): segment the test split, collect the modality-organ Dice matrix (row =
-        modality, column = organ, last row / column = means) and write it to `<expr_root>/<modality>_trois_matrix.csv`.
-        The reference appends the ASSD matrix (medpy, after a connected-component clean-up) to the same file; that
-        block is not produced here.  Returns the matrix."""
+    def test(self, loader_type, expr_root, loader=None, gt_npys=None):
+        """`-p test` (baseTrainer.py:254-318): segment the test split, collect the modality-organ matrices (row =
+        modality, column = organ, last row / column = means) and write them to
+        `<expr_root>/<modality>_trois_matrix.csv`: the Dice block, an empty line, the ASSD block.
+
+        With the label volumes of the processed dataset (`get_label_npys` under cfg.base_root, or `gt_npys`) this is the
+        reference's route: predictions assembled into host volumes, Dice by get_mo_matrix, ASSD by get_all_matrix after
+        the connected-component clean-up (CPU work on the host volumes).  Without them (the synthetic fallback) the Dice
+        block comes from the device-side confusion counts and there is no ASSD block.  Returns the Dice matrix."""
+        from ..misc.utils import get_all_matrix, get_label_npys, get_mo_matrix
+        root = getattr(cfg, 'base_root', None)
         if loader is None:
             if loader_type != 'inTurn':
                 raise NotImplementedError(loader_type)
             loader = self.make_loaders(loader_type, phases=('test',))[0]
+            if gt_npys is None and root and os.path.isdir(root):
+                n_gt_slic, gt_npys = get_label_npys(root, self.modality, 'test')
         self.info(f"Predict and score the test split ({pjoin(expr_root, 'result')}).")
-        self.validate_epoch(loader)
-        dices, matrix = self.validate_dice()
-        log = ''.join(','.join('%.4f' % v for v in row) + '\n' for row in matrix) + '\n'
+        fmt = lambda mat: ''.join(','.join('%.4f' % v for v in row) + '\n' for row in mat)      # noqa: E731
+        if gt_npys is not None:
+            n_prd_slic, prd_npys = self.validate_epoch(loader, gt_npys, None, save_path=pjoin(expr_root, 'result'))
+            assert n_prd_slic == sum(v.shape[0] for v in gt_npys.values()), 'a slice of the test split was not predicted'
+            matrix = get_mo_matrix(prd_npys, gt_npys)
+            _, _, assd_matrix = get_all_matrix(prd_npys, gt_npys)
+            log = fmt(matrix) + '\n' + fmt(assd_matrix)
+        else:
+            self.validate_epoch(loader)
+            matrix = self.validate_dice()[1]
+            log = fmt(matrix) + '\n'
         os.makedirs(expr_root, exist_ok=True)
         with open(pjoin(expr_root, f'{self.modality}_trois_matrix.csv'), 'w') as f:
             f.write(log)
         self.info(log)
-        self.info('dice: %.4f' % dices['dice'])
+        self.info('dice: %.4f' % matrix[-1, -1])
         return matrix
 
     def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None, loaders=None):

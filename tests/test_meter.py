@@ -57,10 +57,14 @@ def test_modality_organ_matrix_matches_reference(pkg, case):
     gt = {k: np.array(v) for k, v in case["gt"].items()}
     prd = {k: np.array(v) for k, v in case["prd"].items()}
     assert np.abs(get_mo_matrix(prd, gt) - np.array(case["matrix"])).max() < 1e-12
-    with pytest.raises(NotImplementedError):
-        get_all_matrix(prd, gt)
-    with pytest.raises(NotImplementedError):
-        connected_components(prd[next(iter(prd))])
+    # get_all_matrix: the Dice block differs from get_mo_matrix only through the connected-component clean-up
+    dice, hd, sd = get_all_matrix({k: v.copy() for k, v in prd.items()}, gt)
+    cleaned = {}
+    for k, v in prd.items():
+        c = connected_components(v)
+        cleaned[k] = np.stack([connected_components(sl) for sl in c])
+    assert np.abs(dice - get_mo_matrix(cleaned, gt)).max() < 1e-12 and np.array_equal(dice, hd)
+    assert sd.shape == dice.shape and np.isfinite(sd).all() and (sd >= 0).all()
 
 
 def test_directory_yaml_and_label_volume_helpers(pkg, tmp_path, monkeypatch):
@@ -300,3 +304,134 @@ def test_validate_epoch_and_dice_the_reference_way(exact, monkeypatch):
     for k in ref_way:
         assert abs(ref_way[k] - device_way[k]) < 1e-12, k
     assert isinstance(tr.validate_epoch(batches), float)
+
+
+def _flood_components(mask, full):
+    """connected components by flood fill: neighbours differ by at most 1 per axis, in at most 2 axes when `full`"""
+    import itertools
+    offsets = [o for o in itertools.product((-1, 0, 1), repeat=mask.ndim)
+               if any(o) and sum(abs(x) for x in o) <= (2 if full else 1)]
+    seen, comps = np.zeros(mask.shape, bool), []
+    for start in zip(*np.nonzero(mask)):
+        if seen[start]:
+            continue
+        comp, stack = [], [start]
+        seen[start] = True
+        while stack:
+            cur = stack.pop()
+            comp.append(cur)
+            for o in offsets:
+                nb = tuple(c + d for c, d in zip(cur, o))
+                if all(0 <= x < s for x, s in zip(nb, mask.shape)) and mask[nb] and not seen[nb]:
+                    seen[nb] = True
+                    stack.append(nb)
+        comps.append(comp)
+    return comps
+
+
+@pytest.mark.parametrize("shape", [(24, 24), (5, 12, 12)])
+def test_connected_components_against_flood_fill(pkg, shape):
+    """utils.py:18-37 on scipy.ndimage.label: per label keep the components with more than 10 % of its voxels"""
+    from smsut_b200 import config as cfg
+    from smsut_b200.misc.utils import connected_components
+    rng = np.random.default_rng(3)
+    pred = np.zeros(shape, dtype=np.int64)
+    for lab in range(1, cfg.n_label + 1):                    # blobs of very different sizes + diagonal contacts + specks
+        for _ in range(4):
+            c = [int(rng.integers(1, s - 1)) for s in shape]
+            r = int(rng.integers(1, 4))
+            sl = tuple(slice(max(x - r, 0), x + r) for x in c)
+            pred[sl] = lab
+        for _ in range(6):
+            pred[tuple(int(rng.integers(0, s)) for s in shape)] = lab
+    got = connected_components(pred)
+    want = np.zeros(shape, dtype=np.uint8)
+    for lab in range(1, cfg.n_modal + 1):
+        comps = _flood_components(pred == lab, full=True)
+        total = sum(len(c) for c in comps)
+        for comp in comps:
+            if len(comp) > 0.1 * total:
+                for v in comp:
+                    want[v] += lab
+    assert got.dtype == np.uint8 and np.array_equal(got, want)
+    assert (got != 0).sum() < (pred != 0).sum()               # the specks went
+
+
+def test_assd_against_brute_force_and_known_cases(pkg):
+    """medpy's assd restated (border = object minus its 1-connected erosion; mean of the two directed mean distances)"""
+    from smsut_b200.misc.utils import _surface_distances, assd
+    a = np.zeros((20, 20), bool); a[4:10, 4:10] = True
+    assert assd(a, a) == 0.0
+    b = np.roll(a, 3, axis=1)                                 # the same square three pixels to the right
+    rng = np.random.default_rng(5)
+    c = np.zeros((6, 16, 16), bool); c[1:5, 3:12, 4:11] = True
+    d = np.zeros((6, 16, 16), bool); d[2:6, 5:14, 2:9] = True; d[0, 0, 0] = True
+    e = rng.uniform(size=(12, 12)) < 0.4
+
+    def border(x):
+        out = np.zeros_like(x)
+        for v in zip(*np.nonzero(x)):
+            for ax in range(x.ndim):
+                for step in (-1, 1):
+                    nb = list(v); nb[ax] += step
+                    if not (0 <= nb[ax] < x.shape[ax]) or not x[tuple(nb)]:
+                        # scipy's erosion treats outside-the-array as background: a voxel on the array edge is border
+                        out[v] = True
+        return out
+
+    def directed(x, y):
+        bx, by = np.argwhere(border(x)), np.argwhere(border(y))
+        return np.mean([np.sqrt(((by - p) ** 2).sum(1)).min() for p in bx])
+
+    for x, y in ((a, b), (c, d), (e, np.roll(e, 2, axis=0)), (e, ~e)):
+        want = (directed(x, y) + directed(y, x)) / 2
+        assert abs(assd(x, y) - want) < 1e-9, (assd(x, y), want)
+        assert abs(assd(x, y) - assd(y, x)) < 1e-12
+    assert 0 < assd(a, b) <= 3.0
+    assert abs(_surface_distances(a, b).max() - 3.0) < 1e-12  # left edge of a -> left edge of b
+    with pytest.raises(RuntimeError):
+        assd(np.zeros((4, 4), bool), a[:4, :4] | True)
+    with pytest.raises(RuntimeError):
+        assd(a, np.zeros_like(a))
+
+
+def test_test_entry_point_with_label_volumes_writes_dice_and_assd_blocks(exact, tmp_path, monkeypatch):
+    """BaseTrainer.test the reference's way (baseTrainer.py:254-318): label volumes in, predictions assembled on the
+    host, `<run>/all_trois_matrix.csv` = Dice block, empty line, ASSD block; the Dice block equals what the device-side
+    confusion counts give"""
+    from types import SimpleNamespace
+    from smsut_b200 import config as cfg
+    from smsut_b200.misc.utils import connected_components, get_all_matrix
+    from smsut_b200.trainer.unetTrainer import UnetTrainer
+    monkeypatch.setattr(cfg, "batch_size", 4)
+    tr = UnetTrainer('test', SimpleNamespace(fold=0, expr_name=None, input_size=32))
+    tr.net.load_state_dict(O.make_weights(O.unet_shapes(), 5))
+    batches, gt = [], {}
+    for bi, (m, pid, n) in enumerate((('ct', 'a', 4), ('t1in', 'b', 4), ('t1out', 'c', 4), ('t2', 'd', 3))):
+        img, lab = O.synthetic_batch(n, 32, 700 + bi)
+        batches.append((img, lab, torch.full((n,), cfg.Modality[m].value), [f"{m}_{pid}_{z}" for z in range(n)]))
+        gt[f"{m}_{pid}"] = lab.numpy()
+    # labels = the network's own predictions shifted by one pixel: every organ a volume predicts is in its labels too
+    # (an organ absent from a label volume raises, medpy's rule: checked at the end), Dice < 1 and ASSD > 0
+    _, prd = tr.validate_epoch(batches, gt)
+    gt_used = {k: np.roll(v, 1, axis=2) for k, v in prd.items()}
+    batches = [(img, torch.from_numpy(gt_used['_'.join(names[0].split('_')[:2])]).long(), mdl, names)
+               for img, _, mdl, names in batches]          # the loader's labels ARE the label volumes
+    run = os.path.join(str(tmp_path), "000")
+    matrix = tr.test('inTurn', run, loader=batches, gt_npys=gt_used)
+    blocks = open(os.path.join(run, "all_trois_matrix.csv")).read().split("\n\n")
+    assert len(blocks) == 2
+    rows = [[float(x) for x in r.split(",")] for r in blocks[0].strip().split("\n")]
+    assert np.abs(np.array(rows) - matrix).max() < 5e-5 and np.array(rows).shape == (5, 5)
+    device_way = tr.validate_dice()[1]
+    assert np.abs(device_way - matrix).max() < 1e-12
+    srows = np.array([[float(x) for x in r.split(",")] for r in blocks[1].strip().split("\n")])
+    _, prd2 = tr.validate_epoch(batches, gt_used)
+    assert np.abs(srows - get_all_matrix(prd2, gt_used)[2]).max() < 5e-5
+    assert 0 < matrix[-1, -1] < 1 and srows[-1, -1] > 0
+    k = next(iter(prd2))
+    organ = next(j for j in range(1, 5) if (connected_components(prd2[k]) == j).any())
+    bad = dict(gt_used)
+    bad[k] = np.where(bad[k] == organ, 0, bad[k])
+    with pytest.raises(RuntimeError):
+        get_all_matrix(prd2, bad)
