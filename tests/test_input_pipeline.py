@@ -191,6 +191,63 @@ def _reference_pipeline(img, msk, p, dev):
     return (x / 255 - 0.5) / 0.5, msk.long()
 
 
+def test_statement_geometry_matches_torchvision_on_pil_images(pkg):
+    """The statement above is what the GPU kernel is held to; THIS test holds the statement to the reference's actual
+    transforms -- torchvision's F.rotate / F.resized_crop on PIL images, as externalTransforms.py:46-65 calls them --
+    with the same drawn angle / crop box.  Geometry (direction, centre, pixel-centre convention) is exact: nearest-
+    neighbour labels agree on all but <= 5e-4 of the pixels (rotation; coordinates within an ulp of a pixel boundary)
+    and on every pixel (crop).  Bilinear values: never more than one u8 step apart in the interior (PIL truncates where
+    the kernel rounds: with truncation the statement equals PIL on all but 1e-4 of the interior pixels) -- except the
+    one-pixel ring along the rotated image's border, where PIL blends with the clamped edge pixel and the kernel with
+    the zero fill (1 - 3 % of the pixels).  elasticdeform is not importable offline: that stage stays
+    held to its own float statement only."""
+    import torchvision.transforms.functional as TF
+    from PIL import Image
+    from torchvision.transforms import InterpolationMode as IM
+    from smsut_b200.data_loader import externalTransforms as extt
+    size = 128
+    g = torch.Generator().manual_seed(5)
+    base = F.interpolate(torch.rand(4, 1, size // 8, size // 8, generator=g), size=(size, size), mode="bilinear")[:, 0]
+    images = (base * 255).round().to(torch.uint8)
+    labels = (F.interpolate(torch.rand(4, 1, size // 16, size // 16, generator=g), size=(size, size))[:, 0] * 5).long() \
+        .clamp(0, 4).to(torch.uint8)
+    yy, xx = np.meshgrid(np.arange(size, dtype=np.float64), np.arange(size, dtype=np.float64), indexing="ij")
+
+    def u8(x):
+        return ((x * 0.5 + 0.5) * 255).round().to(torch.uint8).numpy().astype(int)
+
+    for n, angle in enumerate((7.3, -14.9, 15.0, 0.37)):
+        p = [0.0] * extt.PARAM_FLOATS
+        p[0], p[1:7] = 1, extt.inverse_rotation(angle, size, size)
+        xr, yr = _reference_pipeline(images[n], labels[n], p, "cpu")
+        pil_i = np.array(TF.rotate(Image.fromarray(images[n].numpy()), angle, IM.BILINEAR, False, None)).astype(int)
+        pil_m = np.array(TF.rotate(Image.fromarray(labels[n].numpy()), angle, IM.NEAREST, False, None))
+        assert (yr.numpy() != pil_m).mean() <= 5e-4, angle
+        sx = p[1] * (xx + 0.5) + p[2] * (yy + 0.5) + p[3] - 0.5
+        sy = p[4] * (xx + 0.5) + p[5] * (yy + 0.5) + p[6] - 0.5
+        interior = (sx >= 0.5) & (sx <= size - 1.5) & (sy >= 0.5) & (sy <= size - 1.5)
+        outside = (sx < -1) | (sx > size) | (sy < -1) | (sy > size)
+        d = np.abs(u8(xr) - pil_i)
+        assert interior.mean() > 0.85 and d[interior].max() <= 1, (angle, d[interior].max())
+        assert d[outside].max() == 0 if outside.any() else True          # both fill with zeros
+        assert (~interior & ~outside).mean() < 0.05                        # the ring where the two border rules differ
+        gx, gy = (torch.tensor(sx) + 0.5) * 2 / size - 1, (torch.tensor(sy) + 0.5) * 2 / size - 1
+        exact = F.grid_sample(images[n][None, None].double(), torch.stack([gx, gy], -1)[None], mode="bilinear",
+                              padding_mode="zeros", align_corners=False)[0, 0]
+        trunc = torch.floor(exact).clamp(0, 255).numpy().astype(int)       # PIL's rounding rule
+        assert (np.abs(trunc - pil_i)[interior] > 0).mean() < 1e-3, angle
+    random.seed(3)
+    for n in range(4):
+        i, j, h, w = extt.JointRandomResizedCrop.get_params(size, size, (0.6, 1.0), (3 / 4, 4 / 3))
+        p = [0.0] * extt.PARAM_FLOATS
+        p[8], p[9:13] = 1, [i, j, h, w]
+        xr, yr = _reference_pipeline(images[n], labels[n], p, "cpu")
+        pil_i = np.array(TF.resized_crop(Image.fromarray(images[n].numpy()), i, j, h, w, (size, size), IM.BILINEAR))
+        pil_m = np.array(TF.resized_crop(Image.fromarray(labels[n].numpy()), i, j, h, w, (size, size), IM.NEAREST))
+        assert np.array_equal(yr.numpy(), pil_m), (i, j, h, w)
+        assert np.abs(u8(xr) - pil_i.astype(int)).max() <= 1, (i, j, h, w)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("size", [256, 64])
 def test_augment_kernel_matches_grid_sample_statement(pkg, size):
