@@ -246,6 +246,20 @@ def test_statement_geometry_matches_torchvision_on_pil_images(pkg):
         pil_m = np.array(TF.resized_crop(Image.fromarray(labels[n].numpy()), i, j, h, w, (size, size), IM.NEAREST))
         assert np.array_equal(yr.numpy(), pil_m), (i, j, h, w)
         assert np.abs(u8(xr) - pil_i.astype(int)).max() <= 1, (i, j, h, w)
+    # gamma (externalTransforms.py:23-39 -> F.adjust_gamma on the PIL image) and ToTensor + Normalize(0.5, 0.5)
+    # (baseLoader.py:107-108): the statement's formulas are torchvision's, value for value
+    import torchvision.transforms as transforms
+    to_tensor = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=[0.5], std=[0.5])])
+    for n, gamma in enumerate((0.7, 1.0, 1.31, 1.5)):
+        p = [0.0] * extt.PARAM_FLOATS
+        p[13], p[14] = 1, gamma
+        xr, yr = _reference_pipeline(images[n], labels[n], p, "cpu")
+        ref = to_tensor(TF.adjust_gamma(Image.fromarray(images[n].numpy()), gamma))[0]
+        assert np.abs(u8(xr) - u8(ref)).max() <= (0 if gamma == 1.0 else 1), gamma       # pow() in float vs double
+        assert (u8(xr) != u8(ref)).mean() < 2e-3, gamma
+        assert torch.equal(yr, labels[n].long())
+    plain, _ = _reference_pipeline(images[0], labels[0], [0.0] * extt.PARAM_FLOATS, "cpu")
+    assert torch.equal(plain, to_tensor(Image.fromarray(images[0].numpy()))[0])
 
 
 @pytest.mark.gpu
