@@ -199,8 +199,8 @@ def test_statement_geometry_matches_torchvision_on_pil_images(pkg):
     and on every pixel (crop).  Bilinear values: never more than one u8 step apart in the interior (PIL truncates where
     the kernel rounds: with truncation the statement equals PIL on all but 1e-4 of the interior pixels) -- except the
     one-pixel ring along the rotated image's border, where PIL blends with the clamped edge pixel and the kernel with
-    the zero fill (1 - 3 % of the pixels).  elasticdeform is not importable offline: that stage stays
-    held to its own float statement only."""
+    the zero fill (1 - 3 % of the pixels).  elasticdeform is not importable offline: that stage is held to a
+    scipy.ndimage statement of its documented algorithm (end of this test)."""
     import torchvision.transforms.functional as TF
     from PIL import Image
     from torchvision.transforms import InterpolationMode as IM
@@ -260,6 +260,34 @@ def test_statement_geometry_matches_torchvision_on_pil_images(pkg):
         assert torch.equal(yr, labels[n].long())
     plain, _ = _reference_pipeline(images[0], labels[0], [0.0] * extt.PARAM_FLOATS, "cpu")
     assert torch.equal(plain, to_tensor(Image.fromarray(images[0].numpy()))[0])
+    # elastic stage (externalTransforms.py:68-86 -> elasticdeform.deform_random_grid(order=[0, 0])).  The package is not
+    # importable offline; its documented algorithm -- control-point displacements interpolated over the image by cubic
+    # B-splines with mirrored ends, then the inputs sampled at x + d(x) with order 0 and mode='constant' -- is stated
+    # here with scipy.ndimage (whose map_coordinates it reimplements) and the float statement is held to THAT
+    from scipy import ndimage
+    rng = np.random.default_rng(2)
+    u = np.arange(size) * (2 / (size - 1))
+    gy, gx = np.meshgrid(u, u, indexing="ij")
+    for n in range(3):
+        disp = rng.normal(size=(2, 3, 3)) * (4.0 + n)
+        p = [0.0] * extt.PARAM_FLOATS
+        p[7], p[15] = 1, 3
+        p[16:16 + 18] = extt.bspline_coefficients(disp).astype(np.float32).ravel().tolist()
+        xr, yr = _reference_pipeline(images[n], labels[n], p, "cpu")
+        dy = ndimage.map_coordinates(disp[0], [gy, gx], order=3, mode="mirror")
+        dx = ndimage.map_coordinates(disp[1], [gy, gx], order=3, mode="mirror")
+        ref_i = ndimage.map_coordinates(images[n].numpy(), [yy + dy, xx + dx], order=0, mode="constant", cval=0)
+        ref_m = ndimage.map_coordinates(labels[n].numpy(), [yy + dy, xx + dx], order=0, mode="constant", cval=0)
+        # inside the image: equal but for coordinates within float rounding of a half-integer.  In the half-pixel band
+        # outside the outermost sample centres ndimage's mode='constant' already returns cval where the kernel's
+        # nearest-neighbour rule still picks the edge pixel (a border effect: air on real slices)
+        sy, sx = yy + dy, xx + dx
+        inside = (sy >= 0) & (sy <= size - 1) & (sx >= 0) & (sx <= size - 1)
+        bad_i, bad_m = u8(xr) != ref_i.astype(int), yr.numpy() != ref_m
+        assert inside.mean() > 0.8 and bad_i[inside].mean() < 1e-3 and bad_m[inside].mean() < 1e-3, \
+            (n, inside.mean(), bad_i[inside].mean(), bad_m[inside].mean())
+        far = (sy < -0.5) | (sy > size - 0.5) | (sx < -0.5) | (sx > size - 0.5)
+        assert not bad_i[far].any() and not bad_m[far].any()                       # both fill with zeros
 
 
 @pytest.mark.gpu
