@@ -314,9 +314,14 @@ class UGANConsisTrainer(UGANShp0Trainer):
         ul_itr = iter(ul_loader)
         tic = time.time()
         losses = None
+        # fixed images of the epoch's sample grid (L82-93): the first batch of either loader, taken off the iterators
+        # before the loop as the reference does (the epoch trains on the batches after them)
+        x_fixed1, _, modal_fixed1, inm1 = next(lb_itr)
+        x_fixed2, _, modal_fixed2, inm2 = next(ul_itr)
+        if inm1 is not None and inm2 is not None:
+            self.info(list(inm1) + list(inm2))
         lam_dev = torch.zeros(1, device=self.device)
         timing = self._iter_events = [] if os.environ.get('SMSUT_TIMING') and torch.cuda.is_available() else None
-        fixed = None        # the epoch's first labelled batch: the fixed slices of the sample grid (L83-90)
         for i in range(n_critic * (num_iter or cfg.num_iter_per_epoch)):
             try:
                 x_real1, y_real, modal_org1, _ = next(lb_itr)
@@ -329,8 +334,6 @@ class UGANConsisTrainer(UGANShp0Trainer):
                 ul_itr = iter(ul_loader)
                 x_real2, _, modal_org2, _ = next(ul_itr)
 
-            if fixed is None:
-                fixed = (x_real1, modal_org1)
             mj = random.randint(0, cfg.n_modal - 1)
             batch = self.prepare_batch(x_real1, y_real, modal_org1, x_real2, modal_org2, mj)
             alpha, sample_ids = self.draw(batch[0].size(0))
@@ -370,8 +373,9 @@ class UGANConsisTrainer(UGANShp0Trainer):
                     param_group['lr'] = lr_
                 opt._lr_host = lr_
             self.iter += 1
-        if getattr(self, 'save_samples', False) and fixed is not None:      # L205-214 (off by default: an image file per epoch)
-            self.sample_translations(*fixed, save_path=os.path.join(self.expr_root, self.model_idx, 'sample',
+        if getattr(self, 'save_samples', False):      # L205-214 (off by default: an image file per epoch)
+            self.sample_translations(torch.cat([x_fixed1, x_fixed2], dim=0), torch.cat([modal_fixed1, modal_fixed2], dim=0),
+                                     save_path=os.path.join(self.expr_root, self.model_idx, 'sample',
                                                                     f'train-{self.epoch + 1}-images.png'))
         self.meter_flush()
         return losses

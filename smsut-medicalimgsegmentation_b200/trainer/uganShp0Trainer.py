@@ -225,6 +225,11 @@ class UGANShp0Trainer(BaseTrainer):
         itr = iter(lb_loader)
         tic = time.time()
         losses = None
+        # fixed images of the epoch's sample grid (uganShp0Trainer.py:149-155): the loader's first batch, taken off the
+        # iterator before the loop as the reference does
+        x_fixed, _, modal_fixed, inm = next(itr)
+        if inm is not None:
+            self.info(list(inm))
         lam_dev = torch.zeros(1, device=self.device)
         for i in range(self.n_critic * (num_iter or cfg.num_iter_per_epoch)):
             try:
@@ -270,5 +275,8 @@ class UGANShp0Trainer(BaseTrainer):
                     param_group['lr'] = lr_
                 opt._lr_host = lr_
             self.iter += 1
+        if getattr(self, 'save_samples', False):      # uganShp0Trainer.py:219-228 (off by default: an image file per epoch)
+            self.sample_translations(x_fixed, modal_fixed, save_path=os.path.join(
+                self.expr_root, self.model_idx, 'sample', f'train-{self.epoch + 1}-images.png'))
         self.meter_flush()
         return losses

@@ -200,7 +200,9 @@ def test_consis_epoch_notes_the_segmentation_loss(exact, monkeypatch):
     tr.train_epoch(_loader(lb), _loader(ul), meter, num_iter=2)
     assert tr._meter_queue == [] and len(seen) == 2
     seg = [float(s[LOSS_KEYS.index("G_seg")]) for s in seen]
-    assert abs(meter.cur_values["loss_1"] - seg[0] * 2) < 1e-6 and abs(meter.cur_values["loss_3"] - seg[1] * 2) < 1e-6
+    # the loaders' first batches are the epoch's fixed sample images (L82-93): iteration 0 trains on the SECOND labelled
+    # batch (modality 3), iteration 1 on the first one again (modality 1) after the loader has been restarted
+    assert abs(meter.cur_values["loss_3"] - seg[0] * 2) < 1e-6 and abs(meter.cur_values["loss_1"] - seg[1] * 2) < 1e-6
     assert abs(meter.cur_values["loss"] - (seg[0] + seg[1]) * 2) < 1e-6 and meter.n["loss"] == 4
     assert isinstance(meter, Meter) and meter.n["loss_0"] == 0
 
