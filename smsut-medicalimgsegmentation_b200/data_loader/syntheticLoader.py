@@ -52,6 +52,9 @@ class SyntheticLoader:
             yield item
 
 
-def get_loader(base_root=None, phase='train', fold=0, batch_size=8, data_aug=None, size=256, seed=None, **kw):
+def get_loader(base_root=None, phase='train', fold=0, batch_size=8, data_aug=None, size=256, seed=None, rank=0, **kw):
+    """rank: a data-parallel replica's index -- replicas draw different training slices (and the same test slices)"""
     base = {'train': 2020, 'val': 4040, 'test': 6060}.get(phase, 8080)
+    if phase in ('train', 'val'):
+        base += 100003 * rank
     return SyntheticLoader(batch_size, size=size, seed=base if seed is None else seed, **kw)

@@ -7,6 +7,7 @@ scalars of both meters: :81-98, :165-172, :187-193) except the copy of the worki
 surface metrics are out of scope."""
 import abc
 import os
+import random
 import time
 from os.path import join as pjoin
 
@@ -27,6 +28,9 @@ class BaseTrainer(object):
         self._log_file = None   # <run>/train.log once the run directory exists
         if not torch.cuda.is_available() and os.environ.get("SMSUT_ALLOW_CPU_TEST_DOUBLE") != "1":
             raise RuntimeError("the SMSUT B200 trainers need a CUDA device: there is no CPU fallback")
+        if self.launched_data_parallel() and torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))      # one process per GPU (torchrun)
+        self.target_modality_rng = random       # shared by the replicas of a data-parallel run (setup_data_parallel)
         self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
         self.phase = phase
         self.fold = 0 if args is None else getattr(args, 'fold', 0)
@@ -84,6 +88,43 @@ class BaseTrainer(object):
             ops.param_generation[0] += 1
             self._graphs[key] = g
         return g if g.accepts(inputs) else None
+
+    # ---- data parallelism behind the trainer API: `torchrun --nproc-per-node N trainer/<x>Trainer.py -p train` ------
+    @staticmethod
+    def launched_data_parallel():
+        return int(os.environ.get("WORLD_SIZE", "1")) > 1
+
+    @property
+    def is_main(self):
+        """rank 0 (or a single process): the replica that logs, writes checkpoints, samples and TensorBoard files"""
+        par = getattr(self, 'parallel', None)
+        return par is None or par.rank == 0
+
+    def setup_data_parallel(self):
+        """Called by fit().  The reference wraps its networks in nn.DataParallel when it sees several GPUs
+        (uganShp0Trainer.py:66-68); here every GPU has its own process (torchrun sets RANK / WORLD_SIZE /
+        LOCAL_RANK): attach a parallel.DataParallelContext -- the trainers' steps all-reduce their flat gradients and
+        the Dice statistics through it --, start every replica from rank 0's weights, and give the replicas different
+        data: `random` / numpy / torch are re-seeded with cfg.seed + rank (sampler shuffles, augmentation draws,
+        alpha, patch positions), while the target modality of an iteration comes from ONE stream shared by all
+        replicas (the reference draws one per iteration for its whole batch, uganConsisTrainer.py:114)."""
+        if not self.launched_data_parallel() or self.phase != 'train':
+            return None
+        if not hasattr(self, 'parallel'):
+            raise NotImplementedError(f'{self.__class__.__name__} has no data-parallel step: launch it as one process')
+        if self.parallel is None:
+            from ..parallel import DataParallelContext
+            self.parallel = DataParallelContext()
+        par = self.parallel
+        flats = [o for o in vars(self).values() if hasattr(o, 'flat') and isinstance(o.flat, torch.Tensor)]
+        par.broadcast_params(*flats)                       # optimizers' master weights and EMA teachers
+        ops.param_generation[0] += 1
+        seed = cfg.seed + par.rank
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        self.target_modality_rng = random.Random(cfg.seed)
+        return par
 
     # ---- the epoch meters of `fit` (baseTrainer.py:147-199, misc/utils.py:58-160) -----------------------------------
     def meter_note(self, meter, loss, modal_id, n):
@@ -163,6 +204,8 @@ class BaseTrainer(object):
 
     def info(self, msg):
         """console + <run>/train.log (the reference's FileLogger, baseTrainer.py:94-103)"""
+        if not self.is_main:
+            return
         print(msg, flush=True)
         if self._log_file is not None and not self._log_file.closed:
             self._log_file.write(time.strftime('%Y-%m-%d %H:%M:%S') + f' - INFO: {msg}\n')
@@ -170,7 +213,7 @@ class BaseTrainer(object):
 
     def open_writer(self):
         """TensorBoard scalars under <run>/tb like baseTrainer.py:92 (SMSUT_TENSORBOARD=0 switches them off)"""
-        if self.writer is None and os.environ.get('SMSUT_TENSORBOARD', '1') != '0':
+        if self.writer is None and self.is_main and os.environ.get('SMSUT_TENSORBOARD', '1') != '0':
             try:
                 from torch.utils.tensorboard import SummaryWriter
             except ImportError as e:          # logging only: the training path does not depend on it
@@ -193,6 +236,8 @@ class BaseTrainer(object):
         pass
 
     def save_model(self, prefix):
+        if not self.is_main:
+            return
         path = pjoin(self.expr_root, self.model_idx, 'ckpt', f'{prefix}.ckpt')
         os.makedirs(os.path.dirname(path), exist_ok=True)
         torch.save({k: v.detach().cpu() for k, v in self.net.state_dict().items()}, path)
@@ -219,6 +264,8 @@ class BaseTrainer(object):
         return out
 
     def save_state(self, prefix='resume'):
+        if not self.is_main:
+            return None
         path = pjoin(self.expr_root, self.model_idx, 'ckpt', f'{prefix}.state')
         os.makedirs(os.path.dirname(path), exist_ok=True)
         state = {k: ({n: t.detach().cpu() if isinstance(t, torch.Tensor) else t for n, t in o.state_dict().items()})
@@ -260,8 +307,10 @@ class BaseTrainer(object):
             self.info(f'*** WARNING: no dataset under cfg.base_root = {root!r}: {self.phase}({loader_type!r}) falls back '
                       'to SYNTHETIC abdominal-like slices (data_loader/syntheticLoader.py). Checkpoints and scores of '
                       'this run are NOT those of a model trained / tested on CHAOS / Synapse data. ***')
-        make = dict(train=lambda: synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size),
-                    val=lambda: synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size),
+        par = getattr(self, 'parallel', None)
+        rank = par.rank if par is not None else 0
+        make = dict(train=lambda: synlod.get_loader(None, 'train', self.fold, cfg.batch_size, size=self.input_size, rank=rank),
+                    val=lambda: synlod.get_loader(None, 'val', self.fold, cfg.batch_size, size=self.input_size, rank=rank),
                     test=lambda: synlod.get_loader(None, 'test', 0, cfg.batch_size, size=self.input_size, pool_batches=4))
         return tuple(make[ph]() for ph in phases)
 
@@ -302,7 +351,13 @@ class BaseTrainer(object):
         return matrix
 
     def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None, loaders=None):
-        """loaders: optional (labelled, unlabelled, test) loaders injected by the caller instead of make_loaders"""
+        """loaders: optional (labelled, unlabelled, test) loaders injected by the caller instead of make_loaders.
+        Under torchrun every process runs this loop on its own data (setup_data_parallel); the test stage runs on every
+        replica (same test split, same weights: the Dice-statistics exchange inside the loss stays in step), rank 0
+        alone logs and writes files."""
+        self.setup_data_parallel()
+        if self.is_main:
+            self.init_train_env()           # the run directory and train.log exist before the first epoch line
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
         self.info_loader_sizes(train_lb_loader, train_ul_loader, test_loader)
         train_meter, test_meter = self.make_meters()
@@ -322,6 +377,8 @@ class BaseTrainer(object):
                 best_epoch = epoch
         self.save_model(prefix='last')
         self.meters = (train_meter, test_meter)
+        if getattr(self, 'parallel', None) is not None:
+            self.parallel.barrier()             # rank 0 has written `last` before any replica leaves
 
     def info_loader_sizes(self, train_lb_loader, train_ul_loader, test_loader):
         """baseTrainer.py:139-141"""
@@ -360,7 +417,7 @@ class BaseTrainer(object):
         epoch loop runs at the benchmarked speed).  steady_ms_per_iter = device time of the last epoch's final
         iterations (after graph capture), measured by train_epoch with CUDA events when it keeps them."""
         path = os.environ.get('SMSUT_TIMING')
-        if not path:
+        if not path or not self.is_main:
             return
         import json
         ev = getattr(self, '_iter_events', None)

@@ -351,9 +351,11 @@ class coraNetTrainer(BaseTrainer):
     def prefit(self, loader_type='inTurn', pre_epoch=None, iters_per_epoch=None, loaders=None):
         """(:526-602) supervised pre-training; keeps `pre_best` / `pre_ema_best` on the validation Dice and writes
         `pre_last` / `pre_ema_last` at the end"""
+        self.setup_data_parallel()      # raises under torchrun: this trainer's steps exchange nothing
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
         self.info_loader_sizes(train_lb_loader, train_ul_loader, test_loader)
         train_meter, test_meter = self.make_meters()
+        self.init_train_env()
         self.open_writer()
         best_epoch = -1
         n_epoch = pre_epoch if pre_epoch is not None else cfg.pre_epoch
@@ -374,6 +376,7 @@ class coraNetTrainer(BaseTrainer):
     def fit(self, loader_type='inTurn', max_epoch=None, iters_per_epoch=None, loaders=None):
         """(:604-690) loads `pre_best` / `pre_ema_best` of run `model_id`, predicts the pseudo labels (again every
         cfg.pred_step epochs) and trains; `best` on the validation Dice, `last` at the end"""
+        self.setup_data_parallel()      # raises under torchrun: this trainer's steps exchange nothing
         train_lb_loader, train_ul_loader, test_loader = loaders if loaders is not None else self.make_loaders(loader_type)
         self.info_loader_sizes(train_lb_loader, train_ul_loader, test_loader)
         train_meter, test_meter = self.make_meters()
@@ -381,6 +384,7 @@ class coraNetTrainer(BaseTrainer):
         self.load_model(self.model_id, 'pre_best')
         self.load_ema_model(self.model_id, 'pre_ema_best')
         self.model_idx = None       # this run gets its own directory (the reference allocates it at construction)
+        self.init_train_env()
         self.open_writer()
         new_loader, plab_dice = self.pred_unlabel(train_ul_loader)
         n_epoch = max_epoch if max_epoch is not None else cfg.cora_epoch

@@ -308,7 +308,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
         self.D.train()
         lambda_semi = self.lambda_semi * self.sigmoid_rampup(self.epoch, cfg.max_epoch)
         n_critic = self.n_critic
-        print(f'\nlambda_seg: {self.lambda_seg}, lambda_semi: {lambda_semi}.')
+        self.info(f'\nlambda_seg: {self.lambda_seg}, lambda_semi: {lambda_semi}.')
 
         lb_itr = iter(lb_loader)
         ul_itr = iter(ul_loader)
@@ -334,7 +334,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
                 ul_itr = iter(ul_loader)
                 x_real2, _, modal_org2, _ = next(ul_itr)
 
-            mj = random.randint(0, cfg.n_modal - 1)
+            mj = self.target_modality_rng.randint(0, cfg.n_modal - 1)
             batch = self.prepare_batch(x_real1, y_real, modal_org1, x_real2, modal_org2, mj)
             alpha, sample_ids = self.draw(batch[0].size(0))
             use_semi = self.iter >= self.semi_from_iter
@@ -365,7 +365,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
                 tic = time.time()
                 for k, v in zip(LOSS_KEYS, vals):
                     log += ' %s: %.4f,' % (k, v)
-                print(log, flush=True)
+                self.info(log)
 
             lr_ = self.lr_sched.host_lr(self.iter + 1)
             for opt in (self.optimizer, self.d_optimizer):
@@ -373,7 +373,7 @@ class UGANConsisTrainer(UGANShp0Trainer):
                     param_group['lr'] = lr_
                 opt._lr_host = lr_
             self.iter += 1
-        if getattr(self, 'save_samples', False):      # L205-214 (off by default: an image file per epoch)
+        if getattr(self, 'save_samples', False) and self.is_main:      # L205-214 (off by default: an image file per epoch)
             self.sample_translations(torch.cat([x_fixed1, x_fixed2], dim=0), torch.cat([modal_fixed1, modal_fixed2], dim=0),
                                      save_path=os.path.join(self.expr_root, self.model_idx, 'sample',
                                                                     f'train-{self.epoch + 1}-images.png'))

@@ -70,12 +70,14 @@ class UGANShp0Trainer(BaseTrainer):
 
     def save_model(self, prefix):
         assert self.phase == 'train'
+        if not self.is_main:
+            return
         G_path = pjoin(self.expr_root, self.model_idx, 'ckpt', f'{prefix}_G.ckpt')
         D_path = pjoin(self.expr_root, self.model_idx, 'ckpt', f'{prefix}_D.ckpt')
         os.makedirs(os.path.dirname(G_path), exist_ok=True)
         torch.save({k: v.detach().cpu() for k, v in self.net.state_dict().items()}, G_path)
         torch.save({k: v.detach().cpu() for k, v in self.D.state_dict().items()}, D_path)
-        print(f'[*] Save G and D to {G_path}.')
+        self.info(f'[*] Save G and D to {G_path}.')
 
     def label2onehot(self, modals, dim=cfg.n_modal):
         batch_size = modals.size(0)
@@ -221,7 +223,7 @@ class UGANShp0Trainer(BaseTrainer):
         self.net.train()
         self.D.train()
         lambda_shp = self.epoch_lambda_shp()
-        print(f'\nlambda_seg: {self.lambda_seg}' + ('.' if lambda_shp is None else f', lambda_shp: {lambda_shp}.'))
+        self.info(f'\nlambda_seg: {self.lambda_seg}' + ('.' if lambda_shp is None else f', lambda_shp: {lambda_shp}.'))
         itr = iter(lb_loader)
         tic = time.time()
         losses = None
@@ -237,7 +239,7 @@ class UGANShp0Trainer(BaseTrainer):
             except StopIteration:
                 itr = iter(lb_loader)
                 x_real, y_real, modal_org, _ = next(itr)
-            mj = random.randint(0, cfg.n_modal - 1)
+            mj = self.target_modality_rng.randint(0, cfg.n_modal - 1)
             modal_trg = torch.zeros_like(modal_org).fill_(mj)
             vec_org = self.label2onehot(modal_org, cfg.n_modal)
             vec_trg = self.label2onehot(modal_trg, cfg.n_modal)
@@ -268,14 +270,14 @@ class UGANShp0Trainer(BaseTrainer):
                 for k, v in zip(self.SHP_LOSS_KEYS, losses.tolist()):
                     if k != 'G_shp' or lambda_shp is not None:
                         log += ' %s: %.4f,' % (k, v)
-                print(log, flush=True)
+                self.info(log)
             lr_ = self.lr_sched.host_lr(self.iter + 1)
             for opt in (self.optimizer, self.d_optimizer):
                 for param_group in opt.param_groups:
                     param_group['lr'] = lr_
                 opt._lr_host = lr_
             self.iter += 1
-        if getattr(self, 'save_samples', False):      # uganShp0Trainer.py:219-228 (off by default: an image file per epoch)
+        if getattr(self, 'save_samples', False) and self.is_main:      # uganShp0Trainer.py:219-228 (off by default)
             self.sample_translations(x_fixed, modal_fixed, save_path=os.path.join(
                 self.expr_root, self.model_idx, 'sample', f'train-{self.epoch + 1}-images.png'))
         self.meter_flush()

@@ -264,3 +264,72 @@ def test_two_rank_semi_supervised_steps_equal_single_process_on_global_batch(tmp
         for k in sd:
             assert rel(res[0]["nets"][name][k], res[1]["nets"][name][k]) < 1e-6, (name, k)
             assert rel(res[0]["nets"][name][k], sd[k]) < 2e-3, (name, k)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# data parallelism behind the trainer API: `torchrun ... trainer/<x>Trainer.py -p train` = fit() on every rank
+# ----------------------------------------------------------------------------------------------------------------------
+def _fit_worker(rank, world, port, outdir, trainer_name, size):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), SMSUT_ALLOW_CPU_TEST_DOUBLE="1", SMSUT_TENSORBOARD="0")
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    torch.set_num_threads(2)
+    import random
+    import numpy as np
+    import __graft_entry__ as g
+    g.load_package()
+    from types import SimpleNamespace
+
+    import cpu_ops_mock
+    from smsut_b200 import config as cfg
+    cfg.batch_size, cfg.expr_root = 2, os.path.join(outdir, "expr")
+    module = {"UnetTrainer": "unetTrainer", "UGANConsisTrainer": "uganConsisTrainer"}[trainer_name]
+    mod = __import__(f"smsut_b200.trainer.{module}", fromlist=[trainer_name])
+    with cpu_ops_mock.installed(exact=True):
+        random.seed(cfg.seed); np.random.seed(cfg.seed); torch.manual_seed(cfg.seed)      # what __main__ does on every rank
+        tr = getattr(mod, trainer_name)('train', SimpleNamespace(fold=0, expr_name="dp", input_size=size))
+        seen = []
+        step = tr.train_step
+        tr.train_step = lambda *a, **k: seen.append([t.detach().clone() if isinstance(t, torch.Tensor) else t for t in a]) or step(*a, **k)
+        tr.fit('synthetic', max_epoch=1, iters_per_epoch=2)
+        first = {k: v.detach().clone() for k, v in tr.net.state_dict().items()}
+        torch.save(dict(rank=rank, weights=first, inputs=seen, meters=[m.cur_values for m in tr.meters],
+                        is_main=tr.is_main, world=tr.parallel.world), os.path.join(outdir, f"fit{rank}.pt"))
+        tr.parallel.close()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("trainer_name,size", [("UnetTrainer", 32), ("UGANConsisTrainer", 64)])
+def test_two_rank_fit_through_the_trainer_api(tmp_path, trainer_name, size):
+    """fit() under WORLD_SIZE = 2 (what `torchrun --nproc-per-node 2 trainer/<x>Trainer.py -p train` runs): the replicas
+    attach the data-parallel context themselves, train on DIFFERENT slices, end with identical weights, agree on the
+    target modality of every iteration, and only rank 0 writes the run directory."""
+    ctx = mp.get_context("spawn")
+    port = 29500 + (os.getpid() + 137 + len(trainer_name)) % 400
+    procs = [ctx.Process(target=_fit_worker, args=(r, 2, port, str(tmp_path), trainer_name, size)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(500)
+        assert p.exitcode == 0
+    res = [torch.load(os.path.join(str(tmp_path), f"fit{r}.pt"), weights_only=False) for r in range(2)]
+    assert res[0]["is_main"] and not res[1]["is_main"] and res[0]["world"] == 2
+    for k, v in res[0]["weights"].items():
+        assert torch.equal(v, res[1]["weights"][k]), k                   # replicas stay in step
+    a, b = res[0]["inputs"], res[1]["inputs"]
+    assert len(a) == len(b) == 2
+    assert not torch.equal(a[0][0], b[0][0])                             # different slices per replica
+    if trainer_name == "UGANConsisTrainer":
+        # modal_trg (argument 3 of train_step, prepare_batch's order): ONE target modality per iteration, shared
+        for it in range(2):
+            assert int(a[it][3][0]) == int(b[it][3][0]), "the replicas drew different target modalities"
+            assert len(set(a[it][3].tolist())) == 1
+    run = os.path.join(str(tmp_path), "expr", "dp")
+    assert sorted(os.listdir(run)) == ["000"]                            # one run directory: rank 0's
+    ck = os.listdir(os.path.join(run, "000", "ckpt"))
+    assert any(c.startswith("last") for c in ck) and any(c.startswith("best") for c in ck)
+    log = open(os.path.join(run, "000", "train.log")).read()
+    assert log.count("[TRN] Epoch:") == 1 and log.count("[TST] Epoch:") == 1
+    # the test stage runs on every replica with the same weights and the same test slices
+    for k, v in res[0]["meters"][1].items():
+        assert abs(v - res[1]["meters"][1][k]) < 1e-6, k
