@@ -142,6 +142,20 @@ class BaseTrainer(object):
             for (meter, _, modal_id, n), v in zip(queue, values):
                 meter.accumulate(*meter.collect_loss_by(v, modal_id, n))
 
+    def meter_all_reduce(self, meter):
+        """data-parallel runs: sum the epoch's weighted sums and weights over the replicas before update_cur, so the
+        [TRN] line reports the mean over the global batch (what the reference's meter sees behind nn.DataParallel)"""
+        par = getattr(self, 'parallel', None)
+        if par is None or par.world <= 1:
+            return
+        keys = list(meter.configs)
+        t = torch.tensor([float(meter.cur_values[k]) for k in keys] + [float(meter.n[k]) for k in keys],
+                         dtype=torch.float64, device=self.device)
+        par.all_reduce_sum(t)
+        vals = t.tolist()
+        for i, k in enumerate(keys):
+            meter.cur_values[k], meter.n[k] = vals[i], vals[len(keys) + i]
+
     @staticmethod
     def make_meters():
         """(train meter, test meter) of baseTrainer.py:147-151"""
@@ -390,6 +404,7 @@ class BaseTrainer(object):
     def log_train_stage(self, train_meter, epoch, best_epoch, n_epoch, tic, tag=''):
         """the train logs and scalars of an epoch (baseTrainer.py:158-172); returns the new tic"""
         self.meter_flush()
+        self.meter_all_reduce(train_meter)
         train_meter.update_cur()
         opt = getattr(self, 'optimizer', None) or getattr(self, 'optimizer1')      # crossPseTrainer.py:185-188
         self.info('')

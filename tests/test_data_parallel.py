@@ -330,6 +330,11 @@ def test_two_rank_fit_through_the_trainer_api(tmp_path, trainer_name, size):
     assert any(c.startswith("last") for c in ck) and any(c.startswith("best") for c in ck)
     log = open(os.path.join(run, "000", "train.log")).read()
     assert log.count("[TRN] Epoch:") == 1 and log.count("[TST] Epoch:") == 1
+    # the train meter holds the mean over BOTH replicas' slices (summed before update_cur): equal on both ranks, and
+    # weighted with twice one replica's slice count
+    for k, v in res[0]["meters"][0].items():
+        assert abs(v - res[1]["meters"][0][k]) < 1e-9, k
+    assert res[0]["meters"][0]["loss"] > 0
     # the test stage runs on every replica with the same weights and the same test slices
     for k, v in res[0]["meters"][1].items():
         assert abs(v - res[1]["meters"][1][k]) < 1e-6, k
