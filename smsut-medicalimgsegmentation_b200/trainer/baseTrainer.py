@@ -344,7 +344,10 @@ class BaseTrainer(object):
                 raise NotImplementedError(loader_type)
             loader = self.make_loaders(loader_type, phases=('test',))[0]
             if gt_npys is None and root and os.path.isdir(root):
-                n_gt_slic, gt_npys = get_label_npys(root, self.modality, 'test')
+                try:
+                    n_gt_slic, gt_npys = get_label_npys(root, self.modality, 'test')
+                except FileNotFoundError as e:      # a PNG tree without the pre-processing's <m>_<p>.npy label volumes
+                    self.info(f'No label volumes ({e}): Dice from the device-side confusion counts, no ASSD block.')
         self.info(f"Predict and score the test split ({pjoin(expr_root, 'result')}).")
         fmt = lambda mat: ''.join(','.join('%.4f' % v for v in row) + '\n' for row in mat)      # noqa: E731
         if gt_npys is not None:
